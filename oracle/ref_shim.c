@@ -1,0 +1,310 @@
+/* oracle/ref_shim.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * Thin helpers around the UNMODIFIED reference (libopus 1.5.2 compiled from /root/reference/opus by
+ * oracle/Makefile into oracle/_ref/libopus_ref.so).  Nothing here re-implements codec arithmetic: every
+ * sample and every packet byte comes out of the reference's own public entry points, the very ones the
+ * crate's safe wrappers call:
+ *     Decoder::decode_float -> opus_decode_float   (src/decoder.rs:162-175)
+ *     Encoder::encode_float -> opus_encode_float   (src/encoder.rs:234-242)
+ *     final_range()         -> OPUS_GET_FINAL_RANGE (src/decoder.rs:302-312, src/encoder.rs:411-419)
+ *
+ * Besides whole-stream encode/decode helpers it offers
+ *   - "taps": link-time --wrap interposers on three internal libopus functions that record what
+ *     passed through them (normalised spectrum after quant_all_bands, band energies + MDCT input at
+ *     denormalise_bands, pre-post-filter time signal at comb_filter), so stage-wise parity of the CUDA
+ *     kernels can be checked without touching reference source;
+ *   - a pthread pool that runs one stream per thread for the CPU baseline.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <pthread.h>
+#include <time.h>
+#include "opus.h"
+#include "opus_private.h" /* OPUS_SET_FORCE_MODE, MODE_CELT_ONLY */
+#include "arch.h"
+#include "modes.h"
+#include "entcode.h"
+
+#define REF_EXPORT __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------------
+ * taps
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    /* quant_all_bands (opus/celt/bands.c:1398) */
+    int   n_qab;                 /* calls seen */
+    int   LM, C, shortBlocks, spread, dual_stereo, intensity, codedBands;
+    int   total_bits, balance;
+    int   pulses[21], tf_res[21];
+    uint8_t collapse_masks[42];
+    uint32_t seed_in, seed_out;
+    float X[2 * 960];            /* normalised spectrum after the call: X then Y */
+    /* denormalise_bands (opus/celt/bands.c:196), last call per channel */
+    int   n_denorm;
+    float bandLogE[42];
+    float freq[2 * 960];
+    /* comb_filter (opus/celt/celt.c:190): input of the FIRST call per channel = IMDCT output */
+    int   n_comb;
+    float presyn[2 * (960 + 120)];
+    int   comb_T0[4], comb_T1[4], comb_N[4];
+    float comb_g0[4], comb_g1[4];
+} ref_tap_t;
+
+static __thread ref_tap_t *g_tap = NULL;
+
+REF_EXPORT int ref_tap_size(void) { return (int)sizeof(ref_tap_t); }
+REF_EXPORT void ref_tap_set(void *p) { g_tap = (ref_tap_t *)p; if (g_tap) { g_tap->n_qab = g_tap->n_denorm = g_tap->n_comb = 0; } }
+
+void __real_quant_all_bands(int encode, const CELTMode *m, int start, int end, celt_norm *X_, celt_norm *Y_,
+        unsigned char *collapse_masks, const celt_ener *bandE, int *pulses, int shortBlocks, int spread,
+        int dual_stereo, int intensity, int *tf_res, opus_int32 total_bits, opus_int32 balance, ec_ctx *ec,
+        int LM, int codedBands, opus_uint32 *seed, int complexity, int arch, int disable_inv);
+
+void __wrap_quant_all_bands(int encode, const CELTMode *m, int start, int end, celt_norm *X_, celt_norm *Y_,
+        unsigned char *collapse_masks, const celt_ener *bandE, int *pulses, int shortBlocks, int spread,
+        int dual_stereo, int intensity, int *tf_res, opus_int32 total_bits, opus_int32 balance, ec_ctx *ec,
+        int LM, int codedBands, opus_uint32 *seed, int complexity, int arch, int disable_inv)
+{
+    ref_tap_t *t = g_tap;
+    uint32_t seed_in = *seed;
+    __real_quant_all_bands(encode, m, start, end, X_, Y_, collapse_masks, bandE, pulses, shortBlocks, spread,
+            dual_stereo, intensity, tf_res, total_bits, balance, ec, LM, codedBands, seed, complexity, arch,
+            disable_inv);
+    if (t && !encode) {
+        int N = 120 << LM, C = Y_ ? 2 : 1, i;
+        t->n_qab++;
+        t->LM = LM; t->C = C; t->shortBlocks = shortBlocks; t->spread = spread;
+        t->dual_stereo = dual_stereo; t->intensity = intensity; t->codedBands = codedBands;
+        t->total_bits = total_bits; t->balance = balance;
+        for (i = 0; i < 21; i++) { t->pulses[i] = pulses[i]; t->tf_res[i] = tf_res[i]; }
+        memcpy(t->collapse_masks, collapse_masks, (size_t)C * 21);
+        t->seed_in = seed_in; t->seed_out = *seed;
+        memcpy(t->X, X_, sizeof(float) * N);
+        if (Y_) memcpy(t->X + N, Y_, sizeof(float) * N);
+    }
+}
+
+void __real_denormalise_bands(const CELTMode *m, const celt_norm *X, celt_sig *freq, const opus_val16 *bandLogE,
+        int start, int end, int M, int downsample, int silence);
+void __wrap_denormalise_bands(const CELTMode *m, const celt_norm *X, celt_sig *freq, const opus_val16 *bandLogE,
+        int start, int end, int M, int downsample, int silence)
+{
+    ref_tap_t *t = g_tap;
+    __real_denormalise_bands(m, X, freq, bandLogE, start, end, M, downsample, silence);
+    if (t) {
+        int c = t->n_denorm & 1, N = 120 * M;
+        memcpy(t->bandLogE + 21 * c, bandLogE, sizeof(float) * 21);
+        memcpy(t->freq + N * c, freq, sizeof(float) * N);
+        t->n_denorm++;
+    }
+}
+
+void __real_comb_filter(opus_val32 *y, opus_val32 *x, int T0, int T1, int N, opus_val16 g0, opus_val16 g1,
+        int tapset0, int tapset1, const opus_val16 *window, int overlap, int arch);
+void __wrap_comb_filter(opus_val32 *y, opus_val32 *x, int T0, int T1, int N, opus_val16 g0, opus_val16 g1,
+        int tapset0, int tapset1, const opus_val16 *window, int overlap, int arch)
+{
+    ref_tap_t *t = g_tap;
+    if (t && t->n_comb < 4) {
+        int k = t->n_comb;
+        t->comb_T0[k] = T0; t->comb_T1[k] = T1; t->comb_N[k] = N; t->comb_g0[k] = g0; t->comb_g1[k] = g1;
+    }
+    if (t) {
+        int per = t->LM ? 2 : 1, k = t->n_comb;
+        if (k % per == 0 && k / per < 2)   /* first call of a channel: x[0..Nframe+overlap) is the raw IMDCT output */
+            memcpy(t->presyn + (k / per) * (960 + 120), x, sizeof(float) * ((120 << t->LM) + 120));
+        t->n_comb++;
+    }
+    __real_comb_filter(y, x, T0, T1, N, g0, g1, tapset0, tapset1, window, overlap, arch);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * whole-stream helpers
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Creates an encoder the way the benchmarks configure it:
+ * OPUS_APPLICATION_RESTRICTED_LOWDELAY forces MODE_CELT_ONLY (opus/src/opus_encoder.c:1330-1332).
+ * vbr: 0 = CBR, 1 = VBR, 2 = constrained VBR. */
+static OpusEncoder *make_encoder(int channels, int application, int bitrate, int vbr, int complexity)
+{
+    int err = 0;
+    OpusEncoder *e = opus_encoder_create(48000, channels, application, &err);
+    if (!e || err != OPUS_OK) return NULL;
+    opus_encoder_ctl(e, OPUS_SET_BITRATE(bitrate));
+    opus_encoder_ctl(e, OPUS_SET_COMPLEXITY(complexity));
+    opus_encoder_ctl(e, OPUS_SET_VBR(vbr != 0));
+    opus_encoder_ctl(e, OPUS_SET_VBR_CONSTRAINT(vbr == 2));
+    if (application != OPUS_APPLICATION_RESTRICTED_LOWDELAY)
+        opus_encoder_ctl(e, OPUS_SET_FORCE_MODE(MODE_CELT_ONLY));
+    return e;
+}
+
+/* pcm: nframes*frame_size*channels interleaved floats. out: nframes slots of max_bytes each.
+ * Returns 0 or a negative OPUS_* code. */
+REF_EXPORT int ref_encode_stream(const float *pcm, int nframes, int frame_size, int channels, int application,
+        int bitrate, int vbr, int complexity, unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
+{
+    int f;
+    OpusEncoder *e = make_encoder(channels, application, bitrate, vbr, complexity);
+    if (!e) return OPUS_ALLOC_FAIL;
+    for (f = 0; f < nframes; f++) {
+        opus_uint32 rng = 0;
+        int n = opus_encode_float(e, pcm + (size_t)f * frame_size * channels, frame_size,
+                out + (size_t)f * max_bytes, max_bytes);
+        if (n < 0) { opus_encoder_destroy(e); return n; }
+        lens[f] = n;
+        opus_encoder_ctl(e, OPUS_GET_FINAL_RANGE(&rng));
+        if (ranges) ranges[f] = rng;
+    }
+    opus_encoder_destroy(e);
+    return 0;
+}
+
+/* pkts: nframes slots of `stride` bytes; lens[f] bytes valid (0 => packet loss / PLC).
+ * dec_channels: channel count of the decoder object.  taps (optional): nframes ref_tap_t records. */
+REF_EXPORT int ref_decode_stream(const unsigned char *pkts, const int *lens, int stride, int nframes, int frame_size,
+        int dec_channels, float *pcm_out, uint32_t *ranges, int *samples, void *taps)
+{
+    int f, err = 0;
+    OpusDecoder *d = opus_decoder_create(48000, dec_channels, &err);
+    if (!d || err != OPUS_OK) return OPUS_ALLOC_FAIL;
+    for (f = 0; f < nframes; f++) {
+        opus_uint32 rng = 0;
+        int n;
+        if (taps) ref_tap_set((char *)taps + (size_t)f * sizeof(ref_tap_t));
+        n = opus_decode_float(d, lens[f] > 0 ? pkts + (size_t)f * stride : NULL, lens[f],
+                pcm_out + (size_t)f * frame_size * dec_channels, frame_size, 0);
+        if (taps) ref_tap_set(NULL);
+        if (samples) samples[f] = n;
+        if (n < 0 && !samples) { opus_decoder_destroy(d); return n; }
+        opus_decoder_ctl(d, OPUS_GET_FINAL_RANGE(&rng));
+        if (ranges) ranges[f] = rng;
+    }
+    opus_decoder_destroy(d);
+    return 0;
+}
+
+/* Decode ONE packet with a fresh decoder (used for stateless final-range checks). */
+REF_EXPORT int ref_decode_packet_fresh(const unsigned char *pkt, int len, int frame_size, int dec_channels,
+        float *pcm_out, uint32_t *range)
+{
+    int lens[1]; lens[0] = len;
+    return ref_decode_stream(pkt, lens, len, 1, frame_size, dec_channels, pcm_out, range, NULL, NULL);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * CPU baseline: a pthread pool, one stream per thread at a time.
+ * Streams are handed out round-robin; object creation is outside the timed region.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    int tid, nthreads, nstreams, nframes, frame_size, channels;
+    const unsigned char *pkts; const int *lens; int stride;   /* decode: [stream][frame][stride] */
+    const float *pcm_in;                                      /* encode: [stream][frame][fs*ch]  */
+    float *pcm_out; unsigned char *pkt_out; int *len_out;     /* optional outputs                */
+    uint32_t *ranges;                                         /* [stream][frame], optional       */
+    int application, bitrate, vbr, complexity;
+    int encode;
+    pthread_barrier_t *bar;
+    double t0, t1;
+    int err;
+} pool_arg_t;
+
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
+static void *pool_worker(void *vp)
+{
+    pool_arg_t *a = (pool_arg_t *)vp;
+    int mine = 0, s, f, k, err = 0;
+    void **objs;
+    float *scratch = (float *)malloc(sizeof(float) * 960 * 2);
+    unsigned char pkt[1500];
+    for (s = a->tid; s < a->nstreams; s += a->nthreads) mine++;
+    objs = (void **)calloc((size_t)(mine > 0 ? mine : 1), sizeof(void *));
+    for (k = 0; k < mine; k++) {
+        if (a->encode) objs[k] = make_encoder(a->channels, a->application, a->bitrate, a->vbr, a->complexity);
+        else objs[k] = opus_decoder_create(48000, a->channels, &err);
+        if (!objs[k]) a->err = OPUS_ALLOC_FAIL;
+    }
+    pthread_barrier_wait(a->bar);
+    a->t0 = now_s();
+    if (!a->err) for (k = 0, s = a->tid; s < a->nstreams; s += a->nthreads, k++) {
+        for (f = 0; f < a->nframes; f++) {
+            size_t sf = (size_t)s * a->nframes + f;
+            opus_uint32 rng;
+            int n;
+            if (a->encode) {
+                unsigned char *dst = a->pkt_out ? a->pkt_out + sf * a->stride : pkt;
+                n = opus_encode_float((OpusEncoder *)objs[k], a->pcm_in + sf * a->frame_size * a->channels,
+                        a->frame_size, dst, a->stride);
+                if (a->len_out) a->len_out[sf] = n;
+                if (a->ranges) { opus_encoder_ctl((OpusEncoder *)objs[k], OPUS_GET_FINAL_RANGE(&rng)); a->ranges[sf] = rng; }
+            } else {
+                float *dst = a->pcm_out ? a->pcm_out + sf * a->frame_size * a->channels : scratch;
+                n = opus_decode_float((OpusDecoder *)objs[k], a->pkts + sf * a->stride, a->lens[sf], dst,
+                        a->frame_size, 0);
+                if (a->ranges) { opus_decoder_ctl((OpusDecoder *)objs[k], OPUS_GET_FINAL_RANGE(&rng)); a->ranges[sf] = rng; }
+            }
+            if (n < 0) a->err = n;
+        }
+    }
+    a->t1 = now_s();
+    pthread_barrier_wait(a->bar);
+    for (k = 0; k < mine; k++) {
+        if (!objs[k]) continue;
+        if (a->encode) opus_encoder_destroy((OpusEncoder *)objs[k]); else opus_decoder_destroy((OpusDecoder *)objs[k]);
+    }
+    free(objs); free(scratch);
+    return NULL;
+}
+
+static double run_pool(pool_arg_t *proto, int nthreads, int *err_out)
+{
+    pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+    pool_arg_t *args = (pool_arg_t *)malloc(sizeof(pool_arg_t) * nthreads);
+    pthread_barrier_t bar;
+    double t0 = 1e300, t1 = 0;
+    int i, err = 0;
+    pthread_barrier_init(&bar, NULL, nthreads);
+    for (i = 0; i < nthreads; i++) {
+        args[i] = *proto; args[i].tid = i; args[i].nthreads = nthreads; args[i].bar = &bar; args[i].err = 0;
+        pthread_create(&th[i], NULL, pool_worker, &args[i]);
+    }
+    for (i = 0; i < nthreads; i++) {
+        pthread_join(th[i], NULL);
+        if (args[i].t0 < t0) t0 = args[i].t0;
+        if (args[i].t1 > t1) t1 = args[i].t1;
+        if (args[i].err) err = args[i].err;
+    }
+    pthread_barrier_destroy(&bar);
+    free(th); free(args);
+    if (err_out) *err_out = err;
+    return t1 - t0;
+}
+
+/* Returns wall seconds from the first thread's first frame to the last thread's last frame (<0 on error). */
+REF_EXPORT double ref_decode_pool(const unsigned char *pkts, const int *lens, int stride, int nstreams, int nframes,
+        int frame_size, int channels, int nthreads, float *pcm_out, uint32_t *ranges)
+{
+    pool_arg_t a; int err = 0; double t;
+    memset(&a, 0, sizeof(a));
+    a.nstreams = nstreams; a.nframes = nframes; a.frame_size = frame_size; a.channels = channels;
+    a.pkts = pkts; a.lens = lens; a.stride = stride; a.pcm_out = pcm_out; a.ranges = ranges; a.encode = 0;
+    t = run_pool(&a, nthreads, &err);
+    return err ? (double)err : t;
+}
+
+REF_EXPORT double ref_encode_pool(const float *pcm, int nstreams, int nframes, int frame_size, int channels,
+        int application, int bitrate, int vbr, int complexity, int nthreads,
+        unsigned char *pkt_out, int stride, int *len_out, uint32_t *ranges)
+{
+    pool_arg_t a; int err = 0; double t;
+    memset(&a, 0, sizeof(a));
+    a.nstreams = nstreams; a.nframes = nframes; a.frame_size = frame_size; a.channels = channels;
+    a.pcm_in = pcm; a.pkt_out = pkt_out; a.stride = stride > 0 ? stride : 1500; a.len_out = len_out; a.ranges = ranges;
+    a.application = application; a.bitrate = bitrate; a.vbr = vbr; a.complexity = complexity; a.encode = 1;
+    t = run_pool(&a, nthreads, &err);
+    return err ? (double)err : t;
+}
+
+REF_EXPORT const char *ref_version(void) { return opus_get_version_string(); }
