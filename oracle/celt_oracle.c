@@ -1231,7 +1231,8 @@ static int celt_decode_frame(co_decoder *st, const uint8_t *data, int len, float
     N = M * SHORT;
     for (c = 0; c < CC; c++) out_syn[c] = st->mem[c] + HIST - N;
     rd_init(&dec, data, (uint32_t)len);
-    memset(coarse_qi, 0, sizeof(coarse_qi));
+    memset(coarse_qi, 0, sizeof(coarse_qi)); memset(tf_res, 0, sizeof(tf_res)); memset(pulses, 0, sizeof(pulses));
+    memset(fine_quant, 0, sizeof(fine_quant)); memset(fine_priority, 0, sizeof(fine_priority)); memset(offsets, 0, sizeof(offsets));
     memset(X, 0, sizeof(X));
 
     if (C == 1) for (i = 0; i < NB; i++) oldBandE[i] = fmaxf(oldBandE[i], oldBandE[NB + i]);   /* :1114-1118 */
@@ -1432,7 +1433,7 @@ int co_decode_float(co_decoder *d, const uint8_t *pkt, int len, float *pcm, int 
     if (toc & 0x3) return CO_UNIMPLEMENTED;                          /* multi-frame packets (codes 1-3) */
     fs = SHORT << ((toc >> 3) & 0x3);
     if (fs > frame_size) return CO_BUFFER_TOO_SMALL;
-    if (len <= 1) return CO_UNIMPLEMENTED;                           /* DTX/PLC */
+    if (len <= 2) return CO_UNIMPLEMENTED;                           /* payload <= 1 byte => DTX/PLC (opus_decoder.c:284-290) */
     C = (toc & 0x4) ? 2 : 1;
     bw = (toc >> 5) & 0x3;                                           /* 0 NB, 1 WB, 2 SWB, 3 FB */
     end = bw == 0 ? 13 : bw == 1 ? 17 : bw == 2 ? 19 : 21;

@@ -126,6 +126,14 @@ void __wrap_comb_filter(opus_val32 *y, opus_val32 *x, int T0, int T1, int N, opu
 /* Creates an encoder the way the benchmarks configure it:
  * OPUS_APPLICATION_RESTRICTED_LOWDELAY forces MODE_CELT_ONLY (opus/src/opus_encoder.c:1330-1332).
  * vbr: 0 = CBR, 1 = VBR, 2 = constrained VBR. */
+/* Optional extra CTLs applied by make_encoder (0 / OPUS_AUTO = leave alone): OPUS_SET_BANDWIDTH
+ * (1101..1105) and OPUS_SET_FORCE_CHANNELS.  Used to produce NB/WB/SWB and mono-in-stereo test packets. */
+static int g_extra_bandwidth = 0, g_extra_force_channels = 0;
+REF_EXPORT void ref_set_encoder_extras(int bandwidth, int force_channels)
+{
+    g_extra_bandwidth = bandwidth; g_extra_force_channels = force_channels;
+}
+
 static OpusEncoder *make_encoder(int channels, int application, int bitrate, int vbr, int complexity)
 {
     int err = 0;
@@ -137,6 +145,8 @@ static OpusEncoder *make_encoder(int channels, int application, int bitrate, int
     opus_encoder_ctl(e, OPUS_SET_VBR_CONSTRAINT(vbr == 2));
     if (application != OPUS_APPLICATION_RESTRICTED_LOWDELAY)
         opus_encoder_ctl(e, OPUS_SET_FORCE_MODE(MODE_CELT_ONLY));
+    if (g_extra_bandwidth) opus_encoder_ctl(e, OPUS_SET_BANDWIDTH(g_extra_bandwidth));
+    if (g_extra_force_channels) opus_encoder_ctl(e, OPUS_SET_FORCE_CHANNELS(g_extra_force_channels));
     return e;
 }
 

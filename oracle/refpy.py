@@ -63,8 +63,18 @@ class Tap(C.Structure):
     ]
 
 
-def encode_stream(pcm, frame_size, channels, bitrate, vbr=CBR, complexity=10, application=APP_LOWDELAY, max_bytes=1275):
-    """pcm float32 [nframes*frame_size*channels] -> (packets u8 [nframes,max_bytes], lens i32, ranges u32)."""
+def encode_stream(pcm, frame_size, channels, bitrate, vbr=CBR, complexity=10, application=APP_LOWDELAY, max_bytes=1275,
+                  bandwidth=0, force_channels=0):
+    """pcm float32 [nframes*frame_size*channels] -> (packets u8 [nframes,max_bytes], lens i32, ranges u32).
+    bandwidth: 0 or OPUS_BANDWIDTH_* 1101..1105; force_channels: 0, 1 or 2."""
+    lib().ref_set_encoder_extras(bandwidth, force_channels)
+    try:
+        return _encode_stream(pcm, frame_size, channels, bitrate, vbr, complexity, application, max_bytes)
+    finally:
+        lib().ref_set_encoder_extras(0, 0)
+
+
+def _encode_stream(pcm, frame_size, channels, bitrate, vbr, complexity, application, max_bytes):
     pcm = np.ascontiguousarray(pcm, np.float32)
     nframes = pcm.size // (frame_size * channels)
     out = np.zeros((nframes, max_bytes), np.uint8)
