@@ -1,0 +1,97 @@
+/* opus_b200.h -- C ABI of libopus_b200.so: batched CELT-only Opus decoding (48 kHz) on NVIDIA B200.
+ *
+ * This is the drop-in boundary for the hot path of the Deniskore/opus-codec crate.  Each entry point names
+ * the reference interface it replaces; the Rust-side binding a maintainer would add beside src/bindings.rs
+ * is shown in INTEGRATION.md.  Plain pointers and sizes only; no variadic CTLs (the reference's
+ * opus_decoder_ctl(st, request, ...) at src/bindings.rs:404-411 is awkward to bind for a batch).
+ *
+ * Error convention: identical to libopus (src/bindings.rs:103-109 <-> src/error.rs:36-62):
+ *   0 OK, -1 BAD_ARG, -2 BUFFER_TOO_SMALL, -3 INTERNAL_ERROR, -4 INVALID_PACKET, -5 UNIMPLEMENTED,
+ *   -6 INVALID_STATE, -7 ALLOC_FAIL.  Batch calls return the call-level status; per-stream results
+ *   (samples per channel, or a negative code) are written to samples_out[].
+ *
+ * Scope of this version: Fs = 48000, CELT-only TOC (config >= 16), packet code 0, fec = false, payload
+ * > 1 byte.  Anything else gives that (stream, frame) the status OPUS_UNIMPLEMENTED (-5) and leaves the
+ * stream's state untouched; other streams are unaffected.  There is no CPU fallback: every entry point
+ * that decodes fails with OPUS_INTERNAL_ERROR if no CUDA device is usable.
+ */
+#ifndef OPUS_B200_H
+#define OPUS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OB_ABI_VERSION 1
+
+typedef struct ObDecoder ObDecoder;
+
+/* Replaces n x opus_decoder_create(Fs, channels, &err) (src/bindings.rs:366-373; Decoder::new src/decoder.rs:35-63).
+ * n_streams independent decoders with `channels` output channels each live on CUDA device `device`.
+ * max_frames: the largest number of consecutive frames per stream any single call will pass (>= 1).
+ * Returns NULL and sets *error on failure. */
+ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, int32_t device, int32_t max_frames, int32_t *error);
+
+/* Replaces opus_decoder_destroy (src/bindings.rs:412-415; Drop for Decoder src/decoder.rs:411-417). */
+void ob_decoder_destroy(ObDecoder *dec);
+
+/* Replaces n x opus_decode_float(st, data, len, pcm, frame_size, 0) (src/bindings.rs:393-403; Decoder::decode_float
+ * src/decoder.rs:134-182): one packet per stream.
+ *   packets        concatenated packet bytes (host memory), TOC byte included
+ *   offsets[s]     byte offset of stream s's packet inside `packets`
+ *   lens[s]        its length in bytes (0 = lost packet -> OPUS_UNIMPLEMENTED in this version)
+ *   pcm_out        host buffer, n_streams * frame_size * channels floats, interleaved per stream
+ *   frame_size     capacity per channel of each stream's slot (120/240/480/960...; a packet longer than this
+ *                  gives OPUS_BUFFER_TOO_SMALL for that stream, like src/decoder.rs:149-160)
+ *   samples_out[s] samples per channel decoded for stream s, or a negative OPUS_* code */
+int32_t ob_decode_float(ObDecoder *dec, const uint8_t *packets, const int32_t *offsets, const int32_t *lens,
+                        float *pcm_out, int32_t frame_size, int32_t *samples_out);
+
+/* n_frames consecutive packets per stream in one call (what a jitter buffer or an offline transcode hands over):
+ * equivalent to n_frames calls of ob_decode_float.  offsets/lens/samples_out/ranges_out are [n_streams][n_frames],
+ * pcm_out is [n_streams][n_frames][frame_size*channels].  ranges_out (optional) receives OPUS_GET_FINAL_RANGE
+ * after every frame (src/decoder.rs:302-312). n_frames <= max_frames. */
+int32_t ob_decode_float_multi(ObDecoder *dec, int32_t n_frames, const uint8_t *packets, const int32_t *offsets,
+                              const int32_t *lens, float *pcm_out, int32_t frame_size, int32_t *samples_out,
+                              uint32_t *ranges_out);
+
+/* Same, with every pointer a DEVICE pointer on the decoder's device (inputs already resident in HBM, outputs
+ * left there); asynchronous on the decoder's stream unless sync != 0. */
+int32_t ob_decode_float_device(ObDecoder *dec, int32_t n_frames, const uint8_t *d_packets, const int32_t *d_offsets,
+                               const int32_t *d_lens, float *d_pcm_out, int32_t frame_size, int32_t *d_samples_out,
+                               uint32_t *d_ranges_out, int32_t sync);
+
+/* Replaces n x opus_decoder_ctl(st, OPUS_GET_FINAL_RANGE_REQUEST, &v) (Decoder::final_range src/decoder.rs:302-312):
+ * out[s] = final range of the last packet decoded for stream s (0 before any packet). */
+int32_t ob_decoder_final_range(ObDecoder *dec, uint32_t *out);
+
+/* Replaces opus_decoder_ctl(st, OPUS_RESET_STATE) (Decoder::reset src/decoder.rs:376-386) for the streams listed in
+ * idx[0..n) (idx == NULL: all streams). */
+int32_t ob_decoder_reset(ObDecoder *dec, const int32_t *idx, int32_t n);
+
+/* Replaces opus_decoder_ctl(st, OPUS_GET_LAST_PACKET_DURATION_REQUEST, &v) (src/decoder.rs:335-346). */
+int32_t ob_decoder_last_packet_duration(ObDecoder *dec, int32_t *out);
+
+/* Introspection for benchmarks: number of streams / channels, device-event time in ms of the three kernels of
+ * the most recent call (symbols, bands, synthesis), kernel launches issued so far. */
+int32_t ob_decoder_streams(const ObDecoder *dec);
+int32_t ob_decoder_channels(const ObDecoder *dec);
+int32_t ob_decoder_kernel_ms(ObDecoder *dec, float ms[3]);
+int64_t ob_decoder_launches(const ObDecoder *dec);
+void *ob_decoder_cuda_stream(ObDecoder *dec);
+
+/* Static helpers mirroring src/packet.rs (packet_get_* on the TOC byte; opus/src/opus_decoder.c:1083-1129). */
+int32_t ob_packet_get_nb_channels(const uint8_t *packet);
+int32_t ob_packet_get_samples_per_frame(const uint8_t *packet, int32_t fs);
+int32_t ob_packet_get_bandwidth(const uint8_t *packet);
+int32_t ob_packet_get_nb_frames(const uint8_t *packet, int32_t len);
+
+/* "1.5.2-b200.<abi>" : bitstream compatibility level + ABI version (cf. version() src/lib.rs:52-54). */
+const char *ob_version(void);
+const char *ob_strerror(int32_t error);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

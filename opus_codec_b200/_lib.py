@@ -1,0 +1,68 @@
+"""Loads libopus_b200.so (the CUDA sm_100a library behind include/opus_b200.h) with ctypes.
+
+There is no CPU implementation behind this package: if the library is missing or no CUDA device is
+usable, every decode entry point fails loudly.
+"""
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libopus_b200.so")
+SRC = os.path.join(HERE, "csrc", "opus_b200.cu")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+# Every symbol include/opus_b200.h declares (tests check that the library exports all of them).
+SYMBOLS = [
+    "ob_decoder_create", "ob_decoder_destroy", "ob_decode_float", "ob_decode_float_multi", "ob_decode_float_device",
+    "ob_decoder_final_range", "ob_decoder_reset", "ob_decoder_last_packet_duration", "ob_decoder_streams",
+    "ob_decoder_channels", "ob_decoder_kernel_ms", "ob_decoder_launches", "ob_decoder_cuda_stream",
+    "ob_packet_get_nb_channels", "ob_packet_get_samples_per_frame", "ob_packet_get_bandwidth", "ob_packet_get_nb_frames",
+    "ob_version", "ob_strerror",
+]
+
+_lib = None
+
+
+def build(verbose=False):
+    """nvcc cross-compiles for sm_100a without a GPU; the .so is built in-tree so it travels to the GPU box."""
+    srcs = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))]
+    if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(s) for s in srcs):
+        return SO
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, SRC]
+    subprocess.run(cmd, check=True)
+    return SO
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO):
+        raise ImportError("opus_codec_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a). There is no CPU fallback." % SO)
+    L = C.CDLL(SO)
+    vp, i32, u8p, i32p, u32p, f32p = C.c_void_p, C.c_int32, C.POINTER(C.c_uint8), C.POINTER(C.c_int32), C.POINTER(C.c_uint32), C.POINTER(C.c_float)
+    L.ob_decoder_create.argtypes = [i32, i32, i32, i32, i32, i32p]; L.ob_decoder_create.restype = vp
+    L.ob_decoder_destroy.argtypes = [vp]; L.ob_decoder_destroy.restype = None
+    L.ob_decode_float.argtypes = [vp, vp, vp, vp, vp, i32, vp]; L.ob_decode_float.restype = i32
+    L.ob_decode_float_multi.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp]; L.ob_decode_float_multi.restype = i32
+    L.ob_decode_float_device.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, i32]; L.ob_decode_float_device.restype = i32
+    L.ob_decoder_final_range.argtypes = [vp, vp]; L.ob_decoder_final_range.restype = i32
+    L.ob_decoder_reset.argtypes = [vp, vp, i32]; L.ob_decoder_reset.restype = i32
+    L.ob_decoder_last_packet_duration.argtypes = [vp, vp]; L.ob_decoder_last_packet_duration.restype = i32
+    L.ob_decoder_streams.argtypes = [vp]; L.ob_decoder_streams.restype = i32
+    L.ob_decoder_channels.argtypes = [vp]; L.ob_decoder_channels.restype = i32
+    L.ob_decoder_kernel_ms.argtypes = [vp, f32p]; L.ob_decoder_kernel_ms.restype = i32
+    L.ob_decoder_launches.argtypes = [vp]; L.ob_decoder_launches.restype = C.c_int64
+    L.ob_decoder_cuda_stream.argtypes = [vp]; L.ob_decoder_cuda_stream.restype = vp
+    for n in ("ob_packet_get_nb_channels", "ob_packet_get_bandwidth"):
+        getattr(L, n).argtypes = [vp]; getattr(L, n).restype = i32
+    L.ob_packet_get_samples_per_frame.argtypes = [vp, i32]; L.ob_packet_get_samples_per_frame.restype = i32
+    L.ob_packet_get_nb_frames.argtypes = [vp, i32]; L.ob_packet_get_nb_frames.restype = i32
+    L.ob_version.restype = C.c_char_p
+    L.ob_strerror.argtypes = [i32]; L.ob_strerror.restype = C.c_char_p
+    _lib = L
+    return L

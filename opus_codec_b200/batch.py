@@ -1,0 +1,133 @@
+"""Host-side mirror of the crate's per-stream wrappers for a BATCH of streams.
+
+`BatchDecoder` keeps the semantics of `Decoder` (reference src/decoder.rs:35-346) for every stream of the
+batch -- `decode_float` returns samples per channel, PCM is interleaved, `final_range()` follows each call,
+`reset()` is OPUS_RESET_STATE -- and calls the CUDA library through the C ABI of include/opus_b200.h.
+Error values are the crate's (src/error.rs:36-62).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+OK, BAD_ARG, BUFFER_TOO_SMALL, INTERNAL_ERROR, INVALID_PACKET, UNIMPLEMENTED, INVALID_STATE, ALLOC_FAIL = 0, -1, -2, -3, -4, -5, -6, -7
+MAX_FRAME_SAMPLES_48KHZ = 5760          # src/constants.rs:8
+
+
+class OpusError(Exception):
+    """Mirror of opus_codec::Error (src/error.rs:8-34)."""
+    NAMES = {-1: "BadArg", -2: "BufferTooSmall", -3: "InternalError", -4: "InvalidPacket", -5: "Unimplemented",
+             -6: "InvalidState", -7: "AllocFail"}
+
+    def __init__(self, code):
+        self.code = int(code)
+        super().__init__("%s (%d): %s" % (self.NAMES.get(self.code, "Unknown"), self.code,
+                                          _lib.lib().ob_strerror(self.code).decode()))
+
+
+def _check(code):
+    if code != OK:
+        raise OpusError(code)
+
+
+def _vp(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+def pack_packets(packets):
+    """list (streams) of list (frames) of bytes -> (buf u8, offsets i32 [S,F], lens i32 [S,F])."""
+    S = len(packets)
+    F = len(packets[0])
+    lens = np.array([[len(p) for p in row] for row in packets], np.int32).reshape(S, F)
+    offsets = np.zeros(S * F, np.int64)
+    np.cumsum(lens.reshape(-1)[:-1], out=offsets[1:])
+    buf = np.frombuffer(b"".join(b"".join(row) for row in packets), np.uint8).copy() if lens.sum() else np.zeros(1, np.uint8)
+    return buf, offsets.astype(np.int32).reshape(S, F), lens
+
+
+class BatchDecoder:
+    """n_streams independent 48 kHz CELT-only Opus decoders on one B200 (mirror of Decoder, src/decoder.rs)."""
+
+    def __init__(self, n_streams, sample_rate=48000, channels=1, device=0, max_frames=1):
+        self._L = _lib.lib()
+        err = C.c_int32(0)
+        self._h = self._L.ob_decoder_create(n_streams, sample_rate, channels, device, max_frames, C.byref(err))
+        if not self._h:
+            raise OpusError(err.value)
+        self.n_streams, self.channels, self.sample_rate, self.max_frames, self.device = n_streams, channels, sample_rate, max_frames, device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ob_decoder_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- decode -------------------------------------------------------------------------------------------
+    def decode_float_multi(self, packets, offsets, lens, frame_size, out=None):
+        """packets: u8 buffer; offsets/lens: i32 [S, F].  Returns (pcm f32 [S, F, frame_size*channels], samples i32 [S, F],
+        final ranges u32 [S, F]).  frame_size is the per-channel capacity of each slot (output.len()/channels in
+        Decoder::decode_float, src/decoder.rs:149)."""
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        lens = np.ascontiguousarray(lens, np.int32)
+        packets = np.ascontiguousarray(packets, np.uint8)
+        if offsets.shape != lens.shape or offsets.ndim != 2 or offsets.shape[0] != self.n_streams:
+            raise OpusError(BAD_ARG)
+        if frame_size <= 0 or frame_size > MAX_FRAME_SAMPLES_48KHZ:
+            raise OpusError(BAD_ARG)
+        S, F = offsets.shape
+        pcm = out if out is not None else np.zeros((S, F, frame_size * self.channels), np.float32)
+        samples = np.zeros((S, F), np.int32)
+        ranges = np.zeros((S, F), np.uint32)
+        _check(self._L.ob_decode_float_multi(self._h, F, _vp(packets), _vp(offsets), _vp(lens), _vp(pcm), frame_size,
+                                             _vp(samples), _vp(ranges)))
+        return pcm, samples, ranges
+
+    def decode_float(self, packets, frame_size):
+        """packets: one bytes object per stream.  Returns (pcm [S, frame_size*channels], samples [S])."""
+        if len(packets) != self.n_streams:
+            raise OpusError(BAD_ARG)
+        buf, offsets, lens = pack_packets([[p] for p in packets])
+        pcm, samples, _ = self.decode_float_multi(buf, offsets, lens, frame_size)
+        return pcm[:, 0], samples[:, 0]
+
+    # -- CTLs ------------------------------------------------------------------------------------------------
+    def final_range(self):
+        out = np.zeros(self.n_streams, np.uint32)
+        _check(self._L.ob_decoder_final_range(self._h, _vp(out)))
+        return out
+
+    def last_packet_duration(self):
+        out = np.zeros(self.n_streams, np.int32)
+        _check(self._L.ob_decoder_last_packet_duration(self._h, _vp(out)))
+        return out
+
+    def reset(self, streams=None):
+        if streams is None:
+            _check(self._L.ob_decoder_reset(self._h, None, 0))
+        else:
+            idx = np.ascontiguousarray(streams, np.int32)
+            _check(self._L.ob_decoder_reset(self._h, _vp(idx), idx.size))
+
+    def kernel_ms(self):
+        ms = (C.c_float * 3)()
+        _check(self._L.ob_decoder_kernel_ms(self._h, ms))
+        return [float(v) for v in ms]
+
+    def launches(self):
+        return int(self._L.ob_decoder_launches(self._h))
+
+    @property
+    def handle(self):
+        return self._h
+
+
+def version():
+    return _lib.lib().ob_version().decode()

@@ -1,0 +1,303 @@
+// dec_bands.cuh -- float reconstruction of the normalised spectrum X from the symbol IR, cooperatively
+// by one warp per (stream, frame).
+//
+// Replays, band by band, what the decoder side of quant_all_bands / quant_band / quant_band_stereo /
+// quant_partition does to X (opus/celt/bands.c:1109-1672) once every integer decision is known:
+//   PVQ pulses -> unit-norm vector (vq.c:121-141) + spreading rotation (vq.c:47-117), noise fill / spectral
+//   folding + renormalise (bands.c:1063-1099, vq.c:383-407), Hadamard (de)interleave and Haar recombination
+//   (bands.c:583-645, :1147-1220), stereo merge / inversion (bands.c:426-476, :1371-1380), and the folding
+//   source `norm` (bands.c:1222-1229).
+// Vector steps are strided over the lanes; the LCG noise (bands.c:61-64) is evaluated with a closed-form jump
+// so every lane gets its own sample without a serial chain.
+#pragma once
+#include "ob_ir.h"
+#include "ob_group.cuh"
+#include "dec_symbols.cuh"   // OB_DEV, tables
+
+#ifdef __CUDACC__
+#define OB_SQRTF(x) sqrtf(x)
+#else
+#include <math.h>
+#define OB_SQRTF(x) sqrtf(x)
+#endif
+
+// celt_lcg_rand^k as an affine map s -> a*s + c (mod 2^32): composed by binary powering.
+struct ObLcg { uint32_t a, c; };
+OB_DEV ObLcg ob_lcg_pow(uint32_t k)
+{
+    ObLcg r = {1u, 0u};
+    uint32_t pa = 1664525u, pc = 1013904223u;
+    while (k) {
+        if (k & 1) { r.c = pa * r.c + pc; r.a = pa * r.a; }
+        pc = pa * pc + pc;
+        pa = pa * pa;
+        k >>= 1;
+    }
+    return r;
+}
+
+// haar1 (bands.c:632-645): N0*stride/2 independent butterflies.
+template <class G>
+OB_DEV void ob_haar1(const G &g, float *X, int N0, int stride)
+{
+    N0 >>= 1;
+    const int total = N0 * stride;
+    for (int t = g.lane; t < total; t += g.n) {
+        const int i = t % stride, j = t / stride;
+        const float t1 = .70710678f * X[stride * 2 * j + i], t2 = .70710678f * X[stride * (2 * j + 1) + i];
+        X[stride * 2 * j + i] = t1 + t2;
+        X[stride * (2 * j + 1) + i] = t1 - t2;
+    }
+    g.sync();
+}
+
+OB_DEV int ob_ordery(int stride, int i)
+{
+    // ordery_table (bands.c:576-581) rows for stride 2, 4, 8, 16
+    switch (stride) {
+    case 2: return i == 0 ? 1 : 0;
+    case 4: { const int t[4] = {3, 0, 2, 1}; return t[i]; }
+    case 8: { const int t[8] = {7, 0, 4, 3, 6, 1, 5, 2}; return t[i]; }
+    default: { const int t[16] = {15, 0, 8, 7, 12, 3, 11, 4, 14, 1, 9, 6, 13, 2, 10, 5}; return t[i & 15]; }
+    }
+}
+
+// deinterleave_hadamard / interleave_hadamard (bands.c:583-630) through a scratch buffer.
+template <class G>
+OB_DEV void ob_hadamard(const G &g, float *X, float *tmp, int N0, int stride, int hadamard, int interleave)
+{
+    const int N = N0 * stride;
+    for (int t = g.lane; t < N; t += g.n) {
+        const int i = t / N0, j = t % N0;                 // i: block, j: position inside block
+        const int row = hadamard ? ob_ordery(stride, i) : i;
+        if (interleave) tmp[j * stride + i] = X[row * N0 + j];
+        else tmp[row * N0 + j] = X[j * stride + i];
+    }
+    g.sync();
+    for (int t = g.lane; t < N; t += g.n) X[t] = tmp[t];
+    g.sync();
+}
+
+// exp_rotation(dir=-1) (vq.c:74-117).  Each (block, residue-class) chain of exp_rotation1 is an independent
+// serial recurrence; chains are spread over the lanes.
+template <class G>
+OB_DEV void ob_rot_pass(const G &g, float *X, int nblocks, int len, int stride, float c, float s)
+{
+    const int chains = nblocks * stride;
+    for (int t = g.lane; t < chains; t += g.n) {
+        float *x = X + (t / stride) * len;
+        const int r = t % stride;
+        const float ms = -s;
+        for (int i = r; i < len - stride; i += stride) {
+            const float x1 = x[i], x2 = x[i + stride];
+            x[i + stride] = c * x2 + s * x1;
+            x[i] = c * x1 + ms * x2;
+        }
+        // backward sweep covers i = len-2*stride-1 .. 0; restricted to this residue class
+        int last = len - 2 * stride - 1;
+        if (last >= 0) {
+            int i = last - ((last - r) % stride + stride) % stride;
+            for (; i >= 0; i -= stride) {
+                const float x1 = x[i], x2 = x[i + stride];
+                x[i + stride] = c * x2 + s * x1;
+                x[i] = c * x1 + ms * x2;
+            }
+        }
+    }
+    g.sync();
+}
+
+template <class G>
+OB_DEV void ob_exp_rotation_inv(const G &g, float *X, int len, int stride, int K, int spread)
+{
+    if (2 * K >= len || spread == 0) return;
+    const int factor = spread == 1 ? 15 : spread == 2 ? 10 : 5;
+    const float gain = (float)(1.0f * len) / (float)(len + factor * K);
+    const float theta = .5f * (gain * gain);
+    const float c = (float)cos((double)((.5f * 3.141592653f) * theta));
+    const float s = (float)cos((double)((.5f * 3.141592653f) * (1.0f - theta)));
+    int stride2 = 0;
+    if (len >= 8 * stride) {
+        stride2 = 1;
+        while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
+    }
+    len = len / stride;
+    if (stride2) ob_rot_pass(g, X, stride, len, stride2, s, c);
+    ob_rot_pass(g, X, stride, len, 1, c, s);
+}
+
+// Fills one terminal partition of X (bands.c:1038-1103).  lowband: folding source aligned with the band start.
+template <class G>
+OB_DEV void ob_fill_leaf(const G &g, const ObLeaf &lf, const int16_t *iy, float *Xb, int off_in_band, const float *lowband,
+        uint32_t seed_in, int spread)
+{
+    float *X = Xb + off_in_band;
+    const int n = lf.n;
+    if (lf.kind == OB_LEAF_PULSES) {
+        uint32_t ryy = 0;
+        for (int j = g.lane; j < n; j += g.n) { const int v = iy[j]; ryy += (uint32_t)(v * v); }
+        ryy = g.sum_u32(ryy);
+        const float gg = (1.f / OB_SQRTF((float)ryy)) * lf.gain;            // normalise_residual (vq.c:121-141)
+        for (int j = g.lane; j < n; j += g.n) X[j] = gg * (float)iy[j];
+        g.sync();
+        ob_exp_rotation_inv(g, X, n, lf.B, lf.K, spread);
+    } else if (lf.kind == OB_LEAF_ZERO) {
+        for (int j = g.lane; j < n; j += g.n) X[j] = 0.f;
+        g.sync();
+    } else if (lf.kind == OB_LEAF_ONE) {
+        if (g.lane == 0) X[0] = lf.K ? -1.f : 1.f;
+        g.sync();
+    } else {
+        // noise / folded spectrum + renormalise (bands.c:1070-1098)
+        const ObLcg first = ob_lcg_pow((uint32_t)lf.lcg_before + (uint32_t)g.lane + 1u);
+        const ObLcg step = ob_lcg_pow((uint32_t)g.n);
+        uint32_t seed = first.a * seed_in + first.c;
+        float e = 0.f;
+        for (int j = g.lane; j < n; j += g.n) {
+            float v;
+            if (lf.kind == OB_LEAF_NOISE) v = (float)((int32_t)seed >> 20);
+            else v = lowband[off_in_band + j] + ((seed & 0x8000u) ? (1.0f / 256) : -(1.0f / 256));
+            X[j] = v;
+            e += v * v;
+            seed = step.a * seed + step.c;
+        }
+        e = 1e-15f + g.sum(e);
+        const float gg = (1.f / OB_SQRTF(e)) * lf.gain;                     // renormalise_vector (vq.c:383-407)
+        for (int j = g.lane; j < n; j += g.n) X[j] = gg * X[j];
+        g.sync();
+    }
+}
+
+// quant_band, resynthesis side (bands.c:1109-1231).  Xb: band buffer; lowband: source in norm[] or nullptr;
+// lowband_out: destination in norm[] or nullptr; scratch/tmp: >= 176 floats each.
+template <class G>
+OB_DEV void ob_band_call(const G &g, const ObFrameIR *ir, int leaf_begin, int leaf_cnt, int band_off_abs, float *Xb, int N, int B,
+        int tf_change, const float *lowband, float *lowband_out, float *scratch, float *tmp, uint32_t seed_in, int spread)
+{
+    const int N0 = N, longBlocks = B == 1;
+    int N_B = N / B, time_divide = 0, recombine = 0;
+    if (N == 1) {
+        ob_fill_leaf(g, ir->leaves[leaf_begin], ir->iy, Xb, 0, nullptr, seed_in, spread);
+        if (lowband_out && g.lane == 0) lowband_out[0] = Xb[0];
+        g.sync();
+        return;
+    }
+    if (tf_change > 0) recombine = tf_change;
+    float *lb = nullptr;
+    if (lowband) {
+        if (recombine || ((N_B & 1) == 0 && tf_change < 0) || B > 1) {
+            for (int j = g.lane; j < N; j += g.n) scratch[j] = lowband[j];
+            g.sync();
+            lb = scratch;
+        } else lb = const_cast<float *>(lowband);          // used read-only in this case
+    }
+    for (int k = 0; k < recombine; k++) if (lb) ob_haar1(g, lb, N >> k, 1 << k);
+    B >>= recombine;
+    N_B <<= recombine;
+    while ((N_B & 1) == 0 && tf_change < 0) {
+        if (lb) ob_haar1(g, lb, N_B, B);
+        B <<= 1; N_B >>= 1;
+        time_divide++; tf_change++;
+    }
+    const int B0 = B, N_B0 = N_B;
+    if (B0 > 1 && lb) ob_hadamard(g, lb, tmp, N_B >> recombine, B0 << recombine, longBlocks, 0);
+
+    for (int l = 0; l < leaf_cnt; l++) {
+        const ObLeaf lf = ir->leaves[leaf_begin + l];
+        ob_fill_leaf(g, lf, ir->iy + lf.off, Xb, (int)lf.off - band_off_abs, lb, seed_in, spread);
+    }
+
+    if (B0 > 1) ob_hadamard(g, Xb, tmp, N_B >> recombine, B0 << recombine, longBlocks, 1);
+    N_B = N_B0; B = B0;
+    for (int k = 0; k < time_divide; k++) { B >>= 1; N_B <<= 1; ob_haar1(g, Xb, N_B, B); }
+    for (int k = 0; k < recombine; k++) ob_haar1(g, Xb, N0 >> k, 1 << k);
+    if (lowband_out) {
+        const float n = OB_SQRTF((float)N0);
+        for (int j = g.lane; j < N0; j += g.n) lowband_out[j] = n * Xb[j];
+        g.sync();
+    }
+}
+
+// stereo_merge (bands.c:426-476)
+template <class G>
+OB_DEV void ob_stereo_merge(const G &g, float *X, float *Y, float mid, int N)
+{
+    float xp = 0.f, side = 0.f;
+    for (int j = g.lane; j < N; j += g.n) { xp += Y[j] * X[j]; side += Y[j] * Y[j]; }
+    xp = g.sum(xp); side = g.sum(side);
+    xp = mid * xp;
+    const float El = mid * mid + side - 2 * xp, Er = mid * mid + side + 2 * xp;
+    if (Er < 6e-4f || El < 6e-4f) {
+        for (int j = g.lane; j < N; j += g.n) Y[j] = X[j];
+        g.sync();
+        return;
+    }
+    const float lgain = 1.f / OB_SQRTF(El), rgain = 1.f / OB_SQRTF(Er);
+    for (int j = g.lane; j < N; j += g.n) {
+        const float l = mid * X[j], r = Y[j];
+        X[j] = lgain * (l - r);
+        Y[j] = rgain * (l + r);
+    }
+    g.sync();
+}
+
+// Reconstructs X (C*N floats, channel c at c*N) for one frame.  norm: 2*OB_NORM_LEN floats, scratch/tmp: 176 each.
+// seed_in: the stream's range-coder state left by the previous frame (celt_decoder.c:1275 passes &st->rng).
+template <class G>
+OB_DEV void ob_reconstruct_bands(const G &g, const ObFrameIR *ir, uint32_t seed_in, float *X, float *norm, float *scratch, float *tmp)
+{
+    const ObFrameHdr &h = ir->hdr;
+    const int LM = h.LM, M = 1 << LM, C = h.C, N = OB_SHORT << LM, end = h.end;
+    const int Bfr = (h.flags & OB_F_TRANSIENT) ? M : 1, spread = h.spread;
+    float *norm2 = norm + OB_NORM_LEN;
+    for (int j = g.lane; j < C * N; j += g.n) X[j] = 0.f;
+    g.sync();
+    for (int i = 0; i < end; i++) {
+        const ObBand br = ir->bands[i];
+        const int boff = M * OB_EBANDS[i], Nb = M * (OB_EBANDS[i + 1] - OB_EBANDS[i]);
+        const int last = i == end - 1, tf_change = h.tf_change[i];
+        float *Xb = X + boff, *Yb = X + N + boff;
+        if (br.flags & 8) {                                          // leaving dual stereo (bands.c:1551-1558)
+            for (int j = g.lane; j < boff; j += g.n) norm[j] = .5f * (norm[j] + norm2[j]);
+            g.sync();
+        }
+        const float *lb1 = br.eff_lowband >= 0 ? norm + br.eff_lowband : nullptr;
+        const float *lb2 = br.eff_lowband >= 0 ? norm2 + br.eff_lowband : nullptr;
+        float *lo1 = last ? nullptr : norm + boff, *lo2 = last ? nullptr : norm2 + boff;
+        if (br.mode == OB_BAND_MONO) {
+            ob_band_call(g, ir, br.leaf_begin_a, br.leaf_cnt_a, boff, Xb, Nb, Bfr, tf_change, lb1, lo1, scratch, tmp, seed_in, spread);
+        } else if (br.mode == OB_BAND_DUAL) {
+            ob_band_call(g, ir, br.leaf_begin_a, br.leaf_cnt_a, boff, Xb, Nb, Bfr, tf_change, lb1, lo1, scratch, tmp, seed_in, spread);
+            ob_band_call(g, ir, br.leaf_begin_b, br.leaf_cnt_b, N + boff, Yb, Nb, Bfr, tf_change, lb2, lo2, scratch, tmp, seed_in, spread);
+        } else if (Nb == 1) {                                        // quant_band_n1 with Y (bands.c:904-937)
+            ob_fill_leaf(g, ir->leaves[br.leaf_begin_a], ir->iy, Xb, 0, nullptr, seed_in, spread);
+            ob_fill_leaf(g, ir->leaves[br.leaf_begin_a + 1], ir->iy, Yb, 0, nullptr, seed_in, spread);
+            if (lo1 && g.lane == 0) lo1[0] = Xb[0];
+            g.sync();
+        } else if (br.mode == OB_BAND_JOINT_N2) {                    // bands.c:1273-1323
+            const int c = (br.flags >> 1) & 1, sign = 1 - 2 * ((br.flags >> 2) & 1);
+            float *x2 = c ? Yb : Xb, *y2 = c ? Xb : Yb;
+            ob_band_call(g, ir, br.leaf_begin_a, br.leaf_cnt_a, c ? N + boff : boff, x2, Nb, Bfr, tf_change, lb1, lo1, scratch, tmp, seed_in, spread);
+            if (g.lane == 0) {
+                const float mid = (1.f / 32768) * br.imid, side = (1.f / 32768) * br.iside;
+                y2[0] = -sign * x2[1];
+                y2[1] = sign * x2[0];
+                Xb[0] = mid * Xb[0]; Xb[1] = mid * Xb[1];
+                Yb[0] = side * Yb[0]; Yb[1] = side * Yb[1];
+                float t = Xb[0]; Xb[0] = t - Yb[0]; Yb[0] = t + Yb[0];
+                t = Xb[1]; Xb[1] = t - Yb[1]; Yb[1] = t + Yb[1];
+                if (br.flags & 1) { Yb[0] = -Yb[0]; Yb[1] = -Yb[1]; }
+            }
+            g.sync();
+        } else {                                                     // joint stereo, N > 2 (bands.c:1324-1381)
+            const float mid = (1.f / 32768) * br.imid;
+            ob_band_call(g, ir, br.leaf_begin_a, br.leaf_cnt_a, boff, Xb, Nb, Bfr, tf_change, lb1, lo1, scratch, tmp, seed_in, spread);
+            ob_band_call(g, ir, br.leaf_begin_b, br.leaf_cnt_b, N + boff, Yb, Nb, Bfr, tf_change, nullptr, nullptr, scratch, tmp, seed_in, spread);
+            ob_stereo_merge(g, Xb, Yb, mid, Nb);
+            if (br.flags & 1) {
+                for (int j = g.lane; j < Nb; j += g.n) Yb[j] = -Yb[j];
+                g.sync();
+            }
+        }
+    }
+}

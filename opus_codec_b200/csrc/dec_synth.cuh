@@ -1,0 +1,410 @@
+// dec_synth.cuh -- per-stream synthesis, cooperatively by one thread block per stream, frames in order:
+//   energy de-quantisation (quant_bands.c:428-542) -> anti-collapse (bands.c:268-362) -> denormalise
+//   (bands.c:196-265) -> inverse MDCT = pre-rotation, mixed-radix FFT, post-rotation, TDAC window
+//   (mdct.c:242-342, kiss_fft.c:48-567) -> pitch post-filter (celt.c:162-256, celt_decoder.c:1301-1325)
+//   -> energy-history update (celt_decoder.c:1327-1357) -> de-emphasis (celt_decoder.c:249-377).
+// This is the only stage that carries per-stream float state from frame to frame; it keeps that state in
+// shared memory across all frames of a launch.
+#pragma once
+#include "ob_ir.h"
+#include "ob_group.cuh"
+#include "dec_bands.cuh"     // ObLcg, OB_SQRTF, tables via dec_symbols.cuh
+
+#define OB_HISTK 1032                       // post-filter history kept per channel: >= COMBFILTER_MAXPERIOD + 2 (celt.h:218)
+#define OB_BUF_LEN (OB_HISTK + OB_MAX_N + OB_OVERLAP)
+
+// Persistent per-stream decoder state (the non-PLC part of struct OpusCustomDecoder, celt_decoder.c:80-123).
+struct ObDecState {
+    uint32_t rng;                 // st->rng: range-coder state left by the last decoded frame (noise seed)
+    uint32_t final_range;         // OpusDecoder.rangeFinal of the last call (opus_decoder.c:651-654)
+    int32_t pf_period, pf_period_old, pf_tapset, pf_tapset_old;
+    float pf_gain, pf_gain_old;
+    float preemph_mem[2];
+    int32_t last_packet_duration;
+    int32_t pad;
+    float oldBandE[2 * OB_NB], oldLogE[2 * OB_NB], oldLogE2[2 * OB_NB], backgroundLogE[2 * OB_NB];
+};
+
+struct ObCpx { float r, i; };
+#define OB_TW(k) (((const ObCpx *)OB_FFT_TWIDDLES)[k])
+#define OB_CMUL(m, a, b) do { (m).r = (a).r * (b).r - (a).i * (b).i; (m).i = (a).r * (b).i + (a).i * (b).r; } while (0)
+
+OB_DEV const int16_t *ob_fft_bitrev(int shift) { return shift == 0 ? OB_FFT_BITREV480 : shift == 1 ? OB_FFT_BITREV240 : shift == 2 ? OB_FFT_BITREV120 : OB_FFT_BITREV60; }
+OB_DEV const int16_t *ob_fft_factors(int shift) { return shift == 0 ? OB_FFT_FACTORS480 : shift == 1 ? OB_FFT_FACTORS240 : shift == 2 ? OB_FFT_FACTORS120 : OB_FFT_FACTORS60; }
+
+// One decimation-in-time stage of opus_fft_impl (kiss_fft.c:521-567) over `nblk` independent transforms whose data
+// start blk_stride floats apart; every butterfly of the stage is an independent work item.
+template <class G>
+OB_DEV void ob_fft_stage(const G &g, float *base, int nblk, int blk_stride, int p, int fstride, int m, int Nst, int mm)
+{
+    if (p == 2) {                                                   // kf_bfly2, m == 4 (kiss_fft.c:48-100)
+        const float tw = 0.7071067812f;
+        const int per = Nst * 4, total = nblk * per;
+        for (int t = g.lane; t < total; t += g.n) {
+            ObCpx *F = (ObCpx *)(base + (t / per) * blk_stride) + ((t % per) >> 2) * 8;
+            const int k = t & 3;
+            ObCpx *F2 = F + 4, x = F2[k], tt;
+            if (k == 0) tt = x;
+            else if (k == 1) { tt.r = (x.r + x.i) * tw; tt.i = (x.i - x.r) * tw; }
+            else if (k == 2) { tt.r = x.i; tt.i = -x.r; }
+            else { tt.r = (x.i - x.r) * tw; tt.i = (-(x.i + x.r)) * tw; }
+            F2[k].r = F[k].r - tt.r; F2[k].i = F[k].i - tt.i;
+            F[k].r += tt.r; F[k].i += tt.i;
+        }
+    } else if (p == 4) {                                            // kf_bfly4 (kiss_fft.c:102-171)
+        const int per = Nst * m, total = nblk * per;
+        for (int t = g.lane; t < total; t += g.n) {
+            const int w = t % per, i = w / m, j = w % m;
+            ObCpx *F = (ObCpx *)(base + (t / per) * blk_stride) + i * mm + j;
+            ObCpx s0, s1, s2, s3, s4, s5;
+            if (m == 1) { s0 = F[1]; s1 = F[2]; s2 = F[3]; }
+            else { OB_CMUL(s0, F[m], OB_TW(j * fstride)); OB_CMUL(s1, F[2 * m], OB_TW(j * fstride * 2)); OB_CMUL(s2, F[3 * m], OB_TW(j * fstride * 3)); }
+            s5.r = F->r - s1.r; s5.i = F->i - s1.i;
+            F->r += s1.r; F->i += s1.i;
+            s3.r = s0.r + s2.r; s3.i = s0.i + s2.i;
+            s4.r = s0.r - s2.r; s4.i = s0.i - s2.i;
+            F[2 * m].r = F->r - s3.r; F[2 * m].i = F->i - s3.i;
+            F->r += s3.r; F->i += s3.i;
+            F[m].r = s5.r + s4.i; F[m].i = s5.i - s4.r;
+            F[3 * m].r = s5.r - s4.i; F[3 * m].i = s5.i + s4.r;
+        }
+    } else if (p == 3) {                                            // kf_bfly3 (kiss_fft.c:176-236)
+        const int per = Nst * m, total = nblk * per;
+        const float epi3i = OB_TW(fstride * m).i;
+        for (int t = g.lane; t < total; t += g.n) {
+            const int w = t % per, i = w / m, j = w % m;
+            ObCpx *F = (ObCpx *)(base + (t / per) * blk_stride) + i * mm + j;
+            ObCpx s0, s1, s2, s3;
+            OB_CMUL(s1, F[m], OB_TW(j * fstride)); OB_CMUL(s2, F[2 * m], OB_TW(j * fstride * 2));
+            s3.r = s1.r + s2.r; s3.i = s1.i + s2.i;
+            s0.r = s1.r - s2.r; s0.i = s1.i - s2.i;
+            F[m].r = F->r - s3.r * .5f; F[m].i = F->i - s3.i * .5f;
+            s0.r *= epi3i; s0.i *= epi3i;
+            F->r += s3.r; F->i += s3.i;
+            F[2 * m].r = F[m].r + s0.i; F[2 * m].i = F[m].i - s0.r;
+            F[m].r = F[m].r - s0.i; F[m].i = F[m].i + s0.r;
+        }
+    } else {                                                        // kf_bfly5 (kiss_fft.c:240-308)
+        const int per = Nst * m, total = nblk * per;
+        const ObCpx ya = OB_TW(fstride * m), yb = OB_TW(fstride * 2 * m);
+        for (int t = g.lane; t < total; t += g.n) {
+            const int w = t % per, i = w / m, u = w % m;
+            ObCpx *F0 = (ObCpx *)(base + (t / per) * blk_stride) + i * mm + u;
+            ObCpx *F1 = F0 + m, *F2 = F0 + 2 * m, *F3 = F0 + 3 * m, *F4 = F0 + 4 * m;
+            ObCpx s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12;
+            s0 = *F0;
+            OB_CMUL(s1, *F1, OB_TW(u * fstride)); OB_CMUL(s2, *F2, OB_TW(2 * u * fstride));
+            OB_CMUL(s3, *F3, OB_TW(3 * u * fstride)); OB_CMUL(s4, *F4, OB_TW(4 * u * fstride));
+            s7.r = s1.r + s4.r; s7.i = s1.i + s4.i; s10.r = s1.r - s4.r; s10.i = s1.i - s4.i;
+            s8.r = s2.r + s3.r; s8.i = s2.i + s3.i; s9.r = s2.r - s3.r; s9.i = s2.i - s3.i;
+            F0->r = s0.r + (s7.r + s8.r); F0->i = s0.i + (s7.i + s8.i);
+            s5.r = s0.r + (s7.r * ya.r + s8.r * yb.r); s5.i = s0.i + (s7.i * ya.r + s8.i * yb.r);
+            s6.r = s10.i * ya.i + s9.i * yb.i; s6.i = -(s10.r * ya.i + s9.r * yb.i);
+            F1->r = s5.r - s6.r; F1->i = s5.i - s6.i; F4->r = s5.r + s6.r; F4->i = s5.i + s6.i;
+            s11.r = s0.r + (s7.r * yb.r + s8.r * ya.r); s11.i = s0.i + (s7.i * yb.r + s8.i * ya.r);
+            s12.r = s9.i * ya.i - s10.i * yb.i; s12.i = s10.r * yb.i - s9.r * ya.i;
+            F2->r = s11.r + s12.r; F2->i = s11.i + s12.i; F3->r = s11.r - s12.r; F3->i = s11.i - s12.i;
+        }
+    }
+    g.sync();
+}
+
+// nblk inverse MDCTs of N2 = 1920>>(shift+1) coefficients each, inputs interleaved with stride nblk in `in`,
+// output block b at out + b*N2 .. (clt_mdct_backward, mdct.c:242-342; the B short blocks of celt_synthesis
+// celt_decoder.c:445-447 are independent up to the TDAC step, so all of them run together).
+template <class G>
+OB_DEV void ob_imdct(const G &g, const float *in, float *out, int shift, int nblk)
+{
+    const int N2 = 1920 >> (shift + 1), N4 = N2 >> 1;
+    const float *trig = OB_MDCT_TRIG + (shift == 0 ? 0 : shift == 1 ? 960 : shift == 2 ? 1440 : 1680);
+    const int16_t *br = ob_fft_bitrev(shift);
+    for (int t = g.lane; t < nblk * N4; t += g.n) {                  // pre-rotation into bit-reversed order
+        const int b = t / N4, i = t % N4;
+        const float x1 = in[b + nblk * (2 * i)], x2 = in[b + nblk * (N2 - 1 - 2 * i)];
+        float *yp = out + b * N2 + (OB_OVERLAP >> 1);
+        const int rev = br[i];
+        yp[2 * rev + 1] = x2 * trig[i] + x1 * trig[N4 + i];
+        yp[2 * rev] = x1 * trig[i] - x2 * trig[N4 + i];
+    }
+    g.sync();
+    {
+        const int16_t *fac = ob_fft_factors(shift);
+        int fstride[9], L = 0, m, m2, p;
+        fstride[0] = 1;
+        do { p = fac[2 * L]; m = fac[2 * L + 1]; fstride[L + 1] = fstride[L] * p; L++; } while (m != 1);
+        m = fac[2 * L - 1];
+        for (int i = L - 1; i >= 0; i--) {
+            m2 = i != 0 ? fac[2 * i - 1] : 1;
+            ob_fft_stage(g, out + (OB_OVERLAP >> 1), nblk, N2, fac[2 * i], fstride[i] << shift, m, fstride[i], m2);
+            m = m2;
+        }
+    }
+    const int half = (N4 + 1) >> 1;
+    for (int t = g.lane; t < nblk * half; t += g.n) {                // post-rotation, both ends at once
+        const int b = t / half, i = t % half;
+        float *yp0 = out + b * N2 + (OB_OVERLAP >> 1) + 2 * i, *yp1 = out + b * N2 + (OB_OVERLAP >> 1) + N2 - 2 - 2 * i;
+        float re = yp0[1], im = yp0[0], t0 = trig[i], t1 = trig[N4 + i];
+        const float yr0 = re * t0 + im * t1, yi0 = re * t1 - im * t0;
+        re = yp1[1]; im = yp1[0];
+        t0 = trig[N4 - i - 1]; t1 = trig[N2 - i - 1];
+        const float yr1 = re * t0 + im * t1, yi1 = re * t1 - im * t0;
+        yp0[0] = yr0; yp1[1] = yi0;
+        yp1[0] = yr1; yp0[1] = yi1;
+    }
+    g.sync();
+    for (int t = g.lane; t < nblk * (OB_OVERLAP / 2); t += g.n) {    // TDAC mirror
+        const int b = t / (OB_OVERLAP / 2), i = t % (OB_OVERLAP / 2);
+        float *o = out + b * N2;
+        const float x1 = o[OB_OVERLAP - 1 - i], x2 = o[i], w1 = OB_WINDOW[i], w2 = OB_WINDOW[OB_OVERLAP - 1 - i];
+        o[i] = w2 * x2 - w1 * x1;
+        o[OB_OVERLAP - 1 - i] = w1 * x2 + w2 * x1;
+    }
+    g.sync();
+}
+
+// comb_filter with y == x (celt.c:190-256).  y[i] only reads outputs at least min(T)-2 samples back, so samples are
+// produced in order in chunks of that many, each chunk in parallel.
+template <class G>
+OB_DEV void ob_comb_filter(const G &g, float *x, int T0, int T1, int N, float g0, float g1, int tapset0, int tapset1)
+{
+    if (g0 == 0 && g1 == 0) return;
+    const float gains[3][3] = {{0.3066406250f, 0.2170410156f, 0.1296386719f}, {0.4638671875f, 0.2680664062f, 0.f}, {0.7998046875f, 0.1000976562f, 0.f}};
+    T0 = ob_imax(T0, 15); T1 = ob_imax(T1, 15);
+    const float g00 = g0 * gains[tapset0][0], g01 = g0 * gains[tapset0][1], g02 = g0 * gains[tapset0][2];
+    const float g10 = g1 * gains[tapset1][0], g11 = g1 * gains[tapset1][1], g12 = g1 * gains[tapset1][2];
+    int overlap = OB_OVERLAP;
+    if (g0 == g1 && T0 == T1 && tapset0 == tapset1) overlap = 0;
+    const int chunk0 = ob_imin(T0, T1) - 2, chunk1 = T1 - 2;
+    for (int base = 0; base < overlap; base += chunk0) {
+        const int lim = ob_imin(overlap, base + chunk0);
+        for (int i = base + g.lane; i < lim; i += g.n) {
+            const float f = OB_WINDOW[i] * OB_WINDOW[i];
+            x[i] = x[i] + ((1.0f - f) * g00) * x[i - T0] + ((1.0f - f) * g01) * (x[i - T0 + 1] + x[i - T0 - 1])
+                        + ((1.0f - f) * g02) * (x[i - T0 + 2] + x[i - T0 - 2])
+                        + (f * g10) * x[i - T1] + (f * g11) * (x[i - T1 + 1] + x[i - T1 - 1])
+                        + (f * g12) * (x[i - T1 + 2] + x[i - T1 - 2]);
+        }
+        g.sync();
+    }
+    if (g1 == 0) return;
+    for (int base = overlap; base < N; base += chunk1) {             // comb_filter_const (celt.c:162-185)
+        const int lim = ob_imin(N, base + chunk1);
+        for (int i = base + g.lane; i < lim; i += g.n)
+            x[i] = x[i] + g10 * x[i - T1] + g11 * (x[i - T1 + 1] + x[i - T1 - 1]) + g12 * (x[i - T1 + 2] + x[i - T1 - 2]);
+        g.sync();
+    }
+}
+
+// Shared-memory working set of one stream.
+struct ObSynthShared {
+    float buf[2][OB_BUF_LEN];        // [history | current frame | overlap tail] per channel (the tail of decode_mem)
+    float freq[2][OB_MAX_N];         // X tile -> MDCT coefficients -> PCM staging
+    float oldBandE[2 * OB_NB], oldLogE[2 * OB_NB], oldLogE2[2 * OB_NB], backgroundLogE[2 * OB_NB];
+    float gain[2 * OB_NB];
+    float scanA[256], scanB[256];
+    float red[32];
+    ObFrameHdr hdr;
+    int32_t pf_period, pf_period_old, pf_tapset, pf_tapset_old;
+    float pf_gain, pf_gain_old, preemph_mem[2];
+    uint32_t rng;
+};
+
+// anti_collapse (bands.c:268-362) on the X tile.
+template <class G>
+OB_DEV void ob_anti_collapse(const G &g, ObSynthShared &sh, float *X, int N, uint32_t seed0)
+{
+    const ObFrameHdr &h = sh.hdr;
+    const int LM = h.LM, C = h.C, end = h.end;
+    uint32_t steps = 0;
+    for (int i = 0; i < end; i++) {
+        const int N0 = OB_EBANDS[i + 1] - OB_EBANDS[i];
+        const int depth = (int)((uint32_t)(1 + h.pulses[i]) / (uint32_t)N0) >> LM;
+        const float thresh = .5f * (float)exp(0.6931471805599453094 * (double)(-.125f * depth));
+        const float sqrt_1 = 1.f / OB_SQRTF((float)(N0 << LM));
+        for (int c = 0; c < C; c++) {
+            float prev1 = sh.oldLogE[c * OB_NB + i], prev2 = sh.oldLogE2[c * OB_NB + i];
+            if (C == 1) { prev1 = fmaxf(prev1, sh.oldLogE[OB_NB + i]); prev2 = fmaxf(prev2, sh.oldLogE2[OB_NB + i]); }
+            float Ediff = sh.oldBandE[c * OB_NB + i] - fminf(prev1, prev2);
+            Ediff = fmaxf(0.f, Ediff);
+            float r = 2.f * (float)exp(0.6931471805599453094 * (double)(-Ediff));
+            if (LM == 3) r *= 1.41421356f;
+            r = fminf(thresh, r);
+            r = r * sqrt_1;
+            float *Xb = X + c * N + (OB_EBANDS[i] << LM);
+            int renorm = 0;
+            for (int k = 0; k < 1 << LM; k++) {
+                if (!(h.collapse_masks[i * C + c] & (1 << k))) {
+                    const ObLcg first = ob_lcg_pow(steps + (uint32_t)g.lane + 1u), step = ob_lcg_pow((uint32_t)g.n);
+                    uint32_t seed = first.a * seed0 + first.c;
+                    for (int j = g.lane; j < N0; j += g.n) {
+                        Xb[(j << LM) + k] = (seed & 0x8000u) ? r : -r;
+                        seed = step.a * seed + step.c;
+                    }
+                    steps += (uint32_t)N0;
+                    renorm = 1;
+                }
+            }
+            if (renorm) {
+                g.sync();
+                float e = 0.f;
+                for (int j = g.lane; j < N0 << LM; j += g.n) e += Xb[j] * Xb[j];
+                e = 1e-15f + g.sum(e);
+                const float gg = 1.f / OB_SQRTF(e);
+                for (int j = g.lane; j < N0 << LM; j += g.n) Xb[j] = gg * Xb[j];
+                g.sync();
+            }
+        }
+    }
+}
+
+// Decodes frame `ir` (already reconstructed normalised spectrum Xg: C*N floats in global memory) into pcm
+// (interleaved, CC channels) and advances the shared-memory state.  Returns samples per channel or an error.
+template <class G>
+OB_DEV int ob_synth_frame(const G &g, ObSynthShared &sh, const ObFrameIR *ir, const float *Xg, float *pcm, int CC)
+{
+    // ---- header to shared memory ----
+    if (g.lane == 0) sh.hdr = ir->hdr;
+    g.sync();
+    const ObFrameHdr &h = sh.hdr;
+    if (h.status <= 0) return h.status;
+    const int LM = h.LM, M = 1 << LM, N = OB_SHORT << LM, C = h.C, end = h.end;
+    const int transient = (h.flags & OB_F_TRANSIENT) != 0, silence = (h.flags & OB_F_SILENCE) != 0;
+    const uint32_t seed_in = sh.rng;
+
+    // ---- energies: coarse recurrence + fine + finalise (quant_bands.c:428-542); one lane per channel ----
+    if (C == 1) for (int i = g.lane; i < OB_NB; i += g.n) sh.oldBandE[i] = fmaxf(sh.oldBandE[i], sh.oldBandE[OB_NB + i]);
+    g.sync();
+    for (int c = g.lane; c < C; c += g.n) {
+        const int intra = (h.flags & OB_F_INTRA) != 0;
+        const float coef = intra ? 0.f : OB_PRED_COEF[LM], beta = intra ? OB_BETA_INTRA[0] : OB_BETA_COEF[LM];
+        float prev = 0.f;
+        for (int i = 0; i < end; i++) {
+            const float q = (float)h.coarse_qi[c * OB_NB + i];
+            float e = fmaxf(-9.f, sh.oldBandE[c * OB_NB + i]);
+            e = coef * e + prev + q;
+            prev = prev + q - beta * q;
+            const int fq = h.fine_quant[i];
+            if (fq > 0) e += ((float)h.fine_q2[c * OB_NB + i] + .5f) * (float)(1 << (14 - fq)) * (1.f / 16384) - .5f;
+            const int fb = h.final_bit[c * OB_NB + i];
+            if (fb >= 0) e += ((float)fb - .5f) * (float)(1 << (14 - fq - 1)) * (1.f / 16384);
+            sh.oldBandE[c * OB_NB + i] = e;
+        }
+    }
+    g.sync();
+
+    // ---- X tile: global -> shared, anti-collapse ----
+    for (int j = g.lane; j < C * N; j += g.n) sh.freq[j / N][j % N] = Xg[j];
+    g.sync();
+    if (h.flags & OB_F_ANTICOLLAPSE) {
+        const ObLcg jump = ob_lcg_pow(h.lcg_total);
+        ob_anti_collapse(g, sh, &sh.freq[0][0], OB_MAX_N, jump.a * seed_in + jump.c);   // note: channel stride is OB_MAX_N in the tile
+    }
+    if (silence) { for (int i = g.lane; i < C * OB_NB; i += g.n) sh.oldBandE[i] = -28.f; }
+    g.sync();
+
+    // ---- denormalise (bands.c:196-265): per-band gain, zero above the last coded band ----
+    for (int t = g.lane; t < C * OB_NB; t += g.n) {
+        const int i = t % OB_NB;
+        const float lg = sh.oldBandE[t] + OB_EMEANS[i];
+        sh.gain[t] = (i < end && !silence) ? (float)exp(0.6931471805599453094 * (double)(lg < 32.f ? lg : 32.f)) : 0.f;
+    }
+    g.sync();
+    for (int t = g.lane; t < C * N; t += g.n) {
+        const int c = t / N, j = t % N, bin = j >> LM;
+        int band = 0;
+        while (band < OB_NB && OB_EBANDS[band + 1] <= bin) band++;
+        sh.freq[c][j] = band < OB_NB ? sh.freq[c][j] * sh.gain[c * OB_NB + band] : 0.f;
+    }
+    g.sync();
+    if (CC == 2 && C == 1) { for (int j = g.lane; j < N; j += g.n) sh.freq[1][j] = sh.freq[0][j]; g.sync(); }
+    if (CC == 1 && C == 2) { for (int j = g.lane; j < N; j += g.n) sh.freq[0][j] = .5f * sh.freq[0][j] + .5f * sh.freq[1][j]; g.sync(); }
+
+    // ---- inverse MDCT into buf[c] + HISTK (celt_synthesis, celt_decoder.c:382-458) ----
+    for (int c = 0; c < CC; c++)
+        ob_imdct(g, sh.freq[c], sh.buf[c] + OB_HISTK, transient ? 3 : 3 - LM, transient ? M : 1);
+
+    // ---- pitch post-filter (celt_decoder.c:1301-1325) ----
+    const float pf_gain_new = (h.flags & OB_F_POSTFILTER) ? .09375f * (float)(h.pf_qg + 1) : 0.f;
+    const int pf_pitch_new = (h.flags & OB_F_POSTFILTER) ? h.pf_pitch : 0, pf_tapset_new = (h.flags & OB_F_POSTFILTER) ? h.pf_tapset : 0;
+    {
+        const int p = ob_imax(sh.pf_period, 15), po = ob_imax(sh.pf_period_old, 15);
+        for (int c = 0; c < CC; c++) {
+            float *x = sh.buf[c] + OB_HISTK;
+            ob_comb_filter(g, x, po, p, OB_SHORT, sh.pf_gain_old, sh.pf_gain, sh.pf_tapset_old, sh.pf_tapset);
+            if (LM != 0) ob_comb_filter(g, x + OB_SHORT, p, pf_pitch_new, N - OB_SHORT, sh.pf_gain, pf_gain_new, sh.pf_tapset, pf_tapset_new);
+        }
+        g.sync();
+        if (g.lane == 0) {
+            sh.pf_period_old = p; sh.pf_gain_old = sh.pf_gain; sh.pf_tapset_old = sh.pf_tapset;
+            sh.pf_period = pf_pitch_new; sh.pf_gain = pf_gain_new; sh.pf_tapset = pf_tapset_new;
+            if (LM != 0) { sh.pf_period_old = sh.pf_period; sh.pf_gain_old = sh.pf_gain; sh.pf_tapset_old = sh.pf_tapset; }
+            sh.rng = h.final_range;
+        }
+    }
+
+    // ---- energy history (celt_decoder.c:1327-1357) ----
+    g.sync();
+    if (C == 1) for (int i = g.lane; i < OB_NB; i += g.n) sh.oldBandE[OB_NB + i] = sh.oldBandE[i];
+    g.sync();
+    for (int i = g.lane; i < 2 * OB_NB; i += g.n) {
+        const float e = sh.oldBandE[i];
+        if (!transient) { sh.oldLogE2[i] = sh.oldLogE[i]; sh.oldLogE[i] = e; }
+        else sh.oldLogE[i] = fminf(sh.oldLogE[i], e);
+        sh.backgroundLogE[i] = fminf(sh.backgroundLogE[i] + (float)ob_imin(160, M) * 0.001f, e);
+        if ((i % OB_NB) >= end) { sh.oldBandE[i] = 0.f; sh.oldLogE[i] = sh.oldLogE2[i] = -28.f; }
+    }
+    g.sync();
+
+    // ---- de-emphasis (celt_decoder.c:249-377): y[n] = x[n] + coef*y[n-1] as a two-level scan ----
+    {
+        const float coef = OB_PREEMPH[0];
+        const int per = (N + g.n - 1) / g.n;                         // samples per lane
+        float cp = 1.f;
+        for (int k = 0; k < per; k++) cp *= coef;                    // coef^per
+        for (int c = 0; c < CC; c++) {
+            const float *x = sh.buf[c] + OB_HISTK;
+            float *y = sh.freq[c];
+            const int lo = ob_imin(N, g.lane * per), hi = ob_imin(N, lo + per);
+            float m = 0.f;
+            for (int j = lo; j < hi; j++) { const float t = x[j] + 1e-30f + m; m = coef * t; }
+            // m = coef * (local response at the chunk end); affine map of the carry: m_out = cp' * m_in + m
+            float a = 1.f;
+            for (int j = lo; j < hi; j++) a *= coef;
+            sh.scanA[g.lane] = a; sh.scanB[g.lane] = m;
+            g.sync();
+            // exclusive scan of affine maps (Hillis-Steele inclusive, then shift)
+            for (int o = 1; o < g.n; o <<= 1) {
+                float pa = 1.f, pb = 0.f;
+                const int have = g.lane >= o;
+                if (have) { pa = sh.scanA[g.lane - o]; pb = sh.scanB[g.lane - o]; }
+                g.sync();
+                if (have) { sh.scanB[g.lane] = sh.scanA[g.lane] * pb + sh.scanB[g.lane]; sh.scanA[g.lane] = sh.scanA[g.lane] * pa; }
+                g.sync();
+            }
+            // carry-in of this lane = inclusive result of lane-1 applied to the stream's memory
+            float carry = sh.preemph_mem[c];
+            if (g.lane > 0) carry = sh.scanA[g.lane - 1] * sh.preemph_mem[c] + sh.scanB[g.lane - 1];
+            const float last_all = sh.scanA[g.n - 1] * sh.preemph_mem[c] + sh.scanB[g.n - 1];
+            m = carry;
+            for (int j = lo; j < hi; j++) { const float t = x[j] + 1e-30f + m; m = coef * t; y[j] = t * (1.f / 32768.f); }
+            g.sync();
+            if (g.lane == 0) sh.preemph_mem[c] = last_all;
+            g.sync();
+        }
+        (void)cp;
+        for (int t = g.lane; t < N * CC; t += g.n) pcm[t] = sh.freq[t % CC][t / CC];
+        g.sync();
+    }
+
+    // ---- slide the history: buf[j] <- buf[j+N] for j < HISTK + overlap (celt_decoder.c:1265-1267, done after instead of before) ----
+    for (int c = 0; c < CC; c++) {
+        float *b = sh.buf[c];
+        const int total = OB_HISTK + OB_OVERLAP;
+        for (int base = 0; base < total; base += N) {               // move in blocks of N: source block lies fully ahead of dest
+            const int lim = ob_imin(total, base + N);
+            for (int j = base + g.lane; j < lim; j += g.n) b[j] = b[j + N];
+            g.sync();
+        }
+    }
+    return N;
+}

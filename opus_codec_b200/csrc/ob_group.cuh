@@ -1,0 +1,54 @@
+// ob_group.cuh -- the cooperating set of lanes a device function runs on: a warp (band reconstruction),
+// a thread block (synthesis), or -- when this code is compiled by g++ for tests/host_emul -- one lane.
+// All cooperative device code is written against this interface: strided loops `for (j = g.lane; j < n;
+// j += g.n)`, g.sync() where lanes exchange data through shared memory, g.sum()/g.sum_u32() all-reduces.
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+struct ObWarp {
+    int lane;
+    static constexpr int n = 32;
+    __device__ __forceinline__ ObWarp() : lane((int)(threadIdx.x & 31)) {}
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    __device__ __forceinline__ float sum(float v) const
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    __device__ __forceinline__ uint32_t sum_u32(uint32_t v) const
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+};
+
+// A whole thread block; red points at >= 32 floats of shared memory reserved for reductions.
+struct ObBlock {
+    int lane, n;
+    float *red;
+    __device__ __forceinline__ ObBlock(float *r) : lane((int)threadIdx.x), n((int)blockDim.x), red(r) {}
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ float sum(float v) const
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        __syncthreads();
+        if ((lane & 31) == 0) red[lane >> 5] = v;
+        __syncthreads();
+        float t = 0.f;
+        for (int w = 0; w < (n + 31) >> 5; w++) t += red[w];
+        return t;
+    }
+};
+#else
+struct ObSolo {
+    static constexpr int lane = 0;
+    static constexpr int n = 1;
+    void sync() const {}
+    float sum(float v) const { return v; }
+    uint32_t sum_u32(uint32_t v) const { return v; }
+};
+#endif

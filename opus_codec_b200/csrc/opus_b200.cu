@@ -1,0 +1,378 @@
+// opus_b200.cu -- kernels + C ABI (include/opus_b200.h) of the batched CELT-only Opus decoder for sm_100a.
+//
+// Pipeline per call (S streams x F consecutive frames):
+//   ob_k_symbols  one THREAD per (stream, frame): range decoder + all integer decisions -> ObFrameIR   (dec_symbols.cuh)
+//   ob_k_bands    one WARP   per (stream, frame): IR -> normalised spectrum X                          (dec_bands.cuh)
+//   ob_k_synth    one BLOCK  per stream, frames in order: energies, anti-collapse, denormalise, IMDCT,
+//                 post-filter, de-emphasis; per-stream float state stays in shared memory across frames  (dec_synth.cuh)
+// Streams are independent: multi-GPU use is one ObDecoder per device over disjoint stream ranges, no collective.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/opus_b200.h"
+#include "dec_symbols.cuh"
+#include "dec_bands.cuh"
+#include "dec_synth.cuh"
+
+#define OB_X_STRIDE (2 * OB_MAX_N)
+#define OB_HIST_LEN (OB_HISTK + OB_OVERLAP)
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+#define OB_SYM_THREADS 128
+__global__ void __launch_bounds__(OB_SYM_THREADS)
+ob_k_symbols(const uint8_t *__restrict__ packets, const int32_t *__restrict__ offsets, const int32_t *__restrict__ lens,
+             ObFrameIR *__restrict__ ir, int total, int dec_channels, int max_frame)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int len = lens[t];
+    ob_decode_symbols(len > 0 ? packets + offsets[t] : nullptr, len, dec_channels, max_frame, ir + t);
+}
+
+#define OB_BANDS_WARPS 4
+#define OB_BANDS_SMEM_PER_WARP ((2 * OB_MAX_N + 2 * OB_NORM_LEN + 2 * OB_MAX_BAND) * (int)sizeof(float))
+__global__ void __launch_bounds__(OB_BANDS_WARPS * 32)
+ob_k_bands(const ObFrameIR *__restrict__ ir, const ObDecState *__restrict__ st, float *__restrict__ Xg, int S, int F)
+{
+    extern __shared__ float smem[];
+    const int warp = threadIdx.x >> 5;
+    const int w = blockIdx.x * OB_BANDS_WARPS + warp;
+    if (w >= S * F) return;
+    const ObFrameIR *fr = ir + w;
+    const int status = fr->hdr.status;
+    if (status <= 0) return;
+    const int s = w / F, f = w % F;
+    // seed = range-coder state left by the previous successfully decoded frame of this stream
+    uint32_t seed = st[s].rng;
+    for (int p = f - 1; p >= 0; p--) if (ir[w - (f - p)].hdr.status > 0) { seed = ir[w - (f - p)].hdr.final_range; break; }
+    float *X = smem + warp * (OB_BANDS_SMEM_PER_WARP / (int)sizeof(float));
+    float *norm = X + 2 * OB_MAX_N, *scratch = norm + 2 * OB_NORM_LEN, *tmp = scratch + OB_MAX_BAND;
+    ObWarp g;
+    ob_reconstruct_bands(g, fr, seed, X, norm, scratch, tmp);
+    g.sync();
+    const int n = fr->hdr.C * status;
+    float *dst = Xg + (size_t)w * OB_X_STRIDE;
+    for (int j = g.lane; j < n; j += 32) dst[j] = X[j];
+}
+
+#define OB_SYNTH_THREADS 128
+__global__ void __launch_bounds__(OB_SYNTH_THREADS)
+ob_k_synth(const ObFrameIR *__restrict__ ir, const float *__restrict__ Xg, ObDecState *__restrict__ st, float *__restrict__ hist,
+           float *__restrict__ pcm, int32_t *__restrict__ samples, uint32_t *__restrict__ ranges, int S, int F, int CC, int frame_size)
+{
+    __shared__ ObSynthShared sh;
+    const int s = blockIdx.x;
+    if (s >= S) return;
+    ObBlock g(sh.red);
+    ObDecState *state = st + s;
+    // ---- state: global -> shared ----
+    for (int i = g.lane; i < 2 * OB_NB; i += g.n) {
+        sh.oldBandE[i] = state->oldBandE[i]; sh.oldLogE[i] = state->oldLogE[i];
+        sh.oldLogE2[i] = state->oldLogE2[i]; sh.backgroundLogE[i] = state->backgroundLogE[i];
+    }
+    for (int c = 0; c < CC; c++) {
+        const float *h = hist + ((size_t)s * CC + c) * OB_HIST_LEN;
+        for (int i = g.lane; i < OB_HIST_LEN; i += g.n) sh.buf[c][i] = h[i];
+    }
+    if (g.lane == 0) {
+        sh.pf_period = state->pf_period; sh.pf_period_old = state->pf_period_old;
+        sh.pf_tapset = state->pf_tapset; sh.pf_tapset_old = state->pf_tapset_old;
+        sh.pf_gain = state->pf_gain; sh.pf_gain_old = state->pf_gain_old;
+        sh.preemph_mem[0] = state->preemph_mem[0]; sh.preemph_mem[1] = state->preemph_mem[1];
+        sh.rng = state->rng;
+    }
+    uint32_t final_range = state->final_range;
+    int last_dur = state->last_packet_duration;
+    g.sync();
+    for (int f = 0; f < F; f++) {
+        const size_t w = (size_t)s * F + f;
+        const int n = ob_synth_frame(g, sh, ir + w, Xg + w * OB_X_STRIDE, pcm + w * (size_t)frame_size * CC, CC);
+        if (n > 0) { final_range = sh.hdr.final_range; last_dur = n; }
+        if (g.lane == 0) { samples[w] = n; if (ranges) ranges[w] = final_range; }
+        g.sync();
+    }
+    // ---- state: shared -> global ----
+    for (int i = g.lane; i < 2 * OB_NB; i += g.n) {
+        state->oldBandE[i] = sh.oldBandE[i]; state->oldLogE[i] = sh.oldLogE[i];
+        state->oldLogE2[i] = sh.oldLogE2[i]; state->backgroundLogE[i] = sh.backgroundLogE[i];
+    }
+    for (int c = 0; c < CC; c++) {
+        float *h = hist + ((size_t)s * CC + c) * OB_HIST_LEN;
+        for (int i = g.lane; i < OB_HIST_LEN; i += g.n) h[i] = sh.buf[c][i];
+    }
+    if (g.lane == 0) {
+        state->pf_period = sh.pf_period; state->pf_period_old = sh.pf_period_old;
+        state->pf_tapset = sh.pf_tapset; state->pf_tapset_old = sh.pf_tapset_old;
+        state->pf_gain = sh.pf_gain; state->pf_gain_old = sh.pf_gain_old;
+        state->preemph_mem[0] = sh.preemph_mem[0]; state->preemph_mem[1] = sh.preemph_mem[1];
+        state->rng = sh.rng; state->final_range = final_range; state->last_packet_duration = last_dur;
+    }
+}
+
+// OPUS_RESET_STATE (celt_decoder.c:1514-1529): zero everything, oldLogE = oldLogE2 = -28.
+__global__ void ob_k_reset(ObDecState *st, float *hist, const int32_t *idx, int n, int S, int CC)
+{
+    const int k = blockIdx.x;
+    if (k >= n) return;
+    const int s = idx ? idx[k] : k;
+    if (s < 0 || s >= S) return;
+    ObDecState *state = st + s;
+    for (int i = threadIdx.x; i < (int)(sizeof(ObDecState) / 4); i += blockDim.x) ((uint32_t *)state)[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * OB_NB; i += blockDim.x) { state->oldLogE[i] = -28.f; state->oldLogE2[i] = -28.f; }
+    float *h = hist + (size_t)s * CC * OB_HIST_LEN;
+    for (int i = threadIdx.x; i < CC * OB_HIST_LEN; i += blockDim.x) h[i] = 0.f;
+}
+
+__global__ void ob_k_gather_state(const ObDecState *st, uint32_t *ranges, int32_t *durations, int S)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    if (ranges) ranges[s] = st[s].final_range;
+    if (durations) durations[s] = st[s].last_packet_duration;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct ObDecoder {
+    int S, CC, device, max_frames;
+    cudaStream_t stream;
+    cudaEvent_t ev[4];
+    bool timed;
+    ObDecState *d_state;
+    float *d_hist;
+    ObFrameIR *d_ir;
+    float *d_X;
+    // staging for the host-pointer entry points
+    uint8_t *d_packets; size_t packets_cap;
+    int32_t *d_offsets, *d_lens, *d_samples; uint32_t *d_ranges;
+    float *d_pcm; size_t pcm_cap;
+    int64_t launches;
+};
+
+#define OB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "opus_b200: %s failed: %s\n", #x, cudaGetErrorString(e_)); return OB_INTERNAL_ERROR; } } while (0)
+
+static int ob_launch(ObDecoder *d, int F, const uint8_t *d_packets, const int32_t *d_offsets, const int32_t *d_lens,
+                     float *d_pcm, int frame_size, int32_t *d_samples, uint32_t *d_ranges)
+{
+    const int total = d->S * F;
+    OB_CUDA(cudaEventRecord(d->ev[0], d->stream));
+    ob_k_symbols<<<(total + OB_SYM_THREADS - 1) / OB_SYM_THREADS, OB_SYM_THREADS, 0, d->stream>>>(
+        d_packets, d_offsets, d_lens, d->d_ir, total, d->CC, frame_size);
+    OB_CUDA(cudaEventRecord(d->ev[1], d->stream));
+    ob_k_bands<<<(total + OB_BANDS_WARPS - 1) / OB_BANDS_WARPS, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, d->stream>>>(
+        d->d_ir, d->d_state, d->d_X, d->S, F);
+    OB_CUDA(cudaEventRecord(d->ev[2], d->stream));
+    ob_k_synth<<<d->S, OB_SYNTH_THREADS, 0, d->stream>>>(d->d_ir, d->d_X, d->d_state, d->d_hist, d_pcm, d_samples, d_ranges,
+                                                        d->S, F, d->CC, frame_size);
+    OB_CUDA(cudaEventRecord(d->ev[3], d->stream));
+    OB_CUDA(cudaGetLastError());
+    d->launches += 3;
+    d->timed = true;
+    return OB_OK;
+}
+
+extern "C" {
+
+ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, int32_t device, int32_t max_frames, int32_t *error)
+{
+    int err = OB_OK;
+    ObDecoder *d = nullptr;
+    int ndev = 0;
+    if (n_streams <= 0 || (channels != 1 && channels != 2) || max_frames <= 0) err = OB_BAD_ARG;
+    else if (fs != 48000) err = OB_UNIMPLEMENTED;          // output rates 8-24 kHz: SURVEY 8(f) row 2
+    else if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        fprintf(stderr, "opus_b200: no usable CUDA device (count=%d, requested=%d); there is no CPU fallback\n", ndev, device);
+        err = OB_INTERNAL_ERROR;
+    }
+    if (err == OB_OK) {
+        d = new (std::nothrow) ObDecoder();
+        if (!d) err = OB_ALLOC_FAIL;
+    }
+    if (err == OB_OK) {
+        memset(d, 0, sizeof(*d));
+        d->S = n_streams; d->CC = channels; d->device = device; d->max_frames = max_frames;
+        const size_t total = (size_t)n_streams * max_frames;
+        bool ok = cudaSetDevice(device) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreate(&d->ev[i]) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->d_state, sizeof(ObDecState) * n_streams) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->d_hist, sizeof(float) * (size_t)n_streams * channels * OB_HIST_LEN) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->d_ir, sizeof(ObFrameIR) * total) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->d_X, sizeof(float) * OB_X_STRIDE * total) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->d_offsets, sizeof(int32_t) * total) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->d_lens, sizeof(int32_t) * total) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->d_samples, sizeof(int32_t) * total) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->d_ranges, sizeof(uint32_t) * total) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(ob_k_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP) == cudaSuccess;
+        if (!ok) {
+            fprintf(stderr, "opus_b200: device allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+            ob_decoder_destroy(d);
+            d = nullptr;
+            err = OB_ALLOC_FAIL;
+        } else if (ob_decoder_reset(d, nullptr, 0) != OB_OK) {
+            ob_decoder_destroy(d);
+            d = nullptr;
+            err = OB_INTERNAL_ERROR;
+        }
+    }
+    if (error) *error = err;
+    return d;
+}
+
+void ob_decoder_destroy(ObDecoder *d)
+{
+    if (!d) return;
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    cudaFree(d->d_state); cudaFree(d->d_hist); cudaFree(d->d_ir); cudaFree(d->d_X); cudaFree(d->d_packets);
+    cudaFree(d->d_offsets); cudaFree(d->d_lens); cudaFree(d->d_samples); cudaFree(d->d_ranges); cudaFree(d->d_pcm);
+    for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+}
+
+int32_t ob_decoder_reset(ObDecoder *d, const int32_t *idx, int32_t n)
+{
+    if (!d || n < 0) return OB_BAD_ARG;
+    OB_CUDA(cudaSetDevice(d->device));
+    int32_t *d_idx = nullptr;
+    int count = d->S;
+    if (idx) {
+        if (n == 0) return OB_OK;
+        count = n;
+        OB_CUDA(cudaMalloc(&d_idx, sizeof(int32_t) * n));
+        OB_CUDA(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, d->stream));
+    }
+    ob_k_reset<<<count, 128, 0, d->stream>>>(d->d_state, d->d_hist, d_idx, count, d->S, d->CC);
+    d->launches += 1;
+    OB_CUDA(cudaStreamSynchronize(d->stream));
+    if (d_idx) cudaFree(d_idx);
+    return OB_OK;
+}
+
+int32_t ob_decode_float_device(ObDecoder *d, int32_t n_frames, const uint8_t *d_packets, const int32_t *d_offsets,
+                               const int32_t *d_lens, float *d_pcm_out, int32_t frame_size, int32_t *d_samples_out,
+                               uint32_t *d_ranges_out, int32_t sync)
+{
+    if (!d || !d_packets || !d_offsets || !d_lens || !d_pcm_out || !d_samples_out) return OB_BAD_ARG;
+    if (n_frames <= 0 || n_frames > d->max_frames || frame_size <= 0) return OB_BAD_ARG;
+    OB_CUDA(cudaSetDevice(d->device));
+    const int r = ob_launch(d, n_frames, d_packets, d_offsets, d_lens, d_pcm_out, frame_size, d_samples_out, d_ranges_out);
+    if (r != OB_OK) return r;
+    if (sync) OB_CUDA(cudaStreamSynchronize(d->stream));
+    return OB_OK;
+}
+
+int32_t ob_decode_float_multi(ObDecoder *d, int32_t n_frames, const uint8_t *packets, const int32_t *offsets, const int32_t *lens,
+                              float *pcm_out, int32_t frame_size, int32_t *samples_out, uint32_t *ranges_out)
+{
+    if (!d || !packets || !offsets || !lens || !pcm_out || !samples_out) return OB_BAD_ARG;
+    if (n_frames <= 0 || n_frames > d->max_frames || frame_size <= 0) return OB_BAD_ARG;
+    OB_CUDA(cudaSetDevice(d->device));
+    const size_t total = (size_t)d->S * n_frames;
+    size_t nbytes = 0;
+    for (size_t i = 0; i < total; i++) {
+        if (lens[i] < 0 || offsets[i] < 0) return OB_BAD_ARG;
+        const size_t e = (size_t)offsets[i] + (size_t)lens[i];
+        if (lens[i] > 0 && e > nbytes) nbytes = e;
+    }
+    if (nbytes == 0) nbytes = 1;
+    if (nbytes > d->packets_cap) {
+        cudaFree(d->d_packets); d->d_packets = nullptr; d->packets_cap = 0;
+        OB_CUDA(cudaMalloc(&d->d_packets, nbytes + nbytes / 4));
+        d->packets_cap = nbytes + nbytes / 4;
+    }
+    const size_t pcm_floats = total * (size_t)frame_size * d->CC;
+    if (pcm_floats > d->pcm_cap) {
+        cudaFree(d->d_pcm); d->d_pcm = nullptr; d->pcm_cap = 0;
+        OB_CUDA(cudaMalloc(&d->d_pcm, pcm_floats * sizeof(float)));
+        d->pcm_cap = pcm_floats;
+    }
+    OB_CUDA(cudaMemcpyAsync(d->d_packets, packets, nbytes, cudaMemcpyHostToDevice, d->stream));
+    OB_CUDA(cudaMemcpyAsync(d->d_offsets, offsets, total * sizeof(int32_t), cudaMemcpyHostToDevice, d->stream));
+    OB_CUDA(cudaMemcpyAsync(d->d_lens, lens, total * sizeof(int32_t), cudaMemcpyHostToDevice, d->stream));
+    const int r = ob_launch(d, n_frames, d->d_packets, d->d_offsets, d->d_lens, d->d_pcm, frame_size, d->d_samples, d->d_ranges);
+    if (r != OB_OK) return r;
+    OB_CUDA(cudaMemcpyAsync(pcm_out, d->d_pcm, pcm_floats * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
+    OB_CUDA(cudaMemcpyAsync(samples_out, d->d_samples, total * sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream));
+    if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out, d->d_ranges, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
+    OB_CUDA(cudaStreamSynchronize(d->stream));
+    return OB_OK;
+}
+
+int32_t ob_decode_float(ObDecoder *d, const uint8_t *packets, const int32_t *offsets, const int32_t *lens, float *pcm_out,
+                        int32_t frame_size, int32_t *samples_out)
+{
+    return ob_decode_float_multi(d, 1, packets, offsets, lens, pcm_out, frame_size, samples_out, nullptr);
+}
+
+static int32_t ob_gather(ObDecoder *d, uint32_t *ranges, int32_t *durations)
+{
+    OB_CUDA(cudaSetDevice(d->device));
+    // d_ranges / d_samples have at least S entries (S * max_frames)
+    ob_k_gather_state<<<(d->S + 127) / 128, 128, 0, d->stream>>>(d->d_state, ranges ? d->d_ranges : nullptr, durations ? d->d_samples : nullptr, d->S);
+    d->launches += 1;
+    if (ranges) OB_CUDA(cudaMemcpyAsync(ranges, d->d_ranges, sizeof(uint32_t) * d->S, cudaMemcpyDeviceToHost, d->stream));
+    if (durations) OB_CUDA(cudaMemcpyAsync(durations, d->d_samples, sizeof(int32_t) * d->S, cudaMemcpyDeviceToHost, d->stream));
+    OB_CUDA(cudaStreamSynchronize(d->stream));
+    return OB_OK;
+}
+int32_t ob_decoder_final_range(ObDecoder *d, uint32_t *out) { return (!d || !out) ? OB_BAD_ARG : ob_gather(d, out, nullptr); }
+int32_t ob_decoder_last_packet_duration(ObDecoder *d, int32_t *out) { return (!d || !out) ? OB_BAD_ARG : ob_gather(d, nullptr, out); }
+
+int32_t ob_decoder_streams(const ObDecoder *d) { return d ? d->S : OB_BAD_ARG; }
+int32_t ob_decoder_channels(const ObDecoder *d) { return d ? d->CC : OB_BAD_ARG; }
+int64_t ob_decoder_launches(const ObDecoder *d) { return d ? d->launches : 0; }
+void *ob_decoder_cuda_stream(ObDecoder *d) { return d ? (void *)d->stream : nullptr; }
+int32_t ob_decoder_kernel_ms(ObDecoder *d, float ms[3])
+{
+    if (!d || !ms || !d->timed) return OB_BAD_ARG;
+    OB_CUDA(cudaSetDevice(d->device));
+    OB_CUDA(cudaEventSynchronize(d->ev[3]));
+    for (int i = 0; i < 3; i++) OB_CUDA(cudaEventElapsedTime(&ms[i], d->ev[i], d->ev[i + 1]));
+    return OB_OK;
+}
+
+// ---- TOC helpers (opus/src/opus_decoder.c:1083-1129, opus/src/opus.c:173-192) ----
+int32_t ob_packet_get_nb_channels(const uint8_t *p) { return (p[0] & 0x4) ? 2 : 1; }
+int32_t ob_packet_get_samples_per_frame(const uint8_t *p, int32_t fs)
+{
+    if (p[0] & 0x80) return (fs << ((p[0] >> 3) & 0x3)) / 400;
+    if ((p[0] & 0x60) == 0x60) return (p[0] & 0x08) ? fs / 50 : fs / 100;
+    const int a = (p[0] >> 3) & 0x3;
+    return a == 3 ? fs * 60 / 1000 : (fs << a) / 100;
+}
+int32_t ob_packet_get_bandwidth(const uint8_t *p)
+{
+    int bw;
+    if (p[0] & 0x80) { bw = 1102 + ((p[0] >> 5) & 0x3); if (bw == 1102) bw = 1101; }
+    else if ((p[0] & 0x60) == 0x60) bw = (p[0] & 0x10) ? 1105 : 1104;
+    else bw = 1101 + ((p[0] >> 5) & 0x3);
+    return bw;
+}
+int32_t ob_packet_get_nb_frames(const uint8_t *p, int32_t len)
+{
+    if (len < 1) return OB_BAD_ARG;
+    const int c = p[0] & 0x3;
+    if (c == 0) return 1;
+    if (c != 3) return 2;
+    if (len < 2) return OB_INVALID_PACKET;
+    return p[1] & 0x3F;
+}
+
+const char *ob_version(void) { return "1.5.2-b200.1"; }
+const char *ob_strerror(int32_t e)
+{
+    static const char *const s[8] = {"success", "invalid argument", "buffer too small", "internal error", "corrupted stream",
+                                     "request not implemented", "invalid state", "memory allocation failed"};
+    return (e > 0 || e < -7) ? "unknown error" : s[-e];
+}
+
+}  // extern "C"

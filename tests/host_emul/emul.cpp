@@ -1,0 +1,50 @@
+// tests/host_emul/emul.cpp -- TEST INFRASTRUCTURE.  Compiles the per-thread / per-warp DEVICE code of the
+// product (opus_codec_b200/csrc/*.cuh) as plain C++ with one emulated lane, so its logic can be checked
+// against the oracle on the CPU-only build box before spending GPU time.  Never shipped, never a fallback:
+// the product library contains no host implementation of these functions.
+#include <cstring>
+#include "../../opus_codec_b200/csrc/dec_symbols.cuh"
+
+extern "C" {
+int emul_ir_size() { return (int)sizeof(ObFrameIR); }
+int emul_hdr_size() { return (int)sizeof(ObFrameHdr); }
+void emul_decode_symbols(const uint8_t *pkt, int len, int dec_channels, int max_frame, ObFrameIR *ir)
+{
+    memset(ir, 0, sizeof(*ir));
+    ob_decode_symbols(pkt, len, dec_channels, max_frame, ir);
+}
+}
+
+#include "../../opus_codec_b200/csrc/dec_bands.cuh"
+#include "../../opus_codec_b200/csrc/dec_synth.cuh"
+#include <cstdlib>
+
+extern "C" {
+// Whole-stream decode through the three device stages with ONE emulated lane each.
+// Xtap (optional): nframes * 1920 floats, normalised spectrum after band reconstruction.
+int emul_decode_stream(const uint8_t *pkts, const int *lens, int stride, int nframes, int max_frame, int dec_channels,
+                       float *pcm_out, uint32_t *ranges, int *samples, float *Xtap)
+{
+    ObSynthShared *sh = (ObSynthShared *)calloc(1, sizeof(ObSynthShared));
+    ObFrameIR *ir = (ObFrameIR *)calloc(1, sizeof(ObFrameIR));
+    float *X = (float *)calloc(2 * OB_MAX_N, sizeof(float));
+    float *norm = (float *)calloc(2 * OB_NORM_LEN, sizeof(float));
+    float scratch[OB_MAX_BAND], tmp[OB_MAX_BAND];
+    for (int i = 0; i < 2 * OB_NB; i++) sh->oldLogE[i] = sh->oldLogE2[i] = -28.f;
+    ObSolo g;
+    for (int f = 0; f < nframes; f++) {
+        memset(ir, 0, sizeof(*ir));
+        ob_decode_symbols(pkts + (size_t)f * stride, lens[f], dec_channels, max_frame, ir);
+        int n = ir->hdr.status;
+        if (n > 0) {
+            ob_reconstruct_bands(g, ir, sh->rng, X, norm, scratch, tmp);
+            if (Xtap) memcpy(Xtap + (size_t)f * 1920, X, sizeof(float) * ir->hdr.C * n);
+            n = ob_synth_frame(g, *sh, ir, X, pcm_out + (size_t)f * max_frame * dec_channels, dec_channels);
+        }
+        samples[f] = n;
+        ranges[f] = n > 0 ? ir->hdr.final_range : 0;
+    }
+    free(sh); free(ir); free(X); free(norm);
+    return 0;
+}
+}

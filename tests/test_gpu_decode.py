@@ -1,0 +1,160 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI
+(include/opus_b200.h via opus_codec_b200.batch), against the golden vectors the reference produced,
+against the oracle on the same inputs, and -- at full batch size -- through tiling properties.
+
+Bars (BASELINE.json north_star): OPUS_GET_FINAL_RANGE bit-exact; float PCM max |err| <= 1e-4 of full scale
+and opus_compare pass."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+PCM_TOL = 1e-4
+
+
+def _offsets(S, F, stride):
+    return (np.arange(S * F, dtype=np.int32) * stride).reshape(S, F)
+
+
+def _decode_all(g, max_frames=None, streams=None):
+    from opus_codec_b200.batch import BatchDecoder
+    pk = g["packets"] if streams is None else g["packets"][streams]
+    ln = g["lens"] if streams is None else g["lens"][streams]
+    S, F, stride = pk.shape
+    with BatchDecoder(S, 48000, g["dec_channels"], device=0, max_frames=F) as dec:
+        return dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, g["frame_size"])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_golden_final_range_and_pcm(name):
+    from oracle import oraclepy
+    g = load_golden(name)
+    pcm, samples, ranges = _decode_all(g)
+    assert (samples == g["frame_size"]).all()
+    assert (ranges == g["dec_rng"]).all(), "OPUS_GET_FINAL_RANGE differs from the reference decoder"
+    npcm = g["pcm"].shape[0]
+    assert np.abs(pcm[:npcm] - g["pcm"]).max() <= PCM_TOL
+    for s in range(g["packets"].shape[0]):          # every stream against the oracle on the same packets
+        opcm, orng, _ = oraclepy.decode_stream(g["packets"][s], g["lens"][s], g["frame_size"], g["dec_channels"])
+        assert (ranges[s] == orng).all()
+        assert np.abs(pcm[s] - opcm).max() <= PCM_TOL
+
+
+def test_streaming_one_frame_per_call_matches_multi():
+    """State must persist across calls exactly like Decoder::decode_float called once per packet."""
+    from opus_codec_b200.batch import BatchDecoder
+    g = load_golden("cfg1_stereo_20ms_128k_cbr")
+    S, F, stride = g["packets"].shape
+    F = 20
+    with BatchDecoder(S, 48000, 2, device=0, max_frames=1) as dec:
+        assert (dec.final_range() == 0).all() and (dec.last_packet_duration() == 0).all()
+        for f in range(F):
+            pcm, smp = dec.decode_float([bytes(g["packets"][s, f, :g["lens"][s, f]]) for s in range(S)], 960)
+            assert (smp == 960).all()
+            assert (dec.final_range() == g["dec_rng"][:, f]).all()
+            assert np.abs(pcm[0] - g["pcm"][0, f]).max() <= PCM_TOL
+        assert (dec.last_packet_duration() == 960).all()
+
+
+def test_mixed_frame_sizes_in_one_batch():
+    """BASELINE config 4: 2.5/5/10/20 ms streams (incl. transient class) decoded by ONE launch."""
+    from opus_codec_b200.batch import BatchDecoder
+    names = ["cfg4_stereo_2p5ms_96k", "cfg4_stereo_5ms_96k", "cfg4_stereo_10ms_96k", "cfg3_stereo_20ms_96k_cbr"]
+    gs = [load_golden(n) for n in names]
+    F = 50
+    stride = max(g["packets"].shape[2] for g in gs)
+    pk = np.zeros((len(gs) * 3, F, stride), np.uint8)
+    ln = np.zeros((len(gs) * 3, F), np.int32)
+    for k, g in enumerate(gs):
+        pk[3 * k:3 * k + 3, :, :g["packets"].shape[2]] = g["packets"][:3, :F]
+        ln[3 * k:3 * k + 3] = g["lens"][:3, :F]
+    S = pk.shape[0]
+    with BatchDecoder(S, 48000, 2, device=0, max_frames=F) as dec:
+        pcm, samples, ranges = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, 960)
+    for k, g in enumerate(gs):
+        fs = g["frame_size"]
+        assert (samples[3 * k:3 * k + 3] == fs).all()
+        assert (ranges[3 * k:3 * k + 3] == g["dec_rng"][:3, :F]).all()
+        assert np.abs(pcm[3 * k, :, :fs * 2] - g["pcm"][0, :F]).max() <= PCM_TOL
+
+
+def test_per_stream_errors_do_not_disturb_neighbours():
+    from opus_codec_b200.batch import BatchDecoder, UNIMPLEMENTED, BUFFER_TOO_SMALL
+    g = load_golden("cfg2_mono_20ms_64k_cbr")
+    S, F = 6, 10
+    pk = g["packets"][:S, :F].copy()
+    ln = g["lens"][:S, :F].copy()
+    stride = pk.shape[2]
+    ln[1, 3] = 0                      # lost packet -> PLC is not on this path: UNIMPLEMENTED, state untouched
+    pk[2, 4, 0] = 0x08                # SILK TOC
+    pk[3, 5, 0] = 0xF9                # code-1 packet (two frames)
+    ln[4, 6] = 2                      # 1-byte payload -> DTX/PLC
+    with BatchDecoder(S, 48000, 1, device=0, max_frames=F) as dec:
+        pcm, samples, ranges = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, 960)
+    assert samples[1, 3] == UNIMPLEMENTED and samples[2, 4] == UNIMPLEMENTED
+    assert samples[3, 5] == UNIMPLEMENTED and samples[4, 6] == UNIMPLEMENTED
+    good = np.ones((S, F), bool)
+    for s, f in ((1, 3), (2, 4), (3, 5), (4, 6)):
+        good[s, f] = False
+    assert (samples[good] == 960).all()
+    assert (ranges[0] == g["dec_rng"][0, :F]).all() and (ranges[5] == g["dec_rng"][5, :F]).all()
+    assert np.abs(pcm[0] - g["pcm"][0, :F]).max() <= PCM_TOL
+    # frames before the damaged one are untouched
+    assert (ranges[1, :3] == g["dec_rng"][1, :3]).all()
+    # 20 ms packets into a 10 ms slot
+    with BatchDecoder(S, 48000, 1, device=0, max_frames=F) as dec:
+        _, samples, _ = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), g["lens"][:S, :F], 480)
+    assert (samples == BUFFER_TOO_SMALL).all()
+
+
+def test_reset_restarts_streams():
+    from opus_codec_b200.batch import BatchDecoder
+    g = load_golden("cfg2_mono_20ms_64k_cbr")
+    S, F, stride = g["packets"].shape
+    F = 12
+    with BatchDecoder(S, 48000, 1, device=0, max_frames=F) as dec:
+        a, _, _ = dec.decode_float_multi(g["packets"][:, :F].reshape(-1), _offsets(S, g["packets"].shape[1], stride)[:, :F], g["lens"][:, :F], 960)
+        a = a.copy()
+        dec.reset([0, 2])
+        b, _, rb = dec.decode_float_multi(g["packets"][:, :F].reshape(-1), _offsets(S, g["packets"].shape[1], stride)[:, :F], g["lens"][:, :F], 960)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])      # reset streams replay identically
+    assert not np.array_equal(a[1], b[1])                                   # the others carried their state on
+    assert (rb == g["dec_rng"][:, :F]).all()                               # final range never depends on state
+
+
+def test_opus_compare_passes():
+    """The reference's own conformance metric (opus/src/opus_compare.c) on GPU output vs reference decoder output."""
+    from oracle import refpy
+    if not os.path.exists(refpy.OPUS_COMPARE):
+        pytest.skip("oracle/_ref/opus_compare not built")
+    for name, ch in (("cfg2_mono_20ms_64k_cbr", 1), ("cfg1_stereo_20ms_128k_cbr", 2), ("cfg4_stereo_5ms_96k", 2)):
+        g = load_golden(name)
+        pcm, _, _ = _decode_all(g, streams=[0])
+        with tempfile.TemporaryDirectory() as td:
+            ok, txt = refpy.opus_compare(g["pcm"][0].reshape(-1), pcm[0].reshape(-1), ch, td)
+        assert ok, txt
+
+
+def test_full_size_batch_4096_streams_tiling_property():
+    """BASELINE config 2 at full size: 4096 mono 20 ms 64 kb/s streams.  The batch tiles the 9 golden streams, so every
+    tile must reproduce the golden final ranges bit-exactly and identical PCM across tiles (independence of streams)."""
+    from opus_codec_b200.batch import BatchDecoder
+    g = load_golden("cfg2_mono_20ms_64k_cbr")
+    P, F, stride = g["packets"].shape
+    F = 25
+    S = 4096
+    idx = np.arange(S) % P
+    pk = np.ascontiguousarray(g["packets"][idx, :F])
+    ln = np.ascontiguousarray(g["lens"][idx, :F])
+    with BatchDecoder(S, 48000, 1, device=0, max_frames=F) as dec:
+        pcm, samples, ranges = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, 960)
+        assert dec.launches() >= 3
+    assert (samples == 960).all()
+    assert (ranges == g["dec_rng"][idx, :F]).all()
+    assert np.abs(pcm[0] - g["pcm"][0, :F]).max() <= PCM_TOL
+    for s in range(P, S):
+        assert np.array_equal(pcm[s], pcm[s % P])
