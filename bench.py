@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the batched CELT decode path (BASELINE.json configs[1]):
+4096 mono 48 kHz CELT-only 20 ms @ 64 kb/s streams per GPU, decoded with final-range verification.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference]
+
+A "step" is one pass of the hot path over one batch: every one of the 4096 streams advances by F consecutive
+20 ms frames (default F=50 = 1 s of audio per stream per step).  Packets were pre-encoded by the reference
+(tests/golden/make_golden.py -> tests/golden/pool_cfg2_mono_20ms_64k_cbr.npz: 256 distinct streams, tiled).
+
+  value  = audio-seconds decoded per second (= number of real-time streams one GPU sustains), whole job over all
+           N GPUs, inputs resident in HBM when the timed region starts (device-pointer C-ABI entry point);
+  e2e    = the same metric through the host-pointer C-ABI call (ob_decode_float_multi) with pinned host buffers:
+           H2D of packets/offsets/lengths and D2H of PCM/samples/final ranges are inside the timed region;
+  roofline = HBM roofline of the dominant kernel, from SURVEY.md 8(d)'s algorithmic bytes per frame;
+  cpu_baseline = the UNMODIFIED reference (oracle/_ref, libopus 1.5.2) on this box's host cores, one stream per
+           thread, on a bounded sample of the same workload.
+
+--impl reference prints the same line for the reference's own CPU implementation (all host threads).
+Multi-GPU (torchrun, one rank per GPU): streams are sharded, there is no collective on the data path; "weak" scaling
+(4096 streams per GPU).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+STREAMS_PER_GPU = 4096
+FRAME = 960
+POOL = os.path.join(ROOT, "tests", "golden", "pool_cfg2_mono_20ms_64k_cbr.npz")
+WORKLOAD = "4096 mono 48 kHz CELT-only 20 ms @64 kb/s CBR decode streams per GPU (BASELINE configs[1]), final range verified"
+
+
+def algorithmic_bytes_per_frame(F, C=1, N=FRAME, P=160):
+    """B_dec = P + 4*C*N + S_dec/F, S_dec = per-channel (4576 read + (N+120)*4 written) + energies
+    1344 + scalars 128 (read and written once per launch)."""
+    s_dec = C * (4576 + (N + 120) * 4) + 1344 + 128
+    return P + 4 * C * N + s_dec / F
+
+
+def load_pool(nstreams, F):
+    z = np.load(POOL)
+    pk, ln, rng = z["packets"], z["lens"], z["dec_rng"]
+    P = pk.shape[0]
+    reps = (F + pk.shape[1] - 1) // pk.shape[1]
+    if reps > 1:            # longer runs replay the pool's frames (final range is stateless, PCM is not compared here)
+        pk, ln, rng = np.tile(pk, (1, reps, 1)), np.tile(ln, (1, reps)), np.tile(rng, (1, reps))
+    idx = np.arange(nstreams) % P
+    return np.ascontiguousarray(pk[idx, :F]), np.ascontiguousarray(ln[idx, :F]), np.ascontiguousarray(rng[idx, :F])
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = []
+        for k, name in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+            if any(len(r) >= 7 and r[k].lower().startswith("active") for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def cpu_reference_run(nthreads, target_audio_s, F=50):
+    """Times the unmodified reference (oracle/_ref) decoding a bounded sample of the workload with a pthread pool,
+    one stream per thread at a time.  Returns (audio-s/s, description)."""
+    from oracle import refpy
+    ns = max(nthreads, int(round(target_audio_s / (F * 0.02))))
+    pk, ln, rng = load_pool(ns, F)
+    secs, _, got = refpy.decode_pool(pk, ln, FRAME, 1, nthreads, want_ranges=True)
+    assert (got == rng).all(), "reference decoder final range != stored encoder range?!"
+    audio = ns * F * 0.02
+    return audio / secs, "%d streams x %d frames (%.0f audio-s) of the same packet pool, %d threads, %.2f s wall" % (ns, F, audio, nthreads, secs)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    # bounded sample per step: ~1.5 s of wall time on all cores
+    vals = []
+    target = 450.0 * cores * 1.5
+    for i in range(args.warmup):
+        cpu_reference_run(cores, target / 4, args.frames)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        v, sample = cpu_reference_run(cores, target, args.frames)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    val = float(np.mean(vals))
+    line = {
+        "impl": "reference", "metric": "decode_audio_seconds_per_second", "value": val, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_stream_per_step": args.frames, "note": "reference libopus 1.5.2 (oracle/_ref) on host cores"},
+        "cpu_baseline": {"value": val, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": val, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from opus_codec_b200 import _lib
+    from opus_codec_b200.batch import BatchDecoder
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))   # plumbing only: barrier + max-reduce of timings
+    L = _lib.lib()
+    S, F = STREAMS_PER_GPU, args.frames
+    pk, ln, rng_expect = load_pool(S, F)        # rank-independent content; streams are sharded by rank (disjoint index ranges)
+    stride = pk.shape[2]
+    offsets = (np.arange(S * F, dtype=np.int32) * stride).reshape(S, F)
+
+    dec = BatchDecoder(S, 48000, 1, device=local, max_frames=F)
+    ext = torch.cuda.ExternalStream(L.ob_decoder_cuda_stream(dec.handle), device=local)
+    dev = torch.device("cuda", local)
+
+    # ---- resident inputs / outputs (for `value`) ----
+    d_pk = torch.from_numpy(pk.reshape(-1)).to(dev)
+    d_off = torch.from_numpy(offsets.reshape(-1)).to(dev)
+    d_len = torch.from_numpy(ln.reshape(-1)).to(dev)
+    d_pcm = torch.empty(S * F * FRAME, dtype=torch.float32, device=dev)
+    d_smp = torch.empty(S * F, dtype=torch.int32, device=dev)
+    d_rng = torch.empty(S * F, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def step_device():
+        r = L.ob_decode_float_device(dec.handle, F, d_pk.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_pcm.data_ptr(), FRAME,
+                                     d_smp.data_ptr(), d_rng.data_ptr(), 0)
+        assert r == 0, r
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    barrier()
+    kms = np.zeros(3)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = dec.launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(args.steps):
+        step_device()
+        kms += np.array(dec.kernel_ms())        # per-kernel CUDA-event times on the launching stream (waits for the step)
+    e1.record(ext)
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    launches = dec.launches() - launches0
+    kms /= args.steps
+    # verify what the timed steps produced
+    assert (d_smp.cpu().numpy() == FRAME).all()
+    assert (d_rng.cpu().numpy().view(np.uint32).reshape(S, F) == rng_expect).all(), "final range mismatch"
+
+    # ---- end to end through the host-pointer C ABI (pinned buffers) ----
+    h_pk = torch.from_numpy(pk.reshape(-1).copy()).pin_memory()
+    h_off = torch.from_numpy(offsets.reshape(-1).copy()).pin_memory()
+    h_len = torch.from_numpy(ln.reshape(-1).copy()).pin_memory()
+    h_pcm = torch.empty(S * F * FRAME, dtype=torch.float32).pin_memory()
+    h_smp = torch.empty(S * F, dtype=torch.int32).pin_memory()
+    h_rng = torch.empty(S * F, dtype=torch.int32).pin_memory()
+
+    def step_host():
+        r = L.ob_decode_float_multi(dec.handle, F, h_pk.data_ptr(), h_off.data_ptr(), h_len.data_ptr(), h_pcm.data_ptr(), FRAME,
+                                    h_smp.data_ptr(), h_rng.data_ptr())
+        assert r == 0, r
+
+    e2e_steps = max(2, min(args.steps, 5))
+    step_host()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(ext)
+    for _ in range(e2e_steps):
+        step_host()
+    f1.record(ext)
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop() if rank == 0 else None
+    assert (h_rng.numpy().view(np.uint32).reshape(S, F) == rng_expect).all()
+    h2d = int(h_pk.numel() + 4 * h_off.numel() + 4 * h_len.numel())
+    d2h = int(4 * h_pcm.numel() + 4 * h_smp.numel() + 4 * h_rng.numel())
+
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    audio_per_step = world * S * F * 0.02
+    value = audio_per_step * args.steps / (ms_dev / 1000.0)
+    e2e = audio_per_step * e2e_steps / (ms_e2e / 1000.0)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        names = ["ob_k_symbols", "ob_k_bands", "ob_k_synth"]
+        dom = int(np.argmax(kms))
+        bytes_per_launch = algorithmic_bytes_per_frame(F) * S * F
+        achieved = bytes_per_launch / (kms[dom] / 1000.0) / 1e9
+        roof = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "kernel_ms": dict(zip(names, [float(v) for v in kms])),
+                "algorithmic_bytes_per_frame": algorithmic_bytes_per_frame(F),
+                "pipeline_achieved_GBps": bytes_per_launch / (float(kms.sum()) / 1000.0) / 1e9}
+        cpu = None
+        if world == 1 or True:
+            cores = os.cpu_count() or 1
+            try:
+                v, sample = cpu_reference_run(cores, 450.0 * cores * 2.5, 50)
+                cpu = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample}
+            except Exception as ex:   # the reference .so did not travel: report, do not fake
+                cpu = {"value": None, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": "unavailable: %r" % (ex,)}
+        line = {
+            "metric": "decode_audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "streams_per_gpu": S, "frames_per_stream_per_step": F, "frame_ms": 20, "bitrate": 64000,
+                       "packet_bytes": 160, "rt_stream_capacity": value,
+                       "l2": "per-step working set (IR+spectrum+PCM, %.1f GB) exceeds the 126 MB L2" % ((S * F * (12.6e3 + 7.7e3 + 3.84e3)) / 1e9),
+                       "sharding": "streams split by rank, no collective"},
+            "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    dec.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--frames", type=int, default=50, help="consecutive 20 ms frames per stream per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -14,7 +14,7 @@ def pytest_configure(config):
 
 def golden_names():
     g = os.path.join(ROOT, "tests", "golden")
-    return sorted(f[:-4] for f in os.listdir(g) if f.endswith(".npz"))
+    return sorted(f[:-4] for f in os.listdir(g) if f.endswith(".npz") and not f.startswith("pool_"))
 
 
 def load_golden(name):

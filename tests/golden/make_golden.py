@@ -43,10 +43,15 @@ CONFIGS = {
     "stereo_dec_of_mono_pkts":    (1, 960, 64000, 0, 3, 50, 1, {"dec_channels": 2}),
     "mono_dec_of_stereo_pkts":    (2, 960, 96000, 0, 3, 50, 1, {"dec_channels": 1}),
 }
+# Packet pools for bench.py ("throughput sets reuse a pool of 256 distinct streams tiled to the batch size").
+# No PCM is stored; final ranges are, so the bench can verify every decoded frame.
+POOLS = {
+    "pool_cfg2_mono_20ms_64k_cbr": (1, 960, 64000, 0, 256, 50, 0, {}),
+}
 
 
 def make(name):
-    ch, fs, br, vbr, ns, nf, npcm, ex = CONFIGS[name]
+    ch, fs, br, vbr, ns, nf, npcm, ex = (CONFIGS.get(name) or POOLS[name])
     dec_ch = ex.get("dec_channels", ch)
     pk_all, ln_all, er_all, dr_all, pcm_all = [], [], [], [], []
     stride = 0
@@ -63,11 +68,12 @@ def make(name):
         stride = max(stride, int(ln.max()))
     packets = np.stack([p[:, :stride] for p in pk_all])
     np.savez_compressed(os.path.join(HERE, name + ".npz"), packets=packets, lens=np.stack(ln_all),
-                        enc_rng=np.stack(er_all), dec_rng=np.stack(dr_all), pcm=np.stack(pcm_all),
+                        enc_rng=np.stack(er_all), dec_rng=np.stack(dr_all),
+                        pcm=np.stack(pcm_all) if pcm_all else np.zeros((0, nf, fs * dec_ch), np.float32),
                         meta=np.array([ch, fs, br, vbr, dec_ch], np.int32))
     return packets.shape
 
 
 if __name__ == "__main__":
-    for n in (sys.argv[1:] or CONFIGS):
+    for n in (sys.argv[1:] or list(CONFIGS) + list(POOLS)):
         print(n, make(n))

@@ -107,7 +107,7 @@ def test_per_stream_errors_do_not_disturb_neighbours():
     assert (ranges[1, :3] == g["dec_rng"][1, :3]).all()
     # 20 ms packets into a 10 ms slot
     with BatchDecoder(S, 48000, 1, device=0, max_frames=F) as dec:
-        _, samples, _ = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), g["lens"][:S, :F], 480)
+        _, samples, _ = dec.decode_float_multi(np.ascontiguousarray(g["packets"][:S, :F]).reshape(-1), _offsets(S, F, stride), g["lens"][:S, :F], 480)
     assert (samples == BUFFER_TOO_SMALL).all()
 
 
