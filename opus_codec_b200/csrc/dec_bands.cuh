@@ -87,20 +87,29 @@ OB_DEV void ob_rot_pass(const G &g, float *X, int nblocks, int len, int stride, 
     for (int t = g.lane; t < chains; t += g.n) {
         float *x = X + (t / stride) * len;
         const int r = t % stride;
-        const float ms = -s;
-        for (int i = r; i < len - stride; i += stride) {
-            const float x1 = x[i], x2 = x[i + stride];
-            x[i + stride] = c * x2 + s * x1;
-            x[i] = c * x1 + ms * x2;
+        // forward sweep over i = r, r+stride, ... < len-stride: the rotated x[i+stride] is carried in a register
+        int i = r;
+        if (i < len - stride) {
+            float x1 = x[i];
+            for (; i < len - stride; i += stride) {
+                const float x2 = x[i + stride];
+                x[i] = c * x1 - s * x2;
+                x1 = c * x2 + s * x1;
+            }
+            x[i] = x1;
         }
-        // backward sweep covers i = len-2*stride-1 .. 0; restricted to this residue class
-        int last = len - 2 * stride - 1;
+        // backward sweep covers i = len-2*stride-1 .. 0, restricted to this residue class; x[i] is carried downwards
+        const int last = len - 2 * stride - 1;
         if (last >= 0) {
-            int i = last - ((last - r) % stride + stride) % stride;
-            for (; i >= 0; i -= stride) {
-                const float x1 = x[i], x2 = x[i + stride];
-                x[i + stride] = c * x2 + s * x1;
-                x[i] = c * x1 + ms * x2;
+            i = last - ((last - r) % stride + stride) % stride;
+            if (i >= 0) {
+                float x2 = x[i + stride];
+                for (; i >= 0; i -= stride) {
+                    const float x1 = x[i];
+                    x[i + stride] = c * x2 + s * x1;
+                    x2 = c * x1 - s * x2;
+                }
+                x[i + stride] = x2;
             }
         }
     }

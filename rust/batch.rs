@@ -1,0 +1,105 @@
+//! `BatchDecoder`: safe wrapper over the C ABI of `libopus_b200.so` (include/opus_b200.h).
+//!
+//! REVIEW-ONLY in this repository: the build image has no `cargo`/`rustc`, so this file is not compiled here.
+//! It is the file a maintainer of the `opus-codec` crate would add as `src/batch.rs` (next to `src/decoder.rs`),
+//! with the `extern "C"` block below added beside the bindgen output in `src/bindings.rs`.
+//! It reuses the crate's own `Error`, `Result`, `Channels` and `SampleRate` types (src/error.rs, src/types.rs).
+
+use crate::error::{Error, Result};
+use crate::types::{Channels, SampleRate};
+use std::ptr::NonNull;
+
+#[repr(C)]
+pub struct ObDecoder {
+    _unused: [u8; 0],
+}
+
+unsafe extern "C" {
+    pub fn ob_decoder_create(n_streams: i32, fs: i32, channels: i32, device: i32, max_frames: i32, error: *mut i32) -> *mut ObDecoder;
+    pub fn ob_decoder_destroy(dec: *mut ObDecoder);
+    pub fn ob_decode_float(dec: *mut ObDecoder, packets: *const u8, offsets: *const i32, lens: *const i32,
+                           pcm_out: *mut f32, frame_size: i32, samples_out: *mut i32) -> i32;
+    pub fn ob_decode_float_multi(dec: *mut ObDecoder, n_frames: i32, packets: *const u8, offsets: *const i32, lens: *const i32,
+                                 pcm_out: *mut f32, frame_size: i32, samples_out: *mut i32, ranges_out: *mut u32) -> i32;
+    pub fn ob_decoder_final_range(dec: *mut ObDecoder, out: *mut u32) -> i32;
+    pub fn ob_decoder_reset(dec: *mut ObDecoder, idx: *const i32, n: i32) -> i32;
+    pub fn ob_decoder_last_packet_duration(dec: *mut ObDecoder, out: *mut i32) -> i32;
+}
+
+/// `n_streams` independent CELT-only Opus decoders living on one B200.
+/// Mirrors `Decoder` (src/decoder.rs:18-28): owns the raw handle, frees it in `Drop`, all methods take `&mut self`.
+pub struct BatchDecoder {
+    raw: NonNull<ObDecoder>,
+    n_streams: usize,
+    channels: Channels,
+}
+
+unsafe impl Send for BatchDecoder {}
+
+impl BatchDecoder {
+    /// Cf. `Decoder::new` (src/decoder.rs:35-63). Only `SampleRate::Hz48000` is supported by the CUDA path.
+    pub fn new(n_streams: usize, sample_rate: SampleRate, channels: Channels, device: i32, max_frames: usize) -> Result<Self> {
+        let mut err = 0i32;
+        let raw = unsafe {
+            ob_decoder_create(n_streams as i32, sample_rate as i32, channels as i32, device, max_frames as i32, &mut err)
+        };
+        match NonNull::new(raw) {
+            Some(raw) if err == 0 => Ok(Self { raw, n_streams, channels }),
+            _ => Err(Error::from_code(err)),
+        }
+    }
+
+    /// One packet per stream. `packets[s]` may be empty (lost packet: `Error::Unimplemented` for that stream in this version).
+    /// `output` is `n_streams * frame_size * channels` interleaved floats; `frame_size = output.len() / n_streams / channels`
+    /// exactly like `Decoder::decode_float` derives it (src/decoder.rs:149).
+    /// Returns per-stream `Ok(samples_per_channel)` / `Err(code)`.
+    pub fn decode_float(&mut self, packets: &[&[u8]], output: &mut [f32]) -> Result<Vec<Result<usize>>> {
+        if packets.len() != self.n_streams || output.len() % (self.n_streams * self.channels as usize) != 0 {
+            return Err(Error::BadArg);
+        }
+        let frame_size = output.len() / self.n_streams / self.channels as usize;
+        let mut flat = Vec::with_capacity(packets.iter().map(|p| p.len()).sum());
+        let (mut offsets, mut lens) = (Vec::with_capacity(self.n_streams), Vec::with_capacity(self.n_streams));
+        for p in packets {
+            offsets.push(flat.len() as i32);
+            lens.push(p.len() as i32);
+            flat.extend_from_slice(p);
+        }
+        if flat.is_empty() {
+            flat.push(0);
+        }
+        let mut samples = vec![0i32; self.n_streams];
+        let rc = unsafe {
+            ob_decode_float(self.raw.as_ptr(), flat.as_ptr(), offsets.as_ptr(), lens.as_ptr(), output.as_mut_ptr(),
+                            frame_size as i32, samples.as_mut_ptr())
+        };
+        if rc != 0 {
+            return Err(Error::from_code(rc));
+        }
+        Ok(samples.into_iter().map(|n| if n >= 0 { Ok(n as usize) } else { Err(Error::from_code(n)) }).collect())
+    }
+
+    /// Cf. `Decoder::final_range` (src/decoder.rs:302-312), for every stream.
+    pub fn final_range(&mut self) -> Result<Vec<u32>> {
+        let mut out = vec![0u32; self.n_streams];
+        let rc = unsafe { ob_decoder_final_range(self.raw.as_ptr(), out.as_mut_ptr()) };
+        if rc != 0 { Err(Error::from_code(rc)) } else { Ok(out) }
+    }
+
+    /// Cf. `Decoder::reset` (src/decoder.rs:376-386); `None` resets every stream.
+    pub fn reset(&mut self, streams: Option<&[i32]>) -> Result<()> {
+        let rc = unsafe {
+            match streams {
+                Some(s) => ob_decoder_reset(self.raw.as_ptr(), s.as_ptr(), s.len() as i32),
+                None => ob_decoder_reset(self.raw.as_ptr(), std::ptr::null(), 0),
+            }
+        };
+        if rc != 0 { Err(Error::from_code(rc)) } else { Ok(()) }
+    }
+}
+
+impl Drop for BatchDecoder {
+    fn drop(&mut self) {
+        unsafe { ob_decoder_destroy(self.raw.as_ptr()) }
+    }
+}

@@ -117,10 +117,10 @@ def test_reset_restarts_streams():
     S, F, stride = g["packets"].shape
     F = 12
     with BatchDecoder(S, 48000, 1, device=0, max_frames=F) as dec:
-        a, _, _ = dec.decode_float_multi(g["packets"][:, :F].reshape(-1), _offsets(S, g["packets"].shape[1], stride)[:, :F], g["lens"][:, :F], 960)
+        a, _, _ = dec.decode_float_multi(g["packets"].reshape(-1), _offsets(S, g["packets"].shape[1], stride)[:, :F], g["lens"][:, :F], 960)
         a = a.copy()
         dec.reset([0, 2])
-        b, _, rb = dec.decode_float_multi(g["packets"][:, :F].reshape(-1), _offsets(S, g["packets"].shape[1], stride)[:, :F], g["lens"][:, :F], 960)
+        b, _, rb = dec.decode_float_multi(g["packets"].reshape(-1), _offsets(S, g["packets"].shape[1], stride)[:, :F], g["lens"][:, :F], 960)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])      # reset streams replay identically
     assert not np.array_equal(a[1], b[1])                                   # the others carried their state on
     assert (rb == g["dec_rng"][:, :F]).all()                               # final range never depends on state
