@@ -36,14 +36,35 @@ OB_DEV ObLcg ob_lcg_pow(uint32_t k)
     return r;
 }
 
-// haar1 (bands.c:632-645): N0*stride/2 independent butterflies.
+// Exact t / d for 0 <= t, d < 2^16 with one multiply: magic = floor(2^32 / d) + 1 (d >= 2).
+struct ObDiv { uint32_t d, magic; };
+OB_DEV ObDiv ob_div_make(int d) { ObDiv r; r.d = (uint32_t)d; r.magic = d > 1 ? 0xFFFFFFFFu / (uint32_t)d + 1u : 0u; return r; }
+OB_DEV int ob_div(int t, const ObDiv &dv)
+{
+    if (dv.d <= 1) return t;
+#ifdef __CUDACC__
+    return (int)__umulhi((uint32_t)t, dv.magic);
+#else
+    return (int)(((uint64_t)(uint32_t)t * dv.magic) >> 32);
+#endif
+}
+OB_DEV int ob_log2i(int v) { return 31 - OB_CLZ((uint32_t)v); }
+#ifdef __CUDACC__
+#define OB_RSQRTF(x) rsqrtf(x)
+#define OB_COSF(x) cosf(x)
+#else
+#define OB_RSQRTF(x) (1.f / sqrtf(x))
+#define OB_COSF(x) ((float)cos((double)(x)))
+#endif
+
+// haar1 (bands.c:632-645): N0*stride/2 independent butterflies.  stride is always a power of two here.
 template <class G>
 OB_DEV void ob_haar1(const G &g, float *X, int N0, int stride)
 {
     N0 >>= 1;
-    const int total = N0 * stride;
+    const int total = N0 * stride, ls = ob_log2i(stride);
     for (int t = g.lane; t < total; t += g.n) {
-        const int i = t % stride, j = t / stride;
+        const int i = t & (stride - 1), j = t >> ls;
         const float t1 = .70710678f * X[stride * 2 * j + i], t2 = .70710678f * X[stride * (2 * j + 1) + i];
         X[stride * 2 * j + i] = t1 + t2;
         X[stride * (2 * j + 1) + i] = t1 - t2;
@@ -67,8 +88,9 @@ template <class G>
 OB_DEV void ob_hadamard(const G &g, float *X, float *tmp, int N0, int stride, int hadamard, int interleave)
 {
     const int N = N0 * stride;
+    const ObDiv dv = ob_div_make(N0);
     for (int t = g.lane; t < N; t += g.n) {
-        const int i = t / N0, j = t % N0;                 // i: block, j: position inside block
+        const int i = ob_div(t, dv), j = t - i * N0;      // i: block, j: position inside block
         const int row = hadamard ? ob_ordery(stride, i) : i;
         if (interleave) tmp[j * stride + i] = X[row * N0 + j];
         else tmp[row * N0 + j] = X[j * stride + i];
@@ -80,10 +102,54 @@ OB_DEV void ob_hadamard(const G &g, float *X, float *tmp, int N0, int stride, in
 
 // exp_rotation(dir=-1) (vq.c:74-117).  Each (block, residue-class) chain of exp_rotation1 is an independent
 // serial recurrence; chains are spread over the lanes.
+#ifdef __CUDACC__
+// One exp_rotation1 sweep over a single chain as a first-order linear recurrence, evaluated with a warp scan:
+//   u_0 = a_0, u_t = s*u_{t-1} + c*a_t;  out_t = c*u_t - s*a_{t+1} (t <= L-2), out_{L-1} = u_{L-1}
+// (the forward loop of vq.c:56-63; the backward loop :64-71 is the same recurrence on the reversed array with -s).
+// elem(t) = x[rev ? L-1-t : t].
+__device__ __forceinline__ void ob_rot_scan(float *x, int L, float c, float s, int rev)
+{
+    const int lane = (int)(threadIdx.x & 31);
+    const float s2 = s * s, s4 = s2 * s2, s8 = s4 * s4, s16 = s8 * s8;
+    float slane = s;                                   // s^(lane+1)
+    if (lane & 1) slane *= s;
+    if (lane & 2) slane *= s2;
+    if (lane & 4) slane *= s4;
+    if (lane & 8) slane *= s8;
+    if (lane & 16) slane *= s16;
+    float carry = 0.f;
+    for (int base = 0; base < L; base += 32) {
+        const int t = base + lane;
+        const bool valid = t < L;
+        const float a = valid ? x[rev ? L - 1 - t : t] : 0.f;
+        const float an = (t + 1 < L) ? x[rev ? L - 2 - t : t + 1] : 0.f;
+        float y = (t == 0) ? a : c * a;
+        float p;
+        p = __shfl_up_sync(0xffffffffu, y, 1); if (lane >= 1) y += s * p;
+        p = __shfl_up_sync(0xffffffffu, y, 2); if (lane >= 2) y += s2 * p;
+        p = __shfl_up_sync(0xffffffffu, y, 4); if (lane >= 4) y += s4 * p;
+        p = __shfl_up_sync(0xffffffffu, y, 8); if (lane >= 8) y += s8 * p;
+        p = __shfl_up_sync(0xffffffffu, y, 16); if (lane >= 16) y += s16 * p;
+        y += slane * carry;
+        carry = __shfl_sync(0xffffffffu, y, 31);
+        __syncwarp();
+        if (valid) x[rev ? L - 1 - t : t] = (t + 1 < L) ? c * y - s * an : y;
+        __syncwarp();
+    }
+}
+#endif
+
 template <class G>
 OB_DEV void ob_rot_pass(const G &g, float *X, int nblocks, int len, int stride, float c, float s)
 {
     const int chains = nblocks * stride;
+#ifdef __CUDACC__
+    if (G::n == 32 && chains == 1 && len >= 12) {
+        ob_rot_scan(X, len, c, s, 0);                  // forward sweep i = 0 .. len-2
+        ob_rot_scan(X, len - 1, c, -s, 1);             // backward sweep i = len-3 .. 0 (x[len-1] untouched)
+        return;
+    }
+#endif
     for (int t = g.lane; t < chains; t += g.n) {
         float *x = X + (t / stride) * len;
         const int r = t % stride;
@@ -123,8 +189,8 @@ OB_DEV void ob_exp_rotation_inv(const G &g, float *X, int len, int stride, int K
     const int factor = spread == 1 ? 15 : spread == 2 ? 10 : 5;
     const float gain = (float)(1.0f * len) / (float)(len + factor * K);
     const float theta = .5f * (gain * gain);
-    const float c = (float)cos((double)((.5f * 3.141592653f) * theta));
-    const float s = (float)cos((double)((.5f * 3.141592653f) * (1.0f - theta)));
+    const float c = OB_COSF((.5f * 3.141592653f) * theta);
+    const float s = OB_COSF((.5f * 3.141592653f) * (1.0f - theta));
     int stride2 = 0;
     if (len >= 8 * stride) {
         stride2 = 1;
@@ -135,19 +201,30 @@ OB_DEV void ob_exp_rotation_inv(const G &g, float *X, int len, int stride, int K
     ob_rot_pass(g, X, stride, len, 1, c, s);
 }
 
-// Fills one terminal partition of X (bands.c:1038-1103).  lowband: folding source aligned with the band start.
+// Per-warp shared-memory working set of the band-reconstruction stage.
+struct ObBandsShared {
+    float xb[2 * OB_MAX_BAND];          // current band: channel 0 at [0,176), channel 1 at [176,352)
+    float norm[2 * OB_NORM_LEN];        // folding source per channel (bands.c:1438)
+    float scratch[OB_MAX_BAND];         // transformed copy of the folding source (lowband_scratch)
+    float tmp[OB_MAX_BAND];             // Hadamard permutation buffer
+    ObLeaf leaves[32];                  // leaves of the current band (<= 16 per quant_band call, two calls)
+    ObBand bands[OB_NB];
+};
+
+// Fills one terminal partition (bands.c:1038-1103).  X already holds (float)iy for PULSES leaves.
+// lowband: folding source aligned with the band start.
 template <class G>
-OB_DEV void ob_fill_leaf(const G &g, const ObLeaf &lf, const int16_t *iy, float *Xb, int off_in_band, const float *lowband,
-        uint32_t seed_in, int spread)
+OB_DEV void ob_fill_leaf(const G &g, const ObLeaf &lf, float *Xb, int off_in_band, const float *lowband,
+        uint32_t seed_in, const ObLcg &step, int spread)
 {
     float *X = Xb + off_in_band;
     const int n = lf.n;
     if (lf.kind == OB_LEAF_PULSES) {
-        uint32_t ryy = 0;
-        for (int j = g.lane; j < n; j += g.n) { const int v = iy[j]; ryy += (uint32_t)(v * v); }
-        ryy = g.sum_u32(ryy);
-        const float gg = (1.f / OB_SQRTF((float)ryy)) * lf.gain;            // normalise_residual (vq.c:121-141)
-        for (int j = g.lane; j < n; j += g.n) X[j] = gg * (float)iy[j];
+        float ryy = 0.f;                                                   // exact: sum of squares of small integers
+        for (int j = g.lane; j < n; j += g.n) ryy += X[j] * X[j];
+        ryy = g.sum(ryy);
+        const float gg = OB_RSQRTF(ryy) * lf.gain;                         // normalise_residual (vq.c:121-141)
+        for (int j = g.lane; j < n; j += g.n) X[j] = gg * X[j];
         g.sync();
         ob_exp_rotation_inv(g, X, n, lf.B, lf.K, spread);
     } else if (lf.kind == OB_LEAF_ZERO) {
@@ -159,7 +236,6 @@ OB_DEV void ob_fill_leaf(const G &g, const ObLeaf &lf, const int16_t *iy, float 
     } else {
         // noise / folded spectrum + renormalise (bands.c:1070-1098)
         const ObLcg first = ob_lcg_pow((uint32_t)lf.lcg_before + (uint32_t)g.lane + 1u);
-        const ObLcg step = ob_lcg_pow((uint32_t)g.n);
         uint32_t seed = first.a * seed_in + first.c;
         float e = 0.f;
         for (int j = g.lane; j < n; j += g.n) {
@@ -171,22 +247,23 @@ OB_DEV void ob_fill_leaf(const G &g, const ObLeaf &lf, const int16_t *iy, float 
             seed = step.a * seed + step.c;
         }
         e = 1e-15f + g.sum(e);
-        const float gg = (1.f / OB_SQRTF(e)) * lf.gain;                     // renormalise_vector (vq.c:383-407)
+        const float gg = OB_RSQRTF(e) * lf.gain;                           // renormalise_vector (vq.c:383-407)
         for (int j = g.lane; j < n; j += g.n) X[j] = gg * X[j];
         g.sync();
     }
 }
 
-// quant_band, resynthesis side (bands.c:1109-1231).  Xb: band buffer; lowband: source in norm[] or nullptr;
-// lowband_out: destination in norm[] or nullptr; scratch/tmp: >= 176 floats each.
+// quant_band, resynthesis side (bands.c:1109-1231).  Xb: band buffer of this channel (already holding (float)iy);
+// leaves: staged leaf records [0, leaf_cnt); lowband: source in norm[] or nullptr; lowband_out: destination in norm[] or nullptr.
 template <class G>
-OB_DEV void ob_band_call(const G &g, const ObFrameIR *ir, int leaf_begin, int leaf_cnt, int band_off_abs, float *Xb, int N, int B,
-        int tf_change, const float *lowband, float *lowband_out, float *scratch, float *tmp, uint32_t seed_in, int spread)
+OB_DEV void ob_band_call(const G &g, ObBandsShared &sh, const ObLeaf *leaves, int leaf_cnt, int band_off_abs, float *Xb, int N, int B,
+        int tf_change, const float *lowband, float *lowband_out, uint32_t seed_in, const ObLcg &step, int spread)
 {
     const int N0 = N, longBlocks = B == 1;
     int N_B = N / B, time_divide = 0, recombine = 0;
+    float *scratch = sh.scratch, *tmp = sh.tmp;
     if (N == 1) {
-        ob_fill_leaf(g, ir->leaves[leaf_begin], ir->iy, Xb, 0, nullptr, seed_in, spread);
+        ob_fill_leaf(g, leaves[0], Xb, 0, nullptr, seed_in, step, spread);
         if (lowband_out && g.lane == 0) lowband_out[0] = Xb[0];
         g.sync();
         return;
@@ -212,8 +289,8 @@ OB_DEV void ob_band_call(const G &g, const ObFrameIR *ir, int leaf_begin, int le
     if (B0 > 1 && lb) ob_hadamard(g, lb, tmp, N_B >> recombine, B0 << recombine, longBlocks, 0);
 
     for (int l = 0; l < leaf_cnt; l++) {
-        const ObLeaf lf = ir->leaves[leaf_begin + l];
-        ob_fill_leaf(g, lf, ir->iy + lf.off, Xb, (int)lf.off - band_off_abs, lb, seed_in, spread);
+        const ObLeaf lf = leaves[l];
+        ob_fill_leaf(g, lf, Xb, (int)lf.off - band_off_abs, lb, seed_in, step, spread);
     }
 
     if (B0 > 1) ob_hadamard(g, Xb, tmp, N_B >> recombine, B0 << recombine, longBlocks, 1);
@@ -241,7 +318,7 @@ OB_DEV void ob_stereo_merge(const G &g, float *X, float *Y, float mid, int N)
         g.sync();
         return;
     }
-    const float lgain = 1.f / OB_SQRTF(El), rgain = 1.f / OB_SQRTF(Er);
+    const float lgain = OB_RSQRTF(El), rgain = OB_RSQRTF(Er);
     for (int j = g.lane; j < N; j += g.n) {
         const float l = mid * X[j], r = Y[j];
         X[j] = lgain * (l - r);
@@ -250,43 +327,60 @@ OB_DEV void ob_stereo_merge(const G &g, float *X, float *Y, float mid, int N)
     g.sync();
 }
 
-// Reconstructs X (C*N floats, channel c at c*N) for one frame.  norm: 2*OB_NORM_LEN floats, scratch/tmp: 176 each.
-// seed_in: the stream's range-coder state left by the previous frame (celt_decoder.c:1275 passes &st->rng).
+// Reconstructs the normalised spectrum of one frame band by band and writes it to Xout (C*N floats, channel c at
+// c*N; coefficients of bands >= end are NOT written).  seed_in: the stream's range-coder state left by the previous
+// frame (celt_decoder.c:1275 passes &st->rng).
 template <class G>
-OB_DEV void ob_reconstruct_bands(const G &g, const ObFrameIR *ir, uint32_t seed_in, float *X, float *norm, float *scratch, float *tmp)
+OB_DEV void ob_reconstruct_bands(const G &g, const ObFrameIR *ir, uint32_t seed_in, ObBandsShared &sh, float *Xout)
 {
     const ObFrameHdr &h = ir->hdr;
     const int LM = h.LM, M = 1 << LM, C = h.C, N = OB_SHORT << LM, end = h.end;
     const int Bfr = (h.flags & OB_F_TRANSIENT) ? M : 1, spread = h.spread;
-    float *norm2 = norm + OB_NORM_LEN;
-    for (int j = g.lane; j < C * N; j += g.n) X[j] = 0.f;
+    const ObLcg step = ob_lcg_pow((uint32_t)g.n);
+    float *norm = sh.norm, *norm2 = sh.norm + OB_NORM_LEN;
+    float *Xb = sh.xb, *Yb = sh.xb + OB_MAX_BAND;
+    {   // band records -> shared (16-byte records as 4 words each)
+        const uint32_t *src = (const uint32_t *)ir->bands;
+        uint32_t *dst = (uint32_t *)sh.bands;
+        for (int j = g.lane; j < (int)(sizeof(ObBand) / 4) * OB_NB; j += g.n) dst[j] = src[j];
+    }
     g.sync();
     for (int i = 0; i < end; i++) {
-        const ObBand br = ir->bands[i];
+        const ObBand br = sh.bands[i];
         const int boff = M * OB_EBANDS[i], Nb = M * (OB_EBANDS[i + 1] - OB_EBANDS[i]);
         const int last = i == end - 1, tf_change = h.tf_change[i];
-        float *Xb = X + boff, *Yb = X + N + boff;
+        const int na = br.leaf_cnt_a, nb = br.leaf_cnt_b;
+        {   // stage this band's leaves (12-byte records as 3 words each) and its pulse vector (as float)
+            const uint32_t *sa = (const uint32_t *)(ir->leaves + br.leaf_begin_a), *sb = (const uint32_t *)(ir->leaves + br.leaf_begin_b);
+            uint32_t *dst = (uint32_t *)sh.leaves;
+            for (int j = g.lane; j < 3 * na; j += g.n) dst[j] = sa[j];
+            for (int j = g.lane; j < 3 * nb; j += g.n) dst[3 * na + j] = sb[j];
+            const int16_t *iy = ir->iy + boff;
+            for (int j = g.lane; j < Nb; j += g.n) Xb[j] = (float)iy[j];
+            if (C == 2) for (int j = g.lane; j < Nb; j += g.n) Yb[j] = (float)iy[N + j];
+        }
         if (br.flags & 8) {                                          // leaving dual stereo (bands.c:1551-1558)
             for (int j = g.lane; j < boff; j += g.n) norm[j] = .5f * (norm[j] + norm2[j]);
-            g.sync();
         }
+        g.sync();
+        const ObLeaf *la = sh.leaves, *lbv = sh.leaves + na;
         const float *lb1 = br.eff_lowband >= 0 ? norm + br.eff_lowband : nullptr;
         const float *lb2 = br.eff_lowband >= 0 ? norm2 + br.eff_lowband : nullptr;
         float *lo1 = last ? nullptr : norm + boff, *lo2 = last ? nullptr : norm2 + boff;
         if (br.mode == OB_BAND_MONO) {
-            ob_band_call(g, ir, br.leaf_begin_a, br.leaf_cnt_a, boff, Xb, Nb, Bfr, tf_change, lb1, lo1, scratch, tmp, seed_in, spread);
+            ob_band_call(g, sh, la, na, boff, Xb, Nb, Bfr, tf_change, lb1, lo1, seed_in, step, spread);
         } else if (br.mode == OB_BAND_DUAL) {
-            ob_band_call(g, ir, br.leaf_begin_a, br.leaf_cnt_a, boff, Xb, Nb, Bfr, tf_change, lb1, lo1, scratch, tmp, seed_in, spread);
-            ob_band_call(g, ir, br.leaf_begin_b, br.leaf_cnt_b, N + boff, Yb, Nb, Bfr, tf_change, lb2, lo2, scratch, tmp, seed_in, spread);
+            ob_band_call(g, sh, la, na, boff, Xb, Nb, Bfr, tf_change, lb1, lo1, seed_in, step, spread);
+            ob_band_call(g, sh, lbv, nb, N + boff, Yb, Nb, Bfr, tf_change, lb2, lo2, seed_in, step, spread);
         } else if (Nb == 1) {                                        // quant_band_n1 with Y (bands.c:904-937)
-            ob_fill_leaf(g, ir->leaves[br.leaf_begin_a], ir->iy, Xb, 0, nullptr, seed_in, spread);
-            ob_fill_leaf(g, ir->leaves[br.leaf_begin_a + 1], ir->iy, Yb, 0, nullptr, seed_in, spread);
+            ob_fill_leaf(g, la[0], Xb, 0, nullptr, seed_in, step, spread);
+            ob_fill_leaf(g, la[1], Yb, 0, nullptr, seed_in, step, spread);
             if (lo1 && g.lane == 0) lo1[0] = Xb[0];
             g.sync();
         } else if (br.mode == OB_BAND_JOINT_N2) {                    // bands.c:1273-1323
             const int c = (br.flags >> 1) & 1, sign = 1 - 2 * ((br.flags >> 2) & 1);
             float *x2 = c ? Yb : Xb, *y2 = c ? Xb : Yb;
-            ob_band_call(g, ir, br.leaf_begin_a, br.leaf_cnt_a, c ? N + boff : boff, x2, Nb, Bfr, tf_change, lb1, lo1, scratch, tmp, seed_in, spread);
+            ob_band_call(g, sh, la, na, c ? N + boff : boff, x2, Nb, Bfr, tf_change, lb1, lo1, seed_in, step, spread);
             if (g.lane == 0) {
                 const float mid = (1.f / 32768) * br.imid, side = (1.f / 32768) * br.iside;
                 y2[0] = -sign * x2[1];
@@ -300,13 +394,16 @@ OB_DEV void ob_reconstruct_bands(const G &g, const ObFrameIR *ir, uint32_t seed_
             g.sync();
         } else {                                                     // joint stereo, N > 2 (bands.c:1324-1381)
             const float mid = (1.f / 32768) * br.imid;
-            ob_band_call(g, ir, br.leaf_begin_a, br.leaf_cnt_a, boff, Xb, Nb, Bfr, tf_change, lb1, lo1, scratch, tmp, seed_in, spread);
-            ob_band_call(g, ir, br.leaf_begin_b, br.leaf_cnt_b, N + boff, Yb, Nb, Bfr, tf_change, nullptr, nullptr, scratch, tmp, seed_in, spread);
+            ob_band_call(g, sh, la, na, boff, Xb, Nb, Bfr, tf_change, lb1, lo1, seed_in, step, spread);
+            ob_band_call(g, sh, lbv, nb, N + boff, Yb, Nb, Bfr, tf_change, nullptr, nullptr, seed_in, step, spread);
             ob_stereo_merge(g, Xb, Yb, mid, Nb);
             if (br.flags & 1) {
                 for (int j = g.lane; j < Nb; j += g.n) Yb[j] = -Yb[j];
                 g.sync();
             }
         }
+        for (int j = g.lane; j < Nb; j += g.n) Xout[boff + j] = Xb[j];
+        if (C == 2) for (int j = g.lane; j < Nb; j += g.n) Xout[N + boff + j] = Yb[j];
+        g.sync();
     }
 }

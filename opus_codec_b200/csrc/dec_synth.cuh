@@ -40,8 +40,10 @@ OB_DEV void ob_fft_stage(const G &g, float *base, int nblk, int blk_stride, int 
     if (p == 2) {                                                   // kf_bfly2, m == 4 (kiss_fft.c:48-100)
         const float tw = 0.7071067812f;
         const int per = Nst * 4, total = nblk * per;
+        const ObDiv dper = ob_div_make(per);
         for (int t = g.lane; t < total; t += g.n) {
-            ObCpx *F = (ObCpx *)(base + (t / per) * blk_stride) + ((t % per) >> 2) * 8;
+            const int blk = nblk > 1 ? ob_div(t, dper) : 0;
+            ObCpx *F = (ObCpx *)(base + blk * blk_stride) + ((t - blk * per) >> 2) * 8;
             const int k = t & 3;
             ObCpx *F2 = F + 4, x = F2[k], tt;
             if (k == 0) tt = x;
@@ -52,10 +54,12 @@ OB_DEV void ob_fft_stage(const G &g, float *base, int nblk, int blk_stride, int 
             F[k].r += tt.r; F[k].i += tt.i;
         }
     } else if (p == 4) {                                            // kf_bfly4 (kiss_fft.c:102-171)
-        const int per = Nst * m, total = nblk * per;
+        const int per = Nst * m, total = nblk * per, lm = ob_log2i(m);       // m is a power of two in radix-4 stages
+        const ObDiv dper = ob_div_make(per);
         for (int t = g.lane; t < total; t += g.n) {
-            const int w = t % per, i = w / m, j = w % m;
-            ObCpx *F = (ObCpx *)(base + (t / per) * blk_stride) + i * mm + j;
+            const int blk = nblk > 1 ? ob_div(t, dper) : 0;
+            const int w = t - blk * per, i = w >> lm, j = w & (m - 1);
+            ObCpx *F = (ObCpx *)(base + blk * blk_stride) + i * mm + j;
             ObCpx s0, s1, s2, s3, s4, s5;
             if (m == 1) { s0 = F[1]; s1 = F[2]; s2 = F[3]; }
             else { OB_CMUL(s0, F[m], OB_TW(j * fstride)); OB_CMUL(s1, F[2 * m], OB_TW(j * fstride * 2)); OB_CMUL(s2, F[3 * m], OB_TW(j * fstride * 3)); }
@@ -69,11 +73,13 @@ OB_DEV void ob_fft_stage(const G &g, float *base, int nblk, int blk_stride, int 
             F[3 * m].r = s5.r - s4.i; F[3 * m].i = s5.i + s4.r;
         }
     } else if (p == 3) {                                            // kf_bfly3 (kiss_fft.c:176-236)
-        const int per = Nst * m, total = nblk * per;
+        const int per = Nst * m, total = nblk * per, lm = ob_log2i(m);       // m is a power of two in radix-3 stages
+        const ObDiv dper = ob_div_make(per);
         const float epi3i = OB_TW(fstride * m).i;
         for (int t = g.lane; t < total; t += g.n) {
-            const int w = t % per, i = w / m, j = w % m;
-            ObCpx *F = (ObCpx *)(base + (t / per) * blk_stride) + i * mm + j;
+            const int blk = nblk > 1 ? ob_div(t, dper) : 0;
+            const int w = t - blk * per, i = w >> lm, j = w & (m - 1);
+            ObCpx *F = (ObCpx *)(base + blk * blk_stride) + i * mm + j;
             ObCpx s0, s1, s2, s3;
             OB_CMUL(s1, F[m], OB_TW(j * fstride)); OB_CMUL(s2, F[2 * m], OB_TW(j * fstride * 2));
             s3.r = s1.r + s2.r; s3.i = s1.i + s2.i;
@@ -85,11 +91,13 @@ OB_DEV void ob_fft_stage(const G &g, float *base, int nblk, int blk_stride, int 
             F[m].r = F[m].r - s0.i; F[m].i = F[m].i + s0.r;
         }
     } else {                                                        // kf_bfly5 (kiss_fft.c:240-308)
-        const int per = Nst * m, total = nblk * per;
+        const int per = Nst * m, total = nblk * per;                          // radix-5 is always the last stage: Nst == 1
+        const ObDiv dper = ob_div_make(per);
         const ObCpx ya = OB_TW(fstride * m), yb = OB_TW(fstride * 2 * m);
         for (int t = g.lane; t < total; t += g.n) {
-            const int w = t % per, i = w / m, u = w % m;
-            ObCpx *F0 = (ObCpx *)(base + (t / per) * blk_stride) + i * mm + u;
+            const int blk = nblk > 1 ? ob_div(t, dper) : 0;
+            const int i = 0, u = t - blk * per;
+            ObCpx *F0 = (ObCpx *)(base + blk * blk_stride) + i * mm + u;
             ObCpx *F1 = F0 + m, *F2 = F0 + 2 * m, *F3 = F0 + 3 * m, *F4 = F0 + 4 * m;
             ObCpx s0, s1, s2, s3, s4, s5, s6, s7, s8, s9, s10, s11, s12;
             s0 = *F0;
@@ -118,8 +126,9 @@ OB_DEV void ob_imdct(const G &g, const float *in, float *out, int shift, int nbl
     const int N2 = 1920 >> (shift + 1), N4 = N2 >> 1;
     const float *trig = OB_MDCT_TRIG + (shift == 0 ? 0 : shift == 1 ? 960 : shift == 2 ? 1440 : 1680);
     const int16_t *br = ob_fft_bitrev(shift);
+    const ObDiv dN4 = ob_div_make(N4);
     for (int t = g.lane; t < nblk * N4; t += g.n) {                  // pre-rotation into bit-reversed order
-        const int b = t / N4, i = t % N4;
+        const int b = nblk > 1 ? ob_div(t, dN4) : 0, i = t - b * N4;
         const float x1 = in[b + nblk * (2 * i)], x2 = in[b + nblk * (N2 - 1 - 2 * i)];
         float *yp = out + b * N2 + (OB_OVERLAP >> 1);
         const int rev = br[i];
@@ -140,8 +149,9 @@ OB_DEV void ob_imdct(const G &g, const float *in, float *out, int shift, int nbl
         }
     }
     const int half = (N4 + 1) >> 1;
+    const ObDiv dhalf = ob_div_make(half);
     for (int t = g.lane; t < nblk * half; t += g.n) {                // post-rotation, both ends at once
-        const int b = t / half, i = t % half;
+        const int b = nblk > 1 ? ob_div(t, dhalf) : 0, i = t - b * half;
         float *yp0 = out + b * N2 + (OB_OVERLAP >> 1) + 2 * i, *yp1 = out + b * N2 + (OB_OVERLAP >> 1) + N2 - 2 - 2 * i;
         float re = yp0[1], im = yp0[0], t0 = trig[i], t1 = trig[N4 + i];
         const float yr0 = re * t0 + im * t1, yi0 = re * t1 - im * t0;
@@ -153,7 +163,7 @@ OB_DEV void ob_imdct(const G &g, const float *in, float *out, int shift, int nbl
     }
     g.sync();
     for (int t = g.lane; t < nblk * (OB_OVERLAP / 2); t += g.n) {    // TDAC mirror
-        const int b = t / (OB_OVERLAP / 2), i = t % (OB_OVERLAP / 2);
+        const int b = t / (OB_OVERLAP / 2), i = t - b * (OB_OVERLAP / 2);
         float *o = out + b * N2;
         const float x1 = o[OB_OVERLAP - 1 - i], x2 = o[i], w1 = OB_WINDOW[i], w2 = OB_WINDOW[OB_OVERLAP - 1 - i];
         o[i] = w2 * x2 - w1 * x1;
@@ -204,10 +214,25 @@ struct ObSynthShared {
     float scanA[256], scanB[256];
     float red[32];
     ObFrameHdr hdr;
+    uint32_t lcg_a[33], lcg_c[33];   // celt_lcg_rand^k as affine maps, k = 0..32 (anti-collapse noise, bands.c:335-340)
+    uint8_t band_of_bin[104];        // 2.5 ms bin -> band index (21 = above the last band)
     int32_t pf_period, pf_period_old, pf_tapset, pf_tapset_old;
     float pf_gain, pf_gain_old, preemph_mem[2];
     uint32_t rng;
 };
+
+// Once per block: lookup tables in shared memory.
+template <class G>
+OB_DEV void ob_synth_init(const G &g, ObSynthShared &sh)
+{
+    for (int k = g.lane; k < 33; k += g.n) { const ObLcg p = ob_lcg_pow((uint32_t)k); sh.lcg_a[k] = p.a; sh.lcg_c[k] = p.c; }
+    for (int b = g.lane; b < 104; b += g.n) {
+        int band = 0;
+        while (band < OB_NB && OB_EBANDS[band + 1] <= b) band++;
+        sh.band_of_bin[b] = (uint8_t)band;
+    }
+    g.sync();
+}
 
 // anti_collapse (bands.c:268-362) on the X tile.
 template <class G>
@@ -215,44 +240,40 @@ OB_DEV void ob_anti_collapse(const G &g, ObSynthShared &sh, float *X, int N, uin
 {
     const ObFrameHdr &h = sh.hdr;
     const int LM = h.LM, C = h.C, end = h.end;
-    uint32_t steps = 0;
+    uint32_t seed = seed0;                                           // uniform across lanes: state before the next block
     for (int i = 0; i < end; i++) {
-        const int N0 = OB_EBANDS[i + 1] - OB_EBANDS[i];
+        const int N0 = OB_EBANDS[i + 1] - OB_EBANDS[i];              // <= 22
         const int depth = (int)((uint32_t)(1 + h.pulses[i]) / (uint32_t)N0) >> LM;
-        const float thresh = .5f * (float)exp(0.6931471805599453094 * (double)(-.125f * depth));
+        const float thresh = .5f * exp2f(-.125f * (float)depth);
         const float sqrt_1 = 1.f / OB_SQRTF((float)(N0 << LM));
         for (int c = 0; c < C; c++) {
+            const int mask = h.collapse_masks[i * C + c];
+            if (mask == (1 << (1 << LM)) - 1) continue;
             float prev1 = sh.oldLogE[c * OB_NB + i], prev2 = sh.oldLogE2[c * OB_NB + i];
             if (C == 1) { prev1 = fmaxf(prev1, sh.oldLogE[OB_NB + i]); prev2 = fmaxf(prev2, sh.oldLogE2[OB_NB + i]); }
             float Ediff = sh.oldBandE[c * OB_NB + i] - fminf(prev1, prev2);
             Ediff = fmaxf(0.f, Ediff);
-            float r = 2.f * (float)exp(0.6931471805599453094 * (double)(-Ediff));
+            float r = 2.f * exp2f(-Ediff);
             if (LM == 3) r *= 1.41421356f;
             r = fminf(thresh, r);
             r = r * sqrt_1;
             float *Xb = X + c * N + (OB_EBANDS[i] << LM);
-            int renorm = 0;
             for (int k = 0; k < 1 << LM; k++) {
-                if (!(h.collapse_masks[i * C + c] & (1 << k))) {
-                    const ObLcg first = ob_lcg_pow(steps + (uint32_t)g.lane + 1u), step = ob_lcg_pow((uint32_t)g.n);
-                    uint32_t seed = first.a * seed0 + first.c;
+                if (!(mask & (1 << k))) {
                     for (int j = g.lane; j < N0; j += g.n) {
-                        Xb[(j << LM) + k] = (seed & 0x8000u) ? r : -r;
-                        seed = step.a * seed + step.c;
+                        const uint32_t sj = sh.lcg_a[j + 1] * seed + sh.lcg_c[j + 1];
+                        Xb[(j << LM) + k] = (sj & 0x8000u) ? r : -r;
                     }
-                    steps += (uint32_t)N0;
-                    renorm = 1;
+                    seed = sh.lcg_a[N0] * seed + sh.lcg_c[N0];
                 }
             }
-            if (renorm) {
-                g.sync();
-                float e = 0.f;
-                for (int j = g.lane; j < N0 << LM; j += g.n) e += Xb[j] * Xb[j];
-                e = 1e-15f + g.sum(e);
-                const float gg = 1.f / OB_SQRTF(e);
-                for (int j = g.lane; j < N0 << LM; j += g.n) Xb[j] = gg * Xb[j];
-                g.sync();
-            }
+            g.sync();
+            float e = 0.f;
+            for (int j = g.lane; j < N0 << LM; j += g.n) e += Xb[j] * Xb[j];
+            e = 1e-15f + g.sum(e);
+            const float gg = 1.f / OB_SQRTF(e);
+            for (int j = g.lane; j < N0 << LM; j += g.n) Xb[j] = gg * Xb[j];
+            g.sync();
         }
     }
 }
@@ -263,7 +284,11 @@ template <class G>
 OB_DEV int ob_synth_frame(const G &g, ObSynthShared &sh, const ObFrameIR *ir, const float *Xg, float *pcm, int CC)
 {
     // ---- header to shared memory ----
-    if (g.lane == 0) sh.hdr = ir->hdr;
+    {
+        const uint32_t *src = (const uint32_t *)&ir->hdr;
+        uint32_t *dst = (uint32_t *)&sh.hdr;
+        for (int j = g.lane; j < (int)(sizeof(ObFrameHdr) / 4); j += g.n) dst[j] = src[j];
+    }
     g.sync();
     const ObFrameHdr &h = sh.hdr;
     if (h.status <= 0) return h.status;
@@ -293,7 +318,11 @@ OB_DEV int ob_synth_frame(const G &g, ObSynthShared &sh, const ObFrameIR *ir, co
     g.sync();
 
     // ---- X tile: global -> shared, anti-collapse ----
-    for (int j = g.lane; j < C * N; j += g.n) sh.freq[j / N][j % N] = Xg[j];
+    {
+        const int bound = OB_EBANDS[end] << LM;                      // bands >= end were not written by the bands stage
+        for (int c = 0; c < C; c++)
+            for (int j = g.lane; j < N; j += g.n) sh.freq[c][j] = j < bound ? Xg[c * N + j] : 0.f;
+    }
     g.sync();
     if (h.flags & OB_F_ANTICOLLAPSE) {
         const ObLcg jump = ob_lcg_pow(h.lcg_total);
@@ -309,12 +338,11 @@ OB_DEV int ob_synth_frame(const G &g, ObSynthShared &sh, const ObFrameIR *ir, co
         sh.gain[t] = (i < end && !silence) ? (float)exp(0.6931471805599453094 * (double)(lg < 32.f ? lg : 32.f)) : 0.f;
     }
     g.sync();
-    for (int t = g.lane; t < C * N; t += g.n) {
-        const int c = t / N, j = t % N, bin = j >> LM;
-        int band = 0;
-        while (band < OB_NB && OB_EBANDS[band + 1] <= bin) band++;
-        sh.freq[c][j] = band < OB_NB ? sh.freq[c][j] * sh.gain[c * OB_NB + band] : 0.f;
-    }
+    for (int c = 0; c < C; c++)
+        for (int j = g.lane; j < N; j += g.n) {
+            const int bin = j >> LM, band = bin < 100 ? sh.band_of_bin[bin] : OB_NB;
+            sh.freq[c][j] = band < OB_NB ? sh.freq[c][j] * sh.gain[c * OB_NB + band] : 0.f;
+        }
     g.sync();
     if (CC == 2 && C == 1) { for (int j = g.lane; j < N; j += g.n) sh.freq[1][j] = sh.freq[0][j]; g.sync(); }
     if (CC == 1 && C == 2) { for (int j = g.lane; j < N; j += g.n) sh.freq[0][j] = .5f * sh.freq[0][j] + .5f * sh.freq[1][j]; g.sync(); }
@@ -392,7 +420,8 @@ OB_DEV int ob_synth_frame(const G &g, ObSynthShared &sh, const ObFrameIR *ir, co
             g.sync();
         }
         (void)cp;
-        for (int t = g.lane; t < N * CC; t += g.n) pcm[t] = sh.freq[t % CC][t / CC];
+        if (CC == 1) { for (int t = g.lane; t < N; t += g.n) pcm[t] = sh.freq[0][t]; }
+        else { for (int t = g.lane; t < 2 * N; t += g.n) pcm[t] = sh.freq[t & 1][t >> 1]; }
         g.sync();
     }
 

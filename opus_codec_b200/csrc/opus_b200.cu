@@ -34,12 +34,12 @@ ob_k_symbols(const uint8_t *__restrict__ packets, const int32_t *__restrict__ of
     ob_decode_symbols(len > 0 ? packets + offsets[t] : nullptr, len, dec_channels, max_frame, ir + t);
 }
 
-#define OB_BANDS_WARPS 4
-#define OB_BANDS_SMEM_PER_WARP ((2 * OB_MAX_N + 2 * OB_NORM_LEN + 2 * OB_MAX_BAND) * (int)sizeof(float))
+#define OB_BANDS_WARPS 6
+#define OB_BANDS_SMEM_PER_WARP ((int)sizeof(ObBandsShared))
 __global__ void __launch_bounds__(OB_BANDS_WARPS * 32)
 ob_k_bands(const ObFrameIR *__restrict__ ir, const ObDecState *__restrict__ st, float *__restrict__ Xg, int S, int F)
 {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int w = blockIdx.x * OB_BANDS_WARPS + warp;
     if (w >= S * F) return;
@@ -50,14 +50,9 @@ ob_k_bands(const ObFrameIR *__restrict__ ir, const ObDecState *__restrict__ st, 
     // seed = range-coder state left by the previous successfully decoded frame of this stream
     uint32_t seed = st[s].rng;
     for (int p = f - 1; p >= 0; p--) if (ir[w - (f - p)].hdr.status > 0) { seed = ir[w - (f - p)].hdr.final_range; break; }
-    float *X = smem + warp * (OB_BANDS_SMEM_PER_WARP / (int)sizeof(float));
-    float *norm = X + 2 * OB_MAX_N, *scratch = norm + 2 * OB_NORM_LEN, *tmp = scratch + OB_MAX_BAND;
+    ObBandsShared &sh = *reinterpret_cast<ObBandsShared *>(smem_raw + (size_t)warp * OB_BANDS_SMEM_PER_WARP);
     ObWarp g;
-    ob_reconstruct_bands(g, fr, seed, X, norm, scratch, tmp);
-    g.sync();
-    const int n = fr->hdr.C * status;
-    float *dst = Xg + (size_t)w * OB_X_STRIDE;
-    for (int j = g.lane; j < n; j += 32) dst[j] = X[j];
+    ob_reconstruct_bands(g, fr, seed, sh, Xg + (size_t)w * OB_X_STRIDE);
 }
 
 #define OB_SYNTH_THREADS 128
@@ -70,6 +65,7 @@ ob_k_synth(const ObFrameIR *__restrict__ ir, const float *__restrict__ Xg, ObDec
     if (s >= S) return;
     ObBlock g(sh.red);
     ObDecState *state = st + s;
+    ob_synth_init(g, sh);
     // ---- state: global -> shared ----
     for (int i = g.lane; i < 2 * OB_NB; i += g.n) {
         sh.oldBandE[i] = state->oldBandE[i]; sh.oldLogE[i] = state->oldLogE[i];
@@ -140,10 +136,13 @@ __global__ void ob_k_gather_state(const ObDecState *st, uint32_t *ranges, int32_
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+#ifndef OB_MAX_CHUNKS
+#define OB_MAX_CHUNKS 8
+#endif
 struct ObDecoder {
     int S, CC, device, max_frames;
-    cudaStream_t stream;
-    cudaEvent_t ev[4];
+    cudaStream_t stream, copy_stream, aux_stream;
+    cudaEvent_t ev[4], chunk_ev[OB_MAX_CHUNKS], copy_done, h2d_done;
     bool timed;
     ObDecState *d_state;
     float *d_hist;
@@ -158,23 +157,30 @@ struct ObDecoder {
 
 #define OB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "opus_b200: %s failed: %s\n", #x, cudaGetErrorString(e_)); return OB_INTERNAL_ERROR; } } while (0)
 
-static int ob_launch(ObDecoder *d, int F, const uint8_t *d_packets, const int32_t *d_offsets, const int32_t *d_lens,
-                     float *d_pcm, int frame_size, int32_t *d_samples, uint32_t *d_ranges)
+// Launches the three kernels for streams [s0, s0+Sc).  All per-stream arrays are indexed by stream, so a sub-range is
+// just a pointer offset; timed != 0 brackets the kernels with the handle's events.
+static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packets, const int32_t *d_offsets, const int32_t *d_lens,
+                     float *d_pcm, int frame_size, int32_t *d_samples, uint32_t *d_ranges, int timed, cudaStream_t stream)
 {
-    const int total = d->S * F;
-    OB_CUDA(cudaEventRecord(d->ev[0], d->stream));
-    ob_k_symbols<<<(total + OB_SYM_THREADS - 1) / OB_SYM_THREADS, OB_SYM_THREADS, 0, d->stream>>>(
-        d_packets, d_offsets, d_lens, d->d_ir, total, d->CC, frame_size);
-    OB_CUDA(cudaEventRecord(d->ev[1], d->stream));
-    ob_k_bands<<<(total + OB_BANDS_WARPS - 1) / OB_BANDS_WARPS, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, d->stream>>>(
-        d->d_ir, d->d_state, d->d_X, d->S, F);
-    OB_CUDA(cudaEventRecord(d->ev[2], d->stream));
-    ob_k_synth<<<d->S, OB_SYNTH_THREADS, 0, d->stream>>>(d->d_ir, d->d_X, d->d_state, d->d_hist, d_pcm, d_samples, d_ranges,
-                                                        d->S, F, d->CC, frame_size);
-    OB_CUDA(cudaEventRecord(d->ev[3], d->stream));
+    const int total = Sc * F;
+    const size_t w0 = (size_t)s0 * F;
+    ObFrameIR *ir = d->d_ir + w0;
+    float *X = d->d_X + w0 * OB_X_STRIDE;
+    ObDecState *st = d->d_state + s0;
+    float *hist = d->d_hist + (size_t)s0 * d->CC * OB_HIST_LEN;
+    if (timed) OB_CUDA(cudaEventRecord(d->ev[0], stream));
+    ob_k_symbols<<<(total + OB_SYM_THREADS - 1) / OB_SYM_THREADS, OB_SYM_THREADS, 0, stream>>>(
+        d_packets, d_offsets + w0, d_lens + w0, ir, total, d->CC, frame_size);
+    if (timed) OB_CUDA(cudaEventRecord(d->ev[1], stream));
+    ob_k_bands<<<(total + OB_BANDS_WARPS - 1) / OB_BANDS_WARPS, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, stream>>>(
+        ir, st, X, Sc, F);
+    if (timed) OB_CUDA(cudaEventRecord(d->ev[2], stream));
+    ob_k_synth<<<Sc, OB_SYNTH_THREADS, 0, stream>>>(ir, X, st, hist, d_pcm + w0 * (size_t)frame_size * d->CC, d_samples + w0,
+                                                     d_ranges ? d_ranges + w0 : nullptr, Sc, F, d->CC, frame_size);
+    if (timed) OB_CUDA(cudaEventRecord(d->ev[3], stream));
     OB_CUDA(cudaGetLastError());
     d->launches += 3;
-    d->timed = true;
+    if (timed) d->timed = true;
     return OB_OK;
 }
 
@@ -201,7 +207,12 @@ ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         const size_t total = (size_t)n_streams * max_frames;
         bool ok = cudaSetDevice(device) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreate(&d->ev[i]) == cudaSuccess;
+        for (int i = 0; i < OB_MAX_CHUNKS && ok; i++) ok = cudaEventCreateWithFlags(&d->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&d->copy_done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&d->h2d_done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&d->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_state, sizeof(ObDecState) * n_streams) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_hist, sizeof(float) * (size_t)n_streams * channels * OB_HIST_LEN) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_ir, sizeof(ObFrameIR) * total) == cudaSuccess;
@@ -234,6 +245,11 @@ void ob_decoder_destroy(ObDecoder *d)
     cudaFree(d->d_state); cudaFree(d->d_hist); cudaFree(d->d_ir); cudaFree(d->d_X); cudaFree(d->d_packets);
     cudaFree(d->d_offsets); cudaFree(d->d_lens); cudaFree(d->d_samples); cudaFree(d->d_ranges); cudaFree(d->d_pcm);
     for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+    for (int i = 0; i < OB_MAX_CHUNKS; i++) if (d->chunk_ev[i]) cudaEventDestroy(d->chunk_ev[i]);
+    if (d->copy_done) cudaEventDestroy(d->copy_done);
+    if (d->h2d_done) cudaEventDestroy(d->h2d_done);
+    if (d->aux_stream) cudaStreamDestroy(d->aux_stream);
+    if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
 }
@@ -264,7 +280,7 @@ int32_t ob_decode_float_device(ObDecoder *d, int32_t n_frames, const uint8_t *d_
     if (!d || !d_packets || !d_offsets || !d_lens || !d_pcm_out || !d_samples_out) return OB_BAD_ARG;
     if (n_frames <= 0 || n_frames > d->max_frames || frame_size <= 0) return OB_BAD_ARG;
     OB_CUDA(cudaSetDevice(d->device));
-    const int r = ob_launch(d, n_frames, d_packets, d_offsets, d_lens, d_pcm_out, frame_size, d_samples_out, d_ranges_out);
+    const int r = ob_launch(d, 0, d->S, n_frames, d_packets, d_offsets, d_lens, d_pcm_out, frame_size, d_samples_out, d_ranges_out, 1, d->stream);
     if (r != OB_OK) return r;
     if (sync) OB_CUDA(cudaStreamSynchronize(d->stream));
     return OB_OK;
@@ -298,11 +314,28 @@ int32_t ob_decode_float_multi(ObDecoder *d, int32_t n_frames, const uint8_t *pac
     OB_CUDA(cudaMemcpyAsync(d->d_packets, packets, nbytes, cudaMemcpyHostToDevice, d->stream));
     OB_CUDA(cudaMemcpyAsync(d->d_offsets, offsets, total * sizeof(int32_t), cudaMemcpyHostToDevice, d->stream));
     OB_CUDA(cudaMemcpyAsync(d->d_lens, lens, total * sizeof(int32_t), cudaMemcpyHostToDevice, d->stream));
-    const int r = ob_launch(d, n_frames, d->d_packets, d->d_offsets, d->d_lens, d->d_pcm, frame_size, d->d_samples, d->d_ranges);
-    if (r != OB_OK) return r;
-    OB_CUDA(cudaMemcpyAsync(pcm_out, d->d_pcm, pcm_floats * sizeof(float), cudaMemcpyDeviceToHost, d->stream));
-    OB_CUDA(cudaMemcpyAsync(samples_out, d->d_samples, total * sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream));
-    if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out, d->d_ranges, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->stream));
+    // Streams are processed in chunks so that the device->host copy of chunk k overlaps the kernels of chunk k+1
+    // (kernels on d->stream, copies on d->copy_stream, one event per chunk).
+    int nchunks = d->S * n_frames >= 65536 ? 4 : (d->S * n_frames >= 16384 ? 2 : 1);
+    if (nchunks > OB_MAX_CHUNKS) nchunks = OB_MAX_CHUNKS;
+    const int per = (d->S + nchunks - 1) / nchunks;
+    OB_CUDA(cudaEventRecord(d->h2d_done, d->stream));
+    OB_CUDA(cudaStreamWaitEvent(d->aux_stream, d->h2d_done, 0));
+    for (int k = 0, s0 = 0; s0 < d->S; k++, s0 += per) {
+        const int Sc = d->S - s0 < per ? d->S - s0 : per;
+        const size_t w0 = (size_t)s0 * n_frames, cnt = (size_t)Sc * n_frames;
+        cudaStream_t cs = (k & 1) ? d->aux_stream : d->stream;       // alternate compute streams: kernels of neighbouring chunks overlap
+        const int r = ob_launch(d, s0, Sc, n_frames, d->d_packets, d->d_offsets, d->d_lens, d->d_pcm, frame_size, d->d_samples, d->d_ranges, 0, cs);
+        if (r != OB_OK) return r;
+        OB_CUDA(cudaEventRecord(d->chunk_ev[k], cs));
+        OB_CUDA(cudaStreamWaitEvent(d->copy_stream, d->chunk_ev[k], 0));
+        const size_t pf = (size_t)frame_size * d->CC;
+        OB_CUDA(cudaMemcpyAsync(pcm_out + w0 * pf, d->d_pcm + w0 * pf, cnt * pf * sizeof(float), cudaMemcpyDeviceToHost, d->copy_stream));
+        OB_CUDA(cudaMemcpyAsync(samples_out + w0, d->d_samples + w0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, d->copy_stream));
+        if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out + w0, d->d_ranges + w0, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->copy_stream));
+    }
+    OB_CUDA(cudaEventRecord(d->copy_done, d->copy_stream));
+    OB_CUDA(cudaStreamWaitEvent(d->stream, d->copy_done, 0));      // keep d->stream a faithful timeline of the whole call
     OB_CUDA(cudaStreamSynchronize(d->stream));
     return OB_OK;
 }

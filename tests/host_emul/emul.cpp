@@ -28,23 +28,24 @@ int emul_decode_stream(const uint8_t *pkts, const int *lens, int stride, int nfr
     ObSynthShared *sh = (ObSynthShared *)calloc(1, sizeof(ObSynthShared));
     ObFrameIR *ir = (ObFrameIR *)calloc(1, sizeof(ObFrameIR));
     float *X = (float *)calloc(2 * OB_MAX_N, sizeof(float));
-    float *norm = (float *)calloc(2 * OB_NORM_LEN, sizeof(float));
-    float scratch[OB_MAX_BAND], tmp[OB_MAX_BAND];
+    ObBandsShared *bsh = (ObBandsShared *)calloc(1, sizeof(ObBandsShared));
     for (int i = 0; i < 2 * OB_NB; i++) sh->oldLogE[i] = sh->oldLogE2[i] = -28.f;
     ObSolo g;
+    ob_synth_init(g, *sh);
     for (int f = 0; f < nframes; f++) {
         memset(ir, 0, sizeof(*ir));
         ob_decode_symbols(pkts + (size_t)f * stride, lens[f], dec_channels, max_frame, ir);
         int n = ir->hdr.status;
         if (n > 0) {
-            ob_reconstruct_bands(g, ir, sh->rng, X, norm, scratch, tmp);
+            for (int j = 0; j < 2 * OB_MAX_N; j++) X[j] = __builtin_nanf("");     // bands >= end are never written
+            ob_reconstruct_bands(g, ir, sh->rng, *bsh, X);
             if (Xtap) memcpy(Xtap + (size_t)f * 1920, X, sizeof(float) * ir->hdr.C * n);
             n = ob_synth_frame(g, *sh, ir, X, pcm_out + (size_t)f * max_frame * dec_channels, dec_channels);
         }
         samples[f] = n;
         ranges[f] = n > 0 ? ir->hdr.final_range : 0;
     }
-    free(sh); free(ir); free(X); free(norm);
+    free(sh); free(ir); free(X); free(bsh);
     return 0;
 }
 }
