@@ -230,10 +230,8 @@ def run_ours(args):
     h2d = int(h_pk.numel() + 4 * h_off.numel() + 4 * h_len.numel())
     d2h = int(4 * h_pcm.numel() + 4 * h_smp.numel() + 4 * h_rng.numel())
 
-    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    from opus_codec_b200.shard import max_over_ranks
+    ms_dev, ms_e2e = max_over_ranks(ms_dev, dev), max_over_ranks(ms_e2e, dev)     # slowest rank defines the job's time
     audio_per_step = world * S * F * 0.02
     value = audio_per_step * args.steps / (ms_dev / 1000.0)
     e2e = audio_per_step * e2e_steps / (ms_e2e / 1000.0) if e2e_steps else None
