@@ -1,0 +1,415 @@
+// enc_frame.cuh -- per-stream CELT encoder state and the frame driver: celt_encode_with_ec
+// (opus/celt/celt_encoder.c:1431-2368) for start = 0, no LFE, no surround mask, no Opus-layer signal analysis
+// (analysis.valid == 0), plus the thin Opus layer around it for CELT-only packets
+// (opus/src/opus_encoder.c: dc_reject :430-468, byte budget :1188-1197, TOC gen_toc :299-329).
+#pragma once
+#include "enc_quant.cuh"
+
+#define OB_BITRATE_MAX (-1)
+
+// struct OpusCustomEncoder (celt_encoder.c:58-128), the parts this path uses, + the Opus layer's dc_reject memory.
+struct ObEncState {
+    // configuration (CTLs)
+    int32_t channels, stream_channels, complexity, bitrate, vbr, constrained_vbr, lsb_depth, end, force_intra, loss_rate, disable_inv, clip, disable_pf;
+    // everything below is cleared by OPUS_RESET_STATE (celt_encoder.c:2552-2571)
+    uint32_t rng;
+    int32_t spread_decision;
+    float delayedIntra;
+    int32_t tonal_average, lastCodedBands, hf_average, tapset_decision, prefilter_period;
+    float prefilter_gain;
+    int32_t prefilter_tapset, consec_transient;
+    float preemph_memE[2];
+    int32_t vbr_reservoir, vbr_drift, vbr_offset, vbr_count;
+    float overlap_max, stereo_saving;
+    int32_t intensity;
+    float spec_avg;
+    float hp_mem[4];                                  // Opus layer: dc_reject (opus_encoder.c:430-468)
+    uint32_t final_range;
+    float in_mem[2 * OB_OVERLAP];
+    float prefilter_mem[2 * OB_MAXPERIOD];
+    float oldBandE[2 * OB_NB], oldLogE[2 * OB_NB], oldLogE2[2 * OB_NB], energyError[2 * OB_NB];
+};
+
+// Per-stream working memory of one frame (the reference's stack VLAs).
+struct ObEncScratch {
+    float in[2 * (OB_MAX_N + OB_OVERLAP)];
+    float pre[2 * (OB_MAX_N + OB_MAXPERIOD)];
+    float pitch_buf[(OB_MAXPERIOD + OB_MAX_N) >> 1];
+    float tmp[1280];                                  // pitch_search scratch / yy_lookup / transient_analysis tmp
+    float freq[2 * OB_MAX_N];
+    float X[2 * OB_MAX_N];
+    float mdct_f[OB_MAX_N], mdct_f2[OB_MAX_N];
+    float pcm_hp[2 * OB_MAX_N];                       // dc_reject output
+    ObEncBandsScratch bands;
+    uint8_t coarse_save[1280];
+};
+
+OB_DEV void ob_enc_reset(ObEncState &st)
+{
+    st.rng = 0; st.spread_decision = 2; st.delayedIntra = 1; st.tonal_average = 256; st.lastCodedBands = 0; st.hf_average = 0;
+    st.tapset_decision = 0; st.prefilter_period = 0; st.prefilter_gain = 0; st.prefilter_tapset = 0; st.consec_transient = 0;
+    st.preemph_memE[0] = st.preemph_memE[1] = 0; st.vbr_reservoir = st.vbr_drift = st.vbr_offset = st.vbr_count = 0;
+    st.overlap_max = 0; st.stereo_saving = 0; st.intensity = 0; st.spec_avg = 0; st.final_range = 0;
+    for (int i = 0; i < 4; i++) st.hp_mem[i] = 0;
+    for (int i = 0; i < 2 * OB_OVERLAP; i++) st.in_mem[i] = 0;
+    for (int i = 0; i < 2 * OB_MAXPERIOD; i++) st.prefilter_mem[i] = 0;
+    for (int i = 0; i < 2 * OB_NB; i++) { st.oldBandE[i] = 0; st.oldLogE[i] = st.oldLogE2[i] = -28.f; st.energyError[i] = 0; }
+}
+
+// run_prefilter (celt_encoder.c:1188-1318), analysis invalid
+OB_DEV int ob_run_prefilter(ObEncState &st, ObEncScratch &S, float *in, int CC, int N, int prefilter_tapset, int *pitch, float *gain, int *qgain,
+        int enabled, int nbAvailableBytes)
+{
+    float *pre[2] = {S.pre, S.pre + (N + OB_MAXPERIOD)};
+    int pitch_index, pf_on, qg;
+    float gain1, pf_threshold;
+    for (int c = 0; c < CC; c++) {
+        for (int i = 0; i < OB_MAXPERIOD; i++) pre[c][i] = st.prefilter_mem[c * OB_MAXPERIOD + i];
+        for (int i = 0; i < N; i++) pre[c][OB_MAXPERIOD + i] = in[c * (N + OB_OVERLAP) + OB_OVERLAP + i];
+    }
+    if (enabled) {
+        float *pitch_buf = S.pitch_buf;
+        ob_pitch_downsample(pre[0], pre[1], pitch_buf, OB_MAXPERIOD + N, CC);
+        ob_pitch_search(pitch_buf + (OB_MAXPERIOD >> 1), pitch_buf, N, OB_MAXPERIOD - 3 * OB_MINPERIOD, &pitch_index, S.tmp);
+        pitch_index = OB_MAXPERIOD - pitch_index;
+        gain1 = ob_remove_doubling(pitch_buf, OB_MAXPERIOD, OB_MINPERIOD, N, &pitch_index, st.prefilter_period, st.prefilter_gain, S.tmp);
+        if (pitch_index > OB_MAXPERIOD - 2) pitch_index = OB_MAXPERIOD - 2;
+        gain1 = .7f * gain1;
+        if (st.loss_rate > 2) gain1 = .5f * gain1;
+        if (st.loss_rate > 4) gain1 = .5f * gain1;
+        if (st.loss_rate > 8) gain1 = 0;
+    } else { gain1 = 0; pitch_index = OB_MINPERIOD; }
+    pf_threshold = .2f;
+    int dp = pitch_index - st.prefilter_period; if (dp < 0) dp = -dp;
+    if (dp * 10 > pitch_index) pf_threshold += .2f;
+    if (nbAvailableBytes < 25) pf_threshold += .1f;
+    if (nbAvailableBytes < 35) pf_threshold += .1f;
+    if (st.prefilter_gain > .4f) pf_threshold -= .1f;
+    if (st.prefilter_gain > .55f) pf_threshold -= .1f;
+    pf_threshold = ob_fmax(pf_threshold, .2f);
+    if (gain1 < pf_threshold) { gain1 = 0; pf_on = 0; qg = 0; }
+    else {
+        if (fabsf(gain1 - st.prefilter_gain) < .1f) gain1 = st.prefilter_gain;
+        qg = (int)floor((double)(.5f + gain1 * 32 / 3)) - 1;
+        qg = ob_imax(0, ob_imin(7, qg));
+        gain1 = 0.09375f * (qg + 1);
+        pf_on = 1;
+    }
+    for (int c = 0; c < CC; c++) {
+        const int offset = OB_SHORT - OB_OVERLAP;      // 0 for this mode
+        st.prefilter_period = ob_imax(st.prefilter_period, OB_MINPERIOD);
+        for (int i = 0; i < OB_OVERLAP; i++) in[c * (N + OB_OVERLAP) + i] = st.in_mem[c * OB_OVERLAP + i];
+        if (offset)
+            ob_comb_filter_xy(in + c * (N + OB_OVERLAP) + OB_OVERLAP, pre[c] + OB_MAXPERIOD, st.prefilter_period, st.prefilter_period, offset,
+                    -st.prefilter_gain, -st.prefilter_gain, st.prefilter_tapset, st.prefilter_tapset, 0);
+        ob_comb_filter_xy(in + c * (N + OB_OVERLAP) + OB_OVERLAP + offset, pre[c] + OB_MAXPERIOD + offset, st.prefilter_period, pitch_index, N - offset,
+                -st.prefilter_gain, -gain1, st.prefilter_tapset, prefilter_tapset, OB_OVERLAP);
+        for (int i = 0; i < OB_OVERLAP; i++) st.in_mem[c * OB_OVERLAP + i] = in[c * (N + OB_OVERLAP) + N + i];
+        if (N > OB_MAXPERIOD) {
+            for (int i = 0; i < OB_MAXPERIOD; i++) st.prefilter_mem[c * OB_MAXPERIOD + i] = pre[c][N + i];
+        } else {
+            for (int i = 0; i < OB_MAXPERIOD - N; i++) st.prefilter_mem[c * OB_MAXPERIOD + i] = st.prefilter_mem[c * OB_MAXPERIOD + N + i];
+            for (int i = 0; i < N; i++) st.prefilter_mem[c * OB_MAXPERIOD + OB_MAXPERIOD - N + i] = pre[c][OB_MAXPERIOD + i];
+        }
+    }
+    *gain = gain1; *pitch = pitch_index; *qgain = qg;
+    return pf_on;
+}
+
+OB_DEV float ob_maxabs(const float *x, int len)                      // celt_maxabs16 (mathops.h:79-91)
+{
+    float maxval = 0, minval = 0;
+    for (int i = 0; i < len; i++) { maxval = ob_fmax(maxval, x[i]); minval = ob_fmin(minval, x[i]); }
+    return ob_fmax(maxval, -minval);
+}
+
+// celt_encode_with_ec (celt_encoder.c:1431-2368).  pcm: interleaved floats in [-1,1].  enc: coder created by the caller over the
+// payload buffer (as opus_encode_frame_native does, opus_encoder.c:1791) -- tell == 1 on entry.  Returns bytes used or < 0.
+OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float *pcm, int frame_size, int nbCompressedBytes, ObRangeEnc &enc)
+{
+    const int CC = st.channels, C = st.stream_channels, end = st.end, effEnd = st.end;
+    int LM, shortBlocks = 0, isTransient = 0, tf_select, codedBands, alloc_trim, pitch_index = OB_MINPERIOD, dual_stereo = 0, effectiveBytes;
+    int prefilter_tapset = 0, pf_on, anti_collapse_rsv, anti_collapse_on = 0, silence = 0, tf_chan = 0, pitch_change = 0, secondMdct;
+    int signalBandwidth, transient_got_disabled = 0, enable_tf_analysis, nbFilledBytes, nbAvailableBytes, dynalloc_logp;
+    int32_t vbr_rate, total_bits, total_boost, balance, tell, tot_boost = 0, equiv_rate, bits;
+    float gain1 = 0, tf_estimate = 0, sample_max, maxDepth, temporal_vbr = 0;
+    float bandE[2 * OB_NB], bandLogE[2 * OB_NB], bandLogE2[2 * OB_NB], error[2 * OB_NB];
+    int fine_quant[OB_NB], pulses[OB_NB], cap[OB_NB], offsets[OB_NB], importance[OB_NB], spread_weight[OB_NB], fine_priority[OB_NB], tf_res[OB_NB];
+    uint8_t collapse_masks[2 * OB_NB];
+    float *oldBandE = st.oldBandE, *oldLogE = st.oldLogE, *oldLogE2 = st.oldLogE2, *energyError = st.energyError;
+    float *in = S.in, *freq = S.freq, *X = S.X;
+
+    if (nbCompressedBytes < 2 || pcm == nullptr) return OB_BAD_ARG;
+    for (LM = 0; LM <= 3; LM++) if (OB_SHORT << LM == frame_size) break;
+    if (LM > 3) return OB_BAD_ARG;
+    const int M = 1 << LM, N = M * OB_SHORT;
+    tell = enc.tell();
+    nbFilledBytes = (tell + 4) >> 3;
+    nbCompressedBytes = ob_imin(nbCompressedBytes, 1275);
+    nbAvailableBytes = nbCompressedBytes - nbFilledBytes;
+    if (st.vbr && st.bitrate != OB_BITRATE_MAX) {
+        const int32_t den = 48000 >> OB_BITRES;
+        vbr_rate = (st.bitrate * frame_size + (den >> 1)) / den;
+        effectiveBytes = vbr_rate >> (3 + OB_BITRES);
+    } else {
+        int32_t tmp;
+        vbr_rate = 0;
+        tmp = st.bitrate * frame_size;
+        if (tell > 1) tmp += tell * 48000;
+        if (st.bitrate != OB_BITRATE_MAX) {
+            nbCompressedBytes = ob_imax(2, ob_imin(nbCompressedBytes, (tmp + 4 * 48000) / (8 * 48000)));
+            enc.shrink((uint32_t)nbCompressedBytes);
+        }
+        effectiveBytes = nbCompressedBytes - nbFilledBytes;
+    }
+    equiv_rate = ((int32_t)nbCompressedBytes * 8 * 50 << (3 - LM)) - (40 * C + 20) * ((400 >> LM) - 50);
+    if (st.bitrate != OB_BITRATE_MAX) equiv_rate = ob_imin(equiv_rate, st.bitrate - (40 * C + 20) * ((400 >> LM) - 50));
+    if (vbr_rate > 0 && st.constrained_vbr) {
+        const int32_t vbr_bound = vbr_rate;
+        const int32_t max_allowed = ob_imin(ob_imax(tell == 1 ? 2 : 0, (vbr_rate + vbr_bound - st.vbr_reservoir) >> (OB_BITRES + 3)), nbAvailableBytes);
+        if (max_allowed < nbAvailableBytes) {
+            nbCompressedBytes = nbFilledBytes + max_allowed;
+            nbAvailableBytes = max_allowed;
+            enc.shrink((uint32_t)nbCompressedBytes);
+        }
+    }
+    total_bits = nbCompressedBytes * 8;
+
+    sample_max = ob_fmax(st.overlap_max, ob_maxabs(pcm, C * (N - OB_OVERLAP)));
+    st.overlap_max = ob_maxabs(pcm + C * (N - OB_OVERLAP), C * OB_OVERLAP);
+    sample_max = ob_fmax(sample_max, st.overlap_max);
+    silence = (sample_max <= (float)1 / (1 << st.lsb_depth));
+    if (tell == 1) enc.bit_logp(silence, 15);
+    else silence = 0;
+    if (silence) {
+        if (vbr_rate > 0) {
+            effectiveBytes = nbCompressedBytes = ob_imin(nbCompressedBytes, nbFilledBytes + 2);
+            total_bits = nbCompressedBytes * 8;
+            nbAvailableBytes = 2;
+            enc.shrink((uint32_t)nbCompressedBytes);
+        }
+        tell = nbCompressedBytes * 8;
+        enc.nbits_total += tell - enc.tell();
+    }
+    for (int c = 0; c < CC; c++) {
+        const int need_clip = st.clip && sample_max > 65536.f;
+        ob_preemphasis(pcm + c, in + c * (N + OB_OVERLAP) + OB_OVERLAP, N, CC, &st.preemph_memE[c], need_clip);
+    }
+    {   // pitch pre-filter
+        int qg;
+        const int enabled = nbAvailableBytes > 12 * C && !silence && !st.disable_pf && st.complexity >= 5;
+        prefilter_tapset = st.tapset_decision;
+        pf_on = ob_run_prefilter(st, S, in, CC, N, prefilter_tapset, &pitch_index, &gain1, &qg, enabled, nbAvailableBytes);
+        if ((gain1 > .4f || st.prefilter_gain > .4f) && (pitch_index > 1.26 * st.prefilter_period || pitch_index < .79 * st.prefilter_period))
+            pitch_change = 1;
+        if (pf_on == 0) {
+            if (tell + 16 <= total_bits) enc.bit_logp(0, 1);
+        } else {
+            enc.bit_logp(1, 1);
+            pitch_index += 1;
+            const int octave = ob_ilog((uint32_t)pitch_index) - 5;
+            enc.uint((uint32_t)octave, 6);
+            enc.bits((uint32_t)(pitch_index - (16 << octave)), (uint32_t)(4 + octave));
+            pitch_index -= 1;
+            enc.bits((uint32_t)qg, 3);
+            enc.icdf(prefilter_tapset, OB_TAPSET_ICDF, 2);
+        }
+    }
+    if (st.complexity >= 1) isTransient = ob_transient_analysis(in, N + OB_OVERLAP, CC, &tf_estimate, &tf_chan, S.tmp);
+    if (LM > 0 && enc.tell() + 3 <= total_bits) { if (isTransient) shortBlocks = M; }
+    else { isTransient = 0; transient_got_disabled = 1; }
+
+    secondMdct = shortBlocks && st.complexity >= 8;
+    if (secondMdct) {
+        ob_compute_mdcts(0, in, freq, C, CC, LM, S.mdct_f, S.mdct_f2);
+        ob_band_energies(freq, bandE, effEnd, C, LM);
+        ob_amp2log2(effEnd, end, bandE, bandLogE2, C);
+        for (int c = 0; c < C; c++) for (int i = 0; i < end; i++) bandLogE2[OB_NB * c + i] += .5f * (float)LM;
+    }
+    ob_compute_mdcts(shortBlocks, in, freq, C, CC, LM, S.mdct_f, S.mdct_f2);
+    if (CC == 2 && C == 1) tf_chan = 0;
+    ob_band_energies(freq, bandE, effEnd, C, LM);
+    ob_amp2log2(effEnd, end, bandE, bandLogE, C);
+    {   // temporal VBR (celt_encoder.c:1849-1865)
+        float follow = -10.0f, frame_avg = 0;
+        const float offset = shortBlocks ? .5f * (float)LM : 0;
+        for (int i = 0; i < end; i++) {
+            follow = ob_fmax(follow - 1.f, bandLogE[i] - offset);
+            if (C == 2) follow = ob_fmax(follow, bandLogE[i + OB_NB] - offset);
+            frame_avg += follow;
+        }
+        frame_avg /= (float)end;
+        temporal_vbr = frame_avg - st.spec_avg;
+        temporal_vbr = ob_fmin(3.f, ob_fmax(-1.5f, temporal_vbr));
+        st.spec_avg += .02f * temporal_vbr;
+    }
+    if (!secondMdct) for (int i = 0; i < C * OB_NB; i++) bandLogE2[i] = bandLogE[i];
+    if (LM > 0 && enc.tell() + 3 <= total_bits && !isTransient && st.complexity >= 5) {
+        if (ob_patch_transient(bandLogE, oldBandE, end, C)) {
+            isTransient = 1;
+            shortBlocks = M;
+            ob_compute_mdcts(shortBlocks, in, freq, C, CC, LM, S.mdct_f, S.mdct_f2);
+            ob_band_energies(freq, bandE, effEnd, C, LM);
+            ob_amp2log2(effEnd, end, bandE, bandLogE, C);
+            for (int c = 0; c < C; c++) for (int i = 0; i < end; i++) bandLogE2[OB_NB * c + i] += .5f * (float)LM;
+            tf_estimate = .2f;
+        }
+    }
+    if (LM > 0 && enc.tell() + 3 <= total_bits) enc.bit_logp(isTransient, 3);
+
+    ob_normalise_bands(freq, X, bandE, effEnd, C, M);
+    enable_tf_analysis = effectiveBytes >= 15 * C && st.complexity >= 2;
+    maxDepth = ob_dynalloc_analysis(bandLogE, bandLogE2, oldBandE, end, C, offsets, st.lsb_depth, isTransient, st.vbr, st.constrained_vbr, LM,
+            effectiveBytes, &tot_boost, importance, spread_weight);
+    if (enable_tf_analysis) {
+        const int lambda = ob_imax(80, 20480 / effectiveBytes + 2);
+        tf_select = ob_tf_analysis(effEnd, isTransient, tf_res, lambda, X, N, LM, tf_estimate, tf_chan, importance);
+        for (int i = effEnd; i < end; i++) tf_res[i] = tf_res[effEnd - 1];
+    } else {
+        for (int i = 0; i < end; i++) tf_res[i] = isTransient;
+        tf_select = 0;
+    }
+    for (int c = 0; c < C; c++) for (int i = 0; i < end; i++) {
+        if (fabsf(bandLogE[i + c * OB_NB] - oldBandE[i + c * OB_NB]) < 2.f) bandLogE[i + c * OB_NB] -= energyError[i + c * OB_NB] * 0.25f;
+    }
+    ob_quant_coarse_energy(end, effEnd, bandLogE, oldBandE, (uint32_t)total_bits, error, enc, C, LM, nbAvailableBytes, st.force_intra,
+            &st.delayedIntra, st.complexity >= 4, st.loss_rate, S.coarse_save);
+    ob_tf_encode(end, isTransient, tf_res, LM, tf_select, enc);
+    if (enc.tell() + 4 <= total_bits) {
+        if (shortBlocks || st.complexity < 3 || nbAvailableBytes < 10 * C) {
+            if (st.complexity == 0) st.spread_decision = 0; else st.spread_decision = 2;
+        } else {
+            st.spread_decision = ob_spreading_decision(X, &st.tonal_average, st.spread_decision, &st.hf_average, &st.tapset_decision,
+                    pf_on && !shortBlocks, effEnd, C, M, spread_weight);
+        }
+        enc.icdf(st.spread_decision, OB_SPREAD_ICDF, 5);
+    }
+    for (int i = 0; i < OB_NB; i++) {                                  // init_caps (celt.c:272-281)
+        const int Nb = (OB_EBANDS[i + 1] - OB_EBANDS[i]) << LM;
+        cap[i] = (OB_CACHE_CAPS[OB_NB * (2 * LM + C - 1) + i] + 64) * C * Nb >> 2;
+    }
+    dynalloc_logp = 6;
+    total_bits <<= OB_BITRES;
+    total_boost = 0;
+    tell = (int32_t)enc.tell_frac();
+    for (int i = 0; i < end; i++) {                                    // celt_encoder.c:2017-2050
+        const int width = C * (OB_EBANDS[i + 1] - OB_EBANDS[i]) << LM;
+        const int quanta = ob_imin(width << OB_BITRES, ob_imax(6 << OB_BITRES, width));
+        int dynalloc_loop_logp = dynalloc_logp, boost = 0, j;
+        for (j = 0; tell + (dynalloc_loop_logp << OB_BITRES) < total_bits - total_boost && boost < cap[i]; j++) {
+            const int flag = j < offsets[i];
+            enc.bit_logp(flag, (uint32_t)dynalloc_loop_logp);
+            tell = (int32_t)enc.tell_frac();
+            if (!flag) break;
+            boost += quanta;
+            total_boost += quanta;
+            dynalloc_loop_logp = 1;
+        }
+        if (j) dynalloc_logp = ob_imax(2, dynalloc_logp - 1);
+        offsets[i] = boost;
+    }
+    if (C == 2) {
+        const float intensity_thresholds[21] = {1, 2, 3, 4, 5, 6, 7, 8, 16, 24, 36, 44, 50, 56, 62, 67, 72, 79, 88, 106, 134};
+        const float intensity_histeresis[21] = {1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 3, 3, 4, 5, 6, 8, 8};
+        if (LM != 0) dual_stereo = ob_stereo_analysis(X, LM, N);
+        st.intensity = ob_hysteresis_decision((float)(equiv_rate / 1000), intensity_thresholds, intensity_histeresis, 21, st.intensity);
+        st.intensity = ob_imin(end, ob_imax(0, st.intensity));
+    }
+    alloc_trim = 5;
+    if (tell + (6 << OB_BITRES) <= total_bits - total_boost) {
+        alloc_trim = ob_alloc_trim_analysis(X, bandLogE, end, LM, C, N, &st.stereo_saving, tf_estimate, st.intensity, equiv_rate);
+        enc.icdf(alloc_trim, OB_TRIM_ICDF, 7);
+        tell = (int32_t)enc.tell_frac();
+    }
+    if (vbr_rate > 0) {                                                // celt_encoder.c:2086-2195
+        float alpha;
+        int32_t delta, target, base_target, min_allowed;
+        const int lm_diff = 3 - LM;
+        nbCompressedBytes = ob_imin(nbCompressedBytes, 1275 >> (3 - LM));
+        base_target = vbr_rate - ((40 * C + 20) << OB_BITRES);
+        if (st.constrained_vbr) base_target += (st.vbr_offset >> lm_diff);
+        target = ob_compute_vbr(base_target, LM, equiv_rate, st.lastCodedBands, C, st.intensity, st.constrained_vbr, st.stereo_saving, tot_boost,
+                tf_estimate, maxDepth, temporal_vbr);
+        (void)pitch_change;
+        target = target + tell;
+        min_allowed = ((tell + total_boost + (1 << (OB_BITRES + 3)) - 1) >> (OB_BITRES + 3)) + 2;
+        nbAvailableBytes = (target + (1 << (OB_BITRES + 2))) >> (OB_BITRES + 3);
+        nbAvailableBytes = ob_imax(min_allowed, nbAvailableBytes);
+        nbAvailableBytes = ob_imin(nbCompressedBytes, nbAvailableBytes);
+        delta = target - vbr_rate;
+        target = nbAvailableBytes << (OB_BITRES + 3);
+        if (silence) { nbAvailableBytes = 2; target = 2 * 8 << OB_BITRES; delta = 0; }
+        if (st.vbr_count < 970) { st.vbr_count++; alpha = 1.f / (float)(st.vbr_count + 20); }
+        else alpha = .001f;
+        if (st.constrained_vbr) st.vbr_reservoir += target - vbr_rate;
+        if (st.constrained_vbr) {
+            st.vbr_drift += (int32_t)(alpha * (float)((delta * (1 << lm_diff)) - st.vbr_offset - st.vbr_drift));
+            st.vbr_offset = -st.vbr_drift;
+        }
+        if (st.constrained_vbr && st.vbr_reservoir < 0) {
+            const int adjust = (-st.vbr_reservoir) / (8 << OB_BITRES);
+            nbAvailableBytes += silence ? 0 : adjust;
+            st.vbr_reservoir = 0;
+        }
+        nbCompressedBytes = ob_imin(nbCompressedBytes, nbAvailableBytes);
+        enc.shrink((uint32_t)nbCompressedBytes);
+    }
+    bits = (((int32_t)nbCompressedBytes * 8) << OB_BITRES) - (int32_t)enc.tell_frac() - 1;
+    anti_collapse_rsv = isTransient && LM >= 2 && bits >= ((LM + 2) << OB_BITRES) ? (1 << OB_BITRES) : 0;
+    bits -= anti_collapse_rsv;
+    signalBandwidth = end - 1;
+    codedBands = ob_enc_allocation(enc, end, offsets, cap, alloc_trim, &st.intensity, &dual_stereo, bits, &balance, pulses, fine_quant, fine_priority,
+            C, LM, st.lastCodedBands, signalBandwidth);
+    if (st.lastCodedBands) st.lastCodedBands = ob_imin(st.lastCodedBands + 1, ob_imax(st.lastCodedBands - 1, codedBands));
+    else st.lastCodedBands = codedBands;
+    ob_quant_fine_energy(end, oldBandE, error, fine_quant, enc, C);
+    for (int i = 0; i < 2 * OB_NB; i++) collapse_masks[i] = 0;
+    ob_enc_all_bands(end, X, C == 2 ? X + N : nullptr, collapse_masks, bandE, pulses, shortBlocks, st.spread_decision, dual_stereo, st.intensity, tf_res,
+            nbCompressedBytes * (8 << OB_BITRES) - anti_collapse_rsv, balance, enc, LM, codedBands, &st.rng, st.complexity, st.disable_inv, S.bands);
+    if (anti_collapse_rsv > 0) {
+        anti_collapse_on = st.consec_transient < 2;
+        enc.bits((uint32_t)anti_collapse_on, 1);
+    }
+    ob_quant_energy_finalise(end, oldBandE, error, fine_quant, fine_priority, nbCompressedBytes * 8 - enc.tell(), enc, C);
+    for (int i = 0; i < OB_NB * CC; i++) energyError[i] = 0;
+    for (int c = 0; c < C; c++) for (int i = 0; i < end; i++) energyError[i + c * OB_NB] = ob_fmax(-0.5f, ob_fmin(0.5f, error[i + c * OB_NB]));
+    if (silence) for (int i = 0; i < C * OB_NB; i++) oldBandE[i] = -28.f;
+    st.prefilter_period = pitch_index;
+    st.prefilter_gain = gain1;
+    st.prefilter_tapset = prefilter_tapset;
+    if (CC == 2 && C == 1) for (int i = 0; i < OB_NB; i++) oldBandE[OB_NB + i] = oldBandE[i];
+    if (!isTransient) {
+        for (int i = 0; i < CC * OB_NB; i++) { oldLogE2[i] = oldLogE[i]; oldLogE[i] = oldBandE[i]; }
+    } else for (int i = 0; i < CC * OB_NB; i++) oldLogE[i] = ob_fmin(oldLogE[i], oldBandE[i]);
+    for (int c = 0; c < CC; c++) for (int i = end; i < OB_NB; i++) { oldBandE[c * OB_NB + i] = 0; oldLogE[c * OB_NB + i] = oldLogE2[c * OB_NB + i] = -28.f; }
+    if (isTransient || transient_got_disabled) st.consec_transient++; else st.consec_transient = 0;
+    st.rng = enc.rng;
+    enc.done();
+    if (enc.error) return OB_INTERNAL_ERROR;
+    return nbCompressedBytes;
+}
+
+// dc_reject (opus_encoder.c:430-468), float build, cutoff 3 Hz @ 48 kHz
+OB_DEV void ob_dc_reject(const float *in, float *out, float *hp_mem, int len, int channels)
+{
+    const float coef = 6.3f * 3 / 48000, coef2 = 1 - coef;
+    if (channels == 2) {
+        float m0 = hp_mem[0], m2 = hp_mem[2];
+        for (int i = 0; i < len; i++) {
+            const float x0 = in[2 * i], x1 = in[2 * i + 1];
+            const float out0 = x0 - m0, out1 = x1 - m2;
+            m0 = coef * x0 + 1e-30f + coef2 * m0;
+            m2 = coef * x1 + 1e-30f + coef2 * m2;
+            out[2 * i] = out0; out[2 * i + 1] = out1;
+        }
+        hp_mem[0] = m0; hp_mem[2] = m2;
+    } else {
+        float m0 = hp_mem[0];
+        for (int i = 0; i < len; i++) {
+            const float x = in[i], y = x - m0;
+            m0 = coef * x + 1e-30f + coef2 * m0;
+            out[i] = y;
+        }
+        hp_mem[0] = m0;
+    }
+}

@@ -43,12 +43,18 @@ struct ObBlock {
         return t;
     }
 };
+#endif
+
+// A single lane: the whole "group" is one thread (thread-per-stream device code, and the host emulation in tests/).
+#ifdef __CUDACC__
+#define OB_SOLO_FN __host__ __device__ __forceinline__
 #else
+#define OB_SOLO_FN inline
+#endif
 struct ObSolo {
     static constexpr int lane = 0;
     static constexpr int n = 1;
-    void sync() const {}
-    float sum(float v) const { return v; }
-    uint32_t sum_u32(uint32_t v) const { return v; }
+    OB_SOLO_FN void sync() const {}
+    OB_SOLO_FN float sum(float v) const { return v; }
+    OB_SOLO_FN uint32_t sum_u32(uint32_t v) const { return v; }
 };
-#endif

@@ -317,4 +317,63 @@ REF_EXPORT double ref_encode_pool(const float *pcm, int nstreams, int nframes, i
     return err ? (double)err : t;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * CELT-level encode: drives the reference's celt_encode_with_ec() directly (the CELT encoder object embedded in
+ * OpusEncoder is configured the same way by opus_encoder.c:2085-2116, :2255-2300) WITHOUT the Opus-layer signal
+ * analysis (analysis.valid == 0, SURVEY 2.2 "Signal analysis ... OUT OF SCOPE").  Packets carry no TOC byte.
+ * nbytes: bytes per frame handed to the CELT encoder (CBR size, or the VBR ceiling).
+ * ---------------------------------------------------------------------------------------------- */
+#include "celt.h"
+#include "entenc.h"
+REF_EXPORT int ref_celt_encode_stream(const float *pcm, int nframes, int frame_size, int channels, int bitrate, int vbr,
+        int complexity, int nbytes, unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
+{
+    int f;
+    CELTEncoder *e = (CELTEncoder *)malloc((size_t)celt_encoder_get_size(channels));
+    if (!e) return OPUS_ALLOC_FAIL;
+    if (celt_encoder_init(e, 48000, channels, opus_select_arch()) != OPUS_OK) { free(e); return OPUS_INTERNAL_ERROR; }
+    celt_encoder_ctl(e, CELT_SET_SIGNALLING(0));
+    celt_encoder_ctl(e, OPUS_SET_COMPLEXITY(complexity));
+    celt_encoder_ctl(e, OPUS_SET_LSB_DEPTH(24));
+    celt_encoder_ctl(e, OPUS_SET_VBR(vbr != 0));
+    celt_encoder_ctl(e, OPUS_SET_VBR_CONSTRAINT(vbr == 2));
+    /* exactly what opus_encode_frame_native does: CBR leaves the CELT bitrate at MAX and sizes the frame through the
+       byte budget (opus_encoder.c:2108, :2262-2273); the range coder is created by the caller (:1791, :2299) */
+    celt_encoder_ctl(e, OPUS_SET_BITRATE(vbr ? bitrate : OPUS_BITRATE_MAX));
+    if (nbytes > max_bytes) nbytes = max_bytes;
+    for (f = 0; f < nframes; f++) {
+        opus_uint32 rng = 0;
+        ec_enc enc;
+        int n;
+        ec_enc_init(&enc, out + (size_t)f * max_bytes, (opus_uint32)nbytes);
+        n = celt_encode_with_ec(e, pcm + (size_t)f * frame_size * channels, frame_size, NULL, nbytes, &enc);
+        if (n < 0) { free(e); return n; }
+        lens[f] = n;
+        celt_encoder_ctl(e, OPUS_GET_FINAL_RANGE(&rng));
+        if (ranges) ranges[f] = rng;
+    }
+    free(e);
+    return 0;
+}
+
+/* CELT-level decode of TOC-less packets (celt_decode_with_ec), for round trips of the above. */
+REF_EXPORT int ref_celt_decode_stream(const unsigned char *pkts, const int *lens, int stride, int nframes, int frame_size,
+        int channels, float *pcm_out, uint32_t *ranges)
+{
+    int f;
+    CELTDecoder *d = (CELTDecoder *)malloc((size_t)celt_decoder_get_size(channels));
+    if (!d) return OPUS_ALLOC_FAIL;
+    if (celt_decoder_init(d, 48000, channels) != OPUS_OK) { free(d); return OPUS_INTERNAL_ERROR; }
+    celt_decoder_ctl(d, CELT_SET_SIGNALLING(0));
+    for (f = 0; f < nframes; f++) {
+        opus_uint32 rng = 0;
+        int n = celt_decode_with_ec(d, pkts + (size_t)f * stride, lens[f], pcm_out + (size_t)f * frame_size * channels, frame_size, NULL, 0);
+        if (n < 0) { free(d); return n; }
+        celt_decoder_ctl(d, OPUS_GET_FINAL_RANGE(&rng));
+        if (ranges) ranges[f] = rng;
+    }
+    free(d);
+    return 0;
+}
+
 REF_EXPORT const char *ref_version(void) { return opus_get_version_string(); }

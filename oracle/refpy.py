@@ -10,12 +10,14 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libopus_ref.so")
+REF_C_SO = os.path.join(HERE, "_ref", "libopus_ref_c.so")     # same sources, no x86 intrinsics (bit-reproducible float paths)
 OPUS_COMPARE = os.path.join(HERE, "_ref", "opus_compare")
 
 APP_VOIP, APP_AUDIO, APP_LOWDELAY = 2048, 2049, 2051
 CBR, VBR, CVBR = 0, 1, 2
 
 _lib = None
+_lib_c = None
 
 
 def build(quiet=True):
@@ -42,6 +44,52 @@ def lib():
         L.ref_version.restype = C.c_char_p
         _lib = L
     return _lib
+
+
+def _declare_celt(L):
+    u8p, i32p, u32p, f32p = (C.POINTER(C.c_ubyte), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_float))
+    L.ref_celt_encode_stream.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, i32p, u32p]
+    L.ref_celt_encode_stream.restype = C.c_int
+    L.ref_celt_decode_stream.argtypes = [u8p, i32p, C.c_int, C.c_int, C.c_int, C.c_int, f32p, u32p]
+    L.ref_celt_decode_stream.restype = C.c_int
+    return L
+
+
+def lib_c():
+    """The no-intrinsics build of the reference (pure C float paths)."""
+    global _lib_c
+    if _lib_c is None:
+        if not os.path.exists(REF_C_SO):
+            build()
+        _lib_c = _declare_celt(C.CDLL(REF_C_SO))
+    return _lib_c
+
+
+def celt_encode_stream(pcm, frame_size, channels, bitrate, nbytes, vbr=CBR, complexity=10, max_bytes=1275, pure_c=True):
+    """CELT-level encode (no TOC, no Opus-layer analysis) -> (packets [nframes,max_bytes], lens, ranges)."""
+    L = lib_c() if pure_c else _declare_celt(lib())
+    pcm = np.ascontiguousarray(pcm, np.float32)
+    nframes = pcm.size // (frame_size * channels)
+    out = np.zeros((nframes, max_bytes), np.uint8)
+    lens = np.zeros(nframes, np.int32)
+    rng = np.zeros(nframes, np.uint32)
+    r = L.ref_celt_encode_stream(_p(pcm, C.c_float), nframes, frame_size, channels, bitrate, vbr, complexity, nbytes,
+                                 _p(out, C.c_ubyte), max_bytes, _p(lens, C.c_int), _p(rng, C.c_uint32))
+    if r != 0:
+        raise RuntimeError("ref_celt_encode_stream: opus error %d" % r)
+    return out, lens, rng
+
+
+def celt_decode_stream(pkts, lens, frame_size, channels, pure_c=False):
+    L = lib_c() if pure_c else _declare_celt(lib())
+    pkts = np.ascontiguousarray(pkts, np.uint8); lens = np.ascontiguousarray(lens, np.int32)
+    nframes, stride = pkts.shape
+    pcm = np.zeros((nframes, frame_size * channels), np.float32)
+    rng = np.zeros(nframes, np.uint32)
+    r = L.ref_celt_decode_stream(_p(pkts, C.c_ubyte), _p(lens, C.c_int), stride, nframes, frame_size, channels, _p(pcm, C.c_float), _p(rng, C.c_uint32))
+    if r != 0:
+        raise RuntimeError("ref_celt_decode_stream: opus error %d" % r)
+    return pcm, rng
 
 
 def _p(a, t):

@@ -49,3 +49,31 @@ int emul_decode_stream(const uint8_t *pkts, const int *lens, int stride, int nfr
     return 0;
 }
 }
+
+// ---- encoder -------------------------------------------------------------------------------------------------------------
+#include "../../opus_codec_b200/csrc/enc_frame.cuh"
+extern "C" {
+// CELT-level encode of one stream through the product's per-stream device code (one emulated thread); mirrors
+// ref_celt_encode_stream() in oracle/ref_shim.c (no TOC byte, coder created by the caller over `nbytes`).
+int emul_celt_encode_stream(const float *pcm, int nframes, int frame_size, int channels, int bitrate, int vbr, int complexity, int nbytes,
+                            unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
+{
+    ObEncState *st = (ObEncState *)calloc(1, sizeof(ObEncState));
+    ObEncScratch *S = (ObEncScratch *)calloc(1, sizeof(ObEncScratch));
+    st->channels = st->stream_channels = channels; st->complexity = complexity; st->vbr = vbr != 0; st->constrained_vbr = vbr == 2;
+    st->bitrate = vbr ? bitrate : OB_BITRATE_MAX; st->lsb_depth = 24; st->end = 21; st->clip = 1; st->disable_inv = 0;
+    ob_enc_reset(*st);
+    if (nbytes > max_bytes) nbytes = max_bytes;
+    int rc = 0;
+    for (int f = 0; f < nframes; f++) {
+        ObRangeEnc enc;
+        enc.init(out + (size_t)f * max_bytes, (uint32_t)nbytes);
+        const int n = ob_celt_encode(*st, *S, pcm + (size_t)f * frame_size * channels, frame_size, nbytes, enc);
+        if (n < 0) { rc = n; break; }
+        lens[f] = n;
+        ranges[f] = st->rng;
+    }
+    free(st); free(S);
+    return rc;
+}
+}
