@@ -413,3 +413,136 @@ OB_DEV void ob_dc_reject(const float *in, float *out, float *hp_mem, int len, in
         hp_mem[0] = m0;
     }
 }
+
+// ---- Opus layer for CELT-only packets (OPUS_APPLICATION_RESTRICTED_LOWDELAY => MODE_CELT_ONLY, opus_encoder.c:1330-1332) ----
+// User-visible encoder settings (the CTLs of src/encoder.rs) + the Opus-layer state this path keeps between frames.
+struct ObOpusEncCfg {
+    int32_t bitrate;           // OPUS_SET_BITRATE: bits/s, or -1000 (OPUS_AUTO) / -1 (OPUS_BITRATE_MAX)
+    int32_t complexity, vbr, vbr_constraint, max_bandwidth, user_bandwidth, force_channels, packet_loss, lsb_depth;
+};
+struct ObOpusEncState {
+    int32_t stream_channels, first, auto_bandwidth, bandwidth, hybrid_stereo_width_Q14;
+};
+
+OB_DEV int32_t ob_compute_equiv_rate(int32_t bitrate, int channels, int frame_rate, int vbr, int celt_only, int complexity, int loss)
+{                                                                    // opus_encoder.c:898-931
+    int32_t equiv = bitrate;
+    if (frame_rate > 50) equiv -= (40 * channels + 20) * (frame_rate - 50);
+    if (!vbr) equiv -= equiv / 12;
+    equiv = equiv * (90 + complexity) / 100;
+    if (celt_only) { if (complexity < 5) equiv = equiv * 9 / 10; }
+    else equiv -= equiv * loss / (12 * loss + 20);                   // "mode not known yet"
+    return equiv;
+}
+
+OB_DEV void ob_stereo_fade(float *buf, float g1, float g2, int frame_size)     // opus_encoder.c:471-501, in == out, channels == 2, Fs = 48000
+{
+    g1 = 1.0f - g1; g2 = 1.0f - g2;
+    int i;
+    for (i = 0; i < OB_OVERLAP; i++) {
+        const float w = OB_WINDOW[i] * OB_WINDOW[i];
+        const float g = w * g2 + (1.0f - w) * g1;
+        float diff = .5f * (buf[i * 2] - buf[i * 2 + 1]);
+        diff = g * diff;
+        buf[i * 2] = buf[i * 2] - diff;
+        buf[i * 2 + 1] = buf[i * 2 + 1] + diff;
+    }
+    for (; i < frame_size; i++) {
+        float diff = .5f * (buf[i * 2] - buf[i * 2 + 1]);
+        diff = g2 * diff;
+        buf[i * 2] = buf[i * 2] - diff;
+        buf[i * 2 + 1] = buf[i * 2 + 1] + diff;
+    }
+}
+
+// opus_encode_float -> opus_encode_native -> opus_encode_frame_native for one 2.5/5/10/20 ms frame, CELT-only
+// (opus_encoder.c:1057-1696, :1698-2459; the lines this path executes are listed in SURVEY 8a).  data: out_bytes capacity.
+// Returns the packet length in bytes (TOC included) or a negative OPUS_* code.
+OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, ObEncState &st, ObEncScratch &S, const float *pcm, int frame_size,
+        uint8_t *data, int out_bytes)
+{
+    const int channels = st.channels, Fs = 48000;
+    if (frame_size != 120 && frame_size != 240 && frame_size != 480 && frame_size != 960) return OB_BAD_ARG;   // > 20 ms needs the repacketizer
+    int max_data_bytes = ob_imin(1276, out_bytes);
+    if (max_data_bytes <= 0) return OB_BAD_ARG;
+    const int frame_rate = Fs / frame_size;
+    int32_t bitrate_bps;
+    if (cfg.bitrate == -1000) bitrate_bps = 60 * Fs / frame_size + Fs * channels;                              // user_bitrate_to_bitrate (:639-649)
+    else if (cfg.bitrate == -1) bitrate_bps = max_data_bytes * 8 * Fs / frame_size;
+    else bitrate_bps = cfg.bitrate;
+    if (!cfg.vbr) {                                                                                           // :1188-1197
+        const int frame_rate12 = 12 * Fs / frame_size;
+        const int cbr_bytes = ob_imin((12 * bitrate_bps / 8 + frame_rate12 / 2) / frame_rate12, max_data_bytes);
+        bitrate_bps = cbr_bytes * (int32_t)frame_rate12 * 8 / 12;
+        max_data_bytes = ob_imax(1, cbr_bytes);
+    }
+    if (max_data_bytes < 3 || bitrate_bps < 3 * frame_rate * 8) return OB_UNIMPLEMENTED;                       // the "PLC frame" corner (:1202-1266)
+    int32_t equiv_rate = ob_compute_equiv_rate(bitrate_bps, channels, frame_rate, cfg.vbr, 0, cfg.complexity, cfg.packet_loss);
+    const int voice_est = 48;                                                                                 // :1278-1291, signal AUTO, not VOIP
+    if (cfg.force_channels > 0 && channels == 2) os.stream_channels = cfg.force_channels;
+    else if (channels == 2) {
+        int32_t stereo_threshold = 17000 + ((voice_est * voice_est * (19000 - 17000)) >> 14);
+        if (os.stream_channels == 2) stereo_threshold -= 1000; else stereo_threshold += 1000;
+        os.stream_channels = (equiv_rate > stereo_threshold) ? 2 : 1;
+    } else os.stream_channels = channels;
+    equiv_rate = ob_compute_equiv_rate(bitrate_bps, os.stream_channels, frame_rate, cfg.vbr, 1, cfg.complexity, cfg.packet_loss);
+    {   // automatic bandwidth (:1440-1490); voice and music tables differ only for WB<->SWB and SWB<->FB
+        const int32_t voice_thr[8] = {9000, 700, 9000, 700, 13500, 1000, 14000, 2000}, music_thr[8] = {9000, 700, 9000, 700, 11000, 1000, 12000, 2000};
+        int bandwidth = 1105;
+        do {
+            const int k = 2 * (bandwidth - 1102);
+            int threshold = music_thr[k] + ((voice_est * voice_est * (voice_thr[k] - music_thr[k])) >> 14);
+            const int hysteresis = music_thr[k + 1] + ((voice_est * voice_est * (voice_thr[k + 1] - music_thr[k + 1])) >> 14);
+            if (!os.first) { if (os.auto_bandwidth >= bandwidth) threshold -= hysteresis; else threshold += hysteresis; }
+            if (equiv_rate >= threshold) break;
+        } while (--bandwidth > 1101);
+        if (bandwidth == 1102) bandwidth = 1103;
+        os.bandwidth = os.auto_bandwidth = bandwidth;
+    }
+    if (os.bandwidth > cfg.max_bandwidth) os.bandwidth = cfg.max_bandwidth;
+    if (cfg.user_bandwidth > 0) os.bandwidth = cfg.user_bandwidth;
+    if (os.bandwidth == 1102) os.bandwidth = 1103;
+    const int curr_bandwidth = os.bandwidth;
+
+    ObRangeEnc enc;
+    enc.init(data + 1, (uint32_t)(max_data_bytes - 1));
+    float *pcm_buf = S.pcm_hp;
+    ob_dc_reject(pcm, pcm_buf, st.hp_mem, frame_size, channels);
+    {
+        const float sum = ob_inner_prod(pcm_buf, pcm_buf, frame_size * channels);
+        if (!(sum < 1e9f) || sum != sum) {
+            for (int i = 0; i < frame_size * channels; i++) pcm_buf[i] = 0;
+            st.hp_mem[0] = st.hp_mem[1] = st.hp_mem[2] = st.hp_mem[3] = 0;
+        }
+    }
+    int stereoWidth_Q14;
+    if (equiv_rate > 32000) stereoWidth_Q14 = 16384;
+    else if (equiv_rate < 16000) stereoWidth_Q14 = 0;
+    else stereoWidth_Q14 = 16384 - 2048 * (int32_t)(32000 - equiv_rate) / (equiv_rate - 14000);
+    if (channels == 2 && (os.hybrid_stereo_width_Q14 < (1 << 14) || stereoWidth_Q14 < (1 << 14))) {
+        float g1 = (float)os.hybrid_stereo_width_Q14, g2 = (float)stereoWidth_Q14;
+        g1 *= (1.f / 16384); g2 *= (1.f / 16384);
+        ob_stereo_fade(pcm_buf, g1, g2, frame_size);
+        os.hybrid_stereo_width_Q14 = stereoWidth_Q14;
+    }
+    const int nb_compr_bytes = max_data_bytes - 1;
+    st.end = curr_bandwidth == 1101 ? 13 : curr_bandwidth <= 1103 ? 17 : curr_bandwidth == 1104 ? 19 : 21;
+    st.stream_channels = os.stream_channels;
+    st.complexity = cfg.complexity; st.lsb_depth = cfg.lsb_depth; st.loss_rate = cfg.packet_loss;
+    st.vbr = cfg.vbr; st.constrained_vbr = cfg.vbr_constraint;
+    st.bitrate = cfg.vbr ? bitrate_bps : OB_BITRATE_MAX;
+    int ret = ob_celt_encode(st, S, pcm_buf, frame_size, nb_compr_bytes, enc);
+    if (ret < 0) return OB_INTERNAL_ERROR;
+    {   // gen_toc (:299-329)
+        int period = 0, fr = frame_rate;
+        while (fr < 400) { fr <<= 1; period++; }
+        int tmp = curr_bandwidth - 1102;
+        if (tmp < 0) tmp = 0;
+        data[0] = (uint8_t)(0x80 | tmp << 5 | period << 3 | (os.stream_channels == 2) << 2);
+    }
+    st.final_range = enc.rng;
+    os.first = 0;
+    ret += 1;
+    if (!cfg.vbr && ret != max_data_bytes) return OB_UNIMPLEMENTED;     // opus_packet_pad: CELT CBR always fills its budget on this path
+    return ret;
+}

@@ -77,3 +77,25 @@ int emul_celt_encode_stream(const float *pcm, int nframes, int frame_size, int c
     return rc;
 }
 }
+extern "C" {
+// Opus-level encode (TOC byte included) of one stream; mirrors ref_encode_stream() with OPUS_APPLICATION_RESTRICTED_LOWDELAY.
+int emul_opus_encode_stream(const float *pcm, int nframes, int frame_size, int channels, int bitrate, int vbr, int complexity,
+                            unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
+{
+    ObEncState *st = (ObEncState *)calloc(1, sizeof(ObEncState));
+    ObEncScratch *S = (ObEncScratch *)calloc(1, sizeof(ObEncScratch));
+    ObOpusEncCfg cfg = {bitrate, complexity, vbr != 0, vbr == 2, 1105, 0, 0, 0, 24};
+    ObOpusEncState os = {channels, 1, 0, 1105, 1 << 14};
+    st->channels = st->stream_channels = channels; st->end = 21; st->clip = 1;
+    ob_enc_reset(*st);
+    int rc = 0;
+    for (int f = 0; f < nframes; f++) {
+        const int n = ob_opus_encode(cfg, os, *st, *S, pcm + (size_t)f * frame_size * channels, frame_size, out + (size_t)f * max_bytes, max_bytes);
+        if (n < 0) { rc = n; break; }
+        lens[f] = n;
+        ranges[f] = st->final_range;
+    }
+    free(st); free(S);
+    return rc;
+}
+}
