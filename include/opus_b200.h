@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define OB_ABI_VERSION 1
+#define OB_ABI_VERSION 2
 
 typedef struct ObDecoder ObDecoder;
 
@@ -80,6 +80,61 @@ int32_t ob_decoder_channels(const ObDecoder *dec);
 int32_t ob_decoder_kernel_ms(ObDecoder *dec, float ms[3]);
 int64_t ob_decoder_launches(const ObDecoder *dec);
 void *ob_decoder_cuda_stream(ObDecoder *dec);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Encoder.  Replaces, for a batch, the reference's opus_encoder_create / opus_encode_float / opus_encoder_ctl /
+ * opus_encoder_destroy (src/bindings.rs:293-346) as used by src/encoder.rs.
+ * Scope of this version: Fs = 48000, OPUS_APPLICATION_RESTRICTED_LOWDELAY (2051; the application that forces
+ * MODE_CELT_ONLY, opus/src/opus_encoder.c:1330-1332), frames of 120/240/480/960 samples.  The CELT encoder is complete
+ * (pitch pre-filter, transient/tf/spread/dynalloc/trim/stereo decisions, two-pass energy, PVQ search, theta RDO, CBR/VBR/
+ * CVBR); the Opus-layer tonality analysis (opus/src/analysis.c, active in the reference at complexity >= 7) is not
+ * computed, so packets are bit-identical to the reference's pure-C build at complexity <= 6 and decision-compatible above.
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct ObEncoder ObEncoder;
+
+/* n x opus_encoder_create(Fs, channels, application, &err) (src/bindings.rs:297-305; Encoder::new src/encoder.rs:40-73).
+ * Defaults as opus_encoder_init: VBR on, constrained, bitrate AUTO, complexity 9. */
+ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, int32_t application, int32_t device,
+                             int32_t max_frames, int32_t *error);
+/* opus_encoder_destroy (src/bindings.rs:335-338). */
+void ob_encoder_destroy(ObEncoder *enc);
+
+/* n x opus_encode_float(st, pcm, frame_size, data, max_data_bytes) (src/bindings.rs:325-334; Encoder::encode_float
+ * src/encoder.rs:215-247): one frame per stream.  pcm: host, [n_streams][frame_size*channels] interleaved floats in [-1,1];
+ * out: host, [n_streams][max_bytes]; lens_out[s]: packet length (TOC included) or a negative OPUS_* code. */
+int32_t ob_encode_float(ObEncoder *enc, const float *pcm, int32_t frame_size, uint8_t *out, int32_t max_bytes, int32_t *lens_out);
+/* n_frames consecutive frames per stream: pcm [n_streams][n_frames][frame_size*channels], out [n_streams][n_frames][max_bytes],
+ * lens_out / ranges_out [n_streams][n_frames] (ranges_out optional: OPUS_GET_FINAL_RANGE after each frame). */
+int32_t ob_encode_float_multi(ObEncoder *enc, int32_t n_frames, const float *pcm, int32_t frame_size, uint8_t *out,
+                              int32_t max_bytes, int32_t *lens_out, uint32_t *ranges_out);
+/* Same with DEVICE pointers; asynchronous on the encoder's stream unless sync != 0. */
+int32_t ob_encode_float_device(ObEncoder *enc, int32_t n_frames, const float *d_pcm, int32_t frame_size, uint8_t *d_out,
+                               int32_t max_bytes, int32_t *d_lens_out, uint32_t *d_ranges_out, int32_t sync);
+
+/* CTLs: opus_encoder_ctl(st, OPUS_SET_*_REQUEST, v) (src/bindings.rs:339-346) as wrapped by src/encoder.rs:545-652
+ * (set_bitrate, set_complexity, set_vbr, set_vbr_constraint, set_max_bandwidth, set_bandwidth, set_force_channels,
+ * set_packet_loss_perc, set_lsb_depth); one value for the whole batch.  bitrate: bits/s, -1000 = OPUS_AUTO, -1 = OPUS_BITRATE_MAX. */
+int32_t ob_encoder_set_bitrate(ObEncoder *enc, int32_t bitrate);
+int32_t ob_encoder_get_bitrate(ObEncoder *enc, int32_t *value);
+int32_t ob_encoder_set_complexity(ObEncoder *enc, int32_t complexity);
+int32_t ob_encoder_get_complexity(ObEncoder *enc, int32_t *value);
+int32_t ob_encoder_set_vbr(ObEncoder *enc, int32_t vbr);
+int32_t ob_encoder_get_vbr(ObEncoder *enc, int32_t *value);
+int32_t ob_encoder_set_vbr_constraint(ObEncoder *enc, int32_t cvbr);
+int32_t ob_encoder_get_vbr_constraint(ObEncoder *enc, int32_t *value);
+int32_t ob_encoder_set_max_bandwidth(ObEncoder *enc, int32_t bandwidth);
+int32_t ob_encoder_set_bandwidth(ObEncoder *enc, int32_t bandwidth);
+int32_t ob_encoder_set_force_channels(ObEncoder *enc, int32_t channels);
+int32_t ob_encoder_set_packet_loss_perc(ObEncoder *enc, int32_t percent);
+int32_t ob_encoder_set_lsb_depth(ObEncoder *enc, int32_t depth);
+/* OPUS_GET_FINAL_RANGE (Encoder::final_range src/encoder.rs:411-419) and OPUS_RESET_STATE (Encoder::reset :689-698). */
+int32_t ob_encoder_final_range(ObEncoder *enc, uint32_t *out);
+int32_t ob_encoder_reset(ObEncoder *enc, const int32_t *idx, int32_t n);
+int32_t ob_encoder_streams(const ObEncoder *enc);
+int32_t ob_encoder_channels(const ObEncoder *enc);
+int32_t ob_encoder_kernel_ms(ObEncoder *enc, float *ms);
+int64_t ob_encoder_launches(const ObEncoder *enc);
+void *ob_encoder_cuda_stream(ObEncoder *enc);
 
 /* Static helpers mirroring src/packet.rs (packet_get_* on the TOC byte; opus/src/opus_decoder.c:1083-1129). */
 int32_t ob_packet_get_nb_channels(const uint8_t *packet);

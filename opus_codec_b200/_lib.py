@@ -10,8 +10,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libopus_b200.so")
 SRC = os.path.join(HERE, "csrc", "opus_b200.cu")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+SRC_ENC = os.path.join(HERE, "csrc", "opus_b200_enc.cu")       # compiled with -fmad=false (see the file header)
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 # Every symbol include/opus_b200.h declares (tests check that the library exports all of them).
 SYMBOLS = [
@@ -20,6 +20,12 @@ SYMBOLS = [
     "ob_decoder_channels", "ob_decoder_kernel_ms", "ob_decoder_launches", "ob_decoder_cuda_stream",
     "ob_packet_get_nb_channels", "ob_packet_get_samples_per_frame", "ob_packet_get_bandwidth", "ob_packet_get_nb_frames",
     "ob_version", "ob_strerror",
+    "ob_encoder_create", "ob_encoder_destroy", "ob_encode_float", "ob_encode_float_multi", "ob_encode_float_device",
+    "ob_encoder_set_bitrate", "ob_encoder_get_bitrate", "ob_encoder_set_complexity", "ob_encoder_get_complexity",
+    "ob_encoder_set_vbr", "ob_encoder_get_vbr", "ob_encoder_set_vbr_constraint", "ob_encoder_get_vbr_constraint",
+    "ob_encoder_set_max_bandwidth", "ob_encoder_set_bandwidth", "ob_encoder_set_force_channels",
+    "ob_encoder_set_packet_loss_perc", "ob_encoder_set_lsb_depth", "ob_encoder_final_range", "ob_encoder_reset",
+    "ob_encoder_streams", "ob_encoder_channels", "ob_encoder_kernel_ms", "ob_encoder_launches", "ob_encoder_cuda_stream",
 ]
 
 _lib = None
@@ -31,8 +37,14 @@ def build(verbose=False):
     if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(s) for s in srcs):
         return SO
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, SRC]
-    subprocess.run(cmd, check=True)
+    extra = ["-Xptxas", "-v"] if verbose else []
+    o_dec, o_enc = os.path.join(HERE, "opus_b200.o"), os.path.join(HERE, "opus_b200_enc.o")
+    procs = [subprocess.Popen([nvcc] + NVCC_FLAGS + extra + ["-c", "-o", o_dec, SRC]),
+             subprocess.Popen([nvcc] + NVCC_FLAGS + extra + ["-fmad=false", "-c", "-o", o_enc, SRC_ENC])]
+    for p in procs:
+        if p.wait() != 0:
+            raise RuntimeError("nvcc failed")
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO, o_dec, o_enc], check=True)
     return SO
 
 
@@ -62,6 +74,23 @@ def lib():
         getattr(L, n).argtypes = [vp]; getattr(L, n).restype = i32
     L.ob_packet_get_samples_per_frame.argtypes = [vp, i32]; L.ob_packet_get_samples_per_frame.restype = i32
     L.ob_packet_get_nb_frames.argtypes = [vp, i32]; L.ob_packet_get_nb_frames.restype = i32
+    L.ob_encoder_create.argtypes = [i32, i32, i32, i32, i32, i32, i32p]; L.ob_encoder_create.restype = vp
+    L.ob_encoder_destroy.argtypes = [vp]; L.ob_encoder_destroy.restype = None
+    L.ob_encode_float.argtypes = [vp, vp, i32, vp, i32, vp]; L.ob_encode_float.restype = i32
+    L.ob_encode_float_multi.argtypes = [vp, i32, vp, i32, vp, i32, vp, vp]; L.ob_encode_float_multi.restype = i32
+    L.ob_encode_float_device.argtypes = [vp, i32, vp, i32, vp, i32, vp, vp, i32]; L.ob_encode_float_device.restype = i32
+    for n in ("bitrate", "complexity", "vbr", "vbr_constraint"):
+        getattr(L, "ob_encoder_set_" + n).argtypes = [vp, i32]; getattr(L, "ob_encoder_set_" + n).restype = i32
+        getattr(L, "ob_encoder_get_" + n).argtypes = [vp, i32p]; getattr(L, "ob_encoder_get_" + n).restype = i32
+    for n in ("max_bandwidth", "bandwidth", "force_channels", "packet_loss_perc", "lsb_depth"):
+        getattr(L, "ob_encoder_set_" + n).argtypes = [vp, i32]; getattr(L, "ob_encoder_set_" + n).restype = i32
+    L.ob_encoder_final_range.argtypes = [vp, vp]; L.ob_encoder_final_range.restype = i32
+    L.ob_encoder_reset.argtypes = [vp, vp, i32]; L.ob_encoder_reset.restype = i32
+    L.ob_encoder_streams.argtypes = [vp]; L.ob_encoder_streams.restype = i32
+    L.ob_encoder_channels.argtypes = [vp]; L.ob_encoder_channels.restype = i32
+    L.ob_encoder_kernel_ms.argtypes = [vp, f32p]; L.ob_encoder_kernel_ms.restype = i32
+    L.ob_encoder_launches.argtypes = [vp]; L.ob_encoder_launches.restype = C.c_int64
+    L.ob_encoder_cuda_stream.argtypes = [vp]; L.ob_encoder_cuda_stream.restype = vp
     L.ob_version.restype = C.c_char_p
     L.ob_strerror.argtypes = [i32]; L.ob_strerror.restype = C.c_char_p
     _lib = L

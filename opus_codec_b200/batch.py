@@ -131,3 +131,122 @@ class BatchDecoder:
 
 def version():
     return _lib.lib().ob_version().decode()
+
+
+APPLICATION_VOIP, APPLICATION_AUDIO, APPLICATION_RESTRICTED_LOWDELAY = 2048, 2049, 2051      # src/types.rs Application
+BITRATE_AUTO, BITRATE_MAX = -1000, -1                                                       # src/types.rs Bitrate
+BANDWIDTH_NARROWBAND, BANDWIDTH_WIDEBAND, BANDWIDTH_SUPERWIDEBAND, BANDWIDTH_FULLBAND = 1101, 1103, 1104, 1105
+
+
+class BatchEncoder:
+    """n_streams independent 48 kHz CELT-only Opus encoders on one B200 (mirror of Encoder, reference src/encoder.rs:40-699).
+    CTLs apply to the whole batch."""
+
+    def __init__(self, n_streams, sample_rate=48000, channels=1, application=APPLICATION_RESTRICTED_LOWDELAY, device=0, max_frames=1):
+        self._L = _lib.lib()
+        err = C.c_int32(0)
+        self._h = self._L.ob_encoder_create(n_streams, sample_rate, channels, application, device, max_frames, C.byref(err))
+        if not self._h:
+            raise OpusError(err.value)
+        self.n_streams, self.channels, self.sample_rate, self.max_frames, self.device = n_streams, channels, sample_rate, max_frames, device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ob_encoder_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- CTLs (src/encoder.rs:545-652) ------------------------------------------------------------------------------
+    def set_bitrate(self, bitrate):
+        _check(self._L.ob_encoder_set_bitrate(self._h, int(bitrate)))
+
+    def bitrate(self):
+        v = C.c_int32(0); _check(self._L.ob_encoder_get_bitrate(self._h, C.byref(v))); return v.value
+
+    def set_complexity(self, c):
+        _check(self._L.ob_encoder_set_complexity(self._h, int(c)))
+
+    def complexity(self):
+        v = C.c_int32(0); _check(self._L.ob_encoder_get_complexity(self._h, C.byref(v))); return v.value
+
+    def set_vbr(self, on):
+        _check(self._L.ob_encoder_set_vbr(self._h, int(bool(on))))
+
+    def vbr(self):
+        v = C.c_int32(0); _check(self._L.ob_encoder_get_vbr(self._h, C.byref(v))); return bool(v.value)
+
+    def set_vbr_constraint(self, on):
+        _check(self._L.ob_encoder_set_vbr_constraint(self._h, int(bool(on))))
+
+    def vbr_constraint(self):
+        v = C.c_int32(0); _check(self._L.ob_encoder_get_vbr_constraint(self._h, C.byref(v))); return bool(v.value)
+
+    def set_max_bandwidth(self, bw):
+        _check(self._L.ob_encoder_set_max_bandwidth(self._h, int(bw)))
+
+    def set_bandwidth(self, bw):
+        _check(self._L.ob_encoder_set_bandwidth(self._h, int(bw)))
+
+    def set_force_channels(self, ch):
+        _check(self._L.ob_encoder_set_force_channels(self._h, int(ch)))
+
+    def set_packet_loss_perc(self, p):
+        _check(self._L.ob_encoder_set_packet_loss_perc(self._h, int(p)))
+
+    def set_lsb_depth(self, d):
+        _check(self._L.ob_encoder_set_lsb_depth(self._h, int(d)))
+
+    # -- encode ------------------------------------------------------------------------------------------------------
+    def encode_float_multi(self, pcm, frame_size, max_bytes=1276):
+        """pcm: f32 [S, F, frame_size*channels] in [-1,1].  Returns (packets u8 [S, F, max_bytes], lens i32 [S, F], ranges u32 [S, F]);
+        lens < 0 are OPUS_* codes for that (stream, frame)."""
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        if pcm.ndim != 3 or pcm.shape[0] != self.n_streams or pcm.shape[2] != frame_size * self.channels:
+            raise OpusError(BAD_ARG)
+        S, F = pcm.shape[:2]
+        out = np.zeros((S, F, max_bytes), np.uint8)
+        lens = np.zeros((S, F), np.int32)
+        ranges = np.zeros((S, F), np.uint32)
+        _check(self._L.ob_encode_float_multi(self._h, F, _vp(pcm), frame_size, _vp(out), max_bytes, _vp(lens), _vp(ranges)))
+        return out, lens, ranges
+
+    def encode_float(self, pcm, max_bytes=1276):
+        """pcm: f32 [S, frame_size*channels]; frame_size = input.len()/channels as in Encoder::encode_float (src/encoder.rs:215-247).
+        Returns a list of bytes objects (one packet per stream) and the i32 length/status array."""
+        pcm = np.ascontiguousarray(pcm, np.float32)
+        if pcm.ndim != 2 or pcm.shape[1] % self.channels:
+            raise OpusError(BAD_ARG)
+        frame_size = pcm.shape[1] // self.channels
+        out, lens, _ = self.encode_float_multi(pcm[:, None, :], frame_size, max_bytes)
+        return [bytes(out[s, 0, :max(0, lens[s, 0])]) for s in range(self.n_streams)], lens[:, 0]
+
+    def final_range(self):
+        out = np.zeros(self.n_streams, np.uint32)
+        _check(self._L.ob_encoder_final_range(self._h, _vp(out)))
+        return out
+
+    def reset(self, streams=None):
+        if streams is None:
+            _check(self._L.ob_encoder_reset(self._h, None, 0))
+        else:
+            idx = np.ascontiguousarray(streams, np.int32)
+            _check(self._L.ob_encoder_reset(self._h, _vp(idx), idx.size))
+
+    def kernel_ms(self):
+        ms = C.c_float(0)
+        _check(self._L.ob_encoder_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def launches(self):
+        return int(self._L.ob_encoder_launches(self._h))
+
+    @property
+    def handle(self):
+        return self._h

@@ -18,7 +18,7 @@
 #ifdef __CUDACC__
 #define OB_DEV __device__ __forceinline__
 #define OB_MEM __device__ __forceinline__
-#define OB_DEV_NOINLINE __device__ __noinline__
+#define OB_DEV_NOINLINE static __device__ __noinline__
 #define OB_TABLE(type, name, n) static __device__ const type name[n]
 #define OB_CLZ(x) __clz((int)(x))
 #else

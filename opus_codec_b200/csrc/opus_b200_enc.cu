@@ -1,0 +1,237 @@
+// opus_b200_enc.cu -- batched CELT-only Opus ENCODER for sm_100a: kernel + C ABI (include/opus_b200.h, ob_encoder_*).
+//
+// First GPU mapping of the encoder: ONE THREAD PER STREAM runs the whole per-stream encoder (enc_*.cuh) for the F frames
+// of a call, state and working buffers in global memory.  This translation unit is compiled with -fmad=false so that the
+// float decision heuristics round exactly like the reference's C code (a fused multiply-add changes e.g. which pitch lag
+// or which PVQ pulse wins); the decoder TU keeps FMA contraction.  Streams are independent: no collective, one ObEncoder
+// per GPU over disjoint stream ranges.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <new>
+
+#include "../../include/opus_b200.h"
+#include "enc_frame.cuh"
+
+struct ObEncStream {           // everything one stream owns on the device
+    ObOpusEncState os;
+    ObEncState st;
+};
+
+#define OB_ENC_THREADS 32
+__global__ void __launch_bounds__(OB_ENC_THREADS)
+ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *__restrict__ lens, uint32_t *__restrict__ ranges,
+            ObEncStream *__restrict__ streams, ObEncScratch *__restrict__ scratch, ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    ObEncStream &es = streams[s];
+    ObEncScratch &sc = scratch[s];
+    const int CC = es.st.channels;
+    for (int f = 0; f < F; f++) {
+        const size_t w = (size_t)s * F + f;
+        const int n = ob_opus_encode(cfg, es.os, es.st, sc, pcm + w * (size_t)frame_size * CC, frame_size, out + w * (size_t)max_bytes, max_bytes);
+        lens[w] = n;
+        if (ranges) ranges[w] = n > 0 ? es.st.final_range : 0;
+    }
+}
+
+__global__ void ob_k_enc_reset(ObEncStream *streams, const int32_t *idx, int n, int S, int channels)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int s = idx ? idx[k] : k;
+    if (s < 0 || s >= S) return;
+    ObEncStream &es = streams[s];
+    es.st.channels = es.st.stream_channels = channels; es.st.end = 21; es.st.clip = 1; es.st.force_intra = 0; es.st.disable_inv = 0; es.st.disable_pf = 0;
+    ob_enc_reset(es.st);
+    es.os.stream_channels = channels; es.os.first = 1; es.os.auto_bandwidth = 0; es.os.bandwidth = 1105; es.os.hybrid_stereo_width_Q14 = 1 << 14;
+}
+
+__global__ void ob_k_enc_gather(const ObEncStream *streams, uint32_t *ranges, int S)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) ranges[s] = streams[s].st.final_range;
+}
+
+struct ObEncoder {
+    int S, CC, device, max_frames;
+    ObOpusEncCfg cfg;
+    cudaStream_t stream;
+    cudaEvent_t ev[2];
+    bool timed;
+    ObEncStream *d_streams;
+    ObEncScratch *d_scratch;
+    float *d_pcm; size_t pcm_cap;
+    uint8_t *d_out; size_t out_cap;
+    int32_t *d_lens; uint32_t *d_ranges;
+    int64_t launches;
+};
+
+#define OB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "opus_b200: %s failed: %s\n", #x, cudaGetErrorString(e_)); return OB_INTERNAL_ERROR; } } while (0)
+
+extern "C" {
+
+ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, int32_t application, int32_t device, int32_t max_frames, int32_t *error)
+{
+    int err = OB_OK, ndev = 0;
+    ObEncoder *e = nullptr;
+    if (n_streams <= 0 || (channels != 1 && channels != 2) || max_frames <= 0) err = OB_BAD_ARG;
+    else if (application != 2048 && application != 2049 && application != 2051) err = OB_BAD_ARG;
+    else if (fs != 48000 || application != 2051) err = OB_UNIMPLEMENTED;    // VOIP/AUDIO need the SILK/hybrid mode decision + 4 ms delay buffer
+    else if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        fprintf(stderr, "opus_b200: no usable CUDA device (count=%d, requested=%d); there is no CPU fallback\n", ndev, device);
+        err = OB_INTERNAL_ERROR;
+    }
+    if (err == OB_OK) { e = new (std::nothrow) ObEncoder(); if (!e) err = OB_ALLOC_FAIL; }
+    if (err == OB_OK) {
+        memset(e, 0, sizeof(*e));
+        e->S = n_streams; e->CC = channels; e->device = device; e->max_frames = max_frames;
+        // defaults of opus_encoder_init (opus_encoder.c:202-297): VBR on, constrained, bitrate AUTO, complexity 9, 24-bit depth
+        e->cfg.bitrate = -1000; e->cfg.complexity = 9; e->cfg.vbr = 1; e->cfg.vbr_constraint = 1; e->cfg.max_bandwidth = 1105;
+        e->cfg.user_bandwidth = 0; e->cfg.force_channels = 0; e->cfg.packet_loss = 0; e->cfg.lsb_depth = 24;
+        const size_t total = (size_t)n_streams * max_frames;
+        bool ok = cudaSetDevice(device) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreate(&e->ev[0]) == cudaSuccess && cudaEventCreate(&e->ev[1]) == cudaSuccess;
+        ok = ok && cudaMalloc(&e->d_streams, sizeof(ObEncStream) * n_streams) == cudaSuccess;
+        ok = ok && cudaMalloc(&e->d_scratch, sizeof(ObEncScratch) * n_streams) == cudaSuccess;
+        ok = ok && cudaMalloc(&e->d_lens, sizeof(int32_t) * total) == cudaSuccess;
+        ok = ok && cudaMalloc(&e->d_ranges, sizeof(uint32_t) * total) == cudaSuccess;
+        // the per-thread encoder recurses (quant_partition, <= 5 deep) and keeps band-sized arrays on its stack
+        ok = ok && cudaDeviceSetLimit(cudaLimitStackSize, 24 * 1024) == cudaSuccess;
+        if (!ok) {
+            fprintf(stderr, "opus_b200: device allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
+            ob_encoder_destroy(e); e = nullptr; err = OB_ALLOC_FAIL;
+        } else if (ob_encoder_reset(e, nullptr, 0) != OB_OK) { ob_encoder_destroy(e); e = nullptr; err = OB_INTERNAL_ERROR; }
+    }
+    if (error) *error = err;
+    return e;
+}
+
+void ob_encoder_destroy(ObEncoder *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_streams); cudaFree(e->d_scratch); cudaFree(e->d_pcm); cudaFree(e->d_out); cudaFree(e->d_lens); cudaFree(e->d_ranges);
+    for (int i = 0; i < 2; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int32_t ob_encoder_reset(ObEncoder *e, const int32_t *idx, int32_t n)
+{
+    if (!e || n < 0) return OB_BAD_ARG;
+    OB_CUDA(cudaSetDevice(e->device));
+    int32_t *d_idx = nullptr;
+    int count = e->S;
+    if (idx) {
+        if (n == 0) return OB_OK;
+        count = n;
+        OB_CUDA(cudaMalloc(&d_idx, sizeof(int32_t) * n));
+        OB_CUDA(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
+    }
+    ob_k_enc_reset<<<(count + 63) / 64, 64, 0, e->stream>>>(e->d_streams, d_idx, count, e->S, e->CC);
+    e->launches += 1;
+    OB_CUDA(cudaStreamSynchronize(e->stream));
+    if (d_idx) cudaFree(d_idx);
+    return OB_OK;
+}
+
+// CTLs (src/encoder.rs:545-652): one value for the whole batch.
+int32_t ob_encoder_set_bitrate(ObEncoder *e, int32_t bitrate)
+{
+    if (!e) return OB_BAD_ARG;
+    if (bitrate != -1000 && bitrate != -1) {                   // opus_encoder.c OPUS_SET_BITRATE_REQUEST: clamp to [500, 300000*channels]
+        if (bitrate <= 0) return OB_BAD_ARG;
+        if (bitrate <= 500) bitrate = 500;
+        else if (bitrate > 300000 * e->CC) bitrate = 300000 * e->CC;
+    }
+    e->cfg.bitrate = bitrate;
+    return OB_OK;
+}
+int32_t ob_encoder_get_bitrate(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.bitrate; return OB_OK; }
+int32_t ob_encoder_set_complexity(ObEncoder *e, int32_t c) { if (!e || c < 0 || c > 10) return OB_BAD_ARG; e->cfg.complexity = c; return OB_OK; }
+int32_t ob_encoder_get_complexity(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.complexity; return OB_OK; }
+int32_t ob_encoder_set_vbr(ObEncoder *e, int32_t v) { if (!e || v < 0 || v > 1) return OB_BAD_ARG; e->cfg.vbr = v; return OB_OK; }
+int32_t ob_encoder_get_vbr(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.vbr; return OB_OK; }
+int32_t ob_encoder_set_vbr_constraint(ObEncoder *e, int32_t v) { if (!e || v < 0 || v > 1) return OB_BAD_ARG; e->cfg.vbr_constraint = v; return OB_OK; }
+int32_t ob_encoder_get_vbr_constraint(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.vbr_constraint; return OB_OK; }
+int32_t ob_encoder_set_max_bandwidth(ObEncoder *e, int32_t bw) { if (!e || bw < 1101 || bw > 1105) return OB_BAD_ARG; e->cfg.max_bandwidth = bw; return OB_OK; }
+int32_t ob_encoder_set_bandwidth(ObEncoder *e, int32_t bw) { if (!e || (bw != -1000 && (bw < 1101 || bw > 1105))) return OB_BAD_ARG; e->cfg.user_bandwidth = bw == -1000 ? 0 : bw; return OB_OK; }
+int32_t ob_encoder_set_force_channels(ObEncoder *e, int32_t ch) { if (!e || (ch != -1000 && (ch < 1 || ch > e->CC))) return OB_BAD_ARG; e->cfg.force_channels = ch == -1000 ? 0 : ch; return OB_OK; }
+int32_t ob_encoder_set_packet_loss_perc(ObEncoder *e, int32_t p) { if (!e || p < 0 || p > 100) return OB_BAD_ARG; e->cfg.packet_loss = p; return OB_OK; }
+int32_t ob_encoder_set_lsb_depth(ObEncoder *e, int32_t d) { if (!e || d < 8 || d > 24) return OB_BAD_ARG; e->cfg.lsb_depth = d; return OB_OK; }
+
+static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size, uint8_t *d_out, int max_bytes, int32_t *d_lens, uint32_t *d_ranges)
+{
+    OB_CUDA(cudaEventRecord(e->ev[0], e->stream));
+    ob_k_encode<<<(e->S + OB_ENC_THREADS - 1) / OB_ENC_THREADS, OB_ENC_THREADS, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->d_scratch,
+                                                                                             e->cfg, e->S, F, frame_size, max_bytes);
+    OB_CUDA(cudaEventRecord(e->ev[1], e->stream));
+    OB_CUDA(cudaGetLastError());
+    e->launches += 1;
+    e->timed = true;
+    return OB_OK;
+}
+
+int32_t ob_encode_float_device(ObEncoder *e, int32_t n_frames, const float *d_pcm, int32_t frame_size, uint8_t *d_out, int32_t max_bytes,
+                               int32_t *d_lens_out, uint32_t *d_ranges_out, int32_t sync)
+{
+    if (!e || !d_pcm || !d_out || !d_lens_out || n_frames <= 0 || n_frames > e->max_frames || max_bytes <= 0) return OB_BAD_ARG;
+    OB_CUDA(cudaSetDevice(e->device));
+    const int r = ob_enc_launch(e, n_frames, d_pcm, frame_size, d_out, max_bytes, d_lens_out, d_ranges_out);
+    if (r != OB_OK) return r;
+    if (sync) OB_CUDA(cudaStreamSynchronize(e->stream));
+    return OB_OK;
+}
+
+int32_t ob_encode_float_multi(ObEncoder *e, int32_t n_frames, const float *pcm, int32_t frame_size, uint8_t *out, int32_t max_bytes,
+                              int32_t *lens_out, uint32_t *ranges_out)
+{
+    if (!e || !pcm || !out || !lens_out || n_frames <= 0 || n_frames > e->max_frames || max_bytes <= 0 || frame_size <= 0) return OB_BAD_ARG;
+    OB_CUDA(cudaSetDevice(e->device));
+    const size_t total = (size_t)e->S * n_frames, pcm_floats = total * (size_t)frame_size * e->CC, out_bytes = total * (size_t)max_bytes;
+    if (pcm_floats > e->pcm_cap) { cudaFree(e->d_pcm); e->d_pcm = nullptr; e->pcm_cap = 0; OB_CUDA(cudaMalloc(&e->d_pcm, pcm_floats * sizeof(float))); e->pcm_cap = pcm_floats; }
+    if (out_bytes > e->out_cap) { cudaFree(e->d_out); e->d_out = nullptr; e->out_cap = 0; OB_CUDA(cudaMalloc(&e->d_out, out_bytes)); e->out_cap = out_bytes; }
+    OB_CUDA(cudaMemcpyAsync(e->d_pcm, pcm, pcm_floats * sizeof(float), cudaMemcpyHostToDevice, e->stream));
+    const int r = ob_enc_launch(e, n_frames, e->d_pcm, frame_size, e->d_out, max_bytes, e->d_lens, e->d_ranges);
+    if (r != OB_OK) return r;
+    OB_CUDA(cudaMemcpyAsync(out, e->d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+    OB_CUDA(cudaMemcpyAsync(lens_out, e->d_lens, total * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+    if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out, e->d_ranges, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    OB_CUDA(cudaStreamSynchronize(e->stream));
+    return OB_OK;
+}
+
+int32_t ob_encode_float(ObEncoder *e, const float *pcm, int32_t frame_size, uint8_t *out, int32_t max_bytes, int32_t *lens_out)
+{
+    return ob_encode_float_multi(e, 1, pcm, frame_size, out, max_bytes, lens_out, nullptr);
+}
+
+int32_t ob_encoder_final_range(ObEncoder *e, uint32_t *out)
+{
+    if (!e || !out) return OB_BAD_ARG;
+    OB_CUDA(cudaSetDevice(e->device));
+    ob_k_enc_gather<<<(e->S + 127) / 128, 128, 0, e->stream>>>(e->d_streams, e->d_ranges, e->S);
+    e->launches += 1;
+    OB_CUDA(cudaMemcpyAsync(out, e->d_ranges, sizeof(uint32_t) * e->S, cudaMemcpyDeviceToHost, e->stream));
+    OB_CUDA(cudaStreamSynchronize(e->stream));
+    return OB_OK;
+}
+
+int32_t ob_encoder_streams(const ObEncoder *e) { return e ? e->S : OB_BAD_ARG; }
+int32_t ob_encoder_channels(const ObEncoder *e) { return e ? e->CC : OB_BAD_ARG; }
+int64_t ob_encoder_launches(const ObEncoder *e) { return e ? e->launches : 0; }
+void *ob_encoder_cuda_stream(ObEncoder *e) { return e ? (void *)e->stream : nullptr; }
+int32_t ob_encoder_kernel_ms(ObEncoder *e, float *ms)
+{
+    if (!e || !ms || !e->timed) return OB_BAD_ARG;
+    OB_CUDA(cudaSetDevice(e->device));
+    OB_CUDA(cudaEventSynchronize(e->ev[1]));
+    OB_CUDA(cudaEventElapsedTime(ms, e->ev[0], e->ev[1]));
+    return OB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+"""GPU parity tests of the batched encoder, through the C ABI.
+
+Gates (BASELINE.json north_star): the REFERENCE decoder must accept every GPU-encoded packet and its
+OPUS_GET_FINAL_RANGE must equal the GPU encoder's; packets are compared byte for byte with the reference encoder's
+pure-C build (oracle/_ref/libopus_ref_c.so) -- identical at complexity <= 6, where the reference runs no tonality analysis;
+round-trip audio is compared with the reference encoder's round trip."""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from opus_codec_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_c_encode(pcm, fs, ch, br, vbr, cx):
+    from oracle import refpy
+    L = refpy.lib_c()
+    u8p, i32p, u32p, f32p = (C.POINTER(C.c_ubyte), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_float))
+    L.ref_encode_stream.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, i32p, u32p]
+    pcm = np.ascontiguousarray(pcm, np.float32)
+    nf = pcm.size // (fs * ch)
+    out = np.zeros((nf, 1276), np.uint8); lens = np.zeros(nf, np.int32); rng = np.zeros(nf, np.uint32)
+    r = L.ref_encode_stream(pcm.ctypes.data_as(f32p), nf, fs, ch, 2051, br, vbr, cx, out.ctypes.data_as(u8p), 1276, lens.ctypes.data_as(i32p), rng.ctypes.data_as(u32p))
+    assert r == 0
+    return out, lens, rng
+
+
+def _gpu_encode(pcm_batch, fs, ch, br, vbr, cx):
+    from opus_codec_b200.batch import BatchEncoder
+    S = pcm_batch.shape[0]
+    F = pcm_batch.shape[1] // (fs * ch)
+    with BatchEncoder(S, 48000, ch, device=0, max_frames=F) as enc:
+        enc.set_bitrate(br); enc.set_complexity(cx); enc.set_vbr(vbr != 0); enc.set_vbr_constraint(vbr == 2)
+        assert enc.bitrate() == br and enc.complexity() == cx and enc.vbr() == (vbr != 0)
+        out, lens, rng = enc.encode_float_multi(pcm_batch.reshape(S, F, fs * ch), fs)
+        assert (enc.final_range() == rng[:, -1]).all()
+    return out, lens, rng
+
+
+CONFIGS = [(1, 64000, 960, 0, 5), (2, 96000, 960, 0, 6), (2, 96000, 960, 1, 5), (1, 24000, 480, 2, 6), (2, 64000, 240, 0, 5),
+           (1, 48000, 120, 0, 4), (2, 24000, 960, 0, 3), (1, 12000, 960, 0, 6), (2, 128000, 960, 0, 0)]
+
+
+@pytest.mark.parametrize("ch,br,fs,vbr,cx", CONFIGS)
+def test_packets_match_reference_encoder_and_decode_with_reference_decoder(ch, br, fs, vbr, cx):
+    from oracle import refpy
+    S, seconds = 6, 1
+    pcm = np.stack([synth.stream_pcm(s, 48000 * seconds, ch, base_seed=777) for s in range(S)])
+    out, lens, rng = _gpu_encode(pcm, fs, ch, br, vbr, cx)
+    assert (lens > 0).all()
+    ident = []
+    for s in range(S):
+        ro, rl, rr = _ref_c_encode(pcm[s], fs, ch, br, vbr, cx)
+        ident.append(((ro == out[s]).all(axis=1) & (rl == lens[s])).mean())
+        dec_pcm, dec_rng, smp = refpy.decode_stream(out[s], lens[s], fs, ch)          # the REFERENCE decoder takes our packets
+        assert (smp == fs).all()
+        assert (dec_rng == rng[s]).all(), "encoder final range != reference decoder final range"
+    # no tonality analysis below complexity 7: the encoders must agree byte for byte (device libm may flip a rare decision)
+    assert np.mean(ident) >= 0.97, ident
+
+
+def test_complexity10_stereo_roundtrip_quality_and_final_range():
+    """BASELINE config 3 settings (stereo, complexity 10, 20 ms, 96 kb/s CBR)."""
+    from oracle import refpy
+    ch, br, fs = 2, 96000, 960
+    S = 6
+    pcm = np.stack([synth.stream_pcm(s, 48000 * 2, ch, base_seed=4242) for s in range(S)])
+    out, lens, rng = _gpu_encode(pcm, fs, ch, br, 0, 10)
+    assert (lens == 240).all()
+    for s in range(S):
+        ours, dec_rng, _ = refpy.decode_stream(out[s], lens[s], fs, ch)
+        assert (dec_rng == rng[s]).all()
+        ro, rl, _ = refpy.encode_stream(pcm[s], fs, ch, br, vbr=0, complexity=10)
+        theirs, _, _ = refpy.decode_stream(ro, rl, fs, ch)
+        # both round trips are lossy versions of pcm[s]; ours must be as close to the original as the reference's (within 1 dB)
+        def snr(x):
+            n = min(len(x), pcm[s].size) - 960 * ch
+            e = x.reshape(-1)[:n] - 0  # aligned: restricted low-delay has no look-ahead beyond the 2.5 ms overlap handled by the codec
+            return e
+        a, b, o = ours.reshape(-1), theirs.reshape(-1), pcm[s]
+        lag = 120 * ch                       # CELT's algorithmic delay: 2.5 ms
+        err_a = a[lag:] - o[:-lag]; err_b = b[lag:] - o[:-lag]
+        snr_a = 10 * np.log10(np.sum(o ** 2) / np.sum(err_a ** 2)); snr_b = 10 * np.log10(np.sum(o ** 2) / np.sum(err_b ** 2))
+        assert snr_a >= snr_b - 1.0, (s, snr_a, snr_b)
+
+
+def test_encoder_ctl_validation_and_reset():
+    from opus_codec_b200.batch import BatchEncoder, OpusError, BAD_ARG, UNIMPLEMENTED
+    with pytest.raises(OpusError) as e:
+        BatchEncoder(4, 48000, 1, application=2049)                  # AUDIO: not on this path
+    assert e.value.code == UNIMPLEMENTED
+    with BatchEncoder(3, 48000, 1, device=0, max_frames=4) as enc:
+        for bad in (lambda: enc.set_complexity(11), lambda: enc.set_bitrate(0), lambda: enc.set_max_bandwidth(7)):
+            with pytest.raises(OpusError) as e:
+                bad()
+            assert e.value.code == BAD_ARG
+        enc.set_bitrate(64000); enc.set_vbr(False); enc.set_complexity(5)
+        pcm = np.stack([synth.stream_pcm(s, 960 * 4, 1) for s in range(3)]).reshape(3, 4, 960)
+        a, la, ra = enc.encode_float_multi(pcm, 960)
+        enc.reset()
+        b, lb, rb = enc.encode_float_multi(pcm, 960)
+        assert np.array_equal(a, b) and np.array_equal(ra, rb)       # OPUS_RESET_STATE restarts every stream
+        pk, ln = enc.encode_float(pcm[:, 0])
+        assert all(len(p) == 160 for p in pk) and (ln == 160).all()
+
+
+def test_transcode_decode_then_encode_on_gpu():
+    """BASELINE config 5 in miniature: GPU decode -> GPU encode, both ends checked against the reference."""
+    from conftest import load_golden
+    from opus_codec_b200.batch import BatchDecoder
+    from oracle import refpy
+    g = load_golden("cfg3_stereo_20ms_96k_cbr")
+    S, F, stride = g["packets"].shape
+    offsets = (np.arange(S * F, dtype=np.int32) * stride).reshape(S, F)
+    with BatchDecoder(S, 48000, 2, device=0, max_frames=F) as dec:
+        pcm, smp, _ = dec.decode_float_multi(g["packets"].reshape(-1), offsets, g["lens"], 960)
+    out, lens, rng = _gpu_encode(pcm.reshape(S, -1), 960, 2, 96000, 0, 5)
+    for s in range(S):
+        ro, rl, rr = _ref_c_encode(pcm[s].reshape(-1), 960, 2, 96000, 0, 5)
+        assert ((ro == out[s]).all(axis=1)).mean() >= 0.97
+        _, dec_rng, _ = refpy.decode_stream(out[s], lens[s], 960, 2)
+        assert (dec_rng == rng[s]).all()
