@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <new>
 
 #include "../../include/opus_b200.h"
@@ -28,7 +29,10 @@ ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *_
     ObEncStream &es = streams[s];
     ObEncScratch &sc = scratch[s];
     const int CC = es.st.channels;
-    for (int f = 0; f < F; f++) {
+    // NOTE: the frame counter is deliberately volatile.  The loop body is one huge divergent region; with a plain `int f`
+    // nvcc 12.9 keeps f in a UNIFORM register, and lanes that fall behind re-execute the shared increment -- frames get
+    // skipped / mis-indexed whenever lanes of a warp diverge (found on B200: fine with 1-4 identical lanes, wrong with 5+).
+    for (volatile int f = 0; f < F; f++) {
         const size_t w = (size_t)s * F + f;
         const int n = ob_opus_encode(cfg, es.os, es.st, sc, pcm + w * (size_t)frame_size * CC, frame_size, out + w * (size_t)max_bytes, max_bytes);
         lens[w] = n;
@@ -99,7 +103,9 @@ ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         ok = ok && cudaMalloc(&e->d_lens, sizeof(int32_t) * total) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_ranges, sizeof(uint32_t) * total) == cudaSuccess;
         // the per-thread encoder recurses (quant_partition, <= 5 deep) and keeps band-sized arrays on its stack
-        ok = ok && cudaDeviceSetLimit(cudaLimitStackSize, 24 * 1024) == cudaSuccess;
+        size_t stack_bytes = 24 * 1024;
+        if (const char *v = getenv("OB_ENC_STACK_KB")) { const int t = atoi(v); if (t >= 4 && t <= 256) stack_bytes = (size_t)t * 1024; }   // debugging aid
+        ok = ok && cudaDeviceSetLimit(cudaLimitStackSize, stack_bytes) == cudaSuccess;
         if (!ok) {
             fprintf(stderr, "opus_b200: device allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
             ob_encoder_destroy(e); e = nullptr; err = OB_ALLOC_FAIL;
@@ -167,7 +173,9 @@ int32_t ob_encoder_set_lsb_depth(ObEncoder *e, int32_t d) { if (!e || d < 8 || d
 static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size, uint8_t *d_out, int max_bytes, int32_t *d_lens, uint32_t *d_ranges)
 {
     OB_CUDA(cudaEventRecord(e->ev[0], e->stream));
-    ob_k_encode<<<(e->S + OB_ENC_THREADS - 1) / OB_ENC_THREADS, OB_ENC_THREADS, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->d_scratch,
+    int bs = OB_ENC_THREADS;
+    if (const char *v = getenv("OB_ENC_BLOCK")) { const int t = atoi(v); if (t >= 1 && t <= OB_ENC_THREADS) bs = t; }   // debugging aid
+    ob_k_encode<<<(e->S + bs - 1) / bs, bs, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->d_scratch,
                                                                                              e->cfg, e->S, F, frame_size, max_bytes);
     OB_CUDA(cudaEventRecord(e->ev[1], e->stream));
     OB_CUDA(cudaGetLastError());
