@@ -106,6 +106,104 @@ def cpu_reference_run(nthreads, target_audio_s, F=50):
     return audio / secs, "%d streams x %d frames (%.0f audio-s) of the same packet pool, %d threads, %.2f s wall" % (ns, F, audio, nthreads, secs)
 
 
+ENC_STREAMS_PER_GPU = 16384
+ENC_WORKLOAD = "16384 stereo 48 kHz CELT-only encode streams per GPU, complexity 10, 20 ms @96 kb/s CBR (BASELINE configs[2])"
+
+
+def enc_algorithmic_bytes_per_frame(F, C=2, N=FRAME, P=240):
+    """B_enc = 4*C*N + P + S_enc/F; S_enc = per channel (4576 read + min(N,1024)*4+480 written) + energies 1344 + scalars 256."""
+    s_enc = C * (4576 + min(N, 1024) * 4 + 480) + 1344 + 256
+    return 4 * C * N + P + s_enc / F
+
+
+def enc_pcm(nstreams, F):
+    from opus_codec_b200 import synth
+    pool = np.stack([synth.stream_pcm(s, FRAME * F, 2, base_seed=31337) for s in range(64)])      # 64 distinct streams, tiled
+    return np.ascontiguousarray(pool[np.arange(nstreams) % 64]).reshape(nstreams, F, FRAME * 2)
+
+
+def cpu_reference_encode(nthreads, nstreams, F):
+    from oracle import refpy
+    pcm = enc_pcm(nstreams, F).reshape(nstreams, -1)
+    secs, _, lens, _ = refpy.encode_pool(pcm, FRAME, 2, 96000, 0, 10, nthreads, stride=256, want_packets=False)
+    assert (lens == 240).all()
+    audio = nstreams * F * 0.02
+    return audio / secs, "%d streams x %d frames (%.0f audio-s), %d threads, %.2f s wall" % (nstreams, F, audio, nthreads, secs)
+
+
+def run_encode_leg(args, L, local, world, rank, dev, barrier):
+    """Secondary measurement (BASELINE metric names both directions): batched encode, BASELINE configs[2]."""
+    import torch
+    from opus_codec_b200.batch import BatchEncoder
+    from opus_codec_b200.shard import max_over_ranks
+    S, F = ENC_STREAMS_PER_GPU, args.enc_frames
+    pcm = enc_pcm(S, F)
+    enc = BatchEncoder(S, 48000, 2, device=local, max_frames=F)
+    enc.set_bitrate(96000); enc.set_complexity(10); enc.set_vbr(False)
+    ext = torch.cuda.ExternalStream(L.ob_encoder_cuda_stream(enc.handle), device=local)
+    d_pcm = torch.from_numpy(pcm.reshape(-1)).to(dev)
+    d_out = torch.zeros(S * F * 256, dtype=torch.uint8, device=dev)
+    d_len = torch.zeros(S * F, dtype=torch.int32, device=dev)
+    d_rng = torch.zeros(S * F, dtype=torch.int32, device=dev)
+
+    def step():
+        r = L.ob_encode_float_device(enc.handle, F, d_pcm.data_ptr(), FRAME, d_out.data_ptr(), 256, d_len.data_ptr(), d_rng.data_ptr(), 0)
+        assert r == 0, r
+
+    step()
+    barrier()
+    steps = max(1, min(args.steps, 3))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    kms = 0.0
+    for _ in range(steps):
+        step()
+        kms += enc.kernel_ms()
+    e1.record(ext)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    assert (d_len.cpu().numpy() == 240).all()
+    # end to end: pinned host PCM in, packets + lengths + final ranges out
+    h_pcm = torch.from_numpy(pcm.reshape(-1).copy()).pin_memory()
+    h_out = torch.empty(S * F * 256, dtype=torch.uint8).pin_memory()
+    h_len = torch.empty(S * F, dtype=torch.int32).pin_memory()
+    h_rng = torch.empty(S * F, dtype=torch.int32).pin_memory()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(ext)
+    r = L.ob_encode_float_multi(enc.handle, F, h_pcm.data_ptr(), FRAME, h_out.data_ptr(), 256, h_len.data_ptr(), h_rng.data_ptr())
+    assert r == 0, r
+    f1.record(ext)
+    barrier()
+    ms_e2e = max_over_ranks(f0.elapsed_time(f1), dev)
+    launches = enc.launches()
+    enc.close()
+    audio = world * S * F * 0.02
+    res = {"workload": ENC_WORKLOAD, "frames_per_stream_per_step": F, "steps": steps,
+           "value": audio * steps / (ms / 1000.0), "unit": "audio-s/s", "ms_per_step": ms / steps,
+           "e2e": {"value": audio / (ms_e2e / 1000.0), "unit": "audio-s/s", "h2d_bytes_per_step": int(4 * h_pcm.numel()),
+                   "d2h_bytes_per_step": int(h_out.numel() + 8 * h_len.numel())},
+           "gpu_launches": int(launches)}
+    if rank == 0:
+        peak = 6549.1
+        try:
+            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        except Exception:
+            pass
+        k = kms / steps
+        ach = enc_algorithmic_bytes_per_frame(F) * S * F / (k / 1000.0) / 1e9
+        res["roofline"] = {"bound": "hbm", "kernel": "ob_k_encode", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                           "kernel_ms": k, "algorithmic_bytes_per_frame": enc_algorithmic_bytes_per_frame(F)}
+        if not args.kernels_only:
+            cores = os.cpu_count() or 1
+            try:
+                v, sample = cpu_reference_encode(cores, cores * 16, 50)
+                res["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample}
+            except Exception as ex:
+                res["cpu_baseline"] = {"value": None, "sample": "unavailable: %r" % (ex,)}
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -236,6 +334,10 @@ def run_ours(args):
     value = audio_per_step * args.steps / (ms_dev / 1000.0)
     e2e = audio_per_step * e2e_steps / (ms_e2e / 1000.0) if e2e_steps else None
 
+    encode = None
+    if not args.no_encode:
+        dec.close()
+        encode = run_encode_leg(args, L, local, world, rank, dev, barrier)
     if rank == 0:
         peaks = {}
         try:
@@ -269,7 +371,7 @@ def run_ours(args):
                        "l2": "per-step working set (IR+spectrum+PCM, %.1f GB) exceeds the 126 MB L2" % ((S * F * (12.6e3 + 7.7e3 + 3.84e3)) / 1e9),
                        "sharding": "streams split by rank, no collective"},
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
-            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "encode": encode,
         }
         print(json.dumps(line))
     dec.close()
@@ -284,6 +386,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--frames", type=int, default=50, help="consecutive 20 ms frames per stream per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--enc-frames", type=int, default=10, help="frames per stream per step of the encode leg")
+    ap.add_argument("--no-encode", action="store_true", help="skip the secondary encode measurement")
     ap.add_argument("--kernels-only", action="store_true", help="profiling aid: skip the e2e and cpu_baseline legs")
     args = ap.parse_args()
     if args.impl == "reference":

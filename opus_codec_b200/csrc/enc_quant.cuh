@@ -562,76 +562,112 @@ OB_DEV void ob_enc_theta(ObEncBandCtx &ctx, ObSplit &sp, float *X, float *Y, int
     sp.inv = inv; sp.imid = imid; sp.iside = iside; sp.delta = delta; sp.itheta = itheta;
 }
 
-// quant_partition (bands.c:943-1105), encode = 1
-OB_DEV_NOINLINE uint32_t ob_enc_partition(ObEncBandCtx &ctx, float *X, int N, int b, int B, float *lowband, int LM, float gain, int fill)
+// quant_partition (bands.c:943-1105), encode = 1.  The reference recurses (depth <= LM+1 <= 4); here the recursion is an explicit
+// stack, as in the decoder's symbol kernel: recursion inside a huge divergent thread-per-stream kernel makes nvcc's
+// convergence-barrier bookkeeping (and with it its use of uniform registers) unreliable on sm_100a.
+struct ObEncPartFrame {
+    float *X, *lowband;
+    int N, b, B, B0, LM, fill, mbits, sbits, itheta, stage, mid_first;
+    int32_t rebalance;
+    float gain, mid, side;
+    uint32_t cm;
+};
+
+OB_DEV_NOINLINE uint32_t ob_enc_partition(ObEncBandCtx &ctx, float *X0, int N0, int b0, int Bin, float *lowband0, int LM0, float gain0, int fill0)
 {
-    const uint8_t *cache = ob_pcache(ctx.band, LM);
-    uint32_t cm = 0;
-    const int B0 = B;
-    if (LM != -1 && b > cache[cache[0]] + 12 && N > 2) {
-        ObSplit sp;
-        float *next_lowband2 = nullptr;
-        N >>= 1;
-        float *Y = X + N;
-        LM -= 1;
-        if (B == 1) fill = (fill & 1) | (fill << 1);
-        B = (B + 1) >> 1;
-        ob_enc_theta(ctx, sp, X, Y, N, &b, B, B0, LM, 0, &fill);
-        int delta = sp.delta;
-        const int itheta = sp.itheta;
-        const float mid = (1.f / 32768) * sp.imid, side = (1.f / 32768) * sp.iside;
-        if (B0 > 1 && (itheta & 0x3fff)) {
-            if (itheta > 8192) delta -= delta >> (4 - LM);
-            else delta = ob_imin(0, delta + (N << OB_BITRES >> (5 - LM)));
-        }
-        int mbits = ob_imax(0, ob_imin(b, (b - delta) / 2)), sbits = b - mbits;
-        ctx.remaining_bits -= sp.qalloc;
-        if (lowband) next_lowband2 = lowband + N;
-        int32_t rebalance = ctx.remaining_bits;
-        if (mbits >= sbits) {
-            cm = ob_enc_partition(ctx, X, N, mbits, B, lowband, LM, gain * mid, fill);
-            rebalance = mbits - (rebalance - ctx.remaining_bits);
-            if (rebalance > 3 << OB_BITRES && itheta != 0) sbits += rebalance - (3 << OB_BITRES);
-            cm |= ob_enc_partition(ctx, Y, N, sbits, B, next_lowband2, LM, gain * side, fill >> B) << (B0 >> 1);
-        } else {
-            cm = ob_enc_partition(ctx, Y, N, sbits, B, next_lowband2, LM, gain * side, fill >> B) << (B0 >> 1);
-            rebalance = sbits - (rebalance - ctx.remaining_bits);
-            if (rebalance > 3 << OB_BITRES && itheta != 16384) mbits += rebalance - (3 << OB_BITRES);
-            cm |= ob_enc_partition(ctx, X, N, mbits, B, lowband, LM, gain * mid, fill);
-        }
-    } else {
-        int q = ob_bits2pulses(cache, b);
-        int curr_bits = ob_pulses2bits(cache, q);
-        ctx.remaining_bits -= curr_bits;
-        while (ctx.remaining_bits < 0 && q > 0) {
-            ctx.remaining_bits += curr_bits;
-            q--;
-            curr_bits = ob_pulses2bits(cache, q);
-            ctx.remaining_bits -= curr_bits;
-        }
-        if (q != 0) {
-            cm = ob_alg_quant(X, N, ob_get_pulses(q), ctx.spread, B, *ctx.ec, gain, ctx.resynth);
-        } else if (ctx.resynth) {
-            const uint32_t cm_mask = (1u << B) - 1;
-            fill &= (int)cm_mask;
-            if (!fill) { for (int j = 0; j < N; j++) X[j] = 0; }
-            else {
-                if (lowband == nullptr) {
-                    for (int j = 0; j < N; j++) { ctx.seed = 1664525u * ctx.seed + 1013904223u; X[j] = (float)((int32_t)ctx.seed >> 20); }
-                    cm = cm_mask;
-                } else {
-                    for (int j = 0; j < N; j++) {
-                        ctx.seed = 1664525u * ctx.seed + 1013904223u;
-                        const float tmp = (ctx.seed & 0x8000u) ? (1.0f / 256) : -(1.0f / 256);
-                        X[j] = lowband[j] + tmp;
-                    }
-                    cm = (uint32_t)fill;
+    ObEncPartFrame st[6];
+    int sp = 0;
+    uint32_t ret = 0;
+    st[0].X = X0; st[0].lowband = lowband0; st[0].N = N0; st[0].b = b0; st[0].B = Bin; st[0].LM = LM0; st[0].gain = gain0; st[0].fill = fill0; st[0].stage = 0;
+    while (sp >= 0) {
+        ObEncPartFrame &f = st[sp];
+        if (f.stage == 0) {
+            const uint8_t *cache = ob_pcache(ctx.band, f.LM);
+            if (f.LM != -1 && f.b > cache[cache[0]] + 12 && f.N > 2) {
+                ObSplit s;
+                const int n = f.N >> 1, lm = f.LM - 1;
+                int bb = f.b, fl = f.fill;
+                f.B0 = f.B;
+                if (f.B == 1) fl = (fl & 1) | (fl << 1);
+                const int B1 = (f.B + 1) >> 1;
+                ob_enc_theta(ctx, s, f.X, f.X + n, n, &bb, B1, f.B0, lm, 0, &fl);
+                int delta = s.delta;
+                f.mid = (1.f / 32768) * s.imid;
+                f.side = (1.f / 32768) * s.iside;
+                if (f.B0 > 1 && (s.itheta & 0x3fff)) {
+                    if (s.itheta > 8192) delta -= delta >> (4 - lm);
+                    else delta = ob_imin(0, delta + (n << OB_BITRES >> (5 - lm)));
                 }
-                ob_renormalise_s(X, N, gain);
+                f.mbits = ob_imax(0, ob_imin(bb, (bb - delta) / 2));
+                f.sbits = bb - f.mbits;
+                ctx.remaining_bits -= s.qalloc;
+                f.rebalance = ctx.remaining_bits;
+                f.itheta = s.itheta;
+                f.fill = fl; f.N = n; f.LM = lm; f.B = B1;              // from here on the frame describes its two children
+                f.mid_first = f.mbits >= f.sbits;
+                f.stage = 1;
+                ObEncPartFrame &c = st[++sp];
+                c.N = n; c.B = B1; c.LM = lm; c.stage = 0;
+                if (f.mid_first) { c.X = f.X; c.lowband = f.lowband; c.b = f.mbits; c.gain = f.gain * f.mid; c.fill = fl; }
+                else { c.X = f.X + n; c.lowband = f.lowband ? f.lowband + n : nullptr; c.b = f.sbits; c.gain = f.gain * f.side; c.fill = fl >> B1; }
+            } else {
+                uint32_t cm = 0;
+                int q = ob_bits2pulses(cache, f.b);
+                int curr_bits = ob_pulses2bits(cache, q);
+                ctx.remaining_bits -= curr_bits;
+                while (ctx.remaining_bits < 0 && q > 0) {
+                    ctx.remaining_bits += curr_bits;
+                    q--;
+                    curr_bits = ob_pulses2bits(cache, q);
+                    ctx.remaining_bits -= curr_bits;
+                }
+                if (q != 0) {
+                    cm = ob_alg_quant(f.X, f.N, ob_get_pulses(q), ctx.spread, f.B, *ctx.ec, f.gain, ctx.resynth);
+                } else if (ctx.resynth) {
+                    const uint32_t cm_mask = (1u << f.B) - 1;
+                    const int fl = f.fill & (int)cm_mask;
+                    float *X = f.X;
+                    if (!fl) { for (int j = 0; j < f.N; j++) X[j] = 0; }
+                    else {
+                        if (f.lowband == nullptr) {
+                            for (int j = 0; j < f.N; j++) { ctx.seed = 1664525u * ctx.seed + 1013904223u; X[j] = (float)((int32_t)ctx.seed >> 20); }
+                            cm = cm_mask;
+                        } else {
+                            for (int j = 0; j < f.N; j++) {
+                                ctx.seed = 1664525u * ctx.seed + 1013904223u;
+                                const float tmp = (ctx.seed & 0x8000u) ? (1.0f / 256) : -(1.0f / 256);
+                                X[j] = f.lowband[j] + tmp;
+                            }
+                            cm = (uint32_t)fl;
+                        }
+                        ob_renormalise_s(X, f.N, f.gain);
+                    }
+                }
+                ret = cm;
+                sp--;
             }
+        } else if (f.stage == 1) {
+            ObEncPartFrame &c = st[sp + 1];
+            c.N = f.N; c.B = f.B; c.LM = f.LM; c.stage = 0;
+            if (f.mid_first) {
+                f.cm = ret;
+                const int32_t rb = f.mbits - (f.rebalance - ctx.remaining_bits);
+                if (rb > 3 << OB_BITRES && f.itheta != 0) f.sbits += rb - (3 << OB_BITRES);
+                c.X = f.X + f.N; c.lowband = f.lowband ? f.lowband + f.N : nullptr; c.b = f.sbits; c.gain = f.gain * f.side; c.fill = f.fill >> f.B;
+            } else {
+                f.cm = ret << (f.B0 >> 1);
+                const int32_t rb = f.sbits - (f.rebalance - ctx.remaining_bits);
+                if (rb > 3 << OB_BITRES && f.itheta != 16384) f.mbits += rb - (3 << OB_BITRES);
+                c.X = f.X; c.lowband = f.lowband; c.b = f.mbits; c.gain = f.gain * f.mid; c.fill = f.fill;
+            }
+            f.stage = 2;
+            sp++;
+        } else {
+            ret = f.mid_first ? (f.cm | ret << (f.B0 >> 1)) : (f.cm | ret);
+            sp--;
         }
     }
-    return cm;
+    return ret;
 }
 
 OB_DEV uint32_t ob_enc_band_n1(ObEncBandCtx &ctx, float *X, float *Y, float *lowband_out)       // bands.c:904-937

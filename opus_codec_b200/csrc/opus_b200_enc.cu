@@ -20,14 +20,23 @@ struct ObEncStream {           // everything one stream owns on the device
 };
 
 #define OB_ENC_THREADS 32
+// The per-stream working set (ObEncScratch, ~76 KB) and the stream's state live in LOCAL memory for the duration of the launch:
+// CUDA interleaves local memory across the lanes of a warp, so when the 32 streams of a warp run the same loop (pre-emphasis,
+// pitch cross-correlation, MDCT, band energies ...) element i of every lane's array sits in one 128-byte line -- the accesses
+// coalesce without any change to the per-stream code.  (With the scratch in global memory, one array per stream, every load of
+// a warp touched 32 different lines: 112 ms per frame at 16384 streams.)
 __global__ void __launch_bounds__(OB_ENC_THREADS)
 ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *__restrict__ lens, uint32_t *__restrict__ ranges,
-            ObEncStream *__restrict__ streams, ObEncScratch *__restrict__ scratch, ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes)
+            ObEncStream *__restrict__ streams, ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    ObEncStream &es = streams[s];
-    ObEncScratch &sc = scratch[s];
+    ObEncScratch sc;
+    {   // deterministic start: no stage may depend on stale local memory
+        uint32_t *z = reinterpret_cast<uint32_t *>(&sc);
+        for (int i = 0; i < (int)(sizeof(ObEncScratch) / 4); i++) z[i] = 0;
+    }
+    ObEncStream es = streams[s];
     const int CC = es.st.channels;
     // NOTE: the frame counter is deliberately volatile.  The loop body is one huge divergent region; with a plain `int f`
     // nvcc 12.9 keeps f in a UNIFORM register, and lanes that fall behind re-execute the shared increment -- frames get
@@ -38,6 +47,7 @@ ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *_
         lens[w] = n;
         if (ranges) ranges[w] = n > 0 ? es.st.final_range : 0;
     }
+    streams[s] = es;
 }
 
 __global__ void ob_k_enc_reset(ObEncStream *streams, const int32_t *idx, int n, int S, int channels)
@@ -65,7 +75,6 @@ struct ObEncoder {
     cudaEvent_t ev[2];
     bool timed;
     ObEncStream *d_streams;
-    ObEncScratch *d_scratch;
     float *d_pcm; size_t pcm_cap;
     uint8_t *d_out; size_t out_cap;
     int32_t *d_lens; uint32_t *d_ranges;
@@ -99,12 +108,11 @@ ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         ok = ok && cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
         ok = ok && cudaEventCreate(&e->ev[0]) == cudaSuccess && cudaEventCreate(&e->ev[1]) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_streams, sizeof(ObEncStream) * n_streams) == cudaSuccess;
-        ok = ok && cudaMalloc(&e->d_scratch, sizeof(ObEncScratch) * n_streams) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_lens, sizeof(int32_t) * total) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_ranges, sizeof(uint32_t) * total) == cudaSuccess;
         // the per-thread encoder recurses (quant_partition, <= 5 deep) and keeps band-sized arrays on its stack
-        size_t stack_bytes = 24 * 1024;
-        if (const char *v = getenv("OB_ENC_STACK_KB")) { const int t = atoi(v); if (t >= 4 && t <= 256) stack_bytes = (size_t)t * 1024; }   // debugging aid
+        size_t stack_bytes = sizeof(ObEncScratch) + sizeof(ObEncStream) + 72 * 1024;   // kernel frame + the recursive band coder (measured: 28 KB is not enough for stereo)
+        if (const char *v = getenv("OB_ENC_STACK_KB")) { const int t = atoi(v); if (t >= 4 && t <= 500) stack_bytes = (size_t)t * 1024; }   // debugging aid
         ok = ok && cudaDeviceSetLimit(cudaLimitStackSize, stack_bytes) == cudaSuccess;
         if (!ok) {
             fprintf(stderr, "opus_b200: device allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -120,7 +128,7 @@ void ob_encoder_destroy(ObEncoder *e)
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    cudaFree(e->d_streams); cudaFree(e->d_scratch); cudaFree(e->d_pcm); cudaFree(e->d_out); cudaFree(e->d_lens); cudaFree(e->d_ranges);
+    cudaFree(e->d_streams); cudaFree(e->d_pcm); cudaFree(e->d_out); cudaFree(e->d_lens); cudaFree(e->d_ranges);
     for (int i = 0; i < 2; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -175,8 +183,7 @@ static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size
     OB_CUDA(cudaEventRecord(e->ev[0], e->stream));
     int bs = OB_ENC_THREADS;
     if (const char *v = getenv("OB_ENC_BLOCK")) { const int t = atoi(v); if (t >= 1 && t <= OB_ENC_THREADS) bs = t; }   // debugging aid
-    ob_k_encode<<<(e->S + bs - 1) / bs, bs, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->d_scratch,
-                                                                                             e->cfg, e->S, F, frame_size, max_bytes);
+    ob_k_encode<<<(e->S + bs - 1) / bs, bs, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->cfg, e->S, F, frame_size, max_bytes);
     OB_CUDA(cudaEventRecord(e->ev[1], e->stream));
     OB_CUDA(cudaGetLastError());
     e->launches += 1;
