@@ -1,4 +1,4 @@
-//! `BatchDecoder`: safe wrapper over the C ABI of `libopus_b200.so` (include/opus_b200.h).
+//! `BatchDecoder` / `BatchEncoder`: safe wrappers over the C ABI of `libopus_b200.so` (include/opus_b200.h).
 //!
 //! REVIEW-ONLY in this repository: the build image has no `cargo`/`rustc`, so this file is not compiled here.
 //! It is the file a maintainer of the `opus-codec` crate would add as `src/batch.rs` (next to `src/decoder.rs`),
@@ -6,7 +6,7 @@
 //! It reuses the crate's own `Error`, `Result`, `Channels` and `SampleRate` types (src/error.rs, src/types.rs).
 
 use crate::error::{Error, Result};
-use crate::types::{Channels, SampleRate};
+use crate::types::{Application, Bitrate, Channels, Complexity, SampleRate};
 use std::ptr::NonNull;
 
 #[repr(C)]
@@ -24,6 +24,26 @@ unsafe extern "C" {
     pub fn ob_decoder_final_range(dec: *mut ObDecoder, out: *mut u32) -> i32;
     pub fn ob_decoder_reset(dec: *mut ObDecoder, idx: *const i32, n: i32) -> i32;
     pub fn ob_decoder_last_packet_duration(dec: *mut ObDecoder, out: *mut i32) -> i32;
+
+    pub fn ob_encoder_create(n_streams: i32, fs: i32, channels: i32, application: i32, device: i32, max_frames: i32,
+                             error: *mut i32) -> *mut ObEncoder;
+    pub fn ob_encoder_destroy(enc: *mut ObEncoder);
+    pub fn ob_encode_float(enc: *mut ObEncoder, pcm: *const f32, frame_size: i32, out: *mut u8, max_bytes: i32,
+                           lens_out: *mut i32) -> i32;
+    pub fn ob_encode_float_multi(enc: *mut ObEncoder, n_frames: i32, pcm: *const f32, frame_size: i32, out: *mut u8,
+                                 max_bytes: i32, lens_out: *mut i32, ranges_out: *mut u32) -> i32;
+    pub fn ob_encoder_set_bitrate(enc: *mut ObEncoder, bitrate: i32) -> i32;
+    pub fn ob_encoder_get_bitrate(enc: *mut ObEncoder, value: *mut i32) -> i32;
+    pub fn ob_encoder_set_complexity(enc: *mut ObEncoder, complexity: i32) -> i32;
+    pub fn ob_encoder_set_vbr(enc: *mut ObEncoder, vbr: i32) -> i32;
+    pub fn ob_encoder_set_vbr_constraint(enc: *mut ObEncoder, cvbr: i32) -> i32;
+    pub fn ob_encoder_final_range(enc: *mut ObEncoder, out: *mut u32) -> i32;
+    pub fn ob_encoder_reset(enc: *mut ObEncoder, idx: *const i32, n: i32) -> i32;
+}
+
+#[repr(C)]
+pub struct ObEncoder {
+    _unused: [u8; 0],
 }
 
 /// `n_streams` independent CELT-only Opus decoders living on one B200.
@@ -101,5 +121,97 @@ impl BatchDecoder {
 impl Drop for BatchDecoder {
     fn drop(&mut self) {
         unsafe { ob_decoder_destroy(self.raw.as_ptr()) }
+    }
+}
+
+/// `n_streams` independent CELT-only (`Application::RestrictedLowDelay`) Opus encoders living on one B200.
+/// Mirrors `Encoder` (src/encoder.rs:26-73): owns the raw handle, frees it in `Drop`, all methods take `&mut self`.
+pub struct BatchEncoder {
+    raw: NonNull<ObEncoder>,
+    n_streams: usize,
+    channels: Channels,
+}
+
+unsafe impl Send for BatchEncoder {}
+
+impl BatchEncoder {
+    /// Cf. `Encoder::new` (src/encoder.rs:40-73). The CUDA path supports `Hz48000` + `Application::RestrictedLowDelay`
+    /// (OPUS_APPLICATION_RESTRICTED_LOWDELAY, the CELT-only application); anything else is `Error::Unimplemented`.
+    pub fn new(n_streams: usize, sample_rate: SampleRate, channels: Channels, application: Application, device: i32,
+               max_frames: usize) -> Result<Self> {
+        let mut err = 0i32;
+        let raw = unsafe {
+            ob_encoder_create(n_streams as i32, sample_rate as i32, channels as i32, application as i32, device,
+                              max_frames as i32, &mut err)
+        };
+        match NonNull::new(raw) {
+            Some(raw) if err == 0 => Ok(Self { raw, n_streams, channels }),
+            _ => Err(Error::from_code(err)),
+        }
+    }
+
+    /// One frame per stream. `input` is `n_streams * frame_size * channels` interleaved floats (frame size derived from
+    /// the slice length like `Encoder::encode_float`, src/encoder.rs:215-247); `output` is `n_streams * max_bytes`.
+    /// Returns per-stream `Ok(packet_len)` / `Err(code)`; packet `s` is `output[s*max_bytes .. s*max_bytes + len]`.
+    pub fn encode_float(&mut self, input: &[f32], output: &mut [u8]) -> Result<Vec<Result<usize>>> {
+        let per = self.n_streams * self.channels as usize;
+        if input.is_empty() || input.len() % per != 0 || output.len() % self.n_streams != 0 {
+            return Err(Error::BadArg);
+        }
+        let (frame_size, max_bytes) = (input.len() / per, output.len() / self.n_streams);
+        let mut lens = vec![0i32; self.n_streams];
+        let rc = unsafe {
+            ob_encode_float(self.raw.as_ptr(), input.as_ptr(), frame_size as i32, output.as_mut_ptr(), max_bytes as i32,
+                            lens.as_mut_ptr())
+        };
+        if rc != 0 {
+            return Err(Error::from_code(rc));
+        }
+        Ok(lens.into_iter().map(|n| if n >= 0 { Ok(n as usize) } else { Err(Error::from_code(n)) }).collect())
+    }
+
+    /// Cf. `Encoder::set_bitrate` (src/encoder.rs:545-562): one value for the whole batch.
+    pub fn set_bitrate(&mut self, bitrate: Bitrate) -> Result<()> {
+        let v = match bitrate { Bitrate::Auto => -1000, Bitrate::Max => -1, Bitrate::Custom(b) => b };
+        let rc = unsafe { ob_encoder_set_bitrate(self.raw.as_ptr(), v) };
+        if rc != 0 { Err(Error::from_code(rc)) } else { Ok(()) }
+    }
+
+    /// Cf. `Encoder::set_complexity` (src/encoder.rs:588-610).
+    pub fn set_complexity(&mut self, complexity: Complexity) -> Result<()> {
+        let rc = unsafe { ob_encoder_set_complexity(self.raw.as_ptr(), complexity.value() as i32) };
+        if rc != 0 { Err(Error::from_code(rc)) } else { Ok(()) }
+    }
+
+    /// Cf. `Encoder::set_vbr` / `set_vbr_constraint` (src/encoder.rs:639-656, :311-319).
+    pub fn set_vbr(&mut self, enabled: bool, constrained: bool) -> Result<()> {
+        let rc = unsafe { ob_encoder_set_vbr(self.raw.as_ptr(), enabled as i32) };
+        if rc != 0 { return Err(Error::from_code(rc)); }
+        let rc = unsafe { ob_encoder_set_vbr_constraint(self.raw.as_ptr(), constrained as i32) };
+        if rc != 0 { Err(Error::from_code(rc)) } else { Ok(()) }
+    }
+
+    /// Cf. `Encoder::final_range` (src/encoder.rs:411-419), for every stream.
+    pub fn final_range(&mut self) -> Result<Vec<u32>> {
+        let mut out = vec![0u32; self.n_streams];
+        let rc = unsafe { ob_encoder_final_range(self.raw.as_ptr(), out.as_mut_ptr()) };
+        if rc != 0 { Err(Error::from_code(rc)) } else { Ok(out) }
+    }
+
+    /// Cf. `Encoder::reset` (src/encoder.rs:689-698); `None` resets every stream.
+    pub fn reset(&mut self, streams: Option<&[i32]>) -> Result<()> {
+        let rc = unsafe {
+            match streams {
+                Some(s) => ob_encoder_reset(self.raw.as_ptr(), s.as_ptr(), s.len() as i32),
+                None => ob_encoder_reset(self.raw.as_ptr(), std::ptr::null(), 0),
+            }
+        };
+        if rc != 0 { Err(Error::from_code(rc)) } else { Ok(()) }
+    }
+}
+
+impl Drop for BatchEncoder {
+    fn drop(&mut self) {
+        unsafe { ob_encoder_destroy(self.raw.as_ptr()) }
     }
 }
