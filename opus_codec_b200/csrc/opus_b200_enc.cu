@@ -27,9 +27,14 @@ struct ObEncStream {           // everything one stream owns on the device
 // a warp touched 32 different lines: 112 ms per frame at 16384 streams.)
 __global__ void __launch_bounds__(OB_ENC_THREADS)
 ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *__restrict__ lens, uint32_t *__restrict__ ranges,
-            ObEncStream *__restrict__ streams, ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes)
+            ObEncStream *__restrict__ streams, ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes, int lanes)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    // Only the first `lanes` threads of each warp carry a stream (tuning knob).  Spreading the streams over more, partly filled,
+    // warps was tried to hide the local-memory latency this kernel is bound by (ncu: 0.26 warp-instructions/cycle/SM, 8.6 of 13
+    // stall cycles on long-scoreboard) -- it is SLOWER: a half-filled warp still occupies whole 128-byte local-memory lines,
+    // so the L1/L2 capacity per stream halves.  Full warps (lanes = 32) are the default.
+    if ((int)threadIdx.x >= lanes) return;
+    const int s = blockIdx.x * lanes + threadIdx.x;
     if (s >= S) return;
     ObEncScratch sc;
     {   // deterministic start: no stage may depend on stale local memory
@@ -69,7 +74,7 @@ __global__ void ob_k_enc_gather(const ObEncStream *streams, uint32_t *ranges, in
 }
 
 struct ObEncoder {
-    int S, CC, device, max_frames;
+    int S, CC, device, max_frames, lanes;
     ObOpusEncCfg cfg;
     cudaStream_t stream;
     cudaEvent_t ev[2];
@@ -100,6 +105,7 @@ ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
     if (err == OB_OK) {
         memset(e, 0, sizeof(*e));
         e->S = n_streams; e->CC = channels; e->device = device; e->max_frames = max_frames;
+        e->lanes = 32;    // measured on B200, 16384 stereo c10 streams x 4 frames: 32 lanes 130 ms, 16: 166, 8: 329, 4: 464, 2: 726
         // defaults of opus_encoder_init (opus_encoder.c:202-297): VBR on, constrained, bitrate AUTO, complexity 9, 24-bit depth
         e->cfg.bitrate = -1000; e->cfg.complexity = 9; e->cfg.vbr = 1; e->cfg.vbr_constraint = 1; e->cfg.max_bandwidth = 1105;
         e->cfg.user_bandwidth = 0; e->cfg.force_channels = 0; e->cfg.packet_loss = 0; e->cfg.lsb_depth = 24;
@@ -181,9 +187,9 @@ int32_t ob_encoder_set_lsb_depth(ObEncoder *e, int32_t d) { if (!e || d < 8 || d
 static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size, uint8_t *d_out, int max_bytes, int32_t *d_lens, uint32_t *d_ranges)
 {
     OB_CUDA(cudaEventRecord(e->ev[0], e->stream));
-    int bs = OB_ENC_THREADS;
-    if (const char *v = getenv("OB_ENC_BLOCK")) { const int t = atoi(v); if (t >= 1 && t <= OB_ENC_THREADS) bs = t; }   // debugging aid
-    ob_k_encode<<<(e->S + bs - 1) / bs, bs, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->cfg, e->S, F, frame_size, max_bytes);
+    int lanes = e->lanes;
+    if (const char *v = getenv("OB_ENC_LANES")) { const int t = atoi(v); if (t >= 1 && t <= OB_ENC_THREADS) lanes = t; }   // tuning aid
+    ob_k_encode<<<(e->S + lanes - 1) / lanes, OB_ENC_THREADS, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->cfg, e->S, F, frame_size, max_bytes, lanes);
     OB_CUDA(cudaEventRecord(e->ev[1], e->stream));
     OB_CUDA(cudaGetLastError());
     e->launches += 1;

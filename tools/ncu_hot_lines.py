@@ -7,8 +7,11 @@ rep, kern, so = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
 td = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=td, check=True, stdout=subprocess.DEVNULL)
-cub = [f for f in os.listdir(td) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cub)], capture_output=True, text=True).stdout.splitlines()
+dis = []
+for cub in sorted(f for f in os.listdir(td) if f.endswith(".cubin")):      # one cubin per translation unit: take the one holding the kernel
+    txt = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(td, cub)], capture_output=True, text=True).stdout
+    if re.search(r"\.section\s+\.text\.\S*" + kern, txt):
+        dis = txt.splitlines(); break
 # instruction -> (file,line) in order, per function (functions called by the kernel are separate .text sections inlined or not)
 sections = collections.OrderedDict(); cur = None; loc = ("?", 0)
 for l in dis:
@@ -60,5 +63,6 @@ while i < len(insts):
 tot = sum(agg.values()) or 1; tots = sum(aggs.values()) or 1
 print("kernel %s: %d warp-instructions attributed, %d stall samples" % (kern, tot, tots))
 print("%-22s %6s %7s %7s %7s" % ("file:line", "inst%", "thr/in", "smpl%", ""))
-for loc, v in agg.most_common(top):
+by_samples = os.environ.get("HOT_BY", "inst") == "samples"
+for loc, v in (sorted(agg.items(), key=lambda kv: -aggs[kv[0]])[:top] if by_samples else agg.most_common(top)):
     print("%-22s %6.2f %7.1f %7.2f" % ("%s:%d" % loc, 100.0 * v / tot, aggt[loc] / max(1, v), 100.0 * aggs[loc] / tots))
