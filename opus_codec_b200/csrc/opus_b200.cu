@@ -26,10 +26,12 @@
 #define OB_SYM_THREADS 128
 __global__ void __launch_bounds__(OB_SYM_THREADS)
 ob_k_symbols(const uint8_t *__restrict__ packets, const int32_t *__restrict__ offsets, const int32_t *__restrict__ lens,
-             ObFrameIR *__restrict__ ir, int total, int dec_channels, int max_frame)
+             ObFrameIR *__restrict__ ir, int total, int dec_channels, int max_frame, int F, int f0, int Fc)
 {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= total) return;
+    // a launch covers the frame window [f0, f0+Fc) of every stream of a [S][F] batch: t -> (stream, frame)
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    const size_t t = (size_t)(k / Fc) * F + f0 + k % Fc;
     const int len = lens[t];
     ob_decode_symbols(len > 0 ? packets + offsets[t] : nullptr, len, dec_channels, max_frame, ir + t);
 }
@@ -37,19 +39,21 @@ ob_k_symbols(const uint8_t *__restrict__ packets, const int32_t *__restrict__ of
 #define OB_BANDS_WARPS 6
 #define OB_BANDS_SMEM_PER_WARP ((int)sizeof(ObBandsShared))
 __global__ void __launch_bounds__(OB_BANDS_WARPS * 32)
-ob_k_bands(const ObFrameIR *__restrict__ ir, const ObDecState *__restrict__ st, float *__restrict__ Xg, int S, int F)
+ob_k_bands(const ObFrameIR *__restrict__ ir, const ObDecState *__restrict__ st, float *__restrict__ Xg, int S, int F, int f0, int Fc)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
-    const int w = blockIdx.x * OB_BANDS_WARPS + warp;
-    if (w >= S * F) return;
+    const int k = blockIdx.x * OB_BANDS_WARPS + warp;
+    if (k >= S * Fc) return;
+    const int s = k / Fc, f = f0 + k % Fc;
+    const size_t w = (size_t)s * F + f;
     const ObFrameIR *fr = ir + w;
     const int status = fr->hdr.status;
     if (status <= 0) return;
-    const int s = w / F, f = w % F;
-    // seed = range-coder state left by the previous successfully decoded frame of this stream
+    // seed = range-coder state left by the previous successfully decoded frame of this stream (inside this launch's frame
+    // window: from the IR; before it: the stream state the previous synthesis launch stored)
     uint32_t seed = st[s].rng;
-    for (int p = f - 1; p >= 0; p--) if (ir[w - (f - p)].hdr.status > 0) { seed = ir[w - (f - p)].hdr.final_range; break; }
+    for (int p = f - 1; p >= f0; p--) if (ir[w - (f - p)].hdr.status > 0) { seed = ir[w - (f - p)].hdr.final_range; break; }
     ObBandsShared &sh = *reinterpret_cast<ObBandsShared *>(smem_raw + (size_t)warp * OB_BANDS_SMEM_PER_WARP);
     ObWarp g;
     ob_reconstruct_bands(g, fr, seed, sh, Xg + (size_t)w * OB_X_STRIDE);
@@ -58,7 +62,8 @@ ob_k_bands(const ObFrameIR *__restrict__ ir, const ObDecState *__restrict__ st, 
 #define OB_SYNTH_THREADS 128
 __global__ void __launch_bounds__(OB_SYNTH_THREADS)
 ob_k_synth(const ObFrameIR *__restrict__ ir, const float *__restrict__ Xg, ObDecState *__restrict__ st, float *__restrict__ hist,
-           float *__restrict__ pcm, int32_t *__restrict__ samples, uint32_t *__restrict__ ranges, int S, int F, int CC, int frame_size)
+           float *__restrict__ pcm, int32_t *__restrict__ samples, uint32_t *__restrict__ ranges, int S, int F, int CC, int frame_size,
+           int f0, int Fc)
 {
     __shared__ ObSynthShared sh;
     const int s = blockIdx.x;
@@ -85,7 +90,7 @@ ob_k_synth(const ObFrameIR *__restrict__ ir, const float *__restrict__ Xg, ObDec
     uint32_t final_range = state->final_range;
     int last_dur = state->last_packet_duration;
     g.sync();
-    for (int f = 0; f < F; f++) {
+    for (int f = f0; f < f0 + Fc; f++) {
         const size_t w = (size_t)s * F + f;
         const int n = ob_synth_frame(g, sh, ir + w, Xg + w * OB_X_STRIDE, pcm + w * (size_t)frame_size * CC, CC);
         if (n > 0) { final_range = sh.hdr.final_range; last_dur = n; }
@@ -137,7 +142,7 @@ __global__ void ob_k_gather_state(const ObDecState *st, uint32_t *ranges, int32_
 // host side
 // ------------------------------------------------------------------------------------------------
 #ifndef OB_MAX_CHUNKS
-#define OB_MAX_CHUNKS 8
+#define OB_MAX_CHUNKS 16
 #endif
 struct ObDecoder {
     int S, CC, device, max_frames;
@@ -160,26 +165,34 @@ struct ObDecoder {
 // Launches the three kernels for streams [s0, s0+Sc).  All per-stream arrays are indexed by stream, so a sub-range is
 // just a pointer offset; timed != 0 brackets the kernels with the handle's events.
 static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packets, const int32_t *d_offsets, const int32_t *d_lens,
-                     float *d_pcm, int frame_size, int32_t *d_samples, uint32_t *d_ranges, int timed, cudaStream_t stream)
+                     float *d_pcm, int frame_size, int32_t *d_samples, uint32_t *d_ranges, int timed, cudaStream_t stream,
+                     int f0 = 0, int Fc = -1, int which = 3)
 {
-    const int total = Sc * F;
+    // which: bit 0 = the symbol kernel, bit 1 = band + synthesis kernels, for the frame window [f0, f0+Fc) of streams [s0, s0+Sc)
+    if (Fc < 0) Fc = F;
+    const int total = Sc * Fc;
     const size_t w0 = (size_t)s0 * F;
     ObFrameIR *ir = d->d_ir + w0;
     float *X = d->d_X + w0 * OB_X_STRIDE;
     ObDecState *st = d->d_state + s0;
     float *hist = d->d_hist + (size_t)s0 * d->CC * OB_HIST_LEN;
     if (timed) OB_CUDA(cudaEventRecord(d->ev[0], stream));
-    ob_k_symbols<<<(total + OB_SYM_THREADS - 1) / OB_SYM_THREADS, OB_SYM_THREADS, 0, stream>>>(
-        d_packets, d_offsets + w0, d_lens + w0, ir, total, d->CC, frame_size);
+    if (which & 1) {
+        ob_k_symbols<<<(total + OB_SYM_THREADS - 1) / OB_SYM_THREADS, OB_SYM_THREADS, 0, stream>>>(
+            d_packets, d_offsets + w0, d_lens + w0, ir, total, d->CC, frame_size, F, f0, Fc);
+        d->launches += 1;
+    }
     if (timed) OB_CUDA(cudaEventRecord(d->ev[1], stream));
-    ob_k_bands<<<(total + OB_BANDS_WARPS - 1) / OB_BANDS_WARPS, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, stream>>>(
-        ir, st, X, Sc, F);
-    if (timed) OB_CUDA(cudaEventRecord(d->ev[2], stream));
-    ob_k_synth<<<Sc, OB_SYNTH_THREADS, 0, stream>>>(ir, X, st, hist, d_pcm + w0 * (size_t)frame_size * d->CC, d_samples + w0,
-                                                     d_ranges ? d_ranges + w0 : nullptr, Sc, F, d->CC, frame_size);
+    if (which & 2) {
+        ob_k_bands<<<(total + OB_BANDS_WARPS - 1) / OB_BANDS_WARPS, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, stream>>>(
+            ir, st, X, Sc, F, f0, Fc);
+        if (timed) OB_CUDA(cudaEventRecord(d->ev[2], stream));
+        ob_k_synth<<<Sc, OB_SYNTH_THREADS, 0, stream>>>(ir, X, st, hist, d_pcm + w0 * (size_t)frame_size * d->CC, d_samples + w0,
+                                                         d_ranges ? d_ranges + w0 : nullptr, Sc, F, d->CC, frame_size, f0, Fc);
+        d->launches += 2;
+    }
     if (timed) OB_CUDA(cudaEventRecord(d->ev[3], stream));
     OB_CUDA(cudaGetLastError());
-    d->launches += 3;
     if (timed) d->timed = true;
     return OB_OK;
 }
@@ -314,25 +327,47 @@ int32_t ob_decode_float_multi(ObDecoder *d, int32_t n_frames, const uint8_t *pac
     OB_CUDA(cudaMemcpyAsync(d->d_packets, packets, nbytes, cudaMemcpyHostToDevice, d->stream));
     OB_CUDA(cudaMemcpyAsync(d->d_offsets, offsets, total * sizeof(int32_t), cudaMemcpyHostToDevice, d->stream));
     OB_CUDA(cudaMemcpyAsync(d->d_lens, lens, total * sizeof(int32_t), cudaMemcpyHostToDevice, d->stream));
-    // Streams are processed in chunks so that the device->host copy of chunk k overlaps the kernels of chunk k+1
-    // (kernels on d->stream, copies on d->copy_stream, one event per chunk).
-    int nchunks = d->S * n_frames >= 65536 ? 4 : (d->S * n_frames >= 16384 ? 2 : 1);
+    // The call is processed in chunks so that the device->host copy of chunk k overlaps the kernels of chunk k+1 (kernels on
+    // d->stream, copies on d->copy_stream, one event per chunk).  With several frames per stream the chunks are FRAME windows
+    // of all streams: every launch keeps the full stream-level parallelism the synthesis kernel needs (one block per stream),
+    // and the per-stream state simply carries over from launch to launch.  Single-frame calls are split by stream ranges.
+    int nchunks = total >= 65536 ? 5 : (total >= 16384 ? 2 : 1);
+    if (const char *v = getenv("OB_DEC_CHUNKS")) { const int t = atoi(v); if (t >= 1) nchunks = t; }      // tuning aid
     if (nchunks > OB_MAX_CHUNKS) nchunks = OB_MAX_CHUNKS;
-    const int per = (d->S + nchunks - 1) / nchunks;
-    OB_CUDA(cudaEventRecord(d->h2d_done, d->stream));
-    OB_CUDA(cudaStreamWaitEvent(d->aux_stream, d->h2d_done, 0));
-    for (int k = 0, s0 = 0; s0 < d->S; k++, s0 += per) {
-        const int Sc = d->S - s0 < per ? d->S - s0 : per;
-        const size_t w0 = (size_t)s0 * n_frames, cnt = (size_t)Sc * n_frames;
-        cudaStream_t cs = (k & 1) ? d->aux_stream : d->stream;       // alternate compute streams: kernels of neighbouring chunks overlap
-        const int r = ob_launch(d, s0, Sc, n_frames, d->d_packets, d->d_offsets, d->d_lens, d->d_pcm, frame_size, d->d_samples, d->d_ranges, 0, cs);
-        if (r != OB_OK) return r;
-        OB_CUDA(cudaEventRecord(d->chunk_ev[k], cs));
-        OB_CUDA(cudaStreamWaitEvent(d->copy_stream, d->chunk_ev[k], 0));
-        const size_t pf = (size_t)frame_size * d->CC;
-        OB_CUDA(cudaMemcpyAsync(pcm_out + w0 * pf, d->d_pcm + w0 * pf, cnt * pf * sizeof(float), cudaMemcpyDeviceToHost, d->copy_stream));
-        OB_CUDA(cudaMemcpyAsync(samples_out + w0, d->d_samples + w0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, d->copy_stream));
-        if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out + w0, d->d_ranges + w0, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->copy_stream));
+    const size_t pf = (size_t)frame_size * d->CC;
+    if (n_frames >= nchunks) {
+        // The symbol kernel is one thread per frame and latency bound (a launch takes >= 1.6 ms however few frames it covers:
+        // measured), so it runs once over the whole call; only the band + synthesis kernels are windowed.
+        const int per = (n_frames + nchunks - 1) / nchunks;
+        const int r0 = ob_launch(d, 0, d->S, n_frames, d->d_packets, d->d_offsets, d->d_lens, d->d_pcm, frame_size, d->d_samples, d->d_ranges, 0, d->stream, 0, n_frames, 1);
+        if (r0 != OB_OK) return r0;
+        for (int k = 0, f0 = 0; f0 < n_frames; k++, f0 += per) {
+            const int Fc = n_frames - f0 < per ? n_frames - f0 : per;
+            const int r = ob_launch(d, 0, d->S, n_frames, d->d_packets, d->d_offsets, d->d_lens, d->d_pcm, frame_size, d->d_samples, d->d_ranges, 0, d->stream, f0, Fc, 2);
+            if (r != OB_OK) return r;
+            OB_CUDA(cudaEventRecord(d->chunk_ev[k], d->stream));
+            OB_CUDA(cudaStreamWaitEvent(d->copy_stream, d->chunk_ev[k], 0));
+            OB_CUDA(cudaMemcpy2DAsync(pcm_out + f0 * pf, n_frames * pf * sizeof(float), d->d_pcm + f0 * pf, n_frames * pf * sizeof(float),
+                                      Fc * pf * sizeof(float), d->S, cudaMemcpyDeviceToHost, d->copy_stream));
+        }
+        OB_CUDA(cudaMemcpyAsync(samples_out, d->d_samples, total * sizeof(int32_t), cudaMemcpyDeviceToHost, d->copy_stream));
+        if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out, d->d_ranges, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->copy_stream));
+    } else {
+        const int per = (d->S + nchunks - 1) / nchunks;
+        OB_CUDA(cudaEventRecord(d->h2d_done, d->stream));
+        OB_CUDA(cudaStreamWaitEvent(d->aux_stream, d->h2d_done, 0));
+        for (int k = 0, s0 = 0; s0 < d->S; k++, s0 += per) {
+            const int Sc = d->S - s0 < per ? d->S - s0 : per;
+            const size_t w0 = (size_t)s0 * n_frames, cnt = (size_t)Sc * n_frames;
+            cudaStream_t cs = (k & 1) ? d->aux_stream : d->stream;       // alternate compute streams: kernels of neighbouring chunks overlap
+            const int r = ob_launch(d, s0, Sc, n_frames, d->d_packets, d->d_offsets, d->d_lens, d->d_pcm, frame_size, d->d_samples, d->d_ranges, 0, cs);
+            if (r != OB_OK) return r;
+            OB_CUDA(cudaEventRecord(d->chunk_ev[k], cs));
+            OB_CUDA(cudaStreamWaitEvent(d->copy_stream, d->chunk_ev[k], 0));
+            OB_CUDA(cudaMemcpyAsync(pcm_out + w0 * pf, d->d_pcm + w0 * pf, cnt * pf * sizeof(float), cudaMemcpyDeviceToHost, d->copy_stream));
+            OB_CUDA(cudaMemcpyAsync(samples_out + w0, d->d_samples + w0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, d->copy_stream));
+            if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out + w0, d->d_ranges + w0, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->copy_stream));
+        }
     }
     OB_CUDA(cudaEventRecord(d->copy_done, d->copy_stream));
     OB_CUDA(cudaStreamWaitEvent(d->stream, d->copy_done, 0));      // keep d->stream a faithful timeline of the whole call
