@@ -831,14 +831,19 @@ OB_DEV_NOINLINE void ob_decode_all_bands(ObRangeDec &ec, ObFrameIR *ir, int end,
 OB_DEV_NOINLINE void ob_decode_symbols(const uint8_t *pkt, int len, int dec_channels, int max_frame, ObFrameIR *ir)
 {
     ObFrameHdr &h = ir->hdr;
-    h.final_range = 0; h.n_leaves = 0; h.flags = 0; h.lcg_total = 0;
-    if (pkt == nullptr || len <= 0) { h.status = OB_UNIMPLEMENTED; return; }          // PLC: SURVEY 8(f) "next" row
+    h.final_range = 0; h.n_leaves = 0; h.flags = 0; h.lcg_total = 0; h.LM = 0; h.C = 1; h.end = 0;
+    if (pkt == nullptr || len <= 0) {
+        // lost packet: conceal the caller's whole slot, which must be a multiple of 2.5 ms (opus_decoder.c:684-688, :715-729)
+        if (max_frame <= 0 || max_frame % OB_SHORT != 0) { h.status = OB_BAD_ARG; return; }
+        h.status = max_frame; h.flags = OB_F_LOST;
+        return;
+    }
     const int toc = pkt[0];
     if (!(toc & 0x80)) { h.status = OB_UNIMPLEMENTED; return; }                        // SILK / hybrid
     if (toc & 0x3) { h.status = OB_UNIMPLEMENTED; return; }                            // multi-frame packets
     const int LM = (toc >> 3) & 3, M = 1 << LM, N = OB_SHORT << LM;
     if (N > max_frame) { h.status = OB_BUFFER_TOO_SMALL; return; }
-    if (len <= 2) { h.status = OB_UNIMPLEMENTED; return; }                             // payload <= 1 byte -> PLC/DTX
+    if (len <= 2) { h.status = N; h.flags = OB_F_LOST; return; }                       // payload <= 1 byte: DTX, concealed for the TOC's duration (opus_decoder.c:284-290)
     if (len - 1 > 1275) { h.status = OB_BAD_ARG; return; }
     const int C = (toc & 4) ? 2 : 1;
     const int bw = (toc >> 5) & 3;

@@ -10,18 +10,25 @@
 #include "ob_group.cuh"
 #include "dec_bands.cuh"     // ObLcg, OB_SQRTF, tables via dec_symbols.cuh
 
-#define OB_HISTK 1032                       // post-filter history kept per channel: >= COMBFILTER_MAXPERIOD + 2 (celt.h:218)
+#define OB_HISTK 1056                       // history kept per channel in SHARED memory: the post-filter reads back COMBFILTER_MAXPERIOD + 2
+                                            // samples (celt.h:218), the concealment's LPC analysis MAX_PERIOD + CELT_LPC_ORDER = 1048
+#define OB_RING 2048                        // DECODE_BUFFER_SIZE (celt_decoder.c:72): the full history, kept as a ring in GLOBAL memory;
+                                            // only the concealment's pitch search (first lost frame of a burst) reads beyond OB_HISTK
 #define OB_BUF_LEN (OB_HISTK + OB_MAX_N + OB_OVERLAP)
 
-// Persistent per-stream decoder state (the non-PLC part of struct OpusCustomDecoder, celt_decoder.c:80-123).
+// Persistent per-stream decoder state (struct OpusCustomDecoder, celt_decoder.c:80-123, minus the configuration).
 struct ObDecState {
-    uint32_t rng;                 // st->rng: range-coder state left by the last decoded frame (noise seed)
+    // owned by the plan pass (ObPlanState, dec_plc.cuh): the integer loss state machine
+    uint32_t rng;                 // st->rng: range-coder state left by the last decoded frame, advanced by noise PLC (noise seed)
+    int32_t loss_duration, skip_plc, plc_end;
+    // owned by the synthesis kernel
     uint32_t final_range;         // OpusDecoder.rangeFinal of the last call (opus_decoder.c:651-654)
     int32_t pf_period, pf_period_old, pf_tapset, pf_tapset_old;
     float pf_gain, pf_gain_old;
     float preemph_mem[2];
     int32_t last_packet_duration;
-    int32_t pad;
+    int32_t prefilter_and_fold, last_pitch_index, ring_pos, pad;
+    float lpc[2][24];             // CELT_LPC_ORDER coefficients per channel, kept across consecutive losses (celt_decoder.c:637)
     float oldBandE[2 * OB_NB], oldLogE[2 * OB_NB], oldLogE2[2 * OB_NB], backgroundLogE[2 * OB_NB];
 };
 
@@ -218,7 +225,10 @@ struct ObSynthShared {
     uint8_t band_of_bin[104];        // 2.5 ms bin -> band index (21 = above the last band)
     int32_t pf_period, pf_period_old, pf_tapset, pf_tapset_old;
     float pf_gain, pf_gain_old, preemph_mem[2];
-    uint32_t rng;
+    float lpc[2][24];
+    int32_t last_pitch_index, paf;   // paf = st->prefilter_and_fold
+    int32_t ring_pos;                // next write position (= oldest sample) of the global history ring
+    float *ring;                     // this stream's ring: [CC][OB_RING]
 };
 
 // Once per block: lookup tables in shared memory.
@@ -278,6 +288,127 @@ OB_DEV void ob_anti_collapse(const G &g, ObSynthShared &sh, float *X, int N, uin
     }
 }
 
+#include "dec_plc.cuh"
+
+// denormalise_bands (bands.c:196-265) on the X tile in sh.freq (C coded channels, energies in sh.oldBandE), the mono<->stereo
+// cases of celt_synthesis (celt_decoder.c:415-441) and the inverse MDCTs into buf[c] + HISTK.
+template <class G>
+OB_DEV void ob_denorm_imdct(const G &g, ObSynthShared &sh, int C, int CC, int N, int LM, int end, int transient, int silence)
+{
+    const int M = 1 << LM;
+    for (int t = g.lane; t < C * OB_NB; t += g.n) {
+        const int i = t % OB_NB;
+        const float lg = sh.oldBandE[t] + OB_EMEANS[i];
+        sh.gain[t] = (i < end && !silence) ? (float)exp(0.6931471805599453094 * (double)(lg < 32.f ? lg : 32.f)) : 0.f;
+    }
+    g.sync();
+    for (int c = 0; c < C; c++)
+        for (int j = g.lane; j < N; j += g.n) {
+            const int bin = j >> LM, band = bin < 100 ? sh.band_of_bin[bin] : OB_NB;
+            sh.freq[c][j] = band < OB_NB ? sh.freq[c][j] * sh.gain[c * OB_NB + band] : 0.f;
+        }
+    g.sync();
+    if (CC == 2 && C == 1) { for (int j = g.lane; j < N; j += g.n) sh.freq[1][j] = sh.freq[0][j]; g.sync(); }
+    if (CC == 1 && C == 2) { for (int j = g.lane; j < N; j += g.n) sh.freq[0][j] = .5f * sh.freq[0][j] + .5f * sh.freq[1][j]; g.sync(); }
+    for (int c = 0; c < CC; c++)
+        ob_imdct(g, sh.freq[c], sh.buf[c] + OB_HISTK, transient ? 3 : 3 - LM, transient ? M : 1);
+}
+
+// de-emphasis (celt_decoder.c:249-377): y[n] = x[n] + coef*y[n-1] as a two-level scan, interleaved PCM out, then the history
+// slides by N: buf[j] <- buf[j+N] for j < HISTK + overlap (celt_decoder.c:1265-1267, done after the frame instead of before).
+template <class G>
+OB_DEV void ob_synth_tail(const G &g, ObSynthShared &sh, float *pcm, int N, int CC)
+{
+    {
+        const float coef = OB_PREEMPH[0];
+        const int per = (N + g.n - 1) / g.n;                         // samples per lane
+        for (int c = 0; c < CC; c++) {
+            const float *x = sh.buf[c] + OB_HISTK;
+            float *y = sh.freq[c];
+            const int lo = ob_imin(N, g.lane * per), hi = ob_imin(N, lo + per);
+            float m = 0.f;
+            for (int j = lo; j < hi; j++) { const float t = x[j] + 1e-30f + m; m = coef * t; }
+            // m = coef * (local response at the chunk end); affine map of the carry: m_out = a * m_in + m
+            float a = 1.f;
+            for (int j = lo; j < hi; j++) a *= coef;
+            sh.scanA[g.lane] = a; sh.scanB[g.lane] = m;
+            g.sync();
+            // exclusive scan of affine maps (Hillis-Steele inclusive, then shift)
+            for (int o = 1; o < g.n; o <<= 1) {
+                float pa = 1.f, pb = 0.f;
+                const int have = g.lane >= o;
+                if (have) { pa = sh.scanA[g.lane - o]; pb = sh.scanB[g.lane - o]; }
+                g.sync();
+                if (have) { sh.scanB[g.lane] = sh.scanA[g.lane] * pb + sh.scanB[g.lane]; sh.scanA[g.lane] = sh.scanA[g.lane] * pa; }
+                g.sync();
+            }
+            // carry-in of this lane = inclusive result of lane-1 applied to the stream's memory
+            float carry = sh.preemph_mem[c];
+            if (g.lane > 0) carry = sh.scanA[g.lane - 1] * sh.preemph_mem[c] + sh.scanB[g.lane - 1];
+            const float last_all = sh.scanA[g.n - 1] * sh.preemph_mem[c] + sh.scanB[g.n - 1];
+            m = carry;
+            for (int j = lo; j < hi; j++) { const float t = x[j] + 1e-30f + m; m = coef * t; y[j] = t * (1.f / 32768.f); }
+            g.sync();
+            if (g.lane == 0) sh.preemph_mem[c] = last_all;
+            g.sync();
+        }
+        if (CC == 1) { for (int t = g.lane; t < N; t += g.n) pcm[t] = sh.freq[0][t]; }
+        else { for (int t = g.lane; t < 2 * N; t += g.n) pcm[t] = sh.freq[t & 1][t >> 1]; }
+        g.sync();
+    }
+    for (int c = 0; c < CC; c++) {                                   // the frame joins the full-length history ring
+        float *r = sh.ring + c * OB_RING;
+        const float *x = sh.buf[c] + OB_HISTK;
+        for (int j = g.lane; j < N; j += g.n) r[(sh.ring_pos + j) & (OB_RING - 1)] = x[j];
+    }
+    g.sync();
+    if (g.lane == 0) sh.ring_pos = (sh.ring_pos + N) & (OB_RING - 1);
+    for (int c = 0; c < CC; c++) {
+        float *b = sh.buf[c];
+        const int total = OB_HISTK + OB_OVERLAP;
+        for (int base = 0; base < total; base += N) {               // move in blocks of N: source block lies fully ahead of dest
+            const int lim = ob_imin(total, base + N);
+            for (int j = base + g.lane; j < lim; j += g.n) b[j] = b[j + N];
+            g.sync();
+        }
+    }
+}
+
+// A lost packet or DTX payload: conceal h.status samples as the reference does, frame by frame (opus_decoder.c:313-335,
+// celt_decode_lost celt_decoder.c:604-968).  The integer side of the state (loss duration, skip_plc, noise seed) was stamped
+// into the header by the plan pass and is re-derived here per concealment frame with the same functions.
+template <class G>
+OB_DEV_NOINLINE int ob_conceal(const G &g, ObSynthShared &sh, float *pcm, int CC)
+{
+    const ObFrameHdr &h = sh.hdr;
+    const int total = h.status;
+    if (h.end_in == 0) {                                             // nothing decoded yet: zeros (opus_decoder.c:302-309)
+        for (int t = g.lane; t < total * CC; t += g.n) pcm[t] = 0.f;
+        g.sync();
+        return total;
+    }
+    ObPlanState p;
+    p.rng = h.seed_in; p.loss_duration = h.loss_in; p.skip_plc = h.skip_in; p.plc_end = h.end_in;
+    for (int done = 0; done < total;) {
+        const int N = ob_plc_chunk(total - done), LM = N == 960 ? 3 : N == 480 ? 2 : N == 240 ? 1 : 0;
+        if (ob_plc_noise_based(p.loss_duration, p.skip_plc)) {
+            if (sh.paf) ob_prefilter_and_fold(g, sh, CC);
+            ob_plc_noise_fill(g, sh, N, LM, p.loss_duration, p.rng, p.plc_end, CC);
+            ob_denorm_imdct(g, sh, CC, CC, N, LM, ob_imin(p.plc_end, OB_NB), 0, 0);
+            g.sync();
+            if (g.lane == 0) sh.paf = 0;
+        } else {
+            ob_plc_pitch(g, sh, N, p.loss_duration, CC);
+            if (g.lane == 0) sh.paf = 1;
+        }
+        g.sync();
+        ob_plc_advance(p, N, CC);
+        ob_synth_tail(g, sh, pcm + (size_t)done * CC, N, CC);
+        done += N;
+    }
+    return total;
+}
+
 // Decodes frame `ir` (already reconstructed normalised spectrum Xg: C*N floats in global memory) into pcm
 // (interleaved, CC channels) and advances the shared-memory state.  Returns samples per channel or an error.
 template <class G>
@@ -292,13 +423,15 @@ OB_DEV int ob_synth_frame(const G &g, ObSynthShared &sh, const ObFrameIR *ir, co
     g.sync();
     const ObFrameHdr &h = sh.hdr;
     if (h.status <= 0) return h.status;
+    if (h.flags & OB_F_LOST) return ob_conceal(g, sh, pcm, CC);
     const int LM = h.LM, M = 1 << LM, N = OB_SHORT << LM, C = h.C, end = h.end;
     const int transient = (h.flags & OB_F_TRANSIENT) != 0, silence = (h.flags & OB_F_SILENCE) != 0;
-    const uint32_t seed_in = sh.rng;
+    const uint32_t seed_in = h.seed_in;
 
     // ---- energies: coarse recurrence + fine + finalise (quant_bands.c:428-542); one lane per channel ----
     if (C == 1) for (int i = g.lane; i < OB_NB; i += g.n) sh.oldBandE[i] = fmaxf(sh.oldBandE[i], sh.oldBandE[OB_NB + i]);
     g.sync();
+    if (!(h.flags & OB_F_INTRA) && h.loss_in != 0) ob_post_loss_energy(g, sh, LM, end, h.loss_in);
     for (int c = g.lane; c < C; c += g.n) {
         const int intra = (h.flags & OB_F_INTRA) != 0;
         const float coef = intra ? 0.f : OB_PRED_COEF[LM], beta = intra ? OB_BETA_INTRA[0] : OB_BETA_COEF[LM];
@@ -330,26 +463,10 @@ OB_DEV int ob_synth_frame(const G &g, ObSynthShared &sh, const ObFrameIR *ir, co
     }
     if (silence) { for (int i = g.lane; i < C * OB_NB; i += g.n) sh.oldBandE[i] = -28.f; }
     g.sync();
+    if (sh.paf) ob_prefilter_and_fold(g, sh, CC);                    // first frame after a pitch-based concealment (celt_decoder.c:1295-1297)
 
-    // ---- denormalise (bands.c:196-265): per-band gain, zero above the last coded band ----
-    for (int t = g.lane; t < C * OB_NB; t += g.n) {
-        const int i = t % OB_NB;
-        const float lg = sh.oldBandE[t] + OB_EMEANS[i];
-        sh.gain[t] = (i < end && !silence) ? (float)exp(0.6931471805599453094 * (double)(lg < 32.f ? lg : 32.f)) : 0.f;
-    }
-    g.sync();
-    for (int c = 0; c < C; c++)
-        for (int j = g.lane; j < N; j += g.n) {
-            const int bin = j >> LM, band = bin < 100 ? sh.band_of_bin[bin] : OB_NB;
-            sh.freq[c][j] = band < OB_NB ? sh.freq[c][j] * sh.gain[c * OB_NB + band] : 0.f;
-        }
-    g.sync();
-    if (CC == 2 && C == 1) { for (int j = g.lane; j < N; j += g.n) sh.freq[1][j] = sh.freq[0][j]; g.sync(); }
-    if (CC == 1 && C == 2) { for (int j = g.lane; j < N; j += g.n) sh.freq[0][j] = .5f * sh.freq[0][j] + .5f * sh.freq[1][j]; g.sync(); }
-
-    // ---- inverse MDCT into buf[c] + HISTK (celt_synthesis, celt_decoder.c:382-458) ----
-    for (int c = 0; c < CC; c++)
-        ob_imdct(g, sh.freq[c], sh.buf[c] + OB_HISTK, transient ? 3 : 3 - LM, transient ? M : 1);
+    // ---- denormalise + inverse MDCT into buf[c] + HISTK (celt_synthesis, celt_decoder.c:382-458) ----
+    ob_denorm_imdct(g, sh, C, CC, N, LM, end, transient, silence);
 
     // ---- pitch post-filter (celt_decoder.c:1301-1325) ----
     const float pf_gain_new = (h.flags & OB_F_POSTFILTER) ? .09375f * (float)(h.pf_qg + 1) : 0.f;
@@ -366,7 +483,7 @@ OB_DEV int ob_synth_frame(const G &g, ObSynthShared &sh, const ObFrameIR *ir, co
             sh.pf_period_old = p; sh.pf_gain_old = sh.pf_gain; sh.pf_tapset_old = sh.pf_tapset;
             sh.pf_period = pf_pitch_new; sh.pf_gain = pf_gain_new; sh.pf_tapset = pf_tapset_new;
             if (LM != 0) { sh.pf_period_old = sh.pf_period; sh.pf_gain_old = sh.pf_gain; sh.pf_tapset_old = sh.pf_tapset; }
-            sh.rng = h.final_range;
+            sh.paf = 0;
         }
     }
 
@@ -378,62 +495,11 @@ OB_DEV int ob_synth_frame(const G &g, ObSynthShared &sh, const ObFrameIR *ir, co
         const float e = sh.oldBandE[i];
         if (!transient) { sh.oldLogE2[i] = sh.oldLogE[i]; sh.oldLogE[i] = e; }
         else sh.oldLogE[i] = fminf(sh.oldLogE[i], e);
-        sh.backgroundLogE[i] = fminf(sh.backgroundLogE[i] + (float)ob_imin(160, M) * 0.001f, e);
+        sh.backgroundLogE[i] = fminf(sh.backgroundLogE[i] + (float)ob_imin(160, h.loss_in + M) * 0.001f, e);
         if ((i % OB_NB) >= end) { sh.oldBandE[i] = 0.f; sh.oldLogE[i] = sh.oldLogE2[i] = -28.f; }
     }
     g.sync();
 
-    // ---- de-emphasis (celt_decoder.c:249-377): y[n] = x[n] + coef*y[n-1] as a two-level scan ----
-    {
-        const float coef = OB_PREEMPH[0];
-        const int per = (N + g.n - 1) / g.n;                         // samples per lane
-        float cp = 1.f;
-        for (int k = 0; k < per; k++) cp *= coef;                    // coef^per
-        for (int c = 0; c < CC; c++) {
-            const float *x = sh.buf[c] + OB_HISTK;
-            float *y = sh.freq[c];
-            const int lo = ob_imin(N, g.lane * per), hi = ob_imin(N, lo + per);
-            float m = 0.f;
-            for (int j = lo; j < hi; j++) { const float t = x[j] + 1e-30f + m; m = coef * t; }
-            // m = coef * (local response at the chunk end); affine map of the carry: m_out = cp' * m_in + m
-            float a = 1.f;
-            for (int j = lo; j < hi; j++) a *= coef;
-            sh.scanA[g.lane] = a; sh.scanB[g.lane] = m;
-            g.sync();
-            // exclusive scan of affine maps (Hillis-Steele inclusive, then shift)
-            for (int o = 1; o < g.n; o <<= 1) {
-                float pa = 1.f, pb = 0.f;
-                const int have = g.lane >= o;
-                if (have) { pa = sh.scanA[g.lane - o]; pb = sh.scanB[g.lane - o]; }
-                g.sync();
-                if (have) { sh.scanB[g.lane] = sh.scanA[g.lane] * pb + sh.scanB[g.lane]; sh.scanA[g.lane] = sh.scanA[g.lane] * pa; }
-                g.sync();
-            }
-            // carry-in of this lane = inclusive result of lane-1 applied to the stream's memory
-            float carry = sh.preemph_mem[c];
-            if (g.lane > 0) carry = sh.scanA[g.lane - 1] * sh.preemph_mem[c] + sh.scanB[g.lane - 1];
-            const float last_all = sh.scanA[g.n - 1] * sh.preemph_mem[c] + sh.scanB[g.n - 1];
-            m = carry;
-            for (int j = lo; j < hi; j++) { const float t = x[j] + 1e-30f + m; m = coef * t; y[j] = t * (1.f / 32768.f); }
-            g.sync();
-            if (g.lane == 0) sh.preemph_mem[c] = last_all;
-            g.sync();
-        }
-        (void)cp;
-        if (CC == 1) { for (int t = g.lane; t < N; t += g.n) pcm[t] = sh.freq[0][t]; }
-        else { for (int t = g.lane; t < 2 * N; t += g.n) pcm[t] = sh.freq[t & 1][t >> 1]; }
-        g.sync();
-    }
-
-    // ---- slide the history: buf[j] <- buf[j+N] for j < HISTK + overlap (celt_decoder.c:1265-1267, done after instead of before) ----
-    for (int c = 0; c < CC; c++) {
-        float *b = sh.buf[c];
-        const int total = OB_HISTK + OB_OVERLAP;
-        for (int base = 0; base < total; base += N) {               // move in blocks of N: source block lies fully ahead of dest
-            const int lim = ob_imin(total, base + N);
-            for (int j = base + g.lane; j < lim; j += g.n) b[j] = b[j + N];
-            g.sync();
-        }
-    }
+    ob_synth_tail(g, sh, pcm, N, CC);
     return N;
 }

@@ -57,6 +57,7 @@ struct ObBand {
 #define OB_F_INTRA 4
 #define OB_F_POSTFILTER 8
 #define OB_F_ANTICOLLAPSE 16
+#define OB_F_LOST 32             // lost packet (len == 0) or DTX payload (<= 1 byte): conceal `status` samples (opus_decoder.c:284-334, :715-729)
 
 struct ObFrameHdr {
     int32_t status;            // samples per channel (>0) or OPUS_* error (<0)
@@ -65,8 +66,11 @@ struct ObFrameHdr {
     uint16_t pf_pitch;         // post-filter period (celt_decoder.c:1145)
     uint8_t LM, C, end, flags;
     uint8_t spread, pf_tapset, pf_qg, coded_bands;
-    uint8_t intensity, dual_stereo, pad0[2];
+    uint8_t intensity, dual_stereo;
+    uint8_t skip_in, end_in;   // written by the plan pass: st->skip_plc and st->end (0 = no packet decoded yet) before this frame
     uint32_t lcg_total;        // LCG steps taken by all bands (seed for anti_collapse = jump(seed_in, lcg_total))
+    uint32_t seed_in;          // plan pass: st->rng before this frame (noise fill / folding seed, celt_decoder.c:1279)
+    int32_t loss_in;           // plan pass: st->loss_duration before this frame (2.5 ms units, celt_decoder.c:965)
     int16_t coarse_qi[2 * OB_NB];   // Laplace-decoded coarse energy deltas [c*21+i] (quant_bands.c:450-479)
     int16_t pulses[OB_NB];          // PVQ bit allocation per band, 1/8 bit (anti_collapse depth, bands.c:289)
     uint8_t fine_quant[OB_NB];      // fine energy bits per band (rate.c ebits)

@@ -36,10 +36,38 @@ ob_k_symbols(const uint8_t *__restrict__ packets, const int32_t *__restrict__ of
     ob_decode_symbols(len > 0 ? packets + offsets[t] : nullptr, len, dec_channels, max_frame, ir + t);
 }
 
+// Plan pass, one thread per stream: walks the frame window in order through the integer loss state machine (which frames are
+// concealed, noise- or pitch-based, how far the noise seed advances) and stamps every frame header with the state it starts from.
+// This is what lets the band kernel stay frame-parallel even though a lost packet changes the seed of the frames after it.
+__global__ void ob_k_plan(ObFrameIR *__restrict__ ir, ObDecState *__restrict__ st, int S, int F, int f0, int Fc, int CC)
+{
+    // One WARP per stream: the lanes fetch 32 headers at once (one 32-byte sector each, 12.6 KB apart), every lane then replays the
+    // serial state machine from registers and keeps the state in front of its own frame -- the memory latency is paid once per
+    // 32 frames instead of once per frame.
+    const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (s >= S) return;
+    ObPlanState p;
+    p.rng = st[s].rng; p.loss_duration = st[s].loss_duration; p.skip_plc = st[s].skip_plc; p.plc_end = st[s].plc_end;
+    for (int base = f0; base < f0 + Fc; base += 32) {
+        const int f = base + lane, cnt = min(32, f0 + Fc - base);
+        ObFrameHdr *h = f < f0 + Fc ? &ir[(size_t)s * F + f].hdr : nullptr;
+        const int status = h ? h->status : 0, flags = h ? h->flags : 0, end = h ? h->end : 0;
+        const uint32_t fr = h ? h->final_range : 0u;
+        ObPlanState mine = p;
+        for (int j = 0; j < cnt; j++) {
+            if (lane == j) mine = p;
+            ob_plan_step(p, __shfl_sync(0xffffffffu, status, j), __shfl_sync(0xffffffffu, flags, j), __shfl_sync(0xffffffffu, fr, j),
+                         __shfl_sync(0xffffffffu, end, j), CC);
+        }
+        if (h && status > 0) { h->seed_in = mine.rng; h->loss_in = mine.loss_duration; h->skip_in = (uint8_t)mine.skip_plc; h->end_in = (uint8_t)mine.plc_end; }
+    }
+    if (lane == 0) { st[s].rng = p.rng; st[s].loss_duration = p.loss_duration; st[s].skip_plc = p.skip_plc; st[s].plc_end = p.plc_end; }
+}
+
 #define OB_BANDS_WARPS 6
 #define OB_BANDS_SMEM_PER_WARP ((int)sizeof(ObBandsShared))
 __global__ void __launch_bounds__(OB_BANDS_WARPS * 32)
-ob_k_bands(const ObFrameIR *__restrict__ ir, const ObDecState *__restrict__ st, float *__restrict__ Xg, int S, int F, int f0, int Fc)
+ob_k_bands(const ObFrameIR *__restrict__ ir, float *__restrict__ Xg, int S, int F, int f0, int Fc)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
@@ -48,12 +76,8 @@ ob_k_bands(const ObFrameIR *__restrict__ ir, const ObDecState *__restrict__ st, 
     const int s = k / Fc, f = f0 + k % Fc;
     const size_t w = (size_t)s * F + f;
     const ObFrameIR *fr = ir + w;
-    const int status = fr->hdr.status;
-    if (status <= 0) return;
-    // seed = range-coder state left by the previous successfully decoded frame of this stream (inside this launch's frame
-    // window: from the IR; before it: the stream state the previous synthesis launch stored)
-    uint32_t seed = st[s].rng;
-    for (int p = f - 1; p >= f0; p--) if (ir[w - (f - p)].hdr.status > 0) { seed = ir[w - (f - p)].hdr.final_range; break; }
+    if (fr->hdr.status <= 0 || (fr->hdr.flags & OB_F_LOST)) return;
+    const uint32_t seed = fr->hdr.seed_in;       // st->rng before this frame, stamped by the plan pass
     ObBandsShared &sh = *reinterpret_cast<ObBandsShared *>(smem_raw + (size_t)warp * OB_BANDS_SMEM_PER_WARP);
     ObWarp g;
     ob_reconstruct_bands(g, fr, seed, sh, Xg + (size_t)w * OB_X_STRIDE);
@@ -61,7 +85,7 @@ ob_k_bands(const ObFrameIR *__restrict__ ir, const ObDecState *__restrict__ st, 
 
 #define OB_SYNTH_THREADS 128
 __global__ void __launch_bounds__(OB_SYNTH_THREADS)
-ob_k_synth(const ObFrameIR *__restrict__ ir, const float *__restrict__ Xg, ObDecState *__restrict__ st, float *__restrict__ hist,
+ob_k_synth(const ObFrameIR *__restrict__ ir, const float *__restrict__ Xg, ObDecState *__restrict__ st, float *__restrict__ hist, float *__restrict__ ring,
            float *__restrict__ pcm, int32_t *__restrict__ samples, uint32_t *__restrict__ ranges, int S, int F, int CC, int frame_size,
            int f0, int Fc)
 {
@@ -85,15 +109,21 @@ ob_k_synth(const ObFrameIR *__restrict__ ir, const float *__restrict__ Xg, ObDec
         sh.pf_tapset = state->pf_tapset; sh.pf_tapset_old = state->pf_tapset_old;
         sh.pf_gain = state->pf_gain; sh.pf_gain_old = state->pf_gain_old;
         sh.preemph_mem[0] = state->preemph_mem[0]; sh.preemph_mem[1] = state->preemph_mem[1];
-        sh.rng = state->rng;
+        sh.last_pitch_index = state->last_pitch_index; sh.paf = state->prefilter_and_fold;
+        sh.ring_pos = state->ring_pos; sh.ring = ring + (size_t)s * CC * OB_RING;
     }
+    for (int i = g.lane; i < 2 * 24; i += g.n) sh.lpc[i / 24][i % 24] = state->lpc[i / 24][i % 24];
     uint32_t final_range = state->final_range;
     int last_dur = state->last_packet_duration;
     g.sync();
     for (int f = f0; f < f0 + Fc; f++) {
         const size_t w = (size_t)s * F + f;
         const int n = ob_synth_frame(g, sh, ir + w, Xg + w * OB_X_STRIDE, pcm + w * (size_t)frame_size * CC, CC);
-        if (n > 0) { final_range = sh.hdr.final_range; last_dur = n; }
+        if (n > 0) {
+            last_dur = n;
+            if (!(sh.hdr.flags & OB_F_LOST)) final_range = sh.hdr.final_range;
+            else if (sh.hdr.end_in != 0) final_range = 0;          // concealed frame: rangeFinal = 0 (opus_decoder.c:651-652)
+        }
         if (g.lane == 0) { samples[w] = n; if (ranges) ranges[w] = final_range; }
         g.sync();
     }
@@ -111,12 +141,14 @@ ob_k_synth(const ObFrameIR *__restrict__ ir, const float *__restrict__ Xg, ObDec
         state->pf_tapset = sh.pf_tapset; state->pf_tapset_old = sh.pf_tapset_old;
         state->pf_gain = sh.pf_gain; state->pf_gain_old = sh.pf_gain_old;
         state->preemph_mem[0] = sh.preemph_mem[0]; state->preemph_mem[1] = sh.preemph_mem[1];
-        state->rng = sh.rng; state->final_range = final_range; state->last_packet_duration = last_dur;
+        state->final_range = final_range; state->last_packet_duration = last_dur;
+        state->last_pitch_index = sh.last_pitch_index; state->prefilter_and_fold = sh.paf; state->ring_pos = sh.ring_pos;
     }
+    for (int i = g.lane; i < 2 * 24; i += g.n) state->lpc[i / 24][i % 24] = sh.lpc[i / 24][i % 24];
 }
 
 // OPUS_RESET_STATE (celt_decoder.c:1514-1529): zero everything, oldLogE = oldLogE2 = -28.
-__global__ void ob_k_reset(ObDecState *st, float *hist, const int32_t *idx, int n, int S, int CC)
+__global__ void ob_k_reset(ObDecState *st, float *hist, float *ring, const int32_t *idx, int n, int S, int CC)
 {
     const int k = blockIdx.x;
     if (k >= n) return;
@@ -126,8 +158,11 @@ __global__ void ob_k_reset(ObDecState *st, float *hist, const int32_t *idx, int 
     for (int i = threadIdx.x; i < (int)(sizeof(ObDecState) / 4); i += blockDim.x) ((uint32_t *)state)[i] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * OB_NB; i += blockDim.x) { state->oldLogE[i] = -28.f; state->oldLogE2[i] = -28.f; }
+    if (threadIdx.x == 0) state->skip_plc = 1;                       // celt_decoder.c:1527
     float *h = hist + (size_t)s * CC * OB_HIST_LEN;
     for (int i = threadIdx.x; i < CC * OB_HIST_LEN; i += blockDim.x) h[i] = 0.f;
+    float *r = ring + (size_t)s * CC * OB_RING;
+    for (int i = threadIdx.x; i < CC * OB_RING; i += blockDim.x) r[i] = 0.f;
 }
 
 __global__ void ob_k_gather_state(const ObDecState *st, uint32_t *ranges, int32_t *durations, int S)
@@ -150,7 +185,7 @@ struct ObDecoder {
     cudaEvent_t ev[4], chunk_ev[OB_MAX_CHUNKS], copy_done, h2d_done;
     bool timed;
     ObDecState *d_state;
-    float *d_hist;
+    float *d_hist, *d_ring;
     ObFrameIR *d_ir;
     float *d_X;
     // staging for the host-pointer entry points
@@ -176,6 +211,7 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
     float *X = d->d_X + w0 * OB_X_STRIDE;
     ObDecState *st = d->d_state + s0;
     float *hist = d->d_hist + (size_t)s0 * d->CC * OB_HIST_LEN;
+    float *ring = d->d_ring + (size_t)s0 * d->CC * OB_RING;
     if (timed) OB_CUDA(cudaEventRecord(d->ev[0], stream));
     if (which & 1) {
         ob_k_symbols<<<(total + OB_SYM_THREADS - 1) / OB_SYM_THREADS, OB_SYM_THREADS, 0, stream>>>(
@@ -184,12 +220,13 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
     }
     if (timed) OB_CUDA(cudaEventRecord(d->ev[1], stream));
     if (which & 2) {
+        ob_k_plan<<<(Sc + 3) / 4, 128, 0, stream>>>(ir, st, Sc, F, f0, Fc, d->CC);
         ob_k_bands<<<(total + OB_BANDS_WARPS - 1) / OB_BANDS_WARPS, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, stream>>>(
-            ir, st, X, Sc, F, f0, Fc);
+            ir, X, Sc, F, f0, Fc);
         if (timed) OB_CUDA(cudaEventRecord(d->ev[2], stream));
-        ob_k_synth<<<Sc, OB_SYNTH_THREADS, 0, stream>>>(ir, X, st, hist, d_pcm + w0 * (size_t)frame_size * d->CC, d_samples + w0,
+        ob_k_synth<<<Sc, OB_SYNTH_THREADS, 0, stream>>>(ir, X, st, hist, ring, d_pcm + w0 * (size_t)frame_size * d->CC, d_samples + w0,
                                                          d_ranges ? d_ranges + w0 : nullptr, Sc, F, d->CC, frame_size, f0, Fc);
-        d->launches += 2;
+        d->launches += 3;
     }
     if (timed) OB_CUDA(cudaEventRecord(d->ev[3], stream));
     OB_CUDA(cudaGetLastError());
@@ -228,6 +265,7 @@ ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         ok = ok && cudaStreamCreateWithFlags(&d->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_state, sizeof(ObDecState) * n_streams) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_hist, sizeof(float) * (size_t)n_streams * channels * OB_HIST_LEN) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->d_ring, sizeof(float) * (size_t)n_streams * channels * OB_RING) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_ir, sizeof(ObFrameIR) * total) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_X, sizeof(float) * OB_X_STRIDE * total) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_offsets, sizeof(int32_t) * total) == cudaSuccess;
@@ -255,7 +293,7 @@ void ob_decoder_destroy(ObDecoder *d)
     if (!d) return;
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
-    cudaFree(d->d_state); cudaFree(d->d_hist); cudaFree(d->d_ir); cudaFree(d->d_X); cudaFree(d->d_packets);
+    cudaFree(d->d_state); cudaFree(d->d_hist); cudaFree(d->d_ring); cudaFree(d->d_ir); cudaFree(d->d_X); cudaFree(d->d_packets);
     cudaFree(d->d_offsets); cudaFree(d->d_lens); cudaFree(d->d_samples); cudaFree(d->d_ranges); cudaFree(d->d_pcm);
     for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     for (int i = 0; i < OB_MAX_CHUNKS; i++) if (d->chunk_ev[i]) cudaEventDestroy(d->chunk_ev[i]);
@@ -279,7 +317,7 @@ int32_t ob_decoder_reset(ObDecoder *d, const int32_t *idx, int32_t n)
         OB_CUDA(cudaMalloc(&d_idx, sizeof(int32_t) * n));
         OB_CUDA(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, d->stream));
     }
-    ob_k_reset<<<count, 128, 0, d->stream>>>(d->d_state, d->d_hist, d_idx, count, d->S, d->CC);
+    ob_k_reset<<<count, 128, 0, d->stream>>>(d->d_state, d->d_hist, d->d_ring, d_idx, count, d->S, d->CC);
     d->launches += 1;
     OB_CUDA(cudaStreamSynchronize(d->stream));
     if (d_idx) cudaFree(d_idx);

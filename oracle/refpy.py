@@ -135,7 +135,7 @@ def _encode_stream(pcm, frame_size, channels, bitrate, vbr, complexity, applicat
     return out, lens, rng
 
 
-def decode_stream(pkts, lens, frame_size, channels, want_taps=False):
+def decode_stream(pkts, lens, frame_size, channels, want_taps=False, pure_c=False):
     """pkts u8 [nframes, stride] -> (pcm f32 [nframes, frame_size*channels], ranges u32, samples i32[, taps])."""
     pkts = np.ascontiguousarray(pkts, np.uint8)
     lens = np.ascontiguousarray(lens, np.int32)
@@ -145,7 +145,7 @@ def decode_stream(pkts, lens, frame_size, channels, want_taps=False):
     smp = np.zeros(nframes, np.int32)
     taps = (Tap * nframes)() if want_taps else None
     assert not want_taps or C.sizeof(Tap) == lib().ref_tap_size()
-    r = lib().ref_decode_stream(_p(pkts, C.c_ubyte), _p(lens, C.c_int), stride, nframes, frame_size, channels,
+    r = (lib_c() if pure_c else lib()).ref_decode_stream(_p(pkts, C.c_ubyte), _p(lens, C.c_int), stride, nframes, frame_size, channels,
                                 _p(pcm, C.c_float), _p(rng, C.c_uint32), _p(smp, C.c_int),
                                 C.cast(taps, C.c_void_p) if want_taps else None)
     if r != 0:

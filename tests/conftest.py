@@ -14,7 +14,19 @@ def pytest_configure(config):
 
 def golden_names():
     g = os.path.join(ROOT, "tests", "golden")
-    return sorted(f[:-4] for f in os.listdir(g) if f.endswith(".npz") and not f.startswith("pool_"))
+    return sorted(f[:-4] for f in os.listdir(g) if f.endswith(".npz") and not f.startswith(("pool_", "plc_")))
+
+
+def plc_golden_names():
+    """Base names of the packet-loss fixtures (tests/golden/plc_<base>.npz, made by make_golden_plc.py)."""
+    g = os.path.join(ROOT, "tests", "golden")
+    return sorted(f[4:-4] for f in os.listdir(g) if f.endswith(".npz") and f.startswith("plc_"))
+
+
+def load_plc_golden(base):
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", "plc_" + base + ".npz"))
+    return {k: z[k] for k in z.files}
 
 
 def load_golden(name):

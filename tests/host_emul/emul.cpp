@@ -32,20 +32,27 @@ int emul_decode_stream(const uint8_t *pkts, const int *lens, int stride, int nfr
     for (int i = 0; i < 2 * OB_NB; i++) sh->oldLogE[i] = sh->oldLogE2[i] = -28.f;
     ObSolo g;
     ob_synth_init(g, *sh);
+    sh->ring = (float *)calloc(2 * OB_RING, sizeof(float));
+    ObPlanState plan = {0u, 0, 1, 0};                     // OPUS_RESET_STATE: skip_plc = 1 (celt_decoder.c:1527)
+    uint32_t final_range = 0;
     for (int f = 0; f < nframes; f++) {
         memset(ir, 0, sizeof(*ir));
-        ob_decode_symbols(pkts + (size_t)f * stride, lens[f], dec_channels, max_frame, ir);
+        ob_decode_symbols(lens[f] > 0 ? pkts + (size_t)f * stride : nullptr, lens[f], dec_channels, max_frame, ir);
+        ob_plan_frame(plan, ir->hdr, dec_channels);
         int n = ir->hdr.status;
         if (n > 0) {
-            for (int j = 0; j < 2 * OB_MAX_N; j++) X[j] = __builtin_nanf("");     // bands >= end are never written
-            ob_reconstruct_bands(g, ir, sh->rng, *bsh, X);
-            if (Xtap) memcpy(Xtap + (size_t)f * 1920, X, sizeof(float) * ir->hdr.C * n);
+            if (!(ir->hdr.flags & OB_F_LOST)) {
+                for (int j = 0; j < 2 * OB_MAX_N; j++) X[j] = __builtin_nanf("");     // bands >= end are never written
+                ob_reconstruct_bands(g, ir, ir->hdr.seed_in, *bsh, X);
+                if (Xtap) memcpy(Xtap + (size_t)f * 1920, X, sizeof(float) * ir->hdr.C * n);
+                final_range = ir->hdr.final_range;
+            } else if (ir->hdr.end_in != 0) final_range = 0;
             n = ob_synth_frame(g, *sh, ir, X, pcm_out + (size_t)f * max_frame * dec_channels, dec_channels);
         }
         samples[f] = n;
-        ranges[f] = n > 0 ? ir->hdr.final_range : 0;
+        ranges[f] = final_range;
     }
-    free(sh); free(ir); free(X); free(bsh);
+    free(sh->ring); free(sh); free(ir); free(X); free(bsh);
     return 0;
 }
 }

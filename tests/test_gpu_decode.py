@@ -10,7 +10,7 @@ import tempfile
 import numpy as np
 import pytest
 
-from conftest import golden_names, load_golden
+from conftest import plc_golden_names, load_plc_golden, golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
 PCM_TOL = 1e-4
@@ -89,16 +89,16 @@ def test_per_stream_errors_do_not_disturb_neighbours():
     pk = g["packets"][:S, :F].copy()
     ln = g["lens"][:S, :F].copy()
     stride = pk.shape[2]
-    ln[1, 3] = 0                      # lost packet -> PLC is not on this path: UNIMPLEMENTED, state untouched
+    ln[1, 3] = 0                      # lost packet -> concealed: 960 samples, final range 0
     pk[2, 4, 0] = 0x08                # SILK TOC
     pk[3, 5, 0] = 0xF9                # code-1 packet (two frames)
-    ln[4, 6] = 2                      # 1-byte payload -> DTX/PLC
+    ln[4, 6] = 2                      # 1-byte payload -> DTX, concealed for the TOC's duration
     with BatchDecoder(S, 48000, 1, device=0, max_frames=F) as dec:
         pcm, samples, ranges = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, 960)
-    assert samples[1, 3] == UNIMPLEMENTED and samples[2, 4] == UNIMPLEMENTED
-    assert samples[3, 5] == UNIMPLEMENTED and samples[4, 6] == UNIMPLEMENTED
+    assert samples[2, 4] == UNIMPLEMENTED and samples[3, 5] == UNIMPLEMENTED
+    assert samples[1, 3] == 960 and samples[4, 6] == 960 and ranges[1, 3] == 0 and ranges[4, 6] == 0
     good = np.ones((S, F), bool)
-    for s, f in ((1, 3), (2, 4), (3, 5), (4, 6)):
+    for s, f in ((2, 4), (3, 5)):
         good[s, f] = False
     assert (samples[good] == 960).all()
     assert (ranges[0] == g["dec_rng"][0, :F]).all() and (ranges[5] == g["dec_rng"][5, :F]).all()
@@ -109,6 +109,58 @@ def test_per_stream_errors_do_not_disturb_neighbours():
     with BatchDecoder(S, 48000, 1, device=0, max_frames=F) as dec:
         _, samples, _ = dec.decode_float_multi(np.ascontiguousarray(g["packets"][:S, :F]).reshape(-1), _offsets(S, F, stride), g["lens"][:S, :F], 480)
     assert (samples == BUFFER_TOO_SMALL).all()
+
+
+@pytest.mark.parametrize("base", plc_golden_names())
+def test_packet_loss_concealment_matches_reference(base):
+    """Lost packets (len 0), DTX payloads (<= 1 byte), noise- and pitch-based concealment, recovery after a loss: samples and
+    final range bit-exact, PCM within 1e-4 of the reference's pure-C build (the reference's own SSE build differs from its C build
+    by up to 2e-3 in concealed frames -- stored per frame in the fixture as sse_diff -- so the C build is the bar)."""
+    from opus_codec_b200.batch import BatchDecoder
+    g, p = load_golden(base), load_plc_golden(base)
+    fs, dc = g["frame_size"], g["dec_channels"]
+    S, F = p["lens"].shape
+    pk = np.ascontiguousarray(g["packets"][:S, :F]); stride = pk.shape[2]
+    with BatchDecoder(S, 48000, dc, device=0, max_frames=F) as dec:
+        pcm, samples, ranges = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), p["lens"], fs)
+        assert (samples == p["samples"]).all() and (ranges == p["ranges"]).all()
+        err = np.abs(pcm.reshape(S, F, -1) - p["pcm_c"]).max(axis=2)
+        # Frames on which the reference's two builds agree (sse_diff <= 1e-6: everything but concealed frames and the few
+        # recovery frames after them) must meet the 1e-4 bar.  Concealment re-derives an order-24 LPC filter from the decoded
+        # history; that analysis amplifies last-bit differences of the history by ~1e3 (the reference's SSE build is up to 2e-3
+        # away from its C build there), so those frames are held to the reference's own spread instead.  The exact arithmetic
+        # of the concealment is pinned to 1e-6 by tests/test_host_emul.py.
+        calm = p["sse_diff"] <= 1e-6
+        assert err[calm].max() <= 1e-4, (float(err[calm].max()), np.argwhere(calm & (err > 1e-4))[:5].tolist())
+        assert err.max() <= 3e-3, (float(err.max()), np.argwhere(err > 3e-3)[:5].tolist())
+        # the same packets one call per frame (live streaming): identical output
+        dec.reset()
+        for f in range(F):
+            one, smp1, rng1 = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride)[:, f:f + 1], p["lens"][:, f:f + 1], fs)
+            assert (smp1[:, 0] == p["samples"][:, f]).all() and (rng1[:, 0] == p["ranges"][:, f]).all()
+            assert np.array_equal(one.reshape(S, -1), pcm.reshape(S, F, -1)[:, f])
+
+
+def test_lost_packet_slot_larger_than_20ms_is_concealed_in_pieces(have_ref):
+    """A lost packet conceals the caller's whole slot; slots that are not a CELT frame size are covered by several concealment
+    frames (opus_decoder.c:313-335): 1440 = 960 + 480, 720 = 480 + 240."""
+    from oracle import refpy
+    if not have_ref or not os.path.exists(os.path.join(os.path.dirname(refpy.OPUS_COMPARE), "libopus_ref_c.so")):
+        pytest.skip("oracle/_ref not built")
+    from opus_codec_b200.batch import BatchDecoder
+    g = load_golden("cfg2_mono_20ms_64k_cbr")
+    S, F = 2, 8
+    pk = np.ascontiguousarray(g["packets"][:S, :F]); stride = pk.shape[2]
+    for slot in (1440, 720):
+        ln = g["lens"][:S, :F].copy()
+        ln[:, 4] = 0; ln[1, 5] = 0
+        with BatchDecoder(S, 48000, 1, device=0, max_frames=F) as dec:
+            pcm, samples, ranges = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, slot)
+        for s in range(S):
+            rp, rr, rs = refpy.decode_stream(pk[s], ln[s], slot, 1, pure_c=True)
+            assert (samples[s] == rs).all() and (ranges[s] == rr).all()
+            for f in range(F):
+                assert np.abs(pcm.reshape(S, F, -1)[s, f, :rs[f]] - rp[f, :rs[f]]).max() <= (1e-4 if f < 4 else 3e-3)
 
 
 def test_reset_restarts_streams():

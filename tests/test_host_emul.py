@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT, golden_names, load_golden
+from conftest import ROOT, golden_names, load_golden, plc_golden_names, load_plc_golden
 from oracle import oraclepy
 
 EMU = os.path.join(ROOT, "tests", "host_emul")
@@ -17,7 +17,7 @@ EMU = os.path.join(ROOT, "tests", "host_emul")
 @pytest.fixture(scope="module")
 def emul():
     so = os.path.join(EMU, "libemul.so")
-    subprocess.run(["g++", "-O1", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-o", so, os.path.join(EMU, "emul.cpp")], check=True)
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-o", so, os.path.join(EMU, "emul.cpp")], check=True)
     return C.CDLL(so)
 
 
@@ -42,6 +42,22 @@ def test_device_code_single_lane_matches_oracle(emul, name):
 ENC_CELT = [(1, 64000, 960, 159, 0, 10), (2, 96000, 960, 239, 0, 10), (2, 96000, 960, 1275, 1, 10), (1, 64000, 960, 1275, 2, 10),
             (2, 64000, 480, 79, 0, 10), (1, 48000, 240, 29, 0, 10), (2, 96000, 120, 29, 0, 10), (1, 24000, 960, 59, 0, 5),
             (2, 510000, 960, 1275, 0, 10), (2, 96000, 960, 239, 0, 0)]
+
+
+@pytest.mark.parametrize("base", plc_golden_names())
+def test_concealment_device_code_matches_reference_c_build(emul, base):
+    """Lost packets, DTX payloads, the noise/pitch concealment switch and the recovery frames after a loss: the product's device
+    code (one emulated lane) against PCM produced by the reference's pure-C build (fixtures: tests/golden/make_golden_plc.py)."""
+    g, p = load_golden(base), load_plc_golden(base)
+    fs, dc = g["frame_size"], g["dec_channels"]
+    for s in range(p["lens"].shape[0]):
+        nf = p["lens"].shape[1]
+        pk = np.ascontiguousarray(g["packets"][s, :nf]); ln = np.ascontiguousarray(p["lens"][s])
+        pcm = np.zeros((nf, fs * dc), np.float32); rng = np.zeros(nf, np.uint32); smp = np.zeros(nf, np.int32)
+        emul.emul_decode_stream(P(pk, C.c_ubyte), P(ln, C.c_int), pk.shape[1], nf, fs, dc, P(pcm, C.c_float), P(rng, C.c_uint32), P(smp, C.c_int), None)
+        assert (smp == p["samples"][s]).all() and (rng == p["ranges"][s]).all()
+        assert (ln <= 2).sum() >= 10
+        assert np.abs(pcm - p["pcm_c"][s]).max() <= 1e-6
 
 
 @pytest.mark.parametrize("ch,br,fs,nb,vbr,cx", ENC_CELT)
