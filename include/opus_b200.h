@@ -10,10 +10,11 @@
  *   -6 INVALID_STATE, -7 ALLOC_FAIL.  Batch calls return the call-level status; per-stream results
  *   (samples per channel, or a negative code) are written to samples_out[].
  *
- * Scope of this version: Fs = 48000, CELT-only TOC (config >= 16), packet code 0, fec = false, payload
- * > 1 byte.  Anything else gives that (stream, frame) the status OPUS_UNIMPLEMENTED (-5) and leaves the
- * stream's state untouched; other streams are unaffected.  There is no CPU fallback: every entry point
- * that decodes fails with OPUS_INTERNAL_ERROR if no CUDA device is usable.
+ * Scope of this version: Fs = 48000, CELT-only TOC (config >= 16), packet code 0, fec = false.  Lost packets
+ * (len 0) and DTX payloads (<= 1 byte) are concealed like the reference does (celt_decode_lost).  Anything else
+ * (SILK / hybrid TOC, multi-frame codes 1-3) gives that (stream, frame) the status OPUS_UNIMPLEMENTED (-5) and
+ * leaves the stream's state untouched; other streams are unaffected.  There is no CPU fallback: every entry
+ * point that decodes fails with OPUS_INTERNAL_ERROR if no CUDA device is usable.
  */
 #ifndef OPUS_B200_H
 #define OPUS_B200_H
@@ -23,7 +24,7 @@
 extern "C" {
 #endif
 
-#define OB_ABI_VERSION 2
+#define OB_ABI_VERSION 3
 
 typedef struct ObDecoder ObDecoder;
 
@@ -40,7 +41,8 @@ void ob_decoder_destroy(ObDecoder *dec);
  * src/decoder.rs:134-182): one packet per stream.
  *   packets        concatenated packet bytes (host memory), TOC byte included
  *   offsets[s]     byte offset of stream s's packet inside `packets`
- *   lens[s]        its length in bytes (0 = lost packet -> OPUS_UNIMPLEMENTED in this version)
+ *   lens[s]        its length in bytes; 0 = lost packet: frame_size samples are concealed (must be a multiple of 120),
+ *                  like decode_float(&[], out, false) (src/decoder.rs:134-182 -> opus_decoder.c:715-729)
  *   pcm_out        host buffer, n_streams * frame_size * channels floats, interleaved per stream
  *   frame_size     capacity per channel of each stream's slot (120/240/480/960...; a packet longer than this
  *                  gives OPUS_BUFFER_TOO_SMALL for that stream, like src/decoder.rs:149-160)
@@ -66,12 +68,21 @@ int32_t ob_decode_float_device(ObDecoder *dec, int32_t n_frames, const uint8_t *
  * out[s] = final range of the last packet decoded for stream s (0 before any packet). */
 int32_t ob_decoder_final_range(ObDecoder *dec, uint32_t *out);
 
-/* Replaces opus_decoder_ctl(st, OPUS_RESET_STATE) (Decoder::reset src/decoder.rs:376-386) for the streams listed in
+/* Replaces opus_decoder_ctl(st, OPUS_RESET_STATE) (Decoder::reset src/decoder.rs:241-255) for the streams listed in
  * idx[0..n) (idx == NULL: all streams). */
 int32_t ob_decoder_reset(ObDecoder *dec, const int32_t *idx, int32_t n);
 
-/* Replaces opus_decoder_ctl(st, OPUS_GET_LAST_PACKET_DURATION_REQUEST, &v) (src/decoder.rs:335-346). */
+/* Replaces opus_decoder_ctl(st, OPUS_GET_LAST_PACKET_DURATION_REQUEST, &v) (Decoder::get_last_packet_duration src/decoder.rs:294-296). */
 int32_t ob_decoder_last_packet_duration(ObDecoder *dec, int32_t *out);
+
+/* Replaces opus_decoder_ctl(st, OPUS_SET_GAIN / OPUS_GET_GAIN) (Decoder::set_gain src/decoder.rs:318-320, gain :325-327):
+ * Q8 dB in [-32768, 32767], one value for the whole batch, applied to every decoded and concealed sample. */
+int32_t ob_decoder_set_gain(ObDecoder *dec, int32_t gain_q8);
+int32_t ob_decoder_get_gain(ObDecoder *dec, int32_t *value);
+/* Replaces OPUS_SET / GET_PHASE_INVERSION_DISABLED (Decoder::set_phase_inversion_disabled src/decoder.rs:341-346,
+ * phase_inversion_disabled :333-335). */
+int32_t ob_decoder_set_phase_inversion_disabled(ObDecoder *dec, int32_t disabled);
+int32_t ob_decoder_get_phase_inversion_disabled(ObDecoder *dec, int32_t *value);
 
 /* Introspection for benchmarks: number of streams / channels, device-event time in ms of the three kernels of
  * the most recent call (symbols, bands, synthesis), kernel launches issued so far. */

@@ -18,6 +18,7 @@ SYMBOLS = [
     "ob_decoder_create", "ob_decoder_destroy", "ob_decode_float", "ob_decode_float_multi", "ob_decode_float_device",
     "ob_decoder_final_range", "ob_decoder_reset", "ob_decoder_last_packet_duration", "ob_decoder_streams",
     "ob_decoder_channels", "ob_decoder_kernel_ms", "ob_decoder_launches", "ob_decoder_cuda_stream",
+    "ob_decoder_set_gain", "ob_decoder_get_gain", "ob_decoder_set_phase_inversion_disabled", "ob_decoder_get_phase_inversion_disabled",
     "ob_packet_get_nb_channels", "ob_packet_get_samples_per_frame", "ob_packet_get_bandwidth", "ob_packet_get_nb_frames",
     "ob_version", "ob_strerror",
     "ob_encoder_create", "ob_encoder_destroy", "ob_encode_float", "ob_encode_float_multi", "ob_encode_float_device",
@@ -65,6 +66,10 @@ def lib():
     L.ob_decoder_final_range.argtypes = [vp, vp]; L.ob_decoder_final_range.restype = i32
     L.ob_decoder_reset.argtypes = [vp, vp, i32]; L.ob_decoder_reset.restype = i32
     L.ob_decoder_last_packet_duration.argtypes = [vp, vp]; L.ob_decoder_last_packet_duration.restype = i32
+    for n in ("ob_decoder_set_gain", "ob_decoder_set_phase_inversion_disabled"):
+        getattr(L, n).argtypes = [vp, i32]; getattr(L, n).restype = i32
+    for n in ("ob_decoder_get_gain", "ob_decoder_get_phase_inversion_disabled"):
+        getattr(L, n).argtypes = [vp, i32p]; getattr(L, n).restype = i32
     L.ob_decoder_streams.argtypes = [vp]; L.ob_decoder_streams.restype = i32
     L.ob_decoder_channels.argtypes = [vp]; L.ob_decoder_channels.restype = i32
     L.ob_decoder_kernel_ms.argtypes = [vp, f32p]; L.ob_decoder_kernel_ms.restype = i32

@@ -109,6 +109,24 @@ class BatchDecoder:
         _check(self._L.ob_decoder_last_packet_duration(self._h, _vp(out)))
         return out
 
+    def set_gain(self, q8_db):
+        """Decoder::set_gain (src/decoder.rs:318-320): Q8 dB, whole batch."""
+        _check(self._L.ob_decoder_set_gain(self._h, int(q8_db)))
+
+    def gain(self):
+        v = C.c_int32(0)
+        _check(self._L.ob_decoder_get_gain(self._h, C.byref(v)))
+        return v.value
+
+    def set_phase_inversion_disabled(self, disabled):
+        """Decoder::set_phase_inversion_disabled (src/decoder.rs:341-346)."""
+        _check(self._L.ob_decoder_set_phase_inversion_disabled(self._h, 1 if disabled else 0))
+
+    def phase_inversion_disabled(self):
+        v = C.c_int32(0)
+        _check(self._L.ob_decoder_get_phase_inversion_disabled(self._h, C.byref(v)))
+        return bool(v.value)
+
     def reset(self, streams=None):
         if streams is None:
             _check(self._L.ob_decoder_reset(self._h, None, 0))

@@ -828,7 +828,7 @@ OB_DEV_NOINLINE void ob_decode_all_bands(ObRangeDec &ec, ObFrameIR *ir, int end,
 // celt_decode_with_ec (opus/celt/celt_decoder.c:1100-1290).
 // pkt points at the TOC byte; len includes it.  max_frame is the PCM capacity per channel.
 // ------------------------------------------------------------------------------------------------
-OB_DEV_NOINLINE void ob_decode_symbols(const uint8_t *pkt, int len, int dec_channels, int max_frame, ObFrameIR *ir)
+OB_DEV_NOINLINE void ob_decode_symbols(const uint8_t *pkt, int len, int dec_channels, int max_frame, ObFrameIR *ir, int phase_inv_disabled = 0)
 {
     ObFrameHdr &h = ir->hdr;
     h.final_range = 0; h.n_leaves = 0; h.flags = 0; h.lcg_total = 0; h.LM = 0; h.C = 1; h.end = 0;
@@ -962,7 +962,7 @@ OB_DEV_NOINLINE void ob_decode_symbols(const uint8_t *pkt, int len, int dec_chan
     for (int i = 0; i < 2 * OB_NB; i++) collapse_masks[i] = 0;
     (void)M;
     ob_decode_all_bands(ec, ir, end, C, al, isTransient ? M : 0, spread, tf_res, len * (8 << OB_BITRES) - anti_collapse_rsv,
-            LM, dec_channels == 1, collapse_masks);
+            LM, dec_channels == 1 || phase_inv_disabled, collapse_masks);      // st->disable_inv (celt_decoder.c:227, :1567)
     for (int i = 0; i < 2 * OB_NB; i++) h.collapse_masks[i] = collapse_masks[i];
 
     if (anti_collapse_rsv > 0 && ec.bits(1)) flags |= OB_F_ANTICOLLAPSE;

@@ -227,6 +227,7 @@ struct ObSynthShared {
     float pf_gain, pf_gain_old, preemph_mem[2];
     float lpc[2][24];
     int32_t last_pitch_index, paf;   // paf = st->prefilter_and_fold
+    float decode_gain;               // linear gain of OPUS_SET_GAIN (1 = none)
     int32_t ring_pos;                // next write position (= oldest sample) of the global history ring
     float *ring;                     // this stream's ring: [CC][OB_RING]
 };
@@ -352,8 +353,9 @@ OB_DEV void ob_synth_tail(const G &g, ObSynthShared &sh, float *pcm, int N, int 
             if (g.lane == 0) sh.preemph_mem[c] = last_all;
             g.sync();
         }
-        if (CC == 1) { for (int t = g.lane; t < N; t += g.n) pcm[t] = sh.freq[0][t]; }
-        else { for (int t = g.lane; t < 2 * N; t += g.n) pcm[t] = sh.freq[t & 1][t >> 1]; }
+        const float dg = sh.decode_gain;                             // OPUS_SET_GAIN, applied by the Opus layer (opus_decoder.c:639-649)
+        if (CC == 1) { for (int t = g.lane; t < N; t += g.n) pcm[t] = dg == 1.f ? sh.freq[0][t] : sh.freq[0][t] * dg; }
+        else { for (int t = g.lane; t < 2 * N; t += g.n) { const float v = sh.freq[t & 1][t >> 1]; pcm[t] = dg == 1.f ? v : v * dg; } }
         g.sync();
     }
     for (int c = 0; c < CC; c++) {                                   // the frame joins the full-length history ring

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <math.h>
 #include <string.h>
 #include <new>
 
@@ -26,14 +27,14 @@
 #define OB_SYM_THREADS 128
 __global__ void __launch_bounds__(OB_SYM_THREADS)
 ob_k_symbols(const uint8_t *__restrict__ packets, const int32_t *__restrict__ offsets, const int32_t *__restrict__ lens,
-             ObFrameIR *__restrict__ ir, int total, int dec_channels, int max_frame, int F, int f0, int Fc)
+             ObFrameIR *__restrict__ ir, int total, int dec_channels, int max_frame, int F, int f0, int Fc, int phase_inv_disabled)
 {
     // a launch covers the frame window [f0, f0+Fc) of every stream of a [S][F] batch: t -> (stream, frame)
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= total) return;
     const size_t t = (size_t)(k / Fc) * F + f0 + k % Fc;
     const int len = lens[t];
-    ob_decode_symbols(len > 0 ? packets + offsets[t] : nullptr, len, dec_channels, max_frame, ir + t);
+    ob_decode_symbols(len > 0 ? packets + offsets[t] : nullptr, len, dec_channels, max_frame, ir + t, phase_inv_disabled);
 }
 
 // Plan pass, one thread per stream: walks the frame window in order through the integer loss state machine (which frames are
@@ -87,7 +88,7 @@ ob_k_bands(const ObFrameIR *__restrict__ ir, float *__restrict__ Xg, int S, int 
 __global__ void __launch_bounds__(OB_SYNTH_THREADS)
 ob_k_synth(const ObFrameIR *__restrict__ ir, const float *__restrict__ Xg, ObDecState *__restrict__ st, float *__restrict__ hist, float *__restrict__ ring,
            float *__restrict__ pcm, int32_t *__restrict__ samples, uint32_t *__restrict__ ranges, int S, int F, int CC, int frame_size,
-           int f0, int Fc)
+           int f0, int Fc, float decode_gain)
 {
     __shared__ ObSynthShared sh;
     const int s = blockIdx.x;
@@ -110,7 +111,7 @@ ob_k_synth(const ObFrameIR *__restrict__ ir, const float *__restrict__ Xg, ObDec
         sh.pf_gain = state->pf_gain; sh.pf_gain_old = state->pf_gain_old;
         sh.preemph_mem[0] = state->preemph_mem[0]; sh.preemph_mem[1] = state->preemph_mem[1];
         sh.last_pitch_index = state->last_pitch_index; sh.paf = state->prefilter_and_fold;
-        sh.ring_pos = state->ring_pos; sh.ring = ring + (size_t)s * CC * OB_RING;
+        sh.ring_pos = state->ring_pos; sh.ring = ring + (size_t)s * CC * OB_RING; sh.decode_gain = decode_gain;
     }
     for (int i = g.lane; i < 2 * 24; i += g.n) sh.lpc[i / 24][i % 24] = state->lpc[i / 24][i % 24];
     uint32_t final_range = state->final_range;
@@ -181,6 +182,8 @@ __global__ void ob_k_gather_state(const ObDecState *st, uint32_t *ranges, int32_
 #endif
 struct ObDecoder {
     int S, CC, device, max_frames;
+    int gain_q8, phase_inv_disabled;      // OPUS_SET_GAIN (Q8 dB), OPUS_SET_PHASE_INVERSION_DISABLED: one value for the batch
+    float gain_linear;
     cudaStream_t stream, copy_stream, aux_stream;
     cudaEvent_t ev[4], chunk_ev[OB_MAX_CHUNKS], copy_done, h2d_done;
     bool timed;
@@ -215,7 +218,7 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
     if (timed) OB_CUDA(cudaEventRecord(d->ev[0], stream));
     if (which & 1) {
         ob_k_symbols<<<(total + OB_SYM_THREADS - 1) / OB_SYM_THREADS, OB_SYM_THREADS, 0, stream>>>(
-            d_packets, d_offsets + w0, d_lens + w0, ir, total, d->CC, frame_size, F, f0, Fc);
+            d_packets, d_offsets + w0, d_lens + w0, ir, total, d->CC, frame_size, F, f0, Fc, d->phase_inv_disabled);
         d->launches += 1;
     }
     if (timed) OB_CUDA(cudaEventRecord(d->ev[1], stream));
@@ -225,7 +228,7 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
             ir, X, Sc, F, f0, Fc);
         if (timed) OB_CUDA(cudaEventRecord(d->ev[2], stream));
         ob_k_synth<<<Sc, OB_SYNTH_THREADS, 0, stream>>>(ir, X, st, hist, ring, d_pcm + w0 * (size_t)frame_size * d->CC, d_samples + w0,
-                                                         d_ranges ? d_ranges + w0 : nullptr, Sc, F, d->CC, frame_size, f0, Fc);
+                                                         d_ranges ? d_ranges + w0 : nullptr, Sc, F, d->CC, frame_size, f0, Fc, d->gain_linear);
         d->launches += 3;
     }
     if (timed) OB_CUDA(cudaEventRecord(d->ev[3], stream));
@@ -254,6 +257,7 @@ ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
     if (err == OB_OK) {
         memset(d, 0, sizeof(*d));
         d->S = n_streams; d->CC = channels; d->device = device; d->max_frames = max_frames;
+        d->gain_q8 = 0; d->gain_linear = 1.f; d->phase_inv_disabled = 0;
         const size_t total = (size_t)n_streams * max_frames;
         bool ok = cudaSetDevice(device) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -433,6 +437,20 @@ static int32_t ob_gather(ObDecoder *d, uint32_t *ranges, int32_t *durations)
 int32_t ob_decoder_final_range(ObDecoder *d, uint32_t *out) { return (!d || !out) ? OB_BAD_ARG : ob_gather(d, out, nullptr); }
 int32_t ob_decoder_last_packet_duration(ObDecoder *d, int32_t *out) { return (!d || !out) ? OB_BAD_ARG : ob_gather(d, nullptr, out); }
 
+// OPUS_SET_GAIN / OPUS_GET_GAIN (opus_decoder.c:985-1004): Q8 dB, applied as pcm *= celt_exp2(6.48814081e-4 * gain) (:639-649).
+int32_t ob_decoder_set_gain(ObDecoder *d, int32_t gain_q8)
+{
+    if (!d || gain_q8 < -32768 || gain_q8 > 32767) return OB_BAD_ARG;
+    d->gain_q8 = gain_q8;
+    const float x = 6.48814081e-4f * (float)gain_q8;
+    d->gain_linear = gain_q8 == 0 ? 1.f : (float)exp(0.6931471805599453094 * x);
+    return OB_OK;
+}
+int32_t ob_decoder_get_gain(ObDecoder *d, int32_t *v) { if (!d || !v) return OB_BAD_ARG; *v = d->gain_q8; return OB_OK; }
+// OPUS_SET/GET_PHASE_INVERSION_DISABLED (celt_decoder.c:1560-1579)
+int32_t ob_decoder_set_phase_inversion_disabled(ObDecoder *d, int32_t v) { if (!d || v < 0 || v > 1) return OB_BAD_ARG; d->phase_inv_disabled = v; return OB_OK; }
+int32_t ob_decoder_get_phase_inversion_disabled(ObDecoder *d, int32_t *v) { if (!d || !v) return OB_BAD_ARG; *v = d->phase_inv_disabled; return OB_OK; }
+
 int32_t ob_decoder_streams(const ObDecoder *d) { return d ? d->S : OB_BAD_ARG; }
 int32_t ob_decoder_channels(const ObDecoder *d) { return d ? d->CC : OB_BAD_ARG; }
 int64_t ob_decoder_launches(const ObDecoder *d) { return d ? d->launches : 0; }
@@ -473,7 +491,7 @@ int32_t ob_packet_get_nb_frames(const uint8_t *p, int32_t len)
     return p[1] & 0x3F;
 }
 
-const char *ob_version(void) { return "1.5.2-b200.2"; }
+const char *ob_version(void) { return "1.5.2-b200.3"; }
 const char *ob_strerror(int32_t e)
 {
     static const char *const s[8] = {"success", "invalid argument", "buffer too small", "internal error", "corrupted stream",

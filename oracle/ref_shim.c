@@ -173,12 +173,21 @@ REF_EXPORT int ref_encode_stream(const float *pcm, int nframes, int frame_size, 
 
 /* pkts: nframes slots of `stride` bytes; lens[f] bytes valid (0 => packet loss / PLC).
  * dec_channels: channel count of the decoder object.  taps (optional): nframes ref_tap_t records. */
+/* Optional decoder CTLs applied by ref_decode_stream: OPUS_SET_GAIN (Q8 dB) and OPUS_SET_PHASE_INVERSION_DISABLED. */
+static int g_dec_gain = 0, g_dec_phase_inv_disabled = 0;
+REF_EXPORT void ref_set_decoder_extras(int gain_q8, int phase_inv_disabled)
+{
+    g_dec_gain = gain_q8; g_dec_phase_inv_disabled = phase_inv_disabled;
+}
+
 REF_EXPORT int ref_decode_stream(const unsigned char *pkts, const int *lens, int stride, int nframes, int frame_size,
         int dec_channels, float *pcm_out, uint32_t *ranges, int *samples, void *taps)
 {
     int f, err = 0;
     OpusDecoder *d = opus_decoder_create(48000, dec_channels, &err);
     if (!d || err != OPUS_OK) return OPUS_ALLOC_FAIL;
+    if (g_dec_gain) opus_decoder_ctl(d, OPUS_SET_GAIN(g_dec_gain));
+    if (g_dec_phase_inv_disabled) opus_decoder_ctl(d, OPUS_SET_PHASE_INVERSION_DISABLED(1));
     for (f = 0; f < nframes; f++) {
         opus_uint32 rng = 0;
         int n;

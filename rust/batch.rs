@@ -24,6 +24,8 @@ unsafe extern "C" {
     pub fn ob_decoder_final_range(dec: *mut ObDecoder, out: *mut u32) -> i32;
     pub fn ob_decoder_reset(dec: *mut ObDecoder, idx: *const i32, n: i32) -> i32;
     pub fn ob_decoder_last_packet_duration(dec: *mut ObDecoder, out: *mut i32) -> i32;
+    pub fn ob_decoder_set_gain(dec: *mut ObDecoder, gain_q8: i32) -> i32;
+    pub fn ob_decoder_set_phase_inversion_disabled(dec: *mut ObDecoder, disabled: i32) -> i32;
 
     pub fn ob_encoder_create(n_streams: i32, fs: i32, channels: i32, application: i32, device: i32, max_frames: i32,
                              error: *mut i32) -> *mut ObEncoder;
@@ -69,7 +71,8 @@ impl BatchDecoder {
         }
     }
 
-    /// One packet per stream. `packets[s]` may be empty (lost packet: `Error::Unimplemented` for that stream in this version).
+    /// One packet per stream. `packets[s]` may be empty: a lost packet, concealed for `frame_size` samples exactly like
+    /// `Decoder::decode_float(&[], out, false)`.
     /// `output` is `n_streams * frame_size * channels` interleaved floats; `frame_size = output.len() / n_streams / channels`
     /// exactly like `Decoder::decode_float` derives it (src/decoder.rs:149).
     /// Returns per-stream `Ok(samples_per_channel)` / `Err(code)`.
@@ -106,7 +109,19 @@ impl BatchDecoder {
         if rc != 0 { Err(Error::from_code(rc)) } else { Ok(out) }
     }
 
-    /// Cf. `Decoder::reset` (src/decoder.rs:376-386); `None` resets every stream.
+    /// Cf. `Decoder::set_gain` (src/decoder.rs:318-320): Q8 dB for the whole batch.
+    pub fn set_gain(&mut self, q8_db: i32) -> Result<()> {
+        let rc = unsafe { ob_decoder_set_gain(self.raw.as_ptr(), q8_db) };
+        if rc != 0 { Err(Error::from_code(rc)) } else { Ok(()) }
+    }
+
+    /// Cf. `Decoder::set_phase_inversion_disabled` (src/decoder.rs:341-346).
+    pub fn set_phase_inversion_disabled(&mut self, disabled: bool) -> Result<()> {
+        let rc = unsafe { ob_decoder_set_phase_inversion_disabled(self.raw.as_ptr(), disabled as i32) };
+        if rc != 0 { Err(Error::from_code(rc)) } else { Ok(()) }
+    }
+
+    /// Cf. `Decoder::reset` (src/decoder.rs:241-255); `None` resets every stream.
     pub fn reset(&mut self, streams: Option<&[i32]>) -> Result<()> {
         let rc = unsafe {
             match streams {

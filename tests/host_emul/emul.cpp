@@ -33,6 +33,7 @@ int emul_decode_stream(const uint8_t *pkts, const int *lens, int stride, int nfr
     ObSolo g;
     ob_synth_init(g, *sh);
     sh->ring = (float *)calloc(2 * OB_RING, sizeof(float));
+    sh->decode_gain = 1.f;
     ObPlanState plan = {0u, 0, 1, 0};                     // OPUS_RESET_STATE: skip_plc = 1 (celt_decoder.c:1527)
     uint32_t final_range = 0;
     for (int f = 0; f < nframes; f++) {

@@ -163,6 +163,43 @@ def test_lost_packet_slot_larger_than_20ms_is_concealed_in_pieces(have_ref):
                 assert np.abs(pcm.reshape(S, F, -1)[s, f, :rs[f]] - rp[f, :rs[f]]).max() <= (1e-4 if f < 4 else 3e-3)
 
 
+def test_decode_gain_and_phase_inversion_ctls(have_ref):
+    """OPUS_SET_GAIN and OPUS_SET_PHASE_INVERSION_DISABLED (Decoder::set_gain / set_phase_inversion_disabled) against the
+    reference decoder with the same CTLs; the final range never depends on either."""
+    from opus_codec_b200.batch import BatchDecoder, OpusError, BAD_ARG
+    from oracle import refpy
+    g = load_golden("cfg3_stereo_20ms_96k_cbr")            # these packets carry the stereo inversion flag (checked against the reference)
+    S, F, stride = g["packets"].shape
+    S, F = 3, 25
+    pk = np.ascontiguousarray(g["packets"][:S, :F]); ln = g["lens"][:S, :F]
+    with BatchDecoder(S, 48000, 2, device=0, max_frames=F) as dec:
+        base, _, rng0 = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, 960)
+        base = base.copy()
+        assert dec.gain() == 0 and dec.phase_inversion_disabled() is False
+        with pytest.raises(OpusError) as e:
+            dec.set_gain(40000)
+        assert e.value.code == BAD_ARG
+        for q8 in (-1536, 777):
+            dec.reset(); dec.set_gain(q8)
+            assert dec.gain() == q8
+            out, _, rng = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, 960)
+            assert (rng == rng0).all()
+            lin = np.float32(np.exp(0.6931471805599453094 * np.float32(np.float32(6.48814081e-4) * np.float32(q8))))
+            assert np.abs(out - base * lin).max() <= 1e-6
+            if have_ref:
+                ref = refpy.decode_stream(pk[0], ln[0], 960, 2, gain_q8=q8)[0]
+                assert np.abs(out.reshape(S, F, -1)[0] - ref).max() <= PCM_TOL * max(1.0, float(lin))
+        dec.reset(); dec.set_gain(0); dec.set_phase_inversion_disabled(True)
+        assert dec.phase_inversion_disabled() is True
+        out, _, rng = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, 960)
+        assert (rng == rng0).all()
+        assert np.abs(out - base).max() > 1e-3               # the flag does change the stereo image of these packets
+        if have_ref:
+            for s in range(S):
+                ref = refpy.decode_stream(pk[s], ln[s], 960, 2, phase_inv_disabled=True)[0]
+                assert np.abs(out.reshape(S, F, -1)[s] - ref).max() <= PCM_TOL
+
+
 def test_reset_restarts_streams():
     from opus_codec_b200.batch import BatchDecoder
     g = load_golden("cfg2_mono_20ms_64k_cbr")
