@@ -60,6 +60,41 @@ def test_concealment_device_code_matches_reference_c_build(emul, base):
         assert np.abs(pcm - p["pcm_c"][s]).max() <= 1e-6
 
 
+def _fuzz_streams(seed, trials, nf=10, with_loss=True):
+    """Random (garbage) payloads behind valid CELT TOCs, optionally with lost packets and DTX payloads in between."""
+    rng = np.random.default_rng(seed)
+    for _ in range(trials):
+        cfg = 16 + int(rng.integers(0, 16))
+        toc = (cfg << 3) | (int(rng.integers(0, 2)) << 2)
+        fs = 120 << (cfg & 3)
+        ln = rng.integers(3, 200, nf).astype(np.int32)
+        if with_loss:
+            ln[rng.random(nf) < 0.2] = 0
+            ln[rng.random(nf) < 0.05] = 1
+        pk = rng.integers(0, 256, (nf, 200), dtype=np.uint8)
+        pk[:, 0] = toc
+        yield pk, ln, fs
+
+
+def test_device_code_vs_live_reference_fuzz(emul, have_ref):
+    """Garbage packets, losses and DTX through the product's device code (one emulated lane) and the reference's C build:
+    samples and final range identical, PCM equal to rounding -- whatever the bytes are."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    for pk, ln, fs in _fuzz_streams(2024, 40):
+        nf = pk.shape[0]
+        for dc in (1, 2):
+            ref, rr, rs = refpy.decode_stream(pk, ln, fs, dc, pure_c=True)
+            pcm = np.zeros((nf, fs * dc), np.float32); rng = np.zeros(nf, np.uint32); smp = np.zeros(nf, np.int32)
+            emul.emul_decode_stream(P(pk, C.c_ubyte), P(ln, C.c_int), pk.shape[1], nf, fs, dc, P(pcm, C.c_float), P(rng, C.c_uint32), P(smp, C.c_int), None)
+            assert (smp == rs).all() and (rng == rr).all()
+            m = np.isfinite(ref)
+            assert (m == np.isfinite(pcm)).all()
+            scale = max(1.0, float(np.abs(ref[m]).max()))
+            assert np.abs(pcm[m] - ref[m]).max() <= 1e-5 * scale
+
+
 @pytest.mark.parametrize("ch,br,fs,nb,vbr,cx", ENC_CELT)
 def test_encoder_device_code_bit_identical_to_reference_celt_encoder(emul, have_ref, ch, br, fs, nb, vbr, cx):
     """celt_encode_with_ec driven directly (no Opus-layer analysis): packets must be IDENTICAL, every byte of every frame."""
