@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define OB_ABI_VERSION 3
+#define OB_ABI_VERSION 4
 
 typedef struct ObDecoder ObDecoder;
 
@@ -57,6 +57,16 @@ int32_t ob_decode_float(ObDecoder *dec, const uint8_t *packets, const int32_t *o
 int32_t ob_decode_float_multi(ObDecoder *dec, int32_t n_frames, const uint8_t *packets, const int32_t *offsets,
                               const int32_t *lens, float *pcm_out, int32_t frame_size, int32_t *samples_out,
                               uint32_t *ranges_out);
+
+/* Pipelined form of ob_decode_float_multi for callers that keep two calls in flight (a media server draining jitter buffers):
+ * returns once the work is enqueued; the outputs are valid after ob_decoder_wait.  While call n's PCM travels to the host,
+ * call n+1's kernels already run.  At most two calls may be outstanding: before submitting call n+2 (or touching call n's output
+ * or input buffers) call ob_decoder_wait(dec, 1), which returns when everything except the most recent call has completed;
+ * ob_decoder_wait(dec, 0) drains all.  Host buffers should be pinned.  Results are identical to the blocking call. */
+int32_t ob_decode_float_multi_async(ObDecoder *dec, int32_t n_frames, const uint8_t *packets, const int32_t *offsets,
+                                    const int32_t *lens, float *pcm_out, int32_t frame_size, int32_t *samples_out,
+                                    uint32_t *ranges_out);
+int32_t ob_decoder_wait(ObDecoder *dec, int32_t keep_in_flight);
 
 /* Same, with every pointer a DEVICE pointer on the decoder's device (inputs already resident in HBM, outputs
  * left there); asynchronous on the decoder's stream unless sync != 0. */

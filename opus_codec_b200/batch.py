@@ -90,6 +90,20 @@ class BatchDecoder:
                                              _vp(samples), _vp(ranges)))
         return pcm, samples, ranges
 
+    def decode_float_multi_async(self, packets, offsets, lens, frame_size, pcm, samples, ranges):
+        """Pipelined form (ob_decode_float_multi_async): enqueue and return; all arrays are caller-owned, C-contiguous numpy arrays
+        (ideally over pinned memory) that must stay alive and untouched until wait() says the call has completed."""
+        S, F = offsets.shape
+        if offsets.dtype != np.int32 or lens.dtype != np.int32 or packets.dtype != np.uint8 or pcm.dtype != np.float32 \
+                or samples.dtype != np.int32 or ranges.dtype != np.uint32 or S != self.n_streams or pcm.size < S * F * frame_size * self.channels:
+            raise OpusError(BAD_ARG)
+        _check(self._L.ob_decode_float_multi_async(self._h, F, _vp(packets), _vp(offsets), _vp(lens), _vp(pcm), frame_size,
+                                                   _vp(samples), _vp(ranges)))
+
+    def wait(self, keep_in_flight=0):
+        """ob_decoder_wait: 0 = every outstanding call has completed; 1 = every call but the most recent one."""
+        _check(self._L.ob_decoder_wait(self._h, int(keep_in_flight)))
+
     def decode_float(self, packets, frame_size):
         """packets: one bytes object per stream.  Returns (pcm [S, frame_size*channels], samples [S])."""
         if len(packets) != self.n_streams:

@@ -193,8 +193,11 @@ struct ObDecoder {
     float *d_X;
     // staging for the host-pointer entry points
     uint8_t *d_packets; size_t packets_cap;
-    int32_t *d_offsets, *d_lens, *d_samples; uint32_t *d_ranges;
-    float *d_pcm; size_t pcm_cap;
+    int32_t *d_offsets, *d_lens, *d_samples2[2]; uint32_t *d_ranges2[2];
+    float *d_pcm2[2]; size_t pcm_cap2[2];
+    int32_t *d_gather;                 // S words: scratch of the per-stream getters
+    cudaEvent_t out_done[2], aux_done; // the device->host copies that last read output buffer p have finished / the auxiliary stream is idle
+    uint32_t call_seq;                 // output buffers alternate between consecutive host-pointer calls (pipelined callers)
     int64_t launches;
 };
 
@@ -274,8 +277,12 @@ ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         ok = ok && cudaMalloc(&d->d_X, sizeof(float) * OB_X_STRIDE * total) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_offsets, sizeof(int32_t) * total) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_lens, sizeof(int32_t) * total) == cudaSuccess;
-        ok = ok && cudaMalloc(&d->d_samples, sizeof(int32_t) * total) == cudaSuccess;
-        ok = ok && cudaMalloc(&d->d_ranges, sizeof(uint32_t) * total) == cudaSuccess;
+        for (int p = 0; p < 2 && ok; p++) {
+            ok = cudaMalloc(&d->d_samples2[p], sizeof(int32_t) * total) == cudaSuccess && cudaMalloc(&d->d_ranges2[p], sizeof(uint32_t) * total) == cudaSuccess
+                 && cudaEventCreateWithFlags(&d->out_done[p], cudaEventDisableTiming) == cudaSuccess;
+        }
+        ok = ok && cudaEventCreateWithFlags(&d->aux_done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->d_gather, sizeof(int32_t) * n_streams) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(ob_k_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP) == cudaSuccess;
         if (!ok) {
             fprintf(stderr, "opus_b200: device allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
@@ -298,7 +305,9 @@ void ob_decoder_destroy(ObDecoder *d)
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
     cudaFree(d->d_state); cudaFree(d->d_hist); cudaFree(d->d_ring); cudaFree(d->d_ir); cudaFree(d->d_X); cudaFree(d->d_packets);
-    cudaFree(d->d_offsets); cudaFree(d->d_lens); cudaFree(d->d_samples); cudaFree(d->d_ranges); cudaFree(d->d_pcm);
+    cudaFree(d->d_offsets); cudaFree(d->d_lens); cudaFree(d->d_gather);
+    for (int p = 0; p < 2; p++) { cudaFree(d->d_samples2[p]); cudaFree(d->d_ranges2[p]); cudaFree(d->d_pcm2[p]); if (d->out_done[p]) cudaEventDestroy(d->out_done[p]); }
+    if (d->aux_done) cudaEventDestroy(d->aux_done);
     for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     for (int i = 0; i < OB_MAX_CHUNKS; i++) if (d->chunk_ev[i]) cudaEventDestroy(d->chunk_ev[i]);
     if (d->copy_done) cudaEventDestroy(d->copy_done);
@@ -341,8 +350,11 @@ int32_t ob_decode_float_device(ObDecoder *d, int32_t n_frames, const uint8_t *d_
     return OB_OK;
 }
 
-int32_t ob_decode_float_multi(ObDecoder *d, int32_t n_frames, const uint8_t *packets, const int32_t *offsets, const int32_t *lens,
-                              float *pcm_out, int32_t frame_size, int32_t *samples_out, uint32_t *ranges_out)
+// Enqueues one host-pointer call: packets up, kernels, PCM / samples / ranges down.  wait != 0: returns when the outputs are in
+// the caller's buffers.  wait == 0: returns as soon as everything is enqueued (ob_decoder_wait completes it); the next call's
+// kernels then overlap this call's device->host copies, which is why the device-side output buffers alternate between calls.
+static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *packets, const int32_t *offsets, const int32_t *lens,
+                                float *pcm_out, int32_t frame_size, int32_t *samples_out, uint32_t *ranges_out, int wait)
 {
     if (!d || !packets || !offsets || !lens || !pcm_out || !samples_out) return OB_BAD_ARG;
     if (n_frames <= 0 || n_frames > d->max_frames || frame_size <= 0) return OB_BAD_ARG;
@@ -360,12 +372,19 @@ int32_t ob_decode_float_multi(ObDecoder *d, int32_t n_frames, const uint8_t *pac
         OB_CUDA(cudaMalloc(&d->d_packets, nbytes + nbytes / 4));
         d->packets_cap = nbytes + nbytes / 4;
     }
+    const int par = (int)(d->call_seq++ & 1u);
     const size_t pcm_floats = total * (size_t)frame_size * d->CC;
-    if (pcm_floats > d->pcm_cap) {
-        cudaFree(d->d_pcm); d->d_pcm = nullptr; d->pcm_cap = 0;
-        OB_CUDA(cudaMalloc(&d->d_pcm, pcm_floats * sizeof(float)));
-        d->pcm_cap = pcm_floats;
+    OB_CUDA(cudaStreamWaitEvent(d->stream, d->out_done[par], 0));      // the copies of the call before last (same buffers) are done
+    OB_CUDA(cudaStreamWaitEvent(d->stream, d->aux_done, 0));           // nobody still reads the staged packets of the previous call
+    if (pcm_floats > d->pcm_cap2[par]) {
+        OB_CUDA(cudaEventSynchronize(d->out_done[par]));
+        cudaFree(d->d_pcm2[par]); d->d_pcm2[par] = nullptr; d->pcm_cap2[par] = 0;
+        OB_CUDA(cudaMalloc(&d->d_pcm2[par], pcm_floats * sizeof(float)));
+        d->pcm_cap2[par] = pcm_floats;
     }
+    float *const d_pcm = d->d_pcm2[par];
+    int32_t *const d_samples = d->d_samples2[par];
+    uint32_t *const d_ranges = d->d_ranges2[par];
     OB_CUDA(cudaMemcpyAsync(d->d_packets, packets, nbytes, cudaMemcpyHostToDevice, d->stream));
     OB_CUDA(cudaMemcpyAsync(d->d_offsets, offsets, total * sizeof(int32_t), cudaMemcpyHostToDevice, d->stream));
     OB_CUDA(cudaMemcpyAsync(d->d_lens, lens, total * sizeof(int32_t), cudaMemcpyHostToDevice, d->stream));
@@ -381,19 +400,19 @@ int32_t ob_decode_float_multi(ObDecoder *d, int32_t n_frames, const uint8_t *pac
         // The symbol kernel is one thread per frame and latency bound (a launch takes >= 1.6 ms however few frames it covers:
         // measured), so it runs once over the whole call; only the band + synthesis kernels are windowed.
         const int per = (n_frames + nchunks - 1) / nchunks;
-        const int r0 = ob_launch(d, 0, d->S, n_frames, d->d_packets, d->d_offsets, d->d_lens, d->d_pcm, frame_size, d->d_samples, d->d_ranges, 0, d->stream, 0, n_frames, 1);
+        const int r0 = ob_launch(d, 0, d->S, n_frames, d->d_packets, d->d_offsets, d->d_lens, d_pcm, frame_size, d_samples, d_ranges, 0, d->stream, 0, n_frames, 1);
         if (r0 != OB_OK) return r0;
         for (int k = 0, f0 = 0; f0 < n_frames; k++, f0 += per) {
             const int Fc = n_frames - f0 < per ? n_frames - f0 : per;
-            const int r = ob_launch(d, 0, d->S, n_frames, d->d_packets, d->d_offsets, d->d_lens, d->d_pcm, frame_size, d->d_samples, d->d_ranges, 0, d->stream, f0, Fc, 2);
+            const int r = ob_launch(d, 0, d->S, n_frames, d->d_packets, d->d_offsets, d->d_lens, d_pcm, frame_size, d_samples, d_ranges, 0, d->stream, f0, Fc, 2);
             if (r != OB_OK) return r;
             OB_CUDA(cudaEventRecord(d->chunk_ev[k], d->stream));
             OB_CUDA(cudaStreamWaitEvent(d->copy_stream, d->chunk_ev[k], 0));
-            OB_CUDA(cudaMemcpy2DAsync(pcm_out + f0 * pf, n_frames * pf * sizeof(float), d->d_pcm + f0 * pf, n_frames * pf * sizeof(float),
+            OB_CUDA(cudaMemcpy2DAsync(pcm_out + f0 * pf, n_frames * pf * sizeof(float), d_pcm + f0 * pf, n_frames * pf * sizeof(float),
                                       Fc * pf * sizeof(float), d->S, cudaMemcpyDeviceToHost, d->copy_stream));
         }
-        OB_CUDA(cudaMemcpyAsync(samples_out, d->d_samples, total * sizeof(int32_t), cudaMemcpyDeviceToHost, d->copy_stream));
-        if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out, d->d_ranges, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->copy_stream));
+        OB_CUDA(cudaMemcpyAsync(samples_out, d_samples, total * sizeof(int32_t), cudaMemcpyDeviceToHost, d->copy_stream));
+        if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out, d_ranges, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->copy_stream));
     } else {
         const int per = (d->S + nchunks - 1) / nchunks;
         OB_CUDA(cudaEventRecord(d->h2d_done, d->stream));
@@ -402,18 +421,44 @@ int32_t ob_decode_float_multi(ObDecoder *d, int32_t n_frames, const uint8_t *pac
             const int Sc = d->S - s0 < per ? d->S - s0 : per;
             const size_t w0 = (size_t)s0 * n_frames, cnt = (size_t)Sc * n_frames;
             cudaStream_t cs = (k & 1) ? d->aux_stream : d->stream;       // alternate compute streams: kernels of neighbouring chunks overlap
-            const int r = ob_launch(d, s0, Sc, n_frames, d->d_packets, d->d_offsets, d->d_lens, d->d_pcm, frame_size, d->d_samples, d->d_ranges, 0, cs);
+            const int r = ob_launch(d, s0, Sc, n_frames, d->d_packets, d->d_offsets, d->d_lens, d_pcm, frame_size, d_samples, d_ranges, 0, cs);
             if (r != OB_OK) return r;
             OB_CUDA(cudaEventRecord(d->chunk_ev[k], cs));
             OB_CUDA(cudaStreamWaitEvent(d->copy_stream, d->chunk_ev[k], 0));
-            OB_CUDA(cudaMemcpyAsync(pcm_out + w0 * pf, d->d_pcm + w0 * pf, cnt * pf * sizeof(float), cudaMemcpyDeviceToHost, d->copy_stream));
-            OB_CUDA(cudaMemcpyAsync(samples_out + w0, d->d_samples + w0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, d->copy_stream));
-            if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out + w0, d->d_ranges + w0, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->copy_stream));
+            OB_CUDA(cudaMemcpyAsync(pcm_out + w0 * pf, d_pcm + w0 * pf, cnt * pf * sizeof(float), cudaMemcpyDeviceToHost, d->copy_stream));
+            OB_CUDA(cudaMemcpyAsync(samples_out + w0, d_samples + w0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, d->copy_stream));
+            if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out + w0, d_ranges + w0, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->copy_stream));
         }
     }
-    OB_CUDA(cudaEventRecord(d->copy_done, d->copy_stream));
-    OB_CUDA(cudaStreamWaitEvent(d->stream, d->copy_done, 0));      // keep d->stream a faithful timeline of the whole call
+    OB_CUDA(cudaEventRecord(d->aux_done, d->aux_stream));
+    OB_CUDA(cudaEventRecord(d->out_done[par], d->copy_stream));
+    if (wait) OB_CUDA(cudaEventSynchronize(d->out_done[par]));
+    return OB_OK;
+}
+
+int32_t ob_decode_float_multi(ObDecoder *d, int32_t n_frames, const uint8_t *packets, const int32_t *offsets, const int32_t *lens,
+                              float *pcm_out, int32_t frame_size, int32_t *samples_out, uint32_t *ranges_out)
+{
+    return ob_decode_submit(d, n_frames, packets, offsets, lens, pcm_out, frame_size, samples_out, ranges_out, 1);
+}
+
+int32_t ob_decode_float_multi_async(ObDecoder *d, int32_t n_frames, const uint8_t *packets, const int32_t *offsets, const int32_t *lens,
+                                    float *pcm_out, int32_t frame_size, int32_t *samples_out, uint32_t *ranges_out)
+{
+    return ob_decode_submit(d, n_frames, packets, offsets, lens, pcm_out, frame_size, samples_out, ranges_out, 0);
+}
+
+int32_t ob_decoder_wait(ObDecoder *d, int32_t keep_in_flight)
+{
+    if (!d || keep_in_flight < 0 || keep_in_flight > 1) return OB_BAD_ARG;
+    OB_CUDA(cudaSetDevice(d->device));
+    if (keep_in_flight) {              // everything but the most recent call: its outputs were the other buffer pair
+        if (d->call_seq >= 2) OB_CUDA(cudaEventSynchronize(d->out_done[d->call_seq & 1u]));
+        return OB_OK;
+    }
     OB_CUDA(cudaStreamSynchronize(d->stream));
+    OB_CUDA(cudaStreamSynchronize(d->aux_stream));
+    OB_CUDA(cudaStreamSynchronize(d->copy_stream));
     return OB_OK;
 }
 
@@ -426,11 +471,10 @@ int32_t ob_decode_float(ObDecoder *d, const uint8_t *packets, const int32_t *off
 static int32_t ob_gather(ObDecoder *d, uint32_t *ranges, int32_t *durations)
 {
     OB_CUDA(cudaSetDevice(d->device));
-    // d_ranges / d_samples have at least S entries (S * max_frames)
-    ob_k_gather_state<<<(d->S + 127) / 128, 128, 0, d->stream>>>(d->d_state, ranges ? d->d_ranges : nullptr, durations ? d->d_samples : nullptr, d->S);
+    ob_k_gather_state<<<(d->S + 127) / 128, 128, 0, d->stream>>>(d->d_state, ranges ? (uint32_t *)d->d_gather : nullptr, durations ? d->d_gather : nullptr, d->S);
     d->launches += 1;
-    if (ranges) OB_CUDA(cudaMemcpyAsync(ranges, d->d_ranges, sizeof(uint32_t) * d->S, cudaMemcpyDeviceToHost, d->stream));
-    if (durations) OB_CUDA(cudaMemcpyAsync(durations, d->d_samples, sizeof(int32_t) * d->S, cudaMemcpyDeviceToHost, d->stream));
+    if (ranges) OB_CUDA(cudaMemcpyAsync(ranges, d->d_gather, sizeof(uint32_t) * d->S, cudaMemcpyDeviceToHost, d->stream));
+    if (durations) OB_CUDA(cudaMemcpyAsync(durations, d->d_gather, sizeof(int32_t) * d->S, cudaMemcpyDeviceToHost, d->stream));
     OB_CUDA(cudaStreamSynchronize(d->stream));
     return OB_OK;
 }
@@ -491,7 +535,7 @@ int32_t ob_packet_get_nb_frames(const uint8_t *p, int32_t len)
     return p[1] & 0x3F;
 }
 
-const char *ob_version(void) { return "1.5.2-b200.3"; }
+const char *ob_version(void) { return "1.5.2-b200.4"; }
 const char *ob_strerror(int32_t e)
 {
     static const char *const s[8] = {"success", "invalid argument", "buffer too small", "internal error", "corrupted stream",

@@ -242,6 +242,33 @@ def test_fuzz_garbage_packets_match_reference(have_ref, with_loss):
                 assert np.abs(a[m] - b[m]).max() <= 1e-4 * scale, (s, f, fs)
 
 
+def test_pipelined_async_calls_match_blocking_calls():
+    """ob_decode_float_multi_async with two calls in flight produces exactly what consecutive blocking calls produce."""
+    from opus_codec_b200.batch import BatchDecoder
+    g = load_golden("cfg3_stereo_20ms_96k_cbr")
+    S, Ftot, stride = g["packets"].shape
+    F, ncalls = 5, 8
+    offs = _offsets(S, Ftot, stride)
+    with BatchDecoder(S, 48000, 2, device=0, max_frames=F) as dec:
+        want = [dec.decode_float_multi(g["packets"].reshape(-1), offs[:, k * F:(k + 1) * F], g["lens"][:, k * F:(k + 1) * F], 960) for k in range(ncalls)]
+        want = [(a.copy(), b.copy(), c.copy()) for a, b, c in want]
+        dec.reset()
+        pk = np.ascontiguousarray(g["packets"].reshape(-1))
+        bufs = [(np.zeros((S, F, 1920), np.float32), np.zeros((S, F), np.int32), np.zeros((S, F), np.uint32)) for _ in range(2)]
+        ins = [(np.ascontiguousarray(offs[:, k * F:(k + 1) * F]), np.ascontiguousarray(g["lens"][:, k * F:(k + 1) * F])) for k in range(ncalls)]
+        for k in range(ncalls):
+            pcm, smp, rng = bufs[k & 1]
+            dec.decode_float_multi_async(pk, ins[k][0], ins[k][1], 960, pcm, smp, rng)
+            if k:
+                dec.wait(1)
+                p2, s2, r2 = bufs[(k - 1) & 1]
+                assert np.array_equal(p2, want[k - 1][0]) and np.array_equal(s2, want[k - 1][1]) and np.array_equal(r2, want[k - 1][2])
+        dec.wait(0)
+        p2, s2, r2 = bufs[(ncalls - 1) & 1]
+        assert np.array_equal(p2, want[-1][0]) and np.array_equal(r2, want[-1][2])
+        assert (dec.final_range() == want[-1][2][:, -1]).all()
+
+
 def test_reset_restarts_streams():
     from opus_codec_b200.batch import BatchDecoder
     g = load_golden("cfg2_mono_20ms_64k_cbr")
