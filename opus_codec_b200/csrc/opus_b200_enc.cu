@@ -27,7 +27,7 @@ struct ObEncStream {           // everything one stream owns on the device
 // a warp touched 32 different lines: 112 ms per frame at 16384 streams.)
 __global__ void __launch_bounds__(OB_ENC_THREADS)
 ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *__restrict__ lens, uint32_t *__restrict__ ranges,
-            ObEncStream *__restrict__ streams, ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes, int lanes)
+            ObEncStream *__restrict__ streams, ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes, int lanes, int f0, int Fc)
 {
     // Only the first `lanes` threads of each warp carry a stream (tuning knob).  Spreading the streams over more, partly filled,
     // warps was tried to hide the local-memory latency this kernel is bound by (ncu: 0.26 warp-instructions/cycle/SM, 8.6 of 13
@@ -46,7 +46,7 @@ ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *_
     // NOTE: the frame counter is deliberately volatile.  The loop body is one huge divergent region; with a plain `int f`
     // nvcc 12.9 keeps f in a UNIFORM register, and lanes that fall behind re-execute the shared increment -- frames get
     // skipped / mis-indexed whenever lanes of a warp diverge (found on B200: fine with 1-4 identical lanes, wrong with 5+).
-    for (volatile int f = 0; f < F; f++) {
+    for (volatile int f = f0; f < f0 + Fc; f++) {              // this launch covers the frame window [f0, f0+Fc) of a [S][F] batch
         const size_t w = (size_t)s * F + f;
         const int n = ob_opus_encode(cfg, es.os, es.st, sc, pcm + w * (size_t)frame_size * CC, frame_size, out + w * (size_t)max_bytes, max_bytes);
         lens[w] = n;
@@ -76,8 +76,8 @@ __global__ void ob_k_enc_gather(const ObEncStream *streams, uint32_t *ranges, in
 struct ObEncoder {
     int S, CC, device, max_frames, lanes;
     ObOpusEncCfg cfg;
-    cudaStream_t stream;
-    cudaEvent_t ev[2];
+    cudaStream_t stream, copy_stream;
+    cudaEvent_t ev[2], win_ev[4];
     bool timed;
     ObEncStream *d_streams;
     float *d_pcm; size_t pcm_cap;
@@ -113,6 +113,8 @@ ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         bool ok = cudaSetDevice(device) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
         ok = ok && cudaEventCreate(&e->ev[0]) == cudaSuccess && cudaEventCreate(&e->ev[1]) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreateWithFlags(&e->win_ev[i], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_streams, sizeof(ObEncStream) * n_streams) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_lens, sizeof(int32_t) * total) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_ranges, sizeof(uint32_t) * total) == cudaSuccess;
@@ -136,6 +138,8 @@ void ob_encoder_destroy(ObEncoder *e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_streams); cudaFree(e->d_pcm); cudaFree(e->d_out); cudaFree(e->d_lens); cudaFree(e->d_ranges);
     for (int i = 0; i < 2; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (int i = 0; i < 4; i++) if (e->win_ev[i]) cudaEventDestroy(e->win_ev[i]);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -184,13 +188,15 @@ int32_t ob_encoder_set_force_channels(ObEncoder *e, int32_t ch) { if (!e || (ch 
 int32_t ob_encoder_set_packet_loss_perc(ObEncoder *e, int32_t p) { if (!e || p < 0 || p > 100) return OB_BAD_ARG; e->cfg.packet_loss = p; return OB_OK; }
 int32_t ob_encoder_set_lsb_depth(ObEncoder *e, int32_t d) { if (!e || d < 8 || d > 24) return OB_BAD_ARG; e->cfg.lsb_depth = d; return OB_OK; }
 
-static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size, uint8_t *d_out, int max_bytes, int32_t *d_lens, uint32_t *d_ranges)
+static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size, uint8_t *d_out, int max_bytes, int32_t *d_lens, uint32_t *d_ranges,
+                         int f0 = 0, int Fc = -1)
 {
-    OB_CUDA(cudaEventRecord(e->ev[0], e->stream));
+    if (Fc < 0) Fc = F;
+    if (f0 == 0) OB_CUDA(cudaEventRecord(e->ev[0], e->stream));
     int lanes = e->lanes;
     if (const char *v = getenv("OB_ENC_LANES")) { const int t = atoi(v); if (t >= 1 && t <= OB_ENC_THREADS) lanes = t; }   // tuning aid
-    ob_k_encode<<<(e->S + lanes - 1) / lanes, OB_ENC_THREADS, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->cfg, e->S, F, frame_size, max_bytes, lanes);
-    OB_CUDA(cudaEventRecord(e->ev[1], e->stream));
+    ob_k_encode<<<(e->S + lanes - 1) / lanes, OB_ENC_THREADS, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->cfg, e->S, F, frame_size, max_bytes, lanes, f0, Fc);
+    if (f0 + Fc == F) OB_CUDA(cudaEventRecord(e->ev[1], e->stream));
     OB_CUDA(cudaGetLastError());
     e->launches += 1;
     e->timed = true;
@@ -216,9 +222,20 @@ int32_t ob_encode_float_multi(ObEncoder *e, int32_t n_frames, const float *pcm, 
     const size_t total = (size_t)e->S * n_frames, pcm_floats = total * (size_t)frame_size * e->CC, out_bytes = total * (size_t)max_bytes;
     if (pcm_floats > e->pcm_cap) { cudaFree(e->d_pcm); e->d_pcm = nullptr; e->pcm_cap = 0; OB_CUDA(cudaMalloc(&e->d_pcm, pcm_floats * sizeof(float))); e->pcm_cap = pcm_floats; }
     if (out_bytes > e->out_cap) { cudaFree(e->d_out); e->d_out = nullptr; e->out_cap = 0; OB_CUDA(cudaMalloc(&e->d_out, out_bytes)); e->out_cap = out_bytes; }
-    OB_CUDA(cudaMemcpyAsync(e->d_pcm, pcm, pcm_floats * sizeof(float), cudaMemcpyHostToDevice, e->stream));
-    const int r = ob_enc_launch(e, n_frames, e->d_pcm, frame_size, e->d_out, max_bytes, e->d_lens, e->d_ranges);
-    if (r != OB_OK) return r;
+    // Frame windows: the upload of window k+1 (2-D copy out of the [S][F] host array, on the copy stream) overlaps the kernel of
+    // window k; the per-stream state simply carries over from launch to launch.
+    const int nwin = (total >= 32768 && n_frames >= 4) ? 4 : (total >= 8192 && n_frames >= 2 ? 2 : 1);
+    const int per = (n_frames + nwin - 1) / nwin;
+    const size_t pf = (size_t)frame_size * e->CC;
+    for (int k = 0, f0 = 0; f0 < n_frames; k++, f0 += per) {
+        const int Fc = n_frames - f0 < per ? n_frames - f0 : per;
+        OB_CUDA(cudaMemcpy2DAsync(e->d_pcm + f0 * pf, n_frames * pf * sizeof(float), pcm + f0 * pf, n_frames * pf * sizeof(float),
+                                  Fc * pf * sizeof(float), e->S, cudaMemcpyHostToDevice, e->copy_stream));
+        OB_CUDA(cudaEventRecord(e->win_ev[k], e->copy_stream));
+        OB_CUDA(cudaStreamWaitEvent(e->stream, e->win_ev[k], 0));
+        const int r = ob_enc_launch(e, n_frames, e->d_pcm, frame_size, e->d_out, max_bytes, e->d_lens, e->d_ranges, f0, Fc);
+        if (r != OB_OK) return r;
+    }
     OB_CUDA(cudaMemcpyAsync(out, e->d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
     OB_CUDA(cudaMemcpyAsync(lens_out, e->d_lens, total * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out, e->d_ranges, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
