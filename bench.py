@@ -366,8 +366,16 @@ def run_ours(args):
         dom = int(np.argmax(kms))
         bytes_per_launch = algorithmic_bytes_per_frame(F) * S * F
         achieved = bytes_per_launch / (kms[dom] / 1000.0) / 1e9
+        traffic, traffic_src = None, None
+        try:      # DRAM bytes of one launch of that kernel at this shape, from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01f_dram_traffic.json")))
+            if tj["frames_per_launch"] == S * F:
+                traffic, traffic_src = tj["kernels"][names[dom]]["dram_bytes"], tj["source"]
+        except Exception:
+            pass
         roof = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
+                "traffic": traffic, "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
                 "kernel_ms": dict(zip(names, [float(v) for v in kms])),
                 "algorithmic_bytes_per_frame": algorithmic_bytes_per_frame(F),
                 "pipeline_achieved_GBps": bytes_per_launch / (float(kms.sum()) / 1000.0) / 1e9}
