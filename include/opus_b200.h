@@ -10,11 +10,11 @@
  *   -6 INVALID_STATE, -7 ALLOC_FAIL.  Batch calls return the call-level status; per-stream results
  *   (samples per channel, or a negative code) are written to samples_out[].
  *
- * Scope of this version: Fs = 48000, CELT-only TOC (config >= 16), packet code 0, fec = false.  Lost packets
- * (len 0) and DTX payloads (<= 1 byte) are concealed like the reference does (celt_decode_lost).  Anything else
- * (SILK / hybrid TOC, multi-frame codes 1-3) gives that (stream, frame) the status OPUS_UNIMPLEMENTED (-5) and
- * leaves the stream's state untouched; other streams are unaffected.  There is no CPU fallback: every entry
- * point that decodes fails with OPUS_INTERNAL_ERROR if no CUDA device is usable.
+ * Scope of this version: Fs = 48000, CELT-only TOC (config >= 16), every packet code (0-3: several frames per packet,
+ * CBR / VBR sizes, padding), fec = false.  Lost packets (len 0) and DTX frames (<= 1 byte) are concealed like the
+ * reference does (celt_decode_lost).  A SILK / hybrid TOC gives that (stream, packet) the status OPUS_UNIMPLEMENTED (-5),
+ * a malformed packet OPUS_INVALID_PACKET (-4), both leaving the stream's state untouched; other streams are unaffected.
+ * There is no CPU fallback: every entry point that decodes fails with OPUS_INTERNAL_ERROR if no CUDA device is usable.
  */
 #ifndef OPUS_B200_H
 #define OPUS_B200_H
@@ -30,7 +30,8 @@ typedef struct ObDecoder ObDecoder;
 
 /* Replaces n x opus_decoder_create(Fs, channels, &err) (src/bindings.rs:366-373; Decoder::new src/decoder.rs:35-63).
  * n_streams independent decoders with `channels` output channels each live on CUDA device `device`.
- * max_frames: the largest number of consecutive frames per stream any single call will pass (>= 1).
+ * max_frames: the largest number of CELT frames per stream any single call will hold (>= 1): one per code-0 packet, up to 48
+ * for a code-3 packet.  A packet whose frames do not fit any more gets OPUS_BUFFER_TOO_SMALL.
  * Returns NULL and sets *error on failure. */
 ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, int32_t device, int32_t max_frames, int32_t *error);
 

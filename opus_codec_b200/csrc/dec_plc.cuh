@@ -33,11 +33,14 @@ struct ObPlanState {
     int32_t loss_duration;     // st->loss_duration, 2.5 ms units, saturates at 10000
     int32_t skip_plc;          // st->skip_plc: noise PLC until two consecutive packets have arrived
     int32_t plc_end;           // st->end as left by the last decoded packet; 0 = nothing decoded yet (OpusDecoder.prev_mode == 0)
+    int32_t last_fs;           // OpusDecoder.frame_size: the frame size of the last packet that arrived (120 after a reset)
 };
 
-// Size of the next concealment frame when `remaining` samples are still to be produced (opus_decoder.c:313-335).
-OB_DEV int ob_plc_chunk(int remaining)
+// Size of the next concealment frame when `remaining` samples are still to be produced: never more than the last packet's frame
+// size (opus_decoder.c:288-289), then the nearest CELT frame size below (opus_decoder.c:313-335).
+OB_DEV int ob_plc_chunk(int remaining, int last_fs)
 {
+    remaining = ob_imin(remaining, last_fs);
     if (remaining >= 960) return 960;
     if (remaining > 480) return 480;
     if (remaining > 240 && remaining < 480) return 240;
@@ -57,12 +60,13 @@ OB_DEV void ob_plc_advance(ObPlanState &p, int n, int CC)       // bookkeeping o
     p.loss_duration = ob_imin(10000, p.loss_duration + (1 << LM));
 }
 // Advances the state past one frame slot (status / flags / final_range / end as the symbol kernel left them in the header).
-OB_DEV void ob_plan_step(ObPlanState &p, int status, int flags, uint32_t final_range, int end, int CC)
+OB_DEV void ob_plan_step(ObPlanState &p, int status, int flags, uint32_t final_range, int end, int CC, int LM)
 {
     if (status <= 0) return;                                     // a failed frame leaves the stream untouched
+    if (!(flags & OB_F_LOST) || (flags & OB_F_DTX)) p.last_fs = OB_SHORT << LM;      // st->frame_size = packet_frame_size (opus_decoder.c:778)
     if (flags & OB_F_LOST) {
         if (p.plc_end == 0) return;                              // nothing decoded yet: zeros, no state change (opus_decoder.c:302-309)
-        for (int rem = status; rem > 0;) { const int n = ob_plc_chunk(rem); ob_plc_advance(p, n, CC); rem -= n; }
+        for (int rem = status; rem > 0;) { const int n = ob_plc_chunk(rem, p.last_fs); ob_plc_advance(p, n, CC); rem -= n; }
     } else {
         if (p.loss_duration == 0) p.skip_plc = 0;                // celt_decoder.c:1103
         p.rng = final_range; p.loss_duration = 0; p.plc_end = end;
@@ -71,8 +75,8 @@ OB_DEV void ob_plan_step(ObPlanState &p, int status, int flags, uint32_t final_r
 // Stamps frame header h with the state it starts from and advances the state past it.
 OB_DEV void ob_plan_frame(ObPlanState &p, ObFrameHdr &h, int CC)
 {
-    if (h.status > 0) { h.seed_in = p.rng; h.loss_in = p.loss_duration; h.skip_in = (uint8_t)p.skip_plc; h.end_in = (uint8_t)p.plc_end; }
-    ob_plan_step(p, h.status, h.flags, h.final_range, h.end, CC);
+    if (h.status > 0) { h.seed_in = p.rng; h.loss_in = p.loss_duration; h.skip_in = (uint8_t)p.skip_plc; h.end_in = (uint8_t)p.plc_end; h.lastfs_in = (uint16_t)p.last_fs; }
+    ob_plan_step(p, h.status, h.flags, h.final_range, h.end, CC, h.LM);
 }
 
 // ---- prefilter_and_fold (celt_decoder.c:515-550): undo the post-filter on the concealed overlap and fold it like the TDAC would ----

@@ -828,23 +828,135 @@ OB_DEV_NOINLINE void ob_decode_all_bands(ObRangeDec &ec, ObFrameIR *ir, int end,
 // celt_decode_with_ec (opus/celt/celt_decoder.c:1100-1290).
 // pkt points at the TOC byte; len includes it.  max_frame is the PCM capacity per channel.
 // ------------------------------------------------------------------------------------------------
-OB_DEV_NOINLINE void ob_decode_symbols(const uint8_t *pkt, int len, int dec_channels, int max_frame, ObFrameIR *ir, int phase_inv_disabled = 0)
+// ---- framing: opus_packet_parse_impl (opus/src/opus.c:194-353, self_delimited = 0) ----------------------------------------------
+OB_DEV int ob_parse_size(const uint8_t *data, int len, int *size)                   // opus.c:146-170
+{
+    if (len < 1) { *size = -1; return -1; }
+    if (data[0] < 252) { *size = data[0]; return 1; }
+    if (len < 2) { *size = -1; return -1; }
+    *size = 4 * data[1] + data[0];
+    return 2;
+}
+// data/len: the packet with its TOC.  Returns the frame count (1..48) or an OPUS_* error; sizes[i] = payload bytes of frame i,
+// *first_off = offset of frame 0's payload from data (the frames follow each other; padding, if any, is behind the last one).
+OB_DEV int ob_parse_packet(const uint8_t *data, int len, int16_t *sizes, int *first_off)
+{
+    if (len < 0) return OB_BAD_ARG;
+    if (len == 0) return OB_INVALID_PACKET;
+    const uint8_t *p = data;
+    const int toc = *p++;
+    const int framesize = (toc & 0x80) ? (48000 << ((toc >> 3) & 3)) / 400 : ((toc & 0x60) == 0x60 ? ((toc & 8) ? 960 : 480) : (((toc >> 3) & 3) == 3 ? 2880 : (48000 << ((toc >> 3) & 3)) / 100));
+    int count, cbr = 0, last_size, bytes, sz;
+    len--;
+    last_size = len;
+    switch (toc & 3) {
+    case 0: count = 1; break;
+    case 1:
+        count = 2; cbr = 1;
+        if (len & 1) return OB_INVALID_PACKET;
+        last_size = len / 2;
+        sizes[0] = (int16_t)last_size;
+        break;
+    case 2:
+        count = 2;
+        bytes = ob_parse_size(p, len, &sz);
+        len -= bytes;
+        if (sz < 0 || sz > len) return OB_INVALID_PACKET;
+        sizes[0] = (int16_t)sz;
+        p += bytes;
+        last_size = len - sz;
+        break;
+    default: {
+        if (len < 1) return OB_INVALID_PACKET;
+        const int ch = *p++;
+        count = ch & 0x3F;
+        if (count <= 0 || framesize * count > 5760) return OB_INVALID_PACKET;
+        len--;
+        if (ch & 0x40) {                                         // padding
+            int q;
+            do {
+                if (len <= 0) return OB_INVALID_PACKET;
+                q = *p++;
+                len--;
+                const int tmp = q == 255 ? 254 : q;
+                len -= tmp;
+            } while (q == 255);
+        }
+        if (len < 0) return OB_INVALID_PACKET;
+        cbr = !(ch & 0x80);
+        if (!cbr) {                                              // VBR: every frame but the last carries its size
+            last_size = len;
+            for (int i = 0; i < count - 1; i++) {
+                bytes = ob_parse_size(p, len, &sz);
+                len -= bytes;
+                if (sz < 0 || sz > len) return OB_INVALID_PACKET;
+                sizes[i] = (int16_t)sz;
+                p += bytes;
+                last_size -= bytes + sz;
+            }
+            if (last_size < 0) return OB_INVALID_PACKET;
+        } else {
+            last_size = len / count;
+            if (last_size * count != len) return OB_INVALID_PACKET;
+            for (int i = 0; i < count - 1; i++) sizes[i] = (int16_t)last_size;
+        }
+    } }
+    if (last_size > 1275) return OB_INVALID_PACKET;
+    sizes[count - 1] = (int16_t)last_size;
+    *first_off = (int)(p - data);
+    return count;
+}
+
+// The packets of ONE stream for one call -> frame slots (the frame loop of opus_decode_native, opus_decoder.c:715-799).  frame_size:
+// the caller's per-packet PCM slot.  Returns the number of slots written (<= cap); a packet that does not fit gets one error slot.
+OB_DEV int ob_frame_packets(const uint8_t *packets, const int32_t *offsets, const int32_t *lens, int F, int frame_size, ObSlot *slots, int cap)
+{
+    int n = 0;
+    int16_t sizes[48];
+    for (int f = 0; f < F; f++) {
+        const int len = lens[f];
+        if (n >= cap) break;                                     // cannot happen for code-0 packets (cap >= F); checked by the host for the rest
+        ObSlot one;
+        one.off = 0; one.len = 0; one.toc = 0; one.flags = OB_SLOT_FIRST | OB_SLOT_LAST; one.pkt = (uint16_t)f; one.sample_off = 0; one.status = 0;
+        if (len <= 0) {                                          // lost packet: conceal the whole slot (opus_decoder.c:684-688, :715-729)
+            one.status = len < 0 || frame_size <= 0 || frame_size % OB_SHORT != 0 ? OB_BAD_ARG : frame_size;
+            slots[n++] = one;
+            continue;
+        }
+        const uint8_t *data = packets + offsets[f];
+        const int toc = data[0];
+        int first_off = 0;
+        const int count = (toc & 0x80) ? ob_parse_packet(data, len, sizes, &first_off) : OB_UNIMPLEMENTED;     // SILK / hybrid: not on this path
+        const int N = OB_SHORT << ((toc >> 3) & 3);
+        if (count < 0) one.status = count;
+        else if (count * N > frame_size) one.status = OB_BUFFER_TOO_SMALL;                                     // opus_decoder.c:764-765
+        else if (n + count > cap) one.status = OB_BUFFER_TOO_SMALL;                                            // decoder created with too few frame slots
+        if (one.status < 0) { slots[n++] = one; continue; }
+        uint32_t off = (uint32_t)offsets[f] + (uint32_t)first_off;
+        for (int i = 0; i < count; i++) {
+            ObSlot sl;
+            sl.off = off; sl.len = sizes[i]; sl.toc = (uint8_t)toc; sl.pkt = (uint16_t)f; sl.sample_off = (uint16_t)(i * N);
+            sl.flags = (uint8_t)((i == 0 ? OB_SLOT_FIRST : 0) | (i == count - 1 ? OB_SLOT_LAST : 0));
+            sl.status = sizes[i] <= 1 ? N : 0;                   // payloads of <= 1 byte are DTX: concealed for one frame (opus_decoder.c:284-290)
+            slots[n++] = sl;
+            off += (uint32_t)sizes[i];
+        }
+    }
+    return n;
+}
+
+// One frame slot -> IR.  pay/paylen: the frame's payload (no TOC); toc: the packet's TOC; conceal > 0: nothing to decode, that
+// many samples are to be concealed (lost packet, DTX frame).
+OB_DEV_NOINLINE void ob_decode_symbols(const uint8_t *pay, int paylen, int toc, int conceal, int dec_channels, ObFrameIR *ir, int phase_inv_disabled = 0)
 {
     ObFrameHdr &h = ir->hdr;
     h.final_range = 0; h.n_leaves = 0; h.flags = 0; h.lcg_total = 0; h.LM = 0; h.C = 1; h.end = 0;
-    if (pkt == nullptr || len <= 0) {
-        // lost packet: conceal the caller's whole slot, which must be a multiple of 2.5 ms (opus_decoder.c:684-688, :715-729)
-        if (max_frame <= 0 || max_frame % OB_SHORT != 0) { h.status = OB_BAD_ARG; return; }
-        h.status = max_frame; h.flags = OB_F_LOST;
+    const int LM = (toc >> 3) & 3, M = 1 << LM, N = OB_SHORT << LM;
+    if (conceal > 0) {                                           // toc == 0: the packet itself is lost; else a DTX frame of a packet that arrived
+        h.status = conceal; h.flags = (uint8_t)(OB_F_LOST | (toc ? OB_F_DTX : 0)); h.LM = (uint8_t)LM;
         return;
     }
-    const int toc = pkt[0];
-    if (!(toc & 0x80)) { h.status = OB_UNIMPLEMENTED; return; }                        // SILK / hybrid
-    if (toc & 0x3) { h.status = OB_UNIMPLEMENTED; return; }                            // multi-frame packets
-    const int LM = (toc >> 3) & 3, M = 1 << LM, N = OB_SHORT << LM;
-    if (N > max_frame) { h.status = OB_BUFFER_TOO_SMALL; return; }
-    if (len <= 2) { h.status = N; h.flags = OB_F_LOST; return; }                       // payload <= 1 byte: DTX, concealed for the TOC's duration (opus_decoder.c:284-290)
-    if (len - 1 > 1275) { h.status = OB_BAD_ARG; return; }
+    int len = paylen;
     const int C = (toc & 4) ? 2 : 1;
     const int bw = (toc >> 5) & 3;
     const int end = bw == 0 ? 13 : bw == 1 ? 17 : bw == 2 ? 19 : 21;
@@ -852,8 +964,7 @@ OB_DEV_NOINLINE void ob_decode_symbols(const uint8_t *pkt, int len, int dec_chan
     h.LM = (uint8_t)LM; h.C = (uint8_t)C; h.end = (uint8_t)end; h.status = N;
 
     ObRangeDec ec;
-    ec.init(pkt + 1, (uint32_t)(len - 1));
-    len -= 1;
+    ec.init(pay, (uint32_t)len);
     int32_t total_bits = len * 8;
     int32_t tell = ec.tell();
     int silence, isTransient = 0, flags = 0;

@@ -20,14 +20,16 @@
 struct ObDecState {
     // owned by the plan pass (ObPlanState, dec_plc.cuh): the integer loss state machine
     uint32_t rng;                 // st->rng: range-coder state left by the last decoded frame, advanced by noise PLC (noise seed)
-    int32_t loss_duration, skip_plc, plc_end;
+    int32_t loss_duration, skip_plc, plc_end, last_frame_size;
     // owned by the synthesis kernel
     uint32_t final_range;         // OpusDecoder.rangeFinal of the last call (opus_decoder.c:651-654)
     int32_t pf_period, pf_period_old, pf_tapset, pf_tapset_old;
     float pf_gain, pf_gain_old;
     float preemph_mem[2];
     int32_t last_packet_duration;
-    int32_t prefilter_and_fold, last_pitch_index, ring_pos, pad;
+    int32_t prefilter_and_fold, last_pitch_index, ring_pos;
+    int32_t pad;
+    int32_t pkt_samples;          // samples (or error) accumulated over the frames of a multi-frame packet still being decoded
     float lpc[2][24];             // CELT_LPC_ORDER coefficients per channel, kept across consecutive losses (celt_decoder.c:637)
     float oldBandE[2 * OB_NB], oldLogE[2 * OB_NB], oldLogE2[2 * OB_NB], backgroundLogE[2 * OB_NB];
 };
@@ -391,8 +393,9 @@ OB_DEV_NOINLINE int ob_conceal(const G &g, ObSynthShared &sh, float *pcm, int CC
     }
     ObPlanState p;
     p.rng = h.seed_in; p.loss_duration = h.loss_in; p.skip_plc = h.skip_in; p.plc_end = h.end_in;
+    p.last_fs = (h.flags & OB_F_DTX) ? OB_SHORT << h.LM : h.lastfs_in;
     for (int done = 0; done < total;) {
-        const int N = ob_plc_chunk(total - done), LM = N == 960 ? 3 : N == 480 ? 2 : N == 240 ? 1 : 0;
+        const int N = ob_plc_chunk(total - done, p.last_fs), LM = N == 960 ? 3 : N == 480 ? 2 : N == 240 ? 1 : 0;
         if (ob_plc_noise_based(p.loss_duration, p.skip_plc)) {
             if (sh.paf) ob_prefilter_and_fold(g, sh, CC);
             ob_plc_noise_fill(g, sh, N, LM, p.loss_duration, p.rng, p.plc_end, CC);

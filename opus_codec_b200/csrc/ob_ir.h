@@ -58,6 +58,7 @@ struct ObBand {
 #define OB_F_POSTFILTER 8
 #define OB_F_ANTICOLLAPSE 16
 #define OB_F_LOST 32             // lost packet (len == 0) or DTX payload (<= 1 byte): conceal `status` samples (opus_decoder.c:284-334, :715-729)
+#define OB_F_DTX 64              // with OB_F_LOST: a DTX frame of a packet that did arrive (its TOC still sets the decoder's frame size)
 
 struct ObFrameHdr {
     int32_t status;            // samples per channel (>0) or OPUS_* error (<0)
@@ -71,6 +72,8 @@ struct ObFrameHdr {
     uint32_t lcg_total;        // LCG steps taken by all bands (seed for anti_collapse = jump(seed_in, lcg_total))
     uint32_t seed_in;          // plan pass: st->rng before this frame (noise fill / folding seed, celt_decoder.c:1279)
     int32_t loss_in;           // plan pass: st->loss_duration before this frame (2.5 ms units, celt_decoder.c:965)
+    uint16_t lastfs_in;        // plan pass: OpusDecoder.frame_size before this frame: a concealment never exceeds it (opus_decoder.c:288-289)
+    uint16_t pad2;
     int16_t coarse_qi[2 * OB_NB];   // Laplace-decoded coarse energy deltas [c*21+i] (quant_bands.c:450-479)
     int16_t pulses[OB_NB];          // PVQ bit allocation per band, 1/8 bit (anti_collapse depth, bands.c:289)
     uint8_t fine_quant[OB_NB];      // fine energy bits per band (rate.c ebits)
@@ -79,6 +82,20 @@ struct ObFrameHdr {
     uint8_t collapse_masks[2 * OB_NB];  // [i*C+c] as in the reference (bands.c:1660-1661)
     int8_t tf_change[OB_NB];        // tf_res after tf_select_table (celt_decoder.c:493-496)
     uint8_t pad1[3];
+};
+
+// One CELT frame to decode or conceal, written by the framing pass (opus_packet_parse_impl, opus/src/opus.c:194-353, and the
+// frame loop of opus_decode_native, opus_decoder.c:715-799).  A code-0 packet is one slot; a code-1/2/3 packet is `count` slots.
+#define OB_SLOT_FIRST 1          // first frame of its packet
+#define OB_SLOT_LAST 2           // last frame of its packet: the packet's sample count / final range are written after it
+struct ObSlot {
+    uint32_t off;                // byte offset of the frame's payload in the packet buffer
+    int16_t len;                 // payload bytes (0..1275)
+    uint8_t toc;                 // the packet's TOC byte
+    uint8_t flags;               // OB_SLOT_*
+    uint16_t pkt;                // which of the stream's packets of this call the frame belongs to
+    uint16_t sample_off;         // first output sample (per channel) inside that packet's PCM slot
+    int32_t status;              // 0: decode `len` bytes; > 0: conceal that many samples (lost packet / DTX frame); < 0: OPUS_* error of the packet
 };
 
 // Per-frame IR slot: header, band records, leaves, pulse vector.

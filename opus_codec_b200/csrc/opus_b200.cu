@@ -24,23 +24,42 @@
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-#define OB_SYM_THREADS 128
-__global__ void __launch_bounds__(OB_SYM_THREADS)
-ob_k_symbols(const uint8_t *__restrict__ packets, const int32_t *__restrict__ offsets, const int32_t *__restrict__ lens,
-             ObFrameIR *__restrict__ ir, int total, int dec_channels, int max_frame, int F, int f0, int Fc, int phase_inv_disabled)
+// Framing pass, one thread per stream: the stream's F packets -> frame slots (code-0 packets: one slot each; codes 1-3: one per
+// coded frame; lost packets and DTX frames: concealment slots; anything off this path: an error slot).
+__global__ void ob_k_frame(const uint8_t *__restrict__ packets, const int32_t *__restrict__ offsets, const int32_t *__restrict__ lens,
+                           ObSlot *__restrict__ slots, int32_t *__restrict__ nslots, int S, int F, int frame_size, int cap, int32_t *__restrict__ multi)
 {
-    // a launch covers the frame window [f0, f0+Fc) of every stream of a [S][F] batch: t -> (stream, frame)
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= total) return;
-    const size_t t = (size_t)(k / Fc) * F + f0 + k % Fc;
-    const int len = lens[t];
-    ob_decode_symbols(len > 0 ? packets + offsets[t] : nullptr, len, dec_channels, max_frame, ir + t, phase_inv_disabled);
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const int n = ob_frame_packets(packets, offsets + (size_t)s * F, lens + (size_t)s * F, F, frame_size, slots + (size_t)s * cap, cap);
+    nslots[s] = n;
+    // slot j <-> packet j unless some packet holds several frames (or did not fit): the host pipelines the call in slot windows
+    // only in the one-to-one case
+    int one_to_one = n == F;
+    for (int j = 0; j < n && one_to_one; j++) one_to_one = slots[(size_t)s * cap + j].pkt == j;
+    if (!one_to_one) *(volatile int32_t *)multi = 1;             // `multi` is mapped host memory: no copy on the stream to read it back
 }
 
-// Plan pass, one thread per stream: walks the frame window in order through the integer loss state machine (which frames are
-// concealed, noise- or pitch-based, how far the noise seed advances) and stamps every frame header with the state it starts from.
-// This is what lets the band kernel stay frame-parallel even though a lost packet changes the seed of the frames after it.
-__global__ void ob_k_plan(ObFrameIR *__restrict__ ir, ObDecState *__restrict__ st, int S, int F, int f0, int Fc, int CC)
+#define OB_SYM_THREADS 128
+__global__ void __launch_bounds__(OB_SYM_THREADS, 6)
+ob_k_symbols(const uint8_t *__restrict__ packets, const ObSlot *__restrict__ slots, const int32_t *__restrict__ nslots,
+             ObFrameIR *__restrict__ ir, int total, int dec_channels, int cap, int f0, int Fc, int phase_inv_disabled)
+{
+    // a launch covers the slot window [f0, f0+Fc) of every stream: k -> (stream, slot)
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
+    const int s = k / Fc, j = f0 + k % Fc;
+    if (j >= nslots[s]) return;
+    const size_t t = (size_t)s * cap + j;
+    const ObSlot sl = slots[t];
+    if (sl.status < 0) { ir[t].hdr.status = sl.status; ir[t].hdr.flags = 0; return; }
+    ob_decode_symbols(packets + sl.off, sl.len, sl.toc, sl.status, dec_channels, ir + t, phase_inv_disabled);
+}
+
+// Plan pass: walks a stream's slot window in order through the integer loss state machine (which frames are concealed, noise- or
+// pitch-based, how far the noise seed advances) and stamps every frame header with the state it starts from.  This is what lets
+// the band kernel stay frame-parallel even though a lost packet changes the seed of the frames after it.
+__global__ void ob_k_plan(ObFrameIR *__restrict__ ir, ObDecState *__restrict__ st, const int32_t *__restrict__ nslots, int S, int cap, int f0, int Fc, int CC)
 {
     // One WARP per stream: the lanes fetch 32 headers at once (one 32-byte sector each, 12.6 KB apart), every lane then replays the
     // serial state machine from registers and keeps the state in front of its own frame -- the memory latency is paid once per
@@ -48,34 +67,39 @@ __global__ void ob_k_plan(ObFrameIR *__restrict__ ir, ObDecState *__restrict__ s
     const int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (s >= S) return;
     ObPlanState p;
-    p.rng = st[s].rng; p.loss_duration = st[s].loss_duration; p.skip_plc = st[s].skip_plc; p.plc_end = st[s].plc_end;
-    for (int base = f0; base < f0 + Fc; base += 32) {
-        const int f = base + lane, cnt = min(32, f0 + Fc - base);
-        ObFrameHdr *h = f < f0 + Fc ? &ir[(size_t)s * F + f].hdr : nullptr;
-        const int status = h ? h->status : 0, flags = h ? h->flags : 0, end = h ? h->end : 0;
+    p.rng = st[s].rng; p.loss_duration = st[s].loss_duration; p.skip_plc = st[s].skip_plc; p.plc_end = st[s].plc_end; p.last_fs = st[s].last_frame_size;
+    const int hi = min(f0 + Fc, nslots[s]);
+    for (int base = f0; base < hi; base += 32) {
+        const int f = base + lane, cnt = min(32, hi - base);
+        ObFrameHdr *h = f < hi ? &ir[(size_t)s * cap + f].hdr : nullptr;
+        const int status = h ? h->status : 0, flags = h ? h->flags : 0, end = h ? h->end : 0, LM = h ? h->LM : 0;
         const uint32_t fr = h ? h->final_range : 0u;
         ObPlanState mine = p;
         for (int j = 0; j < cnt; j++) {
             if (lane == j) mine = p;
             ob_plan_step(p, __shfl_sync(0xffffffffu, status, j), __shfl_sync(0xffffffffu, flags, j), __shfl_sync(0xffffffffu, fr, j),
-                         __shfl_sync(0xffffffffu, end, j), CC);
+                         __shfl_sync(0xffffffffu, end, j), CC, __shfl_sync(0xffffffffu, LM, j));
         }
-        if (h && status > 0) { h->seed_in = mine.rng; h->loss_in = mine.loss_duration; h->skip_in = (uint8_t)mine.skip_plc; h->end_in = (uint8_t)mine.plc_end; }
+        if (h && status > 0) {
+            h->seed_in = mine.rng; h->loss_in = mine.loss_duration; h->skip_in = (uint8_t)mine.skip_plc; h->end_in = (uint8_t)mine.plc_end;
+            h->lastfs_in = (uint16_t)mine.last_fs;
+        }
     }
-    if (lane == 0) { st[s].rng = p.rng; st[s].loss_duration = p.loss_duration; st[s].skip_plc = p.skip_plc; st[s].plc_end = p.plc_end; }
+    if (lane == 0) { st[s].rng = p.rng; st[s].loss_duration = p.loss_duration; st[s].skip_plc = p.skip_plc; st[s].plc_end = p.plc_end; st[s].last_frame_size = p.last_fs; }
 }
 
 #define OB_BANDS_WARPS 6
 #define OB_BANDS_SMEM_PER_WARP ((int)sizeof(ObBandsShared))
 __global__ void __launch_bounds__(OB_BANDS_WARPS * 32)
-ob_k_bands(const ObFrameIR *__restrict__ ir, float *__restrict__ Xg, int S, int F, int f0, int Fc)
+ob_k_bands(const ObFrameIR *__restrict__ ir, const int32_t *__restrict__ nslots, float *__restrict__ Xg, int S, int cap, int f0, int Fc)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
     const int k = blockIdx.x * OB_BANDS_WARPS + warp;
     if (k >= S * Fc) return;
     const int s = k / Fc, f = f0 + k % Fc;
-    const size_t w = (size_t)s * F + f;
+    if (f >= nslots[s]) return;
+    const size_t w = (size_t)s * cap + f;
     const ObFrameIR *fr = ir + w;
     if (fr->hdr.status <= 0 || (fr->hdr.flags & OB_F_LOST)) return;
     const uint32_t seed = fr->hdr.seed_in;       // st->rng before this frame, stamped by the plan pass
@@ -85,9 +109,10 @@ ob_k_bands(const ObFrameIR *__restrict__ ir, float *__restrict__ Xg, int S, int 
 }
 
 #define OB_SYNTH_THREADS 128
-__global__ void __launch_bounds__(OB_SYNTH_THREADS)
-ob_k_synth(const ObFrameIR *__restrict__ ir, const float *__restrict__ Xg, ObDecState *__restrict__ st, float *__restrict__ hist, float *__restrict__ ring,
-           float *__restrict__ pcm, int32_t *__restrict__ samples, uint32_t *__restrict__ ranges, int S, int F, int CC, int frame_size,
+__global__ void __launch_bounds__(OB_SYNTH_THREADS, 7)
+ob_k_synth(const ObFrameIR *__restrict__ ir, const ObSlot *__restrict__ slots, const int32_t *__restrict__ nslots, const float *__restrict__ Xg,
+           ObDecState *__restrict__ st, float *__restrict__ hist, float *__restrict__ ring,
+           float *__restrict__ pcm, int32_t *__restrict__ samples, uint32_t *__restrict__ ranges, int S, int F, int cap, int CC, int frame_size,
            int f0, int Fc, float decode_gain)
 {
     __shared__ ObSynthShared sh;
@@ -117,15 +142,23 @@ ob_k_synth(const ObFrameIR *__restrict__ ir, const float *__restrict__ Xg, ObDec
     uint32_t final_range = state->final_range;
     int last_dur = state->last_packet_duration;
     g.sync();
-    for (int f = f0; f < f0 + Fc; f++) {
-        const size_t w = (size_t)s * F + f;
-        const int n = ob_synth_frame(g, sh, ir + w, Xg + w * OB_X_STRIDE, pcm + w * (size_t)frame_size * CC, CC);
+    int acc = state->pkt_samples;                                   // samples / error of the packet whose frames are being decoded
+    const int hi = min(f0 + Fc, nslots[s]);
+    for (int f = f0; f < hi; f++) {
+        const size_t w = (size_t)s * cap + f;
+        const ObSlot sl = slots[w];
+        const size_t pk = (size_t)s * F + sl.pkt;                   // the caller's packet slot
+        const int n = ob_synth_frame(g, sh, ir + w, Xg + w * OB_X_STRIDE, pcm + (pk * (size_t)frame_size + sl.sample_off) * CC, CC);
+        if (sl.flags & OB_SLOT_FIRST) acc = 0;
         if (n > 0) {
-            last_dur = n;
+            if (acc >= 0) acc += n;
             if (!(sh.hdr.flags & OB_F_LOST)) final_range = sh.hdr.final_range;
             else if (sh.hdr.end_in != 0) final_range = 0;          // concealed frame: rangeFinal = 0 (opus_decoder.c:651-652)
+        } else acc = n;                                             // the packet fails with its first failing frame (opus_decoder.c:786-787)
+        if (sl.flags & OB_SLOT_LAST) {
+            if (acc > 0) last_dur = acc;
+            if (g.lane == 0) { samples[pk] = acc; if (ranges) ranges[pk] = final_range; }
         }
-        if (g.lane == 0) { samples[w] = n; if (ranges) ranges[w] = final_range; }
         g.sync();
     }
     // ---- state: shared -> global ----
@@ -144,6 +177,7 @@ ob_k_synth(const ObFrameIR *__restrict__ ir, const float *__restrict__ Xg, ObDec
         state->preemph_mem[0] = sh.preemph_mem[0]; state->preemph_mem[1] = sh.preemph_mem[1];
         state->final_range = final_range; state->last_packet_duration = last_dur;
         state->last_pitch_index = sh.last_pitch_index; state->prefilter_and_fold = sh.paf; state->ring_pos = sh.ring_pos;
+        state->pkt_samples = acc;
     }
     for (int i = g.lane; i < 2 * 24; i += g.n) state->lpc[i / 24][i % 24] = sh.lpc[i / 24][i % 24];
 }
@@ -159,7 +193,7 @@ __global__ void ob_k_reset(ObDecState *st, float *hist, float *ring, const int32
     for (int i = threadIdx.x; i < (int)(sizeof(ObDecState) / 4); i += blockDim.x) ((uint32_t *)state)[i] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * OB_NB; i += blockDim.x) { state->oldLogE[i] = -28.f; state->oldLogE2[i] = -28.f; }
-    if (threadIdx.x == 0) state->skip_plc = 1;                       // celt_decoder.c:1527
+    if (threadIdx.x == 0) { state->skip_plc = 1; state->last_frame_size = OB_SHORT; }      // celt_decoder.c:1527; opus_decoder.c:161 (frame_size = Fs/400)
     float *h = hist + (size_t)s * CC * OB_HIST_LEN;
     for (int i = threadIdx.x; i < CC * OB_HIST_LEN; i += blockDim.x) h[i] = 0.f;
     float *r = ring + (size_t)s * CC * OB_RING;
@@ -189,6 +223,9 @@ struct ObDecoder {
     bool timed;
     ObDecState *d_state;
     float *d_hist, *d_ring;
+    ObSlot *d_slots; int32_t *d_nslots;   // [S][max_frames] frame slots of the current call, [S] their counts
+    int32_t *d_multi, *h_multi;           // "some packet is not one slot": a word of mapped pinned host memory (host pointer, device alias)
+    cudaEvent_t framed;
     ObFrameIR *d_ir;
     float *d_X;
     // staging for the host-pointer entry points
@@ -207,31 +244,40 @@ struct ObDecoder {
 // just a pointer offset; timed != 0 brackets the kernels with the handle's events.
 static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packets, const int32_t *d_offsets, const int32_t *d_lens,
                      float *d_pcm, int frame_size, int32_t *d_samples, uint32_t *d_ranges, int timed, cudaStream_t stream,
-                     int f0 = 0, int Fc = -1, int which = 3)
+                     int f0 = 0, int Fc = -1, int which = 7)
 {
-    // which: bit 0 = the symbol kernel, bit 1 = band + synthesis kernels, for the frame window [f0, f0+Fc) of streams [s0, s0+Sc)
-    if (Fc < 0) Fc = F;
+    // which: bit 2 = framing kernel, bit 0 = symbol kernel, bit 1 = plan + band + synthesis kernels, for the SLOT window [f0, f0+Fc) of streams
+    // [s0, s0+Sc).  Per-packet arrays (offsets, lens, pcm, samples, ranges) have stride F; per-slot arrays (slots, IR, X) have
+    // stride cap = max_frames.  Fc < 0: every slot the decoder has room for (packets may hold several frames).
+    const int cap = d->max_frames;
+    if (Fc < 0) Fc = cap;
     const int total = Sc * Fc;
-    const size_t w0 = (size_t)s0 * F;
-    ObFrameIR *ir = d->d_ir + w0;
-    float *X = d->d_X + w0 * OB_X_STRIDE;
+    const size_t w0 = (size_t)s0 * F, c0 = (size_t)s0 * cap;
+    ObFrameIR *ir = d->d_ir + c0;
+    float *X = d->d_X + c0 * OB_X_STRIDE;
+    ObSlot *slots = d->d_slots + c0;
+    int32_t *nslots = d->d_nslots + s0;
     ObDecState *st = d->d_state + s0;
     float *hist = d->d_hist + (size_t)s0 * d->CC * OB_HIST_LEN;
     float *ring = d->d_ring + (size_t)s0 * d->CC * OB_RING;
     if (timed) OB_CUDA(cudaEventRecord(d->ev[0], stream));
+    if (which & 4) {
+        ob_k_frame<<<(Sc + 127) / 128, 128, 0, stream>>>(d_packets, d_offsets + w0, d_lens + w0, slots, nslots, Sc, F, frame_size, cap, d->d_multi);
+        d->launches += 1;
+    }
     if (which & 1) {
         ob_k_symbols<<<(total + OB_SYM_THREADS - 1) / OB_SYM_THREADS, OB_SYM_THREADS, 0, stream>>>(
-            d_packets, d_offsets + w0, d_lens + w0, ir, total, d->CC, frame_size, F, f0, Fc, d->phase_inv_disabled);
+            d_packets, slots, nslots, ir, total, d->CC, cap, f0, Fc, d->phase_inv_disabled);
         d->launches += 1;
     }
     if (timed) OB_CUDA(cudaEventRecord(d->ev[1], stream));
     if (which & 2) {
-        ob_k_plan<<<(Sc + 3) / 4, 128, 0, stream>>>(ir, st, Sc, F, f0, Fc, d->CC);
+        ob_k_plan<<<(Sc + 3) / 4, 128, 0, stream>>>(ir, st, nslots, Sc, cap, f0, Fc, d->CC);
         ob_k_bands<<<(total + OB_BANDS_WARPS - 1) / OB_BANDS_WARPS, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, stream>>>(
-            ir, X, Sc, F, f0, Fc);
+            ir, nslots, X, Sc, cap, f0, Fc);
         if (timed) OB_CUDA(cudaEventRecord(d->ev[2], stream));
-        ob_k_synth<<<Sc, OB_SYNTH_THREADS, 0, stream>>>(ir, X, st, hist, ring, d_pcm + w0 * (size_t)frame_size * d->CC, d_samples + w0,
-                                                         d_ranges ? d_ranges + w0 : nullptr, Sc, F, d->CC, frame_size, f0, Fc, d->gain_linear);
+        ob_k_synth<<<Sc, OB_SYNTH_THREADS, 0, stream>>>(ir, slots, nslots, X, st, hist, ring, d_pcm + w0 * (size_t)frame_size * d->CC, d_samples + w0,
+                                                         d_ranges ? d_ranges + w0 : nullptr, Sc, F, cap, d->CC, frame_size, f0, Fc, d->gain_linear);
         d->launches += 3;
     }
     if (timed) OB_CUDA(cudaEventRecord(d->ev[3], stream));
@@ -273,6 +319,10 @@ ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         ok = ok && cudaMalloc(&d->d_state, sizeof(ObDecState) * n_streams) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_hist, sizeof(float) * (size_t)n_streams * channels * OB_HIST_LEN) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_ring, sizeof(float) * (size_t)n_streams * channels * OB_RING) == cudaSuccess;
+        ok = ok && cudaHostAlloc(&d->h_multi, sizeof(int32_t), cudaHostAllocMapped) == cudaSuccess
+                && cudaHostGetDevicePointer(&d->d_multi, d->h_multi, 0) == cudaSuccess
+                && cudaEventCreateWithFlags(&d->framed, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaMalloc(&d->d_slots, sizeof(ObSlot) * total) == cudaSuccess && cudaMalloc(&d->d_nslots, sizeof(int32_t) * n_streams) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_ir, sizeof(ObFrameIR) * total) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_X, sizeof(float) * OB_X_STRIDE * total) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_offsets, sizeof(int32_t) * total) == cudaSuccess;
@@ -304,7 +354,7 @@ void ob_decoder_destroy(ObDecoder *d)
     if (!d) return;
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
-    cudaFree(d->d_state); cudaFree(d->d_hist); cudaFree(d->d_ring); cudaFree(d->d_ir); cudaFree(d->d_X); cudaFree(d->d_packets);
+    cudaFree(d->d_state); cudaFree(d->d_hist); cudaFree(d->d_ring); cudaFree(d->d_slots); cudaFree(d->d_nslots); if (d->h_multi) cudaFreeHost(d->h_multi); if (d->framed) cudaEventDestroy(d->framed); cudaFree(d->d_ir); cudaFree(d->d_X); cudaFree(d->d_packets);
     cudaFree(d->d_offsets); cudaFree(d->d_lens); cudaFree(d->d_gather);
     for (int p = 0; p < 2; p++) { cudaFree(d->d_samples2[p]); cudaFree(d->d_ranges2[p]); cudaFree(d->d_pcm2[p]); if (d->out_done[p]) cudaEventDestroy(d->out_done[p]); }
     if (d->aux_done) cudaEventDestroy(d->aux_done);
@@ -388,6 +438,20 @@ static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *p
     OB_CUDA(cudaMemcpyAsync(d->d_packets, packets, nbytes, cudaMemcpyHostToDevice, d->stream));
     OB_CUDA(cudaMemcpyAsync(d->d_offsets, offsets, total * sizeof(int32_t), cudaMemcpyHostToDevice, d->stream));
     OB_CUDA(cudaMemcpyAsync(d->d_lens, lens, total * sizeof(int32_t), cudaMemcpyHostToDevice, d->stream));
+    // Framing first: it tells whether slot j is packet j for every stream (always true for code-0 packets).  The symbol kernel is
+    // launched behind it right away; the host only waits for the one-word answer of the framing kernel.
+    *d->h_multi = 0;                                 // the previous call's framing kernel has completed (we waited for it)
+    {
+        const int r = ob_launch(d, 0, d->S, n_frames, d->d_packets, d->d_offsets, d->d_lens, d_pcm, frame_size, d_samples, d_ranges, 0, d->stream, 0, -1, 4);
+        if (r != OB_OK) return r;
+    }
+    OB_CUDA(cudaEventRecord(d->framed, d->stream));
+    {
+        const int r = ob_launch(d, 0, d->S, n_frames, d->d_packets, d->d_offsets, d->d_lens, d_pcm, frame_size, d_samples, d_ranges, 0, d->stream, 0, -1, 1);
+        if (r != OB_OK) return r;
+    }
+    OB_CUDA(cudaEventSynchronize(d->framed));
+    const int multi = *(volatile int32_t *)d->h_multi;
     // The call is processed in chunks so that the device->host copy of chunk k overlaps the kernels of chunk k+1 (kernels on
     // d->stream, copies on d->copy_stream, one event per chunk).  With several frames per stream the chunks are FRAME windows
     // of all streams: every launch keeps the full stream-level parallelism the synthesis kernel needs (one block per stream),
@@ -396,12 +460,20 @@ static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *p
     if (const char *v = getenv("OB_DEC_CHUNKS")) { const int t = atoi(v); if (t >= 1) nchunks = t; }      // tuning aid
     if (nchunks > OB_MAX_CHUNKS) nchunks = OB_MAX_CHUNKS;
     const size_t pf = (size_t)frame_size * d->CC;
-    if (n_frames >= nchunks) {
+    if (multi) {
+        // Packets with several frames: the slot <-> packet mapping is data dependent, so the call runs as one window over every
+        // slot the decoder has room for and the outputs come down in one piece.
+        const int r = ob_launch(d, 0, d->S, n_frames, d->d_packets, d->d_offsets, d->d_lens, d_pcm, frame_size, d_samples, d_ranges, 0, d->stream, 0, -1, 2);
+        if (r != OB_OK) return r;
+        OB_CUDA(cudaEventRecord(d->chunk_ev[0], d->stream));
+        OB_CUDA(cudaStreamWaitEvent(d->copy_stream, d->chunk_ev[0], 0));
+        OB_CUDA(cudaMemcpyAsync(pcm_out, d_pcm, pcm_floats * sizeof(float), cudaMemcpyDeviceToHost, d->copy_stream));
+        OB_CUDA(cudaMemcpyAsync(samples_out, d_samples, total * sizeof(int32_t), cudaMemcpyDeviceToHost, d->copy_stream));
+        if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out, d_ranges, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->copy_stream));
+    } else if (n_frames >= nchunks) {
         // The symbol kernel is one thread per frame and latency bound (a launch takes >= 1.6 ms however few frames it covers:
         // measured), so it runs once over the whole call; only the band + synthesis kernels are windowed.
         const int per = (n_frames + nchunks - 1) / nchunks;
-        const int r0 = ob_launch(d, 0, d->S, n_frames, d->d_packets, d->d_offsets, d->d_lens, d_pcm, frame_size, d_samples, d_ranges, 0, d->stream, 0, n_frames, 1);
-        if (r0 != OB_OK) return r0;
         for (int k = 0, f0 = 0; f0 < n_frames; k++, f0 += per) {
             const int Fc = n_frames - f0 < per ? n_frames - f0 : per;
             const int r = ob_launch(d, 0, d->S, n_frames, d->d_packets, d->d_offsets, d->d_lens, d_pcm, frame_size, d_samples, d_ranges, 0, d->stream, f0, Fc, 2);
@@ -421,7 +493,7 @@ static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *p
             const int Sc = d->S - s0 < per ? d->S - s0 : per;
             const size_t w0 = (size_t)s0 * n_frames, cnt = (size_t)Sc * n_frames;
             cudaStream_t cs = (k & 1) ? d->aux_stream : d->stream;       // alternate compute streams: kernels of neighbouring chunks overlap
-            const int r = ob_launch(d, s0, Sc, n_frames, d->d_packets, d->d_offsets, d->d_lens, d_pcm, frame_size, d_samples, d_ranges, 0, cs);
+            const int r = ob_launch(d, s0, Sc, n_frames, d->d_packets, d->d_offsets, d->d_lens, d_pcm, frame_size, d_samples, d_ranges, 0, cs, 0, -1, 2);
             if (r != OB_OK) return r;
             OB_CUDA(cudaEventRecord(d->chunk_ev[k], cs));
             OB_CUDA(cudaStreamWaitEvent(d->copy_stream, d->chunk_ev[k], 0));

@@ -40,3 +40,66 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def have_ref():
     return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libopus_ref.so"))
+
+
+def repacketize(frames, code, pad=0):
+    """Builds one Opus packet (RFC 6716 section 3.2) out of code-0 packets that share a TOC configuration.
+    code 1: two equal-size frames; code 2: two frames, first size explicit; code 3: M frames, VBR sizes, `pad` padding bytes."""
+    toc = frames[0][0] & 0xFC
+    body = [bytes(f[1:]) for f in frames]
+    assert all((f[0] & 0xFC) == toc for f in frames)
+
+    def size_bytes(n):
+        return bytes([n]) if n < 252 else bytes([252 + (n & 3), (n - (252 + (n & 3))) >> 2])
+    if code == 1:
+        assert len(body) == 2 and len(body[0]) == len(body[1])
+        return bytes([toc | 1]) + body[0] + body[1]
+    if code == 2:
+        assert len(body) == 2
+        return bytes([toc | 2]) + size_bytes(len(body[0])) + body[0] + body[1]
+    assert code == 3
+    out = bytes([toc | 3, 0x80 | (0x40 if pad else 0) | len(body)])
+    if pad:
+        p = pad
+        while p > 254:
+            out += bytes([255]); p -= 254
+        out += bytes([p])
+    for b in body[:-1]:
+        out += size_bytes(len(b))
+    out += b"".join(body)
+    return out + bytes(pad)
+
+
+def multiframe_stream(g, s, nframes_out):
+    """Code-1/2/3 packets (incl. padding and a DTX frame inside a code-3 packet) built from stream s of a golden's code-0 packets."""
+    pk, ln = g["packets"][s], g["lens"][s]
+    fr = [bytes(pk[f, :ln[f]]) for f in range(pk.shape[0])]
+    pkts, k = [], 0
+    kinds = [("c3", 3, 0), ("c1", 2, 0), ("c2", 2, 0), ("c3", 2, 300), ("c0", 1, 0), ("c3", 3, 7), ("c3dtx", 3, 0)]
+    while len(pkts) < nframes_out and k + 3 <= len(fr):
+        kind, m, pad = kinds[len(pkts) % len(kinds)]
+        grp = fr[k:k + m]
+        k += m
+        if kind == "c0":
+            pkts.append(grp[0])
+        elif kind == "c1":
+            if len(grp[0]) != len(grp[1]):
+                pkts.append(repacketize(grp, 2))
+            else:
+                pkts.append(repacketize(grp, 1))
+        elif kind == "c2":
+            pkts.append(repacketize(grp, 2))
+        elif kind == "c3dtx":
+            grp = [grp[0], grp[1][:1], grp[2]]            # middle frame: TOC only -> zero-length frame inside the packet -> concealed
+            pkts.append(repacketize(grp, 3))
+        else:
+            pkts.append(repacketize(grp, 3, pad))
+    stride = max(len(p) for p in pkts)
+    import numpy as np
+    out = np.zeros((len(pkts), stride), np.uint8)
+    lens = np.zeros(len(pkts), np.int32)
+    for i, p in enumerate(pkts):
+        out[i, :len(p)] = np.frombuffer(p, np.uint8); lens[i] = len(p)
+    return out, lens
+
+

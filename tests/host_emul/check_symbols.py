@@ -9,7 +9,7 @@ class Hdr(C.Structure):
     _fields_=[('status',C.c_int32),('final_range',C.c_uint32),('n_leaves',C.c_uint16),('pf_pitch',C.c_uint16),
       ('LM',C.c_uint8),('C',C.c_uint8),('end',C.c_uint8),('flags',C.c_uint8),
       ('spread',C.c_uint8),('pf_tapset',C.c_uint8),('pf_qg',C.c_uint8),('coded_bands',C.c_uint8),
-      ('intensity',C.c_uint8),('dual_stereo',C.c_uint8),('skip_in',C.c_uint8),('end_in',C.c_uint8),('lcg_total',C.c_uint32),('seed_in',C.c_uint32),('loss_in',C.c_int32),
+      ('intensity',C.c_uint8),('dual_stereo',C.c_uint8),('skip_in',C.c_uint8),('end_in',C.c_uint8),('lcg_total',C.c_uint32),('seed_in',C.c_uint32),('loss_in',C.c_int32),('lastfs_in',C.c_uint16),('pad2',C.c_uint16),
       ('coarse_qi',C.c_int16*42),('pulses',C.c_int16*21),('fine_quant',C.c_uint8*21),('fine_q2',C.c_uint8*42),
       ('final_bit',C.c_int8*42),('collapse_masks',C.c_uint8*42),('tf_change',C.c_int8*21),('pad1',C.c_uint8*3)]
 assert C.sizeof(Hdr)==L.emul_hdr_size(), (C.sizeof(Hdr), L.emul_hdr_size())

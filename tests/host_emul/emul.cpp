@@ -10,8 +10,14 @@ int emul_ir_size() { return (int)sizeof(ObFrameIR); }
 int emul_hdr_size() { return (int)sizeof(ObFrameHdr); }
 void emul_decode_symbols(const uint8_t *pkt, int len, int dec_channels, int max_frame, ObFrameIR *ir)
 {
+    // one code-0 packet through the framing pass and the symbol pass
     memset(ir, 0, sizeof(*ir));
-    ob_decode_symbols(pkt, len, dec_channels, max_frame, ir);
+    ObSlot sl[48];
+    const int32_t off = 0, ln = len;
+    const int n = ob_frame_packets(pkt, &off, &ln, 1, max_frame, sl, 48);
+    if (n < 1) { ir->hdr.status = OB_INTERNAL_ERROR; return; }
+    if (sl[0].status < 0) { ir->hdr.status = sl[0].status; return; }
+    ob_decode_symbols(pkt + sl[0].off, sl[0].len, sl[0].toc, sl[0].status, dec_channels, ir);
 }
 }
 
@@ -34,25 +40,36 @@ int emul_decode_stream(const uint8_t *pkts, const int *lens, int stride, int nfr
     ob_synth_init(g, *sh);
     sh->ring = (float *)calloc(2 * OB_RING, sizeof(float));
     sh->decode_gain = 1.f;
-    ObPlanState plan = {0u, 0, 1, 0};                     // OPUS_RESET_STATE: skip_plc = 1 (celt_decoder.c:1527)
+    ObPlanState plan = {0u, 0, 1, 0, OB_SHORT};                     // OPUS_RESET_STATE: skip_plc = 1 (celt_decoder.c:1527)
     uint32_t final_range = 0;
-    for (int f = 0; f < nframes; f++) {
+    // framing pass over the whole stream, then slot by slot through the symbol, plan, band and synthesis stages
+    const int cap = nframes * 48;
+    ObSlot *slots = (ObSlot *)calloc((size_t)cap, sizeof(ObSlot));
+    int32_t *offs = (int32_t *)calloc((size_t)nframes, sizeof(int32_t));
+    for (int f = 0; f < nframes; f++) offs[f] = f * stride;
+    const int ns = ob_frame_packets(pkts, offs, lens, nframes, max_frame, slots, cap);
+    int acc = 0;
+    for (int j = 0; j < ns; j++) {
+        const ObSlot sl = slots[j];
         memset(ir, 0, sizeof(*ir));
-        ob_decode_symbols(lens[f] > 0 ? pkts + (size_t)f * stride : nullptr, lens[f], dec_channels, max_frame, ir);
+        if (sl.status < 0) ir->hdr.status = sl.status;
+        else ob_decode_symbols(pkts + sl.off, sl.len, sl.toc, sl.status, dec_channels, ir);
         ob_plan_frame(plan, ir->hdr, dec_channels);
         int n = ir->hdr.status;
         if (n > 0) {
             if (!(ir->hdr.flags & OB_F_LOST)) {
-                for (int j = 0; j < 2 * OB_MAX_N; j++) X[j] = __builtin_nanf("");     // bands >= end are never written
+                for (int k = 0; k < 2 * OB_MAX_N; k++) X[k] = __builtin_nanf("");     // bands >= end are never written
                 ob_reconstruct_bands(g, ir, ir->hdr.seed_in, *bsh, X);
-                if (Xtap) memcpy(Xtap + (size_t)f * 1920, X, sizeof(float) * ir->hdr.C * n);
+                if (Xtap && (sl.flags & OB_SLOT_FIRST)) memcpy(Xtap + (size_t)sl.pkt * 1920, X, sizeof(float) * ir->hdr.C * n);
                 final_range = ir->hdr.final_range;
             } else if (ir->hdr.end_in != 0) final_range = 0;
-            n = ob_synth_frame(g, *sh, ir, X, pcm_out + (size_t)f * max_frame * dec_channels, dec_channels);
+            n = ob_synth_frame(g, *sh, ir, X, pcm_out + ((size_t)sl.pkt * max_frame + sl.sample_off) * dec_channels, dec_channels);
         }
-        samples[f] = n;
-        ranges[f] = final_range;
+        if (sl.flags & OB_SLOT_FIRST) acc = 0;
+        if (n > 0) { if (acc >= 0) acc += n; } else acc = n;
+        if (sl.flags & OB_SLOT_LAST) { samples[sl.pkt] = acc; ranges[sl.pkt] = final_range; }
     }
+    free(slots); free(offs);
     free(sh->ring); free(sh); free(ir); free(X); free(bsh);
     return 0;
 }

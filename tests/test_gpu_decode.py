@@ -10,7 +10,7 @@ import tempfile
 import numpy as np
 import pytest
 
-from conftest import plc_golden_names, load_plc_golden, golden_names, load_golden
+from conftest import plc_golden_names, load_plc_golden, multiframe_stream, golden_names, load_golden
 
 pytestmark = pytest.mark.gpu
 PCM_TOL = 1e-4
@@ -83,7 +83,7 @@ def test_mixed_frame_sizes_in_one_batch():
 
 
 def test_per_stream_errors_do_not_disturb_neighbours():
-    from opus_codec_b200.batch import BatchDecoder, UNIMPLEMENTED, BUFFER_TOO_SMALL
+    from opus_codec_b200.batch import BatchDecoder, UNIMPLEMENTED, BUFFER_TOO_SMALL, INVALID_PACKET
     g = load_golden("cfg2_mono_20ms_64k_cbr")
     S, F = 6, 10
     pk = g["packets"][:S, :F].copy()
@@ -91,11 +91,11 @@ def test_per_stream_errors_do_not_disturb_neighbours():
     stride = pk.shape[2]
     ln[1, 3] = 0                      # lost packet -> concealed: 960 samples, final range 0
     pk[2, 4, 0] = 0x08                # SILK TOC
-    pk[3, 5, 0] = 0xF9                # code-1 packet (two frames)
+    pk[3, 5, 0] = 0xF9                # code-1 packet whose payload is not two equal halves (159 bytes): invalid (opus.c:240-242)
     ln[4, 6] = 2                      # 1-byte payload -> DTX, concealed for the TOC's duration
     with BatchDecoder(S, 48000, 1, device=0, max_frames=F) as dec:
         pcm, samples, ranges = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, 960)
-    assert samples[2, 4] == UNIMPLEMENTED and samples[3, 5] == UNIMPLEMENTED
+    assert samples[2, 4] == UNIMPLEMENTED and samples[3, 5] == INVALID_PACKET
     assert samples[1, 3] == 960 and samples[4, 6] == 960 and ranges[1, 3] == 0 and ranges[4, 6] == 0
     good = np.ones((S, F), bool)
     for s, f in ((2, 4), (3, 5)):
@@ -267,6 +267,45 @@ def test_pipelined_async_calls_match_blocking_calls():
         p2, s2, r2 = bufs[(ncalls - 1) & 1]
         assert np.array_equal(p2, want[-1][0]) and np.array_equal(r2, want[-1][2])
         assert (dec.final_range() == want[-1][2][:, -1]).all()
+
+
+@pytest.mark.parametrize("name", ["cfg2_mono_20ms_64k_cbr", "stereo_20ms_vbr_96k", "cfg4_stereo_5ms_96k", "cfg4_mono_2p5ms_64k"])
+def test_multiframe_packets(have_ref, name):
+    """TOC codes 1, 2, 3 (CBR / VBR sizes, padding, a DTX frame inside a packet) and a lost 3-frame slot.  Property: a multi-frame
+    packet decodes to the concatenation of its frames decoded as code-0 packets, final range = the last frame's; and, when the
+    reference is on the box, everything equals the reference's decode of the same packets."""
+    from opus_codec_b200.batch import BatchDecoder
+    g = load_golden(name)
+    fs, dc = g["frame_size"], g["dec_channels"]
+    S = 3
+    built = [multiframe_stream(g, s, 14) for s in range(S)]
+    F = min(b[0].shape[0] for b in built)
+    stride = max(b[0].shape[1] for b in built)
+    pk = np.zeros((S, F, stride), np.uint8); ln = np.zeros((S, F), np.int32)
+    for s, (p, l) in enumerate(built):
+        pk[s, :, :p.shape[1]] = p[:F]; ln[s] = l[:F]
+    ln[1, 4] = 0
+    slot = 3 * fs
+    with BatchDecoder(S, 48000, dc, device=0, max_frames=3 * F) as dec:
+        pcm, samples, ranges = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, slot)
+    pcm = pcm.reshape(S, F, slot * dc)
+    # stream 0 holds no loss and no DTX up to packet 5: compare with the golden's frame-by-frame decode
+    k = 0
+    for f in range(6):
+        n = samples[0, f] // fs
+        assert samples[0, f] > 0 and samples[0, f] % fs == 0
+        want = g["pcm"][0, k:k + n].reshape(-1)
+        assert np.abs(pcm[0, f, :samples[0, f] * dc] - want).max() <= PCM_TOL
+        assert ranges[0, f] == g["dec_rng"][0, k + n - 1]
+        k += n
+    if have_ref:
+        from oracle import refpy
+        for s in range(S):
+            ref, rr, rs = refpy.decode_stream(pk[s], ln[s], slot, dc, pure_c=True)
+            assert (samples[s] == rs).all() and (ranges[s] == rr).all()
+            for f in range(F):
+                tol = PCM_TOL if (s != 1 or f < 4) and f < 6 else 3e-3      # after a concealment: the reference's own spread (see the PLC test)
+                assert np.abs(pcm[s, f, :rs[f] * dc] - ref[f, :rs[f] * dc]).max() <= tol, (s, f)
 
 
 def test_reset_restarts_streams():

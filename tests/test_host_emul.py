@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT, golden_names, load_golden, plc_golden_names, load_plc_golden
+from conftest import ROOT, golden_names, load_golden, plc_golden_names, load_plc_golden, multiframe_stream
 from oracle import oraclepy
 
 EMU = os.path.join(ROOT, "tests", "host_emul")
@@ -58,6 +58,26 @@ def test_concealment_device_code_matches_reference_c_build(emul, base):
         assert (smp == p["samples"][s]).all() and (rng == p["ranges"][s]).all()
         assert (ln <= 2).sum() >= 10
         assert np.abs(pcm - p["pcm_c"][s]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("name", ["cfg2_mono_20ms_64k_cbr", "stereo_20ms_vbr_96k", "cfg4_stereo_5ms_96k", "cfg4_mono_2p5ms_64k"])
+def test_multiframe_packets_device_code_matches_reference(emul, have_ref, name):
+    """TOC codes 1, 2 and 3 (CBR/VBR, padding, a DTX frame inside) through the framing pass of the device code vs the reference."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    g = load_golden(name)
+    fs, dc = g["frame_size"], g["dec_channels"]
+    pk, ln = multiframe_stream(g, 0, 14)
+    ln[4] = 0                                              # and a lost packet in between: 3 frames' worth concealed in pieces
+    nf, slot = pk.shape[0], 3 * fs
+    ref, rr, rs = refpy.decode_stream(pk, ln, slot, dc, pure_c=True)
+    pcm = np.zeros((nf, slot * dc), np.float32); rng = np.zeros(nf, np.uint32); smp = np.zeros(nf, np.int32)
+    emul.emul_decode_stream(P(pk, C.c_ubyte), P(ln, C.c_int), pk.shape[1], nf, slot, dc, P(pcm, C.c_float), P(rng, C.c_uint32), P(smp, C.c_int), None)
+    assert (smp == rs).all() and (rng == rr).all(), (smp, rs)
+    assert set(int(b) & 3 for b in pk[:, 0]) == {0, 1, 2, 3} or name == "stereo_20ms_vbr_96k"
+    for f in range(nf):
+        assert np.abs(pcm[f, :rs[f] * dc] - ref[f, :rs[f] * dc]).max() <= 1e-6
 
 
 def _fuzz_streams(seed, trials, nf=10, with_loss=True):
