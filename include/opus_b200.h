@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define OB_ABI_VERSION 4
+#define OB_ABI_VERSION 5
 
 typedef struct ObDecoder ObDecoder;
 
@@ -58,6 +58,14 @@ int32_t ob_decode_float(ObDecoder *dec, const uint8_t *packets, const int32_t *o
 int32_t ob_decode_float_multi(ObDecoder *dec, int32_t n_frames, const uint8_t *packets, const int32_t *offsets,
                               const int32_t *lens, float *pcm_out, int32_t frame_size, int32_t *samples_out,
                               uint32_t *ranges_out);
+
+/* Replaces n x opus_decode(st, data, len, pcm, frame_size, 0) (src/bindings.rs:382-392; Decoder::decode src/decoder.rs:75-127):
+ * int16 PCM.  As in the reference's float build the packet is decoded in float, run through opus_pcm_soft_clip (whose gain is
+ * carried from packet to packet per stream) and rounded to nearest with saturation.  pcm_out: [n_streams][n_frames][frame_size*channels]. */
+int32_t ob_decode(ObDecoder *dec, const uint8_t *packets, const int32_t *offsets, const int32_t *lens,
+                  int16_t *pcm_out, int32_t frame_size, int32_t *samples_out);
+int32_t ob_decode_multi(ObDecoder *dec, int32_t n_frames, const uint8_t *packets, const int32_t *offsets, const int32_t *lens,
+                        int16_t *pcm_out, int32_t frame_size, int32_t *samples_out, uint32_t *ranges_out);
 
 /* Pipelined form of ob_decode_float_multi for callers that keep two calls in flight (a media server draining jitter buffers):
  * returns once the work is enqueued; the outputs are valid after ob_decoder_wait.  While call n's PCM travels to the host,

@@ -90,6 +90,20 @@ class BatchDecoder:
                                              _vp(samples), _vp(ranges)))
         return pcm, samples, ranges
 
+    def decode_multi(self, packets, offsets, lens, frame_size):
+        """int16 form (ob_decode_multi; Decoder::decode, src/decoder.rs:75-127): soft-clipped, rounded PCM i16 [S, F, frame_size*channels]."""
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        lens = np.ascontiguousarray(lens, np.int32)
+        packets = np.ascontiguousarray(packets, np.uint8)
+        if offsets.shape != lens.shape or offsets.ndim != 2 or offsets.shape[0] != self.n_streams or frame_size <= 0 or frame_size > MAX_FRAME_SAMPLES_48KHZ:
+            raise OpusError(BAD_ARG)
+        S, F = offsets.shape
+        pcm = np.zeros((S, F, frame_size * self.channels), np.int16)
+        samples = np.zeros((S, F), np.int32)
+        ranges = np.zeros((S, F), np.uint32)
+        _check(self._L.ob_decode_multi(self._h, F, _vp(packets), _vp(offsets), _vp(lens), _vp(pcm), frame_size, _vp(samples), _vp(ranges)))
+        return pcm, samples, ranges
+
     def decode_float_multi_async(self, packets, offsets, lens, frame_size, pcm, samples, ranges):
         """Pipelined form (ob_decode_float_multi_async): enqueue and return; all arrays are caller-owned, C-contiguous numpy arrays
         (ideally over pinned memory) that must stay alive and untouched until wait() says the call has completed."""

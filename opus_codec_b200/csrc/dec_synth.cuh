@@ -29,6 +29,7 @@ struct ObDecState {
     int32_t last_packet_duration;
     int32_t prefilter_and_fold, last_pitch_index, ring_pos;
     int32_t pad;
+    float softclip_mem[2];        // OpusDecoder.softclip_mem: the int16 path's soft clipper carries its last gain (opus_decoder.c:96)
     int32_t pkt_samples;          // samples (or error) accumulated over the frames of a multi-frame packet still being decoded
     float lpc[2][24];             // CELT_LPC_ORDER coefficients per channel, kept across consecutive losses (celt_decoder.c:637)
     float oldBandE[2 * OB_NB], oldLogE[2 * OB_NB], oldLogE2[2 * OB_NB], backgroundLogE[2 * OB_NB];
@@ -230,6 +231,7 @@ struct ObSynthShared {
     float lpc[2][24];
     int32_t last_pitch_index, paf;   // paf = st->prefilter_and_fold
     float decode_gain;               // linear gain of OPUS_SET_GAIN (1 = none)
+    float softclip_mem[2];           // OpusDecoder.softclip_mem (int16 API)
     int32_t ring_pos;                // next write position (= oldest sample) of the global history ring
     float *ring;                     // this stream's ring: [CC][OB_RING]
 };
@@ -292,6 +294,13 @@ OB_DEV void ob_anti_collapse(const G &g, ObSynthShared &sh, float *X, int N, uin
 }
 
 #include "dec_plc.cuh"
+
+#ifdef __CUDA_ARCH__
+#define OB_F2I_RN(v) __float2int_rn(v)
+#else
+#include <math.h>
+#define OB_F2I_RN(v) ((int)lrintf(v))
+#endif
 
 // denormalise_bands (bands.c:196-265) on the X tile in sh.freq (C coded channels, energies in sh.oldBandE), the mono<->stereo
 // cases of celt_synthesis (celt_decoder.c:415-441) and the inverse MDCTs into buf[c] + HISTK.
@@ -412,6 +421,78 @@ OB_DEV_NOINLINE int ob_conceal(const G &g, ObSynthShared &sh, float *pcm, int CC
         done += N;
     }
     return total;
+}
+
+// opus_pcm_soft_clip (opus/src/opus.c:39-144) for ONE channel of an interleaved packet that has already been limited to +-2:
+// x[i*C], i < N.  Serial by nature (zero-crossing searches, a gain carried from packet to packet); run by one lane, and only for
+// packets that actually exceed +-1 or follow one that did.
+OB_DEV float ob_soft_clip_channel(float *x, int N, int C, float a)
+{
+    int i;
+    for (i = 0; i < N; i++) {                                        // continue the previous packet's non-linearity
+        if (x[i * C] * a >= 0) break;
+        x[i * C] = OB_MACS(x[i * C], OB_FMUL(a, x[i * C]), x[i * C]);      // x + (a*x)*x, un-fused like the reference's C
+    }
+    int curr = 0;
+    const float x0 = x[0];
+    while (1) {
+        int start, end, peak_pos, special;
+        float maxval;
+        for (i = curr; i < N; i++) if (x[i * C] > 1 || x[i * C] < -1) break;
+        if (i == N) { a = 0; break; }
+        peak_pos = i;
+        start = end = i;
+        maxval = fabsf(x[i * C]);
+        while (start > 0 && x[i * C] * x[(start - 1) * C] >= 0) start--;
+        while (end < N && x[i * C] * x[end * C] >= 0) {
+            if (fabsf(x[end * C]) > maxval) { maxval = fabsf(x[end * C]); peak_pos = end; }
+            end++;
+        }
+        special = (start == 0 && x[i * C] * x[0] >= 0);
+        a = (maxval - 1) / (maxval * maxval);
+        a = OB_MACS(a, a, 2.4e-7f);
+        if (x[i * C] > 0) a = -a;
+        for (i = start; i < end; i++) x[i * C] = OB_MACS(x[i * C], OB_FMUL(a, x[i * C]), x[i * C]);
+        if (special && peak_pos >= 2) {
+            float offset = x0 - x[0];
+            const float delta = offset / peak_pos;
+            for (i = curr; i < peak_pos; i++) {
+                offset -= delta;
+                x[i * C] += offset;
+                x[i * C] = fmaxf(-1.f, fminf(1.f, x[i * C]));
+            }
+        }
+        curr = end;
+        if (curr == N) break;
+    }
+    return a;
+}
+
+// The int16 API (opus_decode, opus_decoder.c:861-894): soft clip over the whole packet, then FLOAT2INT16 (round to nearest even,
+// saturating).  x: the packet's float PCM (global memory, n samples per channel, written by this block); out: its int16 slot.
+template <class G>
+OB_DEV void ob_packet_to_int16(const G &g, float *x, int16_t *out, int n, int CC, float *softclip_mem)
+{
+    g.sync();                                                        // the frames' PCM stores are visible to the whole block
+    float over = 0.f;
+    for (int t = g.lane; t < n * CC; t += g.n) {
+        const float v = fmaxf(-2.f, fminf(2.f, x[t]));
+        x[t] = v;
+        if (v > 1.f || v < -1.f) over = 1.f;
+    }
+    over = g.sum(over);
+    const bool carry = softclip_mem[0] != 0.f || (CC == 2 && softclip_mem[1] != 0.f);
+    g.sync();
+    if (over > 0.f || carry) {
+        for (int c = g.lane; c < CC; c += g.n) softclip_mem[c] = ob_soft_clip_channel(x + c, n, CC, softclip_mem[c]);
+        g.sync();
+    }
+    for (int t = g.lane; t < n * CC; t += g.n) {
+        float v = x[t] * 32768.f;
+        v = fminf(32767.f, fmaxf(-32768.f, v));
+        out[t] = (int16_t)OB_F2I_RN(v);
+    }
+    g.sync();
 }
 
 // Decodes frame `ir` (already reconstructed normalised spectrum Xg: C*N floats in global memory) into pcm

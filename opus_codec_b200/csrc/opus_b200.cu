@@ -112,8 +112,8 @@ ob_k_bands(const ObFrameIR *__restrict__ ir, const int32_t *__restrict__ nslots,
 __global__ void __launch_bounds__(OB_SYNTH_THREADS, 7)
 ob_k_synth(const ObFrameIR *__restrict__ ir, const ObSlot *__restrict__ slots, const int32_t *__restrict__ nslots, const float *__restrict__ Xg,
            ObDecState *__restrict__ st, float *__restrict__ hist, float *__restrict__ ring,
-           float *__restrict__ pcm, int32_t *__restrict__ samples, uint32_t *__restrict__ ranges, int S, int F, int cap, int CC, int frame_size,
-           int f0, int Fc, float decode_gain)
+           float *__restrict__ pcm, int16_t *__restrict__ pcm16, int32_t *__restrict__ samples, uint32_t *__restrict__ ranges, int S, int F, int cap,
+           int CC, int frame_size, int f0, int Fc, float decode_gain)
 {
     __shared__ ObSynthShared sh;
     const int s = blockIdx.x;
@@ -137,6 +137,7 @@ ob_k_synth(const ObFrameIR *__restrict__ ir, const ObSlot *__restrict__ slots, c
         sh.preemph_mem[0] = state->preemph_mem[0]; sh.preemph_mem[1] = state->preemph_mem[1];
         sh.last_pitch_index = state->last_pitch_index; sh.paf = state->prefilter_and_fold;
         sh.ring_pos = state->ring_pos; sh.ring = ring + (size_t)s * CC * OB_RING; sh.decode_gain = decode_gain;
+        sh.softclip_mem[0] = state->softclip_mem[0]; sh.softclip_mem[1] = state->softclip_mem[1];
     }
     for (int i = g.lane; i < 2 * 24; i += g.n) sh.lpc[i / 24][i % 24] = state->lpc[i / 24][i % 24];
     uint32_t final_range = state->final_range;
@@ -158,6 +159,10 @@ ob_k_synth(const ObFrameIR *__restrict__ ir, const ObSlot *__restrict__ slots, c
         if (sl.flags & OB_SLOT_LAST) {
             if (acc > 0) last_dur = acc;
             if (g.lane == 0) { samples[pk] = acc; if (ranges) ranges[pk] = final_range; }
+            if (acc > 0) {                                          // opus_decoder.c:803-807: soft clip for the int16 API, else forget its state
+                if (pcm16) ob_packet_to_int16(g, pcm + pk * (size_t)frame_size * CC, pcm16 + pk * (size_t)frame_size * CC, acc, CC, sh.softclip_mem);
+                else if (g.lane == 0) sh.softclip_mem[0] = sh.softclip_mem[1] = 0.f;
+            }
         }
         g.sync();
     }
@@ -178,6 +183,7 @@ ob_k_synth(const ObFrameIR *__restrict__ ir, const ObSlot *__restrict__ slots, c
         state->final_range = final_range; state->last_packet_duration = last_dur;
         state->last_pitch_index = sh.last_pitch_index; state->prefilter_and_fold = sh.paf; state->ring_pos = sh.ring_pos;
         state->pkt_samples = acc;
+        state->softclip_mem[0] = sh.softclip_mem[0]; state->softclip_mem[1] = sh.softclip_mem[1];
     }
     for (int i = g.lane; i < 2 * 24; i += g.n) state->lpc[i / 24][i % 24] = sh.lpc[i / 24][i % 24];
 }
@@ -224,6 +230,7 @@ struct ObDecoder {
     ObDecState *d_state;
     float *d_hist, *d_ring;
     ObSlot *d_slots; int32_t *d_nslots;   // [S][max_frames] frame slots of the current call, [S] their counts
+    int16_t *d_pcm16_2[2], *cur_pcm16;    // int16 API: device-side int16 output (per buffer pair), the one of the call being enqueued
     int32_t *d_multi, *h_multi;           // "some packet is not one slot": a word of mapped pinned host memory (host pointer, device alias)
     cudaEvent_t framed;
     ObFrameIR *d_ir;
@@ -276,7 +283,8 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
         ob_k_bands<<<(total + OB_BANDS_WARPS - 1) / OB_BANDS_WARPS, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, stream>>>(
             ir, nslots, X, Sc, cap, f0, Fc);
         if (timed) OB_CUDA(cudaEventRecord(d->ev[2], stream));
-        ob_k_synth<<<Sc, OB_SYNTH_THREADS, 0, stream>>>(ir, slots, nslots, X, st, hist, ring, d_pcm + w0 * (size_t)frame_size * d->CC, d_samples + w0,
+        ob_k_synth<<<Sc, OB_SYNTH_THREADS, 0, stream>>>(ir, slots, nslots, X, st, hist, ring, d_pcm + w0 * (size_t)frame_size * d->CC,
+                                                         d->cur_pcm16 ? d->cur_pcm16 + w0 * (size_t)frame_size * d->CC : nullptr, d_samples + w0,
                                                          d_ranges ? d_ranges + w0 : nullptr, Sc, F, cap, d->CC, frame_size, f0, Fc, d->gain_linear);
         d->launches += 3;
     }
@@ -356,7 +364,7 @@ void ob_decoder_destroy(ObDecoder *d)
     if (d->stream) cudaStreamSynchronize(d->stream);
     cudaFree(d->d_state); cudaFree(d->d_hist); cudaFree(d->d_ring); cudaFree(d->d_slots); cudaFree(d->d_nslots); if (d->h_multi) cudaFreeHost(d->h_multi); if (d->framed) cudaEventDestroy(d->framed); cudaFree(d->d_ir); cudaFree(d->d_X); cudaFree(d->d_packets);
     cudaFree(d->d_offsets); cudaFree(d->d_lens); cudaFree(d->d_gather);
-    for (int p = 0; p < 2; p++) { cudaFree(d->d_samples2[p]); cudaFree(d->d_ranges2[p]); cudaFree(d->d_pcm2[p]); if (d->out_done[p]) cudaEventDestroy(d->out_done[p]); }
+    for (int p = 0; p < 2; p++) { cudaFree(d->d_samples2[p]); cudaFree(d->d_ranges2[p]); cudaFree(d->d_pcm2[p]); cudaFree(d->d_pcm16_2[p]); if (d->out_done[p]) cudaEventDestroy(d->out_done[p]); }
     if (d->aux_done) cudaEventDestroy(d->aux_done);
     for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     for (int i = 0; i < OB_MAX_CHUNKS; i++) if (d->chunk_ev[i]) cudaEventDestroy(d->chunk_ev[i]);
@@ -394,6 +402,7 @@ int32_t ob_decode_float_device(ObDecoder *d, int32_t n_frames, const uint8_t *d_
     if (!d || !d_packets || !d_offsets || !d_lens || !d_pcm_out || !d_samples_out) return OB_BAD_ARG;
     if (n_frames <= 0 || n_frames > d->max_frames || frame_size <= 0) return OB_BAD_ARG;
     OB_CUDA(cudaSetDevice(d->device));
+    d->cur_pcm16 = nullptr;
     const int r = ob_launch(d, 0, d->S, n_frames, d_packets, d_offsets, d_lens, d_pcm_out, frame_size, d_samples_out, d_ranges_out, 1, d->stream);
     if (r != OB_OK) return r;
     if (sync) OB_CUDA(cudaStreamSynchronize(d->stream));
@@ -404,9 +413,9 @@ int32_t ob_decode_float_device(ObDecoder *d, int32_t n_frames, const uint8_t *d_
 // the caller's buffers.  wait == 0: returns as soon as everything is enqueued (ob_decoder_wait completes it); the next call's
 // kernels then overlap this call's device->host copies, which is why the device-side output buffers alternate between calls.
 static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *packets, const int32_t *offsets, const int32_t *lens,
-                                float *pcm_out, int32_t frame_size, int32_t *samples_out, uint32_t *ranges_out, int wait)
+                                float *pcm_out, int16_t *pcm16_out, int32_t frame_size, int32_t *samples_out, uint32_t *ranges_out, int wait)
 {
-    if (!d || !packets || !offsets || !lens || !pcm_out || !samples_out) return OB_BAD_ARG;
+    if (!d || !packets || !offsets || !lens || (!pcm_out && !pcm16_out) || !samples_out) return OB_BAD_ARG;
     if (n_frames <= 0 || n_frames > d->max_frames || frame_size <= 0) return OB_BAD_ARG;
     OB_CUDA(cudaSetDevice(d->device));
     const size_t total = (size_t)d->S * n_frames;
@@ -430,8 +439,15 @@ static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *p
         OB_CUDA(cudaEventSynchronize(d->out_done[par]));
         cudaFree(d->d_pcm2[par]); d->d_pcm2[par] = nullptr; d->pcm_cap2[par] = 0;
         OB_CUDA(cudaMalloc(&d->d_pcm2[par], pcm_floats * sizeof(float)));
+        cudaFree(d->d_pcm16_2[par]); d->d_pcm16_2[par] = nullptr;
+        OB_CUDA(cudaMalloc(&d->d_pcm16_2[par], pcm_floats * sizeof(int16_t)));
         d->pcm_cap2[par] = pcm_floats;
     }
+    d->cur_pcm16 = pcm16_out ? d->d_pcm16_2[par] : nullptr;
+    // what travels back to the host: the float PCM, or -- int16 API -- the soft-clipped, rounded int16 PCM (half the bytes)
+    const size_t es = pcm16_out ? sizeof(int16_t) : sizeof(float);
+    const char *const d_out = pcm16_out ? (const char *)d->d_pcm16_2[par] : (const char *)d->d_pcm2[par];
+    char *const h_out = pcm16_out ? (char *)pcm16_out : (char *)pcm_out;
     float *const d_pcm = d->d_pcm2[par];
     int32_t *const d_samples = d->d_samples2[par];
     uint32_t *const d_ranges = d->d_ranges2[par];
@@ -467,7 +483,7 @@ static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *p
         if (r != OB_OK) return r;
         OB_CUDA(cudaEventRecord(d->chunk_ev[0], d->stream));
         OB_CUDA(cudaStreamWaitEvent(d->copy_stream, d->chunk_ev[0], 0));
-        OB_CUDA(cudaMemcpyAsync(pcm_out, d_pcm, pcm_floats * sizeof(float), cudaMemcpyDeviceToHost, d->copy_stream));
+        OB_CUDA(cudaMemcpyAsync(h_out, d_out, pcm_floats * es, cudaMemcpyDeviceToHost, d->copy_stream));
         OB_CUDA(cudaMemcpyAsync(samples_out, d_samples, total * sizeof(int32_t), cudaMemcpyDeviceToHost, d->copy_stream));
         if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out, d_ranges, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->copy_stream));
     } else if (n_frames >= nchunks) {
@@ -480,8 +496,8 @@ static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *p
             if (r != OB_OK) return r;
             OB_CUDA(cudaEventRecord(d->chunk_ev[k], d->stream));
             OB_CUDA(cudaStreamWaitEvent(d->copy_stream, d->chunk_ev[k], 0));
-            OB_CUDA(cudaMemcpy2DAsync(pcm_out + f0 * pf, n_frames * pf * sizeof(float), d_pcm + f0 * pf, n_frames * pf * sizeof(float),
-                                      Fc * pf * sizeof(float), d->S, cudaMemcpyDeviceToHost, d->copy_stream));
+            OB_CUDA(cudaMemcpy2DAsync(h_out + f0 * pf * es, n_frames * pf * es, d_out + f0 * pf * es, n_frames * pf * es,
+                                      Fc * pf * es, d->S, cudaMemcpyDeviceToHost, d->copy_stream));
         }
         OB_CUDA(cudaMemcpyAsync(samples_out, d_samples, total * sizeof(int32_t), cudaMemcpyDeviceToHost, d->copy_stream));
         if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out, d_ranges, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->copy_stream));
@@ -497,7 +513,7 @@ static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *p
             if (r != OB_OK) return r;
             OB_CUDA(cudaEventRecord(d->chunk_ev[k], cs));
             OB_CUDA(cudaStreamWaitEvent(d->copy_stream, d->chunk_ev[k], 0));
-            OB_CUDA(cudaMemcpyAsync(pcm_out + w0 * pf, d_pcm + w0 * pf, cnt * pf * sizeof(float), cudaMemcpyDeviceToHost, d->copy_stream));
+            OB_CUDA(cudaMemcpyAsync(h_out + w0 * pf * es, d_out + w0 * pf * es, cnt * pf * es, cudaMemcpyDeviceToHost, d->copy_stream));
             OB_CUDA(cudaMemcpyAsync(samples_out + w0, d_samples + w0, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, d->copy_stream));
             if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out + w0, d_ranges + w0, cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->copy_stream));
         }
@@ -511,13 +527,24 @@ static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *p
 int32_t ob_decode_float_multi(ObDecoder *d, int32_t n_frames, const uint8_t *packets, const int32_t *offsets, const int32_t *lens,
                               float *pcm_out, int32_t frame_size, int32_t *samples_out, uint32_t *ranges_out)
 {
-    return ob_decode_submit(d, n_frames, packets, offsets, lens, pcm_out, frame_size, samples_out, ranges_out, 1);
+    return ob_decode_submit(d, n_frames, packets, offsets, lens, pcm_out, nullptr, frame_size, samples_out, ranges_out, 1);
+}
+
+// opus_decode (int16 PCM): Decoder::decode (src/decoder.rs:75-127).
+int32_t ob_decode_multi(ObDecoder *d, int32_t n_frames, const uint8_t *packets, const int32_t *offsets, const int32_t *lens,
+                        int16_t *pcm_out, int32_t frame_size, int32_t *samples_out, uint32_t *ranges_out)
+{
+    return ob_decode_submit(d, n_frames, packets, offsets, lens, nullptr, pcm_out, frame_size, samples_out, ranges_out, 1);
+}
+int32_t ob_decode(ObDecoder *d, const uint8_t *packets, const int32_t *offsets, const int32_t *lens, int16_t *pcm_out, int32_t frame_size, int32_t *samples_out)
+{
+    return ob_decode_submit(d, 1, packets, offsets, lens, nullptr, pcm_out, frame_size, samples_out, nullptr, 1);
 }
 
 int32_t ob_decode_float_multi_async(ObDecoder *d, int32_t n_frames, const uint8_t *packets, const int32_t *offsets, const int32_t *lens,
                                     float *pcm_out, int32_t frame_size, int32_t *samples_out, uint32_t *ranges_out)
 {
-    return ob_decode_submit(d, n_frames, packets, offsets, lens, pcm_out, frame_size, samples_out, ranges_out, 0);
+    return ob_decode_submit(d, n_frames, packets, offsets, lens, pcm_out, nullptr, frame_size, samples_out, ranges_out, 0);
 }
 
 int32_t ob_decoder_wait(ObDecoder *d, int32_t keep_in_flight)
@@ -607,7 +634,7 @@ int32_t ob_packet_get_nb_frames(const uint8_t *p, int32_t len)
     return p[1] & 0x3F;
 }
 
-const char *ob_version(void) { return "1.5.2-b200.4"; }
+const char *ob_version(void) { return "1.5.2-b200.5"; }
 const char *ob_strerror(int32_t e)
 {
     static const char *const s[8] = {"success", "invalid argument", "buffer too small", "internal error", "corrupted stream",

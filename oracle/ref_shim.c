@@ -204,6 +204,27 @@ REF_EXPORT int ref_decode_stream(const unsigned char *pkts, const int *lens, int
     return 0;
 }
 
+/* Same through the int16 API (opus_decode: float decode + opus_pcm_soft_clip + FLOAT2INT16). */
+REF_EXPORT int ref_decode_stream_i16(const unsigned char *pkts, const int *lens, int stride, int nframes, int frame_size,
+        int dec_channels, opus_int16 *pcm_out, uint32_t *ranges, int *samples)
+{
+    int f, err = 0;
+    OpusDecoder *d = opus_decoder_create(48000, dec_channels, &err);
+    if (!d || err != OPUS_OK) return OPUS_ALLOC_FAIL;
+    if (g_dec_gain) opus_decoder_ctl(d, OPUS_SET_GAIN(g_dec_gain));
+    if (g_dec_phase_inv_disabled) opus_decoder_ctl(d, OPUS_SET_PHASE_INVERSION_DISABLED(1));
+    for (f = 0; f < nframes; f++) {
+        opus_uint32 rng = 0;
+        int n = opus_decode(d, lens[f] > 0 ? pkts + (size_t)f * stride : NULL, lens[f],
+                pcm_out + (size_t)f * frame_size * dec_channels, frame_size, 0);
+        if (samples) samples[f] = n;
+        opus_decoder_ctl(d, OPUS_GET_FINAL_RANGE(&rng));
+        if (ranges) ranges[f] = rng;
+    }
+    opus_decoder_destroy(d);
+    return 0;
+}
+
 /* Decode ONE packet with a fresh decoder (used for stateless final-range checks). */
 REF_EXPORT int ref_decode_packet_fresh(const unsigned char *pkt, int len, int frame_size, int dec_channels,
         float *pcm_out, uint32_t *range)

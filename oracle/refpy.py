@@ -158,6 +158,31 @@ def decode_stream(pkts, lens, frame_size, channels, want_taps=False, pure_c=Fals
     return (pcm, rng, smp, taps) if want_taps else (pcm, rng, smp)
 
 
+def decode_stream_i16(pkts, lens, frame_size, channels, gain_q8=0, pure_c=False):
+    """opus_decode (int16 API): (pcm i16 [nframes, frame_size*channels], ranges, samples)."""
+    pkts = np.ascontiguousarray(pkts, np.uint8)
+    lens = np.ascontiguousarray(lens, np.int32)
+    nframes, stride = pkts.shape
+    pcm = np.zeros((nframes, frame_size * channels), np.int16)
+    rng = np.zeros(nframes, np.uint32)
+    smp = np.zeros(nframes, np.int32)
+    L = lib_c() if pure_c else lib()
+    L.ref_set_decoder_extras(int(gain_q8), 0)
+    try:
+        r = L.ref_decode_stream_i16(_p(pkts, C.c_ubyte), _p(lens, C.c_int), stride, nframes, frame_size, channels,
+                                    _p(pcm, C.c_int16), _p(rng, C.c_uint32), _p(smp, C.c_int))
+    finally:
+        L.ref_set_decoder_extras(0, 0)
+    if r != 0:
+        raise RuntimeError("ref_decode_stream_i16: opus error %d" % r)
+    return pcm, rng, smp
+
+
+def soft_clip(x, channels, mem):
+    """opus_pcm_soft_clip on interleaved float32 x (in place); mem: float32[channels] carried state."""
+    lib().opus_pcm_soft_clip(_p(x, C.c_float), x.size // channels, channels, _p(mem, C.c_float))
+
+
 def decode_pool(pkts, lens, frame_size, channels, nthreads, want_pcm=False, want_ranges=False):
     """pkts u8 [nstreams, nframes, stride]; returns (seconds, pcm|None, ranges|None)."""
     pkts = np.ascontiguousarray(pkts, np.uint8)

@@ -75,6 +75,15 @@ int emul_decode_stream(const uint8_t *pkts, const int *lens, int stride, int nfr
 }
 }
 
+extern "C" {
+// the int16 back end of the synthesis kernel: soft clip over one packet + rounding, one emulated lane
+void emul_packet_to_int16(float *x, int16_t *out, int n, int channels, float *softclip_mem)
+{
+    ObSolo g;
+    ob_packet_to_int16(g, x, out, n, channels, softclip_mem);
+}
+}
+
 // ---- encoder -------------------------------------------------------------------------------------------------------------
 #include "../../opus_codec_b200/csrc/enc_frame.cuh"
 extern "C" {

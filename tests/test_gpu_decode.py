@@ -308,6 +308,38 @@ def test_multiframe_packets(have_ref, name):
                 assert np.abs(pcm[s, f, :rs[f] * dc] - ref[f, :rs[f] * dc]).max() <= tol, (s, f)
 
 
+def test_int16_api_soft_clip_matches_reference(have_ref):
+    """ob_decode_multi (Decoder::decode): with +12 dB of decode gain the signal clips, so the soft clipper and its packet-to-packet
+    state are exercised; int16 PCM must equal the reference's up to rounding flips: the float paths differ by up to ~0.2 LSB after
+    the gain, so a +-1 on under 2 % of the samples is tolerated (the clipper and the rounding themselves are bit-exact against the
+    reference in tests/test_host_emul.py)."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    from opus_codec_b200.batch import BatchDecoder
+    for name, q8 in (("cfg1_stereo_20ms_128k_cbr", 3072), ("cfg2_mono_20ms_64k_cbr", 0), ("cfg4_stereo_5ms_96k", 3328)):
+        g = load_golden(name)
+        fs, dc = g["frame_size"], g["dec_channels"]
+        S, F, stride = g["packets"].shape
+        S, F = min(S, 3), min(F, 40)
+        pk = np.ascontiguousarray(g["packets"][:S, :F]); ln = g["lens"][:S, :F]
+        with BatchDecoder(S, 48000, dc, device=0, max_frames=F) as dec:
+            dec.set_gain(q8)
+            pcm, samples, ranges = dec.decode_multi(pk.reshape(-1), _offsets(S, F, stride), ln, fs)
+            assert pcm.dtype == np.int16
+            clipped = 0
+            for s in range(S):
+                ref, rr, rs = refpy.decode_stream_i16(pk[s], ln[s], fs, dc, gain_q8=q8)
+                assert (samples[s] == rs).all() and (ranges[s] == rr).all()
+                d = np.abs(pcm[s].astype(np.int32) - ref.astype(np.int32))
+                assert d.max() <= 1 and (d != 0).mean() < 2e-2, (name, int(d.max()), float((d != 0).mean()))
+                clipped += int((np.abs(ref.astype(np.int32)) >= 32000).sum())
+            assert q8 == 0 or clipped > 100          # the gain really drove the signal into the clipper
+            # and the float API afterwards forgets the clipper state (opus_decoder.c:806)
+            f32, _, _ = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, fs)
+            assert np.isfinite(f32).all()
+
+
 def test_reset_restarts_streams():
     from opus_codec_b200.batch import BatchDecoder
     g = load_golden("cfg2_mono_20ms_64k_cbr")

@@ -80,6 +80,29 @@ def test_multiframe_packets_device_code_matches_reference(emul, have_ref, name):
         assert np.abs(pcm[f, :rs[f] * dc] - ref[f, :rs[f] * dc]).max() <= 1e-6
 
 
+def test_soft_clip_and_int16_rounding_match_reference(emul, have_ref):
+    """The int16 back end (opus_pcm_soft_clip with its packet-to-packet gain + FLOAT2INT16) on signals that clip in every way the
+    reference distinguishes: before the first zero crossing, across packet boundaries, beyond +-2, not at all."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    rng = np.random.default_rng(5)
+    for ch in (1, 2):
+        mem_ref = np.zeros(ch, np.float32); mem = np.zeros(2, np.float32)
+        for k in range(60):
+            n = int(rng.choice([120, 240, 480, 960, 2880]))
+            t = np.arange(n)[:, None]
+            amp = rng.choice([0.3, 0.9, 1.05, 1.4, 2.6]) * (1 + 0.3 * rng.random((1, ch)))
+            x = (amp * np.sin(2 * np.pi * (rng.integers(1, 40) / n) * t + rng.random((1, ch)) * 6.28) + 0.05 * rng.standard_normal((n, ch))).astype(np.float32)
+            a = np.ascontiguousarray(x.reshape(-1)); b = a.copy()
+            refpy.soft_clip(a, ch, mem_ref)
+            want = np.clip(np.rint(np.clip(a * np.float32(32768), -32768, 32767)), -32768, 32767).astype(np.int16)
+            out = np.zeros(n * ch, np.int16)
+            emul.emul_packet_to_int16(P(b, C.c_float), P(out, C.c_int16), n, ch, P(mem, C.c_float))
+            assert np.array_equal(a, b), (ch, k)
+            assert np.array_equal(out, want) and np.array_equal(mem[:ch], mem_ref)
+
+
 def _fuzz_streams(seed, trials, nf=10, with_loss=True):
     """Random (garbage) payloads behind valid CELT TOCs, optionally with lost packets and DTX payloads in between."""
     rng = np.random.default_rng(seed)
