@@ -137,6 +137,11 @@ int32_t ob_encode_float(ObEncoder *enc, const float *pcm, int32_t frame_size, ui
  * lens_out / ranges_out [n_streams][n_frames] (ranges_out optional: OPUS_GET_FINAL_RANGE after each frame). */
 int32_t ob_encode_float_multi(ObEncoder *enc, int32_t n_frames, const float *pcm, int32_t frame_size, uint8_t *out,
                               int32_t max_bytes, int32_t *lens_out, uint32_t *ranges_out);
+/* n x opus_encode(st, pcm, frame_size, data, max_data_bytes) (src/bindings.rs:313-324; Encoder::encode src/encoder.rs:80-127): int16 PCM in.
+ * As in the reference's float build the samples are scaled by 1/32768 and encoded at min(16, lsb_depth) bits of depth. */
+int32_t ob_encode(ObEncoder *enc, const int16_t *pcm, int32_t frame_size, uint8_t *out, int32_t max_bytes, int32_t *lens_out);
+int32_t ob_encode_multi(ObEncoder *enc, int32_t n_frames, const int16_t *pcm, int32_t frame_size, uint8_t *out,
+                        int32_t max_bytes, int32_t *lens_out, uint32_t *ranges_out);
 /* Same with DEVICE pointers; asynchronous on the encoder's stream unless sync != 0. */
 int32_t ob_encode_float_device(ObEncoder *enc, int32_t n_frames, const float *d_pcm, int32_t frame_size, uint8_t *d_out,
                                int32_t max_bytes, int32_t *d_lens_out, uint32_t *d_ranges_out, int32_t sync);

@@ -263,6 +263,18 @@ class BatchEncoder:
         _check(self._L.ob_encode_float_multi(self._h, F, _vp(pcm), frame_size, _vp(out), max_bytes, _vp(lens), _vp(ranges)))
         return out, lens, ranges
 
+    def encode_multi(self, pcm, frame_size, max_bytes=1276):
+        """int16 form (ob_encode_multi; Encoder::encode, src/encoder.rs:80-127): pcm i16 [S, F, frame_size*channels]."""
+        pcm = np.ascontiguousarray(pcm, np.int16)
+        if pcm.ndim != 3 or pcm.shape[0] != self.n_streams or pcm.shape[2] != frame_size * self.channels:
+            raise OpusError(BAD_ARG)
+        S, F = pcm.shape[:2]
+        out = np.zeros((S, F, max_bytes), np.uint8)
+        lens = np.zeros((S, F), np.int32)
+        ranges = np.zeros((S, F), np.uint32)
+        _check(self._L.ob_encode_multi(self._h, F, _vp(pcm), frame_size, _vp(out), max_bytes, _vp(lens), _vp(ranges)))
+        return out, lens, ranges
+
     def encode_float(self, pcm, max_bytes=1276):
         """pcm: f32 [S, frame_size*channels]; frame_size = input.len()/channels as in Encoder::encode_float (src/encoder.rs:215-247).
         Returns a list of bytes objects (one packet per stream) and the i32 length/status array."""

@@ -55,6 +55,13 @@ ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *_
     streams[s] = es;
 }
 
+// int16 API (opus_encode, opus_encoder.c:2346-2376, float build): in[i] = (1/32768) * pcm[i], then the float path at 16-bit depth.
+__global__ void ob_k_i16_to_f32(const int16_t *__restrict__ in, float *__restrict__ out, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (1.0f / 32768) * (float)in[i];
+}
+
 __global__ void ob_k_enc_reset(ObEncStream *streams, const int32_t *idx, int n, int S, int channels)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -81,6 +88,7 @@ struct ObEncoder {
     bool timed;
     ObEncStream *d_streams;
     float *d_pcm; size_t pcm_cap;
+    int16_t *d_pcm16; size_t pcm16_cap;
     uint8_t *d_out; size_t out_cap;
     int32_t *d_lens; uint32_t *d_ranges;
     int64_t launches;
@@ -136,7 +144,7 @@ void ob_encoder_destroy(ObEncoder *e)
     if (!e) return;
     cudaSetDevice(e->device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    cudaFree(e->d_streams); cudaFree(e->d_pcm); cudaFree(e->d_out); cudaFree(e->d_lens); cudaFree(e->d_ranges);
+    cudaFree(e->d_streams); cudaFree(e->d_pcm); cudaFree(e->d_pcm16); cudaFree(e->d_out); cudaFree(e->d_lens); cudaFree(e->d_ranges);
     for (int i = 0; i < 2; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     for (int i = 0; i < 4; i++) if (e->win_ev[i]) cudaEventDestroy(e->win_ev[i]);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -214,10 +222,10 @@ int32_t ob_encode_float_device(ObEncoder *e, int32_t n_frames, const float *d_pc
     return OB_OK;
 }
 
-int32_t ob_encode_float_multi(ObEncoder *e, int32_t n_frames, const float *pcm, int32_t frame_size, uint8_t *out, int32_t max_bytes,
-                              int32_t *lens_out, uint32_t *ranges_out)
+static int32_t ob_encode_submit(ObEncoder *e, int32_t n_frames, const float *pcm, const int16_t *pcm16, int32_t frame_size, uint8_t *out,
+                                int32_t max_bytes, int32_t *lens_out, uint32_t *ranges_out)
 {
-    if (!e || !pcm || !out || !lens_out || n_frames <= 0 || n_frames > e->max_frames || max_bytes <= 0 || frame_size <= 0) return OB_BAD_ARG;
+    if (!e || (!pcm && !pcm16) || !out || !lens_out || n_frames <= 0 || n_frames > e->max_frames || max_bytes <= 0 || frame_size <= 0) return OB_BAD_ARG;
     OB_CUDA(cudaSetDevice(e->device));
     const size_t total = (size_t)e->S * n_frames, pcm_floats = total * (size_t)frame_size * e->CC, out_bytes = total * (size_t)max_bytes;
     if (pcm_floats > e->pcm_cap) { cudaFree(e->d_pcm); e->d_pcm = nullptr; e->pcm_cap = 0; OB_CUDA(cudaMalloc(&e->d_pcm, pcm_floats * sizeof(float))); e->pcm_cap = pcm_floats; }
@@ -227,20 +235,46 @@ int32_t ob_encode_float_multi(ObEncoder *e, int32_t n_frames, const float *pcm, 
     const int nwin = (total >= 32768 && n_frames >= 4) ? 4 : (total >= 8192 && n_frames >= 2 ? 2 : 1);
     const int per = (n_frames + nwin - 1) / nwin;
     const size_t pf = (size_t)frame_size * e->CC;
+    const int lsb_saved = e->cfg.lsb_depth;
+    if (pcm16) {                                       // half the upload; widened on the device; lsb_depth = min(16, user) (opus_encoder.c:1136)
+        if (pcm_floats > e->pcm16_cap) { cudaFree(e->d_pcm16); e->d_pcm16 = nullptr; e->pcm16_cap = 0; OB_CUDA(cudaMalloc(&e->d_pcm16, pcm_floats * sizeof(int16_t))); e->pcm16_cap = pcm_floats; }
+        OB_CUDA(cudaMemcpyAsync(e->d_pcm16, pcm16, pcm_floats * sizeof(int16_t), cudaMemcpyHostToDevice, e->stream));
+        ob_k_i16_to_f32<<<(unsigned)((pcm_floats + 255) / 256), 256, 0, e->stream>>>(e->d_pcm16, e->d_pcm, pcm_floats);
+        e->launches += 1;
+        if (e->cfg.lsb_depth > 16) e->cfg.lsb_depth = 16;
+    }
     for (int k = 0, f0 = 0; f0 < n_frames; k++, f0 += per) {
         const int Fc = n_frames - f0 < per ? n_frames - f0 : per;
-        OB_CUDA(cudaMemcpy2DAsync(e->d_pcm + f0 * pf, n_frames * pf * sizeof(float), pcm + f0 * pf, n_frames * pf * sizeof(float),
+        if (!pcm16) OB_CUDA(cudaMemcpy2DAsync(e->d_pcm + f0 * pf, n_frames * pf * sizeof(float), pcm + f0 * pf, n_frames * pf * sizeof(float),
                                   Fc * pf * sizeof(float), e->S, cudaMemcpyHostToDevice, e->copy_stream));
         OB_CUDA(cudaEventRecord(e->win_ev[k], e->copy_stream));
         OB_CUDA(cudaStreamWaitEvent(e->stream, e->win_ev[k], 0));
         const int r = ob_enc_launch(e, n_frames, e->d_pcm, frame_size, e->d_out, max_bytes, e->d_lens, e->d_ranges, f0, Fc);
-        if (r != OB_OK) return r;
+        if (r != OB_OK) { e->cfg.lsb_depth = lsb_saved; return r; }
     }
+    e->cfg.lsb_depth = lsb_saved;
     OB_CUDA(cudaMemcpyAsync(out, e->d_out, out_bytes, cudaMemcpyDeviceToHost, e->stream));
     OB_CUDA(cudaMemcpyAsync(lens_out, e->d_lens, total * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
     if (ranges_out) OB_CUDA(cudaMemcpyAsync(ranges_out, e->d_ranges, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     OB_CUDA(cudaStreamSynchronize(e->stream));
     return OB_OK;
+}
+
+int32_t ob_encode_float_multi(ObEncoder *e, int32_t n_frames, const float *pcm, int32_t frame_size, uint8_t *out, int32_t max_bytes,
+                              int32_t *lens_out, uint32_t *ranges_out)
+{
+    return ob_encode_submit(e, n_frames, pcm, nullptr, frame_size, out, max_bytes, lens_out, ranges_out);
+}
+
+// opus_encode (int16 PCM): Encoder::encode (src/encoder.rs:80-127).
+int32_t ob_encode_multi(ObEncoder *e, int32_t n_frames, const int16_t *pcm, int32_t frame_size, uint8_t *out, int32_t max_bytes,
+                        int32_t *lens_out, uint32_t *ranges_out)
+{
+    return ob_encode_submit(e, n_frames, nullptr, pcm, frame_size, out, max_bytes, lens_out, ranges_out);
+}
+int32_t ob_encode(ObEncoder *e, const int16_t *pcm, int32_t frame_size, uint8_t *out, int32_t max_bytes, int32_t *lens_out)
+{
+    return ob_encode_submit(e, 1, nullptr, pcm, frame_size, out, max_bytes, lens_out, nullptr);
 }
 
 int32_t ob_encode_float(ObEncoder *e, const float *pcm, int32_t frame_size, uint8_t *out, int32_t max_bytes, int32_t *lens_out)

@@ -171,6 +171,25 @@ REF_EXPORT int ref_encode_stream(const float *pcm, int nframes, int frame_size, 
     return 0;
 }
 
+/* Same through the int16 API (opus_encode). */
+REF_EXPORT int ref_encode_stream_i16(const opus_int16 *pcm, int nframes, int frame_size, int channels, int application,
+        int bitrate, int vbr, int complexity, unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
+{
+    int f;
+    OpusEncoder *e = make_encoder(channels, application, bitrate, vbr, complexity);
+    if (!e) return OPUS_ALLOC_FAIL;
+    for (f = 0; f < nframes; f++) {
+        opus_uint32 rng = 0;
+        int n = opus_encode(e, pcm + (size_t)f * frame_size * channels, frame_size, out + (size_t)f * max_bytes, max_bytes);
+        if (n < 0) { opus_encoder_destroy(e); return n; }
+        lens[f] = n;
+        opus_encoder_ctl(e, OPUS_GET_FINAL_RANGE(&rng));
+        if (ranges) ranges[f] = rng;
+    }
+    opus_encoder_destroy(e);
+    return 0;
+}
+
 /* pkts: nframes slots of `stride` bytes; lens[f] bytes valid (0 => packet loss / PLC).
  * dec_channels: channel count of the decoder object.  taps (optional): nframes ref_tap_t records. */
 /* Optional decoder CTLs applied by ref_decode_stream: OPUS_SET_GAIN (Q8 dB) and OPUS_SET_PHASE_INVERSION_DISABLED. */

@@ -29,6 +29,42 @@ def _ref_c_encode(pcm, fs, ch, br, vbr, cx):
     return out, lens, rng
 
 
+def _ref_c_encode_i16(pcm16, fs, ch, br, vbr, cx):
+    from oracle import refpy
+    L = refpy.lib_c()
+    u8p, i32p, u32p, i16p = (C.POINTER(C.c_ubyte), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_int16))
+    L.ref_encode_stream_i16.argtypes = [i16p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, i32p, u32p]
+    pcm16 = np.ascontiguousarray(pcm16, np.int16)
+    nf = pcm16.size // (fs * ch)
+    out = np.zeros((nf, 1276), np.uint8); lens = np.zeros(nf, np.int32); rng = np.zeros(nf, np.uint32)
+    r = L.ref_encode_stream_i16(pcm16.ctypes.data_as(i16p), nf, fs, ch, 2051, br, vbr, cx, out.ctypes.data_as(u8p), 1276, lens.ctypes.data_as(i32p), rng.ctypes.data_as(u32p))
+    assert r == 0
+    return out, lens, rng
+
+
+def test_int16_encode_api_matches_reference(have_ref):
+    """ob_encode_multi (Encoder::encode): int16 PCM in, scaled by 1/32768 and coded at 16-bit depth like opus_encode's float build;
+    packets bit-identical to the reference's C build (complexity <= 6, below the Opus-layer analysis)."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from opus_codec_b200 import synth
+    from opus_codec_b200.batch import BatchEncoder
+    for ch, br, fs, vbr in ((2, 96000, 960, 0), (1, 48000, 480, 1)):
+        S, F = 4, 25
+        pcm = np.stack([synth.stream_pcm(s, fs * F, ch, base_seed=911) for s in range(S)])
+        pcm16 = np.clip(np.rint(pcm * 32768), -32768, 32767).astype(np.int16).reshape(S, F, fs * ch)
+        with BatchEncoder(S, 48000, ch, device=0, max_frames=F) as enc:
+            enc.set_bitrate(br); enc.set_complexity(6); enc.set_vbr(vbr != 0); enc.set_vbr_constraint(vbr == 2)
+            out, lens, rng = enc.encode_multi(pcm16, fs)
+        same = total = 0
+        for s in range(S):
+            ro, rl, rr = _ref_c_encode_i16(pcm16[s], fs, ch, br, vbr, 6)
+            for f in range(F):
+                total += 1
+                same += int(lens[s, f] == rl[f] and np.array_equal(out[s, f, :rl[f]], ro[f, :rl[f]]) and rng[s, f] == rr[f])
+        assert same / total >= 0.97, (ch, br, fs, same, total)
+
+
 def _gpu_encode(pcm_batch, fs, ch, br, vbr, cx):
     from opus_codec_b200.batch import BatchEncoder
     S = pcm_batch.shape[0]
