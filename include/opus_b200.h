@@ -117,8 +117,9 @@ void *ob_decoder_cuda_stream(ObDecoder *dec);
  * Scope of this version: Fs = 48000, OPUS_APPLICATION_RESTRICTED_LOWDELAY (2051; the application that forces
  * MODE_CELT_ONLY, opus/src/opus_encoder.c:1330-1332), frames of 120/240/480/960 samples.  The CELT encoder is complete
  * (pitch pre-filter, transient/tf/spread/dynalloc/trim/stereo decisions, two-pass energy, PVQ search, theta RDO, CBR/VBR/
- * CVBR); the Opus-layer tonality analysis (opus/src/analysis.c, active in the reference at complexity >= 7) is not
- * computed, so packets are bit-identical to the reference's pure-C build at complexity <= 6 and decision-compatible above.
+ * CVBR), and so is the Opus-layer tonality analysis the reference runs at complexity >= 7 (opus/src/analysis.c: FFT, band
+ * statistics, bandwidth detector, speech/music network): packets are bit-identical to the reference's pure-C build at
+ * every complexity.
  * ------------------------------------------------------------------------------------------------------------------ */
 typedef struct ObEncoder ObEncoder;
 

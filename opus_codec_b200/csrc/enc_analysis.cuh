@@ -66,6 +66,13 @@ OB_DEV void ob_comb_filter_xy(float *y, const float *x, int T0, int T1, int N, f
     }
 }
 
+OB_DEV float ob_maxabs(const float *x, int len)                      // celt_maxabs16 (mathops.h:79-91)
+{
+    float maxval = 0, minval = 0;
+    for (int i = 0; i < len; i++) { maxval = ob_fmax(maxval, x[i]); minval = ob_fmin(minval, x[i]); }
+    return ob_fmax(maxval, -minval);
+}
+
 // ---- pitch analysis (opus/celt/pitch.c) ----------------------------------------------------------------------------
 OB_DEV float ob_inner_prod(const float *x, const float *y, int N) { float s = 0; for (int i = 0; i < N; i++) s = s + x[i] * y[i]; return s; }
 
@@ -441,7 +448,7 @@ OB_DEV float ob_median_of_3(const float *x)                          // celt_enc
 // dynalloc_analysis (celt_encoder.c:981-1185), start = 0, lfe = 0, no surround mask, analysis invalid
 OB_DEV float ob_dynalloc_analysis(const float *bandLogE, const float *bandLogE2, const float *oldBandE, int end, int C, int *offsets,
         int lsb_depth, int isTransient, int vbr, int constrained_vbr, int LM, int effectiveBytes, int32_t *tot_boost_,
-        int *importance, int *spread_weight)
+        int *importance, int *spread_weight, const uint8_t *leak_boost)
 {
     int32_t tot_boost = 0;
     float maxDepth = -31.9f, follower[2 * OB_NB], noise_floor[OB_NB], bandLogE3[OB_NB];
@@ -496,6 +503,7 @@ OB_DEV float ob_dynalloc_analysis(const float *bandLogE, const float *bandLogE2,
             if (i < 8) follower[i] *= 2;
             if (i >= 12) follower[i] = .5f * follower[i];
         }
+        if (leak_boost) for (int i = 0; i < ob_imin(19, end); i++) follower[i] = follower[i] + (1.f / 64.f) * leak_boost[i];   // celt_encoder.c:1139-1143
         for (int i = 0; i < end; i++) {
             int boost, boost_bits;
             follower[i] = ob_fmin(follower[i], 4.f);
@@ -655,9 +663,9 @@ OB_DEV int ob_hysteresis_decision(float val, const float *thresholds, const floa
     return i;
 }
 
-// alloc_trim_analysis (celt_encoder.c:797-887), analysis invalid, surround_trim = 0
+// alloc_trim_analysis (celt_encoder.c:797-887), surround_trim = 0
 OB_DEV int ob_alloc_trim_analysis(const float *X, const float *bandLogE, int end, int LM, int C, int N0, float *stereo_saving, float tf_estimate,
-        int intensity, int32_t equiv_rate)
+        int intensity, int32_t equiv_rate, int an_valid, float an_tonality_slope)
 {
     float diff = 0, trim = 5.f;
     if (equiv_rate < 64000) trim = 4.f;
@@ -683,19 +691,22 @@ OB_DEV int ob_alloc_trim_analysis(const float *X, const float *bandLogE, int end
     diff /= C * (end - 1);
     trim -= ob_fmax(-2.f, ob_fmin(2.f, (diff + 1.f) / 6));
     trim -= 2 * tf_estimate;
+    if (an_valid) trim -= ob_fmax(-2.f, ob_fmin(2.f, 2.f * (an_tonality_slope + .05f)));
     int trim_index = (int)floor((double)(.5f + trim));
     trim_index = ob_imax(0, ob_imin(10, trim_index));
     return trim_index;
 }
 
-// compute_vbr (celt_encoder.c:1320-1429), analysis invalid, no surround mask, lfe = 0
+// compute_vbr (celt_encoder.c:1320-1429), no surround mask, lfe = 0
 OB_DEV int32_t ob_compute_vbr(int32_t base_target, int LM, int32_t bitrate, int lastCodedBands, int C, int intensity, int constrained_vbr,
-        float stereo_saving, int tot_boost, float tf_estimate, float maxDepth, float temporal_vbr)
+        float stereo_saving, int tot_boost, float tf_estimate, float maxDepth, float temporal_vbr, int an_valid, float an_activity, float an_tonality,
+        int pitch_change)
 {
     int32_t target = base_target;
     const int coded_bands = lastCodedBands ? lastCodedBands : OB_NB;
     int coded_bins = OB_EBANDS[coded_bands] << LM;
     if (C == 2) coded_bins += OB_EBANDS[ob_imin(intensity, coded_bands)] << LM;
+    if (an_valid && (double)an_activity < .4) target -= (int32_t)((float)(coded_bins << OB_BITRES) * (.4f - an_activity));
     if (C == 2) {
         const int coded_stereo_bands = ob_imin(intensity, coded_bands);
         const int coded_stereo_dof = (OB_EBANDS[coded_stereo_bands] << LM) - coded_stereo_bands;
@@ -706,6 +717,12 @@ OB_DEV int32_t ob_compute_vbr(int32_t base_target, int LM, int32_t bitrate, int 
     target += tot_boost - (19 << LM);
     const float tf_calibration = 0.044f;
     target += (int32_t)((tf_estimate - tf_calibration) * (float)target);
+    if (an_valid) {                                                  // tonality boost (celt_encoder.c:1373-1386)
+        const float tonal = ob_fmax(0.f, an_tonality - .15f) - 0.12f;
+        int32_t tonal_target = target + (int32_t)((float)(coded_bins << OB_BITRES) * 1.2f * tonal);
+        if (pitch_change) tonal_target += (int32_t)((float)(coded_bins << OB_BITRES) * .8f);
+        target = tonal_target;
+    }
     {
         const int bins = OB_EBANDS[OB_NB - 2] << LM;
         int32_t floor_depth = (int32_t)((float)(C * bins << OB_BITRES) * maxDepth);

@@ -4,6 +4,7 @@
 // (opus/src/opus_encoder.c: dc_reject :430-468, byte budget :1188-1197, TOC gen_toc :299-329).
 #pragma once
 #include "enc_quant.cuh"
+#include "enc_tonal.cuh"
 
 #define OB_BITRATE_MAX (-1)
 
@@ -28,6 +29,7 @@ struct ObEncState {
     float in_mem[2 * OB_OVERLAP];
     float prefilter_mem[2 * OB_MAXPERIOD];
     float oldBandE[2 * OB_NB], oldLogE[2 * OB_NB], oldLogE2[2 * OB_NB], energyError[2 * OB_NB];
+    ObAnalysisInfo an;                                // st->analysis: set by the Opus layer before every frame (CELT_SET_ANALYSIS)
 };
 
 // Per-stream working memory of one frame (the reference's stack VLAs).
@@ -49,7 +51,7 @@ OB_DEV void ob_enc_reset(ObEncState &st)
     st.rng = 0; st.spread_decision = 2; st.delayedIntra = 1; st.tonal_average = 256; st.lastCodedBands = 0; st.hf_average = 0;
     st.tapset_decision = 0; st.prefilter_period = 0; st.prefilter_gain = 0; st.prefilter_tapset = 0; st.consec_transient = 0;
     st.preemph_memE[0] = st.preemph_memE[1] = 0; st.vbr_reservoir = st.vbr_drift = st.vbr_offset = st.vbr_count = 0;
-    st.overlap_max = 0; st.stereo_saving = 0; st.intensity = 0; st.spec_avg = 0; st.final_range = 0;
+    st.overlap_max = 0; st.stereo_saving = 0; st.intensity = 0; st.spec_avg = 0; st.final_range = 0; st.an.valid = 0;
     for (int i = 0; i < 4; i++) st.hp_mem[i] = 0;
     for (int i = 0; i < 2 * OB_OVERLAP; i++) st.in_mem[i] = 0;
     for (int i = 0; i < 2 * OB_MAXPERIOD; i++) st.prefilter_mem[i] = 0;
@@ -79,6 +81,7 @@ OB_DEV int ob_run_prefilter(ObEncState &st, ObEncScratch &S, float *in, int CC, 
         if (st.loss_rate > 4) gain1 = .5f * gain1;
         if (st.loss_rate > 8) gain1 = 0;
     } else { gain1 = 0; pitch_index = OB_MINPERIOD; }
+    if (st.an.valid) gain1 = gain1 * st.an.max_pitch_ratio;          // celt_encoder.c:1246-1247
     pf_threshold = .2f;
     int dp = pitch_index - st.prefilter_period; if (dp < 0) dp = -dp;
     if (dp * 10 > pitch_index) pf_threshold += .2f;
@@ -114,13 +117,6 @@ OB_DEV int ob_run_prefilter(ObEncState &st, ObEncScratch &S, float *in, int CC, 
     }
     *gain = gain1; *pitch = pitch_index; *qgain = qg;
     return pf_on;
-}
-
-OB_DEV float ob_maxabs(const float *x, int len)                      // celt_maxabs16 (mathops.h:79-91)
-{
-    float maxval = 0, minval = 0;
-    for (int i = 0; i < len; i++) { maxval = ob_fmax(maxval, x[i]); minval = ob_fmin(minval, x[i]); }
-    return ob_fmax(maxval, -minval);
 }
 
 // celt_encode_with_ec (celt_encoder.c:1431-2368).  pcm: interleaved floats in [-1,1].  enc: coder created by the caller over the
@@ -200,7 +196,8 @@ OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float 
         const int enabled = nbAvailableBytes > 12 * C && !silence && !st.disable_pf && st.complexity >= 5;
         prefilter_tapset = st.tapset_decision;
         pf_on = ob_run_prefilter(st, S, in, CC, N, prefilter_tapset, &pitch_index, &gain1, &qg, enabled, nbAvailableBytes);
-        if ((gain1 > .4f || st.prefilter_gain > .4f) && (pitch_index > 1.26 * st.prefilter_period || pitch_index < .79 * st.prefilter_period))
+        if ((gain1 > .4f || st.prefilter_gain > .4f) && (!st.an.valid || (double)st.an.tonality > .3)
+                && (pitch_index > 1.26 * st.prefilter_period || pitch_index < .79 * st.prefilter_period))
             pitch_change = 1;
         if (pf_on == 0) {
             if (tell + 16 <= total_bits) enc.bit_logp(0, 1);
@@ -260,7 +257,7 @@ OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float 
     ob_normalise_bands(freq, X, bandE, effEnd, C, M);
     enable_tf_analysis = effectiveBytes >= 15 * C && st.complexity >= 2;
     maxDepth = ob_dynalloc_analysis(bandLogE, bandLogE2, oldBandE, end, C, offsets, st.lsb_depth, isTransient, st.vbr, st.constrained_vbr, LM,
-            effectiveBytes, &tot_boost, importance, spread_weight);
+            effectiveBytes, &tot_boost, importance, spread_weight, st.an.valid ? st.an.leak_boost : nullptr);
     if (enable_tf_analysis) {
         const int lambda = ob_imax(80, 20480 / effectiveBytes + 2);
         tf_select = ob_tf_analysis(effEnd, isTransient, tf_res, lambda, X, N, LM, tf_estimate, tf_chan, importance);
@@ -317,7 +314,7 @@ OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float 
     }
     alloc_trim = 5;
     if (tell + (6 << OB_BITRES) <= total_bits - total_boost) {
-        alloc_trim = ob_alloc_trim_analysis(X, bandLogE, end, LM, C, N, &st.stereo_saving, tf_estimate, st.intensity, equiv_rate);
+        alloc_trim = ob_alloc_trim_analysis(X, bandLogE, end, LM, C, N, &st.stereo_saving, tf_estimate, st.intensity, equiv_rate, st.an.valid, st.an.tonality_slope);
         enc.icdf(alloc_trim, OB_TRIM_ICDF, 7);
         tell = (int32_t)enc.tell_frac();
     }
@@ -329,8 +326,7 @@ OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float 
         base_target = vbr_rate - ((40 * C + 20) << OB_BITRES);
         if (st.constrained_vbr) base_target += (st.vbr_offset >> lm_diff);
         target = ob_compute_vbr(base_target, LM, equiv_rate, st.lastCodedBands, C, st.intensity, st.constrained_vbr, st.stereo_saving, tot_boost,
-                tf_estimate, maxDepth, temporal_vbr);
-        (void)pitch_change;
+                tf_estimate, maxDepth, temporal_vbr, st.an.valid, st.an.activity, st.an.tonality, pitch_change);
         target = target + tell;
         min_allowed = ((tell + total_boost + (1 << (OB_BITRES + 3)) - 1) >> (OB_BITRES + 3)) + 2;
         nbAvailableBytes = (target + (1 << (OB_BITRES + 2))) >> (OB_BITRES + 3);
@@ -358,6 +354,15 @@ OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float 
     anti_collapse_rsv = isTransient && LM >= 2 && bits >= ((LM + 2) << OB_BITRES) ? (1 << OB_BITRES) : 0;
     bits -= anti_collapse_rsv;
     signalBandwidth = end - 1;
+    if (st.an.valid) {                                                 // celt_encoder.c:2208-2222
+        int min_bandwidth;
+        if (equiv_rate < (int32_t)32000 * C) min_bandwidth = 13;
+        else if (equiv_rate < (int32_t)48000 * C) min_bandwidth = 16;
+        else if (equiv_rate < (int32_t)60000 * C) min_bandwidth = 18;
+        else if (equiv_rate < (int32_t)80000 * C) min_bandwidth = 19;
+        else min_bandwidth = 20;
+        signalBandwidth = ob_imax(st.an.bandwidth, min_bandwidth);
+    }
     codedBands = ob_enc_allocation(enc, end, offsets, cap, alloc_trim, &st.intensity, &dual_stereo, bits, &balance, pulses, fine_quant, fine_priority,
             C, LM, st.lastCodedBands, signalBandwidth);
     if (st.lastCodedBands) st.lastCodedBands = ob_imin(st.lastCodedBands + 1, ob_imax(st.lastCodedBands - 1, codedBands));
@@ -422,6 +427,8 @@ struct ObOpusEncCfg {
 };
 struct ObOpusEncState {
     int32_t stream_channels, first, auto_bandwidth, bandwidth, hybrid_stereo_width_Q14;
+    int32_t voice_ratio, detected_bandwidth;     // from the signal analysis (opus_encoder.c:1146-1176); voice_ratio = -1: unknown
+    ObTonalState tonal;                          // st->analysis
 };
 
 OB_DEV int32_t ob_compute_equiv_rate(int32_t bitrate, int channels, int frame_rate, int vbr, int celt_only, int complexity, int loss)
@@ -476,9 +483,28 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
         bitrate_bps = cbr_bytes * (int32_t)frame_rate12 * 8 / 12;
         max_data_bytes = ob_imax(1, cbr_bytes);
     }
+    // ---- signal analysis at complexity >= 7 (:1108-1176), on the caller's PCM, before anything else looks at the frame ----
+    ObAnalysisInfo analysis_info;
+    analysis_info.valid = 0;
+    {
+        const int lsb_depth = cfg.lsb_depth;
+        int is_silence = 0;
+        if (cfg.complexity >= 7) {
+            is_silence = ob_maxabs(pcm, frame_size * channels) <= (float)1 / (1 << lsb_depth);
+            ob_run_analysis(os.tonal, pcm, frame_size, channels, lsb_depth, analysis_info, S.pre);
+        } else if (os.tonal.initialized) ob_tonal_reset(os.tonal);
+        if (!is_silence) os.voice_ratio = -1;
+        os.detected_bandwidth = 0;
+        if (analysis_info.valid) {
+            const float prob = os.first ? analysis_info.music_prob : analysis_info.music_prob_max;           // prev_mode == 0 : == MODE_CELT_ONLY
+            os.voice_ratio = (int)floor(.5 + (double)(100 * (1 - prob)));
+            const int ab = analysis_info.bandwidth;
+            os.detected_bandwidth = ab <= 12 ? 1101 : ab <= 14 ? 1102 : ab <= 16 ? 1103 : ab <= 18 ? 1104 : 1105;
+        }
+    }
     if (max_data_bytes < 3 || bitrate_bps < 3 * frame_rate * 8) return OB_UNIMPLEMENTED;                       // the "PLC frame" corner (:1202-1266)
     int32_t equiv_rate = ob_compute_equiv_rate(bitrate_bps, channels, frame_rate, cfg.vbr, 0, cfg.complexity, cfg.packet_loss);
-    const int voice_est = 48;                                                                                 // :1278-1291, signal AUTO, not VOIP
+    const int voice_est = os.voice_ratio >= 0 ? os.voice_ratio * 327 >> 8 : 48;                               // :1276-1289, signal AUTO, application neither VOIP nor AUDIO
     if (cfg.force_channels > 0 && channels == 2) os.stream_channels = cfg.force_channels;
     else if (channels == 2) {
         int32_t stereo_threshold = 17000 + ((voice_est * voice_est * (19000 - 17000)) >> 14);
@@ -501,6 +527,16 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
     }
     if (os.bandwidth > cfg.max_bandwidth) os.bandwidth = cfg.max_bandwidth;
     if (cfg.user_bandwidth > 0) os.bandwidth = cfg.user_bandwidth;
+    if (os.detected_bandwidth && cfg.user_bandwidth <= 0) {                                                   // :1510-1530
+        int min_detected;
+        if (equiv_rate <= 18000 * os.stream_channels) min_detected = 1101;
+        else if (equiv_rate <= 24000 * os.stream_channels) min_detected = 1102;
+        else if (equiv_rate <= 30000 * os.stream_channels) min_detected = 1103;
+        else if (equiv_rate <= 44000 * os.stream_channels) min_detected = 1104;
+        else min_detected = 1105;
+        os.detected_bandwidth = ob_imax(os.detected_bandwidth, min_detected);
+        os.bandwidth = ob_imin(os.bandwidth, os.detected_bandwidth);
+    }
     if (os.bandwidth == 1102) os.bandwidth = 1103;
     const int curr_bandwidth = os.bandwidth;
 
@@ -531,6 +567,7 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
     st.complexity = cfg.complexity; st.lsb_depth = cfg.lsb_depth; st.loss_rate = cfg.packet_loss;
     st.vbr = cfg.vbr; st.constrained_vbr = cfg.vbr_constraint;
     st.bitrate = cfg.vbr ? bitrate_bps : OB_BITRATE_MAX;
+    st.an = analysis_info;                                                                                    // CELT_SET_ANALYSIS (:2229)
     int ret = ob_celt_encode(st, S, pcm_buf, frame_size, nb_compr_bytes, enc);
     if (ret < 0) return OB_INTERNAL_ERROR;
     {   // gen_toc (:299-329)

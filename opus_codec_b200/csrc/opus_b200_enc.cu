@@ -72,6 +72,8 @@ __global__ void ob_k_enc_reset(ObEncStream *streams, const int32_t *idx, int n, 
     es.st.channels = es.st.stream_channels = channels; es.st.end = 21; es.st.clip = 1; es.st.force_intra = 0; es.st.disable_inv = 0; es.st.disable_pf = 0;
     ob_enc_reset(es.st);
     es.os.stream_channels = channels; es.os.first = 1; es.os.auto_bandwidth = 0; es.os.bandwidth = 1105; es.os.hybrid_stereo_width_Q14 = 1 << 14;
+    es.os.voice_ratio = -1; es.os.detected_bandwidth = 0;
+    ob_tonal_reset(es.os.tonal);
 }
 
 __global__ void ob_k_enc_gather(const ObEncStream *streams, uint32_t *ranges, int S)

@@ -119,7 +119,9 @@ int emul_opus_encode_stream(const float *pcm, int nframes, int frame_size, int c
     ObEncState *st = (ObEncState *)calloc(1, sizeof(ObEncState));
     ObEncScratch *S = (ObEncScratch *)calloc(1, sizeof(ObEncScratch));
     ObOpusEncCfg cfg = {bitrate, complexity, vbr != 0, vbr == 2, 1105, 0, 0, 0, 24};
-    ObOpusEncState os = {channels, 1, 0, 1105, 1 << 14};
+    ObOpusEncState *osp = (ObOpusEncState *)calloc(1, sizeof(ObOpusEncState));
+    ObOpusEncState &os = *osp;
+    os.stream_channels = channels; os.first = 1; os.auto_bandwidth = 0; os.bandwidth = 1105; os.hybrid_stereo_width_Q14 = 1 << 14; os.voice_ratio = -1;
     st->channels = st->stream_channels = channels; st->end = 21; st->clip = 1;
     ob_enc_reset(*st);
     int rc = 0;
@@ -129,7 +131,7 @@ int emul_opus_encode_stream(const float *pcm, int nframes, int frame_size, int c
         lens[f] = n;
         ranges[f] = st->final_range;
     }
-    free(st); free(S);
+    free(st); free(S); free(osp);
     return rc;
 }
 }

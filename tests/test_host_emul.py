@@ -155,9 +155,12 @@ def test_encoder_device_code_bit_identical_to_reference_celt_encoder(emul, have_
         assert (lens == ref_ln).all() and (rng == ref_rng).all() and np.array_equal(out, ref_pk)
 
 
-@pytest.mark.parametrize("ch,br,fs,vbr,cx", [(1, 64000, 960, 0, 5), (2, 96000, 960, 0, 6), (2, 96000, 960, 1, 5), (1, 24000, 480, 2, 6), (2, 24000, 960, 0, 4), (1, 12000, 960, 0, 6)])
-def test_encoder_opus_layer_bit_identical_to_reference_below_complexity_7(emul, have_ref, ch, br, fs, vbr, cx):
-    """opus_encode_float (RESTRICTED_LOWDELAY): TOC, byte budget, bandwidth / stereo decisions, dc_reject -- identical packets."""
+@pytest.mark.parametrize("ch,br,fs,vbr,cx", [(1, 64000, 960, 0, 5), (2, 96000, 960, 0, 6), (2, 96000, 960, 1, 5), (1, 24000, 480, 2, 6), (2, 24000, 960, 0, 4), (1, 12000, 960, 0, 6),
+                                             (2, 96000, 960, 0, 10), (1, 64000, 960, 0, 10), (2, 96000, 960, 1, 10), (1, 24000, 480, 2, 9), (2, 64000, 240, 0, 8),
+                                             (1, 48000, 120, 1, 7), (2, 24000, 960, 0, 10), (1, 12000, 960, 1, 10), (2, 510000, 960, 0, 10)])
+def test_encoder_opus_layer_bit_identical_to_reference(emul, have_ref, ch, br, fs, vbr, cx):
+    """opus_encode_float (RESTRICTED_LOWDELAY): TOC, byte budget, bandwidth / stereo decisions, dc_reject and -- at complexity >= 7 --
+    the tonality analysis with its FFT, band statistics, bandwidth detector and GRU network: identical packets."""
     if not have_ref:
         pytest.skip("oracle/_ref not built")
     from opus_codec_b200 import synth
