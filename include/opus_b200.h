@@ -10,7 +10,7 @@
  *   -6 INVALID_STATE, -7 ALLOC_FAIL.  Batch calls return the call-level status; per-stream results
  *   (samples per channel, or a negative code) are written to samples_out[].
  *
- * Scope of this version: Fs = 48000, CELT-only TOC (config >= 16), every packet code (0-3: several frames per packet,
+ * Scope of this version: output rates 48 / 24 / 16 / 12 / 8 kHz (the decoder runs at 48 kHz inside), CELT-only TOC (config >= 16), every packet code (0-3: several frames per packet,
  * CBR / VBR sizes, padding), fec = false.  Lost packets (len 0) and DTX frames (<= 1 byte) are concealed like the
  * reference does (celt_decode_lost).  A SILK / hybrid TOC gives that (stream, packet) the status OPUS_UNIMPLEMENTED (-5),
  * a malformed packet OPUS_INVALID_PACKET (-4), both leaving the stream's state untouched; other streams are unaffected.
@@ -29,7 +29,8 @@ extern "C" {
 typedef struct ObDecoder ObDecoder;
 
 /* Replaces n x opus_decoder_create(Fs, channels, &err) (src/bindings.rs:366-373; Decoder::new src/decoder.rs:35-63).
- * n_streams independent decoders with `channels` output channels each live on CUDA device `device`.
+ * n_streams independent decoders with `channels` output channels each live on CUDA device `device`; fs is the OUTPUT sample
+ * rate (48000, 24000, 16000, 12000 or 8000): frame_size arguments and sample counts are in samples at that rate.
  * max_frames: the largest number of CELT frames per stream any single call will hold (>= 1): one per code-0 packet, up to 48
  * for a code-3 packet.  A packet whose frames do not fit any more gets OPUS_BUFFER_TOO_SMALL.
  * Returns NULL and sets *error on failure. */

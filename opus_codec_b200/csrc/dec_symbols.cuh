@@ -909,7 +909,8 @@ OB_DEV int ob_parse_packet(const uint8_t *data, int len, int16_t *sizes, int *fi
 
 // The packets of ONE stream for one call -> frame slots (the frame loop of opus_decode_native, opus_decoder.c:715-799).  frame_size:
 // the caller's per-packet PCM slot.  Returns the number of slots written (<= cap); a packet that does not fit gets one error slot.
-OB_DEV int ob_frame_packets(const uint8_t *packets, const int32_t *offsets, const int32_t *lens, int F, int frame_size, ObSlot *slots, int cap)
+// ds = 48000 / output rate: frame_size and the slots' sample offsets count OUTPUT samples, concealment lengths 48 kHz samples.
+OB_DEV int ob_frame_packets(const uint8_t *packets, const int32_t *offsets, const int32_t *lens, int F, int frame_size, ObSlot *slots, int cap, int ds = 1)
 {
     int n = 0;
     int16_t sizes[48];
@@ -919,7 +920,7 @@ OB_DEV int ob_frame_packets(const uint8_t *packets, const int32_t *offsets, cons
         ObSlot one;
         one.off = 0; one.len = 0; one.toc = 0; one.flags = OB_SLOT_FIRST | OB_SLOT_LAST; one.pkt = (uint16_t)f; one.sample_off = 0; one.status = 0;
         if (len <= 0) {                                          // lost packet: conceal the whole slot (opus_decoder.c:684-688, :715-729)
-            one.status = len < 0 || frame_size <= 0 || frame_size % OB_SHORT != 0 ? OB_BAD_ARG : frame_size;
+            one.status = len < 0 || frame_size <= 0 || frame_size % (OB_SHORT / ds) != 0 ? OB_BAD_ARG : frame_size * ds;
             slots[n++] = one;
             continue;
         }
@@ -929,13 +930,13 @@ OB_DEV int ob_frame_packets(const uint8_t *packets, const int32_t *offsets, cons
         const int count = (toc & 0x80) ? ob_parse_packet(data, len, sizes, &first_off) : OB_UNIMPLEMENTED;     // SILK / hybrid: not on this path
         const int N = OB_SHORT << ((toc >> 3) & 3);
         if (count < 0) one.status = count;
-        else if (count * N > frame_size) one.status = OB_BUFFER_TOO_SMALL;                                     // opus_decoder.c:764-765
+        else if (count * N > frame_size * ds) one.status = OB_BUFFER_TOO_SMALL;                                // opus_decoder.c:764-765
         else if (n + count > cap) one.status = OB_BUFFER_TOO_SMALL;                                            // decoder created with too few frame slots
         if (one.status < 0) { slots[n++] = one; continue; }
         uint32_t off = (uint32_t)offsets[f] + (uint32_t)first_off;
         for (int i = 0; i < count; i++) {
             ObSlot sl;
-            sl.off = off; sl.len = sizes[i]; sl.toc = (uint8_t)toc; sl.pkt = (uint16_t)f; sl.sample_off = (uint16_t)(i * N);
+            sl.off = off; sl.len = sizes[i]; sl.toc = (uint8_t)toc; sl.pkt = (uint16_t)f; sl.sample_off = (uint16_t)(i * N / ds);
             sl.flags = (uint8_t)((i == 0 ? OB_SLOT_FIRST : 0) | (i == count - 1 ? OB_SLOT_LAST : 0));
             sl.status = sizes[i] <= 1 ? N : 0;                   // payloads of <= 1 byte are DTX: concealed for one frame (opus_decoder.c:284-290)
             slots[n++] = sl;

@@ -232,6 +232,7 @@ struct ObSynthShared {
     int32_t last_pitch_index, paf;   // paf = st->prefilter_and_fold
     float decode_gain;               // linear gain of OPUS_SET_GAIN (1 = none)
     float softclip_mem[2];           // OpusDecoder.softclip_mem (int16 API)
+    int32_t ds;                      // st->downsample = 48000 / output rate (1, 2, 3, 4 or 6): spectrum cut at N/ds, every ds-th sample kept
     int32_t ring_pos;                // next write position (= oldest sample) of the global history ring
     float *ring;                     // this stream's ring: [CC][OB_RING]
 };
@@ -317,7 +318,7 @@ OB_DEV void ob_denorm_imdct(const G &g, ObSynthShared &sh, int C, int CC, int N,
     for (int c = 0; c < C; c++)
         for (int j = g.lane; j < N; j += g.n) {
             const int bin = j >> LM, band = bin < 100 ? sh.band_of_bin[bin] : OB_NB;
-            sh.freq[c][j] = band < OB_NB ? sh.freq[c][j] * sh.gain[c * OB_NB + band] : 0.f;
+            sh.freq[c][j] = (band < OB_NB && j < N / sh.ds) ? sh.freq[c][j] * sh.gain[c * OB_NB + band] : 0.f;     // bound: bands.c:206-208
         }
     g.sync();
     if (CC == 2 && C == 1) { for (int j = g.lane; j < N; j += g.n) sh.freq[1][j] = sh.freq[0][j]; g.sync(); }
@@ -365,8 +366,9 @@ OB_DEV void ob_synth_tail(const G &g, ObSynthShared &sh, float *pcm, int N, int 
             g.sync();
         }
         const float dg = sh.decode_gain;                             // OPUS_SET_GAIN, applied by the Opus layer (opus_decoder.c:639-649)
-        if (CC == 1) { for (int t = g.lane; t < N; t += g.n) pcm[t] = dg == 1.f ? sh.freq[0][t] : sh.freq[0][t] * dg; }
-        else { for (int t = g.lane; t < 2 * N; t += g.n) { const float v = sh.freq[t & 1][t >> 1]; pcm[t] = dg == 1.f ? v : v * dg; } }
+        const int ds = sh.ds, Nd = N / ds;                           // output rates below 48 kHz keep every ds-th sample (celt_decoder.c:326-373)
+        if (CC == 1) { for (int t = g.lane; t < Nd; t += g.n) { const float v = sh.freq[0][t * ds]; pcm[t] = dg == 1.f ? v : v * dg; } }
+        else { for (int t = g.lane; t < 2 * Nd; t += g.n) { const float v = sh.freq[t & 1][(t >> 1) * ds]; pcm[t] = dg == 1.f ? v : v * dg; } }
         g.sync();
     }
     for (int c = 0; c < CC; c++) {                                   // the frame joins the full-length history ring
@@ -396,9 +398,9 @@ OB_DEV_NOINLINE int ob_conceal(const G &g, ObSynthShared &sh, float *pcm, int CC
     const ObFrameHdr &h = sh.hdr;
     const int total = h.status;
     if (h.end_in == 0) {                                             // nothing decoded yet: zeros (opus_decoder.c:302-309)
-        for (int t = g.lane; t < total * CC; t += g.n) pcm[t] = 0.f;
+        for (int t = g.lane; t < total / sh.ds * CC; t += g.n) pcm[t] = 0.f;
         g.sync();
-        return total;
+        return total / sh.ds;
     }
     ObPlanState p;
     p.rng = h.seed_in; p.loss_duration = h.loss_in; p.skip_plc = h.skip_in; p.plc_end = h.end_in;
@@ -417,10 +419,10 @@ OB_DEV_NOINLINE int ob_conceal(const G &g, ObSynthShared &sh, float *pcm, int CC
         }
         g.sync();
         ob_plc_advance(p, N, CC);
-        ob_synth_tail(g, sh, pcm + (size_t)done * CC, N, CC);
+        ob_synth_tail(g, sh, pcm + (size_t)(done / sh.ds) * CC, N, CC);
         done += N;
     }
-    return total;
+    return total / sh.ds;
 }
 
 // opus_pcm_soft_clip (opus/src/opus.c:39-144) for ONE channel of an interleaved packet that has already been limited to +-2:
@@ -587,5 +589,5 @@ OB_DEV int ob_synth_frame(const G &g, ObSynthShared &sh, const ObFrameIR *ir, co
     g.sync();
 
     ob_synth_tail(g, sh, pcm, N, CC);
-    return N;
+    return N / sh.ds;
 }

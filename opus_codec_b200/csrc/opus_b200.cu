@@ -27,11 +27,11 @@
 // Framing pass, one thread per stream: the stream's F packets -> frame slots (code-0 packets: one slot each; codes 1-3: one per
 // coded frame; lost packets and DTX frames: concealment slots; anything off this path: an error slot).
 __global__ void ob_k_frame(const uint8_t *__restrict__ packets, const int32_t *__restrict__ offsets, const int32_t *__restrict__ lens,
-                           ObSlot *__restrict__ slots, int32_t *__restrict__ nslots, int S, int F, int frame_size, int cap, int32_t *__restrict__ multi)
+                           ObSlot *__restrict__ slots, int32_t *__restrict__ nslots, int S, int F, int frame_size, int cap, int32_t *__restrict__ multi, int ds)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    const int n = ob_frame_packets(packets, offsets + (size_t)s * F, lens + (size_t)s * F, F, frame_size, slots + (size_t)s * cap, cap);
+    const int n = ob_frame_packets(packets, offsets + (size_t)s * F, lens + (size_t)s * F, F, frame_size, slots + (size_t)s * cap, cap, ds);
     nslots[s] = n;
     // slot j <-> packet j unless some packet holds several frames (or did not fit): the host pipelines the call in slot windows
     // only in the one-to-one case
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(OB_SYNTH_THREADS, 7)
 ob_k_synth(const ObFrameIR *__restrict__ ir, const ObSlot *__restrict__ slots, const int32_t *__restrict__ nslots, const float *__restrict__ Xg,
            ObDecState *__restrict__ st, float *__restrict__ hist, float *__restrict__ ring,
            float *__restrict__ pcm, int16_t *__restrict__ pcm16, int32_t *__restrict__ samples, uint32_t *__restrict__ ranges, int S, int F, int cap,
-           int CC, int frame_size, int f0, int Fc, float decode_gain)
+           int CC, int frame_size, int f0, int Fc, float decode_gain, int ds)
 {
     __shared__ ObSynthShared sh;
     const int s = blockIdx.x;
@@ -136,7 +136,7 @@ ob_k_synth(const ObFrameIR *__restrict__ ir, const ObSlot *__restrict__ slots, c
         sh.pf_gain = state->pf_gain; sh.pf_gain_old = state->pf_gain_old;
         sh.preemph_mem[0] = state->preemph_mem[0]; sh.preemph_mem[1] = state->preemph_mem[1];
         sh.last_pitch_index = state->last_pitch_index; sh.paf = state->prefilter_and_fold;
-        sh.ring_pos = state->ring_pos; sh.ring = ring + (size_t)s * CC * OB_RING; sh.decode_gain = decode_gain;
+        sh.ring_pos = state->ring_pos; sh.ring = ring + (size_t)s * CC * OB_RING; sh.decode_gain = decode_gain; sh.ds = ds;
         sh.softclip_mem[0] = state->softclip_mem[0]; sh.softclip_mem[1] = state->softclip_mem[1];
     }
     for (int i = g.lane; i < 2 * 24; i += g.n) sh.lpc[i / 24][i % 24] = state->lpc[i / 24][i % 24];
@@ -222,6 +222,7 @@ __global__ void ob_k_gather_state(const ObDecState *st, uint32_t *ranges, int32_
 #endif
 struct ObDecoder {
     int S, CC, device, max_frames;
+    int ds;                               // 48000 / output sample rate
     int gain_q8, phase_inv_disabled;      // OPUS_SET_GAIN (Q8 dB), OPUS_SET_PHASE_INVERSION_DISABLED: one value for the batch
     float gain_linear;
     cudaStream_t stream, copy_stream, aux_stream;
@@ -269,7 +270,7 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
     float *ring = d->d_ring + (size_t)s0 * d->CC * OB_RING;
     if (timed) OB_CUDA(cudaEventRecord(d->ev[0], stream));
     if (which & 4) {
-        ob_k_frame<<<(Sc + 127) / 128, 128, 0, stream>>>(d_packets, d_offsets + w0, d_lens + w0, slots, nslots, Sc, F, frame_size, cap, d->d_multi);
+        ob_k_frame<<<(Sc + 127) / 128, 128, 0, stream>>>(d_packets, d_offsets + w0, d_lens + w0, slots, nslots, Sc, F, frame_size, cap, d->d_multi, d->ds);
         d->launches += 1;
     }
     if (which & 1) {
@@ -285,7 +286,7 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
         if (timed) OB_CUDA(cudaEventRecord(d->ev[2], stream));
         ob_k_synth<<<Sc, OB_SYNTH_THREADS, 0, stream>>>(ir, slots, nslots, X, st, hist, ring, d_pcm + w0 * (size_t)frame_size * d->CC,
                                                          d->cur_pcm16 ? d->cur_pcm16 + w0 * (size_t)frame_size * d->CC : nullptr, d_samples + w0,
-                                                         d_ranges ? d_ranges + w0 : nullptr, Sc, F, cap, d->CC, frame_size, f0, Fc, d->gain_linear);
+                                                         d_ranges ? d_ranges + w0 : nullptr, Sc, F, cap, d->CC, frame_size, f0, Fc, d->gain_linear, d->ds);
         d->launches += 3;
     }
     if (timed) OB_CUDA(cudaEventRecord(d->ev[3], stream));
@@ -302,7 +303,7 @@ ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
     ObDecoder *d = nullptr;
     int ndev = 0;
     if (n_streams <= 0 || (channels != 1 && channels != 2) || max_frames <= 0) err = OB_BAD_ARG;
-    else if (fs != 48000) err = OB_UNIMPLEMENTED;          // output rates 8-24 kHz: SURVEY 8(f) row 2
+    else if (fs != 48000 && fs != 24000 && fs != 16000 && fs != 12000 && fs != 8000) err = OB_BAD_ARG;     // opus_decoder_init, opus_decoder.c:130-131
     else if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
         fprintf(stderr, "opus_b200: no usable CUDA device (count=%d, requested=%d); there is no CPU fallback\n", ndev, device);
         err = OB_INTERNAL_ERROR;
@@ -314,7 +315,7 @@ ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
     if (err == OB_OK) {
         memset(d, 0, sizeof(*d));
         d->S = n_streams; d->CC = channels; d->device = device; d->max_frames = max_frames;
-        d->gain_q8 = 0; d->gain_linear = 1.f; d->phase_inv_disabled = 0;
+        d->gain_q8 = 0; d->gain_linear = 1.f; d->phase_inv_disabled = 0; d->ds = 48000 / fs;
         const size_t total = (size_t)n_streams * max_frames;
         bool ok = cudaSetDevice(device) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) == cudaSuccess;

@@ -193,7 +193,8 @@ REF_EXPORT int ref_encode_stream_i16(const opus_int16 *pcm, int nframes, int fra
 /* pkts: nframes slots of `stride` bytes; lens[f] bytes valid (0 => packet loss / PLC).
  * dec_channels: channel count of the decoder object.  taps (optional): nframes ref_tap_t records. */
 /* Optional decoder CTLs applied by ref_decode_stream: OPUS_SET_GAIN (Q8 dB) and OPUS_SET_PHASE_INVERSION_DISABLED. */
-static int g_dec_gain = 0, g_dec_phase_inv_disabled = 0;
+static int g_dec_gain = 0, g_dec_phase_inv_disabled = 0, g_dec_fs = 48000;
+REF_EXPORT void ref_set_decoder_fs(int fs) { g_dec_fs = fs; }
 REF_EXPORT void ref_set_decoder_extras(int gain_q8, int phase_inv_disabled)
 {
     g_dec_gain = gain_q8; g_dec_phase_inv_disabled = phase_inv_disabled;
@@ -203,7 +204,7 @@ REF_EXPORT int ref_decode_stream(const unsigned char *pkts, const int *lens, int
         int dec_channels, float *pcm_out, uint32_t *ranges, int *samples, void *taps)
 {
     int f, err = 0;
-    OpusDecoder *d = opus_decoder_create(48000, dec_channels, &err);
+    OpusDecoder *d = opus_decoder_create(g_dec_fs, dec_channels, &err);
     if (!d || err != OPUS_OK) return OPUS_ALLOC_FAIL;
     if (g_dec_gain) opus_decoder_ctl(d, OPUS_SET_GAIN(g_dec_gain));
     if (g_dec_phase_inv_disabled) opus_decoder_ctl(d, OPUS_SET_PHASE_INVERSION_DISABLED(1));

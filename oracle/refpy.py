@@ -135,7 +135,7 @@ def _encode_stream(pcm, frame_size, channels, bitrate, vbr, complexity, applicat
     return out, lens, rng
 
 
-def decode_stream(pkts, lens, frame_size, channels, want_taps=False, pure_c=False, gain_q8=0, phase_inv_disabled=False):
+def decode_stream(pkts, lens, frame_size, channels, want_taps=False, pure_c=False, gain_q8=0, phase_inv_disabled=False, fs=48000):
     """pkts u8 [nframes, stride] -> (pcm f32 [nframes, frame_size*channels], ranges u32, samples i32[, taps])."""
     pkts = np.ascontiguousarray(pkts, np.uint8)
     lens = np.ascontiguousarray(lens, np.int32)
@@ -147,12 +147,14 @@ def decode_stream(pkts, lens, frame_size, channels, want_taps=False, pure_c=Fals
     assert not want_taps or C.sizeof(Tap) == lib().ref_tap_size()
     L = lib_c() if pure_c else lib()
     L.ref_set_decoder_extras(int(gain_q8), 1 if phase_inv_disabled else 0)
+    L.ref_set_decoder_fs(int(fs))
     try:
         r = L.ref_decode_stream(_p(pkts, C.c_ubyte), _p(lens, C.c_int), stride, nframes, frame_size, channels,
                                 _p(pcm, C.c_float), _p(rng, C.c_uint32), _p(smp, C.c_int),
                                 C.cast(taps, C.c_void_p) if want_taps else None)
     finally:
         L.ref_set_decoder_extras(0, 0)
+        L.ref_set_decoder_fs(48000)
     if r != 0:
         raise RuntimeError("ref_decode_stream: opus error %d" % r)
     return (pcm, rng, smp, taps) if want_taps else (pcm, rng, smp)

@@ -39,7 +39,7 @@ int emul_decode_stream(const uint8_t *pkts, const int *lens, int stride, int nfr
     ObSolo g;
     ob_synth_init(g, *sh);
     sh->ring = (float *)calloc(2 * OB_RING, sizeof(float));
-    sh->decode_gain = 1.f;
+    sh->decode_gain = 1.f; sh->ds = 1;
     ObPlanState plan = {0u, 0, 1, 0, OB_SHORT};                     // OPUS_RESET_STATE: skip_plc = 1 (celt_decoder.c:1527)
     uint32_t final_range = 0;
     // framing pass over the whole stream, then slot by slot through the symbol, plan, band and synthesis stages

@@ -340,6 +340,34 @@ def test_int16_api_soft_clip_matches_reference(have_ref):
             assert np.isfinite(f32).all()
 
 
+@pytest.mark.parametrize("fs_out", [24000, 16000, 12000, 8000])
+def test_output_sample_rates_below_48k(have_ref, fs_out):
+    """Decoder::new(SampleRate::Hz8000..Hz24000): the spectrum is cut at the new Nyquist and every ds-th de-emphasised sample is
+    kept (celt_decoder.c:326-373, bands.c:206-208); frame sizes, sample counts and lost-packet slots count OUTPUT samples."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    from opus_codec_b200.batch import BatchDecoder
+    ds = 48000 // fs_out
+    for name in ("cfg1_stereo_20ms_128k_cbr", "cfg4_mono_5ms_48k"):
+        g = load_golden(name)
+        fs, dc = g["frame_size"] // ds, g["dec_channels"]
+        S, F, stride = g["packets"].shape
+        S, F = min(S, 3), min(F, 30)
+        pk = np.ascontiguousarray(g["packets"][:S, :F]); ln = g["lens"][:S, :F].copy()
+        ln[1, 7] = 0; ln[2, 3] = 1
+        with BatchDecoder(S, fs_out, dc, device=0, max_frames=F) as dec:
+            pcm, samples, ranges = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, fs)
+        pcm = pcm.reshape(S, F, fs * dc)
+        for s in range(S):
+            ref, rr, rs = refpy.decode_stream(pk[s], ln[s], fs, dc, pure_c=True, fs=fs_out)
+            assert (samples[s] == rs).all() and (ranges[s] == rr).all(), (samples[s], rs)
+            lossy = s != 0
+            for f in range(F):
+                tol = 3e-3 if lossy and f >= 3 else PCM_TOL
+                assert np.abs(pcm[s, f] - ref[f]).max() <= tol, (name, s, f)
+
+
 def test_reset_restarts_streams():
     from opus_codec_b200.batch import BatchDecoder
     g = load_golden("cfg2_mono_20ms_64k_cbr")
