@@ -8,7 +8,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libopus_b200.so")
+SO = os.environ.get("OB_LIB") or os.path.join(HERE, "libopus_b200.so")      # OB_LIB: tuning aid, points at an alternative build of the same library
 SRC = os.path.join(HERE, "csrc", "opus_b200.cu")
 SRC_ENC = os.path.join(HERE, "csrc", "opus_b200_enc.cu")       # compiled with -fmad=false (see the file header)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
