@@ -428,7 +428,7 @@ struct ObOpusEncCfg {
 struct ObOpusEncState {
     int32_t stream_channels, first, auto_bandwidth, bandwidth, hybrid_stereo_width_Q14;
     int32_t voice_ratio, detected_bandwidth;     // from the signal analysis (opus_encoder.c:1146-1176); voice_ratio = -1: unknown
-    ObTonalState tonal;                          // st->analysis
+    ObTonalState *tonal;                         // st->analysis when the analysis runs inline (host emulation); the GPU runs it in its own kernel
 };
 
 OB_DEV int32_t ob_compute_equiv_rate(int32_t bitrate, int channels, int frame_rate, int vbr, int celt_only, int complexity, int loss)
@@ -465,8 +465,10 @@ OB_DEV void ob_stereo_fade(float *buf, float g1, float g2, int frame_size)     /
 // opus_encode_float -> opus_encode_native -> opus_encode_frame_native for one 2.5/5/10/20 ms frame, CELT-only
 // (opus_encoder.c:1057-1696, :1698-2459; the lines this path executes are listed in SURVEY 8a).  data: out_bytes capacity.
 // Returns the packet length in bytes (TOC included) or a negative OPUS_* code.
+// pre_info: the frame's AnalysisInfo when the analysis ran ahead of the encoder in its own kernel (ob_k_analysis); nullptr: run it
+// inline on os.tonal.
 OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, ObEncState &st, ObEncScratch &S, const float *pcm, int frame_size,
-        uint8_t *data, int out_bytes)
+        uint8_t *data, int out_bytes, const ObAnalysisInfo *pre_info = nullptr)
 {
     const int channels = st.channels, Fs = 48000;
     if (frame_size != 120 && frame_size != 240 && frame_size != 480 && frame_size != 960) return OB_BAD_ARG;   // > 20 ms needs the repacketizer
@@ -491,8 +493,9 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
         int is_silence = 0;
         if (cfg.complexity >= 7) {
             is_silence = ob_maxabs(pcm, frame_size * channels) <= (float)1 / (1 << lsb_depth);
-            ob_run_analysis(os.tonal, pcm, frame_size, channels, lsb_depth, analysis_info, S.pre);
-        } else if (os.tonal.initialized) ob_tonal_reset(os.tonal);
+            if (pre_info) analysis_info = *pre_info;
+            else ob_run_analysis(*os.tonal, pcm, frame_size, channels, lsb_depth, analysis_info, S.pre);
+        } else if (os.tonal && os.tonal->initialized) ob_tonal_reset(*os.tonal);
         if (!is_silence) os.voice_ratio = -1;
         os.detected_bandwidth = 0;
         if (analysis_info.valid) {

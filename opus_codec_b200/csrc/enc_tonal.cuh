@@ -66,14 +66,14 @@ OB_DEV void ob_gemm_accum(float *out, const int8_t *w, int rows, int cols, int c
 {
     for (int i = 0; i < rows; i++) for (int j = 0; j < cols; j++) out[i] += w[j * col_stride + i] * x[j];
 }
-OB_DEV void ob_dense(const int8_t *bias, const int8_t *w, int M, int N, int sigmoid, float *output, const float *input)
+OB_DEV_NOINLINE void ob_dense(const int8_t *bias, const int8_t *w, int M, int N, int sigmoid, float *output, const float *input)
 {
     for (int i = 0; i < N; i++) output[i] = bias[i];
     ob_gemm_accum(output, w, N, M, N, input);
     for (int i = 0; i < N; i++) output[i] *= (1.f / 128);
     for (int i = 0; i < N; i++) output[i] = sigmoid ? ob_sigmoid(output[i]) : ob_tansig(output[i]);
 }
-OB_DEV void ob_gru(float *state, const float *input)               // layer1: 32 inputs, 24 neurons
+OB_DEV_NOINLINE void ob_gru(float *state, const float *input)               // layer1: 32 inputs, 24 neurons
 {
     const int M = 32, N = 24, stride = 3 * N;
     float tmp[32], z[32], r[32], h[32];
@@ -94,7 +94,7 @@ OB_DEV void ob_gru(float *state, const float *input)               // layer1: 32
 }
 
 // silk_resampler_down2_hp (analysis.c:115-161), float build; returns the high-pass energy
-OB_DEV float ob_down2_hp(float *S, float *out, const float *in, int inLen)
+OB_DEV_NOINLINE float ob_down2_hp(float *S, float *out, const float *in, int inLen)
 {
     const int len2 = inLen / 2;
     float hp_ener = 0;
@@ -138,7 +138,7 @@ OB_DEV float ob_downmix_and_resample(const float *x, float *y, float *S, int sub
 }
 
 // opus_fft (kiss_fft.c:569-589) of 480 complex points: scale, bit-reverse, then the decoder's radix stages with one lane.
-OB_DEV void ob_fft480(const float *fin, float *fout)
+OB_DEV_NOINLINE void ob_fft480(const float *fin, float *fout)
 {
     const float scale = 0.002083333f;
     const int16_t *br = ob_fft_bitrev(0);
@@ -158,7 +158,7 @@ OB_DEV void ob_fft480(const float *fin, float *fout)
 
 // tonality_analysis (analysis.c:446-953).  x: interleaved float PCM of the frame being encoded; len/offset in 48 kHz samples.
 // work: >= 960 (fft in) + 960 (fft out) + 960 (down-mix) + 3 * 240 floats.
-OB_DEV void ob_tonality_analysis(ObTonalState &tonal, const float *x, int len, int offset, int C, int lsb_depth, float *work)
+OB_DEV_NOINLINE void ob_tonality_analysis(ObTonalState &tonal, const float *x, int len, int offset, int C, int lsb_depth, float *work)
 {
     const int N = 480, N2 = 240, NB = OB_AN_NB_TBANDS;
     float *A = tonal.angle, *dA = tonal.d_angle, *d2A = tonal.d2_angle;
@@ -394,7 +394,7 @@ OB_DEV void ob_tonality_analysis(ObTonalState &tonal, const float *x, int len, i
 }
 
 // tonality_get_info (analysis.c:233-409), Fs = 48000
-OB_DEV void ob_tonality_get_info(ObTonalState &tonal, ObAnalysisInfo &info_out, int len)
+OB_DEV_NOINLINE void ob_tonality_get_info(ObTonalState &tonal, ObAnalysisInfo &info_out, int len)
 {
     int pos = tonal.read_pos, i;
     int curr_lookahead = tonal.write_pos - tonal.read_pos;

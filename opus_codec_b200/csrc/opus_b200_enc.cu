@@ -27,7 +27,8 @@ struct ObEncStream {           // everything one stream owns on the device
 // a warp touched 32 different lines: 112 ms per frame at 16384 streams.)
 __global__ void __launch_bounds__(OB_ENC_THREADS)
 ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *__restrict__ lens, uint32_t *__restrict__ ranges,
-            ObEncStream *__restrict__ streams, ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes, int lanes, int f0, int Fc)
+            ObEncStream *__restrict__ streams, const ObAnalysisInfo *__restrict__ info, ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes,
+            int lanes, int f0, int Fc)
 {
     // Only the first `lanes` threads of each warp carry a stream (tuning knob).  Spreading the streams over more, partly filled,
     // warps was tried to hide the local-memory latency this kernel is bound by (ncu: 0.26 warp-instructions/cycle/SM, 8.6 of 13
@@ -36,11 +37,8 @@ ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *_
     if ((int)threadIdx.x >= lanes) return;
     const int s = blockIdx.x * lanes + threadIdx.x;
     if (s >= S) return;
-    ObEncScratch sc;
-    {   // deterministic start: no stage may depend on stale local memory
-        uint32_t *z = reinterpret_cast<uint32_t *>(&sc);
-        for (int i = 0; i < (int)(sizeof(ObEncScratch) / 4); i++) z[i] = 0;
-    }
+    ObEncScratch sc;      // not initialised: no stage reads what it (or an earlier frame) has not written -- tests/test_host_emul.py runs the
+                          // same code with the work area filled with NaN patterns before every frame
     ObEncStream es = streams[s];
     const int CC = es.st.channels;
     // NOTE: the frame counter is deliberately volatile.  The loop body is one huge divergent region; with a plain `int f`
@@ -48,11 +46,45 @@ ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *_
     // skipped / mis-indexed whenever lanes of a warp diverge (found on B200: fine with 1-4 identical lanes, wrong with 5+).
     for (volatile int f = f0; f < f0 + Fc; f++) {              // this launch covers the frame window [f0, f0+Fc) of a [S][F] batch
         const size_t w = (size_t)s * F + f;
-        const int n = ob_opus_encode(cfg, es.os, es.st, sc, pcm + w * (size_t)frame_size * CC, frame_size, out + w * (size_t)max_bytes, max_bytes);
+        ObAnalysisInfo an;                                      // computed ahead of this kernel by ob_k_analysis (complexity >= 7)
+        if (info) an = info[w];
+        const int n = ob_opus_encode(cfg, es.os, es.st, sc, pcm + w * (size_t)frame_size * CC, frame_size, out + w * (size_t)max_bytes, max_bytes,
+                                     info ? &an : nullptr);
         lens[w] = n;
         if (ranges) ranges[w] = n > 0 ? es.st.final_range : 0;
     }
     streams[s] = es;
+}
+
+// The Opus-layer signal analysis (enc_tonal.cuh) depends on nothing but the input PCM and its own state, so it does not have to sit
+// inside the encoder's serial chain: it runs in this kernel, on its own CUDA stream, one frame window ahead of ob_k_encode.  Both
+// kernels are one thread per stream and latency bound at ~3.4 warps per SM; running them side by side doubles the warps in
+// flight and hides the analysis (16 % of the fused kernel's time) almost completely.
+__global__ void __launch_bounds__(OB_ENC_THREADS)
+ob_k_analysis(const float *__restrict__ pcm, ObTonalState *__restrict__ tonal, ObAnalysisInfo *__restrict__ info, int S, int F, int frame_size,
+              int channels, int lsb_depth, int f0, int Fc)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    float work[3600];                                           // lane-interleaved local memory, like the encoder's scratch
+    ObTonalState t = tonal[s];
+    for (volatile int f = f0; f < f0 + Fc; f++) {
+        const size_t w = (size_t)s * F + f;
+        ObAnalysisInfo a;
+        a.valid = 0;
+        ob_run_analysis(t, pcm + w * (size_t)frame_size * channels, frame_size, channels, lsb_depth, a, work);
+        info[w] = a;
+    }
+    tonal[s] = t;
+}
+__global__ void ob_k_tonal_reset(ObTonalState *tonal, const int32_t *idx, int n, int S)
+{
+    const int k = blockIdx.x;
+    if (k >= n) return;
+    const int s = idx ? idx[k] : k;
+    if (s < 0 || s >= S) return;
+    uint32_t *z = reinterpret_cast<uint32_t *>(tonal + s);
+    for (int i = threadIdx.x; i < (int)(sizeof(ObTonalState) / 4); i += blockDim.x) z[i] = 0;
 }
 
 // int16 API (opus_encode, opus_encoder.c:2346-2376, float build): in[i] = (1/32768) * pcm[i], then the float path at 16-bit depth.
@@ -72,8 +104,7 @@ __global__ void ob_k_enc_reset(ObEncStream *streams, const int32_t *idx, int n, 
     es.st.channels = es.st.stream_channels = channels; es.st.end = 21; es.st.clip = 1; es.st.force_intra = 0; es.st.disable_inv = 0; es.st.disable_pf = 0;
     ob_enc_reset(es.st);
     es.os.stream_channels = channels; es.os.first = 1; es.os.auto_bandwidth = 0; es.os.bandwidth = 1105; es.os.hybrid_stereo_width_Q14 = 1 << 14;
-    es.os.voice_ratio = -1; es.os.detected_bandwidth = 0;
-    ob_tonal_reset(es.os.tonal);
+    es.os.voice_ratio = -1; es.os.detected_bandwidth = 0; es.os.tonal = nullptr;
 }
 
 __global__ void ob_k_enc_gather(const ObEncStream *streams, uint32_t *ranges, int S)
@@ -85,10 +116,12 @@ __global__ void ob_k_enc_gather(const ObEncStream *streams, uint32_t *ranges, in
 struct ObEncoder {
     int S, CC, device, max_frames, lanes;
     ObOpusEncCfg cfg;
-    cudaStream_t stream, copy_stream;
-    cudaEvent_t ev[2], win_ev[4];
-    bool timed;
+    cudaStream_t stream, copy_stream, an_stream;
+    cudaEvent_t ev[2], win_ev[4], an_ev[4], enc_done;
+    bool timed, tonal_dirty;
     ObEncStream *d_streams;
+    ObTonalState *d_tonal;             // [S] state of the signal analysis (complexity >= 7)
+    ObAnalysisInfo *d_info;            // [S][max_frames] its per-frame result, consumed by ob_k_encode
     float *d_pcm; size_t pcm_cap;
     int16_t *d_pcm16; size_t pcm16_cap;
     uint8_t *d_out; size_t out_cap;
@@ -126,6 +159,12 @@ ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         ok = ok && cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreateWithFlags(&e->win_ev[i], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_streams, sizeof(ObEncStream) * n_streams) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&e->an_stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreateWithFlags(&e->an_ev[i], cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&e->enc_done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaMalloc(&e->d_tonal, sizeof(ObTonalState) * n_streams) == cudaSuccess;
+        ok = ok && cudaMemset(e->d_tonal, 0, sizeof(ObTonalState) * n_streams) == cudaSuccess;
+        ok = ok && cudaMalloc(&e->d_info, sizeof(ObAnalysisInfo) * total) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_lens, sizeof(int32_t) * total) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_ranges, sizeof(uint32_t) * total) == cudaSuccess;
         // the per-thread encoder recurses (quant_partition, <= 5 deep) and keeps band-sized arrays on its stack
@@ -148,7 +187,10 @@ void ob_encoder_destroy(ObEncoder *e)
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_streams); cudaFree(e->d_pcm); cudaFree(e->d_pcm16); cudaFree(e->d_out); cudaFree(e->d_lens); cudaFree(e->d_ranges);
     for (int i = 0; i < 2; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
-    for (int i = 0; i < 4; i++) if (e->win_ev[i]) cudaEventDestroy(e->win_ev[i]);
+    for (int i = 0; i < 4; i++) { if (e->win_ev[i]) cudaEventDestroy(e->win_ev[i]); if (e->an_ev[i]) cudaEventDestroy(e->an_ev[i]); }
+    if (e->enc_done) cudaEventDestroy(e->enc_done);
+    if (e->an_stream) cudaStreamDestroy(e->an_stream);
+    cudaFree(e->d_tonal); cudaFree(e->d_info);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -167,7 +209,8 @@ int32_t ob_encoder_reset(ObEncoder *e, const int32_t *idx, int32_t n)
         OB_CUDA(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
     }
     ob_k_enc_reset<<<(count + 63) / 64, 64, 0, e->stream>>>(e->d_streams, d_idx, count, e->S, e->CC);
-    e->launches += 1;
+    ob_k_tonal_reset<<<count, 128, 0, e->stream>>>(e->d_tonal, d_idx, count, e->S);
+    e->launches += 2;
     OB_CUDA(cudaStreamSynchronize(e->stream));
     if (d_idx) cudaFree(d_idx);
     return OB_OK;
@@ -198,15 +241,39 @@ int32_t ob_encoder_set_force_channels(ObEncoder *e, int32_t ch) { if (!e || (ch 
 int32_t ob_encoder_set_packet_loss_perc(ObEncoder *e, int32_t p) { if (!e || p < 0 || p > 100) return OB_BAD_ARG; e->cfg.packet_loss = p; return OB_OK; }
 int32_t ob_encoder_set_lsb_depth(ObEncoder *e, int32_t d) { if (!e || d < 8 || d > 24) return OB_BAD_ARG; e->cfg.lsb_depth = d; return OB_OK; }
 
+// One frame window [f0, f0+Fc) of every stream.  At complexity >= 7 the analysis kernel of the window runs on its own stream, right
+// away (it needs only the PCM), and the encode kernel of the window waits for it; while the encoder works on window k the analysis
+// of window k+1 is already running beside it.  analysis_ahead: the caller has already enqueued the analysis of this window.
+static int ob_enc_analysis(ObEncoder *e, int F, const float *d_pcm, int frame_size, int f0, int Fc, int k, cudaEvent_t pcm_ready)
+{
+    if (e->cfg.complexity < 7) return OB_OK;
+    if (pcm_ready) OB_CUDA(cudaStreamWaitEvent(e->an_stream, pcm_ready, 0));
+    if (f0 == 0) OB_CUDA(cudaStreamWaitEvent(e->an_stream, e->enc_done, 0));       // d_info of the previous call has been consumed
+    ob_k_analysis<<<(e->S + OB_ENC_THREADS - 1) / OB_ENC_THREADS, OB_ENC_THREADS, 0, e->an_stream>>>(d_pcm, e->d_tonal, e->d_info, e->S, F, frame_size, e->CC,
+                                                                                                     e->cfg.lsb_depth, f0, Fc);
+    OB_CUDA(cudaEventRecord(e->an_ev[k & 3], e->an_stream));
+    e->launches += 1;
+    e->tonal_dirty = true;
+    return OB_OK;
+}
+
 static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size, uint8_t *d_out, int max_bytes, int32_t *d_lens, uint32_t *d_ranges,
-                         int f0 = 0, int Fc = -1)
+                         int f0 = 0, int Fc = -1, int k = 0)
 {
     if (Fc < 0) Fc = F;
+    const bool an = e->cfg.complexity >= 7;
+    if (!an && e->tonal_dirty) {                               // "else if (st->analysis.initialized) tonality_analysis_reset()" (opus_encoder.c:1131-1133)
+        ob_k_tonal_reset<<<e->S, 128, 0, e->stream>>>(e->d_tonal, nullptr, e->S, e->S);
+        e->tonal_dirty = false;
+        e->launches += 1;
+    }
     if (f0 == 0) OB_CUDA(cudaEventRecord(e->ev[0], e->stream));
+    if (an) OB_CUDA(cudaStreamWaitEvent(e->stream, e->an_ev[k & 3], 0));
     int lanes = e->lanes;
     if (const char *v = getenv("OB_ENC_LANES")) { const int t = atoi(v); if (t >= 1 && t <= OB_ENC_THREADS) lanes = t; }   // tuning aid
-    ob_k_encode<<<(e->S + lanes - 1) / lanes, OB_ENC_THREADS, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->cfg, e->S, F, frame_size, max_bytes, lanes, f0, Fc);
-    if (f0 + Fc == F) OB_CUDA(cudaEventRecord(e->ev[1], e->stream));
+    ob_k_encode<<<(e->S + lanes - 1) / lanes, OB_ENC_THREADS, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, an ? e->d_info : nullptr, e->cfg,
+                                                                               e->S, F, frame_size, max_bytes, lanes, f0, Fc);
+    if (f0 + Fc == F) { OB_CUDA(cudaEventRecord(e->ev[1], e->stream)); OB_CUDA(cudaEventRecord(e->enc_done, e->stream)); }
     OB_CUDA(cudaGetLastError());
     e->launches += 1;
     e->timed = true;
@@ -218,8 +285,21 @@ int32_t ob_encode_float_device(ObEncoder *e, int32_t n_frames, const float *d_pc
 {
     if (!e || !d_pcm || !d_out || !d_lens_out || n_frames <= 0 || n_frames > e->max_frames || max_bytes <= 0) return OB_BAD_ARG;
     OB_CUDA(cudaSetDevice(e->device));
-    const int r = ob_enc_launch(e, n_frames, d_pcm, frame_size, d_out, max_bytes, d_lens_out, d_ranges_out);
-    if (r != OB_OK) return r;
+    // the caller's PCM is ready in stream order of e->stream; with the analysis on (complexity >= 7) the call runs in frame windows so
+    // that the analysis of window k+1 overlaps the encoder of window k
+    const int nwin = e->cfg.complexity >= 7 ? (n_frames >= 4 ? 4 : (n_frames >= 2 ? 2 : 1)) : 1;
+    const int per = (n_frames + nwin - 1) / nwin;
+    OB_CUDA(cudaEventRecord(e->win_ev[0], e->stream));
+    for (int k = 0, f0 = 0; f0 < n_frames; k++, f0 += per) {
+        const int Fc = n_frames - f0 < per ? n_frames - f0 : per;
+        const int r = ob_enc_analysis(e, n_frames, d_pcm, frame_size, f0, Fc, k, k == 0 ? e->win_ev[0] : nullptr);
+        if (r != OB_OK) return r;
+    }
+    for (int k = 0, f0 = 0; f0 < n_frames; k++, f0 += per) {
+        const int Fc = n_frames - f0 < per ? n_frames - f0 : per;
+        const int r = ob_enc_launch(e, n_frames, d_pcm, frame_size, d_out, max_bytes, d_lens_out, d_ranges_out, f0, Fc, k);
+        if (r != OB_OK) return r;
+    }
     if (sync) OB_CUDA(cudaStreamSynchronize(e->stream));
     return OB_OK;
 }
@@ -249,9 +329,10 @@ static int32_t ob_encode_submit(ObEncoder *e, int32_t n_frames, const float *pcm
         const int Fc = n_frames - f0 < per ? n_frames - f0 : per;
         if (!pcm16) OB_CUDA(cudaMemcpy2DAsync(e->d_pcm + f0 * pf, n_frames * pf * sizeof(float), pcm + f0 * pf, n_frames * pf * sizeof(float),
                                   Fc * pf * sizeof(float), e->S, cudaMemcpyHostToDevice, e->copy_stream));
-        OB_CUDA(cudaEventRecord(e->win_ev[k], e->copy_stream));
+        OB_CUDA(cudaEventRecord(e->win_ev[k], pcm16 ? e->stream : e->copy_stream));      // this window's PCM is on the device
         OB_CUDA(cudaStreamWaitEvent(e->stream, e->win_ev[k], 0));
-        const int r = ob_enc_launch(e, n_frames, e->d_pcm, frame_size, e->d_out, max_bytes, e->d_lens, e->d_ranges, f0, Fc);
+        int r = ob_enc_analysis(e, n_frames, e->d_pcm, frame_size, f0, Fc, k, e->win_ev[k]);
+        if (r == OB_OK) r = ob_enc_launch(e, n_frames, e->d_pcm, frame_size, e->d_out, max_bytes, e->d_lens, e->d_ranges, f0, Fc, k);
         if (r != OB_OK) { e->cfg.lsb_depth = lsb_saved; return r; }
     }
     e->cfg.lsb_depth = lsb_saved;

@@ -122,16 +122,18 @@ int emul_opus_encode_stream(const float *pcm, int nframes, int frame_size, int c
     ObOpusEncState *osp = (ObOpusEncState *)calloc(1, sizeof(ObOpusEncState));
     ObOpusEncState &os = *osp;
     os.stream_channels = channels; os.first = 1; os.auto_bandwidth = 0; os.bandwidth = 1105; os.hybrid_stereo_width_Q14 = 1 << 14; os.voice_ratio = -1;
+    os.tonal = (ObTonalState *)calloc(1, sizeof(ObTonalState));
     st->channels = st->stream_channels = channels; st->end = 21; st->clip = 1;
     ob_enc_reset(*st);
     int rc = 0;
     for (int f = 0; f < nframes; f++) {
+        if (getenv("OB_EMUL_POISON")) memset(S, 0xFF, sizeof(ObEncScratch));      // no stage may depend on what an earlier frame left in the work area
         const int n = ob_opus_encode(cfg, os, *st, *S, pcm + (size_t)f * frame_size * channels, frame_size, out + (size_t)f * max_bytes, max_bytes);
         if (n < 0) { rc = n; break; }
         lens[f] = n;
         ranges[f] = st->final_range;
     }
-    free(st); free(S); free(osp);
+    free(os.tonal); free(st); free(S); free(osp);
     return rc;
 }
 }

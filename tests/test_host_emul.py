@@ -14,6 +14,9 @@ from oracle import oraclepy
 EMU = os.path.join(ROOT, "tests", "host_emul")
 
 
+os.environ["OB_EMUL_POISON"] = "1"      # the encoder's work area is filled with NaN patterns before every frame (see emul.cpp)
+
+
 @pytest.fixture(scope="module")
 def emul():
     so = os.path.join(EMU, "libemul.so")
