@@ -103,3 +103,23 @@ def multiframe_stream(g, s, nframes_out):
     return out, lens
 
 
+
+
+def pathological_pcm(s, n, ch, rng):
+    """Inputs an encoder meets in the wild: digital silence, DC, full-scale and beyond (clipping), denormal-sized noise, bursts,
+    NaN / Inf samples (the reference zeroes such a frame after its DC-reject filter, opus_encoder.c:1966-1976)."""
+    import numpy as np
+    from opus_codec_b200 import synth
+    x = synth.stream_pcm(s, n, ch, base_seed=31).reshape(n, ch).copy()
+    kind = s % 8
+    if kind == 0: x[:] = 0
+    elif kind == 1: x[:] = 0.25
+    elif kind == 2: x *= 6.0                                  # far beyond full scale
+    elif kind == 3: x = (rng.standard_normal((n, ch)) * 1e-7).astype(np.float32)
+    elif kind == 4: x[n // 3:n // 3 + 960] = 0; x[n // 2:n // 2 + 40] = 3.0
+    elif kind == 5: x[n // 4, 0] = np.nan; x[n // 2 + 7, ch - 1] = np.inf
+    elif kind == 6: x[::2] *= -1.0                             # energy at Nyquist
+    else: x = np.sign(x) * np.float32(0.99)                     # square-ish wave at full scale
+    return np.ascontiguousarray(x.reshape(-1), np.float32)
+
+

@@ -11,6 +11,8 @@ import tempfile
 import numpy as np
 import pytest
 
+from conftest import pathological_pcm
+
 from opus_codec_b200 import synth
 
 pytestmark = pytest.mark.gpu
@@ -63,6 +65,26 @@ def test_int16_encode_api_matches_reference(have_ref):
                 total += 1
                 same += int(lens[s, f] == rl[f] and np.array_equal(out[s, f, :rl[f]], ro[f, :rl[f]]) and rng[s, f] == rr[f])
         assert same / total >= 0.97, (ch, br, fs, same, total)
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("ch,br,fs,vbr,cx", [(2, 96000, 960, 0, 10), (1, 32000, 480, 1, 10), (2, 64000, 240, 2, 5)])
+def test_pathological_input_matches_reference(have_ref, ch, br, fs, vbr, cx):
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    rng = np.random.default_rng(12)
+    S, n = 16, 48000
+    pcm = np.stack([pathological_pcm(s, n, ch, rng) for s in range(S)])
+    out, lens, erng = _gpu_encode(pcm, fs, ch, br, vbr, cx)
+    assert (lens > 0).all()
+    ident = []
+    for s in range(S):
+        ro, rl, rr = _ref_c_encode(pcm[s], fs, ch, br, vbr, cx)
+        ident.append(((ro == out[s]).all(axis=1) & (rl == lens[s])).mean())
+        _, dec_rng, smp = refpy.decode_stream(out[s], lens[s], fs, ch)
+        assert (smp == fs).all() and (dec_rng == erng[s]).all(), s
+    assert min(ident) >= 0.9 and np.mean(ident) >= 0.97, ident
 
 
 def _gpu_encode(pcm_batch, fs, ch, br, vbr, cx):

@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import ROOT, golden_names, load_golden, plc_golden_names, load_plc_golden, multiframe_stream
+from conftest import ROOT, golden_names, load_golden, plc_golden_names, load_plc_golden, multiframe_stream, pathological_pcm
 from oracle import oraclepy
 
 EMU = os.path.join(ROOT, "tests", "host_emul")
@@ -104,6 +104,26 @@ def test_soft_clip_and_int16_rounding_match_reference(emul, have_ref):
             emul.emul_packet_to_int16(P(b, C.c_float), P(out, C.c_int16), n, ch, P(mem, C.c_float))
             assert np.array_equal(a, b), (ch, k)
             assert np.array_equal(out, want) and np.array_equal(mem[:ch], mem_ref)
+
+
+@pytest.mark.parametrize("ch,br,fs,vbr,cx", [(2, 96000, 960, 0, 10), (1, 32000, 480, 1, 10), (2, 64000, 240, 2, 5)])
+def test_encoder_pathological_input_bit_identical_to_reference(emul, have_ref, ch, br, fs, vbr, cx):
+    """Digital silence, DC, 6x full scale, 1e-7 noise, bursts, NaN / Inf samples, Nyquist energy, square waves."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    L = refpy.lib_c()
+    u8p, i32p, u32p, f32p = (C.POINTER(C.c_ubyte), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_float))
+    L.ref_encode_stream.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, i32p, u32p]
+    rng = np.random.default_rng(12)
+    for s in range(8):
+        pcm = pathological_pcm(s, 24000, ch, rng)
+        nf = pcm.size // (fs * ch)
+        a = np.zeros((nf, 1275), np.uint8); al = np.zeros(nf, np.int32); ar = np.zeros(nf, np.uint32)
+        b = np.zeros((nf, 1275), np.uint8); bl = np.zeros(nf, np.int32); br_ = np.zeros(nf, np.uint32)
+        assert L.ref_encode_stream(P(pcm, C.c_float), nf, fs, ch, 2051, br, vbr, cx, P(a, C.c_ubyte), 1275, P(al, C.c_int), P(ar, C.c_uint32)) == 0
+        assert emul.emul_opus_encode_stream(P(pcm, C.c_float), nf, fs, ch, br, vbr, cx, P(b, C.c_ubyte), 1275, P(bl, C.c_int), P(br_, C.c_uint32)) == 0
+        assert (al == bl).all() and (ar == br_).all() and np.array_equal(a, b), s
 
 
 def _fuzz_streams(seed, trials, nf=10, with_loss=True):
