@@ -204,6 +204,63 @@ def run_encode_leg(args, L, local, world, rank, dev, barrier):
     return res
 
 
+def run_transcode_leg(args, L, local, world, rank, dev, barrier):
+    """BASELINE configs[4] per GPU: 16384 stereo streams decoded and re-encoded (96 kb/s CBR, complexity 10) without leaving the device --
+    the decoder's PCM buffer is the encoder's input (keep decoded PCM on-device)."""
+    import torch
+    from opus_codec_b200.batch import BatchDecoder, BatchEncoder
+    from opus_codec_b200.shard import max_over_ranks
+    S, F = ENC_STREAMS_PER_GPU, args.enc_frames
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cfg3_stereo_20ms_96k_cbr.npz"))
+    pk0, ln0 = z["packets"], z["lens"]                         # [6, 50, stride]: tiled over streams, the first F frames of each
+    idx = np.arange(S) % pk0.shape[0]
+    pk = np.ascontiguousarray(pk0[idx, :F]); ln = np.ascontiguousarray(ln0[idx, :F]).astype(np.int32)
+    stride = pk.shape[2]
+    offsets = (np.arange(S * F, dtype=np.int32) * stride).reshape(S, F)
+    dec = BatchDecoder(S, 48000, 2, device=local, max_frames=F)
+    enc = BatchEncoder(S, 48000, 2, device=local, max_frames=F)
+    enc.set_bitrate(96000); enc.set_complexity(10); enc.set_vbr(False)
+    dext = torch.cuda.ExternalStream(L.ob_decoder_cuda_stream(dec.handle), device=local)
+    eext = torch.cuda.ExternalStream(L.ob_encoder_cuda_stream(enc.handle), device=local)
+    d_pk = torch.from_numpy(pk.reshape(-1)).to(dev); d_off = torch.from_numpy(offsets.reshape(-1)).to(dev); d_len = torch.from_numpy(ln.reshape(-1)).to(dev)
+    d_pcm = torch.empty(S * F * FRAME * 2, dtype=torch.float32, device=dev)
+    d_smp = torch.empty(S * F, dtype=torch.int32, device=dev); d_rng = torch.empty(S * F, dtype=torch.int32, device=dev)
+    d_out = torch.zeros(S * F * 256, dtype=torch.uint8, device=dev)
+    d_olen = torch.zeros(S * F, dtype=torch.int32, device=dev); d_orng = torch.zeros(S * F, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    ready, consumed = torch.cuda.Event(), torch.cuda.Event()
+
+    def step():
+        dext.wait_event(consumed)                               # the encoder has read the previous step's PCM
+        r = L.ob_decode_float_device(dec.handle, F, d_pk.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_pcm.data_ptr(), FRAME, d_smp.data_ptr(), d_rng.data_ptr(), 0)
+        assert r == 0, r
+        ready.record(dext)
+        eext.wait_event(ready)
+        r = L.ob_encode_float_device(enc.handle, F, d_pcm.data_ptr(), FRAME, d_out.data_ptr(), 256, d_olen.data_ptr(), d_orng.data_ptr(), 0)
+        assert r == 0, r
+        consumed.record(eext)
+
+    consumed.record(eext)
+    step()
+    barrier()
+    steps = max(1, min(args.steps, 3))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(dext)
+    for _ in range(steps):
+        step()
+    e1.record(eext)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev)
+    assert (d_smp.cpu().numpy() == FRAME).all() and (d_olen.cpu().numpy() == 240).all()
+    launches = dec.launches() + enc.launches()
+    dec.close(); enc.close()
+    audio = world * S * F * 0.02
+    return {"workload": "%d stereo streams per GPU decoded (96 kb/s CBR packets) and re-encoded at 96 kb/s CBR, complexity 10, PCM stays on the device "
+                        "(BASELINE configs[4] per-GPU share)" % S,
+            "frames_per_stream_per_step": F, "steps": steps, "value": audio * steps / (ms / 1000.0), "unit": "audio-s/s", "ms_per_step": ms / steps,
+            "gpu_launches": int(launches)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -232,6 +289,42 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa(local):
+    """Pin this process to the CPUs next to its GPU before any pinned buffer is allocated: a NUMA-remote staging buffer halves the
+    PCIe rate and with it the end-to-end number (seen on this pool: 111 k vs 196 k audio-s/s for the same build)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        dev = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(dev + "/numa_node").read())
+        cpus = open(dev + "/local_cpulist").read().strip()
+        if node < 0 or not cpus:
+            return {"node": node, "bound": False}
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if ids:
+            os.sched_setaffinity(0, ids)
+        return {"node": node, "bound": bool(ids), "cpus": cpus}
+    except Exception as ex:      # no sysfs entry, container restrictions: run unbound
+        return {"node": None, "bound": False, "why": repr(ex)[:80]}
+
+
+def pcie_d2h_gbs(dev, nbytes=256 << 20):
+    import torch
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    h.copy_(d, non_blocking=True); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        h.copy_(d, non_blocking=True)
+    e1.record(); torch.cuda.synchronize()
+    return 3 * nbytes / (e0.elapsed_time(e1) / 1e3) / 1e9
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -244,6 +337,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))   # plumbing only: barrier + max-reduce of timings
     L = _lib.lib()
@@ -299,6 +393,7 @@ def run_ours(args):
     assert (d_rng.cpu().numpy().view(np.uint32).reshape(S, F) == rng_expect).all(), "final range mismatch"
 
     # ---- end to end through the host-pointer C ABI (pinned buffers) ----
+    pcie = pcie_d2h_gbs(dev) if not args.kernels_only else None        # the ceiling of this leg: 788 MB of PCM per step cross PCIe
     h_pk = torch.from_numpy(pk.reshape(-1).copy()).pin_memory()
     h_off = torch.from_numpy(offsets.reshape(-1).copy()).pin_memory()
     h_len = torch.from_numpy(ln.reshape(-1).copy()).pin_memory()
@@ -351,10 +446,11 @@ def run_ours(args):
     value = audio_per_step * args.steps / (ms_dev / 1000.0)
     e2e = audio_per_step * e2e_steps / (ms_e2e / 1000.0) if e2e_steps else None
 
-    encode = None
+    encode = transcode = None
     if not args.no_encode:
         dec.close()
         encode = run_encode_leg(args, L, local, world, rank, dev, barrier)
+        transcode = run_transcode_leg(args, L, local, world, rank, dev, barrier)
     if rank == 0:
         peaks = {}
         try:
@@ -396,8 +492,9 @@ def run_ours(args):
                        "l2": "per-step working set (IR+spectrum+PCM, %.1f GB) exceeds the 126 MB L2" % ((S * F * (12.6e3 + 7.7e3 + 3.84e3)) / 1e9),
                        "sharding": "streams split by rank, no collective"},
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "pcie_d2h_GBps": pcie, "numa": numa,
                     "mode": "host wall clock; two host-pointer calls in flight (ob_decode_float_multi_async + ob_decoder_wait), pinned buffers"},
-            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "encode": encode,
+            "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "encode": encode, "transcode": transcode,
         }
         print(json.dumps(line))
     dec.close()
