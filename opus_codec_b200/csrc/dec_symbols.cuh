@@ -568,7 +568,13 @@ OB_DEV_NOINLINE uint32_t ob_decode_partition(ObBandCtx &ctx, int off, int N, int
     uint32_t ret = 0;
     st[0].off = (int16_t)off; st[0].N = (int16_t)N; st[0].b = b; st[0].B = (int8_t)B; st[0].LM = (int8_t)LM;
     st[0].gain = gain; st[0].fill = fill; st[0].stage = 0;
+    // The walk over the split tree is a small state machine.  It is run in two alternating phases so that the threads of a warp
+    // (one frame each) meet again at the expensive step: first every thread advances through its cheap split / merge states
+    // until it stands on a leaf, then all threads that have a leaf decode it together (the PVQ index decode is ~40 % of this
+    // kernel's instructions; interleaved with other threads' split states it ran at 4-9 active lanes).
     while (sp >= 0) {
+      bool at_leaf = false;
+      while (sp >= 0 && !at_leaf) {
         ObPartFrame &f = st[sp];
         if (f.stage == 0) {
             const uint8_t *cache = ob_pcache(ctx.band, f.LM);
@@ -598,7 +604,33 @@ OB_DEV_NOINLINE uint32_t ob_decode_partition(ObBandCtx &ctx, int off, int N, int
                 c.N = (int16_t)n; c.B = (int8_t)B1; c.LM = (int8_t)lm; c.stage = 0;
                 if (f.mid_first) { c.off = f.off; c.b = f.mbits; c.gain = f.gain * f.mid; c.fill = fl; }
                 else { c.off = (int16_t)(f.off + n); c.b = f.sbits; c.gain = f.gain * f.side; c.fill = fl >> B1; }
+            } else at_leaf = true;
+        } else if (f.stage == 1) {
+            // first child done: rebalance (bands.c:1017-1035) and launch the second
+            ObPartFrame &c = st[sp + 1];
+            c.N = f.N; c.B = f.B; c.LM = f.LM; c.stage = 0;
+            if (f.mid_first) {
+                f.cm = ret;
+                int32_t rb = f.mbits - (f.rebalance - ctx.remaining_bits);
+                if (rb > 3 << OB_BITRES && f.itheta != 0) f.sbits += rb - (3 << OB_BITRES);
+                c.off = (int16_t)(f.off + f.N); c.b = f.sbits; c.gain = f.gain * f.side; c.fill = f.fill >> f.B;
             } else {
+                f.cm = ret << (f.B0 >> 1);
+                int32_t rb = f.sbits - (f.rebalance - ctx.remaining_bits);
+                if (rb > 3 << OB_BITRES && f.itheta != 16384) f.mbits += rb - (3 << OB_BITRES);
+                c.off = f.off; c.b = f.mbits; c.gain = f.gain * f.mid; c.fill = f.fill;
+            }
+            f.stage = 2;
+            sp++;
+        } else {
+            ret = f.mid_first ? (f.cm | ret << (f.B0 >> 1)) : (f.cm | ret);
+            sp--;
+        }
+      }
+      if (at_leaf) {
+            ObPartFrame &f = st[sp];
+            const uint8_t *cache = ob_pcache(ctx.band, f.LM);
+            {
                 // leaf: bands.c:1038-1103
                 uint32_t cm = 0;
                 int q = ob_bits2pulses(cache, f.b);
@@ -632,27 +664,7 @@ OB_DEV_NOINLINE uint32_t ob_decode_partition(ObBandCtx &ctx, int off, int N, int
                 ret = cm;
                 sp--;
             }
-        } else if (f.stage == 1) {
-            // first child done: rebalance (bands.c:1017-1035) and launch the second
-            ObPartFrame &c = st[sp + 1];
-            c.N = f.N; c.B = f.B; c.LM = f.LM; c.stage = 0;
-            if (f.mid_first) {
-                f.cm = ret;
-                int32_t rb = f.mbits - (f.rebalance - ctx.remaining_bits);
-                if (rb > 3 << OB_BITRES && f.itheta != 0) f.sbits += rb - (3 << OB_BITRES);
-                c.off = (int16_t)(f.off + f.N); c.b = f.sbits; c.gain = f.gain * f.side; c.fill = f.fill >> f.B;
-            } else {
-                f.cm = ret << (f.B0 >> 1);
-                int32_t rb = f.sbits - (f.rebalance - ctx.remaining_bits);
-                if (rb > 3 << OB_BITRES && f.itheta != 16384) f.mbits += rb - (3 << OB_BITRES);
-                c.off = f.off; c.b = f.mbits; c.gain = f.gain * f.mid; c.fill = f.fill;
-            }
-            f.stage = 2;
-            sp++;
-        } else {
-            ret = f.mid_first ? (f.cm | ret << (f.B0 >> 1)) : (f.cm | ret);
-            sp--;
-        }
+      }
     }
     return ret;
 }
