@@ -579,7 +579,11 @@ OB_DEV_NOINLINE uint32_t ob_enc_partition(ObEncBandCtx &ctx, float *X0, int N0, 
     int sp = 0;
     uint32_t ret = 0;
     st[0].X = X0; st[0].lowband = lowband0; st[0].N = N0; st[0].b = b0; st[0].B = Bin; st[0].LM = LM0; st[0].gain = gain0; st[0].fill = fill0; st[0].stage = 0;
+    // Two alternating phases, as in the decoder's symbol kernel: every thread first walks its cheap split / merge states until it
+    // stands on a leaf, then the threads of the warp run the expensive leaf (PVQ search, rotation, index coding) together.
     while (sp >= 0) {
+      bool at_leaf = false;
+      while (sp >= 0 && !at_leaf) {
         ObEncPartFrame &f = st[sp];
         if (f.stage == 0) {
             const uint8_t *cache = ob_pcache(ctx.band, f.LM);
@@ -610,7 +614,32 @@ OB_DEV_NOINLINE uint32_t ob_enc_partition(ObEncBandCtx &ctx, float *X0, int N0, 
                 c.N = n; c.B = B1; c.LM = lm; c.stage = 0;
                 if (f.mid_first) { c.X = f.X; c.lowband = f.lowband; c.b = f.mbits; c.gain = f.gain * f.mid; c.fill = fl; }
                 else { c.X = f.X + n; c.lowband = f.lowband ? f.lowband + n : nullptr; c.b = f.sbits; c.gain = f.gain * f.side; c.fill = fl >> B1; }
+            } else at_leaf = true;
+        } else if (f.stage == 1) {
+            ObEncPartFrame &c = st[sp + 1];
+            c.N = f.N; c.B = f.B; c.LM = f.LM; c.stage = 0;
+            if (f.mid_first) {
+                f.cm = ret;
+                const int32_t rb = f.mbits - (f.rebalance - ctx.remaining_bits);
+                if (rb > 3 << OB_BITRES && f.itheta != 0) f.sbits += rb - (3 << OB_BITRES);
+                c.X = f.X + f.N; c.lowband = f.lowband ? f.lowband + f.N : nullptr; c.b = f.sbits; c.gain = f.gain * f.side; c.fill = f.fill >> f.B;
             } else {
+                f.cm = ret << (f.B0 >> 1);
+                const int32_t rb = f.sbits - (f.rebalance - ctx.remaining_bits);
+                if (rb > 3 << OB_BITRES && f.itheta != 16384) f.mbits += rb - (3 << OB_BITRES);
+                c.X = f.X; c.lowband = f.lowband; c.b = f.mbits; c.gain = f.gain * f.mid; c.fill = f.fill;
+            }
+            f.stage = 2;
+            sp++;
+        } else {
+            ret = f.mid_first ? (f.cm | ret << (f.B0 >> 1)) : (f.cm | ret);
+            sp--;
+        }
+      }
+      if (at_leaf) {
+            ObEncPartFrame &f = st[sp];
+            const uint8_t *cache = ob_pcache(ctx.band, f.LM);
+            {
                 uint32_t cm = 0;
                 int q = ob_bits2pulses(cache, f.b);
                 int curr_bits = ob_pulses2bits(cache, q);
@@ -646,26 +675,7 @@ OB_DEV_NOINLINE uint32_t ob_enc_partition(ObEncBandCtx &ctx, float *X0, int N0, 
                 ret = cm;
                 sp--;
             }
-        } else if (f.stage == 1) {
-            ObEncPartFrame &c = st[sp + 1];
-            c.N = f.N; c.B = f.B; c.LM = f.LM; c.stage = 0;
-            if (f.mid_first) {
-                f.cm = ret;
-                const int32_t rb = f.mbits - (f.rebalance - ctx.remaining_bits);
-                if (rb > 3 << OB_BITRES && f.itheta != 0) f.sbits += rb - (3 << OB_BITRES);
-                c.X = f.X + f.N; c.lowband = f.lowband ? f.lowband + f.N : nullptr; c.b = f.sbits; c.gain = f.gain * f.side; c.fill = f.fill >> f.B;
-            } else {
-                f.cm = ret << (f.B0 >> 1);
-                const int32_t rb = f.sbits - (f.rebalance - ctx.remaining_bits);
-                if (rb > 3 << OB_BITRES && f.itheta != 16384) f.mbits += rb - (3 << OB_BITRES);
-                c.X = f.X; c.lowband = f.lowband; c.b = f.mbits; c.gain = f.gain * f.mid; c.fill = f.fill;
-            }
-            f.stage = 2;
-            sp++;
-        } else {
-            ret = f.mid_first ? (f.cm | ret << (f.B0 >> 1)) : (f.cm | ret);
-            sp--;
-        }
+      }
     }
     return ret;
 }
