@@ -76,6 +76,9 @@ int32_t ob_decode_multi(ObDecoder *dec, int32_t n_frames, const uint8_t *packets
 int32_t ob_decode_float_multi_async(ObDecoder *dec, int32_t n_frames, const uint8_t *packets, const int32_t *offsets,
                                     const int32_t *lens, float *pcm_out, int32_t frame_size, int32_t *samples_out,
                                     uint32_t *ranges_out);
+int32_t ob_decode_multi_async(ObDecoder *dec, int32_t n_frames, const uint8_t *packets, const int32_t *offsets,
+                              const int32_t *lens, int16_t *pcm_out, int32_t frame_size, int32_t *samples_out,
+                              uint32_t *ranges_out);                     /* the int16 form: half the bytes over PCIe */
 int32_t ob_decoder_wait(ObDecoder *dec, int32_t keep_in_flight);
 
 /* Same, with every pointer a DEVICE pointer on the decoder's device (inputs already resident in HBM, outputs

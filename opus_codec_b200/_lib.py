@@ -18,7 +18,7 @@ SYMBOLS = [
     "ob_decoder_create", "ob_decoder_destroy", "ob_decode_float", "ob_decode_float_multi", "ob_decode_float_device",
     "ob_decoder_final_range", "ob_decoder_reset", "ob_decoder_last_packet_duration", "ob_decoder_streams",
     "ob_decoder_channels", "ob_decoder_kernel_ms", "ob_decoder_launches", "ob_decoder_cuda_stream",
-    "ob_decode_float_multi_async", "ob_decoder_wait", "ob_decode", "ob_decode_multi", "ob_encode", "ob_encode_multi", "ob_decoder_set_gain", "ob_decoder_get_gain", "ob_decoder_set_phase_inversion_disabled", "ob_decoder_get_phase_inversion_disabled",
+    "ob_decode_float_multi_async", "ob_decoder_wait", "ob_decode", "ob_decode_multi", "ob_decode_multi_async", "ob_encode", "ob_encode_multi", "ob_decoder_set_gain", "ob_decoder_get_gain", "ob_decoder_set_phase_inversion_disabled", "ob_decoder_get_phase_inversion_disabled",
     "ob_packet_get_nb_channels", "ob_packet_get_samples_per_frame", "ob_packet_get_bandwidth", "ob_packet_get_nb_frames",
     "ob_version", "ob_strerror",
     "ob_encoder_create", "ob_encoder_destroy", "ob_encode_float", "ob_encode_float_multi", "ob_encode_float_device",
@@ -68,6 +68,7 @@ def lib():
     L.ob_encode_multi.argtypes = [vp, i32, vp, i32, vp, i32, vp, vp]; L.ob_encode_multi.restype = i32
     L.ob_decode.argtypes = [vp, vp, vp, vp, vp, i32, vp]; L.ob_decode.restype = i32
     L.ob_decode_multi.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp]; L.ob_decode_multi.restype = i32
+    L.ob_decode_multi_async.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp]; L.ob_decode_multi_async.restype = i32
     L.ob_decode_float_device.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, i32]; L.ob_decode_float_device.restype = i32
     L.ob_decoder_final_range.argtypes = [vp, vp]; L.ob_decoder_final_range.restype = i32
     L.ob_decoder_reset.argtypes = [vp, vp, i32]; L.ob_decoder_reset.restype = i32

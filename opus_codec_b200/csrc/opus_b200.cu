@@ -537,6 +537,11 @@ int32_t ob_decode_multi(ObDecoder *d, int32_t n_frames, const uint8_t *packets, 
 {
     return ob_decode_submit(d, n_frames, packets, offsets, lens, nullptr, pcm_out, frame_size, samples_out, ranges_out, 1);
 }
+int32_t ob_decode_multi_async(ObDecoder *d, int32_t n_frames, const uint8_t *packets, const int32_t *offsets, const int32_t *lens,
+                              int16_t *pcm_out, int32_t frame_size, int32_t *samples_out, uint32_t *ranges_out)
+{
+    return ob_decode_submit(d, n_frames, packets, offsets, lens, nullptr, pcm_out, frame_size, samples_out, ranges_out, 0);
+}
 int32_t ob_decode(ObDecoder *d, const uint8_t *packets, const int32_t *offsets, const int32_t *lens, int16_t *pcm_out, int32_t frame_size, int32_t *samples_out)
 {
     return ob_decode_submit(d, 1, packets, offsets, lens, nullptr, pcm_out, frame_size, samples_out, nullptr, 1);
