@@ -339,6 +339,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     numa = bind_to_gpu_numa(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL would print its version banner on stdout, in front of the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))   # plumbing only: barrier + max-reduce of timings
     L = _lib.lib()
     S, F = STREAMS_PER_GPU, args.frames
