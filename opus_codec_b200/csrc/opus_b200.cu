@@ -302,7 +302,7 @@ ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
     int err = OB_OK;
     ObDecoder *d = nullptr;
     int ndev = 0;
-    if (n_streams <= 0 || (channels != 1 && channels != 2) || max_frames <= 0) err = OB_BAD_ARG;
+    if (n_streams <= 0 || (channels != 1 && channels != 2) || max_frames <= 0 || max_frames > 65535) err = OB_BAD_ARG;   // ObSlot.pkt is 16 bits
     else if (fs != 48000 && fs != 24000 && fs != 16000 && fs != 12000 && fs != 8000) err = OB_BAD_ARG;     // opus_decoder_init, opus_decoder.c:130-131
     else if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
         fprintf(stderr, "opus_b200: no usable CUDA device (count=%d, requested=%d); there is no CPU fallback\n", ndev, device);

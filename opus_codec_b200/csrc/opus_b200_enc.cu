@@ -167,10 +167,9 @@ ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         ok = ok && cudaMalloc(&e->d_info, sizeof(ObAnalysisInfo) * total) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_lens, sizeof(int32_t) * total) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_ranges, sizeof(uint32_t) * total) == cudaSuccess;
-        // the per-thread encoder recurses (quant_partition, <= 5 deep) and keeps band-sized arrays on its stack
-        size_t stack_bytes = sizeof(ObEncScratch) + sizeof(ObEncStream) + 72 * 1024;   // kernel frame + the recursive band coder (measured: 28 KB is not enough for stereo)
-        if (const char *v = getenv("OB_ENC_STACK_KB")) { const int t = atoi(v); if (t >= 4 && t <= 500) stack_bytes = (size_t)t * 1024; }   // debugging aid
-        ok = ok && cudaDeviceSetLimit(cudaLimitStackSize, stack_bytes) == cudaSuccess;
+        // No cudaLimitStackSize change: the kernel has no recursion or indirect calls, so its whole local frame (~94 KB per thread) is
+        // known at compile time and sized by the driver at launch; the process-wide stack limit (and with it the local-memory
+        // reservation of every other kernel in the process, e.g. the decoder's) stays at its default.
         if (!ok) {
             fprintf(stderr, "opus_b200: device allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
             ob_encoder_destroy(e); e = nullptr; err = OB_ALLOC_FAIL;
