@@ -136,7 +136,10 @@ void ob_encoder_destroy(ObEncoder *enc);
 
 /* n x opus_encode_float(st, pcm, frame_size, data, max_data_bytes) (src/bindings.rs:325-334; Encoder::encode_float
  * src/encoder.rs:215-247): one frame per stream.  pcm: host, [n_streams][frame_size*channels] interleaved floats in [-1,1];
- * out: host, [n_streams][max_bytes]; lens_out[s]: packet length (TOC included) or a negative OPUS_* code. */
+ * out: host, [n_streams][max_bytes]; lens_out[s]: packet length (TOC included) or a negative OPUS_* code.
+ * frame_size (samples per channel at 48 kHz): 120, 240, 480, 960, or 1920 / 2880 / 3840 / 4800 / 5760 (FrameSize::Ms40 ... 120 ms,
+ * src/types.rs): the long ones are coded as 20 ms CELT frames and merged into one code-1/2/3 packet like
+ * opus_encode_native's multi-frame branch (opus/src/opus_encoder.c:1649-1795, repacketizer.c:138-330). */
 int32_t ob_encode_float(ObEncoder *enc, const float *pcm, int32_t frame_size, uint8_t *out, int32_t max_bytes, int32_t *lens_out);
 /* n_frames consecutive frames per stream: pcm [n_streams][n_frames][frame_size*channels], out [n_streams][n_frames][max_bytes],
  * lens_out / ranges_out [n_streams][n_frames] (ranges_out optional: OPUS_GET_FINAL_RANGE after each frame). */

@@ -44,6 +44,7 @@ struct ObEncScratch {
     float pcm_hp[2 * OB_MAX_N];                       // dc_reject output
     ObEncBandsScratch bands;
     uint8_t coarse_save[1280];
+    uint8_t multi_tmp[1284];                          // the 20 ms frames of a 40-120 ms packet before they are repacketized
 };
 
 OB_DEV void ob_enc_reset(ObEncState &st)
@@ -462,85 +463,13 @@ OB_DEV void ob_stereo_fade(float *buf, float g1, float g2, int frame_size)     /
     }
 }
 
-// opus_encode_float -> opus_encode_native -> opus_encode_frame_native for one 2.5/5/10/20 ms frame, CELT-only
-// (opus_encoder.c:1057-1696, :1698-2459; the lines this path executes are listed in SURVEY 8a).  data: out_bytes capacity.
-// Returns the packet length in bytes (TOC included) or a negative OPUS_* code.
-// pre_info: the frame's AnalysisInfo when the analysis ran ahead of the encoder in its own kernel (ob_k_analysis); nullptr: run it
-// inline on os.tonal.
-OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, ObEncState &st, ObEncScratch &S, const float *pcm, int frame_size,
-        uint8_t *data, int out_bytes, const ObAnalysisInfo *pre_info = nullptr)
+// opus_encode_frame_native (opus_encoder.c:1698-2459) for one 2.5/5/10/20 ms frame, CELT-only: DC reject, stereo fade, CELT, TOC.
+// data: max_data_bytes of room for TOC + payload.  bitrate_bps / equiv_rate: the packet-level values (a frame of a multi-frame packet
+// inherits them).  Returns the frame's packet length (TOC included) or a negative OPUS_* code.
+OB_DEV_NOINLINE int ob_opus_encode_frame(const ObOpusEncCfg &cfg, ObOpusEncState &os, ObEncState &st, ObEncScratch &S, const float *pcm, int frame_size,
+        uint8_t *data, int max_data_bytes, int32_t bitrate_bps, int32_t equiv_rate, const ObAnalysisInfo &analysis_info)
 {
-    const int channels = st.channels, Fs = 48000;
-    if (frame_size != 120 && frame_size != 240 && frame_size != 480 && frame_size != 960) return OB_BAD_ARG;   // > 20 ms needs the repacketizer
-    int max_data_bytes = ob_imin(1276, out_bytes);
-    if (max_data_bytes <= 0) return OB_BAD_ARG;
-    const int frame_rate = Fs / frame_size;
-    int32_t bitrate_bps;
-    if (cfg.bitrate == -1000) bitrate_bps = 60 * Fs / frame_size + Fs * channels;                              // user_bitrate_to_bitrate (:639-649)
-    else if (cfg.bitrate == -1) bitrate_bps = max_data_bytes * 8 * Fs / frame_size;
-    else bitrate_bps = cfg.bitrate;
-    if (!cfg.vbr) {                                                                                           // :1188-1197
-        const int frame_rate12 = 12 * Fs / frame_size;
-        const int cbr_bytes = ob_imin((12 * bitrate_bps / 8 + frame_rate12 / 2) / frame_rate12, max_data_bytes);
-        bitrate_bps = cbr_bytes * (int32_t)frame_rate12 * 8 / 12;
-        max_data_bytes = ob_imax(1, cbr_bytes);
-    }
-    // ---- signal analysis at complexity >= 7 (:1108-1176), on the caller's PCM, before anything else looks at the frame ----
-    ObAnalysisInfo analysis_info;
-    analysis_info.valid = 0;
-    {
-        const int lsb_depth = cfg.lsb_depth;
-        int is_silence = 0;
-        if (cfg.complexity >= 7) {
-            is_silence = ob_maxabs(pcm, frame_size * channels) <= (float)1 / (1 << lsb_depth);
-            if (pre_info) analysis_info = *pre_info;
-            else ob_run_analysis(*os.tonal, pcm, frame_size, channels, lsb_depth, analysis_info, S.pre);
-        } else if (os.tonal && os.tonal->initialized) ob_tonal_reset(*os.tonal);
-        if (!is_silence) os.voice_ratio = -1;
-        os.detected_bandwidth = 0;
-        if (analysis_info.valid) {
-            const float prob = os.first ? analysis_info.music_prob : analysis_info.music_prob_max;           // prev_mode == 0 : == MODE_CELT_ONLY
-            os.voice_ratio = (int)floor(.5 + (double)(100 * (1 - prob)));
-            const int ab = analysis_info.bandwidth;
-            os.detected_bandwidth = ab <= 12 ? 1101 : ab <= 14 ? 1102 : ab <= 16 ? 1103 : ab <= 18 ? 1104 : 1105;
-        }
-    }
-    if (max_data_bytes < 3 || bitrate_bps < 3 * frame_rate * 8) return OB_UNIMPLEMENTED;                       // the "PLC frame" corner (:1202-1266)
-    int32_t equiv_rate = ob_compute_equiv_rate(bitrate_bps, channels, frame_rate, cfg.vbr, 0, cfg.complexity, cfg.packet_loss);
-    const int voice_est = os.voice_ratio >= 0 ? os.voice_ratio * 327 >> 8 : 48;                               // :1276-1289, signal AUTO, application neither VOIP nor AUDIO
-    if (cfg.force_channels > 0 && channels == 2) os.stream_channels = cfg.force_channels;
-    else if (channels == 2) {
-        int32_t stereo_threshold = 17000 + ((voice_est * voice_est * (19000 - 17000)) >> 14);
-        if (os.stream_channels == 2) stereo_threshold -= 1000; else stereo_threshold += 1000;
-        os.stream_channels = (equiv_rate > stereo_threshold) ? 2 : 1;
-    } else os.stream_channels = channels;
-    equiv_rate = ob_compute_equiv_rate(bitrate_bps, os.stream_channels, frame_rate, cfg.vbr, 1, cfg.complexity, cfg.packet_loss);
-    {   // automatic bandwidth (:1440-1490); voice and music tables differ only for WB<->SWB and SWB<->FB
-        const int32_t voice_thr[8] = {9000, 700, 9000, 700, 13500, 1000, 14000, 2000}, music_thr[8] = {9000, 700, 9000, 700, 11000, 1000, 12000, 2000};
-        int bandwidth = 1105;
-        do {
-            const int k = 2 * (bandwidth - 1102);
-            int threshold = music_thr[k] + ((voice_est * voice_est * (voice_thr[k] - music_thr[k])) >> 14);
-            const int hysteresis = music_thr[k + 1] + ((voice_est * voice_est * (voice_thr[k + 1] - music_thr[k + 1])) >> 14);
-            if (!os.first) { if (os.auto_bandwidth >= bandwidth) threshold -= hysteresis; else threshold += hysteresis; }
-            if (equiv_rate >= threshold) break;
-        } while (--bandwidth > 1101);
-        if (bandwidth == 1102) bandwidth = 1103;
-        os.bandwidth = os.auto_bandwidth = bandwidth;
-    }
-    if (os.bandwidth > cfg.max_bandwidth) os.bandwidth = cfg.max_bandwidth;
-    if (cfg.user_bandwidth > 0) os.bandwidth = cfg.user_bandwidth;
-    if (os.detected_bandwidth && cfg.user_bandwidth <= 0) {                                                   // :1510-1530
-        int min_detected;
-        if (equiv_rate <= 18000 * os.stream_channels) min_detected = 1101;
-        else if (equiv_rate <= 24000 * os.stream_channels) min_detected = 1102;
-        else if (equiv_rate <= 30000 * os.stream_channels) min_detected = 1103;
-        else if (equiv_rate <= 44000 * os.stream_channels) min_detected = 1104;
-        else min_detected = 1105;
-        os.detected_bandwidth = ob_imax(os.detected_bandwidth, min_detected);
-        os.bandwidth = ob_imin(os.bandwidth, os.detected_bandwidth);
-    }
-    if (os.bandwidth == 1102) os.bandwidth = 1103;
+    const int channels = st.channels, frame_rate = 48000 / frame_size;
     const int curr_bandwidth = os.bandwidth;
 
     ObRangeEnc enc;
@@ -585,4 +514,168 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
     ret += 1;
     if (!cfg.vbr && ret != max_data_bytes) return OB_UNIMPLEMENTED;     // opus_packet_pad: CELT CBR always fills its budget on this path
     return ret;
+}
+
+// opus_encode_float -> opus_encode_native -> opus_encode_frame_native for one packet of 2.5 ... 120 ms, CELT-only
+// (opus_encoder.c:1057-1696, :1698-2459; the lines this path executes are listed in SURVEY 8a).  data: out_bytes capacity.
+// Returns the packet length in bytes (TOC included) or a negative OPUS_* code.
+// pre_info: the frame's AnalysisInfo when the analysis ran ahead of the encoder in its own kernel (ob_k_analysis); nullptr: run it
+// inline on os.tonal.
+OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, ObEncState &st, ObEncScratch &S, const float *pcm, int frame_size,
+        uint8_t *data, int out_bytes, const ObAnalysisInfo *pre_info = nullptr)
+{
+    const int channels = st.channels, Fs = 48000;
+    if (frame_size != 120 && frame_size != 240 && frame_size != 480 && (frame_size % 960 != 0 || frame_size <= 0 || frame_size > 5760)) return OB_BAD_ARG;
+    int max_data_bytes = ob_imin(1276, out_bytes);
+    if (max_data_bytes <= 0) return OB_BAD_ARG;
+    const int frame_rate = Fs / frame_size;
+    int32_t bitrate_bps;
+    int cbr_bytes = -1;
+    if (cfg.bitrate == -1000) bitrate_bps = 60 * Fs / frame_size + Fs * channels;                              // user_bitrate_to_bitrate (:639-649)
+    else if (cfg.bitrate == -1) bitrate_bps = max_data_bytes * 8 * Fs / frame_size;
+    else bitrate_bps = cfg.bitrate;
+    if (!cfg.vbr) {                                                                                           // :1188-1197
+        const int frame_rate12 = 12 * Fs / frame_size;
+        cbr_bytes = ob_imin((12 * bitrate_bps / 8 + frame_rate12 / 2) / frame_rate12, max_data_bytes);
+        bitrate_bps = cbr_bytes * (int32_t)frame_rate12 * 8 / 12;
+        max_data_bytes = ob_imax(1, cbr_bytes);
+    }
+    // ---- signal analysis at complexity >= 7 (:1108-1176), on the caller's PCM, before anything else looks at the frame ----
+    ObAnalysisInfo analysis_info;
+    analysis_info.valid = 0;
+    int read_pos_bak = -1, read_subframe_bak = -1;
+    {
+        const int lsb_depth = cfg.lsb_depth;
+        int is_silence = 0;
+        if (cfg.complexity >= 7) {
+            is_silence = ob_maxabs(pcm, frame_size * channels) <= (float)1 / (1 << lsb_depth);
+            if (pre_info) analysis_info = *pre_info;
+            else {
+                read_pos_bak = os.tonal->read_pos; read_subframe_bak = os.tonal->read_subframe;
+                ob_run_analysis(*os.tonal, pcm, frame_size, channels, lsb_depth, analysis_info, S.pre);
+            }
+        } else if (os.tonal && os.tonal->initialized) ob_tonal_reset(*os.tonal);
+        if (!is_silence) os.voice_ratio = -1;
+        os.detected_bandwidth = 0;
+        if (analysis_info.valid) {
+            const float prob = os.first ? analysis_info.music_prob : analysis_info.music_prob_max;           // prev_mode == 0 : == MODE_CELT_ONLY
+            os.voice_ratio = (int)floor(.5 + (double)(100 * (1 - prob)));
+            const int ab = analysis_info.bandwidth;
+            os.detected_bandwidth = ab <= 12 ? 1101 : ab <= 14 ? 1102 : ab <= 16 ? 1103 : ab <= 18 ? 1104 : 1105;
+        }
+    }
+    if (max_data_bytes < 3 || bitrate_bps < 3 * frame_rate * 8 || (frame_rate < 50 && (max_data_bytes * frame_rate < 300 || bitrate_bps < 2400)))
+        return OB_UNIMPLEMENTED;                                                                              // the "PLC frame" corner (:1202-1266)
+    int32_t equiv_rate = ob_compute_equiv_rate(bitrate_bps, channels, frame_rate, cfg.vbr, 0, cfg.complexity, cfg.packet_loss);
+    const int voice_est = os.voice_ratio >= 0 ? os.voice_ratio * 327 >> 8 : 48;                               // :1276-1289, signal AUTO, application neither VOIP nor AUDIO
+    if (cfg.force_channels > 0 && channels == 2) os.stream_channels = cfg.force_channels;
+    else if (channels == 2) {
+        int32_t stereo_threshold = 17000 + ((voice_est * voice_est * (19000 - 17000)) >> 14);
+        if (os.stream_channels == 2) stereo_threshold -= 1000; else stereo_threshold += 1000;
+        os.stream_channels = (equiv_rate > stereo_threshold) ? 2 : 1;
+    } else os.stream_channels = channels;
+    equiv_rate = ob_compute_equiv_rate(bitrate_bps, os.stream_channels, frame_rate, cfg.vbr, 1, cfg.complexity, cfg.packet_loss);
+    {   // automatic bandwidth (:1440-1490); voice and music tables differ only for WB<->SWB and SWB<->FB
+        const int32_t voice_thr[8] = {9000, 700, 9000, 700, 13500, 1000, 14000, 2000}, music_thr[8] = {9000, 700, 9000, 700, 11000, 1000, 12000, 2000};
+        int bandwidth = 1105;
+        do {
+            const int k = 2 * (bandwidth - 1102);
+            int threshold = music_thr[k] + ((voice_est * voice_est * (voice_thr[k] - music_thr[k])) >> 14);
+            const int hysteresis = music_thr[k + 1] + ((voice_est * voice_est * (voice_thr[k + 1] - music_thr[k + 1])) >> 14);
+            if (!os.first) { if (os.auto_bandwidth >= bandwidth) threshold -= hysteresis; else threshold += hysteresis; }
+            if (equiv_rate >= threshold) break;
+        } while (--bandwidth > 1101);
+        if (bandwidth == 1102) bandwidth = 1103;
+        os.bandwidth = os.auto_bandwidth = bandwidth;
+    }
+    if (os.bandwidth > cfg.max_bandwidth) os.bandwidth = cfg.max_bandwidth;
+    if (cfg.user_bandwidth > 0) os.bandwidth = cfg.user_bandwidth;
+    if (os.detected_bandwidth && cfg.user_bandwidth <= 0) {                                                   // :1510-1530
+        int min_detected;
+        if (equiv_rate <= 18000 * os.stream_channels) min_detected = 1101;
+        else if (equiv_rate <= 24000 * os.stream_channels) min_detected = 1102;
+        else if (equiv_rate <= 30000 * os.stream_channels) min_detected = 1103;
+        else if (equiv_rate <= 44000 * os.stream_channels) min_detected = 1104;
+        else min_detected = 1105;
+        os.detected_bandwidth = ob_imax(os.detected_bandwidth, min_detected);
+        os.bandwidth = ob_imin(os.bandwidth, os.detected_bandwidth);
+    }
+    if (os.bandwidth == 1102) os.bandwidth = 1103;
+    if (frame_size <= 960) return ob_opus_encode_frame(cfg, os, st, S, pcm, frame_size, data, max_data_bytes, bitrate_bps, equiv_rate, analysis_info);
+
+    // ---- 40-120 ms: 20 ms frames encoded one by one and repacketized into one code-1/2/3 packet (opus_encoder.c:1551-1679,
+    // opus_repacketizer_out_range_impl, repacketizer.c:112-320) ----
+    const int nb_frames = frame_size / 960;
+    if (read_pos_bak != -1) { os.tonal->read_pos = read_pos_bak; os.tonal->read_subframe = read_subframe_bak; }     // the analysis is read one frame at a time
+    const int max_header_bytes = nb_frames == 2 ? 3 : (2 + (nb_frames - 1) * 2);
+    const int repacketize_len = (cfg.vbr || cfg.bitrate == -1) ? out_bytes : ob_imin(cbr_bytes, out_bytes);
+    const int max_len_sum = nb_frames + repacketize_len - max_header_bytes;
+    if (max_len_sum > (int)sizeof(S.multi_tmp) || max_len_sum < nb_frames) return OB_BUFFER_TOO_SMALL;
+    uint8_t *curr_data = S.multi_tmp;
+    int16_t flen[6];
+    int tot = 0;
+    for (int i = 0; i < nb_frames; i++) {
+        int curr_max = ob_imin(3 * bitrate_bps / (3 * 8 * 48000 / 960), max_len_sum / nb_frames);
+        curr_max = ob_imin(max_len_sum - tot, curr_max);
+        if (read_pos_bak != -1) ob_tonality_get_info(*os.tonal, analysis_info, 960);
+        const int tmp_len = ob_opus_encode_frame(cfg, os, st, S, pcm + (size_t)i * channels * 960, 960, curr_data, curr_max, bitrate_bps, equiv_rate, analysis_info);
+        if (tmp_len < 0) return OB_INTERNAL_ERROR;
+        flen[i] = (int16_t)(tmp_len - 1);                           // opus_repacketizer_cat: the frame without its TOC
+        tot += tmp_len;
+        curr_data += tmp_len;
+    }
+    const int toc = S.multi_tmp[0] & 0xFC, pad = !cfg.vbr, maxlen = repacketize_len;
+    uint8_t *ptr = data;
+    int tot_size = 0;
+    if (nb_frames == 2) {
+        if (flen[1] == flen[0]) { tot_size = 2 * flen[0] + 1; if (tot_size > maxlen) return OB_INTERNAL_ERROR; *ptr++ = (uint8_t)(toc | 1); }
+        else {
+            tot_size = flen[0] + flen[1] + 2 + (flen[0] >= 252);
+            if (tot_size > maxlen) return OB_INTERNAL_ERROR;
+            *ptr++ = (uint8_t)(toc | 2);
+            if (flen[0] < 252) *ptr++ = (uint8_t)flen[0];
+            else { *ptr++ = (uint8_t)(252 + (flen[0] & 3)); *ptr++ = (uint8_t)((flen[0] - (252 + (flen[0] & 3))) >> 2); }
+        }
+    }
+    if (nb_frames > 2 || (pad && tot_size < maxlen)) {                // code 3
+        ptr = data;
+        int vbr = 0;
+        for (int i = 1; i < nb_frames; i++) if (flen[i] != flen[0]) { vbr = 1; break; }
+        if (vbr) {
+            tot_size = 2;
+            for (int i = 0; i < nb_frames - 1; i++) tot_size += 1 + (flen[i] >= 252) + flen[i];
+            tot_size += flen[nb_frames - 1];
+            if (tot_size > maxlen) return OB_INTERNAL_ERROR;
+            *ptr++ = (uint8_t)(toc | 3);
+            *ptr++ = (uint8_t)(nb_frames | 0x80);
+        } else {
+            tot_size = nb_frames * flen[0] + 2;
+            if (tot_size > maxlen) return OB_INTERNAL_ERROR;
+            *ptr++ = (uint8_t)(toc | 3);
+            *ptr++ = (uint8_t)nb_frames;
+        }
+        const int pad_amount = pad ? (maxlen - tot_size) : 0;
+        if (pad_amount != 0) {
+            data[1] |= 0x40;
+            const int nb_255s = (pad_amount - 1) / 255;
+            if (tot_size + nb_255s + 1 > maxlen) return OB_INTERNAL_ERROR;
+            for (int i = 0; i < nb_255s; i++) *ptr++ = 255;
+            *ptr++ = (uint8_t)(pad_amount - 255 * nb_255s - 1);
+            tot_size += pad_amount;
+        }
+        if (vbr) for (int i = 0; i < nb_frames - 1; i++) {
+            if (flen[i] < 252) *ptr++ = (uint8_t)flen[i];
+            else { *ptr++ = (uint8_t)(252 + (flen[i] & 3)); *ptr++ = (uint8_t)((flen[i] - (252 + (flen[i] & 3))) >> 2); }
+        }
+    }
+    {
+        const uint8_t *src = S.multi_tmp;
+        for (int i = 0; i < nb_frames; i++) {
+            src += 1;                                                // skip the frame's own TOC
+            for (int k = 0; k < flen[i]; k++) *ptr++ = src[k];
+            src += flen[i];
+        }
+    }
+    if (pad) while (ptr < data + maxlen) *ptr++ = 0;
+    return tot_size;
 }

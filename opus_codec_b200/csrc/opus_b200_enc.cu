@@ -27,8 +27,8 @@ struct ObEncStream {           // everything one stream owns on the device
 // a warp touched 32 different lines: 112 ms per frame at 16384 streams.)
 __global__ void __launch_bounds__(OB_ENC_THREADS)
 ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *__restrict__ lens, uint32_t *__restrict__ ranges,
-            ObEncStream *__restrict__ streams, const ObAnalysisInfo *__restrict__ info, ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes,
-            int lanes, int f0, int Fc)
+            ObEncStream *__restrict__ streams, const ObAnalysisInfo *__restrict__ info, ObTonalState *__restrict__ tonal, ObOpusEncCfg cfg, int S, int F,
+            int frame_size, int max_bytes, int lanes, int f0, int Fc)
 {
     // Only the first `lanes` threads of each warp carry a stream (tuning knob).  Spreading the streams over more, partly filled,
     // warps was tried to hide the local-memory latency this kernel is bound by (ncu: 0.26 warp-instructions/cycle/SM, 8.6 of 13
@@ -40,6 +40,7 @@ ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *_
     ObEncScratch sc;      // not initialised: no stage reads what it (or an earlier frame) has not written -- tests/test_host_emul.py runs the
                           // same code with the work area filled with NaN patterns before every frame
     ObEncStream es = streams[s];
+    es.os.tonal = tonal ? tonal + s : nullptr;                 // packets longer than 20 ms run the analysis inline, on the state in global memory
     const int CC = es.st.channels;
     // NOTE: the frame counter is deliberately volatile.  The loop body is one huge divergent region; with a plain `int f`
     // nvcc 12.9 keeps f in a UNIFORM register, and lanes that fall behind re-execute the shared increment -- frames get
@@ -245,7 +246,7 @@ int32_t ob_encoder_set_lsb_depth(ObEncoder *e, int32_t d) { if (!e || d < 8 || d
 // of window k+1 is already running beside it.  analysis_ahead: the caller has already enqueued the analysis of this window.
 static int ob_enc_analysis(ObEncoder *e, int F, const float *d_pcm, int frame_size, int f0, int Fc, int k, cudaEvent_t pcm_ready)
 {
-    if (e->cfg.complexity < 7) return OB_OK;
+    if (e->cfg.complexity < 7 || frame_size > 960) return OB_OK;   // long packets interleave analysis reads with their 20 ms frames: done inline
     if (pcm_ready) OB_CUDA(cudaStreamWaitEvent(e->an_stream, pcm_ready, 0));
     if (f0 == 0) OB_CUDA(cudaStreamWaitEvent(e->an_stream, e->enc_done, 0));       // d_info of the previous call has been consumed
     ob_k_analysis<<<(e->S + OB_ENC_THREADS - 1) / OB_ENC_THREADS, OB_ENC_THREADS, 0, e->an_stream>>>(d_pcm, e->d_tonal, e->d_info, e->S, F, frame_size, e->CC,
@@ -260,8 +261,9 @@ static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size
                          int f0 = 0, int Fc = -1, int k = 0)
 {
     if (Fc < 0) Fc = F;
-    const bool an = e->cfg.complexity >= 7;
-    if (!an && e->tonal_dirty) {                               // "else if (st->analysis.initialized) tonality_analysis_reset()" (opus_encoder.c:1131-1133)
+    const bool an = e->cfg.complexity >= 7 && frame_size <= 960, an_inline = e->cfg.complexity >= 7 && frame_size > 960;
+    if (an_inline) e->tonal_dirty = true;
+    if (e->cfg.complexity < 7 && e->tonal_dirty) {                               // "else if (st->analysis.initialized) tonality_analysis_reset()" (opus_encoder.c:1131-1133)
         ob_k_tonal_reset<<<e->S, 128, 0, e->stream>>>(e->d_tonal, nullptr, e->S, e->S);
         e->tonal_dirty = false;
         e->launches += 1;
@@ -270,8 +272,8 @@ static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size
     if (an) OB_CUDA(cudaStreamWaitEvent(e->stream, e->an_ev[k & 3], 0));
     int lanes = e->lanes;
     if (const char *v = getenv("OB_ENC_LANES")) { const int t = atoi(v); if (t >= 1 && t <= OB_ENC_THREADS) lanes = t; }   // tuning aid
-    ob_k_encode<<<(e->S + lanes - 1) / lanes, OB_ENC_THREADS, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, an ? e->d_info : nullptr, e->cfg,
-                                                                               e->S, F, frame_size, max_bytes, lanes, f0, Fc);
+    ob_k_encode<<<(e->S + lanes - 1) / lanes, OB_ENC_THREADS, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, an ? e->d_info : nullptr,
+                                                                               an_inline ? e->d_tonal : nullptr, e->cfg, e->S, F, frame_size, max_bytes, lanes, f0, Fc);
     if (f0 + Fc == F) { OB_CUDA(cudaEventRecord(e->ev[1], e->stream)); OB_CUDA(cudaEventRecord(e->enc_done, e->stream)); }
     OB_CUDA(cudaGetLastError());
     e->launches += 1;

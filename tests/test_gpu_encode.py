@@ -94,14 +94,16 @@ def _gpu_encode(pcm_batch, fs, ch, br, vbr, cx):
     with BatchEncoder(S, 48000, ch, device=0, max_frames=F) as enc:
         enc.set_bitrate(br); enc.set_complexity(cx); enc.set_vbr(vbr != 0); enc.set_vbr_constraint(vbr == 2)
         assert enc.bitrate() == br and enc.complexity() == cx and enc.vbr() == (vbr != 0)
-        out, lens, rng = enc.encode_float_multi(pcm_batch.reshape(S, F, fs * ch), fs)
+        out, lens, rng = enc.encode_float_multi(pcm_batch[:, :F * fs * ch].reshape(S, F, fs * ch), fs)
         assert (enc.final_range() == rng[:, -1]).all()
     return out, lens, rng
 
 
 CONFIGS = [(1, 64000, 960, 0, 5), (2, 96000, 960, 0, 6), (2, 96000, 960, 1, 5), (1, 24000, 480, 2, 6), (2, 64000, 240, 0, 5),
            (1, 48000, 120, 0, 4), (2, 24000, 960, 0, 3), (1, 12000, 960, 0, 6), (2, 128000, 960, 0, 0),
-           (2, 96000, 960, 0, 10), (1, 64000, 960, 1, 10), (2, 64000, 480, 2, 9), (1, 32000, 240, 0, 8), (2, 48000, 960, 1, 7)]
+           (2, 96000, 960, 0, 10), (1, 64000, 960, 1, 10), (2, 64000, 480, 2, 9), (1, 32000, 240, 0, 8), (2, 48000, 960, 1, 7),
+           # 40 / 60 / 120 ms packets: 20 ms CELT frames repacketized into one code-1/2/3 packet (opus_encoder.c:1649-1795)
+           (1, 64000, 1920, 0, 10), (2, 96000, 2880, 1, 10), (2, 64000, 1920, 0, 5), (1, 48000, 2880, 2, 6), (1, 32000, 5760, 1, 9)]
 
 
 @pytest.mark.parametrize("ch,br,fs,vbr,cx", CONFIGS)

@@ -180,7 +180,10 @@ def test_encoder_device_code_bit_identical_to_reference_celt_encoder(emul, have_
 
 @pytest.mark.parametrize("ch,br,fs,vbr,cx", [(1, 64000, 960, 0, 5), (2, 96000, 960, 0, 6), (2, 96000, 960, 1, 5), (1, 24000, 480, 2, 6), (2, 24000, 960, 0, 4), (1, 12000, 960, 0, 6),
                                              (2, 96000, 960, 0, 10), (1, 64000, 960, 0, 10), (2, 96000, 960, 1, 10), (1, 24000, 480, 2, 9), (2, 64000, 240, 0, 8),
-                                             (1, 48000, 120, 1, 7), (2, 24000, 960, 0, 10), (1, 12000, 960, 1, 10), (2, 510000, 960, 0, 10)])
+                                             (1, 48000, 120, 1, 7), (2, 24000, 960, 0, 10), (1, 12000, 960, 1, 10), (2, 510000, 960, 0, 10),
+                                             # 40 / 60 / 80 / 120 ms packets (FrameSize::Ms40, Ms60, ...): 20 ms CELT frames + repacketizer
+                                             (1, 64000, 1920, 0, 10), (2, 96000, 2880, 1, 10), (2, 64000, 1920, 0, 5), (1, 48000, 2880, 2, 6),
+                                             (2, 128000, 3840, 0, 10), (1, 32000, 5760, 1, 9)])
 def test_encoder_opus_layer_bit_identical_to_reference(emul, have_ref, ch, br, fs, vbr, cx):
     """opus_encode_float (RESTRICTED_LOWDELAY): TOC, byte budget, bandwidth / stereo decisions, dc_reject and -- at complexity >= 7 --
     the tonality analysis with its FFT, band statistics, bandwidth detector and GRU network: identical packets."""
