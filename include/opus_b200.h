@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define OB_ABI_VERSION 5
+#define OB_ABI_VERSION 6
 
 typedef struct ObDecoder ObDecoder;
 
@@ -184,6 +184,36 @@ int32_t ob_packet_get_nb_channels(const uint8_t *packet);
 int32_t ob_packet_get_samples_per_frame(const uint8_t *packet, int32_t fs);
 int32_t ob_packet_get_bandwidth(const uint8_t *packet);
 int32_t ob_packet_get_nb_frames(const uint8_t *packet, int32_t len);
+
+/* opus_packet_parse (src/bindings.rs; packet_parse src/packet.rs:162-215; opus/src/opus.c:194-360): returns the frame count (1..48) or an
+ * OPUS_* code; sizes[i] / frame_offsets[i] (optional; offsets from `packet`) describe frame i; *payload_offset = offset of frame 0. */
+int32_t ob_packet_parse(const uint8_t *packet, int32_t len, uint8_t *out_toc, int32_t *frame_offsets, int16_t *sizes, int32_t *payload_offset);
+/* opus_packet_pad / opus_packet_unpad (packet_pad / packet_unpad, src/packet.rs:220-248; opus/src/repacketizer.c:283-353), in place.
+ * pad: OB_OK or an error; unpad: the new length.  Padding extensions (opus/src/extensions.c) are kept by pad and dropped by unpad. */
+int32_t ob_packet_pad(uint8_t *packet, int32_t len, int32_t new_len);
+int32_t ob_packet_unpad(uint8_t *packet, int32_t len);
+
+/* The repacketizer object: opus_repacketizer_create / _destroy / _init / _cat / _get_nb_frames / _out_range / _out
+ * (Repacketizer::new / drop / reset / push / frames / out_range / out, src/repacketizer.rs:18-100; opus/src/repacketizer.c:37-280).
+ * As in libopus the packets given to _cat are referenced, not copied: they must stay valid until the last _out call. */
+typedef struct ObRepacketizer ObRepacketizer;
+ObRepacketizer *ob_repacketizer_create(void);
+void ob_repacketizer_destroy(ObRepacketizer *rp);
+void ob_repacketizer_init(ObRepacketizer *rp);
+int32_t ob_repacketizer_cat(ObRepacketizer *rp, const uint8_t *packet, int32_t len);
+int32_t ob_repacketizer_get_nb_frames(ObRepacketizer *rp);
+int32_t ob_repacketizer_out_range(ObRepacketizer *rp, int32_t begin, int32_t end, uint8_t *out, int32_t maxlen);
+int32_t ob_repacketizer_out(ObRepacketizer *rp, uint8_t *out, int32_t maxlen);
+/* The same for a batch, on the GPU (a warp per output packet, payload bytes copied coalesced): every `group` consecutive packets of
+ * each stream are merged as  init; cat x group; out  would.  packets / offsets / lens as for ob_decode_float_multi
+ * ([n_streams][n_in]); out: [n_streams][ceil(n_in / group)][max_bytes]; lens_out: the packet length or the OPUS_* code of the first
+ * failing cat / of out.  pad_to > 0: every output is padded to exactly pad_to bytes (opus_packet_pad), else left as short as possible.
+ * Up to 128 padding extensions per output packet (OB_UNIMPLEMENTED beyond; the host object has no such limit).
+ * The _device form takes device pointers and a cudaStream_t and does not synchronise. */
+int32_t ob_repacketize_batch(int32_t device, int32_t n_streams, int32_t n_in, const uint8_t *packets, const int32_t *offsets, const int32_t *lens,
+                             int32_t group, int32_t pad_to, uint8_t *out, int32_t max_bytes, int32_t *lens_out);
+int32_t ob_repacketize_batch_device(int32_t n_streams, int32_t n_in, const uint8_t *d_packets, const int32_t *d_offsets, const int32_t *d_lens,
+                                    int32_t group, int32_t pad_to, uint8_t *d_out, int32_t max_bytes, int32_t *d_lens_out, void *cuda_stream);
 
 /* "1.5.2-b200.<abi>" : bitstream compatibility level + ABI version (cf. version() src/lib.rs:52-54). */
 const char *ob_version(void);

@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.environ.get("OB_LIB") or os.path.join(HERE, "libopus_b200.so")      # OB_LIB: tuning aid, points at an alternative build of the same library
 SRC = os.path.join(HERE, "csrc", "opus_b200.cu")
 SRC_ENC = os.path.join(HERE, "csrc", "opus_b200_enc.cu")       # compiled with -fmad=false (see the file header)
+SRC_PKT = os.path.join(HERE, "csrc", "opus_b200_pkt.cu")       # packet parse / pad / unpad, repacketizer (host objects + batched kernel)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 # Every symbol include/opus_b200.h declares (tests check that the library exports all of them).
@@ -21,6 +22,8 @@ SYMBOLS = [
     "ob_decode_float_multi_async", "ob_decoder_wait", "ob_decode", "ob_decode_multi", "ob_decode_multi_async", "ob_encode", "ob_encode_multi", "ob_decoder_set_gain", "ob_decoder_get_gain", "ob_decoder_set_phase_inversion_disabled", "ob_decoder_get_phase_inversion_disabled",
     "ob_packet_get_nb_channels", "ob_packet_get_samples_per_frame", "ob_packet_get_bandwidth", "ob_packet_get_nb_frames",
     "ob_version", "ob_strerror",
+    "ob_packet_parse", "ob_packet_pad", "ob_packet_unpad", "ob_repacketizer_create", "ob_repacketizer_destroy", "ob_repacketizer_init", "ob_repacketizer_cat",
+    "ob_repacketizer_get_nb_frames", "ob_repacketizer_out_range", "ob_repacketizer_out", "ob_repacketize_batch", "ob_repacketize_batch_device",
     "ob_encoder_create", "ob_encoder_destroy", "ob_encode_float", "ob_encode_float_multi", "ob_encode_float_device",
     "ob_encoder_set_bitrate", "ob_encoder_get_bitrate", "ob_encoder_set_complexity", "ob_encoder_get_complexity",
     "ob_encoder_set_vbr", "ob_encoder_get_vbr", "ob_encoder_set_vbr_constraint", "ob_encoder_get_vbr_constraint",
@@ -39,13 +42,14 @@ def build(verbose=False):
         return SO
     nvcc = os.environ.get("NVCC", "nvcc")
     extra = ["-Xptxas", "-v"] if verbose else []
-    o_dec, o_enc = os.path.join(HERE, "opus_b200.o"), os.path.join(HERE, "opus_b200_enc.o")
+    o_dec, o_enc, o_pkt = os.path.join(HERE, "opus_b200.o"), os.path.join(HERE, "opus_b200_enc.o"), os.path.join(HERE, "opus_b200_pkt.o")
     procs = [subprocess.Popen([nvcc] + NVCC_FLAGS + extra + ["-c", "-o", o_dec, SRC]),
-             subprocess.Popen([nvcc] + NVCC_FLAGS + extra + ["-fmad=false", "-c", "-o", o_enc, SRC_ENC])]
+             subprocess.Popen([nvcc] + NVCC_FLAGS + extra + ["-fmad=false", "-c", "-o", o_enc, SRC_ENC]),
+             subprocess.Popen([nvcc] + NVCC_FLAGS + extra + ["-c", "-o", o_pkt, SRC_PKT])]
     for p in procs:
         if p.wait() != 0:
             raise RuntimeError("nvcc failed")
-    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO, o_dec, o_enc], check=True)
+    subprocess.run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", SO, o_dec, o_enc, o_pkt], check=True)
     return SO
 
 
@@ -86,6 +90,18 @@ def lib():
         getattr(L, n).argtypes = [vp]; getattr(L, n).restype = i32
     L.ob_packet_get_samples_per_frame.argtypes = [vp, i32]; L.ob_packet_get_samples_per_frame.restype = i32
     L.ob_packet_get_nb_frames.argtypes = [vp, i32]; L.ob_packet_get_nb_frames.restype = i32
+    L.ob_packet_parse.argtypes = [vp, i32, vp, vp, vp, vp]; L.ob_packet_parse.restype = i32
+    L.ob_packet_pad.argtypes = [vp, i32, i32]; L.ob_packet_pad.restype = i32
+    L.ob_packet_unpad.argtypes = [vp, i32]; L.ob_packet_unpad.restype = i32
+    L.ob_repacketizer_create.argtypes = []; L.ob_repacketizer_create.restype = vp
+    L.ob_repacketizer_destroy.argtypes = [vp]; L.ob_repacketizer_destroy.restype = None
+    L.ob_repacketizer_init.argtypes = [vp]; L.ob_repacketizer_init.restype = None
+    L.ob_repacketizer_cat.argtypes = [vp, vp, i32]; L.ob_repacketizer_cat.restype = i32
+    L.ob_repacketizer_get_nb_frames.argtypes = [vp]; L.ob_repacketizer_get_nb_frames.restype = i32
+    L.ob_repacketizer_out_range.argtypes = [vp, i32, i32, vp, i32]; L.ob_repacketizer_out_range.restype = i32
+    L.ob_repacketizer_out.argtypes = [vp, vp, i32]; L.ob_repacketizer_out.restype = i32
+    L.ob_repacketize_batch.argtypes = [i32, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp]; L.ob_repacketize_batch.restype = i32
+    L.ob_repacketize_batch_device.argtypes = [i32, i32, vp, vp, vp, i32, i32, vp, i32, vp, vp]; L.ob_repacketize_batch_device.restype = i32
     L.ob_encoder_create.argtypes = [i32, i32, i32, i32, i32, i32, i32p]; L.ob_encoder_create.restype = vp
     L.ob_encoder_destroy.argtypes = [vp]; L.ob_encoder_destroy.restype = None
     L.ob_encode_float.argtypes = [vp, vp, i32, vp, i32, vp]; L.ob_encode_float.restype = i32

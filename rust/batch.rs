@@ -41,6 +41,9 @@ unsafe extern "C" {
     pub fn ob_encoder_set_vbr_constraint(enc: *mut ObEncoder, cvbr: i32) -> i32;
     pub fn ob_encoder_final_range(enc: *mut ObEncoder, out: *mut u32) -> i32;
     pub fn ob_encoder_reset(enc: *mut ObEncoder, idx: *const i32, n: i32) -> i32;
+
+    pub fn ob_repacketize_batch(device: i32, n_streams: i32, n_in: i32, packets: *const u8, offsets: *const i32, lens: *const i32,
+                                group: i32, pad_to: i32, out: *mut u8, max_bytes: i32, lens_out: *mut i32) -> i32;
 }
 
 #[repr(C)]
@@ -229,4 +232,25 @@ impl Drop for BatchEncoder {
     fn drop(&mut self) {
         unsafe { ob_encoder_destroy(self.raw.as_ptr()) }
     }
+}
+
+/// Batched form of `Repacketizer` (src/repacketizer.rs:11-100): every `group` consecutive packets of each stream are merged into
+/// one packet (`reset(); push() x group; out()`), on the GPU. `packets` / `offsets` / `lens` are laid out as for
+/// `BatchDecoder::decode_float_multi` (`[n_streams][n_in]`). Returns one `Result<Vec<u8>>` per (stream, group).
+pub fn repacketize_batch(device: i32, n_streams: usize, n_in: usize, packets: &[u8], offsets: &[i32], lens: &[i32], group: usize,
+                         pad_to: usize, max_bytes: usize) -> Result<Vec<Result<Vec<u8>>>> {
+    if offsets.len() != n_streams * n_in || lens.len() != offsets.len() || group == 0 || max_bytes == 0 {
+        return Err(Error::BadArg);
+    }
+    let n_out = n_streams * n_in.div_ceil(group);
+    let mut out = vec![0u8; n_out * max_bytes];
+    let mut lens_out = vec![0i32; n_out];
+    let rc = unsafe {
+        ob_repacketize_batch(device, n_streams as i32, n_in as i32, packets.as_ptr(), offsets.as_ptr(), lens.as_ptr(), group as i32,
+                             pad_to as i32, out.as_mut_ptr(), max_bytes as i32, lens_out.as_mut_ptr())
+    };
+    if rc != 0 { return Err(Error::from_code(rc)); }
+    Ok(lens_out.iter().enumerate().map(|(k, &n)| {
+        if n < 0 { Err(Error::from_code(n)) } else { Ok(out[k * max_bytes..k * max_bytes + n as usize].to_vec()) }
+    }).collect())
 }

@@ -1,0 +1,243 @@
+"""Packet byte work through the C ABI against the reference library's own functions (oracle/_ref): opus_packet_parse,
+opus_repacketizer_*, opus_packet_pad / _unpad, with padding extensions.  Results must be identical: counts, sizes, offsets, error
+codes and every output byte.  The host entry points need no GPU; the batched kernel is tested in test_gpu_decode.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden, multiframe_stream, repacketize
+
+
+@pytest.fixture(scope="module")
+def ref(have_ref):
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    L = refpy.lib_c()
+    vp, i32 = C.c_void_p, C.c_int32
+    L.opus_packet_parse.argtypes = [vp, i32, vp, vp, vp, vp]; L.opus_packet_parse.restype = C.c_int
+    L.opus_repacketizer_create.argtypes = []; L.opus_repacketizer_create.restype = vp
+    L.opus_repacketizer_destroy.argtypes = [vp]; L.opus_repacketizer_destroy.restype = None
+    L.opus_repacketizer_init.argtypes = [vp]; L.opus_repacketizer_init.restype = vp
+    L.opus_repacketizer_cat.argtypes = [vp, vp, i32]; L.opus_repacketizer_cat.restype = C.c_int
+    L.opus_repacketizer_get_nb_frames.argtypes = [vp]; L.opus_repacketizer_get_nb_frames.restype = C.c_int
+    L.opus_repacketizer_out_range.argtypes = [vp, C.c_int, C.c_int, vp, i32]; L.opus_repacketizer_out_range.restype = i32
+    L.opus_repacketizer_out.argtypes = [vp, vp, i32]; L.opus_repacketizer_out.restype = i32
+    L.opus_packet_pad.argtypes = [vp, i32, i32]; L.opus_packet_pad.restype = C.c_int
+    L.opus_packet_unpad.argtypes = [vp, i32]; L.opus_packet_unpad.restype = i32
+    return L
+
+
+def _buf(b, n=None):
+    n = max(1, len(b) if n is None else n)
+    a = (C.c_uint8 * n)()
+    C.memmove(a, bytes(b), len(b))
+    return a
+
+
+def ref_parse(L, pkt):
+    d = _buf(pkt)
+    toc = C.c_uint8(0); po = C.c_int(0)
+    frames = (C.c_void_p * 48)(); sizes = (C.c_int16 * 48)()
+    n = L.opus_packet_parse(d, len(pkt), C.byref(toc), frames, sizes, C.byref(po))
+    if n < 0:
+        return n, 0, 0, [], []
+    base = C.addressof(d)
+    return n, toc.value, po.value, [frames[i] - base for i in range(n)], list(sizes[:n])
+
+
+def ref_merge(L, pkts, begin=None, end=None, maxlen=8000):
+    """-> bytes, or the error code of the first failing cat / of out."""
+    rp = L.opus_repacketizer_create()
+    keep = []
+    try:
+        for p in pkts:
+            b = _buf(p); keep.append(b)
+            r = L.opus_repacketizer_cat(rp, b, len(p))
+            if r != 0:
+                return r
+        out = (C.c_uint8 * maxlen)()
+        n = L.opus_repacketizer_out(rp, out, maxlen) if begin is None else L.opus_repacketizer_out_range(rp, begin, end, out, maxlen)
+        return bytes(out[:n]) if n >= 0 else n
+    finally:
+        L.opus_repacketizer_destroy(rp)
+
+
+def our_merge(pkts, begin=None, end=None, maxlen=8000):
+    from opus_codec_b200.packet import Repacketizer
+    from opus_codec_b200.batch import OpusError
+    with Repacketizer() as rp:
+        try:
+            for p in pkts:
+                rp.push(p)
+            return rp.out(maxlen) if begin is None else rp.out_range(begin, end, maxlen)
+        except OpusError as e:
+            return e.code
+
+
+def sample_packets():
+    """Code 0-3 packets (padding, DTX frame inside) of every golden configuration."""
+    out = []
+    for name in golden_names():
+        g = load_golden(name)
+        pk, ln = g["packets"][0], g["lens"][0]
+        out += [bytes(pk[f, :ln[f]]) for f in range(min(6, pk.shape[0]))]
+        if pk.shape[0] >= 24:
+            out += [bytes(p) for p in multiframe_stream(g, 0, 7)]
+    return out
+
+
+def ext_padding():
+    """Padding bytes that carry extensions (opus/src/extensions.c): short ids with 0/1 byte, a frame separator, a long extension with an
+    explicit length, 0x01 filler, and a last long extension without length."""
+    return bytes([0x01, 0x01, (2 << 1) | 1, ord("a"), 0x02, (33 << 1) | 1, 5]) + b"HELLO" + bytes([(5 << 1) | 0, 0x03, 2, (40 << 1) | 0]) + b"tail-bytes"
+
+
+def with_padding(frames, padding):
+    """A code-3 VBR packet whose padding is `padding` (may hold extensions)."""
+    toc = frames[0][0] & 0xFC
+    body = [bytes(f[1:]) for f in frames]
+    out = bytes([toc | 3, 0x80 | 0x40 | len(body)])
+    p = len(padding)
+    while p > 254:
+        out += bytes([255]); p -= 254
+    out += bytes([p])
+    for b in body[:-1]:
+        n = len(b)
+        out += bytes([n]) if n < 252 else bytes([252 + (n & 3), (n - (252 + (n & 3))) >> 2])
+    return out + b"".join(body) + padding
+
+
+def test_packet_parse_matches_reference(ref):
+    from opus_codec_b200.packet import packet_parse_raw
+    rng = np.random.default_rng(5)
+    pkts = sample_packets()
+    assert len(pkts) > 40
+    for p in list(pkts):                                      # truncations and bit flips of valid packets
+        for _ in range(6):
+            q = bytearray(p[:int(rng.integers(1, len(p) + 1))])
+            for _ in range(int(rng.integers(0, 3))):
+                q[int(rng.integers(0, min(len(q), 6)))] ^= 1 << int(rng.integers(0, 8))
+            pkts.append(bytes(q))
+    pkts += [bytes(rng.integers(0, 256, int(rng.integers(1, 40)), dtype=np.uint8)) for _ in range(3000)]
+    pkts += [b"\xfb" + bytes([0x80 | 0x40 | 3]) + b"\xff\xff\x10" + bytes(700), b"\xf8" * 1277, b"\xf8" + bytes(1275), b"\xfb\x00", b"\xfb\x31" + bytes(49)]
+    seen = set()
+    for p in pkts:
+        a = ref_parse(ref, p)
+        b = packet_parse_raw(p)
+        assert a[0] == b[0], (p[:8].hex(), a[0], b[0])
+        seen.add(a[0] if a[0] < 0 else "ok%d" % (p[0] & 3))
+        if a[0] > 0:
+            assert a == b, p[:8].hex()
+    assert {"ok0", "ok1", "ok2", "ok3", -4} <= seen
+
+
+def test_packet_parse_wrapper_follows_the_crate():
+    from opus_codec_b200.packet import packet_parse
+    from opus_codec_b200.batch import OpusError
+    g = load_golden(golden_names()[0])
+    fr = [bytes(g["packets"][0][f, :g["lens"][0][f]]) for f in range(3)]
+    toc, po, frames = packet_parse(repacketize(fr, 3, pad=9))
+    assert toc == ((fr[0][0] & 0xFC) | 3) and frames == [f[1:] for f in fr] and po > 2
+    with pytest.raises(OpusError) as e:
+        packet_parse(b"")
+    assert e.value.code == -1
+    with pytest.raises(OpusError) as e:
+        packet_parse(b"\xf9\x00\x00\x00")                      # code 1 with an odd payload
+    assert e.value.code == -4
+
+
+def test_repacketizer_matches_reference(ref):
+    rng = np.random.default_rng(8)
+    checked = 0
+    for name in golden_names():
+        g = load_golden(name)
+        pk, ln = g["packets"][0], g["lens"][0]
+        fr = [bytes(pk[f, :ln[f]]) for f in range(pk.shape[0])]
+        per120 = 5760 // g["frame_size"]
+        for trial in range(12):
+            m = int(rng.integers(1, min(per120, 8, len(fr)) + 1))
+            k0 = int(rng.integers(0, len(fr) - m + 1))
+            grp = fr[k0:k0 + m]
+            if trial % 3 == 1 and m >= 2:                     # feed multi-frame packets (and padding) back in
+                grp = [repacketize(grp[:2], 3, pad=int(rng.integers(0, 400)))] + grp[2:]
+            if trial % 4 == 2:
+                grp[-1] = grp[-1][:1]                          # a DTX frame (TOC only)
+            a, b = ref_merge(ref, grp), our_merge(grp)
+            assert a == b, (name, trial, m)
+            checked += 1
+            if isinstance(a, bytes) and m >= 2:
+                b0, e0 = sorted(rng.choice(m + 1, 2, replace=False).tolist())
+                assert ref_merge(ref, grp, b0, e0) == our_merge(grp, b0, e0)
+                assert ref_merge(ref, grp, maxlen=len(a) - 1) == our_merge(grp, maxlen=len(a) - 1) == -2      # OPUS_BUFFER_TOO_SMALL
+    assert checked > 50
+    # error paths: mismatched configuration, more than 120 ms, bad ranges
+    g1, g2 = load_golden(golden_names()[0]), load_golden(golden_names()[-1])
+    p1, p2 = bytes(g1["packets"][0][0, :g1["lens"][0][0]]), bytes(g2["packets"][0][0, :g2["lens"][0][0]])
+    if (p1[0] & 0xFC) != (p2[0] & 0xFC):
+        assert ref_merge(ref, [p1, p2]) == our_merge([p1, p2]) == -4
+    n = 5760 // g1["frame_size"] + 1
+    assert ref_merge(ref, [p1] * n) == our_merge([p1] * n) == -4
+    assert ref_merge(ref, [p1, p1], 1, 1) == our_merge([p1, p1], 1, 1) == -1
+    assert ref_merge(ref, [p1, p1], 0, 3) == our_merge([p1, p1], 0, 3) == -1
+
+
+def test_repacketizer_object_reset_and_frames():
+    from opus_codec_b200.packet import Repacketizer
+    g = load_golden(golden_names()[0])
+    fr = [bytes(g["packets"][0][f, :g["lens"][0][f]]) for f in range(4)]
+    with Repacketizer() as rp:
+        assert rp.frames() == 0
+        rp.push(fr[0]); rp.push(repacketize(fr[1:3], 3))
+        assert rp.frames() == 3
+        whole = rp.out()
+        assert rp.out_range(1, 2) == bytes([fr[1][0] & 0xFC]) + fr[1][1:]
+        rp.reset()
+        assert rp.frames() == 0
+        rp.push(fr[3])
+        assert rp.out() == bytes([fr[3][0] & 0xFC]) + fr[3][1:]
+    from opus_codec_b200.packet import packet_parse
+    assert packet_parse(whole)[2] == [f[1:] for f in fr[:3]]
+
+
+def test_pad_unpad_and_extensions_match_reference(ref):
+    from opus_codec_b200 import packet as pkt_mod
+    from opus_codec_b200.packet import packet_pad
+    from opus_codec_b200.batch import OpusError
+
+    def packet_unpad(p):
+        try:
+            return pkt_mod.packet_unpad(p)
+        except OpusError as e:
+            return e.code
+
+    def ref_unpad(p):
+        d = _buf(p)
+        n = ref.opus_packet_unpad(d, len(p))
+        return bytes(d[:n]) if n >= 0 else n
+    rng = np.random.default_rng(21)
+    pkts = sample_packets()
+    g = load_golden(golden_names()[0])
+    fr = [bytes(g["packets"][0][f, :g["lens"][0][f]]) for f in range(6)]
+    ext = [with_padding(fr[:1], ext_padding()), with_padding(fr[:3], ext_padding()), with_padding(fr[:2], bytes([0x01] * 5) + ext_padding()),
+           with_padding(fr[:2], bytes([(3 << 1) | 1, 7, 0x02, 0x02, (100 << 1) | 1, 255, 45]) + bytes(range(256)) + bytes(44) + bytes([(2 << 1)]))]
+    for p in pkts + ext:
+        for new_len in (len(p), len(p) + 1, len(p) + 2, len(p) + int(rng.integers(3, 600)), len(p) + 255, len(p) + 256, len(p) + 257):
+            d = _buf(p, new_len)
+            r = ref.opus_packet_pad(d, len(p), new_len)
+            try:
+                ours = packet_pad(p, new_len)
+                assert r == 0 and ours == bytes(d[:new_len]), (p[:4].hex(), new_len)
+                assert packet_unpad(ours) == ref_unpad(ours)
+            except OpusError as e:
+                assert e.code == r, (p[:4].hex(), new_len)
+        assert packet_unpad(p) == ref_unpad(p)
+    # extensions travel through the repacketizer: merged packets renumber the frames they belong to
+    for grp in ([ext[0], fr[3]], [fr[3], ext[0]], [ext[1], ext[0]], [ext[2], ext[2]], [ext[0]], [ext[3], ext[1]]):
+        a, b = ref_merge(ref, grp), our_merge(grp)
+        assert isinstance(a, bytes) and a == b
+    assert ref_merge(ref, [ext[1], ext[0]], 1, 4) == our_merge([ext[1], ext[0]], 1, 4)
+    with pytest.raises(OpusError) as e:
+        packet_pad(fr[0], len(fr[0]) - 1)
+    assert e.value.code == -1
