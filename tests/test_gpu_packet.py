@@ -70,3 +70,64 @@ def test_batch_padding_extensions_and_errors(ref):
         assert lens[s, 0] == 1500 and bytes(out[s, 0]) == bytes(d), s
     out, lens = repacketize_batch(rows[:1], 2, pad_to=100)
     assert lens[0, 0] == -2
+
+
+def test_reference_tool_round_trips_through_the_bit_container(have_ref):
+    """oracle/_ref/opus_demo (the reference's own tool) encodes -> .bit -> GPU int16 decode == the tool's own decode; GPU encode -> .bit ->
+    the tool decodes it and its per-packet final-range check passes."""
+    import os, subprocess, tempfile
+    from conftest import ROOT
+    from opus_codec_b200 import containers, synth
+    from opus_codec_b200.batch import BatchDecoder, BatchEncoder, pack_packets
+    demo = os.path.join(ROOT, "oracle", "_ref", "opus_demo")
+    if not os.path.exists(demo):
+        pytest.skip("oracle/_ref/opus_demo not built")
+    ch, fs, F = 2, 960, 50
+    pcm = synth.stream_pcm(5, fs * F, ch)
+    pcm16 = np.clip(np.rint(pcm * 32768), -32768, 32767).astype("<i2")
+    with tempfile.TemporaryDirectory() as d:
+        pcm16.tofile(os.path.join(d, "in.pcm"))
+        r = subprocess.run([demo, "-e", "restricted-lowdelay", "48000", "2", "96000", "-cbr", os.path.join(d, "in.pcm"), os.path.join(d, "ref.bit")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        r = subprocess.run([demo, "-d", "48000", "2", os.path.join(d, "ref.bit"), os.path.join(d, "ref.pcm")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        want = np.fromfile(os.path.join(d, "ref.pcm"), "<i2")
+        pk, rng = containers.read_bit(open(os.path.join(d, "ref.bit"), "rb").read())
+        with BatchDecoder(1, 48000, ch, device=0, max_frames=len(pk)) as dec:
+            b, o, l = pack_packets([pk])
+            got, smp, drng = dec.decode_multi(b, o, l, fs)
+        assert (smp == fs).all() and (drng[0] == np.array(rng, np.uint32)).all()
+        got = got.reshape(-1)
+        assert got.size == want.size
+        diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+        assert diff.max() <= 1 and (diff != 0).mean() < 0.02
+        # GPU encode -> the tool decodes and checks every final range
+        with BatchEncoder(1, 48000, ch, device=0, max_frames=F) as enc:
+            enc.set_bitrate(96000); enc.set_vbr(False); enc.set_complexity(10)
+            out, lens, erng = enc.encode_multi(pcm16.reshape(1, F, fs * ch), fs)
+        ours = [bytes(out[0, f, :lens[0, f]]) for f in range(F)]
+        open(os.path.join(d, "gpu.bit"), "wb").write(containers.write_bit(ours, erng[0]))
+        r = subprocess.run([demo, "-d", "48000", "2", os.path.join(d, "gpu.bit"), os.path.join(d, "gpu.pcm")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        assert ours == pk[:F]                                   # and the GPU's packets are the tool's packets
+
+
+def test_ogg_and_rtp_feed_the_batch_decoder():
+    """An .opus file written from golden packets with an output gain, and the same packets as RTP with two of them lost: header gain ->
+    set_gain, lost packets -> concealment; results equal the plain packet-list path."""
+    from opus_codec_b200 import containers as c
+    from opus_codec_b200.batch import BatchDecoder, pack_packets
+    g = load_golden("cfg2_mono_20ms_64k_cbr")
+    pk = [bytes(g["packets"][0][f, :g["lens"][0][f]]) for f in range(40)]
+    o = c.ogg_read(c.ogg_write(pk, 1, output_gain_q8=-512))
+    lossy, _ = c.rtp_to_packets([c.rtp_pack(p, i, 960 * i, 9) for i, p in enumerate(pk) if i not in (11, 12)])
+    assert lossy == [b"" if i in (11, 12) else p for i, p in enumerate(pk)]
+    res = []
+    for packets, gain in ((o["packets"], o["output_gain_q8"]), (pk, -512), (lossy, 0), ([b"" if i in (11, 12) else p for i, p in enumerate(pk)], 0)):
+        with BatchDecoder(1, 48000, 1, device=0, max_frames=40) as dec:
+            dec.set_gain(gain)
+            b, of, l = pack_packets([packets])
+            res.append(dec.decode_float_multi(b, of, l, 960))
+    assert np.array_equal(res[0][0], res[1][0]) and (res[0][2] == res[1][2]).all()
+    assert np.array_equal(res[2][0], res[3][0]) and (res[2][1] == 960).all()
+    assert np.abs(res[0][0]).max() > 0 and not np.array_equal(res[0][0], res[2][0])
