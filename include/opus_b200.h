@@ -128,7 +128,10 @@ void *ob_decoder_cuda_stream(ObDecoder *dec);
 typedef struct ObEncoder ObEncoder;
 
 /* n x opus_encoder_create(Fs, channels, application, &err) (src/bindings.rs:297-305; Encoder::new src/encoder.rs:40-73).
- * Defaults as opus_encoder_init: VBR on, constrained, bitrate AUTO, complexity 9. */
+ * Defaults as opus_encoder_init: VBR on, constrained, bitrate AUTO, complexity 9.
+ * application: 2051 (RESTRICTED_LOWDELAY), or 2049 (AUDIO) / 2048 (VOIP): these add the 4 ms delay compensation, the VOIP high-pass and
+ * libopus' SILK / hybrid / CELT mode decision (opus_encoder.c:1333-1392); a frame that decision does not give to CELT returns
+ * OB_UNIMPLEMENTED in lens_out for that stream (every packet before it is what libopus produces).  fs: 48000. */
 ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, int32_t application, int32_t device,
                              int32_t max_frames, int32_t *error);
 /* opus_encoder_destroy (src/bindings.rs:335-338). */

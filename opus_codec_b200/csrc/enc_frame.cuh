@@ -33,6 +33,8 @@ struct ObEncState {
 };
 
 // Per-stream working memory of one frame (the reference's stack VLAs).
+#define OB_ENC_DELAY 192                                  // delay_compensation = Fs/250 (opus_encoder.c:282)
+#define OB_ENC_BUFFER 480                                 // encoder_buffer = Fs/100 (:276)
 struct ObEncScratch {
     float in[2 * (OB_MAX_N + OB_OVERLAP)];
     float pre[2 * (OB_MAX_N + OB_MAXPERIOD)];
@@ -41,7 +43,7 @@ struct ObEncScratch {
     float freq[2 * OB_MAX_N];
     float X[2 * OB_MAX_N];
     float mdct_f[OB_MAX_N], mdct_f2[OB_MAX_N];
-    float pcm_hp[2 * OB_MAX_N];                       // dc_reject output
+    float pcm_hp[2 * (OB_MAX_N + OB_ENC_DELAY)];      // [delay compensation | dc_reject / hp_cutoff output]: what CELT encodes
     ObEncBandsScratch bands;
     uint8_t coarse_save[1280];
     uint8_t multi_tmp[1284];                          // the 20 ms frames of a 40-120 ms packet before they are repacketized
@@ -420,16 +422,84 @@ OB_DEV void ob_dc_reject(const float *in, float *out, float *hp_mem, int len, in
     }
 }
 
-// ---- Opus layer for CELT-only packets (OPUS_APPLICATION_RESTRICTED_LOWDELAY => MODE_CELT_ONLY, opus_encoder.c:1330-1332) ----
+// hp_cutoff (opus_encoder.c:369-404) + silk_biquad_float (:331-366), Fs = 48000.  cutoff_Hz is 60 for as long as a stream stays
+// CELT-only: variable_HP_smth2_Q15 starts at lin2log(60) << 8 and in MODE_CELT_ONLY is smoothed towards the same value (:1795-1805).
+OB_DEV void ob_hp_cutoff(const float *in, float *out, float *hp_mem, int len, int channels)
+{
+    const int32_t cutoff_Hz = 60;
+    const int32_t Fc_Q19 = (int32_t)((int16_t)2471 * (int32_t)(int16_t)cutoff_Hz) / 48;        // SILK_FIX_CONST(1.5 * 3.14159 / 1000, 19) = 2471
+    const int32_t r_Q28 = (1 << 28) - 471 * Fc_Q19;                                          // SILK_FIX_CONST(0.92, 9) = 471
+    const int32_t B_Q28[3] = {r_Q28, (int32_t)((uint32_t)(-r_Q28) << 1), r_Q28};
+    const int32_t r_Q22 = r_Q28 >> 6;
+    const int32_t fc2 = (int32_t)(((int64_t)Fc_Q19 * Fc_Q19) >> 16);                          // silk_SMULWW (64-bit form, OPUS_FAST_INT64)
+    const int32_t A_Q28[2] = {(int32_t)(((int64_t)r_Q22 * (fc2 - (2 << 22))) >> 16), (int32_t)(((int64_t)r_Q22 * r_Q22) >> 16)};
+    const float A0 = (float)(A_Q28[0] * (1.f / ((int32_t)1 << 28))), A1 = (float)(A_Q28[1] * (1.f / ((int32_t)1 << 28)));
+    const float B0 = (float)(B_Q28[0] * (1.f / ((int32_t)1 << 28))), B1 = (float)(B_Q28[1] * (1.f / ((int32_t)1 << 28))), B2 = (float)(B_Q28[2] * (1.f / ((int32_t)1 << 28)));
+    for (int c = 0; c < channels; c++) {
+        float S0 = hp_mem[2 * c], S1 = hp_mem[2 * c + 1];
+        for (int k = 0; k < len; k++) {
+            const float inval = in[k * channels + c];
+            const float vout = S0 + B0 * inval;
+            S0 = S1 - vout * A0 + B1 * inval;
+            S1 = -vout * A1 + B2 * inval + 1e-30f;
+            out[k * channels + c] = vout;
+        }
+        hp_mem[2 * c] = S0; hp_mem[2 * c + 1] = S1;
+    }
+}
+
+// compute_stereo_width (opus_encoder.c:729-809), float build: feeds the SILK / CELT mode thresholds of the non-low-delay applications
+struct ObStereoWidth { float XX, XY, YY, smoothed_width, max_follower; };
+OB_DEV float ob_compute_stereo_width(const float *pcm, int frame_size, ObStereoWidth &mem)
+{
+    const int frame_rate = 48000 / frame_size;
+    const float short_alpha = 1.0f - 25 * 1.0f / ob_imax(50, frame_rate);
+    float xx = 0, xy = 0, yy = 0;
+    for (int i = 0; i < frame_size - 3; i += 4) {
+        float pxx, pxy, pyy, x, y;
+        x = pcm[2 * i]; y = pcm[2 * i + 1];
+        pxx = x * x; pxy = x * y; pyy = y * y;
+        x = pcm[2 * i + 2]; y = pcm[2 * i + 3];
+        pxx += x * x; pxy += x * y; pyy += y * y;
+        x = pcm[2 * i + 4]; y = pcm[2 * i + 5];
+        pxx += x * x; pxy += x * y; pyy += y * y;
+        x = pcm[2 * i + 6]; y = pcm[2 * i + 7];
+        pxx += x * x; pxy += x * y; pyy += y * y;
+        xx += pxx; xy += pxy; yy += pyy;
+    }
+    if (!(xx < 1e9f) || xx != xx || !(yy < 1e9f) || yy != yy) xy = xx = yy = 0;
+    mem.XX += short_alpha * (xx - mem.XX);
+    mem.XY += short_alpha * (xy - mem.XY);
+    mem.YY += short_alpha * (yy - mem.YY);
+    mem.XX = ob_fmax(0, mem.XX); mem.XY = ob_fmax(0, mem.XY); mem.YY = ob_fmax(0, mem.YY);
+    if (ob_fmax(mem.XX, mem.YY) > 8e-4f) {
+        const float sqrt_xx = (float)sqrt((double)mem.XX), sqrt_yy = (float)sqrt((double)mem.YY);
+        const float qrrt_xx = (float)sqrt((double)sqrt_xx), qrrt_yy = (float)sqrt((double)sqrt_yy);
+        mem.XY = ob_fmin(mem.XY, sqrt_xx * sqrt_yy);
+        const float corr = mem.XY / (1e-15f + sqrt_xx * sqrt_yy);
+        const float ldiff = 1.0f * (float)fabs(qrrt_xx - qrrt_yy) / (1e-15f + qrrt_xx + qrrt_yy);
+        const float width = (float)sqrt((double)(1.f - corr * corr)) * ldiff;
+        mem.smoothed_width += (width - mem.smoothed_width) / frame_rate;
+        mem.max_follower = ob_fmax(mem.max_follower - .02f / frame_rate, mem.smoothed_width);
+    }
+    return ob_fmin(1.0f, 20 * mem.max_follower);
+}
+
+// ---- Opus layer for CELT-only packets: OPUS_APPLICATION_RESTRICTED_LOWDELAY => MODE_CELT_ONLY (opus_encoder.c:1330-1332); AUDIO / VOIP
+// for as long as the rate-dependent mode decision (:1333-1385) says MODE_CELT_ONLY -- a frame it would give to SILK is OB_UNIMPLEMENTED ----
 // User-visible encoder settings (the CTLs of src/encoder.rs) + the Opus-layer state this path keeps between frames.
 struct ObOpusEncCfg {
     int32_t bitrate;           // OPUS_SET_BITRATE: bits/s, or -1000 (OPUS_AUTO) / -1 (OPUS_BITRATE_MAX)
     int32_t complexity, vbr, vbr_constraint, max_bandwidth, user_bandwidth, force_channels, packet_loss, lsb_depth;
+    int32_t application;       // 2048 VOIP, 2049 AUDIO, 2051 RESTRICTED_LOWDELAY (0 is read as 2051)
 };
 struct ObOpusEncState {
     int32_t stream_channels, first, auto_bandwidth, bandwidth, hybrid_stereo_width_Q14;
     int32_t voice_ratio, detected_bandwidth;     // from the signal analysis (opus_encoder.c:1146-1176); voice_ratio = -1: unknown
     ObTonalState *tonal;                         // st->analysis when the analysis runs inline (host emulation); the GPU runs it in its own kernel
+    int32_t prev_mode;                           // 0 before the first packet, then 1002 (MODE_CELT_ONLY)
+    ObStereoWidth width_mem;
+    float *delay;                                // st->delay_buffer [OB_ENC_BUFFER * channels] of the AUDIO / VOIP applications (global memory); null: low delay
 };
 
 OB_DEV int32_t ob_compute_equiv_rate(int32_t bitrate, int channels, int frame_rate, int vbr, int celt_only, int complexity, int loss)
@@ -475,13 +545,24 @@ OB_DEV_NOINLINE int ob_opus_encode_frame(const ObOpusEncCfg &cfg, ObOpusEncState
     ObRangeEnc enc;
     enc.init(data + 1, (uint32_t)(max_data_bytes - 1));
     float *pcm_buf = S.pcm_hp;
-    ob_dc_reject(pcm, pcm_buf, st.hp_mem, frame_size, channels);
+    const int total_buffer = os.delay ? OB_ENC_DELAY : 0;                                                     // :1740-1744
+    for (int i = 0; i < total_buffer * channels; i++) pcm_buf[i] = os.delay[(OB_ENC_BUFFER - total_buffer) * channels + i];
+    float *fresh = pcm_buf + total_buffer * channels;
+    if (cfg.application == 2048) ob_hp_cutoff(pcm, fresh, st.hp_mem, frame_size, channels);
+    else ob_dc_reject(pcm, fresh, st.hp_mem, frame_size, channels);
     {
-        const float sum = ob_inner_prod(pcm_buf, pcm_buf, frame_size * channels);
+        const float sum = ob_inner_prod(fresh, fresh, frame_size * channels);
         if (!(sum < 1e9f) || sum != sum) {
-            for (int i = 0; i < frame_size * channels; i++) pcm_buf[i] = 0;
+            for (int i = 0; i < frame_size * channels; i++) fresh[i] = 0;
             st.hp_mem[0] = st.hp_mem[1] = st.hp_mem[2] = st.hp_mem[3] = 0;
         }
+    }
+    if (os.delay) {                                                                                           // :2125-2134, before the fades
+        const int keep = OB_ENC_BUFFER - (frame_size + total_buffer);
+        if (keep > 0) {
+            for (int i = 0; i < channels * keep; i++) os.delay[i] = os.delay[channels * frame_size + i];
+            for (int i = 0; i < (frame_size + total_buffer) * channels; i++) os.delay[channels * keep + i] = pcm_buf[i];
+        } else for (int i = 0; i < OB_ENC_BUFFER * channels; i++) os.delay[i] = pcm_buf[(frame_size + total_buffer - OB_ENC_BUFFER) * channels + i];
     }
     int stereoWidth_Q14;
     if (equiv_rate > 32000) stereoWidth_Q14 = 16384;
@@ -511,6 +592,7 @@ OB_DEV_NOINLINE int ob_opus_encode_frame(const ObOpusEncCfg &cfg, ObOpusEncState
     }
     st.final_range = enc.rng;
     os.first = 0;
+    os.prev_mode = 1002;
     ret += 1;
     if (!cfg.vbr && ret != max_data_bytes) return OB_UNIMPLEMENTED;     // opus_packet_pad: CELT CBR always fills its budget on this path
     return ret;
@@ -564,16 +646,32 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
             os.detected_bandwidth = ab <= 12 ? 1101 : ab <= 14 ? 1102 : ab <= 16 ? 1103 : ab <= 18 ? 1104 : 1105;
         }
     }
+    const float stereo_width = (channels == 2 && cfg.force_channels != 1 && (cfg.application == 2048 || cfg.application == 2049))
+                                   ? ob_compute_stereo_width(pcm, frame_size, os.width_mem) : 0;                // :1181-1184 (only the mode decision reads it)
     if (max_data_bytes < 3 || bitrate_bps < 3 * frame_rate * 8 || (frame_rate < 50 && (max_data_bytes * frame_rate < 300 || bitrate_bps < 2400)))
         return OB_UNIMPLEMENTED;                                                                              // the "PLC frame" corner (:1202-1266)
     int32_t equiv_rate = ob_compute_equiv_rate(bitrate_bps, channels, frame_rate, cfg.vbr, 0, cfg.complexity, cfg.packet_loss);
-    const int voice_est = os.voice_ratio >= 0 ? os.voice_ratio * 327 >> 8 : 48;                               // :1276-1289, signal AUTO, application neither VOIP nor AUDIO
+    int voice_est;                                                                                            // :1276-1289, signal AUTO
+    if (os.voice_ratio >= 0) { voice_est = os.voice_ratio * 327 >> 8; if (cfg.application == 2049) voice_est = ob_imin(voice_est, 115); }
+    else voice_est = cfg.application == 2048 ? 115 : 48;
     if (cfg.force_channels > 0 && channels == 2) os.stream_channels = cfg.force_channels;
     else if (channels == 2) {
         int32_t stereo_threshold = 17000 + ((voice_est * voice_est * (19000 - 17000)) >> 14);
         if (os.stream_channels == 2) stereo_threshold -= 1000; else stereo_threshold += 1000;
         os.stream_channels = (equiv_rate > stereo_threshold) ? 2 : 1;
     } else os.stream_channels = channels;
+    if (cfg.application == 2048 || cfg.application == 2049) {                                                 // mode selection (:1333-1392)
+        equiv_rate = ob_compute_equiv_rate(bitrate_bps, os.stream_channels, frame_rate, cfg.vbr, 0, cfg.complexity, cfg.packet_loss);
+        const int32_t mode_voice = (int32_t)((1.0f - stereo_width) * 64000 + stereo_width * 44000);
+        const int32_t mode_music = (int32_t)((1.0f - stereo_width) * 10000 + stereo_width * 10000);
+        int32_t threshold = mode_music + ((voice_est * voice_est * (mode_voice - mode_music)) >> 14);
+        if (cfg.application == 2048) threshold += 8000;
+        if (os.prev_mode == 1002) threshold -= 4000;
+        int celt_only = equiv_rate >= threshold;
+        if (max_data_bytes < (frame_rate > 50 ? 9000 : 6000) * frame_size / (Fs * 8)) celt_only = 1;
+        if (frame_size < Fs / 100) celt_only = 1;
+        if (!celt_only) return OB_UNIMPLEMENTED;                                                              // SILK / hybrid: not on this path
+    }
     equiv_rate = ob_compute_equiv_rate(bitrate_bps, os.stream_channels, frame_rate, cfg.vbr, 1, cfg.complexity, cfg.packet_loss);
     {   // automatic bandwidth (:1440-1490); voice and music tables differ only for WB<->SWB and SWB<->FB
         const int32_t voice_thr[8] = {9000, 700, 9000, 700, 13500, 1000, 14000, 2000}, music_thr[8] = {9000, 700, 9000, 700, 11000, 1000, 12000, 2000};

@@ -27,7 +27,8 @@ struct ObEncStream {           // everything one stream owns on the device
 // a warp touched 32 different lines: 112 ms per frame at 16384 streams.)
 __global__ void __launch_bounds__(OB_ENC_THREADS)
 ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *__restrict__ lens, uint32_t *__restrict__ ranges,
-            ObEncStream *__restrict__ streams, const ObAnalysisInfo *__restrict__ info, ObTonalState *__restrict__ tonal, ObOpusEncCfg cfg, int S, int F,
+            ObEncStream *__restrict__ streams, const ObAnalysisInfo *__restrict__ info, ObTonalState *__restrict__ tonal, float *__restrict__ delay,
+            ObOpusEncCfg cfg, int S, int F,
             int frame_size, int max_bytes, int lanes, int f0, int Fc)
 {
     // Only the first `lanes` threads of each warp carry a stream (tuning knob).  Spreading the streams over more, partly filled,
@@ -40,6 +41,7 @@ ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *_
     ObEncScratch sc;      // not initialised: no stage reads what it (or an earlier frame) has not written -- tests/test_host_emul.py runs the
                           // same code with the work area filled with NaN patterns before every frame
     ObEncStream es = streams[s];
+    es.os.delay = delay ? delay + (size_t)s * OB_ENC_BUFFER * es.st.channels : nullptr;      // AUDIO / VOIP: the 4 ms delay compensation, state in global memory
     es.os.tonal = tonal ? tonal + s : nullptr;                 // packets longer than 20 ms run the analysis inline, on the state in global memory
     const int CC = es.st.channels;
     // NOTE: the frame counter is deliberately volatile.  The loop body is one huge divergent region; with a plain `int f`
@@ -95,7 +97,7 @@ __global__ void ob_k_i16_to_f32(const int16_t *__restrict__ in, float *__restric
     if (i < n) out[i] = (1.0f / 32768) * (float)in[i];
 }
 
-__global__ void ob_k_enc_reset(ObEncStream *streams, const int32_t *idx, int n, int S, int channels)
+__global__ void ob_k_enc_reset(ObEncStream *streams, float *delay, const int32_t *idx, int n, int S, int channels)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
@@ -106,6 +108,8 @@ __global__ void ob_k_enc_reset(ObEncStream *streams, const int32_t *idx, int n, 
     ob_enc_reset(es.st);
     es.os.stream_channels = channels; es.os.first = 1; es.os.auto_bandwidth = 0; es.os.bandwidth = 1105; es.os.hybrid_stereo_width_Q14 = 1 << 14;
     es.os.voice_ratio = -1; es.os.detected_bandwidth = 0; es.os.tonal = nullptr;
+    es.os.prev_mode = 0; es.os.width_mem = ObStereoWidth{0, 0, 0, 0, 0}; es.os.delay = nullptr;
+    if (delay) for (int i = 0; i < OB_ENC_BUFFER * channels; i++) delay[(size_t)s * OB_ENC_BUFFER * channels + i] = 0;
 }
 
 __global__ void ob_k_enc_gather(const ObEncStream *streams, uint32_t *ranges, int S)
@@ -122,6 +126,7 @@ struct ObEncoder {
     bool timed, tonal_dirty;
     ObEncStream *d_streams;
     ObTonalState *d_tonal;             // [S] state of the signal analysis (complexity >= 7)
+    float *d_delay;                    // [S][OB_ENC_BUFFER * channels] delay buffers of the AUDIO / VOIP applications (null for RESTRICTED_LOWDELAY)
     ObAnalysisInfo *d_info;            // [S][max_frames] its per-frame result, consumed by ob_k_encode
     float *d_pcm; size_t pcm_cap;
     int16_t *d_pcm16; size_t pcm16_cap;
@@ -140,7 +145,7 @@ ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
     ObEncoder *e = nullptr;
     if (n_streams <= 0 || (channels != 1 && channels != 2) || max_frames <= 0) err = OB_BAD_ARG;
     else if (application != 2048 && application != 2049 && application != 2051) err = OB_BAD_ARG;
-    else if (fs != 48000 || application != 2051) err = OB_UNIMPLEMENTED;    // VOIP/AUDIO need the SILK/hybrid mode decision + 4 ms delay buffer
+    else if (fs != 48000) err = OB_UNIMPLEMENTED;
     else if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
         fprintf(stderr, "opus_b200: no usable CUDA device (count=%d, requested=%d); there is no CPU fallback\n", ndev, device);
         err = OB_INTERNAL_ERROR;
@@ -152,7 +157,7 @@ ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         e->lanes = 32;    // measured on B200, 16384 stereo c10 streams x 4 frames: 32 lanes 130 ms, 16: 166, 8: 329, 4: 464, 2: 726
         // defaults of opus_encoder_init (opus_encoder.c:202-297): VBR on, constrained, bitrate AUTO, complexity 9, 24-bit depth
         e->cfg.bitrate = -1000; e->cfg.complexity = 9; e->cfg.vbr = 1; e->cfg.vbr_constraint = 1; e->cfg.max_bandwidth = 1105;
-        e->cfg.user_bandwidth = 0; e->cfg.force_channels = 0; e->cfg.packet_loss = 0; e->cfg.lsb_depth = 24;
+        e->cfg.user_bandwidth = 0; e->cfg.force_channels = 0; e->cfg.packet_loss = 0; e->cfg.lsb_depth = 24; e->cfg.application = application;
         const size_t total = (size_t)n_streams * max_frames;
         bool ok = cudaSetDevice(device) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -166,6 +171,7 @@ ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         ok = ok && cudaMalloc(&e->d_tonal, sizeof(ObTonalState) * n_streams) == cudaSuccess;
         ok = ok && cudaMemset(e->d_tonal, 0, sizeof(ObTonalState) * n_streams) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_info, sizeof(ObAnalysisInfo) * total) == cudaSuccess;
+        if (application != 2051) ok = ok && cudaMalloc(&e->d_delay, sizeof(float) * OB_ENC_BUFFER * channels * n_streams) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_lens, sizeof(int32_t) * total) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_ranges, sizeof(uint32_t) * total) == cudaSuccess;
         // No cudaLimitStackSize change: the kernel has no recursion or indirect calls, so its whole local frame (~94 KB per thread) is
@@ -190,7 +196,7 @@ void ob_encoder_destroy(ObEncoder *e)
     for (int i = 0; i < 4; i++) { if (e->win_ev[i]) cudaEventDestroy(e->win_ev[i]); if (e->an_ev[i]) cudaEventDestroy(e->an_ev[i]); }
     if (e->enc_done) cudaEventDestroy(e->enc_done);
     if (e->an_stream) cudaStreamDestroy(e->an_stream);
-    cudaFree(e->d_tonal); cudaFree(e->d_info);
+    cudaFree(e->d_tonal); cudaFree(e->d_info); cudaFree(e->d_delay);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
@@ -208,7 +214,7 @@ int32_t ob_encoder_reset(ObEncoder *e, const int32_t *idx, int32_t n)
         OB_CUDA(cudaMalloc(&d_idx, sizeof(int32_t) * n));
         OB_CUDA(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
     }
-    ob_k_enc_reset<<<(count + 63) / 64, 64, 0, e->stream>>>(e->d_streams, d_idx, count, e->S, e->CC);
+    ob_k_enc_reset<<<(count + 63) / 64, 64, 0, e->stream>>>(e->d_streams, e->d_delay, d_idx, count, e->S, e->CC);
     ob_k_tonal_reset<<<count, 128, 0, e->stream>>>(e->d_tonal, d_idx, count, e->S);
     e->launches += 2;
     OB_CUDA(cudaStreamSynchronize(e->stream));
@@ -273,7 +279,7 @@ static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size
     int lanes = e->lanes;
     if (const char *v = getenv("OB_ENC_LANES")) { const int t = atoi(v); if (t >= 1 && t <= OB_ENC_THREADS) lanes = t; }   // tuning aid
     ob_k_encode<<<(e->S + lanes - 1) / lanes, OB_ENC_THREADS, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, an ? e->d_info : nullptr,
-                                                                               an_inline ? e->d_tonal : nullptr, e->cfg, e->S, F, frame_size, max_bytes, lanes, f0, Fc);
+                                                                               an_inline ? e->d_tonal : nullptr, e->d_delay, e->cfg, e->S, F, frame_size, max_bytes, lanes, f0, Fc);
     if (f0 + Fc == F) { OB_CUDA(cudaEventRecord(e->ev[1], e->stream)); OB_CUDA(cudaEventRecord(e->enc_done, e->stream)); }
     OB_CUDA(cudaGetLastError());
     e->launches += 1;

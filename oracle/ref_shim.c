@@ -128,7 +128,10 @@ void __wrap_comb_filter(opus_val32 *y, opus_val32 *x, int T0, int T1, int N, opu
  * vbr: 0 = CBR, 1 = VBR, 2 = constrained VBR. */
 /* Optional extra CTLs applied by make_encoder (0 / OPUS_AUTO = leave alone): OPUS_SET_BANDWIDTH
  * (1101..1105) and OPUS_SET_FORCE_CHANNELS.  Used to produce NB/WB/SWB and mono-in-stereo test packets. */
-static int g_extra_bandwidth = 0, g_extra_force_channels = 0;
+static int g_extra_bandwidth = 0, g_extra_force_channels = 0, g_force_celt = 1;
+/* 1 (default): VOIP / AUDIO encoders get OPUS_SET_FORCE_MODE(MODE_CELT_ONLY) (how the CELT goldens were made); 0: the encoder's own
+ * SILK / hybrid / CELT decision, i.e. what a user of the crate gets. */
+REF_EXPORT void ref_set_encoder_force_celt(int on) { g_force_celt = on; }
 REF_EXPORT void ref_set_encoder_extras(int bandwidth, int force_channels)
 {
     g_extra_bandwidth = bandwidth; g_extra_force_channels = force_channels;
@@ -143,7 +146,7 @@ static OpusEncoder *make_encoder(int channels, int application, int bitrate, int
     opus_encoder_ctl(e, OPUS_SET_COMPLEXITY(complexity));
     opus_encoder_ctl(e, OPUS_SET_VBR(vbr != 0));
     opus_encoder_ctl(e, OPUS_SET_VBR_CONSTRAINT(vbr == 2));
-    if (application != OPUS_APPLICATION_RESTRICTED_LOWDELAY)
+    if (application != OPUS_APPLICATION_RESTRICTED_LOWDELAY && g_force_celt)
         opus_encoder_ctl(e, OPUS_SET_FORCE_MODE(MODE_CELT_ONLY));
     if (g_extra_bandwidth) opus_encoder_ctl(e, OPUS_SET_BANDWIDTH(g_extra_bandwidth));
     if (g_extra_force_channels) opus_encoder_ctl(e, OPUS_SET_FORCE_CHANNELS(g_extra_force_channels));

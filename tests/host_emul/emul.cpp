@@ -112,17 +112,25 @@ int emul_celt_encode_stream(const float *pcm, int nframes, int frame_size, int c
 }
 }
 extern "C" {
-// Opus-level encode (TOC byte included) of one stream; mirrors ref_encode_stream() with OPUS_APPLICATION_RESTRICTED_LOWDELAY.
+// Opus-level encode (TOC byte included) of one stream; mirrors ref_encode_stream().  application: 2048 / 2049 / 2051.
+int emul_opus_encode_stream_app(const float *pcm, int nframes, int frame_size, int channels, int application, int bitrate, int vbr, int complexity,
+                                unsigned char *out, int max_bytes, int *lens, uint32_t *ranges);
 int emul_opus_encode_stream(const float *pcm, int nframes, int frame_size, int channels, int bitrate, int vbr, int complexity,
                             unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
 {
+    return emul_opus_encode_stream_app(pcm, nframes, frame_size, channels, 2051, bitrate, vbr, complexity, out, max_bytes, lens, ranges);
+}
+int emul_opus_encode_stream_app(const float *pcm, int nframes, int frame_size, int channels, int application, int bitrate, int vbr, int complexity,
+                                unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
+{
     ObEncState *st = (ObEncState *)calloc(1, sizeof(ObEncState));
     ObEncScratch *S = (ObEncScratch *)calloc(1, sizeof(ObEncScratch));
-    ObOpusEncCfg cfg = {bitrate, complexity, vbr != 0, vbr == 2, 1105, 0, 0, 0, 24};
+    ObOpusEncCfg cfg = {bitrate, complexity, vbr != 0, vbr == 2, 1105, 0, 0, 0, 24, application};
     ObOpusEncState *osp = (ObOpusEncState *)calloc(1, sizeof(ObOpusEncState));
     ObOpusEncState &os = *osp;
     os.stream_channels = channels; os.first = 1; os.auto_bandwidth = 0; os.bandwidth = 1105; os.hybrid_stereo_width_Q14 = 1 << 14; os.voice_ratio = -1;
     os.tonal = (ObTonalState *)calloc(1, sizeof(ObTonalState));
+    os.delay = application != 2051 ? (float *)calloc(OB_ENC_BUFFER * channels, sizeof(float)) : nullptr;
     st->channels = st->stream_channels = channels; st->end = 21; st->clip = 1;
     ob_enc_reset(*st);
     int rc = 0;
@@ -133,7 +141,7 @@ int emul_opus_encode_stream(const float *pcm, int nframes, int frame_size, int c
         lens[f] = n;
         ranges[f] = st->final_range;
     }
-    free(os.tonal); free(st); free(S); free(osp);
+    free(os.tonal); free(os.delay); free(st); free(S); free(osp);
     return rc;
 }
 }

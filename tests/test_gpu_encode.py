@@ -18,7 +18,7 @@ from opus_codec_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def _ref_c_encode(pcm, fs, ch, br, vbr, cx):
+def _ref_c_encode(pcm, fs, ch, br, vbr, cx, app=2051):
     from oracle import refpy
     L = refpy.lib_c()
     u8p, i32p, u32p, f32p = (C.POINTER(C.c_ubyte), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_float))
@@ -26,7 +26,11 @@ def _ref_c_encode(pcm, fs, ch, br, vbr, cx):
     pcm = np.ascontiguousarray(pcm, np.float32)
     nf = pcm.size // (fs * ch)
     out = np.zeros((nf, 1276), np.uint8); lens = np.zeros(nf, np.int32); rng = np.zeros(nf, np.uint32)
-    r = L.ref_encode_stream(pcm.ctypes.data_as(f32p), nf, fs, ch, 2051, br, vbr, cx, out.ctypes.data_as(u8p), 1276, lens.ctypes.data_as(i32p), rng.ctypes.data_as(u32p))
+    L.ref_set_encoder_force_celt(0)                               # the encoder's own mode decision (matters for app != 2051 only)
+    try:
+        r = L.ref_encode_stream(pcm.ctypes.data_as(f32p), nf, fs, ch, app, br, vbr, cx, out.ctypes.data_as(u8p), 1276, lens.ctypes.data_as(i32p), rng.ctypes.data_as(u32p))
+    finally:
+        L.ref_set_encoder_force_celt(1)
     assert r == 0
     return out, lens, rng
 
@@ -87,11 +91,11 @@ def test_pathological_input_matches_reference(have_ref, ch, br, fs, vbr, cx):
     assert min(ident) >= 0.9 and np.mean(ident) >= 0.97, ident
 
 
-def _gpu_encode(pcm_batch, fs, ch, br, vbr, cx):
+def _gpu_encode(pcm_batch, fs, ch, br, vbr, cx, app=2051):
     from opus_codec_b200.batch import BatchEncoder
     S = pcm_batch.shape[0]
     F = pcm_batch.shape[1] // (fs * ch)
-    with BatchEncoder(S, 48000, ch, device=0, max_frames=F) as enc:
+    with BatchEncoder(S, 48000, ch, application=app, device=0, max_frames=F) as enc:
         enc.set_bitrate(br); enc.set_complexity(cx); enc.set_vbr(vbr != 0); enc.set_vbr_constraint(vbr == 2)
         assert enc.bitrate() == br and enc.complexity() == cx and enc.vbr() == (vbr != 0)
         out, lens, rng = enc.encode_float_multi(pcm_batch[:, :F * fs * ch].reshape(S, F, fs * ch), fs)
@@ -153,8 +157,11 @@ def test_complexity10_stereo_roundtrip_quality_and_final_range():
 def test_encoder_ctl_validation_and_reset():
     from opus_codec_b200.batch import BatchEncoder, OpusError, BAD_ARG, UNIMPLEMENTED
     with pytest.raises(OpusError) as e:
-        BatchEncoder(4, 48000, 1, application=2049)                  # AUDIO: not on this path
+        BatchEncoder(4, 16000, 1)                                    # input rates other than 48 kHz: not on this path
     assert e.value.code == UNIMPLEMENTED
+    with pytest.raises(OpusError) as e:
+        BatchEncoder(4, 48000, 1, application=2050)
+    assert e.value.code == BAD_ARG
     with BatchEncoder(3, 48000, 1, device=0, max_frames=4) as enc:
         for bad in (lambda: enc.set_complexity(11), lambda: enc.set_bitrate(0), lambda: enc.set_max_bandwidth(7)):
             with pytest.raises(OpusError) as e:
@@ -186,3 +193,34 @@ def test_transcode_decode_then_encode_on_gpu():
         assert ((ro == out[s]).all(axis=1)).mean() >= 0.97
         _, dec_rng, _ = refpy.decode_stream(out[s], lens[s], 960, 2)
         assert (dec_rng == rng[s]).all()
+
+
+@pytest.mark.parametrize("app,ch,br,fs,vbr,cx", [(2049, 2, 96000, 960, 0, 10), (2049, 1, 64000, 960, 1, 9), (2049, 2, 128000, 480, 2, 5), (2049, 1, 96000, 2880, 0, 10),
+                                                 (2048, 2, 96000, 960, 0, 10), (2048, 1, 96000, 240, 1, 6)])
+def test_audio_and_voip_applications_match_reference(have_ref, app, ch, br, fs, vbr, cx):
+    """Application::Audio / ::Voip on the GPU (delay compensation, VOIP high-pass, mode decision): packets equal the reference's for
+    configurations whose mode decision stays MODE_CELT_ONLY; the reference decoder accepts them with a matching final range."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    S = 6
+    pcm = np.stack([synth.stream_pcm(s, 48000, ch, base_seed=4242) for s in range(S)])
+    out, lens, rng = _gpu_encode(pcm, fs, ch, br, vbr, cx, app)
+    assert (lens > 0).all()
+    ident = []
+    for s in range(S):
+        ro, rl, rr = _ref_c_encode(pcm[s], fs, ch, br, vbr, cx, app)
+        assert ((ro[:, 0] & 0x80) != 0).all()
+        ident.append(((ro == out[s]).all(axis=1) & (rl == lens[s])).mean())
+        _, dec_rng, smp = refpy.decode_stream(out[s], lens[s], fs, ch)
+        assert (smp == fs).all() and (dec_rng == rng[s]).all()
+    assert np.mean(ident) >= 0.97, ident
+
+
+def test_voip_low_rate_reports_unimplemented_when_the_reference_would_use_silk():
+    from opus_codec_b200.batch import BatchEncoder
+    pcm = np.stack([synth.stream_pcm(s, 48000, 1, base_seed=1) for s in range(2)]).reshape(2, 50, 960)
+    with BatchEncoder(2, 48000, 1, application=2048, device=0, max_frames=50) as enc:
+        enc.set_bitrate(16000)
+        out, lens, rng = enc.encode_float_multi(pcm, 960)
+    assert (lens == -5).all()

@@ -202,3 +202,39 @@ def test_encoder_opus_layer_bit_identical_to_reference(emul, have_ref, ch, br, f
         assert L.ref_encode_stream(P(pcm, C.c_float), nf, fs, ch, 2051, br, vbr, cx, P(a, C.c_ubyte), 1275, P(al, C.c_int), P(ar, C.c_uint32)) == 0
         assert emul.emul_opus_encode_stream(P(pcm, C.c_float), nf, fs, ch, br, vbr, cx, P(b, C.c_ubyte), 1275, P(bl, C.c_int), P(br_, C.c_uint32)) == 0
         assert (al == bl).all() and (ar == br_).all() and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("app,ch,br,fs,vbr,cx", [(2049, 2, 96000, 960, 0, 10), (2049, 1, 64000, 960, 1, 10), (2049, 2, 128000, 480, 0, 5), (2049, 1, 96000, 240, 2, 8),
+                                                 (2049, 2, 96000, 2880, 0, 10), (2049, 1, 64000, 120, 0, 10), (2048, 2, 96000, 960, 0, 10), (2048, 2, 128000, 480, 0, 5),
+                                                 (2048, 1, 96000, 240, 2, 8), (2048, 2, 96000, 1920, 1, 6), (2048, 1, 48000, 960, 0, 5),
+                                                 # the reference leaves CELT at once, after one frame, or in mid-stream (frame 18 of stream 1)
+                                                 (2049, 2, 48000, 960, 1, 10), (2049, 2, 32000, 480, 0, 7), (2048, 1, 64000, 960, 1, 10), (2049, 1, 24000, 960, 1, 5)])
+def test_encoder_audio_and_voip_applications_bit_identical_while_celt_only(emul, have_ref, app, ch, br, fs, vbr, cx):
+    """Application::Audio / ::Voip (src/types.rs): 4 ms delay compensation (delay_buffer), the VOIP high-pass (hp_cutoff), the stereo-width
+    tracker and the SILK / CELT mode decision.  While the reference stays in MODE_CELT_ONLY the packets are identical; the first frame the
+    reference gives to SILK / hybrid is OPUS_UNIMPLEMENTED here (and every frame before it is still identical)."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from opus_codec_b200 import synth
+    from oracle import refpy
+    L = refpy.lib_c()
+    u8p, i32p, u32p, f32p = (C.POINTER(C.c_ubyte), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_float))
+    L.ref_encode_stream.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, i32p, u32p]
+    emul.emul_opus_encode_stream_app.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, i32p, u32p]
+    for s in range(4):
+        pcm = np.ascontiguousarray(synth.stream_pcm(s, 48000, ch))
+        nf = pcm.size // (fs * ch)
+        a = np.zeros((nf, 1275), np.uint8); al = np.zeros(nf, np.int32); ar = np.zeros(nf, np.uint32)
+        b = np.zeros((nf, 1275), np.uint8); bl = np.zeros(nf, np.int32); br_ = np.zeros(nf, np.uint32)
+        L.ref_set_encoder_force_celt(0)                           # the encoder's own SILK / hybrid / CELT decision, as a user of the crate gets it
+        try:
+            assert L.ref_encode_stream(P(pcm, C.c_float), nf, fs, ch, app, br, vbr, cx, P(a, C.c_ubyte), 1275, P(al, C.c_int), P(ar, C.c_uint32)) == 0
+        finally:
+            L.ref_set_encoder_force_celt(1)
+        rc = emul.emul_opus_encode_stream_app(P(pcm, C.c_float), nf, fs, ch, app, br, vbr, cx, P(b, C.c_ubyte), 1275, P(bl, C.c_int), P(br_, C.c_uint32))
+        celt = (a[:, 0] & 0x80) != 0
+        n = nf if celt.all() else int(np.argmin(celt))            # frames before the reference's first SILK / hybrid packet
+        assert rc == (0 if n == nf else -5)
+        assert (al[:n] == bl[:n]).all() and (ar[:n] == br_[:n]).all() and np.array_equal(a[:n], b[:n])
+        if br >= 96000:
+            assert n == nf                                        # these configurations never leave CELT
