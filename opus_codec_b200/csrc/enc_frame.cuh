@@ -5,6 +5,7 @@
 #pragma once
 #include "enc_quant.cuh"
 #include "enc_tonal.cuh"
+#include "repacketizer.cuh"
 
 #define OB_BITRATE_MAX (-1)
 
@@ -46,6 +47,7 @@ struct ObEncScratch {
     float pcm_hp[2 * (OB_MAX_N + OB_ENC_DELAY)];      // [delay compensation | dc_reject / hp_cutoff output]: what CELT encodes
     ObEncBandsScratch bands;
     uint8_t coarse_save[1280];
+    ObRepack rp;                                      // opus_packet_pad of a 'PLC frame'
     uint8_t multi_tmp[1284];                          // the 20 ms frames of a 40-120 ms packet before they are repacketized
 };
 
@@ -607,9 +609,11 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
         uint8_t *data, int out_bytes, const ObAnalysisInfo *pre_info = nullptr)
 {
     const int channels = st.channels, Fs = 48000;
+    st.final_range = 0;                                                                                       // st->rangeFinal = 0 (:1092)
     if (frame_size != 120 && frame_size != 240 && frame_size != 480 && (frame_size % 960 != 0 || frame_size <= 0 || frame_size > 5760)) return OB_BAD_ARG;
     int max_data_bytes = ob_imin(1276, out_bytes);
     if (max_data_bytes <= 0) return OB_BAD_ARG;
+    if (max_data_bytes == 1 && Fs == frame_size * 10) return OB_BUFFER_TOO_SMALL;                             // "cannot encode 100 ms in 1 byte"
     const int frame_rate = Fs / frame_size;
     int32_t bitrate_bps;
     int cbr_bytes = -1;
@@ -648,8 +652,42 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
     }
     const float stereo_width = (channels == 2 && cfg.force_channels != 1 && (cfg.application == 2048 || cfg.application == 2049))
                                    ? ob_compute_stereo_width(pcm, frame_size, os.width_mem) : 0;                // :1181-1184 (only the mode decision reads it)
-    if (max_data_bytes < 3 || bitrate_bps < 3 * frame_rate * 8 || (frame_rate < 50 && (max_data_bytes * frame_rate < 300 || bitrate_bps < 2400)))
-        return OB_UNIMPLEMENTED;                                                                              // the "PLC frame" corner (:1202-1266)
+    if (max_data_bytes < 3 || bitrate_bps < 3 * frame_rate * 8 || (frame_rate < 50 && (max_data_bytes * frame_rate < 300 || bitrate_bps < 2400))) {
+        // too little room to code anything: a 'PLC frame', i.e. a TOC and nothing else (:1202-1266); st->mode is still the previous packet's
+        // (MODE_HYBRID = 1001 from opus_encoder_init until a packet has been coded)
+        int tocmode = os.prev_mode ? os.prev_mode : 1001, bw = os.bandwidth == 0 ? 1101 : os.bandwidth, packet_code = 0, num_multiframes = 0, fr = frame_rate;
+        if (fr > 100) tocmode = 1002;
+        if (fr == 25 && tocmode != 1000) { fr = 50; packet_code = 1; }
+        if (fr <= 16) {
+            if (out_bytes == 1 || (tocmode == 1000 && fr != 10)) { tocmode = 1000; packet_code = fr <= 12; fr = fr == 12 ? 25 : 16; }
+            else { num_multiframes = 50 / fr; fr = 50; packet_code = 3; }
+        }
+        if (tocmode == 1000 && bw > 1103) bw = 1103;
+        else if (tocmode == 1002 && bw == 1102) bw = 1101;
+        else if (tocmode == 1001 && bw <= 1104) bw = 1104;
+        int period = 0;
+        while (fr < 400) { fr <<= 1; period++; }
+        int toc;                                                                                              // gen_toc (:299-329)
+        if (tocmode == 1000) toc = (bw - 1101) << 5 | (period - 2) << 3;
+        else if (tocmode == 1001) toc = 0x60 | (bw - 1104) << 4 | (period - 2) << 3;
+        else { int tmp = bw - 1102; if (tmp < 0) tmp = 0; toc = 0x80 | tmp << 5 | period << 3; }
+        toc |= (os.stream_channels == 2) << 2;
+        data[0] = (uint8_t)(toc | packet_code);
+        int ret = packet_code <= 1 ? 1 : 2;
+        max_data_bytes = ob_imax(max_data_bytes, ret);
+        if (packet_code == 3) data[1] = (uint8_t)num_multiframes;
+        st.final_range = 0;
+        if (!cfg.vbr && ret != max_data_bytes) {                                                              // opus_packet_pad(data, ret, max_data_bytes)
+            uint8_t copy[2] = {data[0], data[1]};
+            ObRepack &rp = S.rp;
+            ob_repack_init(&rp);
+            if (ob_repack_cat(&rp, copy, ret, 0) != OB_OK) return OB_INTERNAL_ERROR;
+            ObExt none;
+            if (ob_repack_out_range(ObRpLanes1(), &rp, 0, rp.nb_frames, data, max_data_bytes, 0, 1, &none, 0) <= 0) return OB_INTERNAL_ERROR;
+            ret = max_data_bytes;
+        }
+        return ret;
+    }
     int32_t equiv_rate = ob_compute_equiv_rate(bitrate_bps, channels, frame_rate, cfg.vbr, 0, cfg.complexity, cfg.packet_loss);
     int voice_est;                                                                                            // :1276-1289, signal AUTO
     if (os.voice_ratio >= 0) { voice_est = os.voice_ratio * 327 >> 8; if (cfg.application == 2049) voice_est = ob_imin(voice_est, 115); }

@@ -224,3 +224,27 @@ def test_voip_low_rate_reports_unimplemented_when_the_reference_would_use_silk()
         enc.set_bitrate(16000)
         out, lens, rng = enc.encode_float_multi(pcm, 960)
     assert (lens == -5).all()
+
+
+def test_too_small_budgets_emit_the_reference_plc_frames(have_ref):
+    """opus_encoder.c:1202-1266 on the GPU: TOC-only packets (padded in CBR) when the budget cannot hold a coded frame; final range 0."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from opus_codec_b200.batch import BatchEncoder
+    for ch, br, fs, vbr, mb in ((1, 6000, 120, 0, 1276), (2, 2000, 1920, 0, 1276), (1, 64000, 960, 1, 2), (1, 2000, 5760, 1, 1276)):
+        S = 3
+        F = 48000 // fs
+        pcm = np.stack([synth.stream_pcm(s, F * fs, ch, base_seed=31) for s in range(S)])
+        with BatchEncoder(S, 48000, ch, device=0, max_frames=F) as enc:
+            enc.set_bitrate(br); enc.set_complexity(9); enc.set_vbr(vbr != 0); enc.set_vbr_constraint(False)
+            out, lens, rng = enc.encode_float_multi(pcm.reshape(S, F, fs * ch), fs, max_bytes=mb)
+        assert (rng == 0).all() and (lens > 0).all() and (lens <= 15).all()
+        for s in range(S):
+            from oracle import refpy
+            L = refpy.lib_c()
+            u8p, i32p, u32p, f32p = (C.POINTER(C.c_ubyte), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_float))
+            L.ref_encode_stream.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, i32p, u32p]
+            ro = np.zeros((F, mb), np.uint8); rl = np.zeros(F, np.int32); rr = np.ones(F, np.uint32)
+            p = np.ascontiguousarray(pcm[s])
+            assert L.ref_encode_stream(p.ctypes.data_as(f32p), F, fs, ch, 2051, br, vbr, 9, ro.ctypes.data_as(u8p), mb, rl.ctypes.data_as(i32p), rr.ctypes.data_as(u32p)) == 0
+            assert (rl == lens[s]).all() and np.array_equal(ro, out[s]) and (rr == 0).all()

@@ -238,3 +238,32 @@ def test_encoder_audio_and_voip_applications_bit_identical_while_celt_only(emul,
         assert (al[:n] == bl[:n]).all() and (ar[:n] == br_[:n]).all() and np.array_equal(a[:n], b[:n])
         if br >= 96000:
             assert n == nf                                        # these configurations never leave CELT
+
+
+@pytest.mark.parametrize("app", [2051, 2049, 2048])
+def test_encoder_too_small_budgets_emit_the_reference_plc_frames(emul, have_ref, app):
+    """Budgets too small to code anything (opus_encoder.c:1202-1266): a TOC-only 'PLC frame' (code 0 / 1 / 3, padded in CBR), with the mode of
+    the previous packet (MODE_HYBRID before the first one); 100 ms in one byte is OPUS_BUFFER_TOO_SMALL.  Final range 0."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from opus_codec_b200 import synth
+    from oracle import refpy
+    L = refpy.lib_c()
+    u8p, i32p, u32p, f32p = (C.POINTER(C.c_ubyte), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_float))
+    L.ref_encode_stream.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, i32p, u32p]
+    emul.emul_opus_encode_stream_app.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, i32p, u32p]
+    for ch, br, fs, vbr, cx, mb in [(1, 6000, 120, 0, 10, 1275), (1, 1000, 960, 1, 5, 1275), (1, 2000, 2880, 0, 10, 1275), (2, 2000, 1920, 0, 5, 1275),
+                                    (2, 2000, 1920, 1, 5, 1275), (1, 2000, 5760, 1, 9, 1275), (1, 64000, 960, 1, 9, 2), (2, 64000, 2880, 1, 9, 1),
+                                    (1, 64000, 480, 0, 9, 2), (1, 500, 3840, 0, 5, 1275), (2, 96000, 4800, 1, 9, 1), (1, 8000, 240, 0, 5, 1275)]:
+        pcm = np.ascontiguousarray(synth.stream_pcm(1, 48000, ch))
+        nf = pcm.size // (fs * ch)
+        a = np.zeros((nf, mb), np.uint8); al = np.zeros(nf, np.int32); ar = np.ones(nf, np.uint32)
+        b = np.zeros((nf, mb), np.uint8); bl = np.zeros(nf, np.int32); br_ = np.ones(nf, np.uint32)
+        L.ref_set_encoder_force_celt(0)
+        try:
+            r0 = L.ref_encode_stream(P(pcm, C.c_float), nf, fs, ch, app, br, vbr, cx, P(a, C.c_ubyte), mb, P(al, C.c_int), P(ar, C.c_uint32))
+        finally:
+            L.ref_set_encoder_force_celt(1)
+        r1 = emul.emul_opus_encode_stream_app(P(pcm, C.c_float), nf, fs, ch, app, br, vbr, cx, P(b, C.c_ubyte), mb, P(bl, C.c_int), P(br_, C.c_uint32))
+        assert r0 == r1 == (-2 if fs == 4800 else 0), (ch, br, fs, vbr, cx, mb)
+        assert (al == bl).all() and (ar == br_).all() and np.array_equal(a, b), (ch, br, fs, vbr, cx, mb)
