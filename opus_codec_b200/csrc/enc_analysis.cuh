@@ -79,7 +79,18 @@ OB_DEV float ob_inner_prod(const float *x, const float *y, int N) { float s = 0;
 // celt_pitch_xcorr_c (pitch.c:225-300): every lag is a plain in-order sum (xcorr_kernel_c accumulates lag by lag in j order)
 OB_DEV void ob_pitch_xcorr(const float *x, const float *y, float *xcorr, int len, int max_pitch)
 {
-    for (int i = 0; i < max_pitch; i++) xcorr[i] = ob_inner_prod(x, y + i, len);
+    int i = 0;
+    for (; i + 4 <= max_pitch; i += 4) {                   // four lags share every x[j] and a sliding window of y: 2 loads per 4 MACs instead of 8
+        float s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+        float y0 = y[i], y1 = y[i + 1], y2 = y[i + 2];
+        for (int j = 0; j < len; j++) {
+            const float xj = x[j], y3 = y[i + j + 3];
+            s0 = s0 + xj * y0; s1 = s1 + xj * y1; s2 = s2 + xj * y2; s3 = s3 + xj * y3;
+            y0 = y1; y1 = y2; y2 = y3;
+        }
+        xcorr[i] = s0; xcorr[i + 1] = s1; xcorr[i + 2] = s2; xcorr[i + 3] = s3;
+    }
+    for (; i < max_pitch; i++) xcorr[i] = ob_inner_prod(x, y + i, len);
 }
 
 // pitch_downsample (pitch.c:140-217) incl. _celt_autocorr (celt_lpc.c:277-351, lag 4, no window), _celt_lpc (:37-91), celt_fir5 (pitch.c:105-137)

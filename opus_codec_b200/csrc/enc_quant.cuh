@@ -310,6 +310,17 @@ OB_DEV int ob_enc_allocation(ObRangeEnc &ec, int end, const int *offsets, const 
 OB_DEV void ob_exp_rotation1_s(float *X, int len, int stride, float c, float s)                 // vq.c:47-71
 {
     const float ms = -s;
+    if (stride == 1) {                                     // the value written to p[1] is the next step's p[0]: carried in a register (same arithmetic)
+        if (len < 2) return;
+        float x1 = X[0];
+        for (int i = 0; i < len - 1; i++) { const float x2 = X[i + 1]; X[i] = c * x1 + ms * x2; x1 = c * x2 + s * x1; }
+        X[len - 1] = x1;
+        if (len < 3) return;
+        float x2 = X[len - 2];
+        for (int i = len - 3; i >= 0; i--) { const float a = X[i]; X[i + 1] = c * x2 + s * a; x2 = c * a + ms * x2; }
+        X[0] = x2;
+        return;
+    }
     float *p = X;
     for (int i = 0; i < len - stride; i++) { const float x1 = p[0], x2 = p[stride]; p[stride] = c * x2 + s * x1; *p++ = c * x1 + ms * x2; }
     p = &X[len - 2 * stride - 1];
