@@ -196,6 +196,10 @@ int32_t ob_packet_parse(const uint8_t *packet, int32_t len, uint8_t *out_toc, in
 int32_t ob_packet_pad(uint8_t *packet, int32_t len, int32_t new_len);
 int32_t ob_packet_unpad(uint8_t *packet, int32_t len);
 
+/* n x opus_pcm_soft_clip(pcm, frame_size, channels, softclip_mem) (soft_clip, src/packet.rs:123-155; opus/src/opus.c:39-144) on the GPU, in
+ * place: pcm host [n_streams][frame_size*channels], softclip_mem host [n_streams][channels] (zeros for a new stream). */
+int32_t ob_pcm_soft_clip_batch(int32_t device, int32_t n_streams, float *pcm, int32_t frame_size, int32_t channels, float *softclip_mem);
+
 /* The repacketizer object: opus_repacketizer_create / _destroy / _init / _cat / _get_nb_frames / _out_range / _out
  * (Repacketizer::new / drop / reset / push / frames / out_range / out, src/repacketizer.rs:18-100; opus/src/repacketizer.c:37-280).
  * As in libopus the packets given to _cat are referenced, not copied: they must stay valid until the last _out call. */

@@ -23,7 +23,7 @@ SYMBOLS = [
     "ob_packet_get_nb_channels", "ob_packet_get_samples_per_frame", "ob_packet_get_bandwidth", "ob_packet_get_nb_frames",
     "ob_version", "ob_strerror",
     "ob_packet_parse", "ob_packet_pad", "ob_packet_unpad", "ob_repacketizer_create", "ob_repacketizer_destroy", "ob_repacketizer_init", "ob_repacketizer_cat",
-    "ob_repacketizer_get_nb_frames", "ob_repacketizer_out_range", "ob_repacketizer_out", "ob_repacketize_batch", "ob_repacketize_batch_device",
+    "ob_repacketizer_get_nb_frames", "ob_repacketizer_out_range", "ob_repacketizer_out", "ob_repacketize_batch", "ob_repacketize_batch_device", "ob_pcm_soft_clip_batch",
     "ob_encoder_create", "ob_encoder_destroy", "ob_encode_float", "ob_encode_float_multi", "ob_encode_float_device",
     "ob_encoder_set_bitrate", "ob_encoder_get_bitrate", "ob_encoder_set_complexity", "ob_encoder_get_complexity",
     "ob_encoder_set_vbr", "ob_encoder_get_vbr", "ob_encoder_set_vbr_constraint", "ob_encoder_get_vbr_constraint",
@@ -101,6 +101,7 @@ def lib():
     L.ob_repacketizer_out_range.argtypes = [vp, i32, i32, vp, i32]; L.ob_repacketizer_out_range.restype = i32
     L.ob_repacketizer_out.argtypes = [vp, vp, i32]; L.ob_repacketizer_out.restype = i32
     L.ob_repacketize_batch.argtypes = [i32, i32, i32, vp, vp, vp, i32, i32, vp, i32, vp]; L.ob_repacketize_batch.restype = i32
+    L.ob_pcm_soft_clip_batch.argtypes = [i32, i32, vp, i32, i32, vp]; L.ob_pcm_soft_clip_batch.restype = i32
     L.ob_repacketize_batch_device.argtypes = [i32, i32, vp, vp, vp, i32, i32, vp, i32, vp, vp]; L.ob_repacketize_batch_device.restype = i32
     L.ob_encoder_create.argtypes = [i32, i32, i32, i32, i32, i32, i32p]; L.ob_encoder_create.restype = vp
     L.ob_encoder_destroy.argtypes = [vp]; L.ob_encoder_destroy.restype = None

@@ -613,6 +613,40 @@ int32_t ob_decoder_kernel_ms(ObDecoder *d, float ms[3])
     return OB_OK;
 }
 
+// ---- opus_pcm_soft_clip for a batch (soft_clip, src/packet.rs:123-155; opus/src/opus.c:39-144): a warp per stream, one lane per channel for the
+// serial part.  pcm / softclip_mem: host, in place. ----
+}  // extern "C"
+__global__ void ob_k_soft_clip(float *pcm, float *mem, int S, int n, int C)
+{
+    const int w = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (w >= S) return;
+    float *x = pcm + (size_t)w * n * C;
+    for (int t = lane; t < n * C; t += 32) x[t] = fmaxf(-2.f, fminf(2.f, x[t]));
+    __syncwarp();
+    if (lane < C) mem[(size_t)w * C + lane] = ob_soft_clip_channel(x + lane, n, C, mem[(size_t)w * C + lane]);
+}
+extern "C" {
+int32_t ob_pcm_soft_clip_batch(int32_t device, int32_t n_streams, float *pcm, int32_t frame_size, int32_t channels, float *softclip_mem)
+{
+    if (n_streams <= 0 || frame_size <= 0 || channels <= 0 || channels > 32 || !pcm || !softclip_mem) return OB_BAD_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return OB_INTERNAL_ERROR;       // no CPU fallback
+    if (device < 0 || device >= ndev || cudaSetDevice(device) != cudaSuccess) return OB_BAD_ARG;
+    const size_t nb = (size_t)n_streams * frame_size * channels * sizeof(float), mb = (size_t)n_streams * channels * sizeof(float);
+    float *d_x = nullptr, *d_m = nullptr;
+    int32_t rc = OB_ALLOC_FAIL;
+    if (cudaMalloc(&d_x, nb) == cudaSuccess && cudaMalloc(&d_m, mb) == cudaSuccess) {
+        rc = OB_INTERNAL_ERROR;
+        if (cudaMemcpy(d_x, pcm, nb, cudaMemcpyHostToDevice) == cudaSuccess && cudaMemcpy(d_m, softclip_mem, mb, cudaMemcpyHostToDevice) == cudaSuccess) {
+            ob_k_soft_clip<<<(n_streams + 3) / 4, 128>>>(d_x, d_m, n_streams, frame_size, channels);
+            if (cudaGetLastError() == cudaSuccess && cudaMemcpy(pcm, d_x, nb, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                cudaMemcpy(softclip_mem, d_m, mb, cudaMemcpyDeviceToHost) == cudaSuccess) rc = OB_OK;
+        }
+    }
+    cudaFree(d_x); cudaFree(d_m);
+    return rc;
+}
+
 // ---- TOC helpers (opus/src/opus_decoder.c:1083-1129, opus/src/opus.c:173-192) ----
 int32_t ob_packet_get_nb_channels(const uint8_t *p) { return (p[0] & 0x4) ? 2 : 1; }
 int32_t ob_packet_get_samples_per_frame(const uint8_t *p, int32_t fs)

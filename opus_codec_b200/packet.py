@@ -136,3 +136,13 @@ def repacketize_batch(packets, group, pad_to=0, max_bytes=None, device=0):
     if r != 0:
         raise OpusError(r)
     return out, lens_out
+
+
+def soft_clip_batch(pcm, channels, softclip_mem, device=0):
+    """soft_clip (src/packet.rs:123-155) for a batch, in place on the GPU: pcm f32 [S, frame_size*channels], softclip_mem f32 [S, channels]."""
+    if pcm.dtype != np.float32 or softclip_mem.dtype != np.float32 or pcm.ndim != 2 or softclip_mem.shape != (pcm.shape[0], channels) \
+            or pcm.shape[1] % channels or not pcm.flags.c_contiguous or not softclip_mem.flags.c_contiguous:
+        raise OpusError(BAD_ARG)
+    r = _lib.lib().ob_pcm_soft_clip_batch(device, pcm.shape[0], pcm.ctypes.data, pcm.shape[1] // channels, channels, softclip_mem.ctypes.data)
+    if r != 0:
+        raise OpusError(r)

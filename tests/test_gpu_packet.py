@@ -131,3 +131,29 @@ def test_ogg_and_rtp_feed_the_batch_decoder():
     assert np.array_equal(res[0][0], res[1][0]) and (res[0][2] == res[1][2]).all()
     assert np.array_equal(res[2][0], res[3][0]) and (res[2][1] == 960).all()
     assert np.abs(res[0][0]).max() > 0 and not np.array_equal(res[0][0], res[2][0])
+
+
+def test_soft_clip_batch_matches_reference(have_ref):
+    """ob_pcm_soft_clip_batch == opus_pcm_soft_clip of the reference's C build, sample for sample, with the carried state across calls."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    import ctypes as C
+    from oracle import refpy
+    from opus_codec_b200.packet import soft_clip_batch
+    L = refpy.lib_c()
+    rng = np.random.default_rng(77)
+    for ch in (1, 2):
+        S, n = 9, 480
+        mem = np.zeros((S, ch), np.float32); rmem = mem.copy()
+        for call in range(4):
+            t = np.arange(n * ch, dtype=np.float32).reshape(1, -1)
+            amp = rng.uniform(0.2, 3.5, (S, 1)).astype(np.float32)
+            x = (amp * np.sin(t * rng.uniform(0.01, 0.3, (S, 1)) + call) + rng.normal(0, 0.2, (S, n * ch))).astype(np.float32)
+            x[0] *= 0.1                                           # never clips
+            want = x.copy()
+            for s in range(S):
+                L.opus_pcm_soft_clip(want[s].ctypes.data_as(C.POINTER(C.c_float)), n, ch, rmem[s].ctypes.data_as(C.POINTER(C.c_float)))
+            got = x.copy()
+            soft_clip_batch(got, ch, mem)
+            assert np.array_equal(got, want) and np.array_equal(mem, rmem), (ch, call)
+            assert np.abs(got).max() <= 1.0 and np.abs(x).max() > 1.5
