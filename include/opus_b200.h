@@ -173,6 +173,29 @@ int32_t ob_encoder_set_bandwidth(ObEncoder *enc, int32_t bandwidth);
 int32_t ob_encoder_set_force_channels(ObEncoder *enc, int32_t channels);
 int32_t ob_encoder_set_packet_loss_perc(ObEncoder *enc, int32_t percent);
 int32_t ob_encoder_set_lsb_depth(ObEncoder *enc, int32_t depth);
+int32_t ob_encoder_get_max_bandwidth(ObEncoder *enc, int32_t *value);
+int32_t ob_encoder_get_force_channels(ObEncoder *enc, int32_t *value);
+int32_t ob_encoder_get_packet_loss_perc(ObEncoder *enc, int32_t *value);
+int32_t ob_encoder_get_lsb_depth(ObEncoder *enc, int32_t *value);
+/* OPUS_SET/GET_SIGNAL (-1000 auto, 3001 voice, 3002 music; Encoder::set_signal src/encoder.rs), _PREDICTION_DISABLED, _PHASE_INVERSION_DISABLED,
+ * _DTX (generalised DTX: after 200 ms without activity a packet is its TOC byte alone, opus_encoder.c:2364-2378; needs complexity >= 7 or
+ * digital silence), _INBAND_FEC (0/1/2: a SILK feature -- on this path it only enters the mode decision of the AUDIO / VOIP applications),
+ * _EXPERT_FRAME_DURATION (5000 = from the call's frame_size, 5001..5009 = 2.5..120 ms: must equal the call's frame_size, a shorter one is
+ * OB_UNIMPLEMENTED), OPUS_GET_LOOKAHEAD (120, or 312 for AUDIO / VOIP), OPUS_GET_IN_DTX (one flag per stream). */
+int32_t ob_encoder_set_signal(ObEncoder *enc, int32_t signal);
+int32_t ob_encoder_get_signal(ObEncoder *enc, int32_t *value);
+int32_t ob_encoder_set_prediction_disabled(ObEncoder *enc, int32_t disabled);
+int32_t ob_encoder_get_prediction_disabled(ObEncoder *enc, int32_t *value);
+int32_t ob_encoder_set_phase_inversion_disabled(ObEncoder *enc, int32_t disabled);
+int32_t ob_encoder_get_phase_inversion_disabled(ObEncoder *enc, int32_t *value);
+int32_t ob_encoder_set_dtx(ObEncoder *enc, int32_t enabled);
+int32_t ob_encoder_get_dtx(ObEncoder *enc, int32_t *value);
+int32_t ob_encoder_set_inband_fec(ObEncoder *enc, int32_t mode);
+int32_t ob_encoder_get_inband_fec(ObEncoder *enc, int32_t *value);
+int32_t ob_encoder_set_expert_frame_duration(ObEncoder *enc, int32_t duration);
+int32_t ob_encoder_get_expert_frame_duration(ObEncoder *enc, int32_t *value);
+int32_t ob_encoder_get_lookahead(ObEncoder *enc, int32_t *value);
+int32_t ob_encoder_in_dtx(ObEncoder *enc, int32_t *out);
 /* OPUS_GET_FINAL_RANGE (Encoder::final_range src/encoder.rs:411-419) and OPUS_RESET_STATE (Encoder::reset :689-698). */
 int32_t ob_encoder_final_range(ObEncoder *enc, uint32_t *out);
 int32_t ob_encoder_reset(ObEncoder *enc, const int32_t *idx, int32_t n);

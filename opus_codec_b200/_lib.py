@@ -29,6 +29,7 @@ SYMBOLS = [
     "ob_encoder_set_vbr", "ob_encoder_get_vbr", "ob_encoder_set_vbr_constraint", "ob_encoder_get_vbr_constraint",
     "ob_encoder_set_max_bandwidth", "ob_encoder_set_bandwidth", "ob_encoder_set_force_channels",
     "ob_encoder_set_packet_loss_perc", "ob_encoder_set_lsb_depth", "ob_encoder_final_range", "ob_encoder_reset",
+    "ob_encoder_get_max_bandwidth", "ob_encoder_get_force_channels", "ob_encoder_get_packet_loss_perc", "ob_encoder_get_lsb_depth", "ob_encoder_set_signal", "ob_encoder_get_signal", "ob_encoder_set_prediction_disabled", "ob_encoder_get_prediction_disabled", "ob_encoder_set_phase_inversion_disabled", "ob_encoder_get_phase_inversion_disabled", "ob_encoder_set_dtx", "ob_encoder_get_dtx", "ob_encoder_set_inband_fec", "ob_encoder_get_inband_fec", "ob_encoder_set_expert_frame_duration", "ob_encoder_get_expert_frame_duration", "ob_encoder_get_lookahead", "ob_encoder_in_dtx",
     "ob_encoder_streams", "ob_encoder_channels", "ob_encoder_kernel_ms", "ob_encoder_launches", "ob_encoder_cuda_stream",
 ]
 
@@ -90,6 +91,24 @@ def lib():
         getattr(L, n).argtypes = [vp]; getattr(L, n).restype = i32
     L.ob_packet_get_samples_per_frame.argtypes = [vp, i32]; L.ob_packet_get_samples_per_frame.restype = i32
     L.ob_packet_get_nb_frames.argtypes = [vp, i32]; L.ob_packet_get_nb_frames.restype = i32
+    L.ob_encoder_get_max_bandwidth.argtypes = [vp, vp]; L.ob_encoder_get_max_bandwidth.restype = i32
+    L.ob_encoder_get_force_channels.argtypes = [vp, vp]; L.ob_encoder_get_force_channels.restype = i32
+    L.ob_encoder_get_packet_loss_perc.argtypes = [vp, vp]; L.ob_encoder_get_packet_loss_perc.restype = i32
+    L.ob_encoder_get_lsb_depth.argtypes = [vp, vp]; L.ob_encoder_get_lsb_depth.restype = i32
+    L.ob_encoder_set_signal.argtypes = [vp, i32]; L.ob_encoder_set_signal.restype = i32
+    L.ob_encoder_get_signal.argtypes = [vp, vp]; L.ob_encoder_get_signal.restype = i32
+    L.ob_encoder_set_prediction_disabled.argtypes = [vp, i32]; L.ob_encoder_set_prediction_disabled.restype = i32
+    L.ob_encoder_get_prediction_disabled.argtypes = [vp, vp]; L.ob_encoder_get_prediction_disabled.restype = i32
+    L.ob_encoder_set_phase_inversion_disabled.argtypes = [vp, i32]; L.ob_encoder_set_phase_inversion_disabled.restype = i32
+    L.ob_encoder_get_phase_inversion_disabled.argtypes = [vp, vp]; L.ob_encoder_get_phase_inversion_disabled.restype = i32
+    L.ob_encoder_set_dtx.argtypes = [vp, i32]; L.ob_encoder_set_dtx.restype = i32
+    L.ob_encoder_get_dtx.argtypes = [vp, vp]; L.ob_encoder_get_dtx.restype = i32
+    L.ob_encoder_set_inband_fec.argtypes = [vp, i32]; L.ob_encoder_set_inband_fec.restype = i32
+    L.ob_encoder_get_inband_fec.argtypes = [vp, vp]; L.ob_encoder_get_inband_fec.restype = i32
+    L.ob_encoder_set_expert_frame_duration.argtypes = [vp, i32]; L.ob_encoder_set_expert_frame_duration.restype = i32
+    L.ob_encoder_get_expert_frame_duration.argtypes = [vp, vp]; L.ob_encoder_get_expert_frame_duration.restype = i32
+    L.ob_encoder_get_lookahead.argtypes = [vp, vp]; L.ob_encoder_get_lookahead.restype = i32
+    L.ob_encoder_in_dtx.argtypes = [vp, vp]; L.ob_encoder_in_dtx.restype = i32
     L.ob_packet_parse.argtypes = [vp, i32, vp, vp, vp, vp]; L.ob_packet_parse.restype = i32
     L.ob_packet_pad.argtypes = [vp, i32, i32]; L.ob_packet_pad.restype = i32
     L.ob_packet_unpad.argtypes = [vp, i32]; L.ob_packet_unpad.restype = i32

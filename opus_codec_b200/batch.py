@@ -249,6 +249,35 @@ class BatchEncoder:
     def set_lsb_depth(self, d):
         _check(self._L.ob_encoder_set_lsb_depth(self._h, int(d)))
 
+    def _get(self, fn):
+        v = C.c_int32(0)
+        _check(fn(self._h, C.byref(v)))
+        return v.value
+
+    # the remaining CTLs of Encoder (src/encoder.rs): same names, same value ranges, BadArg outside them
+    def max_bandwidth(self): return self._get(self._L.ob_encoder_get_max_bandwidth)
+    def force_channels(self): return self._get(self._L.ob_encoder_get_force_channels)
+    def packet_loss_perc(self): return self._get(self._L.ob_encoder_get_packet_loss_perc)
+    def lsb_depth(self): return self._get(self._L.ob_encoder_get_lsb_depth)
+    def set_signal(self, v): _check(self._L.ob_encoder_set_signal(self._h, int(v)))
+    def signal(self): return self._get(self._L.ob_encoder_get_signal)
+    def set_prediction_disabled(self, on): _check(self._L.ob_encoder_set_prediction_disabled(self._h, int(bool(on))))
+    def prediction_disabled(self): return bool(self._get(self._L.ob_encoder_get_prediction_disabled))
+    def set_phase_inversion_disabled(self, on): _check(self._L.ob_encoder_set_phase_inversion_disabled(self._h, int(bool(on))))
+    def phase_inversion_disabled(self): return bool(self._get(self._L.ob_encoder_get_phase_inversion_disabled))
+    def set_dtx(self, on): _check(self._L.ob_encoder_set_dtx(self._h, int(bool(on))))
+    def dtx(self): return bool(self._get(self._L.ob_encoder_get_dtx))
+    def set_inband_fec(self, mode): _check(self._L.ob_encoder_set_inband_fec(self._h, int(mode)))
+    def inband_fec(self): return self._get(self._L.ob_encoder_get_inband_fec)
+    def set_expert_frame_duration(self, v): _check(self._L.ob_encoder_set_expert_frame_duration(self._h, int(v)))
+    def expert_frame_duration(self): return self._get(self._L.ob_encoder_get_expert_frame_duration)
+    def lookahead(self): return self._get(self._L.ob_encoder_get_lookahead)
+
+    def in_dtx(self):
+        out = np.zeros(self.n_streams, np.int32)
+        _check(self._L.ob_encoder_in_dtx(self._h, _vp(out)))
+        return out.astype(bool)
+
     # -- encode ------------------------------------------------------------------------------------------------------
     def encode_float_multi(self, pcm, frame_size, max_bytes=1276):
         """pcm: f32 [S, F, frame_size*channels] in [-1,1].  Returns (packets u8 [S, F, max_bytes], lens i32 [S, F], ranges u32 [S, F]);

@@ -494,12 +494,17 @@ struct ObOpusEncCfg {
     int32_t bitrate;           // OPUS_SET_BITRATE: bits/s, or -1000 (OPUS_AUTO) / -1 (OPUS_BITRATE_MAX)
     int32_t complexity, vbr, vbr_constraint, max_bandwidth, user_bandwidth, force_channels, packet_loss, lsb_depth;
     int32_t application;       // 2048 VOIP, 2049 AUDIO, 2051 RESTRICTED_LOWDELAY (0 is read as 2051)
+    int32_t signal_type;       // OPUS_SET_SIGNAL: 0 auto, 3001 voice, 3002 music
+    int32_t prediction_disabled, phase_inversion_disabled, use_dtx, inband_fec;
+    int32_t variable_duration; // OPUS_SET_EXPERT_FRAME_DURATION: 0 / 5000 = FRAMESIZE_ARG, 5001 (2.5 ms) ... 5009 (120 ms)
 };
 struct ObOpusEncState {
     int32_t stream_channels, first, auto_bandwidth, bandwidth, hybrid_stereo_width_Q14;
     int32_t voice_ratio, detected_bandwidth;     // from the signal analysis (opus_encoder.c:1146-1176); voice_ratio = -1: unknown
     ObTonalState *tonal;                         // st->analysis when the analysis runs inline (host emulation); the GPU runs it in its own kernel
     int32_t prev_mode;                           // 0 before the first packet, then 1002 (MODE_CELT_ONLY)
+    int32_t nb_no_activity_ms_Q1;                // generalised DTX (opus_encoder.c:988-1013)
+    float peak_signal_energy;
     ObStereoWidth width_mem;
     float *delay;                                // st->delay_buffer [OB_ENC_BUFFER * channels] of the AUDIO / VOIP applications (global memory); null: low delay
 };
@@ -539,10 +544,19 @@ OB_DEV void ob_stereo_fade(float *buf, float g1, float g2, int frame_size)     /
 // data: max_data_bytes of room for TOC + payload.  bitrate_bps / equiv_rate: the packet-level values (a frame of a multi-frame packet
 // inherits them).  Returns the frame's packet length (TOC included) or a negative OPUS_* code.
 OB_DEV_NOINLINE int ob_opus_encode_frame(const ObOpusEncCfg &cfg, ObOpusEncState &os, ObEncState &st, ObEncScratch &S, const float *pcm, int frame_size,
-        uint8_t *data, int max_data_bytes, int32_t bitrate_bps, int32_t equiv_rate, const ObAnalysisInfo &analysis_info)
+        uint8_t *data, int max_data_bytes, int32_t bitrate_bps, int32_t equiv_rate, const ObAnalysisInfo &analysis_info, int is_silence)
 {
     const int channels = st.channels, frame_rate = 48000 / frame_size;
     const int curr_bandwidth = os.bandwidth;
+    int activity = -1;                                                                                        // VAD_NO_DECISION (:1748-1762)
+    if (is_silence) activity = 0;
+    else if (analysis_info.valid) {
+        activity = analysis_info.activity_probability >= .1f;
+        if (!activity) {
+            const float noise_energy = ob_inner_prod(pcm, pcm, frame_size * channels) / (frame_size * channels);
+            activity = os.peak_signal_energy < (316.23f * noise_energy);
+        }
+    }
 
     ObRangeEnc enc;
     enc.init(data + 1, (uint32_t)(max_data_bytes - 1));
@@ -581,6 +595,8 @@ OB_DEV_NOINLINE int ob_opus_encode_frame(const ObOpusEncCfg &cfg, ObOpusEncState
     st.stream_channels = os.stream_channels;
     st.complexity = cfg.complexity; st.lsb_depth = cfg.lsb_depth; st.loss_rate = cfg.packet_loss;
     st.vbr = cfg.vbr; st.constrained_vbr = cfg.vbr_constraint;
+    st.disable_pf = st.force_intra = cfg.prediction_disabled != 0;                                            // CELT_SET_PREDICTION(reducedDependency ? 0 : 2) (:2109-2116)
+    st.disable_inv = cfg.phase_inversion_disabled != 0;
     st.bitrate = cfg.vbr ? bitrate_bps : OB_BITRATE_MAX;
     st.an = analysis_info;                                                                                    // CELT_SET_ANALYSIS (:2229)
     int ret = ob_celt_encode(st, S, pcm_buf, frame_size, nb_compr_bytes, enc);
@@ -595,6 +611,17 @@ OB_DEV_NOINLINE int ob_opus_encode_frame(const ObOpusEncCfg &cfg, ObOpusEncState
     st.final_range = enc.rng;
     os.first = 0;
     os.prev_mode = 1002;
+    if (cfg.use_dtx && (analysis_info.valid || is_silence)) {                                                 // DTX decision (:2364-2378)
+        int dtx = 0;
+        if (!activity) {
+            os.nb_no_activity_ms_Q1 += 2 * 1000 * frame_size / 48000;
+            if (os.nb_no_activity_ms_Q1 > 10 * 20 * 2) {
+                if (os.nb_no_activity_ms_Q1 <= (10 + 20) * 20 * 2) dtx = 1;
+                else os.nb_no_activity_ms_Q1 = 10 * 20 * 2;
+            }
+        } else os.nb_no_activity_ms_Q1 = 0;
+        if (dtx) { st.final_range = 0; return 1; }                                                            // data[0] already holds the TOC
+    } else os.nb_no_activity_ms_Q1 = 0;
     ret += 1;
     if (!cfg.vbr && ret != max_data_bytes) return OB_UNIMPLEMENTED;     // opus_packet_pad: CELT CBR always fills its budget on this path
     return ret;
@@ -630,9 +657,9 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
     ObAnalysisInfo analysis_info;
     analysis_info.valid = 0;
     int read_pos_bak = -1, read_subframe_bak = -1;
+    int is_silence = 0;
     {
         const int lsb_depth = cfg.lsb_depth;
-        int is_silence = 0;
         if (cfg.complexity >= 7) {
             is_silence = ob_maxabs(pcm, frame_size * channels) <= (float)1 / (1 << lsb_depth);
             if (pre_info) analysis_info = *pre_info;
@@ -640,12 +667,14 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
                 read_pos_bak = os.tonal->read_pos; read_subframe_bak = os.tonal->read_subframe;
                 ob_run_analysis(*os.tonal, pcm, frame_size, channels, lsb_depth, analysis_info, S.pre);
             }
+            if (!is_silence && analysis_info.activity_probability > .1f)                                      // peak signal energy (:1127-1130)
+                os.peak_signal_energy = ob_fmax(.999f * os.peak_signal_energy, ob_inner_prod(pcm, pcm, frame_size * channels) / (frame_size * channels));
         } else if (os.tonal && os.tonal->initialized) ob_tonal_reset(*os.tonal);
         if (!is_silence) os.voice_ratio = -1;
         os.detected_bandwidth = 0;
         if (analysis_info.valid) {
             const float prob = os.first ? analysis_info.music_prob : analysis_info.music_prob_max;           // prev_mode == 0 : == MODE_CELT_ONLY
-            os.voice_ratio = (int)floor(.5 + (double)(100 * (1 - prob)));
+            if (cfg.signal_type == 0) os.voice_ratio = (int)floor(.5 + (double)(100 * (1 - prob)));
             const int ab = analysis_info.bandwidth;
             os.detected_bandwidth = ab <= 12 ? 1101 : ab <= 14 ? 1102 : ab <= 16 ? 1103 : ab <= 18 ? 1104 : 1105;
         }
@@ -689,8 +718,10 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
         return ret;
     }
     int32_t equiv_rate = ob_compute_equiv_rate(bitrate_bps, channels, frame_rate, cfg.vbr, 0, cfg.complexity, cfg.packet_loss);
-    int voice_est;                                                                                            // :1276-1289, signal AUTO
-    if (os.voice_ratio >= 0) { voice_est = os.voice_ratio * 327 >> 8; if (cfg.application == 2049) voice_est = ob_imin(voice_est, 115); }
+    int voice_est;                                                                                            // :1276-1289
+    if (cfg.signal_type == 3001) voice_est = 127;
+    else if (cfg.signal_type == 3002) voice_est = 0;
+    else if (os.voice_ratio >= 0) { voice_est = os.voice_ratio * 327 >> 8; if (cfg.application == 2049) voice_est = ob_imin(voice_est, 115); }
     else voice_est = cfg.application == 2048 ? 115 : 48;
     if (cfg.force_channels > 0 && channels == 2) os.stream_channels = cfg.force_channels;
     else if (channels == 2) {
@@ -706,6 +737,8 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
         if (cfg.application == 2048) threshold += 8000;
         if (os.prev_mode == 1002) threshold -= 4000;
         int celt_only = equiv_rate >= threshold;
+        if (cfg.inband_fec && cfg.packet_loss > (128 - voice_est) >> 4 && (cfg.inband_fec != 2 || voice_est > 25)) celt_only = 0;
+        if (cfg.use_dtx && !(analysis_info.valid || is_silence) && voice_est > 100) celt_only = 0;           // SILK's own DTX
         if (max_data_bytes < (frame_rate > 50 ? 9000 : 6000) * frame_size / (Fs * 8)) celt_only = 1;
         if (frame_size < Fs / 100) celt_only = 1;
         if (!celt_only) return OB_UNIMPLEMENTED;                                                              // SILK / hybrid: not on this path
@@ -737,7 +770,7 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
         os.bandwidth = ob_imin(os.bandwidth, os.detected_bandwidth);
     }
     if (os.bandwidth == 1102) os.bandwidth = 1103;
-    if (frame_size <= 960) return ob_opus_encode_frame(cfg, os, st, S, pcm, frame_size, data, max_data_bytes, bitrate_bps, equiv_rate, analysis_info);
+    if (frame_size <= 960) return ob_opus_encode_frame(cfg, os, st, S, pcm, frame_size, data, max_data_bytes, bitrate_bps, equiv_rate, analysis_info, is_silence);
 
     // ---- 40-120 ms: 20 ms frames encoded one by one and repacketized into one code-1/2/3 packet (opus_encoder.c:1551-1679,
     // opus_repacketizer_out_range_impl, repacketizer.c:112-320) ----
@@ -749,18 +782,19 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
     if (max_len_sum > (int)sizeof(S.multi_tmp) || max_len_sum < nb_frames) return OB_BUFFER_TOO_SMALL;
     uint8_t *curr_data = S.multi_tmp;
     int16_t flen[6];
-    int tot = 0;
+    int tot = 0, dtx_count = 0;
     for (int i = 0; i < nb_frames; i++) {
         int curr_max = ob_imin(3 * bitrate_bps / (3 * 8 * 48000 / 960), max_len_sum / nb_frames);
         curr_max = ob_imin(max_len_sum - tot, curr_max);
         if (read_pos_bak != -1) ob_tonality_get_info(*os.tonal, analysis_info, 960);
-        const int tmp_len = ob_opus_encode_frame(cfg, os, st, S, pcm + (size_t)i * channels * 960, 960, curr_data, curr_max, bitrate_bps, equiv_rate, analysis_info);
+        const int tmp_len = ob_opus_encode_frame(cfg, os, st, S, pcm + (size_t)i * channels * 960, 960, curr_data, curr_max, bitrate_bps, equiv_rate, analysis_info, is_silence);
         if (tmp_len < 0) return OB_INTERNAL_ERROR;
+        if (tmp_len == 1) dtx_count++;
         flen[i] = (int16_t)(tmp_len - 1);                           // opus_repacketizer_cat: the frame without its TOC
         tot += tmp_len;
         curr_data += tmp_len;
     }
-    const int toc = S.multi_tmp[0] & 0xFC, pad = !cfg.vbr, maxlen = repacketize_len;
+    const int toc = S.multi_tmp[0] & 0xFC, pad = !cfg.vbr && dtx_count != nb_frames, maxlen = repacketize_len;
     uint8_t *ptr = data;
     int tot_size = 0;
     if (nb_frames == 2) {

@@ -109,6 +109,7 @@ __global__ void ob_k_enc_reset(ObEncStream *streams, float *delay, const int32_t
     es.os.stream_channels = channels; es.os.first = 1; es.os.auto_bandwidth = 0; es.os.bandwidth = 1105; es.os.hybrid_stereo_width_Q14 = 1 << 14;
     es.os.voice_ratio = -1; es.os.detected_bandwidth = 0; es.os.tonal = nullptr;
     es.os.prev_mode = 0; es.os.width_mem = ObStereoWidth{0, 0, 0, 0, 0}; es.os.delay = nullptr;
+    es.os.nb_no_activity_ms_Q1 = 0; es.os.peak_signal_energy = 0;
     if (delay) for (int i = 0; i < OB_ENC_BUFFER * channels; i++) delay[(size_t)s * OB_ENC_BUFFER * channels + i] = 0;
 }
 
@@ -116,6 +117,12 @@ __global__ void ob_k_enc_gather(const ObEncStream *streams, uint32_t *ranges, in
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s < S) ranges[s] = streams[s].st.final_range;
+}
+
+__global__ void ob_k_enc_gather_dtx(const ObEncStream *streams, uint32_t *out, int S)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) out[s] = streams[s].os.nb_no_activity_ms_Q1 >= 10 * 20 * 2;          // OPUS_GET_IN_DTX, "DTX determined by Opus" (opus_encoder.c:3038-3042)
 }
 
 struct ObEncoder {
@@ -246,6 +253,39 @@ int32_t ob_encoder_set_bandwidth(ObEncoder *e, int32_t bw) { if (!e || (bw != -1
 int32_t ob_encoder_set_force_channels(ObEncoder *e, int32_t ch) { if (!e || (ch != -1000 && (ch < 1 || ch > e->CC))) return OB_BAD_ARG; e->cfg.force_channels = ch == -1000 ? 0 : ch; return OB_OK; }
 int32_t ob_encoder_set_packet_loss_perc(ObEncoder *e, int32_t p) { if (!e || p < 0 || p > 100) return OB_BAD_ARG; e->cfg.packet_loss = p; return OB_OK; }
 int32_t ob_encoder_set_lsb_depth(ObEncoder *e, int32_t d) { if (!e || d < 8 || d > 24) return OB_BAD_ARG; e->cfg.lsb_depth = d; return OB_OK; }
+int32_t ob_encoder_get_max_bandwidth(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.max_bandwidth; return OB_OK; }
+int32_t ob_encoder_get_force_channels(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.force_channels ? e->cfg.force_channels : -1000; return OB_OK; }
+int32_t ob_encoder_get_packet_loss_perc(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.packet_loss; return OB_OK; }
+int32_t ob_encoder_get_lsb_depth(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.lsb_depth; return OB_OK; }
+// OPUS_SET_SIGNAL / _PREDICTION_DISABLED / _PHASE_INVERSION_DISABLED / _DTX / _INBAND_FEC / _EXPERT_FRAME_DURATION (opus_encoder.c:2815-2940)
+int32_t ob_encoder_set_signal(ObEncoder *e, int32_t v) { if (!e || (v != -1000 && v != 3001 && v != 3002)) return OB_BAD_ARG; e->cfg.signal_type = v == -1000 ? 0 : v; return OB_OK; }
+int32_t ob_encoder_get_signal(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.signal_type ? e->cfg.signal_type : -1000; return OB_OK; }
+int32_t ob_encoder_set_prediction_disabled(ObEncoder *e, int32_t v) { if (!e || v < 0 || v > 1) return OB_BAD_ARG; e->cfg.prediction_disabled = v; return OB_OK; }
+int32_t ob_encoder_get_prediction_disabled(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.prediction_disabled; return OB_OK; }
+int32_t ob_encoder_set_phase_inversion_disabled(ObEncoder *e, int32_t v) { if (!e || v < 0 || v > 1) return OB_BAD_ARG; e->cfg.phase_inversion_disabled = v; return OB_OK; }
+int32_t ob_encoder_get_phase_inversion_disabled(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.phase_inversion_disabled; return OB_OK; }
+int32_t ob_encoder_set_dtx(ObEncoder *e, int32_t v) { if (!e || v < 0 || v > 1) return OB_BAD_ARG; e->cfg.use_dtx = v; return OB_OK; }
+int32_t ob_encoder_get_dtx(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.use_dtx; return OB_OK; }
+int32_t ob_encoder_set_inband_fec(ObEncoder *e, int32_t v) { if (!e || v < 0 || v > 2) return OB_BAD_ARG; e->cfg.inband_fec = v; return OB_OK; }
+int32_t ob_encoder_get_inband_fec(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.inband_fec; return OB_OK; }
+int32_t ob_encoder_set_expert_frame_duration(ObEncoder *e, int32_t v) { if (!e || v < 5000 || v > 5009) return OB_BAD_ARG; e->cfg.variable_duration = v; return OB_OK; }
+int32_t ob_encoder_get_expert_frame_duration(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.variable_duration ? e->cfg.variable_duration : 5000; return OB_OK; }
+// OPUS_GET_LOOKAHEAD (:2835-2846)
+int32_t ob_encoder_get_lookahead(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = 48000 / 400 + (e->cfg.application != 2051 ? OB_ENC_DELAY : 0); return OB_OK; }
+
+// frame_size_select (opus_encoder.c:704-728)
+static int ob_frame_size_select(int frame_size, int variable_duration, int Fs)
+{
+    int new_size;
+    if (frame_size < Fs / 400) return -1;
+    if (variable_duration == 0 || variable_duration == 5000) new_size = frame_size;
+    else if (variable_duration >= 5001 && variable_duration <= 5009) new_size = variable_duration <= 5005 ? (Fs / 400) << (variable_duration - 5001) : (variable_duration - 5001 - 2) * Fs / 50;
+    else return -1;
+    if (new_size > frame_size) return -1;
+    if (400 * new_size != Fs && 200 * new_size != Fs && 100 * new_size != Fs && 50 * new_size != Fs && 25 * new_size != Fs && 50 * new_size != 3 * Fs &&
+        50 * new_size != 4 * Fs && 50 * new_size != 5 * Fs && 50 * new_size != 6 * Fs) return -1;
+    return new_size;
+}
 
 // One frame window [f0, f0+Fc) of every stream.  At complexity >= 7 the analysis kernel of the window runs on its own stream, right
 // away (it needs only the PCM), and the encode kernel of the window waits for it; while the encoder works on window k the analysis
@@ -291,6 +331,11 @@ int32_t ob_encode_float_device(ObEncoder *e, int32_t n_frames, const float *d_pc
                                int32_t *d_lens_out, uint32_t *d_ranges_out, int32_t sync)
 {
     if (!e || !d_pcm || !d_out || !d_lens_out || n_frames <= 0 || n_frames > e->max_frames || max_bytes <= 0) return OB_BAD_ARG;
+    if (e->cfg.variable_duration > 5000) {                          // OPUS_SET_EXPERT_FRAME_DURATION: the duration must be the one the caller's buffers have
+        const int sel = ob_frame_size_select(frame_size, e->cfg.variable_duration, 48000);
+        if (sel <= 0) return OB_BAD_ARG;
+        if (sel != frame_size) return OB_UNIMPLEMENTED;              // libopus would code the first `sel` samples of each longer buffer
+    }
     OB_CUDA(cudaSetDevice(e->device));
     // the caller's PCM is ready in stream order of e->stream; with the analysis on (complexity >= 7) the call runs in frame windows so
     // that the analysis of window k+1 overlaps the encoder of window k
@@ -315,6 +360,11 @@ static int32_t ob_encode_submit(ObEncoder *e, int32_t n_frames, const float *pcm
                                 int32_t max_bytes, int32_t *lens_out, uint32_t *ranges_out)
 {
     if (!e || (!pcm && !pcm16) || !out || !lens_out || n_frames <= 0 || n_frames > e->max_frames || max_bytes <= 0 || frame_size <= 0) return OB_BAD_ARG;
+    if (e->cfg.variable_duration > 5000) {                          // OPUS_SET_EXPERT_FRAME_DURATION: the duration must be the one the caller's buffers have
+        const int sel = ob_frame_size_select(frame_size, e->cfg.variable_duration, 48000);
+        if (sel <= 0) return OB_BAD_ARG;
+        if (sel != frame_size) return OB_UNIMPLEMENTED;              // libopus would code the first `sel` samples of each longer buffer
+    }
     OB_CUDA(cudaSetDevice(e->device));
     const size_t total = (size_t)e->S * n_frames, pcm_floats = total * (size_t)frame_size * e->CC, out_bytes = total * (size_t)max_bytes;
     if (pcm_floats > e->pcm_cap) { cudaFree(e->d_pcm); e->d_pcm = nullptr; e->pcm_cap = 0; OB_CUDA(cudaMalloc(&e->d_pcm, pcm_floats * sizeof(float))); e->pcm_cap = pcm_floats; }
@@ -377,6 +427,18 @@ int32_t ob_encoder_final_range(ObEncoder *e, uint32_t *out)
     if (!e || !out) return OB_BAD_ARG;
     OB_CUDA(cudaSetDevice(e->device));
     ob_k_enc_gather<<<(e->S + 127) / 128, 128, 0, e->stream>>>(e->d_streams, e->d_ranges, e->S);
+    e->launches += 1;
+    OB_CUDA(cudaMemcpyAsync(out, e->d_ranges, sizeof(uint32_t) * e->S, cudaMemcpyDeviceToHost, e->stream));
+    OB_CUDA(cudaStreamSynchronize(e->stream));
+    return OB_OK;
+}
+
+int32_t ob_encoder_in_dtx(ObEncoder *e, int32_t *out)
+{
+    if (!e || !out) return OB_BAD_ARG;
+    OB_CUDA(cudaSetDevice(e->device));
+    if (!e->cfg.use_dtx) { for (int s = 0; s < e->S; s++) out[s] = 0; return OB_OK; }
+    ob_k_enc_gather_dtx<<<(e->S + 127) / 128, 128, 0, e->stream>>>(e->d_streams, e->d_ranges, e->S);
     e->launches += 1;
     OB_CUDA(cudaMemcpyAsync(out, e->d_ranges, sizeof(uint32_t) * e->S, cudaMemcpyDeviceToHost, e->stream));
     OB_CUDA(cudaStreamSynchronize(e->stream));

@@ -137,6 +137,19 @@ REF_EXPORT void ref_set_encoder_extras(int bandwidth, int force_channels)
     g_extra_bandwidth = bandwidth; g_extra_force_channels = force_channels;
 }
 
+/* More optional encoder CTLs (all 0 / OPUS_AUTO = leave alone): OPUS_SET_SIGNAL (3001 voice / 3002 music), OPUS_SET_PREDICTION_DISABLED,
+ * OPUS_SET_PHASE_INVERSION_DISABLED, OPUS_SET_DTX, OPUS_SET_INBAND_FEC, OPUS_SET_EXPERT_FRAME_DURATION (5000..5009), OPUS_SET_PACKET_LOSS_PERC. */
+static int g_x_signal = 0, g_x_pred_disabled = 0, g_x_phase_inv_disabled = 0, g_x_dtx = 0, g_x_fec = 0, g_x_duration = 0, g_x_loss = 0;
+REF_EXPORT void ref_set_encoder_extras2(int signal, int pred_disabled, int phase_inv_disabled, int dtx, int fec, int duration, int loss)
+{
+    g_x_signal = signal; g_x_pred_disabled = pred_disabled; g_x_phase_inv_disabled = phase_inv_disabled; g_x_dtx = dtx; g_x_fec = fec;
+    g_x_duration = duration; g_x_loss = loss;
+}
+/* OPUS_GET_IN_DTX / OPUS_GET_LOOKAHEAD of the encoder after the last ref_encode_stream call. */
+static int g_last_in_dtx = 0, g_last_lookahead = 0;
+REF_EXPORT int ref_last_in_dtx(void) { return g_last_in_dtx; }
+REF_EXPORT int ref_last_lookahead(void) { return g_last_lookahead; }
+
 static OpusEncoder *make_encoder(int channels, int application, int bitrate, int vbr, int complexity)
 {
     int err = 0;
@@ -150,6 +163,13 @@ static OpusEncoder *make_encoder(int channels, int application, int bitrate, int
         opus_encoder_ctl(e, OPUS_SET_FORCE_MODE(MODE_CELT_ONLY));
     if (g_extra_bandwidth) opus_encoder_ctl(e, OPUS_SET_BANDWIDTH(g_extra_bandwidth));
     if (g_extra_force_channels) opus_encoder_ctl(e, OPUS_SET_FORCE_CHANNELS(g_extra_force_channels));
+    if (g_x_signal) opus_encoder_ctl(e, OPUS_SET_SIGNAL(g_x_signal));
+    if (g_x_pred_disabled) opus_encoder_ctl(e, OPUS_SET_PREDICTION_DISABLED(1));
+    if (g_x_phase_inv_disabled) opus_encoder_ctl(e, OPUS_SET_PHASE_INVERSION_DISABLED(1));
+    if (g_x_dtx) opus_encoder_ctl(e, OPUS_SET_DTX(1));
+    if (g_x_fec) opus_encoder_ctl(e, OPUS_SET_INBAND_FEC(g_x_fec));
+    if (g_x_duration) opus_encoder_ctl(e, OPUS_SET_EXPERT_FRAME_DURATION(g_x_duration));
+    if (g_x_loss) opus_encoder_ctl(e, OPUS_SET_PACKET_LOSS_PERC(g_x_loss));
     return e;
 }
 
@@ -170,6 +190,7 @@ REF_EXPORT int ref_encode_stream(const float *pcm, int nframes, int frame_size, 
         opus_encoder_ctl(e, OPUS_GET_FINAL_RANGE(&rng));
         if (ranges) ranges[f] = rng;
     }
+    { opus_int32 v = 0; opus_encoder_ctl(e, OPUS_GET_IN_DTX(&v)); g_last_in_dtx = v; opus_encoder_ctl(e, OPUS_GET_LOOKAHEAD(&v)); g_last_lookahead = v; }
     opus_encoder_destroy(e);
     return 0;
 }

@@ -120,12 +120,18 @@ int emul_opus_encode_stream(const float *pcm, int nframes, int frame_size, int c
 {
     return emul_opus_encode_stream_app(pcm, nframes, frame_size, channels, 2051, bitrate, vbr, complexity, out, max_bytes, lens, ranges);
 }
+static int g_signal = 0, g_pred_disabled = 0, g_phase_inv_disabled = 0, g_dtx = 0, g_fec = 0, g_loss = 0, g_last_in_dtx = 0;
+void emul_set_encoder_extras(int signal, int pred_disabled, int phase_inv_disabled, int dtx, int fec, int loss)
+{
+    g_signal = signal; g_pred_disabled = pred_disabled; g_phase_inv_disabled = phase_inv_disabled; g_dtx = dtx; g_fec = fec; g_loss = loss;
+}
+int emul_last_in_dtx(void) { return g_last_in_dtx; }
 int emul_opus_encode_stream_app(const float *pcm, int nframes, int frame_size, int channels, int application, int bitrate, int vbr, int complexity,
                                 unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
 {
     ObEncState *st = (ObEncState *)calloc(1, sizeof(ObEncState));
     ObEncScratch *S = (ObEncScratch *)calloc(1, sizeof(ObEncScratch));
-    ObOpusEncCfg cfg = {bitrate, complexity, vbr != 0, vbr == 2, 1105, 0, 0, 0, 24, application};
+    ObOpusEncCfg cfg = {bitrate, complexity, vbr != 0, vbr == 2, 1105, 0, 0, g_loss, 24, application, g_signal, g_pred_disabled, g_phase_inv_disabled, g_dtx, g_fec, 0};
     ObOpusEncState *osp = (ObOpusEncState *)calloc(1, sizeof(ObOpusEncState));
     ObOpusEncState &os = *osp;
     os.stream_channels = channels; os.first = 1; os.auto_bandwidth = 0; os.bandwidth = 1105; os.hybrid_stereo_width_Q14 = 1 << 14; os.voice_ratio = -1;
@@ -141,6 +147,7 @@ int emul_opus_encode_stream_app(const float *pcm, int nframes, int frame_size, i
         lens[f] = n;
         ranges[f] = st->final_range;
     }
+    g_last_in_dtx = cfg.use_dtx && os.nb_no_activity_ms_Q1 >= 10 * 20 * 2;
     free(os.tonal); free(os.delay); free(st); free(S); free(osp);
     return rc;
 }

@@ -248,3 +248,56 @@ def test_too_small_budgets_emit_the_reference_plc_frames(have_ref):
             p = np.ascontiguousarray(pcm[s])
             assert L.ref_encode_stream(p.ctypes.data_as(f32p), F, fs, ch, 2051, br, vbr, 9, ro.ctypes.data_as(u8p), mb, rl.ctypes.data_as(i32p), rr.ctypes.data_as(u32p)) == 0
             assert (rl == lens[s]).all() and np.array_equal(ro, out[s]) and (rr == 0).all()
+
+
+def test_encoder_ctls_on_gpu_match_reference(have_ref):
+    """DTX (TOC-only packets, OPUS_GET_IN_DTX), OPUS_SET_SIGNAL, prediction / phase-inversion disabled, lookahead and the getters, through the ABI."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    from opus_codec_b200.batch import BatchEncoder, OpusError, BAD_ARG, UNIMPLEMENTED
+    from test_host_emul import _gappy_pcm
+    L = refpy.lib_c()
+    ch, fs, br, S = 2, 960, 96000, 4
+    pcm = np.stack([_gappy_pcm(s, ch, 48000 * 2) for s in range(S)])
+    F = pcm.shape[1] // (fs * ch)
+    for app, extras in ((2051, (0, 0, 0, 1, 0, 0)), (2049, (3002, 1, 1, 1, 0, 5)), (2048, (3001, 0, 1, 0, 0, 0))):
+        with BatchEncoder(S, 48000, ch, application=app, device=0, max_frames=F) as enc:
+            enc.set_bitrate(br); enc.set_complexity(10); enc.set_vbr(False)
+            if extras[0]:
+                enc.set_signal(extras[0])
+            enc.set_prediction_disabled(extras[1]); enc.set_phase_inversion_disabled(extras[2]); enc.set_dtx(extras[3]); enc.set_packet_loss_perc(extras[5])
+            assert enc.signal() == (extras[0] or -1000) and enc.prediction_disabled() == bool(extras[1]) and enc.phase_inversion_disabled() == bool(extras[2])
+            assert enc.dtx() == bool(extras[3]) and enc.packet_loss_perc() == extras[5] and enc.lookahead() == (120 if app == 2051 else 312)
+            assert enc.lsb_depth() == 24 and enc.max_bandwidth() == 1105 and enc.force_channels() == -1000 and enc.inband_fec() == 0
+            out, lens, rng = enc.encode_float_multi(pcm.reshape(S, F, fs * ch), fs)
+            in_dtx = enc.in_dtx()
+        L.ref_set_encoder_extras2(extras[0], extras[1], extras[2], extras[3], extras[4], 0, extras[5])
+        try:
+            same = total = 0
+            for s in range(S):
+                ro, rl, rr = _ref_c_encode(pcm[s], fs, ch, br, 0, 10, app)
+                assert ((ro[:, 0] & 0x80) != 0).all()
+                assert (rl == lens[s]).all()                         # in particular: the same packets are DTX packets
+                same += int(((ro == out[s]).all(axis=1) & (rr == rng[s])).sum()); total += F
+                assert bool(L.ref_last_in_dtx()) == bool(in_dtx[s])
+            assert same / total >= 0.97
+            assert ((lens == 1).sum() > 20) == bool(extras[3])
+        finally:
+            L.ref_set_encoder_extras2(0, 0, 0, 0, 0, 0, 0)
+    with BatchEncoder(2, 48000, 1, device=0, max_frames=2) as enc:
+        for bad in (lambda: enc.set_signal(3000), lambda: enc.set_inband_fec(3), lambda: enc.set_expert_frame_duration(4999)):
+            with pytest.raises(OpusError) as e:
+                bad()
+            assert e.value.code == BAD_ARG
+        x = np.zeros((2, 2, 960), np.float32)
+        enc.set_expert_frame_duration(5004)                              # 20 ms: matches the call
+        assert (enc.encode_float_multi(x, 960)[1] > 0).all() and enc.expert_frame_duration() == 5004
+        enc.set_expert_frame_duration(5003)                              # 10 ms out of a 20 ms buffer: not on this path
+        with pytest.raises(OpusError) as e:
+            enc.encode_float_multi(x, 960)
+        assert e.value.code == UNIMPLEMENTED
+        enc.set_expert_frame_duration(5005)                              # 40 ms does not fit a 20 ms buffer
+        with pytest.raises(OpusError) as e:
+            enc.encode_float_multi(x, 960)
+        assert e.value.code == BAD_ARG

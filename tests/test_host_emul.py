@@ -267,3 +267,52 @@ def test_encoder_too_small_budgets_emit_the_reference_plc_frames(emul, have_ref,
         r1 = emul.emul_opus_encode_stream_app(P(pcm, C.c_float), nf, fs, ch, app, br, vbr, cx, P(b, C.c_ubyte), mb, P(bl, C.c_int), P(br_, C.c_uint32))
         assert r0 == r1 == (-2 if fs == 4800 else 0), (ch, br, fs, vbr, cx, mb)
         assert (al == bl).all() and (ar == br_).all() and np.array_equal(a, b), (ch, br, fs, vbr, cx, mb)
+
+
+def _gappy_pcm(s, ch, n):
+    """Programme material with a stretch of digital silence and a stretch of faint noise: what the generalised DTX reacts to."""
+    from opus_codec_b200 import synth
+    x = synth.stream_pcm(s, n, ch).reshape(-1, ch).copy()
+    x[n // 4:n // 4 + n // 3] = 0
+    x[3 * n // 4:3 * n // 4 + n // 5] = np.random.default_rng(s).normal(0, 2e-4, (n // 5, ch)).astype(np.float32)
+    return np.ascontiguousarray(x.reshape(-1))
+
+
+#                                  signal pred phase_inv dtx fec loss
+@pytest.mark.parametrize("extras", [(0, 0, 0, 1, 0, 0), (3001, 0, 0, 0, 0, 0), (3002, 0, 0, 0, 0, 0), (0, 1, 0, 0, 0, 0), (0, 0, 1, 0, 0, 0), (0, 1, 1, 1, 0, 10),
+                                    (0, 0, 0, 0, 1, 20), (3001, 0, 0, 1, 2, 30)])
+def test_encoder_ctls_signal_prediction_phase_inversion_dtx_fec(emul, have_ref, extras):
+    """OPUS_SET_SIGNAL / _PREDICTION_DISABLED / _PHASE_INVERSION_DISABLED / _DTX / _INBAND_FEC (+ loss): identical packets (DTX packets are the TOC
+    byte alone, final range 0), identical OPUS_GET_IN_DTX, for the three applications; SILK / hybrid frames are OPUS_UNIMPLEMENTED as before."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    L = refpy.lib_c()
+    u8p, i32p, u32p, f32p = (C.POINTER(C.c_ubyte), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_float))
+    L.ref_encode_stream.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, i32p, u32p]
+    emul.emul_opus_encode_stream_app.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, i32p, u32p]
+    dtx_packets = 0
+    L.ref_set_encoder_force_celt(0)
+    L.ref_set_encoder_extras2(extras[0], extras[1], extras[2], extras[3], extras[4], 0, extras[5])
+    emul.emul_set_encoder_extras(*extras)
+    try:
+        for app in (2051, 2049, 2048):
+            for ch, br, fs, vbr, cx in [(2, 96000, 960, 0, 10), (1, 64000, 960, 1, 9), (2, 64000, 480, 0, 7), (1, 96000, 2880, 1, 10), (2, 128000, 240, 2, 5)]:
+                pcm = _gappy_pcm(1, ch, 48000 * 2)
+                nf = pcm.size // (fs * ch)
+                a = np.zeros((nf, 1275), np.uint8); al = np.zeros(nf, np.int32); ar = np.ones(nf, np.uint32)
+                b = np.zeros((nf, 1275), np.uint8); bl = np.zeros(nf, np.int32); br_ = np.ones(nf, np.uint32)
+                assert L.ref_encode_stream(P(pcm, C.c_float), nf, fs, ch, app, br, vbr, cx, P(a, C.c_ubyte), 1275, P(al, C.c_int), P(ar, C.c_uint32)) == 0
+                rc = emul.emul_opus_encode_stream_app(P(pcm, C.c_float), nf, fs, ch, app, br, vbr, cx, P(b, C.c_ubyte), 1275, P(bl, C.c_int), P(br_, C.c_uint32))
+                celt = (a[:, 0] & 0x80) != 0
+                n = nf if celt.all() else int(np.argmin(celt))
+                assert rc == (0 if n == nf else -5), (app, ch, br, fs, vbr, cx)
+                assert (al[:n] == bl[:n]).all() and (ar[:n] == br_[:n]).all() and np.array_equal(a[:n], b[:n]), (app, ch, br, fs, vbr, cx)
+                if n == nf:
+                    assert L.ref_last_in_dtx() == emul.emul_last_in_dtx()
+                dtx_packets += int((bl[:n] == 1).sum())
+    finally:
+        L.ref_set_encoder_extras2(0, 0, 0, 0, 0, 0, 0)
+        L.ref_set_encoder_force_celt(1)
+        emul.emul_set_encoder_extras(0, 0, 0, 0, 0, 0)
+    assert (dtx_packets > 20) == bool(extras[3])
