@@ -22,11 +22,12 @@ OB_DEV float ob_log2(float x) { return (float)(1.442695040888963387 * log((doubl
 OB_DEV float ob_exp2(float x) { return (float)exp(0.6931471805599453094 * (double)x); }      // celt_exp2 (mathops.h:169)
 
 // celt_preemphasis fast path (celt_encoder.c:507-531): inp = 32768*x - m ; m = coef0 * 32768*x
-OB_DEV void ob_preemphasis(const float *pcm, float *inp, int N, int CC, float *mem, int clip)
+OB_DEV void ob_preemphasis(const float *__restrict__ pcm, float *__restrict__ inp, int N, int CC, float *mem, int clip)
 {
     const float coef0 = OB_PREEMPH[0];
     float m = *mem;
     if (!clip) {
+#pragma unroll 8
         for (int i = 0; i < N; i++) { const float x = pcm[CC * i] * 32768.f; inp[i] = x - m; m = coef0 * x; }
     } else {
         for (int i = 0; i < N; i++) {
@@ -277,6 +278,7 @@ OB_DEV int ob_transient_analysis(const float *in, int len, int C, float *tf_esti
     for (int c = 0; c < C; c++) {
         float mean, mem0 = 0, mem1 = 0, maxE, norm;
         int unmask = 0;
+#pragma unroll 8
         for (int i = 0; i < len; i++) {
             const float x = in[i + c * len];
             const float y = mem0 + x;
@@ -321,7 +323,7 @@ OB_DEV int ob_transient_analysis(const float *in, int len, int C, float *tf_esti
 }
 
 // ---- forward MDCT (mdct.c:119-238); f: N2 floats scratch, f2: N4 complex scratch --------------------------------------
-OB_DEV void ob_mdct_forward(const float *in, float *out, int shift, int stride, float *f, float *f2)
+OB_DEV void ob_mdct_forward(const float *__restrict__ in, float *__restrict__ out, int shift, int stride, float *__restrict__ f, float *__restrict__ f2)
 {
     int N = 1920;
     const float *trig = OB_MDCT_TRIG;
@@ -329,8 +331,8 @@ OB_DEV void ob_mdct_forward(const float *in, float *out, int shift, int stride, 
     const int N2 = N >> 1, N4 = N >> 2, overlap = OB_OVERLAP;
     const float scale = shift == 0 ? 0.002083333f : shift == 1 ? 0.004166667f : shift == 2 ? 0.008333333f : 0.016666667f;   // kiss_fft_state.scale
     {
-        const float *xp1 = in + (overlap >> 1), *xp2 = in + N2 - 1 + (overlap >> 1);
-        float *yp = f;
+        const float *__restrict__ xp1 = in + (overlap >> 1), *__restrict__ xp2 = in + N2 - 1 + (overlap >> 1);
+        float *__restrict__ yp = f;
         const float *wp1 = OB_WINDOW + (overlap >> 1), *wp2 = OB_WINDOW + (overlap >> 1) - 1;
         int i;
         for (i = 0; i < ((overlap + 3) >> 2); i++) {
@@ -339,6 +341,7 @@ OB_DEV void ob_mdct_forward(const float *in, float *out, int shift, int stride, 
             xp1 += 2; xp2 -= 2; wp1 += 2; wp2 -= 2;
         }
         wp1 = OB_WINDOW; wp2 = OB_WINDOW + overlap - 1;
+#pragma unroll 8
         for (; i < N4 - ((overlap + 3) >> 2); i++) { *yp++ = *xp2; *yp++ = *xp1; xp1 += 2; xp2 -= 2; }
         for (; i < N4; i++) {
             *yp++ = -(*wp1 * xp1[-N2]) + *wp2 * *xp2;
@@ -348,7 +351,8 @@ OB_DEV void ob_mdct_forward(const float *in, float *out, int shift, int stride, 
     }
     {
         const int16_t *br = ob_fft_bitrev(shift);
-        const float *yp = f;
+        const float *__restrict__ yp = f;
+#pragma unroll 4
         for (int i = 0; i < N4; i++) {
             const float t0 = trig[i], t1 = trig[N4 + i], re = *yp++, im = *yp++;
             const float yr = re * t0 - im * t1, yi = im * t0 + re * t1;
@@ -370,8 +374,9 @@ OB_DEV void ob_mdct_forward(const float *in, float *out, int shift, int stride, 
         }
     }
     {
-        const float *fp = f2;
-        float *yp1 = out, *yp2 = out + stride * (N2 - 1);
+        const float *__restrict__ fp = f2;
+        float *__restrict__ yp1 = out, *__restrict__ yp2 = out + stride * (N2 - 1);
+#pragma unroll 4
         for (int i = 0; i < N4; i++) {
             const float yr = fp[1] * trig[N4 + i] - fp[0] * trig[i];
             const float yi = fp[0] * trig[N4 + i] + fp[1] * trig[i];
@@ -410,11 +415,12 @@ OB_DEV void ob_amp2log2(int effEnd, int end, const float *bandE, float *bandLogE
         for (int i = effEnd; i < end; i++) bandLogE[c * OB_NB + i] = -14.f;
     }
 }
-OB_DEV void ob_normalise_bands(const float *freq, float *X, const float *bandE, int end, int C, int M)
+OB_DEV void ob_normalise_bands(const float *__restrict__ freq, float *__restrict__ X, const float *__restrict__ bandE, int end, int C, int M)
 {
     const int N = M * OB_SHORT;
     for (int c = 0; c < C; c++) for (int i = 0; i < end; i++) {
         const float g = 1.f / (1e-27f + bandE[i + c * OB_NB]);
+#pragma unroll 8
         for (int j = M * OB_EBANDS[i]; j < M * OB_EBANDS[i + 1]; j++) X[j + c * N] = freq[j + c * N] * g;
     }
 }

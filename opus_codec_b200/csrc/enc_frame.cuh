@@ -71,8 +71,12 @@ OB_DEV int ob_run_prefilter(ObEncState &st, ObEncScratch &S, float *in, int CC, 
     int pitch_index, pf_on, qg;
     float gain1, pf_threshold;
     for (int c = 0; c < CC; c++) {
-        for (int i = 0; i < OB_MAXPERIOD; i++) pre[c][i] = st.prefilter_mem[c * OB_MAXPERIOD + i];
-        for (int i = 0; i < N; i++) pre[c][OB_MAXPERIOD + i] = in[c * (N + OB_OVERLAP) + OB_OVERLAP + i];
+        float *__restrict__ dst = pre[c];
+        const float *__restrict__ mem = st.prefilter_mem + c * OB_MAXPERIOD, *__restrict__ src = in + c * (N + OB_OVERLAP) + OB_OVERLAP;
+#pragma unroll 8
+        for (int i = 0; i < OB_MAXPERIOD; i++) dst[i] = mem[i];
+#pragma unroll 8
+        for (int i = 0; i < N; i++) dst[OB_MAXPERIOD + i] = src[i];
     }
     if (enabled) {
         float *pitch_buf = S.pitch_buf;
@@ -116,8 +120,18 @@ OB_DEV int ob_run_prefilter(ObEncState &st, ObEncScratch &S, float *in, int CC, 
         if (N > OB_MAXPERIOD) {
             for (int i = 0; i < OB_MAXPERIOD; i++) st.prefilter_mem[c * OB_MAXPERIOD + i] = pre[c][N + i];
         } else {
-            for (int i = 0; i < OB_MAXPERIOD - N; i++) st.prefilter_mem[c * OB_MAXPERIOD + i] = st.prefilter_mem[c * OB_MAXPERIOD + N + i];
-            for (int i = 0; i < N; i++) st.prefilter_mem[c * OB_MAXPERIOD + OB_MAXPERIOD - N + i] = pre[c][OB_MAXPERIOD + i];
+            float *mem = st.prefilter_mem + c * OB_MAXPERIOD;
+            for (int i = 0; i < OB_MAXPERIOD - N; i += 8) {          // a move towards the front by N >= 120: 8 loads can go out before the 8 stores
+                float v[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = mem[N + i + k];
+#pragma unroll
+                for (int k = 0; k < 8; k++) mem[i + k] = v[k];
+            }
+            const float *__restrict__ src = pre[c] + OB_MAXPERIOD;
+            float *__restrict__ dst = mem + OB_MAXPERIOD - N;
+#pragma unroll 8
+            for (int i = 0; i < N; i++) dst[i] = src[i];
         }
     }
     *gain = gain1; *pitch = pitch_index; *qgain = qg;
