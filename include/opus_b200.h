@@ -106,6 +106,11 @@ int32_t ob_decoder_get_gain(ObDecoder *dec, int32_t *value);
  * phase_inversion_disabled :333-335). */
 int32_t ob_decoder_set_phase_inversion_disabled(ObDecoder *dec, int32_t disabled);
 int32_t ob_decoder_get_phase_inversion_disabled(ObDecoder *dec, int32_t *value);
+/* The decode_fec argument of opus_decode / opus_decode_float (Decoder::decode(.., fec), src/decoder.rs:75-182) for the calls that follow.
+ * CELT-only packets carry no FEC: with the flag on, a packet that parses is concealed over the whole frame_size like a lost one
+ * (opus/src/opus_decoder.c:744-750); frame_size must then be a multiple of 2.5 ms.  SILK / hybrid packets stay OB_UNIMPLEMENTED. */
+int32_t ob_decoder_set_decode_fec(ObDecoder *dec, int32_t decode_fec);
+int32_t ob_decoder_get_decode_fec(ObDecoder *dec, int32_t *value);
 
 /* Introspection for benchmarks: number of streams / channels, device-event time in ms of the three kernels of
  * the most recent call (symbols, bands, synthesis), kernel launches issued so far. */

@@ -146,6 +146,10 @@ class BatchDecoder:
         _check(self._L.ob_decoder_get_gain(self._h, C.byref(v)))
         return v.value
 
+    def set_decode_fec(self, on):
+        """decode_fec of the calls that follow (Decoder::decode(.., fec)): CELT-only packets are then concealed like lost ones."""
+        _check(self._L.ob_decoder_set_decode_fec(self._h, int(bool(on))))
+
     def set_phase_inversion_disabled(self, disabled):
         """Decoder::set_phase_inversion_disabled (src/decoder.rs:341-346)."""
         _check(self._L.ob_decoder_set_phase_inversion_disabled(self._h, 1 if disabled else 0))

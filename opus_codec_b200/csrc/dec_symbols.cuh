@@ -922,7 +922,10 @@ OB_DEV int ob_parse_packet(const uint8_t *data, int len, int16_t *sizes, int *fi
 // The packets of ONE stream for one call -> frame slots (the frame loop of opus_decode_native, opus_decoder.c:715-799).  frame_size:
 // the caller's per-packet PCM slot.  Returns the number of slots written (<= cap); a packet that does not fit gets one error slot.
 // ds = 48000 / output rate: frame_size and the slots' sample offsets count OUTPUT samples, concealment lengths 48 kHz samples.
-OB_DEV int ob_frame_packets(const uint8_t *packets, const int32_t *offsets, const int32_t *lens, int F, int frame_size, ObSlot *slots, int cap, int ds = 1)
+// fec: opus_decode(..., decode_fec = 1): a packet that parses and is CELT-only carries no FEC, so the whole slot is concealed as if it
+// were lost (opus_decoder.c:744-750).
+OB_DEV int ob_frame_packets(const uint8_t *packets, const int32_t *offsets, const int32_t *lens, int F, int frame_size, ObSlot *slots, int cap, int ds = 1,
+                            int fec = 0)
 {
     int n = 0;
     int16_t sizes[48];
@@ -941,6 +944,11 @@ OB_DEV int ob_frame_packets(const uint8_t *packets, const int32_t *offsets, cons
         int first_off = 0;
         const int count = (toc & 0x80) ? ob_parse_packet(data, len, sizes, &first_off) : OB_UNIMPLEMENTED;     // SILK / hybrid: not on this path
         const int N = OB_SHORT << ((toc >> 3) & 3);
+        if (fec && (count >= 0 || frame_size <= 0 || frame_size % (OB_SHORT / ds) != 0)) {
+            one.status = frame_size <= 0 || frame_size % (OB_SHORT / ds) != 0 ? OB_BAD_ARG : frame_size * ds;       // (:683-684)
+            slots[n++] = one;
+            continue;
+        }
         if (count < 0) one.status = count;
         else if (count * N > frame_size * ds) one.status = OB_BUFFER_TOO_SMALL;                                // opus_decoder.c:764-765
         else if (n + count > cap) one.status = OB_BUFFER_TOO_SMALL;                                            // decoder created with too few frame slots

@@ -27,11 +27,11 @@
 // Framing pass, one thread per stream: the stream's F packets -> frame slots (code-0 packets: one slot each; codes 1-3: one per
 // coded frame; lost packets and DTX frames: concealment slots; anything off this path: an error slot).
 __global__ void ob_k_frame(const uint8_t *__restrict__ packets, const int32_t *__restrict__ offsets, const int32_t *__restrict__ lens,
-                           ObSlot *__restrict__ slots, int32_t *__restrict__ nslots, int S, int F, int frame_size, int cap, int32_t *__restrict__ multi, int ds)
+                           ObSlot *__restrict__ slots, int32_t *__restrict__ nslots, int S, int F, int frame_size, int cap, int32_t *__restrict__ multi, int ds, int fec)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
-    const int n = ob_frame_packets(packets, offsets + (size_t)s * F, lens + (size_t)s * F, F, frame_size, slots + (size_t)s * cap, cap, ds);
+    const int n = ob_frame_packets(packets, offsets + (size_t)s * F, lens + (size_t)s * F, F, frame_size, slots + (size_t)s * cap, cap, ds, fec);
     nslots[s] = n;
     // slot j <-> packet j unless some packet holds several frames (or did not fit): the host pipelines the call in slot windows
     // only in the one-to-one case
@@ -224,6 +224,7 @@ struct ObDecoder {
     int S, CC, device, max_frames;
     int ds;                               // 48000 / output sample rate
     int gain_q8, phase_inv_disabled;      // OPUS_SET_GAIN (Q8 dB), OPUS_SET_PHASE_INVERSION_DISABLED: one value for the batch
+    int decode_fec;                       // the decode_fec argument of opus_decode / opus_decode_float for the calls that follow
     float gain_linear;
     cudaStream_t stream, copy_stream, aux_stream;
     cudaEvent_t ev[4], chunk_ev[OB_MAX_CHUNKS], copy_done, h2d_done;
@@ -270,7 +271,7 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
     float *ring = d->d_ring + (size_t)s0 * d->CC * OB_RING;
     if (timed) OB_CUDA(cudaEventRecord(d->ev[0], stream));
     if (which & 4) {
-        ob_k_frame<<<(Sc + 127) / 128, 128, 0, stream>>>(d_packets, d_offsets + w0, d_lens + w0, slots, nslots, Sc, F, frame_size, cap, d->d_multi, d->ds);
+        ob_k_frame<<<(Sc + 127) / 128, 128, 0, stream>>>(d_packets, d_offsets + w0, d_lens + w0, slots, nslots, Sc, F, frame_size, cap, d->d_multi, d->ds, d->decode_fec);
         d->launches += 1;
     }
     if (which & 1) {
@@ -315,7 +316,7 @@ ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
     if (err == OB_OK) {
         memset(d, 0, sizeof(*d));
         d->S = n_streams; d->CC = channels; d->device = device; d->max_frames = max_frames;
-        d->gain_q8 = 0; d->gain_linear = 1.f; d->phase_inv_disabled = 0; d->ds = 48000 / fs;
+        d->gain_q8 = 0; d->gain_linear = 1.f; d->phase_inv_disabled = 0; d->decode_fec = 0; d->ds = 48000 / fs;
         const size_t total = (size_t)n_streams * max_frames;
         bool ok = cudaSetDevice(device) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -599,6 +600,8 @@ int32_t ob_decoder_get_gain(ObDecoder *d, int32_t *v) { if (!d || !v) return OB_
 // OPUS_SET/GET_PHASE_INVERSION_DISABLED (celt_decoder.c:1560-1579)
 int32_t ob_decoder_set_phase_inversion_disabled(ObDecoder *d, int32_t v) { if (!d || v < 0 || v > 1) return OB_BAD_ARG; d->phase_inv_disabled = v; return OB_OK; }
 int32_t ob_decoder_get_phase_inversion_disabled(ObDecoder *d, int32_t *v) { if (!d || !v) return OB_BAD_ARG; *v = d->phase_inv_disabled; return OB_OK; }
+int32_t ob_decoder_set_decode_fec(ObDecoder *d, int32_t v) { if (!d || v < 0 || v > 1) return OB_BAD_ARG; d->decode_fec = v; return OB_OK; }
+int32_t ob_decoder_get_decode_fec(ObDecoder *d, int32_t *v) { if (!d || !v) return OB_BAD_ARG; *v = d->decode_fec; return OB_OK; }
 
 int32_t ob_decoder_streams(const ObDecoder *d) { return d ? d->S : OB_BAD_ARG; }
 int32_t ob_decoder_channels(const ObDecoder *d) { return d ? d->CC : OB_BAD_ARG; }

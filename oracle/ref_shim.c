@@ -218,6 +218,9 @@ REF_EXPORT int ref_encode_stream_i16(const opus_int16 *pcm, int nframes, int fra
  * dec_channels: channel count of the decoder object.  taps (optional): nframes ref_tap_t records. */
 /* Optional decoder CTLs applied by ref_decode_stream: OPUS_SET_GAIN (Q8 dB) and OPUS_SET_PHASE_INVERSION_DISABLED. */
 static int g_dec_gain = 0, g_dec_phase_inv_disabled = 0, g_dec_fs = 48000;
+/* Optional per-frame decode_fec flags for ref_decode_stream (NULL = all 0). */
+static const int *g_dec_fec_flags = 0;
+REF_EXPORT void ref_set_decoder_fec_flags(const int *flags) { g_dec_fec_flags = flags; }
 REF_EXPORT void ref_set_decoder_fs(int fs) { g_dec_fs = fs; }
 REF_EXPORT void ref_set_decoder_extras(int gain_q8, int phase_inv_disabled)
 {
@@ -237,7 +240,7 @@ REF_EXPORT int ref_decode_stream(const unsigned char *pkts, const int *lens, int
         int n;
         if (taps) ref_tap_set((char *)taps + (size_t)f * sizeof(ref_tap_t));
         n = opus_decode_float(d, lens[f] > 0 ? pkts + (size_t)f * stride : NULL, lens[f],
-                pcm_out + (size_t)f * frame_size * dec_channels, frame_size, 0);
+                pcm_out + (size_t)f * frame_size * dec_channels, frame_size, g_dec_fec_flags ? g_dec_fec_flags[f] : 0);
         if (taps) ref_tap_set(NULL);
         if (samples) samples[f] = n;
         if (n < 0 && !samples) { opus_decoder_destroy(d); return n; }

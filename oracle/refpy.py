@@ -135,7 +135,7 @@ def _encode_stream(pcm, frame_size, channels, bitrate, vbr, complexity, applicat
     return out, lens, rng
 
 
-def decode_stream(pkts, lens, frame_size, channels, want_taps=False, pure_c=False, gain_q8=0, phase_inv_disabled=False, fs=48000):
+def decode_stream(pkts, lens, frame_size, channels, want_taps=False, pure_c=False, gain_q8=0, phase_inv_disabled=False, fs=48000, fec_flags=None):
     """pkts u8 [nframes, stride] -> (pcm f32 [nframes, frame_size*channels], ranges u32, samples i32[, taps])."""
     pkts = np.ascontiguousarray(pkts, np.uint8)
     lens = np.ascontiguousarray(lens, np.int32)
@@ -148,6 +148,8 @@ def decode_stream(pkts, lens, frame_size, channels, want_taps=False, pure_c=Fals
     L = lib_c() if pure_c else lib()
     L.ref_set_decoder_extras(int(gain_q8), 1 if phase_inv_disabled else 0)
     L.ref_set_decoder_fs(int(fs))
+    fec = np.ascontiguousarray(fec_flags, np.int32) if fec_flags is not None else None
+    L.ref_set_decoder_fec_flags(_p(fec, C.c_int) if fec is not None else None)
     try:
         r = L.ref_decode_stream(_p(pkts, C.c_ubyte), _p(lens, C.c_int), stride, nframes, frame_size, channels,
                                 _p(pcm, C.c_float), _p(rng, C.c_uint32), _p(smp, C.c_int),
@@ -155,6 +157,7 @@ def decode_stream(pkts, lens, frame_size, channels, want_taps=False, pure_c=Fals
     finally:
         L.ref_set_decoder_extras(0, 0)
         L.ref_set_decoder_fs(48000)
+        L.ref_set_decoder_fec_flags(None)
     if r != 0:
         raise RuntimeError("ref_decode_stream: opus error %d" % r)
     return (pcm, rng, smp, taps) if want_taps else (pcm, rng, smp)

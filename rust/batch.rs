@@ -26,6 +26,7 @@ unsafe extern "C" {
     pub fn ob_decoder_last_packet_duration(dec: *mut ObDecoder, out: *mut i32) -> i32;
     pub fn ob_decoder_set_gain(dec: *mut ObDecoder, gain_q8: i32) -> i32;
     pub fn ob_decoder_set_phase_inversion_disabled(dec: *mut ObDecoder, disabled: i32) -> i32;
+    pub fn ob_decoder_set_decode_fec(dec: *mut ObDecoder, decode_fec: i32) -> i32;
 
     pub fn ob_encoder_create(n_streams: i32, fs: i32, channels: i32, application: i32, device: i32, max_frames: i32,
                              error: *mut i32) -> *mut ObEncoder;
@@ -39,6 +40,14 @@ unsafe extern "C" {
     pub fn ob_encoder_set_complexity(enc: *mut ObEncoder, complexity: i32) -> i32;
     pub fn ob_encoder_set_vbr(enc: *mut ObEncoder, vbr: i32) -> i32;
     pub fn ob_encoder_set_vbr_constraint(enc: *mut ObEncoder, cvbr: i32) -> i32;
+    pub fn ob_encoder_set_signal(enc: *mut ObEncoder, signal: i32) -> i32;
+    pub fn ob_encoder_set_prediction_disabled(enc: *mut ObEncoder, disabled: i32) -> i32;
+    pub fn ob_encoder_set_phase_inversion_disabled(enc: *mut ObEncoder, disabled: i32) -> i32;
+    pub fn ob_encoder_set_dtx(enc: *mut ObEncoder, enabled: i32) -> i32;
+    pub fn ob_encoder_in_dtx(enc: *mut ObEncoder, out: *mut i32) -> i32;
+    pub fn ob_encoder_set_inband_fec(enc: *mut ObEncoder, mode: i32) -> i32;
+    pub fn ob_encoder_set_expert_frame_duration(enc: *mut ObEncoder, duration: i32) -> i32;
+    pub fn ob_encoder_get_lookahead(enc: *mut ObEncoder, value: *mut i32) -> i32;
     pub fn ob_encoder_final_range(enc: *mut ObEncoder, out: *mut u32) -> i32;
     pub fn ob_encoder_reset(enc: *mut ObEncoder, idx: *const i32, n: i32) -> i32;
 
@@ -78,10 +87,16 @@ impl BatchDecoder {
     /// `Decoder::decode_float(&[], out, false)`.
     /// `output` is `n_streams * frame_size * channels` interleaved floats; `frame_size = output.len() / n_streams / channels`
     /// exactly like `Decoder::decode_float` derives it (src/decoder.rs:149).
+    /// `fec` is the flag of `Decoder::decode_float` (src/decoder.rs:134): CELT-only packets carry no FEC, libopus (and this path)
+    /// then conceals the frame like a lost packet.
     /// Returns per-stream `Ok(samples_per_channel)` / `Err(code)`.
-    pub fn decode_float(&mut self, packets: &[&[u8]], output: &mut [f32]) -> Result<Vec<Result<usize>>> {
+    pub fn decode_float(&mut self, packets: &[&[u8]], output: &mut [f32], fec: bool) -> Result<Vec<Result<usize>>> {
         if packets.len() != self.n_streams || output.len() % (self.n_streams * self.channels as usize) != 0 {
             return Err(Error::BadArg);
+        }
+        let rc = unsafe { ob_decoder_set_decode_fec(self.raw.as_ptr(), fec as i32) };
+        if rc != 0 {
+            return Err(Error::from_code(rc));
         }
         let frame_size = output.len() / self.n_streams / self.channels as usize;
         let mut flat = Vec::with_capacity(packets.iter().map(|p| p.len()).sum());

@@ -415,3 +415,51 @@ def test_full_size_batch_4096_streams_tiling_property():
     assert np.abs(pcm[0] - g["pcm"][0, :F]).max() <= PCM_TOL
     for s in range(P, S):
         assert np.array_equal(pcm[s], pcm[s % P])
+
+
+def test_decode_fec_flag_conceals_celt_packets_like_the_reference(have_ref):
+    """Decoder::decode(.., fec = true): a CELT-only packet carries no FEC, so libopus conceals the frame as if the packet were lost -- after
+    parsing it (a malformed packet is still an error).  Checked both ways: the reference gives the same PCM for `fec` and for a lost packet,
+    and so does the GPU; the GPU's PCM equals the reference's within the concealment tolerance."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    from opus_codec_b200.batch import BatchDecoder, pack_packets
+    g = load_golden("cfg1_stereo_20ms_128k_cbr")
+    ch, fs, F, S = g["channels"], g["frame_size"], 30, 3
+    fec_at = {7, 8, 15, 22}
+    pk = [[bytes(g["packets"][s][f, :g["lens"][s][f]]) for f in range(F)] for s in range(S)]
+    stride = g["packets"].shape[2]
+    for s in range(S):
+        flags = np.array([int(f in fec_at) for f in range(F)], np.int32)
+        lens_lost = g["lens"][s][:F].copy(); lens_lost[list(fec_at)] = 0
+        a, ra, sa = refpy.decode_stream(g["packets"][s][:F], g["lens"][s][:F], fs, ch, pure_c=True, fec_flags=flags)
+        b, rb, sb = refpy.decode_stream(g["packets"][s][:F], lens_lost, fs, ch, pure_c=True)
+        assert np.array_equal(a, b) and (ra == rb).all() and (sa == sb).all()
+    out = np.zeros((S, F, fs * ch), np.float32); rng = np.zeros((S, F), np.uint32)
+    out2 = np.zeros_like(out)
+    with BatchDecoder(S, 48000, ch, device=0, max_frames=1) as dec, BatchDecoder(S, 48000, ch, device=0, max_frames=1) as dec2:
+        for f in range(F):
+            dec.set_decode_fec(f in fec_at)
+            bb, oo, ll = pack_packets([[pk[s][f]] for s in range(S)])
+            p, smp, r = dec.decode_float_multi(bb, oo, ll, fs)
+            assert (smp == fs).all()
+            out[:, f] = p[:, 0]; rng[:, f] = r[:, 0]
+            bb, oo, ll = pack_packets([[b"" if f in fec_at else pk[s][f]] for s in range(S)])
+            out2[:, f] = dec2.decode_float_multi(bb, oo, ll, fs)[0][:, 0]
+        # errors: a malformed packet is reported even with fec on; the frame size must be a multiple of 2.5 ms
+        dec.set_decode_fec(True)
+        bad = bytes([pk[0][0][0] | 1]) + pk[0][0][1:4]                       # code 1 with an odd payload
+        bb, oo, ll = pack_packets([[bad], [pk[1][0]], [pk[2][0]]])
+        p, smp, r = dec.decode_float_multi(bb, oo, ll, fs)
+        assert smp[0, 0] == -4 and (smp[1:, 0] == fs).all() and (r[1:, 0] == 0).all()
+        p, smp, r = dec.decode_float_multi(bb, oo, ll, 1000)
+        assert (smp[:, 0] == -1).all()
+    assert np.array_equal(out, out2)
+    for s in range(S):
+        flags = np.array([int(f in fec_at) for f in range(F)], np.int32)
+        a, ra, _ = refpy.decode_stream(g["packets"][s][:F], g["lens"][s][:F], fs, ch, pure_c=True, fec_flags=flags)
+        assert (ra == rng[s]).all()
+        assert np.abs(a - out[s]).max() <= 3e-3
+        first = min(fec_at)
+        assert np.abs(a[:first] - out[s][:first]).max() <= 1e-4
