@@ -97,6 +97,8 @@ int32_t ob_decoder_reset(ObDecoder *dec, const int32_t *idx, int32_t n);
 
 /* Replaces opus_decoder_ctl(st, OPUS_GET_LAST_PACKET_DURATION_REQUEST, &v) (Decoder::get_last_packet_duration src/decoder.rs:294-296). */
 int32_t ob_decoder_last_packet_duration(ObDecoder *dec, int32_t *out);
+/* OPUS_GET_PITCH (Decoder::get_pitch, src/decoder.rs): the post-filter period of the last decoded frame, 0 before the first. */
+int32_t ob_decoder_get_pitch(ObDecoder *dec, int32_t *out);
 
 /* Replaces opus_decoder_ctl(st, OPUS_SET_GAIN / OPUS_GET_GAIN) (Decoder::set_gain src/decoder.rs:318-320, gain :325-327):
  * Q8 dB in [-32768, 32767], one value for the whole batch, applied to every decoded and concealed sample. */

@@ -146,6 +146,12 @@ class BatchDecoder:
         _check(self._L.ob_decoder_get_gain(self._h, C.byref(v)))
         return v.value
 
+    def pitch(self):
+        """OPUS_GET_PITCH per stream (Decoder::get_pitch)."""
+        out = np.zeros(self.n_streams, np.int32)
+        _check(self._L.ob_decoder_get_pitch(self._h, _vp(out)))
+        return out
+
     def set_decode_fec(self, on):
         """decode_fec of the calls that follow (Decoder::decode(.., fec)): CELT-only packets are then concealed like lost ones."""
         _check(self._L.ob_decoder_set_decode_fec(self._h, int(bool(on))))

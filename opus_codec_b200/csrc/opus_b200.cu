@@ -206,12 +206,12 @@ __global__ void ob_k_reset(ObDecState *st, float *hist, float *ring, const int32
     for (int i = threadIdx.x; i < CC * OB_RING; i += blockDim.x) r[i] = 0.f;
 }
 
-__global__ void ob_k_gather_state(const ObDecState *st, uint32_t *ranges, int32_t *durations, int S)
+__global__ void ob_k_gather_state(const ObDecState *st, uint32_t *ranges, int32_t *durations, int S, int pitch)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     if (ranges) ranges[s] = st[s].final_range;
-    if (durations) durations[s] = st[s].last_packet_duration;
+    if (durations) durations[s] = pitch ? st[s].pf_period : st[s].last_packet_duration;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -574,10 +574,10 @@ int32_t ob_decode_float(ObDecoder *d, const uint8_t *packets, const int32_t *off
     return ob_decode_float_multi(d, 1, packets, offsets, lens, pcm_out, frame_size, samples_out, nullptr);
 }
 
-static int32_t ob_gather(ObDecoder *d, uint32_t *ranges, int32_t *durations)
+static int32_t ob_gather(ObDecoder *d, uint32_t *ranges, int32_t *durations, int pitch = 0)
 {
     OB_CUDA(cudaSetDevice(d->device));
-    ob_k_gather_state<<<(d->S + 127) / 128, 128, 0, d->stream>>>(d->d_state, ranges ? (uint32_t *)d->d_gather : nullptr, durations ? d->d_gather : nullptr, d->S);
+    ob_k_gather_state<<<(d->S + 127) / 128, 128, 0, d->stream>>>(d->d_state, ranges ? (uint32_t *)d->d_gather : nullptr, durations ? d->d_gather : nullptr, d->S, pitch);
     d->launches += 1;
     if (ranges) OB_CUDA(cudaMemcpyAsync(ranges, d->d_gather, sizeof(uint32_t) * d->S, cudaMemcpyDeviceToHost, d->stream));
     if (durations) OB_CUDA(cudaMemcpyAsync(durations, d->d_gather, sizeof(int32_t) * d->S, cudaMemcpyDeviceToHost, d->stream));
@@ -586,6 +586,8 @@ static int32_t ob_gather(ObDecoder *d, uint32_t *ranges, int32_t *durations)
 }
 int32_t ob_decoder_final_range(ObDecoder *d, uint32_t *out) { return (!d || !out) ? OB_BAD_ARG : ob_gather(d, out, nullptr); }
 int32_t ob_decoder_last_packet_duration(ObDecoder *d, int32_t *out) { return (!d || !out) ? OB_BAD_ARG : ob_gather(d, nullptr, out); }
+// OPUS_GET_PITCH (opus_decoder.c:987-999 -> celt_decoder.c OPUS_GET_PITCH: st->postfilter_period; 0 before the first packet)
+int32_t ob_decoder_get_pitch(ObDecoder *d, int32_t *out) { return (!d || !out) ? OB_BAD_ARG : ob_gather(d, nullptr, out, 1); }
 
 // OPUS_SET_GAIN / OPUS_GET_GAIN (opus_decoder.c:985-1004): Q8 dB, applied as pcm *= celt_exp2(6.48814081e-4 * gain) (:639-649).
 int32_t ob_decoder_set_gain(ObDecoder *d, int32_t gain_q8)

@@ -221,6 +221,9 @@ static int g_dec_gain = 0, g_dec_phase_inv_disabled = 0, g_dec_fs = 48000;
 /* Optional per-frame decode_fec flags for ref_decode_stream (NULL = all 0). */
 static const int *g_dec_fec_flags = 0;
 REF_EXPORT void ref_set_decoder_fec_flags(const int *flags) { g_dec_fec_flags = flags; }
+/* Optional per-frame OPUS_GET_PITCH output of ref_decode_stream (NULL = off). */
+static int *g_dec_pitch_out = 0;
+REF_EXPORT void ref_set_decoder_pitch_out(int *buf) { g_dec_pitch_out = buf; }
 REF_EXPORT void ref_set_decoder_fs(int fs) { g_dec_fs = fs; }
 REF_EXPORT void ref_set_decoder_extras(int gain_q8, int phase_inv_disabled)
 {
@@ -243,6 +246,7 @@ REF_EXPORT int ref_decode_stream(const unsigned char *pkts, const int *lens, int
                 pcm_out + (size_t)f * frame_size * dec_channels, frame_size, g_dec_fec_flags ? g_dec_fec_flags[f] : 0);
         if (taps) ref_tap_set(NULL);
         if (samples) samples[f] = n;
+        if (g_dec_pitch_out) { opus_int32 v = 0; opus_decoder_ctl(d, OPUS_GET_PITCH(&v)); g_dec_pitch_out[f] = v; }
         if (n < 0 && !samples) { opus_decoder_destroy(d); return n; }
         opus_decoder_ctl(d, OPUS_GET_FINAL_RANGE(&rng));
         if (ranges) ranges[f] = rng;

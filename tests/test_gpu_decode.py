@@ -463,3 +463,32 @@ def test_decode_fec_flag_conceals_celt_packets_like_the_reference(have_ref):
         assert np.abs(a - out[s]).max() <= 3e-3
         first = min(fec_at)
         assert np.abs(a[:first] - out[s][:first]).max() <= 1e-4
+
+
+def test_get_pitch_matches_reference(have_ref):
+    """OPUS_GET_PITCH after every packet (post-filter period of the last decoded frame; unchanged by a concealed one; 0 on a fresh decoder)."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    import ctypes as C
+    from oracle import refpy
+    from opus_codec_b200.batch import BatchDecoder, pack_packets
+    g = load_golden("cfg2_mono_20ms_64k_cbr")
+    ch, fs, F, S = g["channels"], g["frame_size"], 40, 4
+    L = refpy.lib()
+    want = np.zeros((S, F), np.int32)
+    for s in range(S):
+        lens = g["lens"][s][:F].copy(); lens[[9, 10, 25]] = 0
+        buf = np.zeros(F, np.int32)
+        L.ref_set_decoder_pitch_out(buf.ctypes.data_as(C.POINTER(C.c_int)))
+        try:
+            refpy.decode_stream(g["packets"][s][:F], lens, fs, ch)
+        finally:
+            L.ref_set_decoder_pitch_out(None)
+        want[s] = buf
+    assert (want > 0).any()
+    with BatchDecoder(S, 48000, ch, device=0, max_frames=1) as dec:
+        assert (dec.pitch() == 0).all()
+        for f in range(F):
+            bb, oo, ll = pack_packets([[b"" if f in (9, 10, 25) else bytes(g["packets"][s][f, :g["lens"][s][f]])] for s in range(S)])
+            dec.decode_float_multi(bb, oo, ll, fs)
+            assert (dec.pitch() == want[:, f]).all(), f
