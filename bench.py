@@ -178,12 +178,24 @@ def run_encode_leg(args, L, local, world, rank, dev, barrier):
     ms_e2e = max_over_ranks(f0.elapsed_time(f1), dev)
     launches = enc.launches()
     enc.close()
+    verified = None
+    if rank == 0:                                               # checker only: the reference decoder takes a sample of the packets just produced
+        try:
+            from oracle import refpy
+            o = h_out.numpy().reshape(S, F, 256); ln = h_len.numpy().reshape(S, F); rg = h_rng.numpy().view(np.uint32).reshape(S, F)
+            idx = list(range(0, S, max(1, S // 16)))[:16]
+            for s_ in idx:
+                _, dr, smp = refpy.decode_stream(o[s_], ln[s_], FRAME, 2)
+                assert (smp == FRAME).all() and (dr == rg[s_]).all(), "reference decoder final range != GPU encoder final range (stream %d)" % s_
+            verified = "reference decoder accepts the packets of %d sampled streams, final ranges equal" % len(idx)
+        except ImportError:
+            verified = "not checked (oracle/_ref missing)"
     audio = world * S * F * 0.02
     res = {"workload": ENC_WORKLOAD, "frames_per_stream_per_step": F, "steps": steps,
            "value": audio * steps / (ms / 1000.0), "unit": "audio-s/s", "ms_per_step": ms / steps,
            "e2e": {"value": audio / (ms_e2e / 1000.0), "unit": "audio-s/s", "h2d_bytes_per_step": int(4 * h_pcm.numel()),
                    "d2h_bytes_per_step": int(h_out.numel() + 8 * h_len.numel())},
-           "gpu_launches": int(launches)}
+           "gpu_launches": int(launches), "verified": verified}
     if rank == 0:
         peak = 6549.1
         try:
@@ -192,7 +204,9 @@ def run_encode_leg(args, L, local, world, rank, dev, barrier):
             pass
         k = kms / steps
         ach = enc_algorithmic_bytes_per_frame(F) * S * F / (k / 1000.0) / 1e9
-        res["roofline"] = {"bound": "hbm", "kernel": "ob_k_encode", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        res["roofline"] = {"bound": "hbm", "kernel": "ob_k_encode", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                           "traffic": 8.259e9 * F, "traffic_unit": "bytes per step of F frames (dram__bytes_read.sum + dram__bytes_write.sum per 16384-stream frame x F)",
+                           "traffic_source": "profiles/r01l_ncu_encoder_kernel.txt (ncu --set full --clock-control none, tools/prof_encode.py 16384 1 2)",
                            "kernel_ms": k, "algorithmic_bytes_per_frame": enc_algorithmic_bytes_per_frame(F)}
         if not args.kernels_only:
             cores = os.cpu_count() or 1

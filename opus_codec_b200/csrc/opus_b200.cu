@@ -235,6 +235,8 @@ struct ObDecoder {
     int16_t *d_pcm16_2[2], *cur_pcm16;    // int16 API: device-side int16 output (per buffer pair), the one of the call being enqueued
     int32_t *d_multi, *h_multi;           // "some packet is not one slot": a word of mapped pinned host memory (host pointer, device alias)
     cudaEvent_t framed;
+    cudaStream_t in_stream;               // host->device staging of a call's packets: runs beside the previous call's band / synthesis kernels
+    cudaEvent_t syms_done, in_ready;      // the symbol kernel has read the staged packets / the next call's packets are staged
     ObFrameIR *d_ir;
     float *d_X;
     // staging for the host-pointer entry points
@@ -342,6 +344,9 @@ ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
                  && cudaEventCreateWithFlags(&d->out_done[p], cudaEventDisableTiming) == cudaSuccess;
         }
         ok = ok && cudaEventCreateWithFlags(&d->aux_done, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&d->in_stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&d->syms_done, cudaEventDisableTiming) == cudaSuccess
+                && cudaEventCreateWithFlags(&d->in_ready, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_gather, sizeof(int32_t) * n_streams) == cudaSuccess;
         ok = ok && cudaFuncSetAttribute(ob_k_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP) == cudaSuccess;
         if (!ok) {
@@ -368,6 +373,9 @@ void ob_decoder_destroy(ObDecoder *d)
     cudaFree(d->d_offsets); cudaFree(d->d_lens); cudaFree(d->d_gather);
     for (int p = 0; p < 2; p++) { cudaFree(d->d_samples2[p]); cudaFree(d->d_ranges2[p]); cudaFree(d->d_pcm2[p]); cudaFree(d->d_pcm16_2[p]); if (d->out_done[p]) cudaEventDestroy(d->out_done[p]); }
     if (d->aux_done) cudaEventDestroy(d->aux_done);
+    if (d->syms_done) cudaEventDestroy(d->syms_done);
+    if (d->in_ready) cudaEventDestroy(d->in_ready);
+    if (d->in_stream) cudaStreamDestroy(d->in_stream);
     for (int i = 0; i < 4; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
     for (int i = 0; i < OB_MAX_CHUNKS; i++) if (d->chunk_ev[i]) cudaEventDestroy(d->chunk_ev[i]);
     if (d->copy_done) cudaEventDestroy(d->copy_done);
@@ -453,9 +461,15 @@ static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *p
     float *const d_pcm = d->d_pcm2[par];
     int32_t *const d_samples = d->d_samples2[par];
     uint32_t *const d_ranges = d->d_ranges2[par];
-    OB_CUDA(cudaMemcpyAsync(d->d_packets, packets, nbytes, cudaMemcpyHostToDevice, d->stream));
-    OB_CUDA(cudaMemcpyAsync(d->d_offsets, offsets, total * sizeof(int32_t), cudaMemcpyHostToDevice, d->stream));
-    OB_CUDA(cudaMemcpyAsync(d->d_lens, lens, total * sizeof(int32_t), cudaMemcpyHostToDevice, d->stream));
+    // Only the framing and symbol kernels read the staged packets: once the previous call's symbol kernel is done the staging buffers are
+    // free, and this call's packets come up on their own stream while that call's band / synthesis windows are still running.
+    OB_CUDA(cudaStreamWaitEvent(d->in_stream, d->syms_done, 0));
+    OB_CUDA(cudaStreamWaitEvent(d->in_stream, d->aux_done, 0));
+    OB_CUDA(cudaMemcpyAsync(d->d_packets, packets, nbytes, cudaMemcpyHostToDevice, d->in_stream));
+    OB_CUDA(cudaMemcpyAsync(d->d_offsets, offsets, total * sizeof(int32_t), cudaMemcpyHostToDevice, d->in_stream));
+    OB_CUDA(cudaMemcpyAsync(d->d_lens, lens, total * sizeof(int32_t), cudaMemcpyHostToDevice, d->in_stream));
+    OB_CUDA(cudaEventRecord(d->in_ready, d->in_stream));
+    OB_CUDA(cudaStreamWaitEvent(d->stream, d->in_ready, 0));
     // Framing first: it tells whether slot j is packet j for every stream (always true for code-0 packets).  The symbol kernel is
     // launched behind it right away; the host only waits for the one-word answer of the framing kernel.
     *d->h_multi = 0;                                 // the previous call's framing kernel has completed (we waited for it)
@@ -468,13 +482,14 @@ static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *p
         const int r = ob_launch(d, 0, d->S, n_frames, d->d_packets, d->d_offsets, d->d_lens, d_pcm, frame_size, d_samples, d_ranges, 0, d->stream, 0, -1, 1);
         if (r != OB_OK) return r;
     }
+    OB_CUDA(cudaEventRecord(d->syms_done, d->stream));
     OB_CUDA(cudaEventSynchronize(d->framed));
     const int multi = *(volatile int32_t *)d->h_multi;
     // The call is processed in chunks so that the device->host copy of chunk k overlaps the kernels of chunk k+1 (kernels on
     // d->stream, copies on d->copy_stream, one event per chunk).  With several frames per stream the chunks are FRAME windows
     // of all streams: every launch keeps the full stream-level parallelism the synthesis kernel needs (one block per stream),
     // and the per-stream state simply carries over from launch to launch.  Single-frame calls are split by stream ranges.
-    int nchunks = total >= 65536 ? 5 : (total >= 16384 ? 2 : 1);
+    int nchunks = total >= 65536 ? 3 : (total >= 16384 ? 2 : 1);   // measured (204 800 frames, two calls in flight): 1: 202 k, 2: 208 k, 3: 209 k, 5: 209 k (int16: 205 / 206 / 206 / 200 k), 8: 202 k
     if (const char *v = getenv("OB_DEC_CHUNKS")) { const int t = atoi(v); if (t >= 1) nchunks = t; }      // tuning aid
     if (nchunks > OB_MAX_CHUNKS) nchunks = OB_MAX_CHUNKS;
     const size_t pf = (size_t)frame_size * d->CC;
