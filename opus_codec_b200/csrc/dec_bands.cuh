@@ -201,15 +201,19 @@ OB_DEV void ob_exp_rotation_inv(const G &g, float *X, int len, int stride, int K
     ob_rot_pass(g, X, stride, len, 1, c, s);
 }
 
-// Per-warp shared-memory working set of the band-reconstruction stage.
-struct ObBandsShared {
-    float xb[2 * OB_MAX_BAND];          // current band: channel 0 at [0,176), channel 1 at [176,352)
-    float norm[2 * OB_NORM_LEN];        // folding source per channel (bands.c:1438)
+// Per-warp shared-memory working set of the band-reconstruction stage.  CH = 1: room for mono frames only (5.3 KB instead of 8.5 KB per
+// warp: 30 instead of 24 resident warps per SM, the kernel is occupancy bound); the second-channel halves are then never touched.
+template <int CH>
+struct ObBandsSharedT {
+    static constexpr int channels = CH;
+    float xb[CH * OB_MAX_BAND];         // current band: channel 0 at [0,176), channel 1 at [176,352)
+    float norm[CH * OB_NORM_LEN];       // folding source per channel (bands.c:1438)
     float scratch[OB_MAX_BAND];         // transformed copy of the folding source (lowband_scratch)
     float tmp[OB_MAX_BAND];             // Hadamard permutation buffer
     ObLeaf leaves[32];                  // leaves of the current band (<= 16 per quant_band call, two calls)
     ObBand bands[OB_NB];
 };
+typedef ObBandsSharedT<2> ObBandsShared;
 
 // Fills one terminal partition (bands.c:1038-1103).  X already holds (float)iy for PULSES leaves.
 // lowband: folding source aligned with the band start.
@@ -255,8 +259,8 @@ OB_DEV void ob_fill_leaf(const G &g, const ObLeaf &lf, float *Xb, int off_in_ban
 
 // quant_band, resynthesis side (bands.c:1109-1231).  Xb: band buffer of this channel (already holding (float)iy);
 // leaves: staged leaf records [0, leaf_cnt); lowband: source in norm[] or nullptr; lowband_out: destination in norm[] or nullptr.
-template <class G>
-OB_DEV void ob_band_call(const G &g, ObBandsShared &sh, const ObLeaf *leaves, int leaf_cnt, int band_off_abs, float *Xb, int N, int B,
+template <class G, class SH>
+OB_DEV void ob_band_call(const G &g, SH &sh, const ObLeaf *leaves, int leaf_cnt, int band_off_abs, float *Xb, int N, int B,
         int tf_change, const float *lowband, float *lowband_out, uint32_t seed_in, const ObLcg &step, int spread)
 {
     const int N0 = N, longBlocks = B == 1;
@@ -330,11 +334,11 @@ OB_DEV void ob_stereo_merge(const G &g, float *X, float *Y, float mid, int N)
 // Reconstructs the normalised spectrum of one frame band by band and writes it to Xout (C*N floats, channel c at
 // c*N; coefficients of bands >= end are NOT written).  seed_in: the stream's range-coder state left by the previous
 // frame (celt_decoder.c:1275 passes &st->rng).
-template <class G>
-OB_DEV void ob_reconstruct_bands(const G &g, const ObFrameIR *ir, uint32_t seed_in, ObBandsShared &sh, float *Xout)
+template <class G, class SH>
+OB_DEV void ob_reconstruct_bands(const G &g, const ObFrameIR *ir, uint32_t seed_in, SH &sh, float *Xout)
 {
     const ObFrameHdr &h = ir->hdr;
-    const int LM = h.LM, M = 1 << LM, C = h.C, N = OB_SHORT << LM, end = h.end;
+    const int LM = h.LM, M = 1 << LM, C = SH::channels == 1 ? 1 : h.C, N = OB_SHORT << LM, end = h.end;     // mono-only instantiation: the stereo paths compile away
     const int Bfr = (h.flags & OB_F_TRANSIENT) ? M : 1, spread = h.spread;
     const ObLcg step = ob_lcg_pow((uint32_t)g.n);
     float *norm = sh.norm, *norm2 = sh.norm + OB_NORM_LEN;

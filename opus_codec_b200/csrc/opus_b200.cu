@@ -89,23 +89,48 @@ __global__ void ob_k_plan(ObFrameIR *__restrict__ ir, ObDecState *__restrict__ s
 }
 
 #define OB_BANDS_WARPS 6
+#define OB_BANDS_WARPS_MONO 4      // measured, 204 800 mono frames: 2 warps / block 5.99 ms, 3: 6.10, 4: 6.08, 5: 6.23, 6: 6.24 (stereo-sized: 7.64)
 #define OB_BANDS_SMEM_PER_WARP ((int)sizeof(ObBandsShared))
+#define OB_BANDS_SMEM_PER_WARP_MONO ((int)sizeof(ObBandsSharedT<1>))
+// CH = 2: any frame.  CH = 1 (decoders created with one channel): shared memory for mono frames only -- more resident warps; a stereo frame
+// (legal: a mono decoder down-mixes it) is put on the straggler list instead and reconstructed by ob_k_bands_stragglers right after.
+template <int CH>
 __global__ void __launch_bounds__(OB_BANDS_WARPS * 32)
-ob_k_bands(const ObFrameIR *__restrict__ ir, const int32_t *__restrict__ nslots, float *__restrict__ Xg, int S, int cap, int f0, int Fc)
+ob_k_bands(const ObFrameIR *__restrict__ ir, const int32_t *__restrict__ nslots, float *__restrict__ Xg, int S, int cap, int f0, int Fc,
+           int32_t *__restrict__ strag_list, int32_t *__restrict__ strag_count)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5;
-    const int k = blockIdx.x * OB_BANDS_WARPS + warp;
+    const int k = blockIdx.x * (blockDim.x >> 5) + warp;
     if (k >= S * Fc) return;
     const int s = k / Fc, f = f0 + k % Fc;
     if (f >= nslots[s]) return;
     const size_t w = (size_t)s * cap + f;
     const ObFrameIR *fr = ir + w;
     if (fr->hdr.status <= 0 || (fr->hdr.flags & OB_F_LOST)) return;
+    if (CH == 1 && fr->hdr.C == 2) {
+        if ((threadIdx.x & 31) == 0) strag_list[atomicAdd(strag_count, 1)] = (int32_t)w;
+        return;
+    }
     const uint32_t seed = fr->hdr.seed_in;       // st->rng before this frame, stamped by the plan pass
-    ObBandsShared &sh = *reinterpret_cast<ObBandsShared *>(smem_raw + (size_t)warp * OB_BANDS_SMEM_PER_WARP);
+    ObBandsSharedT<CH> &sh = *reinterpret_cast<ObBandsSharedT<CH> *>(smem_raw + (size_t)warp * sizeof(ObBandsSharedT<CH>));
     ObWarp g;
     ob_reconstruct_bands(g, fr, seed, sh, Xg + (size_t)w * OB_X_STRIDE);
+}
+
+__global__ void __launch_bounds__(OB_BANDS_WARPS * 32)
+ob_k_bands_stragglers(const ObFrameIR *__restrict__ ir, float *__restrict__ Xg, const int32_t *__restrict__ strag_list, const int32_t *__restrict__ strag_count)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, n = *strag_count;
+    ObBandsShared &sh = *reinterpret_cast<ObBandsShared *>(smem_raw + (size_t)warp * OB_BANDS_SMEM_PER_WARP);
+    ObWarp g;
+    for (int i = blockIdx.x * OB_BANDS_WARPS + warp; i < n; i += gridDim.x * OB_BANDS_WARPS) {
+        const size_t w = (size_t)strag_list[i];
+        const ObFrameIR *fr = ir + w;
+        ob_reconstruct_bands(g, fr, fr->hdr.seed_in, sh, Xg + w * OB_X_STRIDE);
+        __syncwarp();
+    }
 }
 
 #define OB_SYNTH_THREADS 128
@@ -235,6 +260,7 @@ struct ObDecoder {
     int16_t *d_pcm16_2[2], *cur_pcm16;    // int16 API: device-side int16 output (per buffer pair), the one of the call being enqueued
     int32_t *d_multi, *h_multi;           // "some packet is not one slot": a word of mapped pinned host memory (host pointer, device alias)
     cudaEvent_t framed;
+    int32_t *d_strag_list, *d_strag_count; int n_sm;   // mono decoders: stereo frames met by the mono-sized band kernel (ob_k_bands<1>)
     cudaStream_t in_stream;               // host->device staging of a call's packets: runs beside the previous call's band / synthesis kernels
     cudaEvent_t syms_done, in_ready;      // the symbol kernel has read the staged packets / the next call's packets are staged
     ObFrameIR *d_ir;
@@ -284,8 +310,17 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
     if (timed) OB_CUDA(cudaEventRecord(d->ev[1], stream));
     if (which & 2) {
         ob_k_plan<<<(Sc + 3) / 4, 128, 0, stream>>>(ir, st, nslots, Sc, cap, f0, Fc, d->CC);
-        ob_k_bands<<<(total + OB_BANDS_WARPS - 1) / OB_BANDS_WARPS, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, stream>>>(
-            ir, nslots, X, Sc, cap, f0, Fc);
+        if (d->CC == 1) {
+            // one counter per compute stream (launches on a stream are ordered), one list region per stream range
+            int32_t *cnt = d->d_strag_count + (stream == d->aux_stream ? 1 : 0), *list = d->d_strag_list + c0;
+            OB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int32_t), stream));
+            const int mw = OB_BANDS_WARPS_MONO;
+            ob_k_bands<1><<<(total + mw - 1) / mw, mw * 32, mw * OB_BANDS_SMEM_PER_WARP_MONO, stream>>>(ir, nslots, X, Sc, cap, f0, Fc, list, cnt);
+            ob_k_bands_stragglers<<<d->n_sm, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, stream>>>(ir, X, list, cnt);
+            d->launches += 1;
+        } else
+            ob_k_bands<2><<<(total + OB_BANDS_WARPS - 1) / OB_BANDS_WARPS, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, stream>>>(
+                ir, nslots, X, Sc, cap, f0, Fc, nullptr, nullptr);
         if (timed) OB_CUDA(cudaEventRecord(d->ev[2], stream));
         ob_k_synth<<<Sc, OB_SYNTH_THREADS, 0, stream>>>(ir, slots, nslots, X, st, hist, ring, d_pcm + w0 * (size_t)frame_size * d->CC,
                                                          d->cur_pcm16 ? d->cur_pcm16 + w0 * (size_t)frame_size * d->CC : nullptr, d_samples + w0,
@@ -305,7 +340,7 @@ ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
     int err = OB_OK;
     ObDecoder *d = nullptr;
     int ndev = 0;
-    if (n_streams <= 0 || (channels != 1 && channels != 2) || max_frames <= 0 || max_frames > 65535) err = OB_BAD_ARG;   // ObSlot.pkt is 16 bits
+    if (n_streams <= 0 || (channels != 1 && channels != 2) || max_frames <= 0 || max_frames > 65535 || (size_t)n_streams * (size_t)max_frames > 0x7fffffffu) err = OB_BAD_ARG;   // ObSlot.pkt is 16 bits; slot indices are 32 bits
     else if (fs != 48000 && fs != 24000 && fs != 16000 && fs != 12000 && fs != 8000) err = OB_BAD_ARG;     // opus_decoder_init, opus_decoder.c:130-131
     else if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
         fprintf(stderr, "opus_b200: no usable CUDA device (count=%d, requested=%d); there is no CPU fallback\n", ndev, device);
@@ -348,7 +383,15 @@ ObDecoder *ob_decoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         ok = ok && cudaEventCreateWithFlags(&d->syms_done, cudaEventDisableTiming) == cudaSuccess
                 && cudaEventCreateWithFlags(&d->in_ready, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaMalloc(&d->d_gather, sizeof(int32_t) * n_streams) == cudaSuccess;
-        ok = ok && cudaFuncSetAttribute(ob_k_bands, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(ob_k_bands<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP) == cudaSuccess;
+        ok = ok && cudaFuncSetAttribute(ob_k_bands_stragglers, cudaFuncAttributeMaxDynamicSharedMemorySize, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP) == cudaSuccess;
+        if (channels == 1) {
+            cudaDeviceProp prop;
+            ok = ok && cudaGetDeviceProperties(&prop, device) == cudaSuccess;
+            d->n_sm = ok ? prop.multiProcessorCount : 1;
+            ok = ok && cudaMalloc(&d->d_strag_list, sizeof(int32_t) * (size_t)n_streams * max_frames) == cudaSuccess
+                    && cudaMalloc(&d->d_strag_count, 2 * sizeof(int32_t)) == cudaSuccess;
+        }
         if (!ok) {
             fprintf(stderr, "opus_b200: device allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
             ob_decoder_destroy(d);
@@ -369,7 +412,7 @@ void ob_decoder_destroy(ObDecoder *d)
     if (!d) return;
     cudaSetDevice(d->device);
     if (d->stream) cudaStreamSynchronize(d->stream);
-    cudaFree(d->d_state); cudaFree(d->d_hist); cudaFree(d->d_ring); cudaFree(d->d_slots); cudaFree(d->d_nslots); if (d->h_multi) cudaFreeHost(d->h_multi); if (d->framed) cudaEventDestroy(d->framed); cudaFree(d->d_ir); cudaFree(d->d_X); cudaFree(d->d_packets);
+    cudaFree(d->d_state); cudaFree(d->d_hist); cudaFree(d->d_ring); cudaFree(d->d_slots); cudaFree(d->d_nslots); if (d->h_multi) cudaFreeHost(d->h_multi); if (d->framed) cudaEventDestroy(d->framed); cudaFree(d->d_ir); cudaFree(d->d_X); cudaFree(d->d_packets); cudaFree(d->d_strag_list); cudaFree(d->d_strag_count);
     cudaFree(d->d_offsets); cudaFree(d->d_lens); cudaFree(d->d_gather);
     for (int p = 0; p < 2; p++) { cudaFree(d->d_samples2[p]); cudaFree(d->d_ranges2[p]); cudaFree(d->d_pcm2[p]); cudaFree(d->d_pcm16_2[p]); if (d->out_done[p]) cudaEventDestroy(d->out_done[p]); }
     if (d->aux_done) cudaEventDestroy(d->aux_done);
