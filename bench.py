@@ -505,7 +505,7 @@ def run_ours(args):
         achieved = bytes_per_launch / (kms[dom] / 1000.0) / 1e9
         traffic, traffic_src = None, None
         try:      # DRAM bytes of one launch of that kernel at this shape, from the committed ncu --set full capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01f_dram_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01m_dram_traffic.json")))
             if tj["frames_per_launch"] == S * F:
                 traffic, traffic_src = tj["kernels"][names[dom]]["dram_bytes"], tj["source"]
         except Exception:
