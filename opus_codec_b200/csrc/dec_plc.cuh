@@ -80,8 +80,8 @@ OB_DEV void ob_plan_frame(ObPlanState &p, ObFrameHdr &h, int CC)
 }
 
 // ---- prefilter_and_fold (celt_decoder.c:515-550): undo the post-filter on the concealed overlap and fold it like the TDAC would ----
-template <class G>
-OB_DEV void ob_prefilter_and_fold(const G &g, ObSynthShared &sh, int CC)
+template <class G, class SH>
+OB_DEV void ob_prefilter_and_fold(const G &g, SH &sh, int CC)
 {
     const float gains[3][3] = {{0.3066406250f, 0.2170410156f, 0.1296386719f}, {0.4638671875f, 0.2680664062f, 0.f}, {0.7998046875f, 0.1000976562f, 0.f}};
     const int T1 = ob_imax(sh.pf_period, 15), ts = sh.pf_tapset;
@@ -105,8 +105,8 @@ OB_DEV void ob_prefilter_and_fold(const G &g, ObSynthShared &sh, int CC)
 
 // ---- noise-based PLC / comfort noise (celt_decoder.c:648-699).  Leaves the denormalised spectrum source in sh.freq (normalised X)
 // and the decayed energies in sh.oldBandE; the caller runs the common denormalise + IMDCT + de-emphasis. ----
-template <class G>
-OB_DEV void ob_plc_noise_fill(const G &g, ObSynthShared &sh, int N, int LM, int loss_duration, uint32_t seed0, int end, int CC)
+template <class G, class SH>
+OB_DEV void ob_plc_noise_fill(const G &g, SH &sh, int N, int LM, int loss_duration, uint32_t seed0, int end, int CC)
 {
     const int effEnd = ob_imin(end, OB_NB);
     const float decay = loss_duration == 0 ? 1.5f : .5f;
@@ -142,8 +142,8 @@ OB_DEV void ob_plc_noise_fill(const G &g, ObSynthShared &sh, int N, int LM, int 
 
 // ---- pitch search on the decoder history (celt_plc_pitch_search: pitch_downsample + pitch_search, pitch.c:140-217, :302-411) ----
 // work: >= 1024 + 332 + 487 floats; xc: >= 310 floats.  Every lag's correlation is one lane's in-order sum.
-template <class G>
-OB_DEV int ob_plc_pitch_search(const G &g, ObSynthShared &sh, int CC, float *work, float *xc)
+template <class G, class SH>
+OB_DEV int ob_plc_pitch_search(const G &g, SH &sh, int CC, float *work, float *xc)
 {
     const int n = OB_RING >> 1;                                   // 1024
     float *lp = work;
@@ -294,8 +294,8 @@ OB_DEV int ob_plc_pitch_search(const G &g, ObSynthShared &sh, int CC, float *wor
 }
 
 // ---- pitch-based PLC (celt_decoder.c:700-905): writes N + overlap concealed samples at buf[c] + HISTK ----
-template <class G>
-OB_DEV void ob_plc_pitch(const G &g, ObSynthShared &sh, int N, int loss_duration, int CC)
+template <class G, class SH>
+OB_DEV void ob_plc_pitch(const G &g, SH &sh, int N, int loss_duration, int CC)
 {
     float *work = &sh.freq[0][0];                                  // 1920 floats, free while no spectrum is in flight
     float fade = 1.f;
@@ -443,8 +443,8 @@ OB_DEV void ob_plc_pitch(const G &g, ObSynthShared &sh, int N, int loss_duration
 }
 
 // ---- energy safety of the first good frame after a loss (celt_decoder.c:1171-1198); acts on both channels' energies ----
-template <class G>
-OB_DEV void ob_post_loss_energy(const G &g, ObSynthShared &sh, int LM, int end, int loss_duration)
+template <class G, class SH>
+OB_DEV void ob_post_loss_energy(const G &g, SH &sh, int LM, int end, int loss_duration)
 {
     const int missing = ob_imin(10, loss_duration >> LM);
     const float safety = LM == 0 ? 1.5f : LM == 1 ? .5f : 0.f;

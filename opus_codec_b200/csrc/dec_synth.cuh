@@ -215,10 +215,11 @@ OB_DEV void ob_comb_filter(const G &g, float *x, int T0, int T1, int N, float g0
     }
 }
 
-// Shared-memory working set of one stream.
-struct ObSynthShared {
-    float buf[2][OB_BUF_LEN];        // [history | current frame | overlap tail] per channel (the tail of decode_mem)
-    float freq[2][OB_MAX_N];         // X tile -> MDCT coefficients -> PCM staging
+// Shared-memory working set of one stream.  CH = 1: a mono decoder that meets mono frames only (20 KB instead of 29 KB: 8 blocks per SM).
+template <int CH>
+struct ObSynthSharedT {
+    float buf[CH][OB_BUF_LEN];       // [history | current frame | overlap tail] per channel (the tail of decode_mem)
+    float freq[2][OB_MAX_N];         // X tile -> MDCT coefficients -> PCM staging; both halves are the pitch concealment's work area, mono or not
     float oldBandE[2 * OB_NB], oldLogE[2 * OB_NB], oldLogE2[2 * OB_NB], backgroundLogE[2 * OB_NB];
     float gain[2 * OB_NB];
     float scanA[256], scanB[256];
@@ -236,10 +237,11 @@ struct ObSynthShared {
     int32_t ring_pos;                // next write position (= oldest sample) of the global history ring
     float *ring;                     // this stream's ring: [CC][OB_RING]
 };
+typedef ObSynthSharedT<2> ObSynthShared;
 
 // Once per block: lookup tables in shared memory.
-template <class G>
-OB_DEV void ob_synth_init(const G &g, ObSynthShared &sh)
+template <class G, class SH>
+OB_DEV void ob_synth_init(const G &g, SH &sh)
 {
     for (int k = g.lane; k < 33; k += g.n) { const ObLcg p = ob_lcg_pow((uint32_t)k); sh.lcg_a[k] = p.a; sh.lcg_c[k] = p.c; }
     for (int b = g.lane; b < 104; b += g.n) {
@@ -251,8 +253,8 @@ OB_DEV void ob_synth_init(const G &g, ObSynthShared &sh)
 }
 
 // anti_collapse (bands.c:268-362) on the X tile.
-template <class G>
-OB_DEV void ob_anti_collapse(const G &g, ObSynthShared &sh, float *X, int N, uint32_t seed0)
+template <class G, class SH>
+OB_DEV void ob_anti_collapse(const G &g, SH &sh, float *X, int N, uint32_t seed0)
 {
     const ObFrameHdr &h = sh.hdr;
     const int LM = h.LM, C = h.C, end = h.end;
@@ -305,8 +307,8 @@ OB_DEV void ob_anti_collapse(const G &g, ObSynthShared &sh, float *X, int N, uin
 
 // denormalise_bands (bands.c:196-265) on the X tile in sh.freq (C coded channels, energies in sh.oldBandE), the mono<->stereo
 // cases of celt_synthesis (celt_decoder.c:415-441) and the inverse MDCTs into buf[c] + HISTK.
-template <class G>
-OB_DEV void ob_denorm_imdct(const G &g, ObSynthShared &sh, int C, int CC, int N, int LM, int end, int transient, int silence)
+template <class G, class SH>
+OB_DEV void ob_denorm_imdct(const G &g, SH &sh, int C, int CC, int N, int LM, int end, int transient, int silence)
 {
     const int M = 1 << LM;
     for (int t = g.lane; t < C * OB_NB; t += g.n) {
@@ -329,8 +331,8 @@ OB_DEV void ob_denorm_imdct(const G &g, ObSynthShared &sh, int C, int CC, int N,
 
 // de-emphasis (celt_decoder.c:249-377): y[n] = x[n] + coef*y[n-1] as a two-level scan, interleaved PCM out, then the history
 // slides by N: buf[j] <- buf[j+N] for j < HISTK + overlap (celt_decoder.c:1265-1267, done after the frame instead of before).
-template <class G>
-OB_DEV void ob_synth_tail(const G &g, ObSynthShared &sh, float *pcm, int N, int CC)
+template <class G, class SH>
+OB_DEV void ob_synth_tail(const G &g, SH &sh, float *pcm, int N, int CC)
 {
     {
         const float coef = OB_PREEMPH[0];
@@ -392,8 +394,8 @@ OB_DEV void ob_synth_tail(const G &g, ObSynthShared &sh, float *pcm, int N, int 
 // A lost packet or DTX payload: conceal h.status samples as the reference does, frame by frame (opus_decoder.c:313-335,
 // celt_decode_lost celt_decoder.c:604-968).  The integer side of the state (loss duration, skip_plc, noise seed) was stamped
 // into the header by the plan pass and is re-derived here per concealment frame with the same functions.
-template <class G>
-OB_DEV_NOINLINE int ob_conceal(const G &g, ObSynthShared &sh, float *pcm, int CC)
+template <class G, class SH>
+OB_DEV_NOINLINE int ob_conceal(const G &g, SH &sh, float *pcm, int CC)
 {
     const ObFrameHdr &h = sh.hdr;
     const int total = h.status;
@@ -499,8 +501,8 @@ OB_DEV void ob_packet_to_int16(const G &g, float *x, int16_t *out, int n, int CC
 
 // Decodes frame `ir` (already reconstructed normalised spectrum Xg: C*N floats in global memory) into pcm
 // (interleaved, CC channels) and advances the shared-memory state.  Returns samples per channel or an error.
-template <class G>
-OB_DEV int ob_synth_frame(const G &g, ObSynthShared &sh, const ObFrameIR *ir, const float *Xg, float *pcm, int CC)
+template <class G, class SH>
+OB_DEV int ob_synth_frame(const G &g, SH &sh, const ObFrameIR *ir, const float *Xg, float *pcm, int CC)
 {
     // ---- header to shared memory ----
     {

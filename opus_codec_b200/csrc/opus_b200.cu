@@ -134,15 +134,20 @@ ob_k_bands_stragglers(const ObFrameIR *__restrict__ ir, float *__restrict__ Xg, 
 }
 
 #define OB_SYNTH_THREADS 128
-__global__ void __launch_bounds__(OB_SYNTH_THREADS, 7)
-ob_k_synth(const ObFrameIR *__restrict__ ir, const ObSlot *__restrict__ slots, const int32_t *__restrict__ nslots, const float *__restrict__ Xg,
+// CH = 2: any decoder.  CH = 1: mono decoders while every frame of the launch is mono (mono-sized shared memory, 64 registers: 8 blocks
+// per SM instead of 7).  `stereo_frames` is the straggler counter the mono band kernel has just filled: the <1> instantiation runs when
+// it is zero, the <2> instantiation launched behind it when it is not -- the choice needs no host round trip.
+template <int CH>
+__global__ void __launch_bounds__(OB_SYNTH_THREADS, CH == 1 ? 8 : 7)
+ob_k_synth(const int32_t *__restrict__ stereo_frames, const ObFrameIR *__restrict__ ir, const ObSlot *__restrict__ slots, const int32_t *__restrict__ nslots, const float *__restrict__ Xg,
            ObDecState *__restrict__ st, float *__restrict__ hist, float *__restrict__ ring,
            float *__restrict__ pcm, int16_t *__restrict__ pcm16, int32_t *__restrict__ samples, uint32_t *__restrict__ ranges, int S, int F, int cap,
            int CC, int frame_size, int f0, int Fc, float decode_gain, int ds)
 {
-    __shared__ ObSynthShared sh;
+    __shared__ ObSynthSharedT<CH> sh;
     const int s = blockIdx.x;
     if (s >= S) return;
+    if (stereo_frames && (*stereo_frames != 0) == (CH == 1)) return;
     ObBlock g(sh.red);
     ObDecState *state = st + s;
     ob_synth_init(g, sh);
@@ -322,9 +327,19 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
             ob_k_bands<2><<<(total + OB_BANDS_WARPS - 1) / OB_BANDS_WARPS, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, stream>>>(
                 ir, nslots, X, Sc, cap, f0, Fc, nullptr, nullptr);
         if (timed) OB_CUDA(cudaEventRecord(d->ev[2], stream));
-        ob_k_synth<<<Sc, OB_SYNTH_THREADS, 0, stream>>>(ir, slots, nslots, X, st, hist, ring, d_pcm + w0 * (size_t)frame_size * d->CC,
-                                                         d->cur_pcm16 ? d->cur_pcm16 + w0 * (size_t)frame_size * d->CC : nullptr, d_samples + w0,
-                                                         d_ranges ? d_ranges + w0 : nullptr, Sc, F, cap, d->CC, frame_size, f0, Fc, d->gain_linear, d->ds);
+        float *pcm_w = d_pcm + w0 * (size_t)frame_size * d->CC;
+        int16_t *pcm16_w = d->cur_pcm16 ? d->cur_pcm16 + w0 * (size_t)frame_size * d->CC : nullptr;
+        uint32_t *ranges_w = d_ranges ? d_ranges + w0 : nullptr;
+        if (d->CC == 1) {
+            const int32_t *cnt = d->d_strag_count + (stream == d->aux_stream ? 1 : 0);
+            ob_k_synth<1><<<Sc, OB_SYNTH_THREADS, 0, stream>>>(cnt, ir, slots, nslots, X, st, hist, ring, pcm_w, pcm16_w, d_samples + w0, ranges_w, Sc, F, cap, d->CC,
+                                                                frame_size, f0, Fc, d->gain_linear, d->ds);
+            ob_k_synth<2><<<Sc, OB_SYNTH_THREADS, 0, stream>>>(cnt, ir, slots, nslots, X, st, hist, ring, pcm_w, pcm16_w, d_samples + w0, ranges_w, Sc, F, cap, d->CC,
+                                                                frame_size, f0, Fc, d->gain_linear, d->ds);
+            d->launches += 1;
+        } else
+            ob_k_synth<2><<<Sc, OB_SYNTH_THREADS, 0, stream>>>(nullptr, ir, slots, nslots, X, st, hist, ring, pcm_w, pcm16_w, d_samples + w0, ranges_w, Sc, F, cap, d->CC,
+                                                                frame_size, f0, Fc, d->gain_linear, d->ds);
         d->launches += 3;
     }
     if (timed) OB_CUDA(cudaEventRecord(d->ev[3], stream));
