@@ -15,6 +15,7 @@ print("Opus Codec Basic Example, batched")
 print("=================================")
 with BatchEncoder(N_STREAMS, 48000, 1, application=2049, device=0) as encoder, BatchDecoder(N_STREAMS, 48000, 1, device=0) as decoder:
     print("created %d encoders and %d decoders: 48000 Hz, 1 channel, Audio application" % (N_STREAMS, N_STREAMS))
+    encoder.set_bitrate(96000)      # at the default (51 kb/s mono) libopus gives tonal, speech-like frames to SILK: those come back as Unimplemented (-5)
     num_samples = 960                                                       # one 20 ms frame
     t = np.arange(num_samples, dtype=np.float32) / 48000.0
     freqs = 220.0 * 2.0 ** (np.arange(N_STREAMS, dtype=np.float32)[:, None] / 256.0)     # a different note per stream

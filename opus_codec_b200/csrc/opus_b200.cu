@@ -40,8 +40,10 @@ __global__ void ob_k_frame(const uint8_t *__restrict__ packets, const int32_t *_
     if (!one_to_one) *(volatile int32_t *)multi = 1;             // `multi` is mapped host memory: no copy on the stream to read it back
 }
 
+#ifndef OB_SYM_THREADS
 #define OB_SYM_THREADS 128
-__global__ void __launch_bounds__(OB_SYM_THREADS, 6)
+#endif
+__global__ void __launch_bounds__(OB_SYM_THREADS, 768 / OB_SYM_THREADS)
 ob_k_symbols(const uint8_t *__restrict__ packets, const ObSlot *__restrict__ slots, const int32_t *__restrict__ nslots,
              ObFrameIR *__restrict__ ir, int total, int dec_channels, int cap, int f0, int Fc, int phase_inv_disabled)
 {
