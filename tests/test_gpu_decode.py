@@ -492,3 +492,36 @@ def test_get_pitch_matches_reference(have_ref):
             bb, oo, ll = pack_packets([[b"" if f in (9, 10, 25) else bytes(g["packets"][s][f, :g["lens"][s][f]])] for s in range(S)])
             dec.decode_float_multi(bb, oo, ll, fs)
             assert (dec.pitch() == want[:, f]).all(), f
+
+
+def test_mono_decoder_with_mono_and_stereo_packets_across_windows(have_ref):
+    """A mono decoder fed streams that switch between mono and stereo packets (legal: the decoder down-mixes), in a call large enough to run
+    in several frame windows: some windows are all-mono (mono-sized band / synthesis kernels), others hold stereo frames (straggler pass +
+    the two-channel synthesis kernel), and the stream state must carry across the variants.  Checked against the reference on a sample."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    from opus_codec_b200.batch import BatchDecoder
+    gm, gs = load_golden("cfg2_mono_20ms_64k_cbr"), load_golden("cfg3_stereo_20ms_96k_cbr")
+    S, F = 1400, 48                                             # 67 200 frames: three windows of 16 frames
+    stride = max(gm["packets"].shape[2], gs["packets"].shape[2])
+    pk = np.zeros((S, F, stride), np.uint8); ln = np.zeros((S, F), np.int32)
+    rng = np.random.default_rng(3)
+    for s in range(S):
+        a, b = s % gm["packets"].shape[0], s % gs["packets"].shape[0]
+        kind = s % 4                                            # 0: all mono, 1: stereo in the middle window only, 2: random blocks, 3: stereo with a lost packet
+        for f in range(F):
+            stereo = (kind == 1 and 16 <= f < 32) or (kind == 2 and rng.random() < 0.3) or kind == 3
+            g, i = (gs, b) if stereo else (gm, a)
+            n = g["lens"][i][f]
+            pk[s, f, :n] = g["packets"][i][f, :n]; ln[s, f] = n
+        if kind == 3:
+            ln[s, 20] = 0
+    with BatchDecoder(S, 48000, 1, device=0, max_frames=F) as dec:
+        pcm, smp, ranges = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, 960)
+    assert (smp == 960).all()
+    for s in list(range(8)) + [S - 4, S - 3, S - 2, S - 1]:
+        ref_pcm, ref_rng, ref_smp = refpy.decode_stream(pk[s], ln[s], 960, 1, pure_c=True)
+        assert (ref_rng == ranges[s]).all(), s
+        tol = 3e-3 if s % 4 == 3 else PCM_TOL                   # concealment tolerance for the stream with a lost packet
+        assert np.abs(ref_pcm - pcm[s]).max() <= tol, s
