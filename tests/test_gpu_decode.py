@@ -525,3 +525,29 @@ def test_mono_decoder_with_mono_and_stereo_packets_across_windows(have_ref):
         assert (ref_rng == ranges[s]).all(), s
         tol = 3e-3 if s % 4 == 3 else PCM_TOL                   # concealment tolerance for the stream with a lost packet
         assert np.abs(ref_pcm - pcm[s]).max() <= tol, s
+
+
+def test_single_frame_call_split_over_two_compute_streams_with_stereo_frames():
+    """One frame per stream, 20 000 mono-decoder streams: the call is split by stream ranges over two CUDA streams, each with its own
+    stereo-frame counter and straggler list.  Every stream must decode exactly as it does in a small batch."""
+    from opus_codec_b200.batch import BatchDecoder
+    gm, gs = load_golden("cfg2_mono_20ms_64k_cbr"), load_golden("cfg3_stereo_20ms_96k_cbr")
+    S, F = 20000, 3
+    stride = max(gm["packets"].shape[2], gs["packets"].shape[2])
+    pk = np.zeros((S, F, stride), np.uint8); ln = np.zeros((S, F), np.int32)
+    for s in range(S):
+        for f in range(F):
+            g = gs if (s * 7 + f) % 5 == 0 else gm
+            i = s % g["packets"].shape[0]
+            n = g["lens"][i][f]
+            pk[s, f, :n] = g["packets"][i][f, :n]; ln[s, f] = n
+    out = np.zeros((S, F, 960), np.float32); rngs = np.zeros((S, F), np.uint32)
+    with BatchDecoder(S, 48000, 1, device=0, max_frames=1) as dec:
+        for f in range(F):                                      # one frame per call: the stream-range split
+            p, smp, r = dec.decode_float_multi(np.ascontiguousarray(pk[:, f]).reshape(-1), _offsets(S, 1, stride), ln[:, f:f + 1], 960)
+            assert (smp == 960).all()
+            out[:, f] = p[:, 0]; rngs[:, f] = r[:, 0]
+    sub = np.r_[0:40, 9990:10030, S - 40:S]
+    with BatchDecoder(len(sub), 48000, 1, device=0, max_frames=F) as dec:
+        p, smp, r = dec.decode_float_multi(np.ascontiguousarray(pk[sub]).reshape(-1), _offsets(len(sub), F, stride), ln[sub], 960)
+    assert np.array_equal(p, out[sub]) and (r == rngs[sub]).all()
