@@ -301,3 +301,29 @@ def test_encoder_ctls_on_gpu_match_reference(have_ref):
         with pytest.raises(OpusError) as e:
             enc.encode_float_multi(x, 960)
         assert e.value.code == BAD_ARG
+
+
+@pytest.mark.timeout(600)
+def test_full_size_batch_16384_streams_tiling_property(have_ref):
+    """BASELINE configs[2] at full size (16 384 stereo streams, complexity 10, 96 kb/s CBR): the streams are a tiling of 64 distinct inputs,
+    so stream s must produce exactly the packets of stream s % 64 encoded in a small batch -- every one of the 65 536 packets is checked
+    through that property, and the small batch against the reference encoder."""
+    from opus_codec_b200.batch import BatchEncoder
+    S, F, P = 16384, 4, 64
+    pool = np.stack([synth.stream_pcm(s, 960 * F, 2, base_seed=2024) for s in range(P)]).reshape(P, F, 1920)
+    with BatchEncoder(P, 48000, 2, device=0, max_frames=F) as enc:
+        enc.set_bitrate(96000); enc.set_complexity(10); enc.set_vbr(False)
+        small, small_len, small_rng = enc.encode_float_multi(pool, 960, max_bytes=256)
+    big_in = np.ascontiguousarray(pool[np.arange(S) % P])
+    with BatchEncoder(S, 48000, 2, device=0, max_frames=F) as enc:
+        enc.set_bitrate(96000); enc.set_complexity(10); enc.set_vbr(False)
+        out, lens, rng = enc.encode_float_multi(big_in, 960, max_bytes=256)
+    assert (lens == 240).all()
+    idx = np.arange(S) % P
+    assert np.array_equal(out, small[idx]) and np.array_equal(rng, small_rng[idx])
+    if have_ref:
+        same = 0
+        for s in range(8):
+            ro, rl, rr = _ref_c_encode(pool[s].reshape(-1), 960, 2, 96000, 0, 10)
+            same += int(((ro[:, :256] == small[s]).all(axis=1) & (rl == small_len[s]) & (rr == small_rng[s])).sum())
+        assert same >= 0.97 * 8 * F
