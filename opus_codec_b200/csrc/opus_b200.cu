@@ -99,8 +99,11 @@ __global__ void ob_k_plan(ObFrameIR *__restrict__ ir, ObDecState *__restrict__ s
 #define OB_BANDS_SMEM_PER_WARP_MONO ((int)sizeof(ObBandsSharedT<1>))
 // CH = 2: any frame.  CH = 1 (decoders created with one channel): shared memory for mono frames only -- more resident warps; a stereo frame
 // (legal: a mono decoder down-mixes it) is put on the straggler list instead and reconstructed by ob_k_bands_stragglers right after.
+#ifndef OB_BANDS_BLOCKS_MONO
+#define OB_BANDS_BLOCKS_MONO 8      // 64 registers; 9 blocks (56 registers) and 10 (48) spill and measured 3 % slower
+#endif
 template <int CH>
-__global__ void __launch_bounds__(OB_BANDS_WARPS * 32)
+__global__ void __launch_bounds__(CH == 1 ? OB_BANDS_WARPS_MONO * 32 : OB_BANDS_WARPS * 32, CH == 1 ? OB_BANDS_BLOCKS_MONO : 1)
 ob_k_bands(const ObFrameIR *__restrict__ ir, const int32_t *__restrict__ nslots, float *__restrict__ Xg, int S, int cap, int f0, int Fc,
            int32_t *__restrict__ strag_list, int32_t *__restrict__ strag_count)
 {
