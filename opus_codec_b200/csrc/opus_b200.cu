@@ -103,7 +103,7 @@ __global__ void ob_k_plan(ObFrameIR *__restrict__ ir, ObDecState *__restrict__ s
 #define OB_BANDS_BLOCKS_MONO 8      // 64 registers; 9 blocks (56 registers) and 10 (48) spill and measured 3 % slower
 #endif
 template <int CH>
-__global__ void __launch_bounds__(CH == 1 ? OB_BANDS_WARPS_MONO * 32 : OB_BANDS_WARPS * 32, CH == 1 ? OB_BANDS_BLOCKS_MONO : 1)
+__global__ void __launch_bounds__(CH == 1 ? OB_BANDS_WARPS_MONO * 32 : OB_BANDS_WARPS * 32, CH == 1 ? OB_BANDS_BLOCKS_MONO : 0)      // 0 = no minimum for the stereo-sized variant, as before
 ob_k_bands(const ObFrameIR *__restrict__ ir, const int32_t *__restrict__ nslots, float *__restrict__ Xg, int S, int cap, int f0, int Fc,
            int32_t *__restrict__ strag_list, int32_t *__restrict__ strag_count)
 {
