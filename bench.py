@@ -548,7 +548,8 @@ def run_ours(args):
                        "l2": "per-step working set (IR+spectrum+PCM, %.1f GB) exceeds the 126 MB L2" % ((S * F * (12.6e3 + 7.7e3 + 3.84e3)) / 1e9),
                        "sharding": "streams split by rank, no collective"},
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "pcie_d2h_GBps": pcie, "numa": numa,
+                    "pcie_d2h_GBps": pcie, "d2h_achieved_GBps": (d2h * e2e_steps / (ms_e2e / 1000.0) / 1e9) if e2e_steps else None,
+                    "pcie_note": "the float leg needs d2h_bytes_per_step x steps/s of sustained host-bound traffic; pcie_d2h_GBps is a short 256 MB probe", "numa": numa,
                     "int16_api": {"value": audio_per_step * e2e_steps / (ms_i16 / 1000.0) if ms_i16 else None, "unit": "audio-s/s",
                                   "d2h_bytes_per_step": int(2 * h_pcm[0].numel() + 8 * h_smp[0].numel())},
                     "mode": "host wall clock; two host-pointer calls in flight (ob_decode_float_multi_async + ob_decoder_wait), pinned buffers"},
