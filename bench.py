@@ -278,10 +278,12 @@ def run_transcode_leg(args, L, local, world, rank, dev, barrier):
     g1.record(dext)
     barrier()
     ms_dec = max_over_ranks(g0.elapsed_time(g1), dev)
+    kms_stereo = [float(v) for v in dec.kernel_ms()]           # symbols, bands, synthesis of the last step
     dec.close(); enc.close()
     audio = world * S * F * 0.02
     stereo = {"workload": "%d stereo 48 kHz CELT-only 20 ms @96 kb/s decode streams per GPU, kernel-resident" % S, "value": audio * steps / (ms_dec / 1000.0),
-              "unit": "audio-s/s", "ms_per_step": ms_dec / steps, "rt_stream_capacity_per_gpu": audio * steps / (ms_dec / 1000.0) / world, "target": 4096}
+              "unit": "audio-s/s", "ms_per_step": ms_dec / steps, "rt_stream_capacity_per_gpu": audio * steps / (ms_dec / 1000.0) / world, "target": 4096,
+              "kernel_ms": dict(zip(["ob_k_symbols", "ob_k_bands", "ob_k_synth"], kms_stereo))}
     return {"decode_stereo": stereo, "workload": "%d stereo streams per GPU decoded (96 kb/s CBR packets) and re-encoded at 96 kb/s CBR, complexity 10, PCM stays on the device "
                         "(BASELINE configs[4] per-GPU share)" % S,
             "frames_per_stream_per_step": F, "steps": steps, "value": audio * steps / (ms / 1000.0), "unit": "audio-s/s", "ms_per_step": ms / steps,
