@@ -434,7 +434,11 @@ void ob_decoder_destroy(ObDecoder *d)
 {
     if (!d) return;
     cudaSetDevice(d->device);
+    // every stream of this decoder drains first: an asynchronous call may still be copying into the caller's buffers
+    if (d->in_stream) cudaStreamSynchronize(d->in_stream);
     if (d->stream) cudaStreamSynchronize(d->stream);
+    if (d->aux_stream) cudaStreamSynchronize(d->aux_stream);
+    if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
     cudaFree(d->d_state); cudaFree(d->d_hist); cudaFree(d->d_ring); cudaFree(d->d_slots); cudaFree(d->d_nslots); if (d->h_multi) cudaFreeHost(d->h_multi); if (d->framed) cudaEventDestroy(d->framed); cudaFree(d->d_ir); cudaFree(d->d_X); cudaFree(d->d_packets); cudaFree(d->d_strag_list); cudaFree(d->d_strag_count);
     cudaFree(d->d_offsets); cudaFree(d->d_lens); cudaFree(d->d_gather);
     for (int p = 0; p < 2; p++) { cudaFree(d->d_samples2[p]); cudaFree(d->d_ranges2[p]); cudaFree(d->d_pcm2[p]); cudaFree(d->d_pcm16_2[p]); if (d->out_done[p]) cudaEventDestroy(d->out_done[p]); }
