@@ -197,6 +197,8 @@ void ob_encoder_destroy(ObEncoder *e)
 {
     if (!e) return;
     cudaSetDevice(e->device);
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+    if (e->an_stream) cudaStreamSynchronize(e->an_stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_streams); cudaFree(e->d_pcm); cudaFree(e->d_pcm16); cudaFree(e->d_out); cudaFree(e->d_lens); cudaFree(e->d_ranges);
     for (int i = 0; i < 2; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
