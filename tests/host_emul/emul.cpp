@@ -152,3 +152,32 @@ int emul_opus_encode_stream_app(const float *pcm, int nframes, int frame_size, i
     return rc;
 }
 }
+
+// ---- self-delimited framing (opus_packet_parse_impl / opus_repacketizer_out_range_impl with self_delimited = 1): the form multistream
+// packets use for all but their last stream.  Not reachable through the public ABI; exercised here against the reference's internals. ----
+extern "C" {
+// Parses one (possibly self-delimited) packet at data.  sizes: 48 entries; offs: frame offsets from data.  Returns the frame count or an error.
+int emul_parse_packet(const unsigned char *data, int len, int self_delimited, unsigned char *toc, int *offs, short *sizes, int *payload_offset,
+                      int *packet_offset, int *padding_len)
+{
+    const uint8_t *frames[48];
+    const uint8_t *padding = nullptr;
+    int16_t sz[48];
+    const int n = ob_rp_parse(data, len, self_delimited, toc, frames, sz, payload_offset, packet_offset, &padding, padding_len);
+    for (int i = 0; i < n; i++) { sizes[i] = sz[i]; offs[i] = (int)(frames[i] - data); }
+    return n;
+}
+// cat (plain framing) of n packets, then out_range in the self-delimited form.
+int emul_repacketize_self_delimited(const unsigned char *packets, const int *offsets, const int *lens, int n, int begin, int end, unsigned char *out,
+                                    int maxlen, int pad)
+{
+    ObRepack rp;
+    ob_repack_init(&rp);
+    for (int i = 0; i < n; i++) { const int r = ob_repack_cat(&rp, packets + offsets[i], lens[i], 0); if (r != OB_OK) return r; }
+    const int ne = ob_repack_count_ext(&rp, begin < 0 ? 0 : begin, end > rp.nb_frames ? rp.nb_frames : end);
+    ObExt *ext = (ObExt *)calloc((size_t)(ne > 0 ? ne : 1), sizeof(ObExt));
+    const int r = ob_repack_out_range(ObRpLanes1(), &rp, begin, end, out, maxlen, 1, pad, ext, ne > 0 ? ne : 0);
+    free(ext);
+    return r;
+}
+}

@@ -241,3 +241,65 @@ def test_pad_unpad_and_extensions_match_reference(ref):
     with pytest.raises(OpusError) as e:
         packet_pad(fr[0], len(fr[0]) - 1)
     assert e.value.code == -1
+
+
+def test_self_delimited_framing_matches_reference_internals(ref):
+    """opus_packet_parse_impl / opus_repacketizer_out_range_impl with self_delimited = 1 (the framing of all but the last stream of a
+    multistream packet): the restatement in csrc/repacketizer.cuh, compiled by g++, against the reference's internal functions."""
+    import os, subprocess, tempfile
+    from conftest import ROOT
+    so = os.path.join(tempfile.gettempdir(), "ob_emul_pkt_%d.so" % os.getpid())
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-o", so,
+                    os.path.join(ROOT, "tests", "host_emul", "emul.cpp")], check=True)
+    E = C.CDLL(so)
+    vp, i32 = C.c_void_p, C.c_int32
+    ref.opus_packet_parse_impl.argtypes = [vp, i32, C.c_int, vp, vp, vp, vp, vp, vp, vp]; ref.opus_packet_parse_impl.restype = C.c_int
+    ref.opus_repacketizer_out_range_impl.argtypes = [vp, C.c_int, C.c_int, vp, i32, C.c_int, C.c_int, vp, C.c_int]
+    ref.opus_repacketizer_out_range_impl.restype = i32
+    rng = np.random.default_rng(17)
+    pkts = [p for p in sample_packets() if len(p) < 4000]
+    g = load_golden(golden_names()[0])
+    fr = [bytes(g["packets"][0][f, :g["lens"][0][f]]) for f in range(6)]
+    pkts += [with_padding(fr[:2], ext_padding())]
+    made = []
+    for p in pkts:                                            # plain packet -> self-delimited packet, both implementations
+        for pad in (0, 1):
+            maxlen = len(p) + 3 + (40 if pad else 0)
+            rp = ref.opus_repacketizer_create()
+            b = _buf(p)
+            if ref.opus_repacketizer_cat(rp, b, len(p)) != 0:
+                ref.opus_repacketizer_destroy(rp); continue
+            nfr = ref.opus_repacketizer_get_nb_frames(rp)
+            want = (C.c_uint8 * maxlen)()
+            n0 = ref.opus_repacketizer_out_range_impl(rp, 0, nfr, want, maxlen, 1, pad, None, 0)
+            ref.opus_repacketizer_destroy(rp)
+            got = (C.c_uint8 * maxlen)()
+            off = (C.c_int * 1)(0); ln = (C.c_int * 1)(len(p))
+            n1 = E.emul_repacketize_self_delimited(b, off, ln, 1, 0, nfr, got, maxlen, pad)
+            assert n0 == n1 and (n0 < 0 or bytes(want[:n0]) == bytes(got[:n0])), (p[:4].hex(), pad, n0, n1)
+            if n0 > 0:
+                made.append(bytes(want[:n0]))
+    assert len(made) > 60
+    # parse them back (self-delimited), followed by trailing bytes of another packet, plus damaged variants
+    cases = []
+    for m in made:
+        cases.append(m + fr[5])
+        q = bytearray(m + fr[5]); q[int(rng.integers(0, min(len(q), 8)))] ^= 1 << int(rng.integers(0, 8)); cases.append(bytes(q))
+        cases.append(m[:int(rng.integers(1, len(m)))])
+    seen = set()
+    for c in cases:
+        b = _buf(c)
+        toc0 = C.c_uint8(0); po0 = C.c_int(0); pko0 = C.c_int32(0); pad0 = C.c_int32(0); padp = C.c_void_p(0)
+        frames = (C.c_void_p * 48)(); sz0 = (C.c_int16 * 48)()
+        n0 = ref.opus_packet_parse_impl(b, len(c), 1, C.byref(toc0), frames, sz0, C.byref(po0), C.byref(pko0), C.byref(padp), C.byref(pad0))
+        toc1 = C.c_uint8(0); po1 = C.c_int(0); pko1 = C.c_int(0); pad1 = C.c_int(0)
+        offs = (C.c_int * 48)(); sz1 = (C.c_int16 * 48)()
+        n1 = E.emul_parse_packet(b, len(c), 1, C.byref(toc1), offs, sz1, C.byref(po1), C.byref(pko1), C.byref(pad1))
+        assert n0 == n1, (c[:6].hex(), n0, n1)
+        seen.add(n0 if n0 < 0 else "ok")
+        if n0 > 0:
+            base = C.addressof(b)
+            assert toc0.value == toc1.value and po0.value == po1.value and pko0.value == pko1.value and pad0.value == pad1.value
+            assert list(sz0[:n0]) == list(sz1[:n0]) and [frames[i] - base for i in range(n0)] == list(offs[:n0])
+    assert {"ok", -4} <= seen
+    os.remove(so)
