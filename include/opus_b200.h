@@ -225,6 +225,11 @@ int32_t ob_packet_parse(const uint8_t *packet, int32_t len, uint8_t *out_toc, in
  * pad: OB_OK or an error; unpad: the new length.  Padding extensions (opus/src/extensions.c) are kept by pad and dropped by unpad. */
 int32_t ob_packet_pad(uint8_t *packet, int32_t len, int32_t new_len);
 int32_t ob_packet_unpad(uint8_t *packet, int32_t len);
+/* opus_multistream_packet_pad / _unpad (multistream_packet_pad / _unpad, src/packet.rs:253-290; opus/src/repacketizer.c:355-464): the same for a
+ * multistream packet of nb_streams concatenated streams (all but the last in the self-delimited framing).  Byte work only: multistream
+ * coding itself is out of scope. */
+int32_t ob_multistream_packet_pad(uint8_t *packet, int32_t len, int32_t new_len, int32_t nb_streams);
+int32_t ob_multistream_packet_unpad(uint8_t *packet, int32_t len, int32_t nb_streams);
 
 /* n x opus_pcm_soft_clip(pcm, frame_size, channels, softclip_mem) (soft_clip, src/packet.rs:123-155; opus/src/opus.c:39-144) on the GPU, in
  * place: pcm host [n_streams][frame_size*channels], softclip_mem host [n_streams][channels] (zeros for a new stream). */

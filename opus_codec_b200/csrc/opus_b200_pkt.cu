@@ -86,6 +86,54 @@ int32_t ob_packet_parse(const uint8_t *data, int32_t len, uint8_t *out_toc, int3
     return n;
 }
 
+// ---- opus_multistream_packet_pad / _unpad (multistream_packet_pad / _unpad, src/packet.rs:253-290; repacketizer.c:355-464) ----
+int32_t ob_multistream_packet_pad(uint8_t *data, int32_t len, int32_t new_len, int32_t nb_streams)
+{
+    if (!data || len < 1) return OB_BAD_ARG;
+    if (len == new_len) return OB_OK;
+    if (len > new_len) return OB_BAD_ARG;
+    const int32_t amount = new_len - len;
+    for (int s = 0; s < nb_streams - 1; s++) {               // seek to the last stream: the others are self-delimited
+        if (len <= 0) return OB_INVALID_PACKET;
+        uint8_t toc;
+        int16_t size[48];
+        int packet_offset = 0;
+        const int count = ob_rp_parse(data, len, 1, &toc, nullptr, size, nullptr, &packet_offset, nullptr, nullptr);
+        if (count < 0) return count;
+        data += packet_offset;
+        len -= packet_offset;
+    }
+    return ob_packet_pad(data, len, len + amount);
+}
+int32_t ob_multistream_packet_unpad(uint8_t *data, int32_t len, int32_t nb_streams)
+{
+    if (!data || len < 1) return OB_BAD_ARG;
+    uint8_t *dst = data;
+    int32_t dst_len = 0;
+    for (int s = 0; s < nb_streams; s++) {
+        const int self_delimited = s != nb_streams - 1;
+        if (len <= 0) return OB_INVALID_PACKET;
+        uint8_t toc;
+        int16_t size[48];
+        int packet_offset = 0;
+        int ret = ob_rp_parse(data, len, self_delimited, &toc, nullptr, size, nullptr, &packet_offset, nullptr, nullptr);
+        if (ret < 0) return ret;
+        ObRepack rp;
+        ob_repack_init(&rp);
+        ret = ob_repack_cat(&rp, data, packet_offset, self_delimited);
+        if (ret < 0) return ret;
+        for (int i = 0; i < rp.nb_frames; i++) { rp.padding_len[i] = 0; rp.paddings[i] = nullptr; }       // padding and extensions are dropped
+        ObExt none;
+        ret = ob_repack_out_range(ObRpLanes1(), &rp, 0, rp.nb_frames, dst, len, self_delimited, 0, &none, 0);
+        if (ret < 0) return ret;
+        dst_len += ret;
+        dst += ret;
+        data += packet_offset;
+        len -= packet_offset;
+    }
+    return dst_len;
+}
+
 }  // extern "C"
 
 // ---- batched: each `group` consecutive packets of a stream -> one packet ----------------------------------------------------------

@@ -61,6 +61,27 @@ def packet_unpad(packet):
     return bytes(data[:n])
 
 
+def multistream_packet_pad(packet, new_len, nb_streams):
+    """-> the multistream packet padded to new_len bytes (multistream_packet_pad, src/packet.rs:253-272)."""
+    if new_len < len(packet):
+        raise OpusError(BAD_ARG)
+    data = (C.c_uint8 * max(1, new_len))()
+    C.memmove(data, bytes(packet), len(packet))
+    r = _lib.lib().ob_multistream_packet_pad(data, len(packet), new_len, nb_streams)
+    if r != 0:
+        raise OpusError(r)
+    return bytes(data[:new_len])
+
+
+def multistream_packet_unpad(packet, nb_streams):
+    """-> the multistream packet without padding (multistream_packet_unpad, src/packet.rs:277-290)."""
+    data = _buf(packet)
+    n = _lib.lib().ob_multistream_packet_unpad(data, len(packet), nb_streams)
+    if n < 0:
+        raise OpusError(n)
+    return bytes(data[:n])
+
+
 class Repacketizer:
     """Repacketizer of the crate (src/repacketizer.rs): push() packets of one configuration, out()/out_range() merged packets.
     Pushed packets are kept alive by this object (libopus references them)."""

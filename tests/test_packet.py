@@ -303,3 +303,52 @@ def test_self_delimited_framing_matches_reference_internals(ref):
             assert list(sz0[:n0]) == list(sz1[:n0]) and [frames[i] - base for i in range(n0)] == list(offs[:n0])
     assert {"ok", -4} <= seen
     os.remove(so)
+
+
+def test_multistream_packet_pad_unpad_match_reference(ref):
+    """multistream_packet_pad / _unpad (src/packet.rs:253-290): 2- and 3-stream packets built with the reference's self-delimited output."""
+    from opus_codec_b200.packet import multistream_packet_pad, multistream_packet_unpad
+    from opus_codec_b200.batch import OpusError
+    vp, i32 = C.c_void_p, C.c_int32
+    ref.opus_repacketizer_out_range_impl.argtypes = [vp, C.c_int, C.c_int, vp, i32, C.c_int, C.c_int, vp, C.c_int]
+    ref.opus_repacketizer_out_range_impl.restype = i32
+    ref.opus_multistream_packet_pad.argtypes = [vp, i32, i32, C.c_int]; ref.opus_multistream_packet_pad.restype = C.c_int
+    ref.opus_multistream_packet_unpad.argtypes = [vp, i32, C.c_int]; ref.opus_multistream_packet_unpad.restype = i32
+
+    def self_delimited(p):
+        rp = ref.opus_repacketizer_create()
+        b = _buf(p)
+        assert ref.opus_repacketizer_cat(rp, b, len(p)) == 0
+        out = (C.c_uint8 * (len(p) + 4))()
+        n = ref.opus_repacketizer_out_range_impl(rp, 0, ref.opus_repacketizer_get_nb_frames(rp), out, len(p) + 4, 1, 0, None, 0)
+        ref.opus_repacketizer_destroy(rp)
+        assert n > 0
+        return bytes(out[:n])
+
+    g1, g2 = load_golden("cfg3_stereo_20ms_96k_cbr"), load_golden("cfg2_mono_20ms_64k_cbr")
+    a = [bytes(g1["packets"][0][f, :g1["lens"][0][f]]) for f in range(4)]
+    m = [bytes(g2["packets"][0][f, :g2["lens"][0][f]]) for f in range(4)]
+    streams = [([a[0], m[0]], 2), ([repacketize(a[:2], 3, pad=30), m[1]], 2), ([a[1], repacketize(m[:3], 3, pad=5), m[3]], 3),
+               ([with_padding(a[2:3], ext_padding()), a[3]], 2)]
+    for parts, nb in streams:
+        ms = b"".join(self_delimited(p) for p in parts[:-1]) + parts[-1]
+        for new_len in (len(ms), len(ms) + 1, len(ms) + 2, len(ms) + 77, len(ms) + 300):
+            d = _buf(ms, new_len)
+            r = ref.opus_multistream_packet_pad(d, len(ms), new_len, nb)
+            assert r == 0
+            padded = multistream_packet_pad(ms, new_len, nb)
+            assert padded == bytes(d[:new_len])
+            d2 = _buf(padded)
+            n = ref.opus_multistream_packet_unpad(d2, len(padded), nb)
+            assert n > 0 and multistream_packet_unpad(padded, nb) == bytes(d2[:n])
+        d = _buf(ms)
+        n = ref.opus_multistream_packet_unpad(d, len(ms), nb)
+        assert multistream_packet_unpad(ms, nb) == bytes(d[:n])
+        # wrong stream count: same error as the reference
+        d = _buf(ms)
+        n = ref.opus_multistream_packet_unpad(d, len(ms), nb + 2)
+        try:
+            got = multistream_packet_unpad(ms, nb + 2)
+            assert n > 0 and got == bytes(d[:n])
+        except OpusError as e:
+            assert e.code == n
