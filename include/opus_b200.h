@@ -217,6 +217,9 @@ int32_t ob_packet_get_nb_channels(const uint8_t *packet);
 int32_t ob_packet_get_samples_per_frame(const uint8_t *packet, int32_t fs);
 int32_t ob_packet_get_bandwidth(const uint8_t *packet);
 int32_t ob_packet_get_nb_frames(const uint8_t *packet, int32_t len);
+/* opus_packet_get_nb_samples / opus_packet_has_lbrr (packet_nb_samples / packet_has_lbrr, src/packet.rs:72-120; opus/src/opus_decoder.c:1119-1162). */
+int32_t ob_packet_get_nb_samples(const uint8_t *packet, int32_t len, int32_t fs);
+int32_t ob_packet_has_lbrr(const uint8_t *packet, int32_t len);
 
 /* opus_packet_parse (src/bindings.rs; packet_parse src/packet.rs:162-215; opus/src/opus.c:194-360): returns the frame count (1..48) or an
  * OPUS_* code; sizes[i] / frame_offsets[i] (optional; offsets from `packet`) describe frame i; *payload_offset = offset of frame 0. */

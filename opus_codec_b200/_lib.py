@@ -22,7 +22,7 @@ SYMBOLS = [
     "ob_decode_float_multi_async", "ob_decoder_wait", "ob_decode", "ob_decode_multi", "ob_decode_multi_async", "ob_encode", "ob_encode_multi", "ob_decoder_set_gain", "ob_decoder_get_gain", "ob_decoder_set_phase_inversion_disabled", "ob_decoder_get_phase_inversion_disabled", "ob_decoder_get_pitch", "ob_decoder_set_decode_fec", "ob_decoder_get_decode_fec",
     "ob_packet_get_nb_channels", "ob_packet_get_samples_per_frame", "ob_packet_get_bandwidth", "ob_packet_get_nb_frames",
     "ob_version", "ob_strerror",
-    "ob_packet_parse", "ob_packet_pad", "ob_packet_unpad", "ob_multistream_packet_pad", "ob_multistream_packet_unpad", "ob_repacketizer_create", "ob_repacketizer_destroy", "ob_repacketizer_init", "ob_repacketizer_cat",
+    "ob_packet_get_nb_samples", "ob_packet_has_lbrr", "ob_packet_parse", "ob_packet_pad", "ob_packet_unpad", "ob_multistream_packet_pad", "ob_multistream_packet_unpad", "ob_repacketizer_create", "ob_repacketizer_destroy", "ob_repacketizer_init", "ob_repacketizer_cat",
     "ob_repacketizer_get_nb_frames", "ob_repacketizer_out_range", "ob_repacketizer_out", "ob_repacketize_batch", "ob_repacketize_batch_device", "ob_pcm_soft_clip_batch",
     "ob_encoder_create", "ob_encoder_destroy", "ob_encode_float", "ob_encode_float_multi", "ob_encode_float_device",
     "ob_encoder_set_bitrate", "ob_encoder_get_bitrate", "ob_encoder_set_complexity", "ob_encoder_get_complexity",
@@ -112,6 +112,8 @@ def lib():
     L.ob_decoder_get_pitch.argtypes = [vp, vp]; L.ob_decoder_get_pitch.restype = i32
     L.ob_decoder_set_decode_fec.argtypes = [vp, i32]; L.ob_decoder_set_decode_fec.restype = i32
     L.ob_decoder_get_decode_fec.argtypes = [vp, vp]; L.ob_decoder_get_decode_fec.restype = i32
+    L.ob_packet_get_nb_samples.argtypes = [vp, i32, i32]; L.ob_packet_get_nb_samples.restype = i32
+    L.ob_packet_has_lbrr.argtypes = [vp, i32]; L.ob_packet_has_lbrr.restype = i32
     L.ob_packet_parse.argtypes = [vp, i32, vp, vp, vp, vp]; L.ob_packet_parse.restype = i32
     L.ob_packet_pad.argtypes = [vp, i32, i32]; L.ob_packet_pad.restype = i32
     L.ob_packet_unpad.argtypes = [vp, i32]; L.ob_packet_unpad.restype = i32

@@ -86,6 +86,31 @@ int32_t ob_packet_parse(const uint8_t *data, int32_t len, uint8_t *out_toc, int3
     return n;
 }
 
+// ---- opus_packet_get_nb_samples / opus_packet_has_lbrr (packet_nb_samples / packet_has_lbrr, src/packet.rs:72-120; opus_decoder.c:1119-1162) ----
+int32_t ob_packet_get_nb_samples(const uint8_t *packet, int32_t len, int32_t fs)
+{
+    if (!packet || len < 1) return OB_BAD_ARG;
+    const int code = packet[0] & 3;
+    const int count = code == 0 ? 1 : code != 3 ? 2 : (len < 2 ? OB_INVALID_PACKET : (packet[1] & 0x3F));
+    if (count < 0) return count;
+    const int samples = count * ob_rp_samples_per_frame(packet[0], fs);
+    return samples * 25 > fs * 3 ? OB_INVALID_PACKET : samples;             // more than 120 ms
+}
+int32_t ob_packet_has_lbrr(const uint8_t *packet, int32_t len)
+{
+    if (!packet || len < 1) return OB_BAD_ARG;
+    if (packet[0] & 0x80) return 0;                                           // CELT-only packets carry no LBRR
+    const int frame_size = ob_rp_samples_per_frame(packet[0], 48000), nb_frames = frame_size > 960 ? frame_size / 960 : 1;
+    const uint8_t *frames[48];
+    int16_t size[48];
+    const int ret = ob_rp_parse(packet, len, 0, nullptr, frames, size, nullptr, nullptr, nullptr, nullptr);
+    if (ret <= 0) return ret;
+    if (frames[0] >= packet + len) return 0;                                  // an empty first frame at the very end of the buffer: nothing to look at
+    int lbrr = (frames[0][0] >> (7 - nb_frames)) & 1;
+    if (packet[0] & 4) lbrr = lbrr || ((frames[0][0] >> (6 - 2 * nb_frames)) & 1);
+    return lbrr;
+}
+
 // ---- opus_multistream_packet_pad / _unpad (multistream_packet_pad / _unpad, src/packet.rs:253-290; repacketizer.c:355-464) ----
 int32_t ob_multistream_packet_pad(uint8_t *data, int32_t len, int32_t new_len, int32_t nb_streams)
 {

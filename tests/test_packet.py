@@ -352,3 +352,39 @@ def test_multistream_packet_pad_unpad_match_reference(ref):
             assert n > 0 and got == bytes(d[:n])
         except OpusError as e:
             assert e.code == n
+
+
+def test_packet_nb_samples_and_has_lbrr_match_reference(ref):
+    """packet_nb_samples / packet_has_lbrr (src/packet.rs:72-120) on CELT, SILK and hybrid packets (the latter two from the reference's VOIP
+    encoder with in-band FEC on) and on random TOCs."""
+    from opus_codec_b200 import _lib
+    from oracle import refpy
+    L = _lib.lib()
+    ref.opus_packet_get_nb_samples.argtypes = [C.c_void_p, C.c_int32, C.c_int32]; ref.opus_packet_get_nb_samples.restype = C.c_int
+    ref.opus_packet_has_lbrr.argtypes = [C.c_void_p, C.c_int32]; ref.opus_packet_has_lbrr.restype = C.c_int
+    pkts = [p for p in sample_packets() if len(p) < 4000]
+    # SILK / hybrid packets with LBRR: VOIP, 24 kb/s, FEC on, 20 % loss
+    u8p, i32p, u32p, f32p = C.POINTER(C.c_ubyte), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_float)
+    ref.ref_encode_stream.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, i32p, u32p]
+    from opus_codec_b200 import synth
+    for ch, fs in ((1, 960), (2, 960), (1, 2880)):
+        pcm = np.ascontiguousarray(synth.stream_pcm(2, 48000, ch))
+        nf = pcm.size // (fs * ch)
+        out = np.zeros((nf, 600), np.uint8); lens = np.zeros(nf, np.int32); rg = np.zeros(nf, np.uint32)
+        ref.ref_set_encoder_force_celt(0); ref.ref_set_encoder_extras2(3001, 0, 0, 0, 1, 0, 20)
+        try:
+            assert ref.ref_encode_stream(pcm.ctypes.data_as(f32p), nf, fs, ch, 2048, 24000, 1, 5, out.ctypes.data_as(u8p), 600, lens.ctypes.data_as(i32p), rg.ctypes.data_as(u32p)) == 0
+        finally:
+            ref.ref_set_encoder_force_celt(1); ref.ref_set_encoder_extras2(0, 0, 0, 0, 0, 0, 0)
+        pkts += [bytes(out[f, :lens[f]]) for f in range(nf)]
+    rng = np.random.default_rng(9)
+    pkts += [bytes(rng.integers(0, 256, int(rng.integers(2, 30)), dtype=np.uint8)) for _ in range(2000)]
+    lbrr_seen = set()
+    for p in pkts:
+        b = _buf(p, len(p) + 1)                                 # one zero byte behind: the reference peeks at frames[0][0] even when that frame is empty
+        for fs in (48000, 16000, 8000):
+            assert ref.opus_packet_get_nb_samples(b, len(p), fs) == L.ob_packet_get_nb_samples(bytes(p), len(p), fs)
+        a = ref.opus_packet_has_lbrr(b, len(p))
+        assert a == L.ob_packet_has_lbrr(bytes(p), len(p)), p[:6].hex()
+        lbrr_seen.add(a)
+    assert {0, 1} <= lbrr_seen
