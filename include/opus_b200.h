@@ -203,6 +203,8 @@ int32_t ob_encoder_set_expert_frame_duration(ObEncoder *enc, int32_t duration);
 int32_t ob_encoder_get_expert_frame_duration(ObEncoder *enc, int32_t *value);
 int32_t ob_encoder_get_lookahead(ObEncoder *enc, int32_t *value);
 int32_t ob_encoder_in_dtx(ObEncoder *enc, int32_t *out);
+/* OPUS_GET_BANDWIDTH (Encoder::bandwidth, src/encoder.rs): the bandwidth (1101..1105) each stream's last packet was coded with; 1105 before the first. */
+int32_t ob_encoder_get_bandwidth(ObEncoder *enc, int32_t *out);
 /* OPUS_GET_FINAL_RANGE (Encoder::final_range src/encoder.rs:411-419) and OPUS_RESET_STATE (Encoder::reset :689-698). */
 int32_t ob_encoder_final_range(ObEncoder *enc, uint32_t *out);
 int32_t ob_encoder_reset(ObEncoder *enc, const int32_t *idx, int32_t n);

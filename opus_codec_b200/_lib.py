@@ -29,7 +29,7 @@ SYMBOLS = [
     "ob_encoder_set_vbr", "ob_encoder_get_vbr", "ob_encoder_set_vbr_constraint", "ob_encoder_get_vbr_constraint",
     "ob_encoder_set_max_bandwidth", "ob_encoder_set_bandwidth", "ob_encoder_set_force_channels",
     "ob_encoder_set_packet_loss_perc", "ob_encoder_set_lsb_depth", "ob_encoder_final_range", "ob_encoder_reset",
-    "ob_encoder_get_max_bandwidth", "ob_encoder_get_force_channels", "ob_encoder_get_packet_loss_perc", "ob_encoder_get_lsb_depth", "ob_encoder_set_signal", "ob_encoder_get_signal", "ob_encoder_set_prediction_disabled", "ob_encoder_get_prediction_disabled", "ob_encoder_set_phase_inversion_disabled", "ob_encoder_get_phase_inversion_disabled", "ob_encoder_set_dtx", "ob_encoder_get_dtx", "ob_encoder_set_inband_fec", "ob_encoder_get_inband_fec", "ob_encoder_set_expert_frame_duration", "ob_encoder_get_expert_frame_duration", "ob_encoder_get_lookahead", "ob_encoder_in_dtx",
+    "ob_encoder_get_max_bandwidth", "ob_encoder_get_force_channels", "ob_encoder_get_packet_loss_perc", "ob_encoder_get_lsb_depth", "ob_encoder_set_signal", "ob_encoder_get_signal", "ob_encoder_set_prediction_disabled", "ob_encoder_get_prediction_disabled", "ob_encoder_set_phase_inversion_disabled", "ob_encoder_get_phase_inversion_disabled", "ob_encoder_set_dtx", "ob_encoder_get_dtx", "ob_encoder_set_inband_fec", "ob_encoder_get_inband_fec", "ob_encoder_set_expert_frame_duration", "ob_encoder_get_expert_frame_duration", "ob_encoder_get_lookahead", "ob_encoder_in_dtx", "ob_encoder_get_bandwidth",
     "ob_encoder_streams", "ob_encoder_channels", "ob_encoder_kernel_ms", "ob_encoder_launches", "ob_encoder_cuda_stream",
 ]
 
@@ -112,6 +112,7 @@ def lib():
     L.ob_decoder_get_pitch.argtypes = [vp, vp]; L.ob_decoder_get_pitch.restype = i32
     L.ob_decoder_set_decode_fec.argtypes = [vp, i32]; L.ob_decoder_set_decode_fec.restype = i32
     L.ob_decoder_get_decode_fec.argtypes = [vp, vp]; L.ob_decoder_get_decode_fec.restype = i32
+    L.ob_encoder_get_bandwidth.argtypes = [vp, vp]; L.ob_encoder_get_bandwidth.restype = i32
     L.ob_packet_get_nb_samples.argtypes = [vp, i32, i32]; L.ob_packet_get_nb_samples.restype = i32
     L.ob_packet_has_lbrr.argtypes = [vp, i32]; L.ob_packet_has_lbrr.restype = i32
     L.ob_packet_parse.argtypes = [vp, i32, vp, vp, vp, vp]; L.ob_packet_parse.restype = i32

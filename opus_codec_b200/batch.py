@@ -283,6 +283,12 @@ class BatchEncoder:
     def expert_frame_duration(self): return self._get(self._L.ob_encoder_get_expert_frame_duration)
     def lookahead(self): return self._get(self._L.ob_encoder_get_lookahead)
 
+    def bandwidth(self):
+        """OPUS_GET_BANDWIDTH per stream (Encoder::bandwidth): the bandwidth of each stream's last packet."""
+        out = np.zeros(self.n_streams, np.int32)
+        _check(self._L.ob_encoder_get_bandwidth(self._h, _vp(out)))
+        return out
+
     def in_dtx(self):
         out = np.zeros(self.n_streams, np.int32)
         _check(self._L.ob_encoder_in_dtx(self._h, _vp(out)))

@@ -119,10 +119,12 @@ __global__ void ob_k_enc_gather(const ObEncStream *streams, uint32_t *ranges, in
     if (s < S) ranges[s] = streams[s].st.final_range;
 }
 
-__global__ void ob_k_enc_gather_dtx(const ObEncStream *streams, uint32_t *out, int S)
+__global__ void ob_k_enc_gather_dtx(const ObEncStream *streams, uint32_t *out, int S, int what)
 {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < S) out[s] = streams[s].os.nb_no_activity_ms_Q1 >= 10 * 20 * 2;          // OPUS_GET_IN_DTX, "DTX determined by Opus" (opus_encoder.c:3038-3042)
+    if (s >= S) return;
+    if (what == 0) out[s] = streams[s].os.nb_no_activity_ms_Q1 >= 10 * 20 * 2;       // OPUS_GET_IN_DTX, "DTX determined by Opus" (opus_encoder.c:3038-3042)
+    else out[s] = (uint32_t)streams[s].os.bandwidth;                                  // OPUS_GET_BANDWIDTH: st->bandwidth of the last packet (:2700-2708)
 }
 
 struct ObEncoder {
@@ -440,7 +442,18 @@ int32_t ob_encoder_in_dtx(ObEncoder *e, int32_t *out)
     if (!e || !out) return OB_BAD_ARG;
     OB_CUDA(cudaSetDevice(e->device));
     if (!e->cfg.use_dtx) { for (int s = 0; s < e->S; s++) out[s] = 0; return OB_OK; }
-    ob_k_enc_gather_dtx<<<(e->S + 127) / 128, 128, 0, e->stream>>>(e->d_streams, e->d_ranges, e->S);
+    ob_k_enc_gather_dtx<<<(e->S + 127) / 128, 128, 0, e->stream>>>(e->d_streams, e->d_ranges, e->S, 0);
+    e->launches += 1;
+    OB_CUDA(cudaMemcpyAsync(out, e->d_ranges, sizeof(uint32_t) * e->S, cudaMemcpyDeviceToHost, e->stream));
+    OB_CUDA(cudaStreamSynchronize(e->stream));
+    return OB_OK;
+}
+
+int32_t ob_encoder_get_bandwidth(ObEncoder *e, int32_t *out)
+{
+    if (!e || !out) return OB_BAD_ARG;
+    OB_CUDA(cudaSetDevice(e->device));
+    ob_k_enc_gather_dtx<<<(e->S + 127) / 128, 128, 0, e->stream>>>(e->d_streams, e->d_ranges, e->S, 1);
     e->launches += 1;
     OB_CUDA(cudaMemcpyAsync(out, e->d_ranges, sizeof(uint32_t) * e->S, cudaMemcpyDeviceToHost, e->stream));
     OB_CUDA(cudaStreamSynchronize(e->stream));

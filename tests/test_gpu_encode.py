@@ -272,6 +272,11 @@ def test_encoder_ctls_on_gpu_match_reference(have_ref):
             assert enc.lsb_depth() == 24 and enc.max_bandwidth() == 1105 and enc.force_channels() == -1000 and enc.inband_fec() == 0
             out, lens, rng = enc.encode_float_multi(pcm.reshape(S, F, fs * ch), fs)
             in_dtx = enc.in_dtx()
+            bw = enc.bandwidth()
+            for s_ in range(S):                                  # OPUS_GET_BANDWIDTH == the bandwidth in the TOC of the stream's last coded packet
+                last = [f for f in range(F) if lens[s_, f] > 1][-1]
+                toc_bw = 1102 + ((int(out[s_, last, 0]) >> 5) & 3)
+                assert bw[s_] == (1101 if toc_bw == 1102 else toc_bw) or lens[s_, F - 1] == 1
         L.ref_set_encoder_extras2(extras[0], extras[1], extras[2], extras[3], extras[4], 0, extras[5])
         try:
             same = total = 0
