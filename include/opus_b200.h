@@ -118,6 +118,7 @@ int32_t ob_decoder_get_decode_fec(ObDecoder *dec, int32_t *value);
  * the most recent call (symbols, bands, synthesis), kernel launches issued so far. */
 int32_t ob_decoder_streams(const ObDecoder *dec);
 int32_t ob_decoder_channels(const ObDecoder *dec);
+int32_t ob_decoder_sample_rate(const ObDecoder *dec);       /* OPUS_GET_SAMPLE_RATE (Decoder::get_sample_rate, src/decoder.rs) */
 int32_t ob_decoder_kernel_ms(ObDecoder *dec, float ms[3]);
 int64_t ob_decoder_launches(const ObDecoder *dec);
 void *ob_decoder_cuda_stream(ObDecoder *dec);
@@ -210,6 +211,7 @@ int32_t ob_encoder_final_range(ObEncoder *enc, uint32_t *out);
 int32_t ob_encoder_reset(ObEncoder *enc, const int32_t *idx, int32_t n);
 int32_t ob_encoder_streams(const ObEncoder *enc);
 int32_t ob_encoder_channels(const ObEncoder *enc);
+int32_t ob_encoder_sample_rate(const ObEncoder *enc);       /* OPUS_GET_SAMPLE_RATE (Encoder::sample_rate) */
 int32_t ob_encoder_kernel_ms(ObEncoder *enc, float *ms);
 int64_t ob_encoder_launches(const ObEncoder *enc);
 void *ob_encoder_cuda_stream(ObEncoder *enc);

@@ -18,7 +18,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
 SYMBOLS = [
     "ob_decoder_create", "ob_decoder_destroy", "ob_decode_float", "ob_decode_float_multi", "ob_decode_float_device",
     "ob_decoder_final_range", "ob_decoder_reset", "ob_decoder_last_packet_duration", "ob_decoder_streams",
-    "ob_decoder_channels", "ob_decoder_kernel_ms", "ob_decoder_launches", "ob_decoder_cuda_stream",
+    "ob_decoder_channels", "ob_decoder_sample_rate", "ob_encoder_sample_rate", "ob_decoder_kernel_ms", "ob_decoder_launches", "ob_decoder_cuda_stream",
     "ob_decode_float_multi_async", "ob_decoder_wait", "ob_decode", "ob_decode_multi", "ob_decode_multi_async", "ob_encode", "ob_encode_multi", "ob_decoder_set_gain", "ob_decoder_get_gain", "ob_decoder_set_phase_inversion_disabled", "ob_decoder_get_phase_inversion_disabled", "ob_decoder_get_pitch", "ob_decoder_set_decode_fec", "ob_decoder_get_decode_fec",
     "ob_packet_get_nb_channels", "ob_packet_get_samples_per_frame", "ob_packet_get_bandwidth", "ob_packet_get_nb_frames",
     "ob_version", "ob_strerror",
@@ -113,6 +113,8 @@ def lib():
     L.ob_decoder_set_decode_fec.argtypes = [vp, i32]; L.ob_decoder_set_decode_fec.restype = i32
     L.ob_decoder_get_decode_fec.argtypes = [vp, vp]; L.ob_decoder_get_decode_fec.restype = i32
     L.ob_encoder_get_bandwidth.argtypes = [vp, vp]; L.ob_encoder_get_bandwidth.restype = i32
+    L.ob_decoder_sample_rate.argtypes = [vp]; L.ob_decoder_sample_rate.restype = i32
+    L.ob_encoder_sample_rate.argtypes = [vp]; L.ob_encoder_sample_rate.restype = i32
     L.ob_packet_get_nb_samples.argtypes = [vp, i32, i32]; L.ob_packet_get_nb_samples.restype = i32
     L.ob_packet_has_lbrr.argtypes = [vp, i32]; L.ob_packet_has_lbrr.restype = i32
     L.ob_packet_parse.argtypes = [vp, i32, vp, vp, vp, vp]; L.ob_packet_parse.restype = i32

@@ -692,6 +692,7 @@ int32_t ob_decoder_get_decode_fec(ObDecoder *d, int32_t *v) { if (!d || !v) retu
 
 int32_t ob_decoder_streams(const ObDecoder *d) { return d ? d->S : OB_BAD_ARG; }
 int32_t ob_decoder_channels(const ObDecoder *d) { return d ? d->CC : OB_BAD_ARG; }
+int32_t ob_decoder_sample_rate(const ObDecoder *d) { return d ? 48000 / d->ds : OB_BAD_ARG; }          // OPUS_GET_SAMPLE_RATE
 int64_t ob_decoder_launches(const ObDecoder *d) { return d ? d->launches : 0; }
 void *ob_decoder_cuda_stream(ObDecoder *d) { return d ? (void *)d->stream : nullptr; }
 int32_t ob_decoder_kernel_ms(ObDecoder *d, float ms[3])

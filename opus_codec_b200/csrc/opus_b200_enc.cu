@@ -462,6 +462,7 @@ int32_t ob_encoder_get_bandwidth(ObEncoder *e, int32_t *out)
 
 int32_t ob_encoder_streams(const ObEncoder *e) { return e ? e->S : OB_BAD_ARG; }
 int32_t ob_encoder_channels(const ObEncoder *e) { return e ? e->CC : OB_BAD_ARG; }
+int32_t ob_encoder_sample_rate(const ObEncoder *e) { return e ? 48000 : OB_BAD_ARG; }                   // OPUS_GET_SAMPLE_RATE
 int64_t ob_encoder_launches(const ObEncoder *e) { return e ? e->launches : 0; }
 void *ob_encoder_cuda_stream(ObEncoder *e) { return e ? (void *)e->stream : nullptr; }
 int32_t ob_encoder_kernel_ms(ObEncoder *e, float *ms)

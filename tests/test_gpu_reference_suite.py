@@ -66,7 +66,7 @@ def test_decoder_control_roundtrip():
         assert decoder.phase_inversion_disabled()
         decoder.set_phase_inversion_disabled(False)
         assert not decoder.phase_inversion_disabled()
-        assert decoder.sample_rate == 48000
+        assert decoder.sample_rate == 48000 and decoder._L.ob_decoder_sample_rate(decoder._h) == 48000      # get_sample_rate
         assert (decoder.last_packet_duration() == 0).all()       # before any decode
 
 
