@@ -371,39 +371,49 @@ OB_DEV void ob_reconstruct_bands(const G &g, const ObFrameIR *ir, uint32_t seed_
         const float *lb1 = br.eff_lowband >= 0 ? norm + br.eff_lowband : nullptr;
         const float *lb2 = br.eff_lowband >= 0 ? norm2 + br.eff_lowband : nullptr;
         float *lo1 = last ? nullptr : norm + boff, *lo2 = last ? nullptr : norm2 + boff;
-        if (br.mode == OB_BAND_MONO) {
-            ob_band_call(g, sh, la, na, boff, Xb, Nb, Bfr, tf_change, lb1, lo1, seed_in, step, spread);
-        } else if (br.mode == OB_BAND_DUAL) {
-            ob_band_call(g, sh, la, na, boff, Xb, Nb, Bfr, tf_change, lb1, lo1, seed_in, step, spread);
-            ob_band_call(g, sh, lbv, nb, N + boff, Yb, Nb, Bfr, tf_change, lb2, lo2, seed_in, step, spread);
-        } else if (Nb == 1) {                                        // quant_band_n1 with Y (bands.c:904-937)
+        // One ob_band_call site for every mode (the loop is kept rolled): the call inlines ~5 k instructions, and with one copy per mode
+        // `no_instruction` was the band kernel's largest stall on stereo frames (8.9 cycles per issued instruction, profiles/r01n_*).
+        const int mode = SH::channels == 1 ? (int)OB_BAND_MONO : (int)br.mode;       // mono-sized instantiation: mono frames only
+        if (mode != OB_BAND_MONO && mode != OB_BAND_DUAL && Nb == 1) {                // quant_band_n1 with Y (bands.c:904-937)
             ob_fill_leaf(g, la[0], Xb, 0, nullptr, seed_in, step, spread);
             ob_fill_leaf(g, la[1], Yb, 0, nullptr, seed_in, step, spread);
             if (lo1 && g.lane == 0) lo1[0] = Xb[0];
             g.sync();
-        } else if (br.mode == OB_BAND_JOINT_N2) {                    // bands.c:1273-1323
-            const int c = (br.flags >> 1) & 1, sign = 1 - 2 * ((br.flags >> 2) & 1);
-            float *x2 = c ? Yb : Xb, *y2 = c ? Xb : Yb;
-            ob_band_call(g, sh, la, na, c ? N + boff : boff, x2, Nb, Bfr, tf_change, lb1, lo1, seed_in, step, spread);
-            if (g.lane == 0) {
-                const float mid = (1.f / 32768) * br.imid, side = (1.f / 32768) * br.iside;
-                y2[0] = -sign * x2[1];
-                y2[1] = sign * x2[0];
-                Xb[0] = mid * Xb[0]; Xb[1] = mid * Xb[1];
-                Yb[0] = side * Yb[0]; Yb[1] = side * Yb[1];
-                float t = Xb[0]; Xb[0] = t - Yb[0]; Yb[0] = t + Yb[0];
-                t = Xb[1]; Xb[1] = t - Yb[1]; Yb[1] = t + Yb[1];
-                if (br.flags & 1) { Yb[0] = -Yb[0]; Yb[1] = -Yb[1]; }
+        } else {
+            // MONO: X.  DUAL: X then Y, each with its own folding source.  JOINT_N2 (bands.c:1273-1323): x2 only, which is Y when c is set.
+            // JOINT, N > 2 (bands.c:1324-1381): mid on X with folding, side on Y without.
+            const int c = mode == OB_BAND_JOINT_N2 ? (br.flags >> 1) & 1 : 0;
+            const int ncall = (mode == OB_BAND_DUAL || mode == OB_BAND_JOINT) ? 2 : 1;
+#ifdef __CUDACC__
+#pragma unroll 1
+#endif
+            for (int q = 0; q < ncall; q++) {
+                const int onY = q | c;
+                const float *lbq = q ? (mode == OB_BAND_DUAL ? lb2 : nullptr) : lb1;
+                float *loq = q ? (mode == OB_BAND_DUAL ? lo2 : nullptr) : lo1;
+                ob_band_call(g, sh, q ? lbv : la, q ? nb : na, onY ? N + boff : boff, onY ? Yb : Xb, Nb, Bfr, tf_change, lbq, loq, seed_in, step, spread);
             }
-            g.sync();
-        } else {                                                     // joint stereo, N > 2 (bands.c:1324-1381)
-            const float mid = (1.f / 32768) * br.imid;
-            ob_band_call(g, sh, la, na, boff, Xb, Nb, Bfr, tf_change, lb1, lo1, seed_in, step, spread);
-            ob_band_call(g, sh, lbv, nb, N + boff, Yb, Nb, Bfr, tf_change, nullptr, nullptr, seed_in, step, spread);
-            ob_stereo_merge(g, Xb, Yb, mid, Nb);
-            if (br.flags & 1) {
-                for (int j = g.lane; j < Nb; j += g.n) Yb[j] = -Yb[j];
+            if (mode == OB_BAND_JOINT_N2) {
+                const int sign = 1 - 2 * ((br.flags >> 2) & 1);
+                float *x2 = c ? Yb : Xb, *y2 = c ? Xb : Yb;
+                if (g.lane == 0) {
+                    const float mid = (1.f / 32768) * br.imid, side = (1.f / 32768) * br.iside;
+                    y2[0] = -sign * x2[1];
+                    y2[1] = sign * x2[0];
+                    Xb[0] = mid * Xb[0]; Xb[1] = mid * Xb[1];
+                    Yb[0] = side * Yb[0]; Yb[1] = side * Yb[1];
+                    float t = Xb[0]; Xb[0] = t - Yb[0]; Yb[0] = t + Yb[0];
+                    t = Xb[1]; Xb[1] = t - Yb[1]; Yb[1] = t + Yb[1];
+                    if (br.flags & 1) { Yb[0] = -Yb[0]; Yb[1] = -Yb[1]; }
+                }
                 g.sync();
+            } else if (mode == OB_BAND_JOINT) {
+                const float mid = (1.f / 32768) * br.imid;
+                ob_stereo_merge(g, Xb, Yb, mid, Nb);
+                if (br.flags & 1) {
+                    for (int j = g.lane; j < Nb; j += g.n) Yb[j] = -Yb[j];
+                    g.sync();
+                }
             }
         }
         for (int j = g.lane; j < Nb; j += g.n) Xout[boff + j] = Xb[j];
