@@ -197,8 +197,11 @@ OB_DEV void ob_exp_rotation_inv(const G &g, float *X, int len, int stride, int K
         while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
     }
     len = len / stride;
-    if (stride2) ob_rot_pass(g, X, stride, len, stride2, s, c);
-    ob_rot_pass(g, X, stride, len, 1, c, s);
+    // one inlined copy of the pass for both strides (code size: see ob_reconstruct_bands)
+#ifdef __CUDACC__
+#pragma unroll 1
+#endif
+    for (int p = stride2 ? 0 : 1; p < 2; p++) ob_rot_pass(g, X, stride, len, p ? 1 : stride2, p ? c : s, p ? s : c);
 }
 
 // Per-warp shared-memory working set of the band-reconstruction stage.  CH = 1: room for mono frames only (5.3 KB instead of 8.5 KB per
@@ -299,8 +302,15 @@ OB_DEV void ob_band_call(const G &g, SH &sh, const ObLeaf *leaves, int leaf_cnt,
 
     if (B0 > 1) ob_hadamard(g, Xb, tmp, N_B >> recombine, B0 << recombine, longBlocks, 1);
     N_B = N_B0; B = B0;
-    for (int k = 0; k < time_divide; k++) { B >>= 1; N_B <<= 1; ob_haar1(g, Xb, N_B, B); }
-    for (int k = 0; k < recombine; k++) ob_haar1(g, Xb, N0 >> k, 1 << k);
+#ifdef __CUDACC__
+#pragma unroll 1
+#endif
+    for (int k = 0; k < time_divide + recombine; k++) {              // undo the time divisions, then the recombinations: one ob_haar1 site
+        int hn, hs;
+        if (k < time_divide) { B >>= 1; N_B <<= 1; hn = N_B; hs = B; }
+        else { hn = N0 >> (k - time_divide); hs = 1 << (k - time_divide); }
+        ob_haar1(g, Xb, hn, hs);
+    }
     if (lowband_out) {
         const float n = OB_SQRTF((float)N0);
         for (int j = g.lane; j < N0; j += g.n) lowband_out[j] = n * Xb[j];
