@@ -19,12 +19,14 @@
 #define OB_DEV __device__ __forceinline__
 #define OB_MEM __device__ __forceinline__
 #define OB_DEV_NOINLINE static __device__ __noinline__
+#define OB_STAGE static __device__ __noinline__      // a whole encoder stage: compiled once, called (warp-uniformly) from the frame driver
 #define OB_TABLE(type, name, n) static __device__ const type name[n]
 #define OB_CLZ(x) __clz((int)(x))
 #else
 #define OB_DEV static inline
 #define OB_MEM inline
 #define OB_DEV_NOINLINE static
+#define OB_STAGE static
 #define OB_TABLE(type, name, n) static const type name[n]
 #define OB_CLZ(x) __builtin_clz(x)
 #endif

@@ -1,7 +1,13 @@
-// enc_frame.cuh -- per-stream CELT encoder state and the frame driver: celt_encode_with_ec
-// (opus/celt/celt_encoder.c:1431-2368) for start = 0, no LFE, no surround mask, no Opus-layer signal analysis
-// (analysis.valid == 0), plus the thin Opus layer around it for CELT-only packets
-// (opus/src/opus_encoder.c: dc_reject :430-468, byte budget :1188-1197, TOC gen_toc :299-329).
+// enc_frame.cuh -- per-stream CELT encoder state, the warp's working set, and the frame driver: celt_encode_with_ec
+// (opus/celt/celt_encoder.c:1431-2368) for start = 0, no LFE, no surround mask, plus the thin Opus layer around it for CELT-only
+// packets (opus/src/opus_encoder.c: dc_reject :430-468, byte budget :1188-1197, TOC gen_toc :299-329).
+//
+// ONE WARP PER STREAM.  Memory plan per warp:
+//   shared (ObEncShared, ~18 KB): everything touched element by element or out of order -- the FFT / pitch / transient scratch, the band
+//     being quantised with its folding source, the coder's output bytes, and the per-band tables of the frame;
+//   global, per resident warp (ObEncWork, ~60 KB, stays in L2): the long time / frequency vectors that are only streamed with
+//     lane-strided (coalesced) loops -- [history | frame] of the pre-filter, the MDCT input, the spectrum, the normalised spectrum;
+//   global, per stream (ObEncStream + ObEncHist): state between calls, read at the start and written at the end of a launch.
 #pragma once
 #include "enc_quant.cuh"
 #include "enc_tonal.cuh"
@@ -9,7 +15,7 @@
 
 #define OB_BITRATE_MAX (-1)
 
-// struct OpusCustomEncoder (celt_encoder.c:58-128), the parts this path uses, + the Opus layer's dc_reject memory.
+// struct OpusCustomEncoder (celt_encoder.c:58-128), the scalar part, + the Opus layer's dc_reject memory.  Every lane holds a copy.
 struct ObEncState {
     // configuration (CTLs)
     int32_t channels, stream_channels, complexity, bitrate, vbr, constrained_vbr, lsb_depth, end, force_intra, loss_rate, disable_inv, clip, disable_pf;
@@ -27,26 +33,41 @@ struct ObEncState {
     float spec_avg;
     float hp_mem[4];                                  // Opus layer: dc_reject (opus_encoder.c:430-468)
     uint32_t final_range;
+    ObAnalysisInfo an;                                // st->analysis: set by the Opus layer before every frame (CELT_SET_ANALYSIS)
+};
+// ... and its vectors (in_mem, prefilter_mem, oldBandE, oldLogE, oldLogE2, energyError): per stream in HBM between launches
+struct ObEncHist {
     float in_mem[2 * OB_OVERLAP];
     float prefilter_mem[2 * OB_MAXPERIOD];
     float oldBandE[2 * OB_NB], oldLogE[2 * OB_NB], oldLogE2[2 * OB_NB], energyError[2 * OB_NB];
-    ObAnalysisInfo an;                                // st->analysis: set by the Opus layer before every frame (CELT_SET_ANALYSIS)
 };
 
-// Per-stream working memory of one frame (the reference's stack VLAs).
 #define OB_ENC_DELAY 192                                  // delay_compensation = Fs/250 (opus_encoder.c:282)
 #define OB_ENC_BUFFER 480                                 // encoder_buffer = Fs/100 (:276)
-struct ObEncScratch {
+#define OB_ENC_SCR 1280
+
+struct ObEncShared {
+    float A[OB_ENC_SCR];                              // pitch-search scratch / transient high-pass output / FFT work / small per-band scratch
+    union {
+        struct { float pitch_buf[(OB_MAXPERIOD + OB_MAX_N) >> 1]; } t;                                                  // time-domain phase
+        ObEncBandsShared bands;                                                                                          // quantisation phase
+    } u;
+    float oldBandE[2 * OB_NB], oldLogE[2 * OB_NB], oldLogE2[2 * OB_NB], energyError[2 * OB_NB];
+    float bandE[2 * OB_NB], bandLogE[2 * OB_NB], bandLogE2[2 * OB_NB], error[2 * OB_NB];
+    int fine_quant[OB_NB], pulses[OB_NB], cap[OB_NB], offsets[OB_NB], importance[OB_NB], spread_weight[OB_NB], fine_priority[OB_NB], tf_res[OB_NB];
+    ObAnalysisInfo an_tmp;                            // lane 0 -> warp hand-over of an inline analysis result
+    uint8_t collapse_masks[2 * OB_NB + 2];
+    uint8_t bytes[1280];                              // the range coder's buffer (payload without the TOC)
+};
+struct ObEncWork {
     float in[2 * (OB_MAX_N + OB_OVERLAP)];
     float pre[2 * (OB_MAX_N + OB_MAXPERIOD)];
-    float pitch_buf[(OB_MAXPERIOD + OB_MAX_N) >> 1];
-    float tmp[1280];                                  // pitch_search scratch / yy_lookup / transient_analysis tmp
     float freq[2 * OB_MAX_N];
     float X[2 * OB_MAX_N];
-    float mdct_f[OB_MAX_N], mdct_f2[OB_MAX_N];
     float pcm_hp[2 * (OB_MAX_N + OB_ENC_DELAY)];      // [delay compensation | dc_reject / hp_cutoff output]: what CELT encodes
-    ObEncBandsScratch bands;
-    uint8_t coarse_save[1280];
+    float env[(OB_MAX_N + OB_OVERLAP + 7) >> 1];      // transient_analysis: the masking envelope (chunk-per-lane scans)
+    ObEncHist hist;                                   // in_mem / prefilter_mem of the stream being coded (the four energy arrays live in shared memory)
+    ObEncBandsWork bw;
     ObRepack rp;                                      // opus_packet_pad of a 'PLC frame'
     uint8_t multi_tmp[1284];                          // the 20 ms frames of a 40-120 ms packet before they are repacketized
 };
@@ -58,32 +79,56 @@ OB_DEV void ob_enc_reset(ObEncState &st)
     st.preemph_memE[0] = st.preemph_memE[1] = 0; st.vbr_reservoir = st.vbr_drift = st.vbr_offset = st.vbr_count = 0;
     st.overlap_max = 0; st.stereo_saving = 0; st.intensity = 0; st.spec_avg = 0; st.final_range = 0; st.an.valid = 0;
     for (int i = 0; i < 4; i++) st.hp_mem[i] = 0;
-    for (int i = 0; i < 2 * OB_OVERLAP; i++) st.in_mem[i] = 0;
-    for (int i = 0; i < 2 * OB_MAXPERIOD; i++) st.prefilter_mem[i] = 0;
-    for (int i = 0; i < 2 * OB_NB; i++) { st.oldBandE[i] = 0; st.oldLogE[i] = st.oldLogE2[i] = -28.f; st.energyError[i] = 0; }
+}
+OB_DEV void ob_enc_hist_reset(ObEncHist &h)
+{
+    for (int i = 0; i < 2 * OB_OVERLAP; i++) h.in_mem[i] = 0;
+    for (int i = 0; i < 2 * OB_MAXPERIOD; i++) h.prefilter_mem[i] = 0;
+    for (int i = 0; i < 2 * OB_NB; i++) { h.oldBandE[i] = 0; h.oldLogE[i] = h.oldLogE2[i] = -28.f; h.energyError[i] = 0; }
+}
+// stream state <-> the warp's working set, at the two ends of a launch
+template <class G>
+OB_DEV void ob_enc_load_hist(const G &g, ObEncShared &sh, ObEncWork &wk, const ObEncHist &h)
+{
+    for (int i = g.lane; i < 2 * OB_OVERLAP; i += g.n) wk.hist.in_mem[i] = h.in_mem[i];
+    for (int i = g.lane; i < 2 * OB_MAXPERIOD; i += g.n) wk.hist.prefilter_mem[i] = h.prefilter_mem[i];
+    for (int i = g.lane; i < 2 * OB_NB; i += g.n) { sh.oldBandE[i] = h.oldBandE[i]; sh.oldLogE[i] = h.oldLogE[i]; sh.oldLogE2[i] = h.oldLogE2[i]; sh.energyError[i] = h.energyError[i]; }
+    g.sync();
+}
+template <class G>
+OB_DEV void ob_enc_store_hist(const G &g, const ObEncShared &sh, const ObEncWork &wk, ObEncHist &h)
+{
+    g.sync();
+    for (int i = g.lane; i < 2 * OB_OVERLAP; i += g.n) h.in_mem[i] = wk.hist.in_mem[i];
+    for (int i = g.lane; i < 2 * OB_MAXPERIOD; i += g.n) h.prefilter_mem[i] = wk.hist.prefilter_mem[i];
+    for (int i = g.lane; i < 2 * OB_NB; i += g.n) { h.oldBandE[i] = sh.oldBandE[i]; h.oldLogE[i] = sh.oldLogE[i]; h.oldLogE2[i] = sh.oldLogE2[i]; h.energyError[i] = sh.energyError[i]; }
+    g.sync();
 }
 
-// run_prefilter (celt_encoder.c:1188-1318), analysis invalid
-OB_DEV int ob_run_prefilter(ObEncState &st, ObEncScratch &S, float *in, int CC, int N, int prefilter_tapset, int *pitch, float *gain, int *qgain,
-        int enabled, int nbAvailableBytes)
+// run_prefilter (celt_encoder.c:1188-1318)
+template <class G>
+OB_STAGE int ob_run_prefilter(const G &g, ObEncState &st, ObEncShared &sh, ObEncWork &wk, float *in, int CC, int N, int prefilter_tapset, int *pitch, float *gain,
+        int *qgain, int enabled, int nbAvailableBytes)
 {
-    float *pre[2] = {S.pre, S.pre + (N + OB_MAXPERIOD)};
+    float *pre[2] = {wk.pre, wk.pre + (N + OB_MAXPERIOD)};
     int pitch_index, pf_on, qg;
     float gain1, pf_threshold;
     for (int c = 0; c < CC; c++) {
         float *__restrict__ dst = pre[c];
-        const float *__restrict__ mem = st.prefilter_mem + c * OB_MAXPERIOD, *__restrict__ src = in + c * (N + OB_OVERLAP) + OB_OVERLAP;
-#pragma unroll 8
-        for (int i = 0; i < OB_MAXPERIOD; i++) dst[i] = mem[i];
-#pragma unroll 8
-        for (int i = 0; i < N; i++) dst[OB_MAXPERIOD + i] = src[i];
+        const float *__restrict__ mem = wk.hist.prefilter_mem + c * OB_MAXPERIOD, *__restrict__ src = in + c * (N + OB_OVERLAP) + OB_OVERLAP;
+        for (int i = g.lane; i < OB_MAXPERIOD; i += g.n) dst[i] = mem[i];
+        for (int i = g.lane; i < N; i += g.n) dst[OB_MAXPERIOD + i] = src[i];
     }
+    g.sync();
     if (enabled) {
-        float *pitch_buf = S.pitch_buf;
-        ob_pitch_downsample(pre[0], pre[1], pitch_buf, OB_MAXPERIOD + N, CC);
-        ob_pitch_search(pitch_buf + (OB_MAXPERIOD >> 1), pitch_buf, N, OB_MAXPERIOD - 3 * OB_MINPERIOD, &pitch_index, S.tmp);
+        float *pitch_buf = sh.u.t.pitch_buf;
+        g.pace(3);
+        ob_pitch_downsample(g, pre[0], pre[1], pitch_buf, sh.A, OB_MAXPERIOD + N, CC);
+        g.pace(4);
+        ob_pitch_search(g, pitch_buf + (OB_MAXPERIOD >> 1), pitch_buf, N, OB_MAXPERIOD - 3 * OB_MINPERIOD, &pitch_index, sh.A);
         pitch_index = OB_MAXPERIOD - pitch_index;
-        gain1 = ob_remove_doubling(pitch_buf, OB_MAXPERIOD, OB_MINPERIOD, N, &pitch_index, st.prefilter_period, st.prefilter_gain, S.tmp);
+        g.pace(5);
+        gain1 = ob_remove_doubling(g, pitch_buf, OB_MAXPERIOD, OB_MINPERIOD, N, &pitch_index, st.prefilter_period, st.prefilter_gain, sh.A);
         if (pitch_index > OB_MAXPERIOD - 2) pitch_index = OB_MAXPERIOD - 2;
         gain1 = .7f * gain1;
         if (st.loss_rate > 2) gain1 = .5f * gain1;
@@ -107,52 +152,44 @@ OB_DEV int ob_run_prefilter(ObEncState &st, ObEncScratch &S, float *in, int CC, 
         gain1 = 0.09375f * (qg + 1);
         pf_on = 1;
     }
+    g.pace(6);
     for (int c = 0; c < CC; c++) {
         const int offset = OB_SHORT - OB_OVERLAP;      // 0 for this mode
         st.prefilter_period = ob_imax(st.prefilter_period, OB_MINPERIOD);
-        for (int i = 0; i < OB_OVERLAP; i++) in[c * (N + OB_OVERLAP) + i] = st.in_mem[c * OB_OVERLAP + i];
+        float *inc = in + c * (N + OB_OVERLAP), *mem_in = wk.hist.in_mem + c * OB_OVERLAP, *mem_pf = wk.hist.prefilter_mem + c * OB_MAXPERIOD;
+        for (int i = g.lane; i < OB_OVERLAP; i += g.n) inc[i] = mem_in[i];
         if (offset)
-            ob_comb_filter_xy(in + c * (N + OB_OVERLAP) + OB_OVERLAP, pre[c] + OB_MAXPERIOD, st.prefilter_period, st.prefilter_period, offset,
+            ob_comb_filter_xy(g, inc + OB_OVERLAP, pre[c] + OB_MAXPERIOD, st.prefilter_period, st.prefilter_period, offset,
                     -st.prefilter_gain, -st.prefilter_gain, st.prefilter_tapset, st.prefilter_tapset, 0);
-        ob_comb_filter_xy(in + c * (N + OB_OVERLAP) + OB_OVERLAP + offset, pre[c] + OB_MAXPERIOD + offset, st.prefilter_period, pitch_index, N - offset,
+        ob_comb_filter_xy(g, inc + OB_OVERLAP + offset, pre[c] + OB_MAXPERIOD + offset, st.prefilter_period, pitch_index, N - offset,
                 -st.prefilter_gain, -gain1, st.prefilter_tapset, prefilter_tapset, OB_OVERLAP);
-        for (int i = 0; i < OB_OVERLAP; i++) st.in_mem[c * OB_OVERLAP + i] = in[c * (N + OB_OVERLAP) + N + i];
-        if (N > OB_MAXPERIOD) {
-            for (int i = 0; i < OB_MAXPERIOD; i++) st.prefilter_mem[c * OB_MAXPERIOD + i] = pre[c][N + i];
-        } else {
-            float *mem = st.prefilter_mem + c * OB_MAXPERIOD;
-            for (int i = 0; i < OB_MAXPERIOD - N; i += 8) {          // a move towards the front by N >= 120: 8 loads can go out before the 8 stores
-                float v[8];
-#pragma unroll
-                for (int k = 0; k < 8; k++) v[k] = mem[N + i + k];
-#pragma unroll
-                for (int k = 0; k < 8; k++) mem[i + k] = v[k];
-            }
-            const float *__restrict__ src = pre[c] + OB_MAXPERIOD;
-            float *__restrict__ dst = mem + OB_MAXPERIOD - N;
-#pragma unroll 8
-            for (int i = 0; i < N; i++) dst[i] = src[i];
-        }
+        for (int i = g.lane; i < OB_OVERLAP; i += g.n) mem_in[i] = inc[N + i];
+        // the new pre-filter memory is the last MAXPERIOD samples of [old memory | frame] (N <= 960 < MAXPERIOD), read from the assembled copy
+        for (int i = g.lane; i < OB_MAXPERIOD; i += g.n) mem_pf[i] = pre[c][N + i];
     }
+    g.sync();
     *gain = gain1; *pitch = pitch_index; *qgain = qg;
     return pf_on;
 }
 
 // celt_encode_with_ec (celt_encoder.c:1431-2368).  pcm: interleaved floats in [-1,1].  enc: coder created by the caller over the
 // payload buffer (as opus_encode_frame_native does, opus_encoder.c:1791) -- tell == 1 on entry.  Returns bytes used or < 0.
-OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float *pcm, int frame_size, int nbCompressedBytes, ObRangeEnc &enc)
+template <class G>
+OB_STAGE int ob_celt_encode(const G &g, ObEncState &st, ObEncShared &sh, ObEncWork &wk, const float *pcm, int frame_size, int nbCompressedBytes, ObRangeEnc &enc_io)
 {
+    ObRangeEnc enc = enc_io;                                      // the coder works in registers inside a stage
     const int CC = st.channels, C = st.stream_channels, end = st.end, effEnd = st.end;
     int LM, shortBlocks = 0, isTransient = 0, tf_select, codedBands, alloc_trim, pitch_index = OB_MINPERIOD, dual_stereo = 0, effectiveBytes;
     int prefilter_tapset = 0, pf_on, anti_collapse_rsv, anti_collapse_on = 0, silence = 0, tf_chan = 0, pitch_change = 0, secondMdct;
     int signalBandwidth, transient_got_disabled = 0, enable_tf_analysis, nbFilledBytes, nbAvailableBytes, dynalloc_logp;
     int32_t vbr_rate, total_bits, total_boost, balance, tell, tot_boost = 0, equiv_rate, bits;
     float gain1 = 0, tf_estimate = 0, sample_max, maxDepth, temporal_vbr = 0;
-    float bandE[2 * OB_NB], bandLogE[2 * OB_NB], bandLogE2[2 * OB_NB], error[2 * OB_NB];
-    int fine_quant[OB_NB], pulses[OB_NB], cap[OB_NB], offsets[OB_NB], importance[OB_NB], spread_weight[OB_NB], fine_priority[OB_NB], tf_res[OB_NB];
-    uint8_t collapse_masks[2 * OB_NB];
-    float *oldBandE = st.oldBandE, *oldLogE = st.oldLogE, *oldLogE2 = st.oldLogE2, *energyError = st.energyError;
-    float *in = S.in, *freq = S.freq, *X = S.X;
+    float *bandE = sh.bandE, *bandLogE = sh.bandLogE, *bandLogE2 = sh.bandLogE2, *error = sh.error;
+    int *fine_quant = sh.fine_quant, *pulses = sh.pulses, *cap = sh.cap, *offsets = sh.offsets, *importance = sh.importance, *spread_weight = sh.spread_weight,
+        *fine_priority = sh.fine_priority, *tf_res = sh.tf_res;
+    uint8_t *collapse_masks = sh.collapse_masks;
+    float *oldBandE = sh.oldBandE, *oldLogE = sh.oldLogE, *oldLogE2 = sh.oldLogE2, *energyError = sh.energyError;
+    float *in = wk.in, *freq = wk.freq, *X = wk.X;
 
     if (nbCompressedBytes < 2 || pcm == nullptr) return OB_BAD_ARG;
     for (LM = 0; LM <= 3; LM++) if (OB_SHORT << LM == frame_size) break;
@@ -190,8 +227,8 @@ OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float 
     }
     total_bits = nbCompressedBytes * 8;
 
-    sample_max = ob_fmax(st.overlap_max, ob_maxabs(pcm, C * (N - OB_OVERLAP)));
-    st.overlap_max = ob_maxabs(pcm + C * (N - OB_OVERLAP), C * OB_OVERLAP);
+    sample_max = ob_fmax(st.overlap_max, ob_maxabs(g, pcm, C * (N - OB_OVERLAP)));
+    st.overlap_max = ob_maxabs(g, pcm + C * (N - OB_OVERLAP), C * OB_OVERLAP);
     sample_max = ob_fmax(sample_max, st.overlap_max);
     silence = (sample_max <= (float)1 / (1 << st.lsb_depth));
     if (tell == 1) enc.bit_logp(silence, 15);
@@ -206,15 +243,16 @@ OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float 
         tell = nbCompressedBytes * 8;
         enc.nbits_total += tell - enc.tell();
     }
+    g.pace(2);
     for (int c = 0; c < CC; c++) {
         const int need_clip = st.clip && sample_max > 65536.f;
-        ob_preemphasis(pcm + c, in + c * (N + OB_OVERLAP) + OB_OVERLAP, N, CC, &st.preemph_memE[c], need_clip);
+        ob_preemphasis(g, pcm + c, in + c * (N + OB_OVERLAP) + OB_OVERLAP, N, CC, &st.preemph_memE[c], need_clip);
     }
     {   // pitch pre-filter
         int qg;
         const int enabled = nbAvailableBytes > 12 * C && !silence && !st.disable_pf && st.complexity >= 5;
         prefilter_tapset = st.tapset_decision;
-        pf_on = ob_run_prefilter(st, S, in, CC, N, prefilter_tapset, &pitch_index, &gain1, &qg, enabled, nbAvailableBytes);
+        pf_on = ob_run_prefilter(g, st, sh, wk, in, CC, N, prefilter_tapset, &pitch_index, &gain1, &qg, enabled, nbAvailableBytes);
         if ((gain1 > .4f || st.prefilter_gain > .4f) && (!st.an.valid || (double)st.an.tonality > .3)
                 && (pitch_index > 1.26 * st.prefilter_period || pitch_index < .79 * st.prefilter_period))
             pitch_change = 1;
@@ -231,21 +269,23 @@ OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float 
             enc.icdf(prefilter_tapset, OB_TAPSET_ICDF, 2);
         }
     }
-    if (st.complexity >= 1) isTransient = ob_transient_analysis(in, N + OB_OVERLAP, CC, &tf_estimate, &tf_chan, S.tmp);
+    g.pace(7);
+    if (st.complexity >= 1) isTransient = ob_transient_analysis(g, in, N + OB_OVERLAP, CC, &tf_estimate, &tf_chan, sh.A, wk.env);
     if (LM > 0 && enc.tell() + 3 <= total_bits) { if (isTransient) shortBlocks = M; }
     else { isTransient = 0; transient_got_disabled = 1; }
 
+    g.pace(8);
     secondMdct = shortBlocks && st.complexity >= 8;
     if (secondMdct) {
-        ob_compute_mdcts(0, in, freq, C, CC, LM, S.mdct_f, S.mdct_f2);
-        ob_band_energies(freq, bandE, effEnd, C, LM);
-        ob_amp2log2(effEnd, end, bandE, bandLogE2, C);
+        ob_compute_mdcts(g, 0, in, freq, C, CC, LM, sh.A);
+        ob_band_energies(g, freq, bandE, effEnd, C, LM);
+        ob_amp2log2(g, effEnd, end, bandE, bandLogE2, C);
         for (int c = 0; c < C; c++) for (int i = 0; i < end; i++) bandLogE2[OB_NB * c + i] += .5f * (float)LM;
     }
-    ob_compute_mdcts(shortBlocks, in, freq, C, CC, LM, S.mdct_f, S.mdct_f2);
+    ob_compute_mdcts(g, shortBlocks, in, freq, C, CC, LM, sh.A);
     if (CC == 2 && C == 1) tf_chan = 0;
-    ob_band_energies(freq, bandE, effEnd, C, LM);
-    ob_amp2log2(effEnd, end, bandE, bandLogE, C);
+    ob_band_energies(g, freq, bandE, effEnd, C, LM);
+    ob_amp2log2(g, effEnd, end, bandE, bandLogE, C);
     {   // temporal VBR (celt_encoder.c:1849-1865)
         float follow = -10.0f, frame_avg = 0;
         const float offset = shortBlocks ? .5f * (float)LM : 0;
@@ -261,25 +301,29 @@ OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float 
     }
     if (!secondMdct) for (int i = 0; i < C * OB_NB; i++) bandLogE2[i] = bandLogE[i];
     if (LM > 0 && enc.tell() + 3 <= total_bits && !isTransient && st.complexity >= 5) {
-        if (ob_patch_transient(bandLogE, oldBandE, end, C)) {
+        if (ob_patch_transient(bandLogE, oldBandE, end, C, sh.A)) {
             isTransient = 1;
             shortBlocks = M;
-            ob_compute_mdcts(shortBlocks, in, freq, C, CC, LM, S.mdct_f, S.mdct_f2);
-            ob_band_energies(freq, bandE, effEnd, C, LM);
-            ob_amp2log2(effEnd, end, bandE, bandLogE, C);
+            g.sync();
+            ob_compute_mdcts(g, shortBlocks, in, freq, C, CC, LM, sh.A);
+            ob_band_energies(g, freq, bandE, effEnd, C, LM);
+            ob_amp2log2(g, effEnd, end, bandE, bandLogE, C);
             for (int c = 0; c < C; c++) for (int i = 0; i < end; i++) bandLogE2[OB_NB * c + i] += .5f * (float)LM;
             tf_estimate = .2f;
         }
     }
     if (LM > 0 && enc.tell() + 3 <= total_bits) enc.bit_logp(isTransient, 3);
 
-    ob_normalise_bands(freq, X, bandE, effEnd, C, M);
+    g.pace(10);
+    ob_normalise_bands(g, freq, X, bandE, effEnd, C, M);
     enable_tf_analysis = effectiveBytes >= 15 * C && st.complexity >= 2;
     maxDepth = ob_dynalloc_analysis(bandLogE, bandLogE2, oldBandE, end, C, offsets, st.lsb_depth, isTransient, st.vbr, st.constrained_vbr, LM,
-            effectiveBytes, &tot_boost, importance, spread_weight, st.an.valid ? st.an.leak_boost : nullptr);
+            effectiveBytes, &tot_boost, importance, spread_weight, st.an.valid ? st.an.leak_boost : nullptr, sh.A);
+    g.pace(11);
     if (enable_tf_analysis) {
         const int lambda = ob_imax(80, 20480 / effectiveBytes + 2);
-        tf_select = ob_tf_analysis(effEnd, isTransient, tf_res, lambda, X, N, LM, tf_estimate, tf_chan, importance);
+        tf_select = ob_tf_analysis(g, effEnd, isTransient, tf_res, lambda, X, N, LM, tf_estimate, tf_chan, importance, sh.u.bands.xb, sh.u.bands.xb + OB_MAX_BAND,
+                                   (int *)sh.A);
         for (int i = effEnd; i < end; i++) tf_res[i] = tf_res[effEnd - 1];
     } else {
         for (int i = 0; i < end; i++) tf_res[i] = isTransient;
@@ -288,14 +332,16 @@ OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float 
     for (int c = 0; c < C; c++) for (int i = 0; i < end; i++) {
         if (fabsf(bandLogE[i + c * OB_NB] - oldBandE[i + c * OB_NB]) < 2.f) bandLogE[i + c * OB_NB] -= energyError[i + c * OB_NB] * 0.25f;
     }
-    ob_quant_coarse_energy(end, effEnd, bandLogE, oldBandE, (uint32_t)total_bits, error, enc, C, LM, nbAvailableBytes, st.force_intra,
-            &st.delayedIntra, st.complexity >= 4, st.loss_rate, S.coarse_save);
+    g.pace(12);
+    ob_quant_coarse_energy(g, end, effEnd, bandLogE, oldBandE, (uint32_t)total_bits, error, enc, C, LM, nbAvailableBytes, st.force_intra,
+            &st.delayedIntra, st.complexity >= 4, st.loss_rate, wk.bw.bytes_save, sh.A);
+    g.pace(13);
     ob_tf_encode(end, isTransient, tf_res, LM, tf_select, enc);
     if (enc.tell() + 4 <= total_bits) {
         if (shortBlocks || st.complexity < 3 || nbAvailableBytes < 10 * C) {
             if (st.complexity == 0) st.spread_decision = 0; else st.spread_decision = 2;
         } else {
-            st.spread_decision = ob_spreading_decision(X, &st.tonal_average, st.spread_decision, &st.hf_average, &st.tapset_decision,
+            st.spread_decision = ob_spreading_decision(g, X, &st.tonal_average, st.spread_decision, &st.hf_average, &st.tapset_decision,
                     pf_on && !shortBlocks, effEnd, C, M, spread_weight);
         }
         enc.icdf(st.spread_decision, OB_SPREAD_ICDF, 5);
@@ -327,13 +373,13 @@ OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float 
     if (C == 2) {
         const float intensity_thresholds[21] = {1, 2, 3, 4, 5, 6, 7, 8, 16, 24, 36, 44, 50, 56, 62, 67, 72, 79, 88, 106, 134};
         const float intensity_histeresis[21] = {1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 3, 3, 4, 5, 6, 8, 8};
-        if (LM != 0) dual_stereo = ob_stereo_analysis(X, LM, N);
+        if (LM != 0) dual_stereo = ob_stereo_analysis(g, X, LM, N);
         st.intensity = ob_hysteresis_decision((float)(equiv_rate / 1000), intensity_thresholds, intensity_histeresis, 21, st.intensity);
         st.intensity = ob_imin(end, ob_imax(0, st.intensity));
     }
     alloc_trim = 5;
     if (tell + (6 << OB_BITRES) <= total_bits - total_boost) {
-        alloc_trim = ob_alloc_trim_analysis(X, bandLogE, end, LM, C, N, &st.stereo_saving, tf_estimate, st.intensity, equiv_rate, st.an.valid, st.an.tonality_slope);
+        alloc_trim = ob_alloc_trim_analysis(g, X, bandLogE, end, LM, C, N, &st.stereo_saving, tf_estimate, st.intensity, equiv_rate, st.an.valid, st.an.tonality_slope);
         enc.icdf(alloc_trim, OB_TRIM_ICDF, 7);
         tell = (int32_t)enc.tell_frac();
     }
@@ -382,14 +428,17 @@ OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float 
         else min_bandwidth = 20;
         signalBandwidth = ob_imax(st.an.bandwidth, min_bandwidth);
     }
+    g.pace(14);
     codedBands = ob_enc_allocation(enc, end, offsets, cap, alloc_trim, &st.intensity, &dual_stereo, bits, &balance, pulses, fine_quant, fine_priority,
-            C, LM, st.lastCodedBands, signalBandwidth);
+            C, LM, st.lastCodedBands, signalBandwidth, (int *)sh.A);
     if (st.lastCodedBands) st.lastCodedBands = ob_imin(st.lastCodedBands + 1, ob_imax(st.lastCodedBands - 1, codedBands));
     else st.lastCodedBands = codedBands;
     ob_quant_fine_energy(end, oldBandE, error, fine_quant, enc, C);
     for (int i = 0; i < 2 * OB_NB; i++) collapse_masks[i] = 0;
-    ob_enc_all_bands(end, X, C == 2 ? X + N : nullptr, collapse_masks, bandE, pulses, shortBlocks, st.spread_decision, dual_stereo, st.intensity, tf_res,
-            nbCompressedBytes * (8 << OB_BITRES) - anti_collapse_rsv, balance, enc, LM, codedBands, &st.rng, st.complexity, st.disable_inv, S.bands);
+    g.sync();
+    ob_enc_all_bands(g, end, X, C, N, collapse_masks, bandE, pulses, shortBlocks, st.spread_decision, dual_stereo, st.intensity, tf_res,
+            nbCompressedBytes * (8 << OB_BITRES) - anti_collapse_rsv, balance, enc, LM, codedBands, &st.rng, st.complexity, st.disable_inv, sh.u.bands, wk.bw);
+    g.pace(60);
     if (anti_collapse_rsv > 0) {
         anti_collapse_on = st.consec_transient < 2;
         enc.bits((uint32_t)anti_collapse_on, 1);
@@ -409,38 +458,34 @@ OB_DEV_NOINLINE int ob_celt_encode(ObEncState &st, ObEncScratch &S, const float 
     if (isTransient || transient_got_disabled) st.consec_transient++; else st.consec_transient = 0;
     st.rng = enc.rng;
     enc.done();
+    enc_io = enc;
+    g.sync();
     if (enc.error) return OB_INTERNAL_ERROR;
     return nbCompressedBytes;
 }
 
-// dc_reject (opus_encoder.c:430-468), float build, cutoff 3 Hz @ 48 kHz
-OB_DEV void ob_dc_reject(const float *in, float *out, float *hp_mem, int len, int channels)
+// dc_reject (opus_encoder.c:430-468), float build, cutoff 3 Hz @ 48 kHz: out = x - m, m <- coef*x + 1e-30 + coef2*m: a first-order scan per channel
+template <class G>
+OB_STAGE void ob_dc_reject(const G &g, const float *in, float *out, float *hp_mem, int len, int channels)
 {
     const float coef = 6.3f * 3 / 48000, coef2 = 1 - coef;
-    if (channels == 2) {
-        float m0 = hp_mem[0], m2 = hp_mem[2];
-        for (int i = 0; i < len; i++) {
-            const float x0 = in[2 * i], x1 = in[2 * i + 1];
-            const float out0 = x0 - m0, out1 = x1 - m2;
-            m0 = coef * x0 + 1e-30f + coef2 * m0;
-            m2 = coef * x1 + 1e-30f + coef2 * m2;
-            out[2 * i] = out0; out[2 * i + 1] = out1;
-        }
-        hp_mem[0] = m0; hp_mem[2] = m2;
-    } else {
-        float m0 = hp_mem[0];
-        for (int i = 0; i < len; i++) {
-            const float x = in[i], y = x - m0;
-            m0 = coef * x + 1e-30f + coef2 * m0;
-            out[i] = y;
-        }
-        hp_mem[0] = m0;
+    for (int c = 0; c < channels; c++) {
+        const float m0 = hp_mem[2 * c];
+        const float *x = in + c;
+        float *y = out + c;
+        // y_i (stored) needs the memory BEFORE sample i: put(i, m_i) writes the output of sample i+1; sample 0 uses the carried memory
+        if (g.lane == 0) y[0] = x[0] - m0;
+        hp_mem[2 * c] = ob_scan1(g, len, coef2, m0, false, [&](int i) { return coef * x[channels * i] + 1e-30f; },
+                                 [&](int i, float m) { if (i + 1 < len) y[channels * (i + 1)] = x[channels * (i + 1)] - m; });
     }
+    g.sync();
 }
 
 // hp_cutoff (opus_encoder.c:369-404) + silk_biquad_float (:331-366), Fs = 48000.  cutoff_Hz is 60 for as long as a stream stays
 // CELT-only: variable_HP_smth2_Q15 starts at lin2log(60) << 8 and in MODE_CELT_ONLY is smoothed towards the same value (:1795-1805).
-OB_DEV void ob_hp_cutoff(const float *in, float *out, float *hp_mem, int len, int channels)
+// The biquad's two memories form a second-order linear recurrence: chunk-per-lane scan.
+template <class G>
+OB_STAGE void ob_hp_cutoff(const G &g, const float *in, float *out, float *hp_mem, int len, int channels)
 {
     const int32_t cutoff_Hz = 60;
     const int32_t Fc_Q19 = (int32_t)((int16_t)2471 * (int32_t)(int16_t)cutoff_Hz) / 48;        // SILK_FIX_CONST(1.5 * 3.14159 / 1000, 19) = 2471
@@ -452,37 +497,45 @@ OB_DEV void ob_hp_cutoff(const float *in, float *out, float *hp_mem, int len, in
     const float A0 = (float)(A_Q28[0] * (1.f / ((int32_t)1 << 28))), A1 = (float)(A_Q28[1] * (1.f / ((int32_t)1 << 28)));
     const float B0 = (float)(B_Q28[0] * (1.f / ((int32_t)1 << 28))), B1 = (float)(B_Q28[1] * (1.f / ((int32_t)1 << 28))), B2 = (float)(B_Q28[2] * (1.f / ((int32_t)1 << 28)));
     for (int c = 0; c < channels; c++) {
-        float S0 = hp_mem[2 * c], S1 = hp_mem[2 * c + 1];
-        for (int k = 0; k < len; k++) {
+        ObState2 s; s.s0 = hp_mem[2 * c]; s.s1 = hp_mem[2 * c + 1];
+        s = ob_scan2(g, len, -A0, 1.f, -A1, 0.f, s, [&](int k, float &S0, float &S1, bool emit) {
             const float inval = in[k * channels + c];
             const float vout = S0 + B0 * inval;
             S0 = S1 - vout * A0 + B1 * inval;
             S1 = -vout * A1 + B2 * inval + 1e-30f;
-            out[k * channels + c] = vout;
-        }
-        hp_mem[2 * c] = S0; hp_mem[2 * c + 1] = S1;
+            if (emit) out[k * channels + c] = vout;
+        });
+        hp_mem[2 * c] = s.s0; hp_mem[2 * c + 1] = s.s1;
     }
+    g.sync();
 }
 
 // compute_stereo_width (opus_encoder.c:729-809), float build: feeds the SILK / CELT mode thresholds of the non-low-delay applications
 struct ObStereoWidth { float XX, XY, YY, smoothed_width, max_follower; };
-OB_DEV float ob_compute_stereo_width(const float *pcm, int frame_size, ObStereoWidth &mem)
+template <class G>
+OB_STAGE float ob_compute_stereo_width(const G &g, const float *pcm, int frame_size, ObStereoWidth &mem)
 {
     const int frame_rate = 48000 / frame_size;
     const float short_alpha = 1.0f - 25 * 1.0f / ob_imax(50, frame_rate);
     float xx = 0, xy = 0, yy = 0;
-    for (int i = 0; i < frame_size - 3; i += 4) {
-        float pxx, pxy, pyy, x, y;
-        x = pcm[2 * i]; y = pcm[2 * i + 1];
-        pxx = x * x; pxy = x * y; pyy = y * y;
-        x = pcm[2 * i + 2]; y = pcm[2 * i + 3];
-        pxx += x * x; pxy += x * y; pyy += y * y;
-        x = pcm[2 * i + 4]; y = pcm[2 * i + 5];
-        pxx += x * x; pxy += x * y; pyy += y * y;
-        x = pcm[2 * i + 6]; y = pcm[2 * i + 7];
-        pxx += x * x; pxy += x * y; pyy += y * y;
-        xx += pxx; xy += pxy; yy += pyy;
-    }
+    ob_psum2(g, (frame_size - 3 + 3) / 4, xx, xy, [&](int q, float &a, float &b) {
+        const int i = 4 * q;
+        float pxx, pxy, x, y;
+        x = pcm[2 * i]; y = pcm[2 * i + 1]; pxx = x * x; pxy = x * y;
+        x = pcm[2 * i + 2]; y = pcm[2 * i + 3]; pxx += x * x; pxy += x * y;
+        x = pcm[2 * i + 4]; y = pcm[2 * i + 5]; pxx += x * x; pxy += x * y;
+        x = pcm[2 * i + 6]; y = pcm[2 * i + 7]; pxx += x * x; pxy += x * y;
+        a += pxx; b += pxy;
+    });
+    yy = ob_psum(g, (frame_size - 3 + 3) / 4, 0.f, [&](int q) {
+        const int i = 4 * q;
+        float pyy, y;
+        y = pcm[2 * i + 1]; pyy = y * y;
+        y = pcm[2 * i + 3]; pyy += y * y;
+        y = pcm[2 * i + 5]; pyy += y * y;
+        y = pcm[2 * i + 7]; pyy += y * y;
+        return pyy;
+    });
     if (!(xx < 1e9f) || xx != xx || !(yy < 1e9f) || yy != yy) xy = xx = yy = 0;
     mem.XX += short_alpha * (xx - mem.XX);
     mem.XY += short_alpha * (xy - mem.XY);
@@ -534,30 +587,30 @@ OB_DEV int32_t ob_compute_equiv_rate(int32_t bitrate, int channels, int frame_ra
     return equiv;
 }
 
-OB_DEV void ob_stereo_fade(float *buf, float g1, float g2, int frame_size)     // opus_encoder.c:471-501, in == out, channels == 2, Fs = 48000
+template <class G>
+OB_DEV void ob_stereo_fade(const G &g, float *buf, float g1, float g2, int frame_size)     // opus_encoder.c:471-501, in == out, channels == 2, Fs = 48000
 {
     g1 = 1.0f - g1; g2 = 1.0f - g2;
-    int i;
-    for (i = 0; i < OB_OVERLAP; i++) {
-        const float w = OB_WINDOW[i] * OB_WINDOW[i];
-        const float g = w * g2 + (1.0f - w) * g1;
+    for (int i = g.lane; i < frame_size; i += g.n) {
+        float gg = g2;
+        if (i < OB_OVERLAP) { const float w = OB_WINDOW[i] * OB_WINDOW[i]; gg = w * g2 + (1.0f - w) * g1; }
         float diff = .5f * (buf[i * 2] - buf[i * 2 + 1]);
-        diff = g * diff;
+        diff = gg * diff;
         buf[i * 2] = buf[i * 2] - diff;
         buf[i * 2 + 1] = buf[i * 2 + 1] + diff;
     }
-    for (; i < frame_size; i++) {
-        float diff = .5f * (buf[i * 2] - buf[i * 2 + 1]);
-        diff = g2 * diff;
-        buf[i * 2] = buf[i * 2] - diff;
-        buf[i * 2 + 1] = buf[i * 2 + 1] + diff;
-    }
+    g.sync();
 }
+
+// mean square of a frame: celt_inner_prod(pcm, pcm, n) / n (opus_encoder.c:1127-1130, :1757)
+template <class G>
+OB_DEV float ob_mean_square(const G &g, const float *x, int n) { return ob_psum(g, n, 0.f, [&](int i) { return x[i] * x[i]; }) / n; }
 
 // opus_encode_frame_native (opus_encoder.c:1698-2459) for one 2.5/5/10/20 ms frame, CELT-only: DC reject, stereo fade, CELT, TOC.
 // data: max_data_bytes of room for TOC + payload.  bitrate_bps / equiv_rate: the packet-level values (a frame of a multi-frame packet
 // inherits them).  Returns the frame's packet length (TOC included) or a negative OPUS_* code.
-OB_DEV_NOINLINE int ob_opus_encode_frame(const ObOpusEncCfg &cfg, ObOpusEncState &os, ObEncState &st, ObEncScratch &S, const float *pcm, int frame_size,
+template <class G>
+OB_STAGE int ob_opus_encode_frame(const G &g, const ObOpusEncCfg &cfg, ObOpusEncState &os, ObEncState &st, ObEncShared &sh, ObEncWork &wk, const float *pcm, int frame_size,
         uint8_t *data, int max_data_bytes, int32_t bitrate_bps, int32_t equiv_rate, const ObAnalysisInfo &analysis_info, int is_silence)
 {
     const int channels = st.channels, frame_rate = 48000 / frame_size;
@@ -567,32 +620,38 @@ OB_DEV_NOINLINE int ob_opus_encode_frame(const ObOpusEncCfg &cfg, ObOpusEncState
     else if (analysis_info.valid) {
         activity = analysis_info.activity_probability >= .1f;
         if (!activity) {
-            const float noise_energy = ob_inner_prod(pcm, pcm, frame_size * channels) / (frame_size * channels);
+            const float noise_energy = ob_mean_square(g, pcm, frame_size * channels);
             activity = os.peak_signal_energy < (316.23f * noise_energy);
         }
     }
 
+    g.pace(1);
     ObRangeEnc enc;
-    enc.init(data + 1, (uint32_t)(max_data_bytes - 1));
-    float *pcm_buf = S.pcm_hp;
+    enc.init(sh.bytes, (uint32_t)(max_data_bytes - 1));
+    float *pcm_buf = wk.pcm_hp;
     const int total_buffer = os.delay ? OB_ENC_DELAY : 0;                                                     // :1740-1744
-    for (int i = 0; i < total_buffer * channels; i++) pcm_buf[i] = os.delay[(OB_ENC_BUFFER - total_buffer) * channels + i];
+    for (int i = g.lane; i < total_buffer * channels; i += g.n) pcm_buf[i] = os.delay[(OB_ENC_BUFFER - total_buffer) * channels + i];
     float *fresh = pcm_buf + total_buffer * channels;
-    if (cfg.application == 2048) ob_hp_cutoff(pcm, fresh, st.hp_mem, frame_size, channels);
-    else ob_dc_reject(pcm, fresh, st.hp_mem, frame_size, channels);
+    if (cfg.application == 2048) ob_hp_cutoff(g, pcm, fresh, st.hp_mem, frame_size, channels);
+    else ob_dc_reject(g, pcm, fresh, st.hp_mem, frame_size, channels);
     {
-        const float sum = ob_inner_prod(fresh, fresh, frame_size * channels);
+        const float sum = ob_psum(g, frame_size * channels, 0.f, [&](int i) { return fresh[i] * fresh[i]; });
         if (!(sum < 1e9f) || sum != sum) {
-            for (int i = 0; i < frame_size * channels; i++) fresh[i] = 0;
+            for (int i = g.lane; i < frame_size * channels; i += g.n) fresh[i] = 0;
             st.hp_mem[0] = st.hp_mem[1] = st.hp_mem[2] = st.hp_mem[3] = 0;
+            g.sync();
         }
     }
     if (os.delay) {                                                                                           // :2125-2134, before the fades
         const int keep = OB_ENC_BUFFER - (frame_size + total_buffer);
         if (keep > 0) {
-            for (int i = 0; i < channels * keep; i++) os.delay[i] = os.delay[channels * frame_size + i];
-            for (int i = 0; i < (frame_size + total_buffer) * channels; i++) os.delay[channels * keep + i] = pcm_buf[i];
-        } else for (int i = 0; i < OB_ENC_BUFFER * channels; i++) os.delay[i] = pcm_buf[(frame_size + total_buffer - OB_ENC_BUFFER) * channels + i];
+            float *t = sh.A;                                                                                  // keep * channels <= 336 floats, moved through scratch
+            for (int i = g.lane; i < channels * keep; i += g.n) t[i] = os.delay[channels * frame_size + i];
+            g.sync();
+            for (int i = g.lane; i < channels * keep; i += g.n) os.delay[i] = t[i];
+            for (int i = g.lane; i < (frame_size + total_buffer) * channels; i += g.n) os.delay[channels * keep + i] = pcm_buf[i];
+        } else for (int i = g.lane; i < OB_ENC_BUFFER * channels; i += g.n) os.delay[i] = pcm_buf[(frame_size + total_buffer - OB_ENC_BUFFER) * channels + i];
+        g.sync();
     }
     int stereoWidth_Q14;
     if (equiv_rate > 32000) stereoWidth_Q14 = 16384;
@@ -601,7 +660,7 @@ OB_DEV_NOINLINE int ob_opus_encode_frame(const ObOpusEncCfg &cfg, ObOpusEncState
     if (channels == 2 && (os.hybrid_stereo_width_Q14 < (1 << 14) || stereoWidth_Q14 < (1 << 14))) {
         float g1 = (float)os.hybrid_stereo_width_Q14, g2 = (float)stereoWidth_Q14;
         g1 *= (1.f / 16384); g2 *= (1.f / 16384);
-        ob_stereo_fade(pcm_buf, g1, g2, frame_size);
+        ob_stereo_fade(g, pcm_buf, g1, g2, frame_size);
         os.hybrid_stereo_width_Q14 = stereoWidth_Q14;
     }
     const int nb_compr_bytes = max_data_bytes - 1;
@@ -613,15 +672,17 @@ OB_DEV_NOINLINE int ob_opus_encode_frame(const ObOpusEncCfg &cfg, ObOpusEncState
     st.disable_inv = cfg.phase_inversion_disabled != 0;
     st.bitrate = cfg.vbr ? bitrate_bps : OB_BITRATE_MAX;
     st.an = analysis_info;                                                                                    // CELT_SET_ANALYSIS (:2229)
-    int ret = ob_celt_encode(st, S, pcm_buf, frame_size, nb_compr_bytes, enc);
+    int ret = ob_celt_encode(g, st, sh, wk, pcm_buf, frame_size, nb_compr_bytes, enc);
     if (ret < 0) return OB_INTERNAL_ERROR;
     {   // gen_toc (:299-329)
         int period = 0, fr = frame_rate;
         while (fr < 400) { fr <<= 1; period++; }
         int tmp = curr_bandwidth - 1102;
         if (tmp < 0) tmp = 0;
-        data[0] = (uint8_t)(0x80 | tmp << 5 | period << 3 | (os.stream_channels == 2) << 2);
+        if (g.lane == 0) data[0] = (uint8_t)(0x80 | tmp << 5 | period << 3 | (os.stream_channels == 2) << 2);
     }
+    for (int i = g.lane; i < ret; i += g.n) data[1 + i] = sh.bytes[i];                                       // the payload leaves shared memory in one coalesced copy
+    g.sync();
     st.final_range = enc.rng;
     os.first = 0;
     os.prev_mode = 1002;
@@ -645,11 +706,13 @@ OB_DEV_NOINLINE int ob_opus_encode_frame(const ObOpusEncCfg &cfg, ObOpusEncState
 // (opus_encoder.c:1057-1696, :1698-2459; the lines this path executes are listed in SURVEY 8a).  data: out_bytes capacity.
 // Returns the packet length in bytes (TOC included) or a negative OPUS_* code.
 // pre_info: the frame's AnalysisInfo when the analysis ran ahead of the encoder in its own kernel (ob_k_analysis); nullptr: run it
-// inline on os.tonal.
-OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, ObEncState &st, ObEncScratch &S, const float *pcm, int frame_size,
-        uint8_t *data, int out_bytes, const ObAnalysisInfo *pre_info = nullptr)
+// inline on os.tonal (lane 0; the result reaches the other lanes through shared memory).
+template <class G>
+OB_STAGE int ob_opus_encode(const G &g, const ObOpusEncCfg &cfg, ObOpusEncState &os, ObEncState &st, ObEncShared &sh, ObEncWork &wk, const float *pcm, int frame_size,
+        uint8_t *data, int out_bytes, const ObAnalysisInfo *pre_info = nullptr, int pace_base = 0)
 {
     const int channels = st.channels, Fs = 48000;
+    g.set_base(pace_base);
     st.final_range = 0;                                                                                       // st->rangeFinal = 0 (:1092)
     if (frame_size != 120 && frame_size != 240 && frame_size != 480 && (frame_size % 960 != 0 || frame_size <= 0 || frame_size > 5760)) return OB_BAD_ARG;
     int max_data_bytes = ob_imin(1276, out_bytes);
@@ -675,15 +738,19 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
     {
         const int lsb_depth = cfg.lsb_depth;
         if (cfg.complexity >= 7) {
-            is_silence = ob_maxabs(pcm, frame_size * channels) <= (float)1 / (1 << lsb_depth);
+            is_silence = ob_maxabs(g, pcm, frame_size * channels) <= (float)1 / (1 << lsb_depth);
             if (pre_info) analysis_info = *pre_info;
             else {
                 read_pos_bak = os.tonal->read_pos; read_subframe_bak = os.tonal->read_subframe;
-                ob_run_analysis(*os.tonal, pcm, frame_size, channels, lsb_depth, analysis_info, S.pre);
+                g.sync();
+                if (g.lane == 0) { ObAnalysisInfo a; a.valid = 0; ob_run_analysis(*os.tonal, pcm, frame_size, channels, lsb_depth, a, wk.pre); sh.an_tmp = a; }
+                g.sync();
+                analysis_info = sh.an_tmp;
+                g.sync();
             }
             if (!is_silence && analysis_info.activity_probability > .1f)                                      // peak signal energy (:1127-1130)
-                os.peak_signal_energy = ob_fmax(.999f * os.peak_signal_energy, ob_inner_prod(pcm, pcm, frame_size * channels) / (frame_size * channels));
-        } else if (os.tonal && os.tonal->initialized) ob_tonal_reset(*os.tonal);
+                os.peak_signal_energy = ob_fmax(.999f * os.peak_signal_energy, ob_mean_square(g, pcm, frame_size * channels));
+        } else if (os.tonal && os.tonal->initialized) { g.sync(); if (g.lane == 0) ob_tonal_reset(*os.tonal); g.sync(); }
         if (!is_silence) os.voice_ratio = -1;
         os.detected_bandwidth = 0;
         if (analysis_info.valid) {
@@ -694,7 +761,7 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
         }
     }
     const float stereo_width = (channels == 2 && cfg.force_channels != 1 && (cfg.application == 2048 || cfg.application == 2049))
-                                   ? ob_compute_stereo_width(pcm, frame_size, os.width_mem) : 0;                // :1181-1184 (only the mode decision reads it)
+                                   ? ob_compute_stereo_width(g, pcm, frame_size, os.width_mem) : 0;             // :1181-1184 (only the mode decision reads it)
     if (max_data_bytes < 3 || bitrate_bps < 3 * frame_rate * 8 || (frame_rate < 50 && (max_data_bytes * frame_rate < 300 || bitrate_bps < 2400))) {
         // too little room to code anything: a 'PLC frame', i.e. a TOC and nothing else (:1202-1266); st->mode is still the previous packet's
         // (MODE_HYBRID = 1001 from opus_encoder_init until a packet has been coded)
@@ -715,21 +782,27 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
         else if (tocmode == 1001) toc = 0x60 | (bw - 1104) << 4 | (period - 2) << 3;
         else { int tmp = bw - 1102; if (tmp < 0) tmp = 0; toc = 0x80 | tmp << 5 | period << 3; }
         toc |= (os.stream_channels == 2) << 2;
-        data[0] = (uint8_t)(toc | packet_code);
         int ret = packet_code <= 1 ? 1 : 2;
         max_data_bytes = ob_imax(max_data_bytes, ret);
-        if (packet_code == 3) data[1] = (uint8_t)num_multiframes;
         st.final_range = 0;
-        if (!cfg.vbr && ret != max_data_bytes) {                                                              // opus_packet_pad(data, ret, max_data_bytes)
-            uint8_t copy[2] = {data[0], data[1]};
-            ObRepack &rp = S.rp;
-            ob_repack_init(&rp);
-            if (ob_repack_cat(&rp, copy, ret, 0) != OB_OK) return OB_INTERNAL_ERROR;
-            ObExt none;
-            if (ob_repack_out_range(ObRpLanes1(), &rp, 0, rp.nb_frames, data, max_data_bytes, 0, 1, &none, 0) <= 0) return OB_INTERNAL_ERROR;
-            ret = max_data_bytes;
+        int rc = ret;
+        g.sync();
+        if (g.lane == 0) {                                                                                    // byte work of a rare path: one lane
+            data[0] = (uint8_t)(toc | packet_code);
+            if (packet_code == 3) data[1] = (uint8_t)num_multiframes;
+            if (!cfg.vbr && ret != max_data_bytes) {                                                          // opus_packet_pad(data, ret, max_data_bytes)
+                uint8_t copy[2] = {data[0], data[1]};
+                ObRepack &rp = wk.rp;
+                ob_repack_init(&rp);
+                ObExt none;
+                if (ob_repack_cat(&rp, copy, ret, 0) != OB_OK) rc = OB_INTERNAL_ERROR;
+                else if (ob_repack_out_range(ObRpLanes1(), &rp, 0, rp.nb_frames, data, max_data_bytes, 0, 1, &none, 0) <= 0) rc = OB_INTERNAL_ERROR;
+                else rc = max_data_bytes;
+            }
         }
-        return ret;
+        rc = ob_bcast(g, rc, 0);
+        g.sync();
+        return rc;
     }
     int32_t equiv_rate = ob_compute_equiv_rate(bitrate_bps, channels, frame_rate, cfg.vbr, 0, cfg.complexity, cfg.packet_loss);
     int voice_est;                                                                                            // :1276-1289
@@ -784,31 +857,42 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
         os.bandwidth = ob_imin(os.bandwidth, os.detected_bandwidth);
     }
     if (os.bandwidth == 1102) os.bandwidth = 1103;
-    if (frame_size <= 960) return ob_opus_encode_frame(cfg, os, st, S, pcm, frame_size, data, max_data_bytes, bitrate_bps, equiv_rate, analysis_info, is_silence);
+    if (frame_size <= 960) return ob_opus_encode_frame(g, cfg, os, st, sh, wk, pcm, frame_size, data, max_data_bytes, bitrate_bps, equiv_rate, analysis_info, is_silence);
 
     // ---- 40-120 ms: 20 ms frames encoded one by one and repacketized into one code-1/2/3 packet (opus_encoder.c:1551-1679,
     // opus_repacketizer_out_range_impl, repacketizer.c:112-320) ----
     const int nb_frames = frame_size / 960;
-    if (read_pos_bak != -1) { os.tonal->read_pos = read_pos_bak; os.tonal->read_subframe = read_subframe_bak; }     // the analysis is read one frame at a time
+    g.sync();
+    if (read_pos_bak != -1 && g.lane == 0) { os.tonal->read_pos = read_pos_bak; os.tonal->read_subframe = read_subframe_bak; }     // the analysis is read one frame at a time
+    g.sync();
     const int max_header_bytes = nb_frames == 2 ? 3 : (2 + (nb_frames - 1) * 2);
     const int repacketize_len = (cfg.vbr || cfg.bitrate == -1) ? out_bytes : ob_imin(cbr_bytes, out_bytes);
     const int max_len_sum = nb_frames + repacketize_len - max_header_bytes;
-    if (max_len_sum > (int)sizeof(S.multi_tmp) || max_len_sum < nb_frames) return OB_BUFFER_TOO_SMALL;
-    uint8_t *curr_data = S.multi_tmp;
+    if (max_len_sum > (int)sizeof(wk.multi_tmp) || max_len_sum < nb_frames) return OB_BUFFER_TOO_SMALL;
+    uint8_t *curr_data = wk.multi_tmp;
     int16_t flen[6];
     int tot = 0, dtx_count = 0;
     for (int i = 0; i < nb_frames; i++) {
         int curr_max = ob_imin(3 * bitrate_bps / (3 * 8 * 48000 / 960), max_len_sum / nb_frames);
         curr_max = ob_imin(max_len_sum - tot, curr_max);
-        if (read_pos_bak != -1) ob_tonality_get_info(*os.tonal, analysis_info, 960);
-        const int tmp_len = ob_opus_encode_frame(cfg, os, st, S, pcm + (size_t)i * channels * 960, 960, curr_data, curr_max, bitrate_bps, equiv_rate, analysis_info, is_silence);
+        if (read_pos_bak != -1) {
+            g.sync();
+            if (g.lane == 0) { ObAnalysisInfo a; ob_tonality_get_info(*os.tonal, a, 960); sh.an_tmp = a; }
+            g.sync();
+            analysis_info = sh.an_tmp;
+            g.sync();
+        }
+        g.set_base(pace_base + 64 * i);
+        const int tmp_len = ob_opus_encode_frame(g, cfg, os, st, sh, wk, pcm + (size_t)i * channels * 960, 960, curr_data, curr_max, bitrate_bps, equiv_rate, analysis_info, is_silence);
         if (tmp_len < 0) return OB_INTERNAL_ERROR;
         if (tmp_len == 1) dtx_count++;
         flen[i] = (int16_t)(tmp_len - 1);                           // opus_repacketizer_cat: the frame without its TOC
         tot += tmp_len;
         curr_data += tmp_len;
     }
-    const int toc = S.multi_tmp[0] & 0xFC, pad = !cfg.vbr && dtx_count != nb_frames, maxlen = repacketize_len;
+    g.sync();
+    const int toc = wk.multi_tmp[0] & 0xFC, pad = !cfg.vbr && dtx_count != nb_frames, maxlen = repacketize_len;
+    // header bytes: warp-uniform (every lane stores the same byte); frame payloads: strided copies
     uint8_t *ptr = data;
     int tot_size = 0;
     if (nb_frames == 2) {
@@ -825,22 +909,24 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
         ptr = data;
         int vbr = 0;
         for (int i = 1; i < nb_frames; i++) if (flen[i] != flen[0]) { vbr = 1; break; }
+        int hdr1;
         if (vbr) {
             tot_size = 2;
             for (int i = 0; i < nb_frames - 1; i++) tot_size += 1 + (flen[i] >= 252) + flen[i];
             tot_size += flen[nb_frames - 1];
             if (tot_size > maxlen) return OB_INTERNAL_ERROR;
             *ptr++ = (uint8_t)(toc | 3);
-            *ptr++ = (uint8_t)(nb_frames | 0x80);
+            hdr1 = nb_frames | 0x80;
         } else {
             tot_size = nb_frames * flen[0] + 2;
             if (tot_size > maxlen) return OB_INTERNAL_ERROR;
             *ptr++ = (uint8_t)(toc | 3);
-            *ptr++ = (uint8_t)nb_frames;
+            hdr1 = nb_frames;
         }
         const int pad_amount = pad ? (maxlen - tot_size) : 0;
+        if (pad_amount != 0) hdr1 |= 0x40;
+        *ptr++ = (uint8_t)hdr1;
         if (pad_amount != 0) {
-            data[1] |= 0x40;
             const int nb_255s = (pad_amount - 1) / 255;
             if (tot_size + nb_255s + 1 > maxlen) return OB_INTERNAL_ERROR;
             for (int i = 0; i < nb_255s; i++) *ptr++ = 255;
@@ -853,13 +939,15 @@ OB_DEV_NOINLINE int ob_opus_encode(const ObOpusEncCfg &cfg, ObOpusEncState &os, 
         }
     }
     {
-        const uint8_t *src = S.multi_tmp;
+        const uint8_t *src = wk.multi_tmp;
         for (int i = 0; i < nb_frames; i++) {
             src += 1;                                                // skip the frame's own TOC
-            for (int k = 0; k < flen[i]; k++) *ptr++ = src[k];
+            for (int k = g.lane; k < flen[i]; k += g.n) ptr[k] = src[k];
+            ptr += flen[i];
             src += flen[i];
         }
     }
-    if (pad) while (ptr < data + maxlen) *ptr++ = 0;
+    if (pad) for (int k = g.lane; k < (int)(data + maxlen - ptr); k += g.n) ptr[k] = 0;
+    g.sync();
     return tot_size;
 }

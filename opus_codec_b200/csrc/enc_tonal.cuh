@@ -180,7 +180,7 @@ OB_DEV_NOINLINE void ob_tonality_analysis(ObTonalState &tonal, const float *x, i
     hp_ener = tonal.hp_ener_accum;
     ObAnalysisInfo *info = &tonal.info[tonal.write_pos++];
     if (tonal.write_pos >= OB_AN_DETECT) tonal.write_pos -= OB_AN_DETECT;
-    const int is_silence = ob_maxabs(tonal.inmem, OB_AN_BUF) <= (float)1 / (1 << lsb_depth);
+    const int is_silence = ob_maxabs(ObSolo(), tonal.inmem, OB_AN_BUF) <= (float)1 / (1 << lsb_depth);
     for (i = 0; i < N2; i++) {
         const float w = OB_AN_WINDOW[i];
         in[2 * i] = w * tonal.inmem[i];

@@ -55,6 +55,8 @@ struct ObSolo {
     static constexpr int lane = 0;
     static constexpr int n = 1;
     OB_SOLO_FN void sync() const {}
+    OB_SOLO_FN void pace(int) const {}
+    OB_SOLO_FN void set_base(int) const {}
     OB_SOLO_FN float sum(float v) const { return v; }
     OB_SOLO_FN uint32_t sum_u32(uint32_t v) const { return v; }
 };

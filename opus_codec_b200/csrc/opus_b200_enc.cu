@@ -1,9 +1,12 @@
 // opus_b200_enc.cu -- batched CELT-only Opus ENCODER for sm_100a: kernel + C ABI (include/opus_b200.h, ob_encoder_*).
 //
-// First GPU mapping of the encoder: ONE THREAD PER STREAM runs the whole per-stream encoder (enc_*.cuh) for the F frames
-// of a call, state and working buffers in global memory.  This translation unit is compiled with -fmad=false so that the
-// float decision heuristics round exactly like the reference's C code (a fused multiply-add changes e.g. which pitch lag
-// or which PVQ pulse wins); the decoder TU keeps FMA contraction.  Streams are independent: no collective, one ObEncoder
+// GPU mapping: ONE WARP PER STREAM (enc_frame.cuh, enc_analysis.cuh, enc_quant.cuh).  The warp runs the stream's frames in order --
+// every encoder decision feeds the range coder and the inter-frame float state, so there is no stateless pass to split off as in
+// the decoder -- with warp-uniform control flow: scalars and the coder registers are replicated in every lane, vectors are strided
+// over the lanes, cross-lane work goes through ob_coop.cuh (reductions, arg-max, recurrence scans).  Resident warps pull streams
+// from a work counter, so the long work vectors need one slot per RESIDENT warp (they stay in L2) and not one per stream.
+// This translation unit is compiled with -fmad=false: the float decision heuristics then round like the host emulation of the same
+// source (tests/host_emul), which is what the packets are checked against.  Streams are independent: no collective, one ObEncoder
 // per GPU over disjoint stream ranges.
 #include <cuda_runtime.h>
 #include <stdio.h>
@@ -14,49 +17,61 @@
 #include "../../include/opus_b200.h"
 #include "enc_frame.cuh"
 
-struct ObEncStream {           // everything one stream owns on the device
+struct ObEncStream {           // the scalar state one stream owns on the device (its vectors: ObEncHist)
     ObOpusEncState os;
     ObEncState st;
 };
 
-#define OB_ENC_THREADS 32
-// The per-stream working set (ObEncScratch, ~76 KB) and the stream's state live in LOCAL memory for the duration of the launch:
-// CUDA interleaves local memory across the lanes of a warp, so when the 32 streams of a warp run the same loop (pre-emphasis,
-// pitch cross-correlation, MDCT, band energies ...) element i of every lane's array sits in one 128-byte line -- the accesses
-// coalesce without any change to the per-stream code.  (With the scratch in global memory, one array per stream, every load of
-// a warp touched 32 different lines: 112 ms per frame at 16384 streams.)
-__global__ void __launch_bounds__(OB_ENC_THREADS)
+#define OB_ENC_THREADS 32             // ob_k_analysis: one thread per stream
+#ifndef OB_ENC_WARPS
+#define OB_ENC_WARPS 16               // ob_k_encode: warps (= streams in flight) per block; 16 x 13.2 KB of shared memory = one block per SM
+#endif
+struct ObEncBlockShared {
+    ObEncShared sh[OB_ENC_WARPS];
+    int progress[OB_ENC_WARPS];       // ObWarpPaced: how far each warp of the block has come
+    int base_stream;
+};
+__global__ void __launch_bounds__(32 * OB_ENC_WARPS, 1)
 ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *__restrict__ lens, uint32_t *__restrict__ ranges,
-            ObEncStream *__restrict__ streams, const ObAnalysisInfo *__restrict__ info, ObTonalState *__restrict__ tonal, float *__restrict__ delay,
-            ObOpusEncCfg cfg, int S, int F,
-            int frame_size, int max_bytes, int lanes, int f0, int Fc)
+            ObEncStream *__restrict__ streams, ObEncHist *__restrict__ hist, ObEncWork *__restrict__ work, int *__restrict__ counter,
+            const ObAnalysisInfo *__restrict__ info, ObTonalState *__restrict__ tonal, float *__restrict__ delay,
+            ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes, int f0, int Fc, int paced)
 {
-    // Only the first `lanes` threads of each warp carry a stream (tuning knob).  Spreading the streams over more, partly filled,
-    // warps was tried to hide the local-memory latency this kernel is bound by (ncu: 0.26 warp-instructions/cycle/SM, 8.6 of 13
-    // stall cycles on long-scoreboard) -- it is SLOWER: a half-filled warp still occupies whole 128-byte local-memory lines,
-    // so the L1/L2 capacity per stream halves.  Full warps (lanes = 32) are the default.
-    if ((int)threadIdx.x >= lanes) return;
-    const int s = blockIdx.x * lanes + threadIdx.x;
-    if (s >= S) return;
-    ObEncScratch sc;      // not initialised: no stage reads what it (or an earlier frame) has not written -- tests/test_host_emul.py runs the
-                          // same code with the work area filled with NaN patterns before every frame
-    ObEncStream es = streams[s];
-    es.os.delay = delay ? delay + (size_t)s * OB_ENC_BUFFER * es.st.channels : nullptr;      // AUDIO / VOIP: the 4 ms delay compensation, state in global memory
-    es.os.tonal = tonal ? tonal + s : nullptr;                 // packets longer than 20 ms run the analysis inline, on the state in global memory
-    const int CC = es.st.channels;
-    // NOTE: the frame counter is deliberately volatile.  The loop body is one huge divergent region; with a plain `int f`
-    // nvcc 12.9 keeps f in a UNIFORM register, and lanes that fall behind re-execute the shared increment -- frames get
-    // skipped / mis-indexed whenever lanes of a warp diverge (found on B200: fine with 1-4 identical lanes, wrong with 5+).
-    for (volatile int f = f0; f < f0 + Fc; f++) {              // this launch covers the frame window [f0, f0+Fc) of a [S][F] batch
-        const size_t w = (size_t)s * F + f;
-        ObAnalysisInfo an;                                      // computed ahead of this kernel by ob_k_analysis (complexity >= 7)
-        if (info) an = info[w];
-        const int n = ob_opus_encode(cfg, es.os, es.st, sc, pcm + w * (size_t)frame_size * CC, frame_size, out + w * (size_t)max_bytes, max_bytes,
-                                     info ? &an : nullptr);
-        lens[w] = n;
-        if (ranges) ranges[w] = n > 0 ? es.st.final_range : 0;
+    extern __shared__ __align__(16) unsigned char ob_enc_smem[];
+    ObEncBlockShared &bs = *reinterpret_cast<ObEncBlockShared *>(ob_enc_smem);
+    const int nw = (int)(blockDim.x >> 5), w = (int)(threadIdx.x >> 5);
+    const ObWarpPaced g(bs.progress, paced ? nw : 1);
+    ObEncShared &sh = bs.sh[w];
+    ObEncWork &wk = work[blockIdx.x * nw + w];
+    for (;;) {
+        // the block pulls nw consecutive streams, one per warp; its warps then walk the frames side by side (ObWarpPaced)
+        __syncthreads();
+        if (threadIdx.x == 0) bs.base_stream = atomicAdd(counter, nw);
+        if (g.lane == 0) bs.progress[w] = 0;
+        __syncthreads();
+        const int s = bs.base_stream + w;
+        if (bs.base_stream >= S) break;
+        if (s >= S) { g.publish(0x7fffffff); continue; }          // a tail block: this warp has nothing to do and must hold nobody up
+        ObEncStream es = streams[s];
+        es.os.delay = delay ? delay + (size_t)s * OB_ENC_BUFFER * es.st.channels : nullptr;      // AUDIO / VOIP: the 4 ms delay compensation, state in global memory
+        es.os.tonal = tonal ? tonal + s : nullptr;                 // packets longer than 20 ms run the analysis inline (lane 0), on the state in global memory
+        const int CC = es.st.channels;
+        ob_enc_load_hist(g, sh, wk, hist[s]);
+        for (int f = f0; f < f0 + Fc; f++) {                       // this launch covers the frame window [f0, f0+Fc) of a [S][F] batch
+            const size_t wi = (size_t)s * F + f;
+            ObAnalysisInfo an;                                      // computed ahead of this kernel by ob_k_analysis (complexity >= 7)
+            if (info) an = info[wi];
+            const int n = ob_opus_encode(g, cfg, es.os, es.st, sh, wk, pcm + wi * (size_t)frame_size * CC, frame_size, out + wi * (size_t)max_bytes, max_bytes,
+                                         info ? &an : nullptr, (f - f0 + 1) * 512);
+            if (g.lane == 0) {
+                lens[wi] = n;
+                if (ranges) ranges[wi] = n > 0 ? es.st.final_range : 0;
+            }
+        }
+        g.publish(0x7fffffff);                                      // done with this stream: wait for nobody, hold nobody up
+        ob_enc_store_hist(g, sh, wk, hist[s]);
+        if (g.lane == 0) streams[s] = es;
     }
-    streams[s] = es;
 }
 
 // The Opus-layer signal analysis (enc_tonal.cuh) depends on nothing but the input PCM and its own state, so it does not have to sit
@@ -97,20 +112,26 @@ __global__ void ob_k_i16_to_f32(const int16_t *__restrict__ in, float *__restric
     if (i < n) out[i] = (1.0f / 32768) * (float)in[i];
 }
 
-__global__ void ob_k_enc_reset(ObEncStream *streams, float *delay, const int32_t *idx, int n, int S, int channels)
+__global__ void ob_k_enc_reset(ObEncStream *streams, ObEncHist *hist, float *delay, const int32_t *idx, int n, int S, int channels)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.x;                                      // one block per stream to reset
     if (k >= n) return;
     const int s = idx ? idx[k] : k;
     if (s < 0 || s >= S) return;
-    ObEncStream &es = streams[s];
-    es.st.channels = es.st.stream_channels = channels; es.st.end = 21; es.st.clip = 1; es.st.force_intra = 0; es.st.disable_inv = 0; es.st.disable_pf = 0;
-    ob_enc_reset(es.st);
-    es.os.stream_channels = channels; es.os.first = 1; es.os.auto_bandwidth = 0; es.os.bandwidth = 1105; es.os.hybrid_stereo_width_Q14 = 1 << 14;
-    es.os.voice_ratio = -1; es.os.detected_bandwidth = 0; es.os.tonal = nullptr;
-    es.os.prev_mode = 0; es.os.width_mem = ObStereoWidth{0, 0, 0, 0, 0}; es.os.delay = nullptr;
-    es.os.nb_no_activity_ms_Q1 = 0; es.os.peak_signal_energy = 0;
-    if (delay) for (int i = 0; i < OB_ENC_BUFFER * channels; i++) delay[(size_t)s * OB_ENC_BUFFER * channels + i] = 0;
+    if (threadIdx.x == 0) {
+        ObEncStream &es = streams[s];
+        es.st.channels = es.st.stream_channels = channels; es.st.end = 21; es.st.clip = 1; es.st.force_intra = 0; es.st.disable_inv = 0; es.st.disable_pf = 0;
+        ob_enc_reset(es.st);
+        es.os.stream_channels = channels; es.os.first = 1; es.os.auto_bandwidth = 0; es.os.bandwidth = 1105; es.os.hybrid_stereo_width_Q14 = 1 << 14;
+        es.os.voice_ratio = -1; es.os.detected_bandwidth = 0; es.os.tonal = nullptr;
+        es.os.prev_mode = 0; es.os.width_mem = ObStereoWidth{0, 0, 0, 0, 0}; es.os.delay = nullptr;
+        es.os.nb_no_activity_ms_Q1 = 0; es.os.peak_signal_energy = 0;
+    }
+    ObEncHist &h = hist[s];
+    for (int i = threadIdx.x; i < 2 * OB_OVERLAP; i += blockDim.x) h.in_mem[i] = 0;
+    for (int i = threadIdx.x; i < 2 * OB_MAXPERIOD; i += blockDim.x) h.prefilter_mem[i] = 0;
+    for (int i = threadIdx.x; i < 2 * OB_NB; i += blockDim.x) { h.oldBandE[i] = 0; h.oldLogE[i] = h.oldLogE2[i] = -28.f; h.energyError[i] = 0; }
+    if (delay) for (int i = threadIdx.x; i < OB_ENC_BUFFER * channels; i += blockDim.x) delay[(size_t)s * OB_ENC_BUFFER * channels + i] = 0;
 }
 
 __global__ void ob_k_enc_gather(const ObEncStream *streams, uint32_t *ranges, int S)
@@ -128,12 +149,15 @@ __global__ void ob_k_enc_gather_dtx(const ObEncStream *streams, uint32_t *out, i
 }
 
 struct ObEncoder {
-    int S, CC, device, max_frames, lanes;
+    int S, CC, device, max_frames, slots;      // slots: resident blocks of ob_k_encode (OB_ENC_WARPS streams each)
     ObOpusEncCfg cfg;
     cudaStream_t stream, copy_stream, an_stream;
     cudaEvent_t ev[2], win_ev[4], an_ev[4], enc_done;
     bool timed, tonal_dirty;
     ObEncStream *d_streams;
+    ObEncHist *d_hist;                 // [S] the streams' vectors (pre-filter memory, overlap, band energies)
+    ObEncWork *d_work;                 // [slots] long work vectors, one per RESIDENT warp of ob_k_encode
+    int *d_counter;                    // work counter the resident warps pull stream indices from
     ObTonalState *d_tonal;             // [S] state of the signal analysis (complexity >= 7)
     float *d_delay;                    // [S][OB_ENC_BUFFER * channels] delay buffers of the AUDIO / VOIP applications (null for RESTRICTED_LOWDELAY)
     ObAnalysisInfo *d_info;            // [S][max_frames] its per-frame result, consumed by ob_k_encode
@@ -163,7 +187,6 @@ ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
     if (err == OB_OK) {
         memset(e, 0, sizeof(*e));
         e->S = n_streams; e->CC = channels; e->device = device; e->max_frames = max_frames;
-        e->lanes = 32;    // measured on B200, 16384 stereo c10 streams x 4 frames: 32 lanes 130 ms, 16: 166, 8: 329, 4: 464, 2: 726
         // defaults of opus_encoder_init (opus_encoder.c:202-297): VBR on, constrained, bitrate AUTO, complexity 9, 24-bit depth
         e->cfg.bitrate = -1000; e->cfg.complexity = 9; e->cfg.vbr = 1; e->cfg.vbr_constraint = 1; e->cfg.max_bandwidth = 1105;
         e->cfg.user_bandwidth = 0; e->cfg.force_channels = 0; e->cfg.packet_loss = 0; e->cfg.lsb_depth = 24; e->cfg.application = application;
@@ -174,6 +197,18 @@ ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         ok = ok && cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreateWithFlags(&e->win_ev[i], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_streams, sizeof(ObEncStream) * n_streams) == cudaSuccess;
+        ok = ok && cudaMalloc(&e->d_hist, sizeof(ObEncHist) * n_streams) == cudaSuccess;
+        if (ok) {   // one work slot per warp that can be resident at once (a persistent grid; streams are pulled from d_counter)
+            int per_sm = 0, sms = 0;
+            ok = cudaFuncSetAttribute(ob_k_encode, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ObEncBlockShared)) == cudaSuccess
+                 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ob_k_encode, 32 * OB_ENC_WARPS, sizeof(ObEncBlockShared)) == cudaSuccess
+                 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && per_sm > 0 && sms > 0;
+            e->slots = per_sm * sms;                               // resident blocks
+            const int need = (n_streams + OB_ENC_WARPS - 1) / OB_ENC_WARPS;
+            if (e->slots > need) e->slots = need;
+        }
+        ok = ok && cudaMalloc(&e->d_work, sizeof(ObEncWork) * e->slots * OB_ENC_WARPS) == cudaSuccess;
+        ok = ok && cudaMalloc(&e->d_counter, sizeof(int)) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&e->an_stream, cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreateWithFlags(&e->an_ev[i], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&e->enc_done, cudaEventDisableTiming) == cudaSuccess;
@@ -183,9 +218,6 @@ ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         if (application != 2051) ok = ok && cudaMalloc(&e->d_delay, sizeof(float) * OB_ENC_BUFFER * channels * n_streams) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_lens, sizeof(int32_t) * total) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_ranges, sizeof(uint32_t) * total) == cudaSuccess;
-        // No cudaLimitStackSize change: the kernel has no recursion or indirect calls, so its whole local frame (~94 KB per thread) is
-        // known at compile time and sized by the driver at launch; the process-wide stack limit (and with it the local-memory
-        // reservation of every other kernel in the process, e.g. the decoder's) stays at its default.
         if (!ok) {
             fprintf(stderr, "opus_b200: device allocation failed: %s\n", cudaGetErrorString(cudaGetLastError()));
             ob_encoder_destroy(e); e = nullptr; err = OB_ALLOC_FAIL;
@@ -202,7 +234,7 @@ void ob_encoder_destroy(ObEncoder *e)
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->an_stream) cudaStreamSynchronize(e->an_stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    cudaFree(e->d_streams); cudaFree(e->d_pcm); cudaFree(e->d_pcm16); cudaFree(e->d_out); cudaFree(e->d_lens); cudaFree(e->d_ranges);
+    cudaFree(e->d_streams); cudaFree(e->d_hist); cudaFree(e->d_work); cudaFree(e->d_counter); cudaFree(e->d_pcm); cudaFree(e->d_pcm16); cudaFree(e->d_out); cudaFree(e->d_lens); cudaFree(e->d_ranges);
     for (int i = 0; i < 2; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     for (int i = 0; i < 4; i++) { if (e->win_ev[i]) cudaEventDestroy(e->win_ev[i]); if (e->an_ev[i]) cudaEventDestroy(e->an_ev[i]); }
     if (e->enc_done) cudaEventDestroy(e->enc_done);
@@ -217,19 +249,24 @@ int32_t ob_encoder_reset(ObEncoder *e, const int32_t *idx, int32_t n)
 {
     if (!e || n < 0) return OB_BAD_ARG;
     OB_CUDA(cudaSetDevice(e->device));
+    // Legal with calls in flight: the reset is ordered on e->stream behind every encode kernel, and waits for the analysis stream's last kernel
+    if (e->an_stream) OB_CUDA(cudaStreamSynchronize(e->an_stream));
     int32_t *d_idx = nullptr;
     int count = e->S;
     if (idx) {
         if (n == 0) return OB_OK;
         count = n;
         OB_CUDA(cudaMalloc(&d_idx, sizeof(int32_t) * n));
-        OB_CUDA(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream));
     }
-    ob_k_enc_reset<<<(count + 63) / 64, 64, 0, e->stream>>>(e->d_streams, e->d_delay, d_idx, count, e->S, e->CC);
-    ob_k_tonal_reset<<<count, 128, 0, e->stream>>>(e->d_tonal, d_idx, count, e->S);
-    e->launches += 2;
-    OB_CUDA(cudaStreamSynchronize(e->stream));
-    if (d_idx) cudaFree(d_idx);
+    cudaError_t err = d_idx ? cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, e->stream) : cudaSuccess;
+    if (err == cudaSuccess) {
+        ob_k_enc_reset<<<count, 128, 0, e->stream>>>(e->d_streams, e->d_hist, e->d_delay, d_idx, count, e->S, e->CC);
+        ob_k_tonal_reset<<<count, 128, 0, e->stream>>>(e->d_tonal, d_idx, count, e->S);
+        e->launches += 2;
+        err = cudaStreamSynchronize(e->stream);
+    }
+    if (d_idx) cudaFree(d_idx);                                    // on every exit path
+    if (err != cudaSuccess) { fprintf(stderr, "opus_b200: encoder reset failed: %s\n", cudaGetErrorString(err)); return OB_INTERNAL_ERROR; }
     return OB_OK;
 }
 
@@ -320,10 +357,11 @@ static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size
     }
     if (f0 == 0) OB_CUDA(cudaEventRecord(e->ev[0], e->stream));
     if (an) OB_CUDA(cudaStreamWaitEvent(e->stream, e->an_ev[k & 3], 0));
-    int lanes = e->lanes;
-    if (const char *v = getenv("OB_ENC_LANES")) { const int t = atoi(v); if (t >= 1 && t <= OB_ENC_THREADS) lanes = t; }   // tuning aid
-    ob_k_encode<<<(e->S + lanes - 1) / lanes, OB_ENC_THREADS, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, an ? e->d_info : nullptr,
-                                                                               an_inline ? e->d_tonal : nullptr, e->d_delay, e->cfg, e->S, F, frame_size, max_bytes, lanes, f0, Fc);
+    OB_CUDA(cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
+    int paced = 1;
+    if (const char *v = getenv("OB_ENC_PACED")) paced = atoi(v) != 0;                                       // tuning aid
+    ob_k_encode<<<e->slots, 32 * OB_ENC_WARPS, sizeof(ObEncBlockShared), e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->d_hist, e->d_work, e->d_counter,
+            an ? e->d_info : nullptr, an_inline ? e->d_tonal : nullptr, e->d_delay, e->cfg, e->S, F, frame_size, max_bytes, f0, Fc, paced);
     if (f0 + Fc == F) { OB_CUDA(cudaEventRecord(e->ev[1], e->stream)); OB_CUDA(cudaEventRecord(e->enc_done, e->stream)); }
     OB_CUDA(cudaGetLastError());
     e->launches += 1;

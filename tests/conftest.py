@@ -37,6 +37,72 @@ def load_golden(name):
                 channels=ch, frame_size=fs, bitrate=br, vbr=vbr, dec_channels=dec_ch, name=name)
 
 
+_EMUL = None
+
+
+def emul_lib():
+    """tests/host_emul/libemul.so: the product's device code compiled by g++ for one host lane (TEST INFRASTRUCTURE, see emul.cpp).
+    Rebuilt when any source is newer.  The encoder entry points run in the reference's summation order by default and in the 32-lane
+    warp's order after emul_set_warp_order(1)."""
+    global _EMUL
+    if _EMUL is not None:
+        return _EMUL
+    import ctypes
+    import subprocess
+    emu = os.path.join(ROOT, "tests", "host_emul")
+    so, src = os.path.join(emu, "libemul.so"), os.path.join(emu, "emul.cpp")
+    csrc = os.path.join(ROOT, "opus_codec_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc)]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-o", so, src], check=True)
+    _EMUL = ctypes.CDLL(so)
+    return _EMUL
+
+
+def emul_warp_encode(pcm, fs, ch, br, vbr, cx, app=2051, extras=None, lsb_depth=24):
+    """One stream through the encoder's device code on the host, in the WARP's summation order: the packets the GPU must produce."""
+    import ctypes as C
+    import numpy as np
+    L = emul_lib()
+    pcm = np.ascontiguousarray(pcm, np.float32)
+    nf = pcm.size // (fs * ch)
+    out = np.zeros((nf, 1276), np.uint8); lens = np.zeros(nf, np.int32); rng = np.zeros(nf, np.uint32)
+    P = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    L.emul_set_warp_order(1)
+    L.emul_set_lsb_depth(lsb_depth)
+    if extras is not None:
+        L.emul_set_encoder_extras(*extras)
+    try:
+        r = L.emul_opus_encode_stream_app(P(pcm, C.c_float), nf, fs, ch, app, br, vbr, cx, P(out, C.c_ubyte), 1276, P(lens, C.c_int), P(rng, C.c_uint32))
+    finally:
+        L.emul_set_warp_order(0)
+        L.emul_set_lsb_depth(24)
+        if extras is not None:
+            L.emul_set_encoder_extras(0, 0, 0, 0, 0, 0)
+    return out, lens, rng, r
+
+
+def opus_compare(ref_pcm, test_pcm, channels):
+    """oracle/_ref/opus_compare (opus/src/opus_compare.c) on two float PCM arrays; returns (passed, weighted_error, text).  The reference file is
+    always read as stereo by the tool, so a mono reference is written with both channels equal."""
+    import subprocess
+    import tempfile
+    import numpy as np
+    import re
+    exe = os.path.join(ROOT, "oracle", "_ref", "opus_compare")
+    to16 = lambda x: np.clip(np.rint(np.asarray(x, np.float64).reshape(-1) * 32768), -32768, 32767).astype("<i2")
+    with tempfile.TemporaryDirectory() as d:
+        fa, fb = os.path.join(d, "ref.sw"), os.path.join(d, "test.sw")
+        a = to16(ref_pcm)
+        if channels == 1:
+            a = np.repeat(a, 2)
+        a.tofile(fa); to16(test_pcm).tofile(fb)
+        r = subprocess.run([exe] + (["-s"] if channels == 2 else []) + [fa, fb], capture_output=True, text=True)
+    text = (r.stdout + r.stderr).strip().splitlines()[-1]
+    m = re.search(r"rror is ([0-9.eE+-]+)", text)
+    return r.returncode == 0, float(m.group(1)) if m else float("nan"), text
+
+
 @pytest.fixture(scope="session")
 def have_ref():
     return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libopus_ref.so"))

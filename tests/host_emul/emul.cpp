@@ -85,53 +85,73 @@ void emul_packet_to_int16(float *x, int16_t *out, int n, int channels, float *so
 }
 
 // ---- encoder -------------------------------------------------------------------------------------------------------------
+// The warp-per-stream encoder source, compiled for ONE host lane in two summation orders (ob_coop.cuh): ObSolo = the reference's
+// order (bit-identical to the reference's C build), ObSoloW = the order of the 32-lane warp (what the GPU must produce).
 #include "../../opus_codec_b200/csrc/enc_frame.cuh"
-extern "C" {
-// CELT-level encode of one stream through the product's per-stream device code (one emulated thread); mirrors
-// ref_celt_encode_stream() in oracle/ref_shim.c (no TOC byte, coder created by the caller over `nbytes`).
-int emul_celt_encode_stream(const float *pcm, int nframes, int frame_size, int channels, int bitrate, int vbr, int complexity, int nbytes,
-                            unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
+static int g_warp_order = 0;
+extern "C" void emul_set_warp_order(int on) { g_warp_order = on; }
+
+struct EmulEnc {
+    ObEncState st; ObEncHist hist; ObEncShared sh; ObEncWork wk;
+};
+static void emul_poison(EmulEnc *e)
 {
-    ObEncState *st = (ObEncState *)calloc(1, sizeof(ObEncState));
-    ObEncScratch *S = (ObEncScratch *)calloc(1, sizeof(ObEncScratch));
+    // no stage may depend on what an earlier frame left in the work area: everything but the state carried between frames
+    if (!getenv("OB_EMUL_POISON")) return;
+    memset(e->wk.in, 0xFF, sizeof(e->wk.in)); memset(e->wk.pre, 0xFF, sizeof(e->wk.pre)); memset(e->wk.freq, 0xFF, sizeof(e->wk.freq));
+    memset(e->wk.X, 0xFF, sizeof(e->wk.X)); memset(e->wk.pcm_hp, 0xFF, sizeof(e->wk.pcm_hp)); memset(&e->wk.bw, 0xFF, sizeof(e->wk.bw));
+    memset(e->wk.multi_tmp, 0xFF, sizeof(e->wk.multi_tmp)); memset(e->wk.env, 0xFF, sizeof(e->wk.env));
+    memset(e->sh.A, 0xFF, sizeof(e->sh.A)); memset(&e->sh.u, 0xFF, sizeof(e->sh.u)); memset(e->sh.bandE, 0xFF, sizeof(e->sh.bandE));
+    memset(e->sh.bandLogE, 0xFF, sizeof(e->sh.bandLogE)); memset(e->sh.bandLogE2, 0xFF, sizeof(e->sh.bandLogE2)); memset(e->sh.error, 0xFF, sizeof(e->sh.error));
+    memset(e->sh.fine_quant, 0xFF, 8 * sizeof(e->sh.fine_quant)); memset(e->sh.bytes, 0xFF, sizeof(e->sh.bytes));
+}
+
+template <class G>
+static int emul_celt_encode_T(const float *pcm, int nframes, int frame_size, int channels, int bitrate, int vbr, int complexity, int nbytes,
+                              unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
+{
+    const G g;
+    EmulEnc *e = (EmulEnc *)calloc(1, sizeof(EmulEnc));
+    ObEncState *st = &e->st;
     st->channels = st->stream_channels = channels; st->complexity = complexity; st->vbr = vbr != 0; st->constrained_vbr = vbr == 2;
     st->bitrate = vbr ? bitrate : OB_BITRATE_MAX; st->lsb_depth = 24; st->end = 21; st->clip = 1; st->disable_inv = 0;
     ob_enc_reset(*st);
+    ob_enc_hist_reset(e->hist);
+    ob_enc_load_hist(g, e->sh, e->wk, e->hist);
     if (nbytes > max_bytes) nbytes = max_bytes;
     int rc = 0;
     for (int f = 0; f < nframes; f++) {
+        emul_poison(e);
         ObRangeEnc enc;
         enc.init(out + (size_t)f * max_bytes, (uint32_t)nbytes);
-        const int n = ob_celt_encode(*st, *S, pcm + (size_t)f * frame_size * channels, frame_size, nbytes, enc);
+        const int n = ob_celt_encode(g, *st, e->sh, e->wk, pcm + (size_t)f * frame_size * channels, frame_size, nbytes, enc);
         if (n < 0) { rc = n; break; }
         lens[f] = n;
         ranges[f] = st->rng;
     }
-    free(st); free(S);
+    free(e);
     return rc;
 }
-}
 extern "C" {
-// Opus-level encode (TOC byte included) of one stream; mirrors ref_encode_stream().  application: 2048 / 2049 / 2051.
-int emul_opus_encode_stream_app(const float *pcm, int nframes, int frame_size, int channels, int application, int bitrate, int vbr, int complexity,
-                                unsigned char *out, int max_bytes, int *lens, uint32_t *ranges);
-int emul_opus_encode_stream(const float *pcm, int nframes, int frame_size, int channels, int bitrate, int vbr, int complexity,
+// CELT-level encode of one stream through the product's per-stream device code (one emulated lane); mirrors
+// ref_celt_encode_stream() in oracle/ref_shim.c (no TOC byte, coder created by the caller over `nbytes`).
+int emul_celt_encode_stream(const float *pcm, int nframes, int frame_size, int channels, int bitrate, int vbr, int complexity, int nbytes,
                             unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
 {
-    return emul_opus_encode_stream_app(pcm, nframes, frame_size, channels, 2051, bitrate, vbr, complexity, out, max_bytes, lens, ranges);
+    return g_warp_order ? emul_celt_encode_T<ObSoloW>(pcm, nframes, frame_size, channels, bitrate, vbr, complexity, nbytes, out, max_bytes, lens, ranges)
+                        : emul_celt_encode_T<ObSolo>(pcm, nframes, frame_size, channels, bitrate, vbr, complexity, nbytes, out, max_bytes, lens, ranges);
 }
-static int g_signal = 0, g_pred_disabled = 0, g_phase_inv_disabled = 0, g_dtx = 0, g_fec = 0, g_loss = 0, g_last_in_dtx = 0;
-void emul_set_encoder_extras(int signal, int pred_disabled, int phase_inv_disabled, int dtx, int fec, int loss)
-{
-    g_signal = signal; g_pred_disabled = pred_disabled; g_phase_inv_disabled = phase_inv_disabled; g_dtx = dtx; g_fec = fec; g_loss = loss;
 }
-int emul_last_in_dtx(void) { return g_last_in_dtx; }
-int emul_opus_encode_stream_app(const float *pcm, int nframes, int frame_size, int channels, int application, int bitrate, int vbr, int complexity,
-                                unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
+static int g_signal = 0, g_pred_disabled = 0, g_phase_inv_disabled = 0, g_dtx = 0, g_fec = 0, g_loss = 0, g_last_in_dtx = 0, g_lsb_depth = 24;
+extern "C" void emul_set_lsb_depth(int d) { g_lsb_depth = d; }
+template <class G>
+static int emul_opus_encode_T(const float *pcm, int nframes, int frame_size, int channels, int application, int bitrate, int vbr, int complexity,
+                              unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
 {
-    ObEncState *st = (ObEncState *)calloc(1, sizeof(ObEncState));
-    ObEncScratch *S = (ObEncScratch *)calloc(1, sizeof(ObEncScratch));
-    ObOpusEncCfg cfg = {bitrate, complexity, vbr != 0, vbr == 2, 1105, 0, 0, g_loss, 24, application, g_signal, g_pred_disabled, g_phase_inv_disabled, g_dtx, g_fec, 0};
+    const G g;
+    EmulEnc *e = (EmulEnc *)calloc(1, sizeof(EmulEnc));
+    ObEncState *st = &e->st;
+    ObOpusEncCfg cfg = {bitrate, complexity, vbr != 0, vbr == 2, 1105, 0, 0, g_loss, g_lsb_depth, application, g_signal, g_pred_disabled, g_phase_inv_disabled, g_dtx, g_fec, 0};
     ObOpusEncState *osp = (ObOpusEncState *)calloc(1, sizeof(ObOpusEncState));
     ObOpusEncState &os = *osp;
     os.stream_channels = channels; os.first = 1; os.auto_bandwidth = 0; os.bandwidth = 1105; os.hybrid_stereo_width_Q14 = 1 << 14; os.voice_ratio = -1;
@@ -139,18 +159,38 @@ int emul_opus_encode_stream_app(const float *pcm, int nframes, int frame_size, i
     os.delay = application != 2051 ? (float *)calloc(OB_ENC_BUFFER * channels, sizeof(float)) : nullptr;
     st->channels = st->stream_channels = channels; st->end = 21; st->clip = 1;
     ob_enc_reset(*st);
+    ob_enc_hist_reset(e->hist);
+    ob_enc_load_hist(g, e->sh, e->wk, e->hist);
     int rc = 0;
     for (int f = 0; f < nframes; f++) {
-        if (getenv("OB_EMUL_POISON")) memset(S, 0xFF, sizeof(ObEncScratch));      // no stage may depend on what an earlier frame left in the work area
-        const int n = ob_opus_encode(cfg, os, *st, *S, pcm + (size_t)f * frame_size * channels, frame_size, out + (size_t)f * max_bytes, max_bytes);
+        emul_poison(e);
+        const int n = ob_opus_encode(g, cfg, os, *st, e->sh, e->wk, pcm + (size_t)f * frame_size * channels, frame_size, out + (size_t)f * max_bytes, max_bytes);
         if (n < 0) { rc = n; break; }
         lens[f] = n;
         ranges[f] = st->final_range;
     }
     g_last_in_dtx = cfg.use_dtx && os.nb_no_activity_ms_Q1 >= 10 * 20 * 2;
-    free(os.tonal); free(os.delay); free(st); free(S); free(osp);
+    free(os.tonal); free(os.delay); free(e); free(osp);
     return rc;
 }
+extern "C" {
+// Opus-level encode (TOC byte included) of one stream; mirrors ref_encode_stream().  application: 2048 / 2049 / 2051.
+int emul_opus_encode_stream_app(const float *pcm, int nframes, int frame_size, int channels, int application, int bitrate, int vbr, int complexity,
+                                unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
+{
+    return g_warp_order ? emul_opus_encode_T<ObSoloW>(pcm, nframes, frame_size, channels, application, bitrate, vbr, complexity, out, max_bytes, lens, ranges)
+                        : emul_opus_encode_T<ObSolo>(pcm, nframes, frame_size, channels, application, bitrate, vbr, complexity, out, max_bytes, lens, ranges);
+}
+int emul_opus_encode_stream(const float *pcm, int nframes, int frame_size, int channels, int bitrate, int vbr, int complexity,
+                            unsigned char *out, int max_bytes, int *lens, uint32_t *ranges)
+{
+    return emul_opus_encode_stream_app(pcm, nframes, frame_size, channels, 2051, bitrate, vbr, complexity, out, max_bytes, lens, ranges);
+}
+void emul_set_encoder_extras(int signal, int pred_disabled, int phase_inv_disabled, int dtx, int fec, int loss)
+{
+    g_signal = signal; g_pred_disabled = pred_disabled; g_phase_inv_disabled = phase_inv_disabled; g_dtx = dtx; g_fec = fec; g_loss = loss;
+}
+int emul_last_in_dtx(void) { return g_last_in_dtx; }
 }
 
 // ---- self-delimited framing (opus_packet_parse_impl / opus_repacketizer_out_range_impl with self_delimited = 1): the form multistream

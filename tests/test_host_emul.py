@@ -19,13 +19,21 @@ os.environ["OB_EMUL_POISON"] = "1"      # the encoder's work area is filled with
 
 @pytest.fixture(scope="module")
 def emul():
-    so = os.path.join(EMU, "libemul.so")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-Wno-unknown-pragmas", "-o", so, os.path.join(EMU, "emul.cpp")], check=True)
-    return C.CDLL(so)
+    from conftest import emul_lib
+    return emul_lib()
 
 
 def P(a, t):
     return a.ctypes.data_as(C.POINTER(t))
+
+
+def same_packets(a, al, b, bl):
+    """Packets equal byte for byte over their lengths (what lies beyond a packet's length in its slot is not part of the packet: the
+    reference leaves stale raw-bit bytes there when a VBR frame shrinks, the device code builds the payload in shared memory)."""
+    if not (np.asarray(al) == np.asarray(bl)).all():
+        return False
+    m = np.arange(a.shape[1])[None, :] < np.maximum(np.asarray(al), 0)[:, None]
+    return bool(((a == b) | ~m).all())
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -123,7 +131,7 @@ def test_encoder_pathological_input_bit_identical_to_reference(emul, have_ref, c
         b = np.zeros((nf, 1275), np.uint8); bl = np.zeros(nf, np.int32); br_ = np.zeros(nf, np.uint32)
         assert L.ref_encode_stream(P(pcm, C.c_float), nf, fs, ch, 2051, br, vbr, cx, P(a, C.c_ubyte), 1275, P(al, C.c_int), P(ar, C.c_uint32)) == 0
         assert emul.emul_opus_encode_stream(P(pcm, C.c_float), nf, fs, ch, br, vbr, cx, P(b, C.c_ubyte), 1275, P(bl, C.c_int), P(br_, C.c_uint32)) == 0
-        assert (al == bl).all() and (ar == br_).all() and np.array_equal(a, b), s
+        assert (ar == br_).all() and same_packets(a, al, b, bl), s
 
 
 def _fuzz_streams(seed, trials, nf=10, with_loss=True):
@@ -175,7 +183,7 @@ def test_encoder_device_code_bit_identical_to_reference_celt_encoder(emul, have_
         out = np.zeros((nf, 1275), np.uint8); lens = np.zeros(nf, np.int32); rng = np.zeros(nf, np.uint32)
         r = emul.emul_celt_encode_stream(P(np.ascontiguousarray(pcm), C.c_float), nf, fs, ch, br, vbr, cx, nb, P(out, C.c_ubyte), 1275, P(lens, C.c_int), P(rng, C.c_uint32))
         assert r == 0
-        assert (lens == ref_ln).all() and (rng == ref_rng).all() and np.array_equal(out, ref_pk)
+        assert (rng == ref_rng).all() and same_packets(out, lens, ref_pk, ref_ln)
 
 
 @pytest.mark.parametrize("ch,br,fs,vbr,cx", [(1, 64000, 960, 0, 5), (2, 96000, 960, 0, 6), (2, 96000, 960, 1, 5), (1, 24000, 480, 2, 6), (2, 24000, 960, 0, 4), (1, 12000, 960, 0, 6),
@@ -201,7 +209,7 @@ def test_encoder_opus_layer_bit_identical_to_reference(emul, have_ref, ch, br, f
         b = np.zeros((nf, 1275), np.uint8); bl = np.zeros(nf, np.int32); br_ = np.zeros(nf, np.uint32)
         assert L.ref_encode_stream(P(pcm, C.c_float), nf, fs, ch, 2051, br, vbr, cx, P(a, C.c_ubyte), 1275, P(al, C.c_int), P(ar, C.c_uint32)) == 0
         assert emul.emul_opus_encode_stream(P(pcm, C.c_float), nf, fs, ch, br, vbr, cx, P(b, C.c_ubyte), 1275, P(bl, C.c_int), P(br_, C.c_uint32)) == 0
-        assert (al == bl).all() and (ar == br_).all() and np.array_equal(a, b)
+        assert (ar == br_).all() and same_packets(a, al, b, bl)
 
 
 @pytest.mark.parametrize("app,ch,br,fs,vbr,cx", [(2049, 2, 96000, 960, 0, 10), (2049, 1, 64000, 960, 1, 10), (2049, 2, 128000, 480, 0, 5), (2049, 1, 96000, 240, 2, 8),
@@ -235,7 +243,7 @@ def test_encoder_audio_and_voip_applications_bit_identical_while_celt_only(emul,
         celt = (a[:, 0] & 0x80) != 0
         n = nf if celt.all() else int(np.argmin(celt))            # frames before the reference's first SILK / hybrid packet
         assert rc == (0 if n == nf else -5)
-        assert (al[:n] == bl[:n]).all() and (ar[:n] == br_[:n]).all() and np.array_equal(a[:n], b[:n])
+        assert (ar[:n] == br_[:n]).all() and same_packets(a[:n], al[:n], b[:n], bl[:n])
         if br >= 96000:
             assert n == nf                                        # these configurations never leave CELT
 
@@ -266,7 +274,7 @@ def test_encoder_too_small_budgets_emit_the_reference_plc_frames(emul, have_ref,
             L.ref_set_encoder_force_celt(1)
         r1 = emul.emul_opus_encode_stream_app(P(pcm, C.c_float), nf, fs, ch, app, br, vbr, cx, P(b, C.c_ubyte), mb, P(bl, C.c_int), P(br_, C.c_uint32))
         assert r0 == r1 == (-2 if fs == 4800 else 0), (ch, br, fs, vbr, cx, mb)
-        assert (al == bl).all() and (ar == br_).all() and np.array_equal(a, b), (ch, br, fs, vbr, cx, mb)
+        assert (ar == br_).all() and same_packets(a, al, b, bl), (ch, br, fs, vbr, cx, mb)
 
 
 def _gappy_pcm(s, ch, n):
@@ -307,7 +315,7 @@ def test_encoder_ctls_signal_prediction_phase_inversion_dtx_fec(emul, have_ref, 
                 celt = (a[:, 0] & 0x80) != 0
                 n = nf if celt.all() else int(np.argmin(celt))
                 assert rc == (0 if n == nf else -5), (app, ch, br, fs, vbr, cx)
-                assert (al[:n] == bl[:n]).all() and (ar[:n] == br_[:n]).all() and np.array_equal(a[:n], b[:n]), (app, ch, br, fs, vbr, cx)
+                assert (ar[:n] == br_[:n]).all() and same_packets(a[:n], al[:n], b[:n], bl[:n]), (app, ch, br, fs, vbr, cx)
                 if n == nf:
                     assert L.ref_last_in_dtx() == emul.emul_last_in_dtx()
                 dtx_packets += int((bl[:n] == 1).sum())
