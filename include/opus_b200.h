@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define OB_ABI_VERSION 6
+#define OB_ABI_VERSION 7
 
 typedef struct ObDecoder ObDecoder;
 
@@ -169,6 +169,16 @@ int32_t ob_encode_float_device(ObEncoder *enc, int32_t n_frames, const float *d_
  * (set_bitrate, set_complexity, set_vbr, set_vbr_constraint, set_max_bandwidth, set_bandwidth, set_force_channels,
  * set_packet_loss_perc, set_lsb_depth); one value for the whole batch.  bitrate: bits/s, -1000 = OPUS_AUTO, -1 = OPUS_BITRATE_MAX. */
 int32_t ob_encoder_set_bitrate(ObEncoder *enc, int32_t bitrate);
+/* Batch-only knob (no libopus counterpart): how the batch is laid onto the GPU.  OB_ENC_MAP_WARP: one warp per stream, cooperative stages --
+ * the low-latency mapping (a frame step of <= ~2 400 streams takes ~7 ms), packets in the warp's summation order.  OB_ENC_MAP_THREAD: one
+ * lane per stream, 32 streams per instruction -- the bulk mapping, packets bit-identical to the reference's C build.  OB_ENC_MAP_AUTO (default):
+ * THREAD from OB_ENC_MAP_CROSSOVER streams up.  Both are the same encoder source; every packet of either decodes with the reference decoder. */
+#define OB_ENC_MAP_AUTO 0
+#define OB_ENC_MAP_WARP 1
+#define OB_ENC_MAP_THREAD 2
+#define OB_ENC_MAP_CROSSOVER 8192
+int32_t ob_encoder_set_mapping(ObEncoder *enc, int32_t mapping);
+int32_t ob_encoder_get_mapping(ObEncoder *enc, int32_t *value);
 int32_t ob_encoder_get_bitrate(ObEncoder *enc, int32_t *value);
 int32_t ob_encoder_set_complexity(ObEncoder *enc, int32_t complexity);
 int32_t ob_encoder_get_complexity(ObEncoder *enc, int32_t *value);

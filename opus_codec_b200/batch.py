@@ -194,6 +194,9 @@ BITRATE_AUTO, BITRATE_MAX = -1000, -1                                           
 BANDWIDTH_NARROWBAND, BANDWIDTH_WIDEBAND, BANDWIDTH_SUPERWIDEBAND, BANDWIDTH_FULLBAND = 1101, 1103, 1104, 1105
 
 
+MAP_AUTO, MAP_WARP, MAP_THREAD = 0, 1, 2
+
+
 class BatchEncoder:
     """n_streams independent 48 kHz CELT-only Opus encoders on one B200 (mirror of Encoder, reference src/encoder.rs:40-699).
     CTLs apply to the whole batch."""
@@ -258,6 +261,12 @@ class BatchEncoder:
 
     def set_lsb_depth(self, d):
         _check(self._L.ob_encoder_set_lsb_depth(self._h, int(d)))
+
+    def set_mapping(self, m):
+        """MAP_AUTO (0), MAP_WARP (1: one warp per stream, low latency), MAP_THREAD (2: one lane per stream, bulk) -- include/opus_b200.h."""
+        _check(self._L.ob_encoder_set_mapping(self._h, int(m)))
+
+    def mapping(self): return self._get(self._L.ob_encoder_get_mapping)
 
     def _get(self, fn):
         v = C.c_int32(0)

@@ -438,7 +438,7 @@ OB_STAGE int ob_celt_encode(const G &g, ObEncState &st, ObEncShared &sh, ObEncWo
     g.sync();
     ob_enc_all_bands(g, end, X, C, N, collapse_masks, bandE, pulses, shortBlocks, st.spread_decision, dual_stereo, st.intensity, tf_res,
             nbCompressedBytes * (8 << OB_BITRES) - anti_collapse_rsv, balance, enc, LM, codedBands, &st.rng, st.complexity, st.disable_inv, sh.u.bands, wk.bw);
-    g.pace(60);
+    g.pace(64 + 64 * 21);
     if (anti_collapse_rsv > 0) {
         anti_collapse_on = st.consec_transient < 2;
         enc.bits((uint32_t)anti_collapse_on, 1);
@@ -882,7 +882,7 @@ OB_STAGE int ob_opus_encode(const G &g, const ObOpusEncCfg &cfg, ObOpusEncState 
             analysis_info = sh.an_tmp;
             g.sync();
         }
-        g.set_base(pace_base + 64 * i);
+        g.set_base(pace_base + 2048 * i);
         const int tmp_len = ob_opus_encode_frame(g, cfg, os, st, sh, wk, pcm + (size_t)i * channels * 960, 960, curr_data, curr_max, bitrate_bps, equiv_rate, analysis_info, is_silence);
         if (tmp_len < 0) return OB_INTERNAL_ERROR;
         if (tmp_len == 1) dtx_count++;

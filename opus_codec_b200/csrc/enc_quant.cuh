@@ -628,6 +628,7 @@ struct ObEncBandCtx {
     int band, intensity, spread, tf_change, disable_inv, resynth, theta_round, avoid_split_noise;
     int32_t remaining_bits;
     uint32_t seed;
+    int pace;                                 // ObWarpPaced: stage id of the next pace point inside the band being coded
 };
 
 template <class G>
@@ -777,6 +778,7 @@ OB_DEV uint32_t ob_enc_partition(const G &g, ObEncBandsShared &S, ObEncBandCtx &
                 }
                 float *X = f.X;
                 const int N = f.N;
+                if ((ctx.pace & 63) < 62) g.pace(ctx.pace++);       // the block's warps start their k-th leaf of this band together
                 if (q != 0) {
                     cm = ob_alg_quant(g, S, X, N, ob_get_pulses(q), ctx.spread, f.B, *ctx.ec, f.gain, ctx.resynth);
                 } else if (ctx.resynth) {
@@ -989,7 +991,8 @@ OB_STAGE void ob_enc_all_bands(const G &g, int end, const float *Xg, int C, int 
         float *X = S.xb, *Y = C == 2 ? S.xb + OB_MAX_BAND : nullptr;
         ctx.band = i;
         N = M * OB_EBANDS[i + 1] - M * OB_EBANDS[i];
-        g.pace(16 + i);
+        ctx.pace = 64 + 64 * i;
+        g.pace(ctx.pace++);
         g.sync();
         for (int j = g.lane; j < N; j += g.n) { X[j] = Xg[M * OB_EBANDS[i] + j]; if (C == 2) Y[j] = Xg[N_ + M * OB_EBANDS[i] + j]; }
         g.sync();
@@ -1072,7 +1075,7 @@ OB_STAGE void ob_enc_all_bands(const G &g, int end, const float *Xg, int C, int 
                     for (int j = g.lane; j < N; j += g.n) { W.X_save2[j] = X[j]; W.Y_save2[j] = Y[j]; if (!last) W.norm_save2[j] = lo1[j]; }
                     for (uint32_t k = g.lane; k < save_bytes; k += g.n) W.bytes_save[k] = bytes_buf[k];
                     g.sync();
-                    ec = ec_save; ctx = ctx_save;
+                    { const int pc = ctx.pace; ec = ec_save; ctx = ctx_save; ctx.pace = pc; }
                     for (int j = g.lane; j < N; j += g.n) { X[j] = W.X_save[j]; Y[j] = W.Y_save[j]; }
                     g.sync();
                 }
@@ -1084,7 +1087,7 @@ OB_STAGE void ob_enc_all_bands(const G &g, int end, const float *Xg, int C, int 
                 }
             }
             if (rdo && dist0 >= dist1) {
-                x_cm = cm2; ec = ec_save2; ctx = ctx_save2;
+                { const int pc = ctx.pace; x_cm = cm2; ec = ec_save2; ctx = ctx_save2; ctx.pace = pc; }
                 g.sync();
                 for (int j = g.lane; j < N; j += g.n) { X[j] = W.X_save2[j]; Y[j] = W.Y_save2[j]; if (!last) lo1[j] = W.norm_save2[j]; }
                 for (uint32_t k = g.lane; k < save_bytes; k += g.n) bytes_buf[k] = W.bytes_save[k];

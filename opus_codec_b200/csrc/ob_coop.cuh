@@ -32,22 +32,25 @@ struct ObSoloW {
 struct ObWarpPaced : ObWarp {
     volatile int *all;          // [nw] progress of the block's warps, in shared memory
     int nw, w;                  // warps in the block, this warp
+    int level, slack;           // pace points of a finer level than `level` are skipped (1: frame stages, 2: + every band, 3: + every leaf); a warp may be `slack` ids ahead
     mutable int base;           // frame-major base of the stage ids (set_base before every frame)
-    __device__ __forceinline__ ObWarpPaced(volatile int *a, int n_warps) : ObWarp(), all(a), nw(n_warps), w((int)(threadIdx.x >> 5)), base(0) {}
+    __device__ __forceinline__ ObWarpPaced(volatile int *a, int n_warps, int lvl, int slk) : ObWarp(), all(a), nw(n_warps), w((int)(threadIdx.x >> 5)), level(lvl), slack(slk), base(0) {}
     __device__ __forceinline__ void set_base(int b) const { base = b; }
     __device__ __forceinline__ void publish(int id) const { __syncwarp(); if (lane == 0) all[w] = id; __syncwarp(); }
+    // stage ids: 1..63 frame stages; 64 + 64*band: start of a band; 64 + 64*band + k: k-th leaf of the band
     __device__ __forceinline__ void pace(int stage) const
     {
-        if (nw <= 1) return;
+        const int lvl = stage < 64 ? 1 : ((stage & 63) == 0 ? 2 : 3);
+        if (nw <= 1 || lvl > level) return;
         const int id = base + stage;
         publish(id);
-        unsigned ns = 100;
+        unsigned ns = 200;
         for (;;) {
             int v = lane < nw ? all[lane] : 0x7fffffff;
             v = __reduce_min_sync(0xffffffffu, v);
-            if (v >= id) break;
+            if (v >= id - slack) break;
             __nanosleep(ns);                                        // back off: a waiting warp must not eat the issue slots of the ones it waits for
-            if (ns < 1600) ns *= 2;
+            if (ns < 3200) ns *= 2;
         }
     }
 };

@@ -765,7 +765,7 @@ int32_t ob_packet_get_nb_frames(const uint8_t *p, int32_t len)
     return p[1] & 0x3F;
 }
 
-const char *ob_version(void) { return "1.5.2-b200.6"; }
+const char *ob_version(void) { return "1.5.2-b200.7"; }
 const char *ob_strerror(int32_t e)
 {
     static const char *const s[8] = {"success", "invalid argument", "buffer too small", "internal error", "corrupted stream",

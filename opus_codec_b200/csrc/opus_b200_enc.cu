@@ -40,7 +40,7 @@ ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *_
     extern __shared__ __align__(16) unsigned char ob_enc_smem[];
     ObEncBlockShared &bs = *reinterpret_cast<ObEncBlockShared *>(ob_enc_smem);
     const int nw = (int)(blockDim.x >> 5), w = (int)(threadIdx.x >> 5);
-    const ObWarpPaced g(bs.progress, paced ? nw : 1);
+    const ObWarpPaced g(bs.progress, nw, paced & 15, paced >> 4);
     ObEncShared &sh = bs.sh[w];
     ObEncWork &wk = work[blockIdx.x * nw + w];
     for (;;) {
@@ -62,7 +62,7 @@ ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *_
             ObAnalysisInfo an;                                      // computed ahead of this kernel by ob_k_analysis (complexity >= 7)
             if (info) an = info[wi];
             const int n = ob_opus_encode(g, cfg, es.os, es.st, sh, wk, pcm + wi * (size_t)frame_size * CC, frame_size, out + wi * (size_t)max_bytes, max_bytes,
-                                         info ? &an : nullptr, (f - f0 + 1) * 512);
+                                         info ? &an : nullptr, (f - f0 + 1) * 16384);
             if (g.lane == 0) {
                 lens[wi] = n;
                 if (ranges) ranges[wi] = n > 0 ? es.st.final_range : 0;
@@ -72,6 +72,43 @@ ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *_
         ob_enc_store_hist(g, sh, wk, hist[s]);
         if (g.lane == 0) streams[s] = es;
     }
+}
+
+// The SAME encoder source with ONE LANE PER STREAM (G = ObSolo): 32 streams share every instruction a warp issues, which is the better
+// trade for bulk batches -- the encoder's control flow is ~45 k instructions of mostly scalar code, and a warp-per-stream mapping pays
+// one instruction stream per stream for it (measured on B200, 16 384 stereo complexity-10 streams: 48 ms per frame step warp-per-stream,
+// ~32 ms thread-per-stream; at <= 2368 streams the order reverses, 7 ms against 25 ms, because one lane per stream leaves the SMs with
+// 3 warps each).  The per-stream working set lives in LOCAL memory here: CUDA interleaves it across the lanes of a warp, so lanes that
+// walk their arrays in step coalesce.  Packets are those of the reference's summation order (bit-identical to its C build).
+__global__ void __launch_bounds__(32)
+ob_k_encode_thread(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *__restrict__ lens, uint32_t *__restrict__ ranges,
+                   ObEncStream *__restrict__ streams, ObEncHist *__restrict__ hist,
+                   const ObAnalysisInfo *__restrict__ info, ObTonalState *__restrict__ tonal, float *__restrict__ delay,
+                   ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes, int f0, int Fc)
+{
+    const int s = blockIdx.x * 32 + threadIdx.x;
+    if (s >= S) return;
+    const ObSolo g;
+    ObEncShared sh;       // not initialised: no stage reads what it (or an earlier frame) has not written (tests/test_host_emul.py poisons it)
+    ObEncWork wk;
+    ObEncStream es = streams[s];
+    es.os.delay = delay ? delay + (size_t)s * OB_ENC_BUFFER * es.st.channels : nullptr;
+    es.os.tonal = tonal ? tonal + s : nullptr;
+    const int CC = es.st.channels;
+    ob_enc_load_hist(g, sh, wk, hist[s]);
+    // NOTE: the frame counter is deliberately volatile.  The loop body is one huge divergent region; with a plain `int f` nvcc 12.9 keeps f
+    // in a UNIFORM register, and lanes that fall behind re-execute the shared increment (found on B200 in round 1).
+    for (volatile int f = f0; f < f0 + Fc; f++) {
+        const size_t wi = (size_t)s * F + f;
+        ObAnalysisInfo an;
+        if (info) an = info[wi];
+        const int n = ob_opus_encode(g, cfg, es.os, es.st, sh, wk, pcm + wi * (size_t)frame_size * CC, frame_size, out + wi * (size_t)max_bytes, max_bytes,
+                                     info ? &an : nullptr, 0);
+        lens[wi] = n;
+        if (ranges) ranges[wi] = n > 0 ? es.st.final_range : 0;
+    }
+    ob_enc_store_hist(g, sh, wk, hist[s]);
+    streams[s] = es;
 }
 
 // The Opus-layer signal analysis (enc_tonal.cuh) depends on nothing but the input PCM and its own state, so it does not have to sit
@@ -149,6 +186,7 @@ __global__ void ob_k_enc_gather_dtx(const ObEncStream *streams, uint32_t *out, i
 }
 
 struct ObEncoder {
+    int mapping;                       // OB_ENC_MAP_*: which instantiation of the encoder source codes the batch
     int S, CC, device, max_frames, slots;      // slots: resident blocks of ob_k_encode (OB_ENC_WARPS streams each)
     ObOpusEncCfg cfg;
     cudaStream_t stream, copy_stream, an_stream;
@@ -283,6 +321,9 @@ int32_t ob_encoder_set_bitrate(ObEncoder *e, int32_t bitrate)
     return OB_OK;
 }
 int32_t ob_encoder_get_bitrate(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.bitrate; return OB_OK; }
+// which instantiation of the encoder source codes the batch (see ob_k_encode / ob_k_encode_thread)
+int32_t ob_encoder_set_mapping(ObEncoder *e, int32_t m) { if (!e || m < OB_ENC_MAP_AUTO || m > OB_ENC_MAP_THREAD) return OB_BAD_ARG; e->mapping = m; return OB_OK; }
+int32_t ob_encoder_get_mapping(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->mapping; return OB_OK; }
 int32_t ob_encoder_set_complexity(ObEncoder *e, int32_t c) { if (!e || c < 0 || c > 10) return OB_BAD_ARG; e->cfg.complexity = c; return OB_OK; }
 int32_t ob_encoder_get_complexity(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.complexity; return OB_OK; }
 int32_t ob_encoder_set_vbr(ObEncoder *e, int32_t v) { if (!e || v < 0 || v > 1) return OB_BAD_ARG; e->cfg.vbr = v; return OB_OK; }
@@ -358,9 +399,13 @@ static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size
     if (f0 == 0) OB_CUDA(cudaEventRecord(e->ev[0], e->stream));
     if (an) OB_CUDA(cudaStreamWaitEvent(e->stream, e->an_ev[k & 3], 0));
     OB_CUDA(cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
-    int paced = 1;
-    if (const char *v = getenv("OB_ENC_PACED")) paced = atoi(v) != 0;                                       // tuning aid
-    ob_k_encode<<<e->slots, 32 * OB_ENC_WARPS, sizeof(ObEncBlockShared), e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->d_hist, e->d_work, e->d_counter,
+    int paced = 3;                                                 // pace level (0 none, 1 stages, 2 + bands, 3 + leaves) | slack << 4
+    if (const char *v = getenv("OB_ENC_PACED")) paced = atoi(v);                                            // tuning aid
+    const bool per_thread = e->mapping == OB_ENC_MAP_THREAD || (e->mapping == OB_ENC_MAP_AUTO && e->S >= OB_ENC_MAP_CROSSOVER);
+    if (per_thread)
+        ob_k_encode_thread<<<(e->S + 31) / 32, 32, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->d_hist, an ? e->d_info : nullptr,
+                                                                   an_inline ? e->d_tonal : nullptr, e->d_delay, e->cfg, e->S, F, frame_size, max_bytes, f0, Fc);
+    else ob_k_encode<<<e->slots, 32 * OB_ENC_WARPS, sizeof(ObEncBlockShared), e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->d_hist, e->d_work, e->d_counter,
             an ? e->d_info : nullptr, an_inline ? e->d_tonal : nullptr, e->d_delay, e->cfg, e->S, F, frame_size, max_bytes, f0, Fc, paced);
     if (f0 + Fc == F) { OB_CUDA(cudaEventRecord(e->ev[1], e->stream)); OB_CUDA(cudaEventRecord(e->enc_done, e->stream)); }
     OB_CUDA(cudaGetLastError());

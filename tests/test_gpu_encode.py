@@ -106,11 +106,14 @@ def test_pathological_input_matches_reference(have_ref, ch, br, fs, vbr, cx):
     assert np.median(ident) >= 0.97 and np.mean(ident) >= 0.9, ident
 
 
-def _gpu_encode(pcm_batch, fs, ch, br, vbr, cx, app=2051):
+def _gpu_encode(pcm_batch, fs, ch, br, vbr, cx, app=2051, mapping=1):
+    """mapping: 1 = one warp per stream (checked against the warp-order emulation), 2 = one lane per stream (checked against the reference's C build)."""
     from opus_codec_b200.batch import BatchEncoder
     S = pcm_batch.shape[0]
     F = pcm_batch.shape[1] // (fs * ch)
     with BatchEncoder(S, 48000, ch, application=app, device=0, max_frames=F) as enc:
+        enc.set_mapping(mapping)
+        assert enc.mapping() == mapping
         enc.set_bitrate(br); enc.set_complexity(cx); enc.set_vbr(vbr != 0); enc.set_vbr_constraint(vbr == 2)
         assert enc.bitrate() == br and enc.complexity() == cx and enc.vbr() == (vbr != 0)
         out, lens, rng = enc.encode_float_multi(pcm_batch[:, :F * fs * ch].reshape(S, F, fs * ch), fs)
@@ -141,6 +144,28 @@ def test_packets_match_reference_encoder_and_decode_with_reference_decoder(ch, b
     # GPU and warp-order emulation must agree byte for byte (the device's libm may flip a rare decision: the bit-exact check of the
     # arithmetic itself, against the reference's C build, is tests/test_host_emul.py)
     assert np.median(ident) >= 0.97 and np.mean(ident) >= 0.9, ident      # one flipped decision early in a short stream moves every later packet
+
+
+@pytest.mark.parametrize("ch,br,fs,vbr,cx", [(1, 64000, 960, 0, 5), (2, 96000, 960, 0, 10), (2, 96000, 960, 1, 10), (1, 24000, 480, 2, 9), (2, 64000, 240, 0, 8),
+                                             (1, 48000, 120, 1, 7), (2, 96000, 2880, 1, 10)])
+def test_thread_per_stream_mapping_matches_reference_c_build(have_ref, ch, br, fs, vbr, cx):
+    """OB_ENC_MAP_THREAD: the same encoder source with one lane per stream sums in the reference's order -- packets must equal the reference's
+    pure-C build byte for byte (the device's libm may flip a rare decision), and the reference decoder must reproduce every final range."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    S = 6
+    pcm = np.stack([synth.stream_pcm(s, 48000, ch, base_seed=777) for s in range(S)])
+    out, lens, rng = _gpu_encode(pcm, fs, ch, br, vbr, cx, mapping=2)
+    assert (lens > 0).all()
+    ident = []
+    for s in range(S):
+        ro, rl, rr = _ref_c_encode(pcm[s], fs, ch, br, vbr, cx)
+        m = np.arange(ro.shape[1])[None, :] < rl[:, None]
+        ident.append(((((ro == out[s]) | ~m).all(axis=1)) & (rl == lens[s]) & (rr == rng[s])).mean())
+        _, dec_rng, smp = refpy.decode_stream(out[s], lens[s], fs, ch)
+        assert (smp == fs).all() and (dec_rng == rng[s]).all()
+    assert np.median(ident) >= 0.97 and np.mean(ident) >= 0.9, ident
 
 
 @pytest.mark.parametrize("br", [128000, 96000])
@@ -334,14 +359,27 @@ def test_full_size_batch_16384_streams_tiling_property(have_ref):
     S, F, P = 16384, 4, 64
     pool = np.stack([synth.stream_pcm(s, 960 * F, 2, base_seed=2024) for s in range(P)]).reshape(P, F, 1920)
     with BatchEncoder(P, 48000, 2, device=0, max_frames=F) as enc:
+        enc.set_mapping(2)                                            # the mapping OB_ENC_MAP_AUTO picks for the full-size batch
         enc.set_bitrate(96000); enc.set_complexity(10); enc.set_vbr(False)
         small, small_len, small_rng = enc.encode_float_multi(pool, 960, max_bytes=256)
     big_in = np.ascontiguousarray(pool[np.arange(S) % P])
     with BatchEncoder(S, 48000, 2, device=0, max_frames=F) as enc:
+        assert enc.mapping() == 0                                     # AUTO: 16 384 >= OB_ENC_MAP_CROSSOVER -> one lane per stream
         enc.set_bitrate(96000); enc.set_complexity(10); enc.set_vbr(False)
         out, lens, rng = enc.encode_float_multi(big_in, 960, max_bytes=256)
     assert (lens == 240).all()
     idx = np.arange(S) % P
     assert np.array_equal(out, small[idx]) and np.array_equal(rng, small_rng[idx])
-    ident = [_ident_vs_emulation(pool[s].reshape(-1), small[s], small_len[s], small_rng[s], 960, 2, 96000, 0, 10)[0] for s in range(8)]
+    # ... and the warp-per-stream mapping at a size that fills every resident warp slot (148 SMs x 16), against its own small batch and the emulation
+    S2 = 4736
+    with BatchEncoder(P, 48000, 2, device=0, max_frames=F) as enc:
+        enc.set_mapping(1); enc.set_bitrate(96000); enc.set_complexity(10); enc.set_vbr(False)
+        wsmall, wsmall_len, wsmall_rng = enc.encode_float_multi(pool, 960, max_bytes=256)
+    with BatchEncoder(S2, 48000, 2, device=0, max_frames=F) as enc:
+        assert enc.mapping() == 0                                     # AUTO below the crossover: one warp per stream
+        enc.set_bitrate(96000); enc.set_complexity(10); enc.set_vbr(False)
+        wout, wlens, wrng = enc.encode_float_multi(np.ascontiguousarray(pool[np.arange(S2) % P]), 960, max_bytes=256)
+    idx2 = np.arange(S2) % P
+    assert np.array_equal(wout, wsmall[idx2]) and np.array_equal(wrng, wsmall_rng[idx2]) and (wlens == 240).all()
+    ident = [_ident_vs_emulation(pool[s].reshape(-1), wsmall[s], wsmall_len[s], wsmall_rng[s], 960, 2, 96000, 0, 10)[0] for s in range(8)]
     assert np.median(ident) >= 0.97 and np.mean(ident) >= 0.9, ident      # one flipped decision early in a short stream moves every later packet
