@@ -274,6 +274,14 @@ int32_t ob_repacketize_batch(int32_t device, int32_t n_streams, int32_t n_in, co
 int32_t ob_repacketize_batch_device(int32_t n_streams, int32_t n_in, const uint8_t *d_packets, const int32_t *d_offsets, const int32_t *d_lens,
                                     int32_t group, int32_t pad_to, uint8_t *d_out, int32_t max_bytes, int32_t *d_lens_out, void *cuda_stream);
 
+/* Test / debug access to the integer intermediate representation of the LAST decode call (csrc/ob_ir.h: coarse energy indices, tf, allocation,
+ * fine bits, collapse masks, leaves, pulse vectors) -- what BASELINE's "decoded energy indices and pulse vectors must match exactly" is checked
+ * on (tests/test_gpu_decode.py).  ob_debug_ir_layout: {sizeof(ObFrameIR), sizeof(ObFrameHdr), offsetof bands, leaves, iy, sizeof(ObLeaf),
+ * sizeof(ObBand), OB_MAX_LEAVES}.  ob_decoder_debug_read_ir: copies the record of (stream, frame slot) to out (>= sizeof(ObFrameIR) bytes).
+ * No libopus counterpart (the reference exposes these values only through the test taps of oracle/ref_shim.c). */
+int32_t ob_debug_ir_layout(int32_t *out, int32_t n);
+int32_t ob_decoder_debug_read_ir(ObDecoder *dec, int32_t stream, int32_t slot, void *out, int32_t nbytes);
+
 /* "1.5.2-b200.<abi>" : bitstream compatibility level + ABI version (cf. version() src/lib.rs:52-54). */
 const char *ob_version(void);
 const char *ob_strerror(int32_t error);

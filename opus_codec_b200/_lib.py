@@ -21,7 +21,7 @@ SYMBOLS = [
     "ob_decoder_channels", "ob_decoder_sample_rate", "ob_encoder_sample_rate", "ob_decoder_kernel_ms", "ob_decoder_launches", "ob_decoder_cuda_stream",
     "ob_decode_float_multi_async", "ob_decoder_wait", "ob_decode", "ob_decode_multi", "ob_decode_multi_async", "ob_encode", "ob_encode_multi", "ob_decoder_set_gain", "ob_decoder_get_gain", "ob_decoder_set_phase_inversion_disabled", "ob_decoder_get_phase_inversion_disabled", "ob_decoder_get_pitch", "ob_decoder_set_decode_fec", "ob_decoder_get_decode_fec",
     "ob_packet_get_nb_channels", "ob_packet_get_samples_per_frame", "ob_packet_get_bandwidth", "ob_packet_get_nb_frames",
-    "ob_version", "ob_strerror",
+    "ob_version", "ob_strerror", "ob_debug_ir_layout", "ob_decoder_debug_read_ir",
     "ob_packet_get_nb_samples", "ob_packet_has_lbrr", "ob_packet_parse", "ob_packet_pad", "ob_packet_unpad", "ob_multistream_packet_pad", "ob_multistream_packet_unpad", "ob_repacketizer_create", "ob_repacketizer_destroy", "ob_repacketizer_init", "ob_repacketizer_cat",
     "ob_repacketizer_get_nb_frames", "ob_repacketizer_out_range", "ob_repacketizer_out", "ob_repacketize_batch", "ob_repacketize_batch_device", "ob_pcm_soft_clip_batch",
     "ob_encoder_create", "ob_encoder_destroy", "ob_encode_float", "ob_encode_float_multi", "ob_encode_float_device",
@@ -76,6 +76,8 @@ def lib():
     L.ob_decode_multi_async.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp]; L.ob_decode_multi_async.restype = i32
     L.ob_decode_float_device.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, vp, i32]; L.ob_decode_float_device.restype = i32
     L.ob_decoder_final_range.argtypes = [vp, vp]; L.ob_decoder_final_range.restype = i32
+    L.ob_debug_ir_layout.argtypes = [vp, i32]; L.ob_debug_ir_layout.restype = i32
+    L.ob_decoder_debug_read_ir.argtypes = [vp, i32, i32, vp, i32]; L.ob_decoder_debug_read_ir.restype = i32
     L.ob_decoder_reset.argtypes = [vp, vp, i32]; L.ob_decoder_reset.restype = i32
     L.ob_decoder_last_packet_duration.argtypes = [vp, vp]; L.ob_decoder_last_packet_duration.restype = i32
     for n in ("ob_decoder_set_gain", "ob_decoder_set_phase_inversion_disabled"):

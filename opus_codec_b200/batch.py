@@ -71,6 +71,15 @@ class BatchDecoder:
         self.close()
 
     # -- decode -------------------------------------------------------------------------------------------
+    @staticmethod
+    def _check_packet_table(packets, offsets, lens):
+        """The C side copies lens[i] bytes from packets + offsets[i]: every (offset, length) pair must lie inside the packet buffer."""
+        pos = lens > 0
+        if (lens < 0).any() or (offsets[pos] < 0).any():
+            raise OpusError(BAD_ARG)
+        if pos.any() and int((offsets[pos].astype(np.int64) + lens[pos]).max()) > packets.size:
+            raise OpusError(BAD_ARG)
+
     def decode_float_multi(self, packets, offsets, lens, frame_size, out=None):
         """packets: u8 buffer; offsets/lens: i32 [S, F].  Returns (pcm f32 [S, F, frame_size*channels], samples i32 [S, F],
         final ranges u32 [S, F]).  frame_size is the per-channel capacity of each slot (output.len()/channels in
@@ -83,6 +92,10 @@ class BatchDecoder:
         if frame_size <= 0 or frame_size > MAX_FRAME_SAMPLES_48KHZ:
             raise OpusError(BAD_ARG)
         S, F = offsets.shape
+        self._check_packet_table(packets, offsets, lens)
+        if out is not None and (not isinstance(out, np.ndarray) or out.dtype != np.float32 or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]
+                                or out.size < S * F * frame_size * self.channels):
+            raise OpusError(BAD_ARG)
         pcm = out if out is not None else np.zeros((S, F, frame_size * self.channels), np.float32)
         samples = np.zeros((S, F), np.int32)
         ranges = np.zeros((S, F), np.uint32)
@@ -98,6 +111,7 @@ class BatchDecoder:
         if offsets.shape != lens.shape or offsets.ndim != 2 or offsets.shape[0] != self.n_streams or frame_size <= 0 or frame_size > MAX_FRAME_SAMPLES_48KHZ:
             raise OpusError(BAD_ARG)
         S, F = offsets.shape
+        self._check_packet_table(packets, offsets, lens)
         pcm = np.zeros((S, F, frame_size * self.channels), np.int16)
         samples = np.zeros((S, F), np.int32)
         ranges = np.zeros((S, F), np.uint32)
@@ -109,8 +123,11 @@ class BatchDecoder:
         (ideally over pinned memory) that must stay alive and untouched until wait() says the call has completed."""
         S, F = offsets.shape
         if offsets.dtype != np.int32 or lens.dtype != np.int32 or packets.dtype != np.uint8 or pcm.dtype != np.float32 \
-                or samples.dtype != np.int32 or ranges.dtype != np.uint32 or S != self.n_streams or pcm.size < S * F * frame_size * self.channels:
+                or samples.dtype != np.int32 or ranges.dtype != np.uint32 or S != self.n_streams or pcm.size < S * F * frame_size * self.channels \
+                or lens.shape != offsets.shape or samples.size < S * F or ranges.size < S * F \
+                or not all(a.flags["C_CONTIGUOUS"] for a in (packets, offsets, lens, pcm, samples, ranges)):
             raise OpusError(BAD_ARG)
+        self._check_packet_table(packets, offsets, lens)
         _check(self._L.ob_decode_float_multi_async(self._h, F, _vp(packets), _vp(offsets), _vp(lens), _vp(pcm), frame_size,
                                                    _vp(samples), _vp(ranges)))
 

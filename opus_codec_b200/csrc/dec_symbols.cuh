@@ -933,7 +933,10 @@ OB_DEV int ob_frame_packets(const uint8_t *packets, const int32_t *offsets, cons
     int16_t sizes[48];
     for (int f = 0; f < F; f++) {
         const int len = lens[f];
-        if (n >= cap) break;                                     // cannot happen for code-0 packets (cap >= F); checked by the host for the rest
+        // every packet still to come keeps one slot in reserve (cap >= F), so each packet of the call gets at least its error slot and
+        // its samples / range / status are always written: a multi-frame packet that would eat into the reserve is OB_BUFFER_TOO_SMALL
+        const int avail = cap - n - (F - 1 - f);
+        if (avail < 1) break;                                    // unreachable for cap >= F
         ObSlot one;
         one.off = 0; one.len = 0; one.toc = 0; one.flags = OB_SLOT_FIRST | OB_SLOT_LAST; one.pkt = (uint16_t)f; one.sample_off = 0; one.status = 0;
         if (len <= 0) {                                          // lost packet: conceal the whole slot (opus_decoder.c:684-688, :715-729)
@@ -953,7 +956,7 @@ OB_DEV int ob_frame_packets(const uint8_t *packets, const int32_t *offsets, cons
         }
         if (count < 0) one.status = count;
         else if (count * N > frame_size * ds) one.status = OB_BUFFER_TOO_SMALL;                                // opus_decoder.c:764-765
-        else if (n + count > cap) one.status = OB_BUFFER_TOO_SMALL;                                            // decoder created with too few frame slots
+        else if (count > avail) one.status = OB_BUFFER_TOO_SMALL;                                              // decoder created with too few frame slots
         if (one.status < 0) { slots[n++] = one; continue; }
         uint32_t off = (uint32_t)offsets[f] + (uint32_t)first_off;
         for (int i = 0; i < count; i++) {

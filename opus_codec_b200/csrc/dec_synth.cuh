@@ -475,9 +475,18 @@ OB_DEV float ob_soft_clip_channel(float *x, int N, int C, float a)
 // The int16 API (opus_decode, opus_decoder.c:861-894): soft clip over the whole packet, then FLOAT2INT16 (round to nearest even,
 // saturating).  x: the packet's float PCM (global memory, n samples per channel, written by this block); out: its int16 slot.
 template <class G>
-OB_DEV void ob_packet_to_int16(const G &g, float *x, int16_t *out, int n, int CC, float *softclip_mem)
+OB_DEV void ob_packet_to_int16(const G &g, float *x, int16_t *out, int n, int CC, float *softclip_mem, int soft = 1)
 {
     g.sync();                                                        // the frames' PCM stores are visible to the whole block
+    if (!soft) {                                                     // a concealed packet: opus_decode_native returns before its soft clip (opus_decoder.c:714-729)
+        for (int t = g.lane; t < n * CC; t += g.n) {
+            float v = x[t] * 32768.f;
+            v = fminf(32767.f, fmaxf(-32768.f, v));
+            out[t] = (int16_t)OB_F2I_RN(v);
+        }
+        g.sync();
+        return;
+    }
     float over = 0.f;
     for (int t = g.lane; t < n * CC; t += g.n) {
         const float v = fmaxf(-2.f, fminf(2.f, x[t]));

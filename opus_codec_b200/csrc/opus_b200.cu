@@ -198,8 +198,11 @@ ob_k_synth(const int32_t *__restrict__ stereo_frames, const ObFrameIR *__restric
             if (acc > 0) last_dur = acc;
             if (g.lane == 0) { samples[pk] = acc; if (ranges) ranges[pk] = final_range; }
             if (acc > 0) {                                          // opus_decoder.c:803-807: soft clip for the int16 API, else forget its state
-                if (pcm16) ob_packet_to_int16(g, pcm + pk * (size_t)frame_size * CC, pcm16 + pk * (size_t)frame_size * CC, acc, CC, sh.softclip_mem);
-                else if (g.lane == 0) sh.softclip_mem[0] = sh.softclip_mem[1] = 0.f;
+                // a whole-packet concealment (lost packet, or decode_fec on a CELT packet) leaves opus_decode_native through its len == 0
+                // branch (:714-729), before the soft clip and before softclip_mem is touched: saturate only, keep the clipper's state
+                const int concealed = sl.status > 0 && sl.toc == 0;
+                if (pcm16) ob_packet_to_int16(g, pcm + pk * (size_t)frame_size * CC, pcm16 + pk * (size_t)frame_size * CC, acc, CC, sh.softclip_mem, !concealed);
+                else if (g.lane == 0 && !concealed) sh.softclip_mem[0] = sh.softclip_mem[1] = 0.f;
             }
         }
         g.sync();
@@ -460,18 +463,25 @@ int32_t ob_decoder_reset(ObDecoder *d, const int32_t *idx, int32_t n)
 {
     if (!d || n < 0) return OB_BAD_ARG;
     OB_CUDA(cudaSetDevice(d->device));
+    // Legal with asynchronous calls in flight: they are drained first (their synthesis may still be running on the auxiliary stream
+    // over the very state this call clears).
+    { const int r = ob_decoder_wait(d, 0); if (r != OB_OK && r != OB_BAD_ARG) return r; }
+    if (d->aux_stream) OB_CUDA(cudaStreamSynchronize(d->aux_stream));
     int32_t *d_idx = nullptr;
     int count = d->S;
     if (idx) {
         if (n == 0) return OB_OK;
         count = n;
         OB_CUDA(cudaMalloc(&d_idx, sizeof(int32_t) * n));
-        OB_CUDA(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, d->stream));
     }
-    ob_k_reset<<<count, 128, 0, d->stream>>>(d->d_state, d->d_hist, d->d_ring, d_idx, count, d->S, d->CC);
-    d->launches += 1;
-    OB_CUDA(cudaStreamSynchronize(d->stream));
-    if (d_idx) cudaFree(d_idx);
+    cudaError_t err = d_idx ? cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * n, cudaMemcpyHostToDevice, d->stream) : cudaSuccess;
+    if (err == cudaSuccess) {
+        ob_k_reset<<<count, 128, 0, d->stream>>>(d->d_state, d->d_hist, d->d_ring, d_idx, count, d->S, d->CC);
+        d->launches += 1;
+        err = cudaStreamSynchronize(d->stream);
+    }
+    if (d_idx) cudaFree(d_idx);                                    // on every exit path
+    if (err != cudaSuccess) { fprintf(stderr, "opus_b200: decoder reset failed: %s\n", cudaGetErrorString(err)); return OB_INTERNAL_ERROR; }
     return OB_OK;
 }
 
@@ -637,6 +647,25 @@ int32_t ob_decode_float_multi_async(ObDecoder *d, int32_t n_frames, const uint8_
                                     float *pcm_out, int32_t frame_size, int32_t *samples_out, uint32_t *ranges_out)
 {
     return ob_decode_submit(d, n_frames, packets, offsets, lens, pcm_out, nullptr, frame_size, samples_out, ranges_out, 0);
+}
+
+// Debug / test access to the integer intermediate representation of the LAST call (ob_ir.h): the record the symbol kernel wrote for
+// (stream, slot).  Lets a test compare the decoded energy indices, allocation and pulse vectors with the reference's, exactly.
+int32_t ob_debug_ir_layout(int32_t *out, int32_t n)
+{
+    const int32_t v[8] = {(int32_t)sizeof(ObFrameIR), (int32_t)sizeof(ObFrameHdr), (int32_t)offsetof(ObFrameIR, bands), (int32_t)offsetof(ObFrameIR, leaves),
+                          (int32_t)offsetof(ObFrameIR, iy), (int32_t)sizeof(ObLeaf), (int32_t)sizeof(ObBand), OB_MAX_LEAVES};
+    if (!out || n < 8) return OB_BAD_ARG;
+    for (int i = 0; i < 8; i++) out[i] = v[i];
+    return OB_OK;
+}
+int32_t ob_decoder_debug_read_ir(ObDecoder *d, int32_t stream, int32_t slot, void *out, int32_t nbytes)
+{
+    if (!d || !out || stream < 0 || stream >= d->S || slot < 0 || slot >= d->max_frames || nbytes < (int32_t)sizeof(ObFrameIR)) return OB_BAD_ARG;
+    OB_CUDA(cudaSetDevice(d->device));
+    { const int r = ob_decoder_wait(d, 0); if (r != OB_OK) return r; }
+    OB_CUDA(cudaMemcpy(out, d->d_ir + (size_t)stream * d->max_frames + slot, sizeof(ObFrameIR), cudaMemcpyDeviceToHost));
+    return OB_OK;
 }
 
 int32_t ob_decoder_wait(ObDecoder *d, int32_t keep_in_flight)

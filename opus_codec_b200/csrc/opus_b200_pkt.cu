@@ -163,7 +163,7 @@ int32_t ob_multistream_packet_unpad(uint8_t *data, int32_t len, int32_t nb_strea
 
 // ---- batched: each `group` consecutive packets of a stream -> one packet ----------------------------------------------------------
 #define OB_RP_WARPS 4
-struct ObRpWarp { int lane; static constexpr int n = 32; };
+struct ObRpWarp { int lane; static constexpr int n = 32;  __device__ __forceinline__ void sync() const { __syncwarp(); } };
 
 __global__ void __launch_bounds__(OB_RP_WARPS * 32)
 ob_k_repacketize(const uint8_t *__restrict__ packets, const int32_t *__restrict__ offsets, const int32_t *__restrict__ lens, int S, int n_in, int group,

@@ -26,7 +26,12 @@
 
 #define OB_RP_MAX_EXT 128                 // extensions one output packet may carry on the DEVICE path (the host path sizes its list exactly)
 
-struct ObRpLanes1 { static constexpr int lane = 0, n = 1; };     // one thread does everything (host, tests)
+#ifdef __CUDACC__
+#define OB_RP_MEM __host__ __device__
+#else
+#define OB_RP_MEM
+#endif
+struct ObRpLanes1 { static constexpr int lane = 0, n = 1; OB_RP_MEM void sync() const {} };     // one thread does everything (host, tests)
 
 struct ObExt { int id, frame; const uint8_t *data; int len; };
 
@@ -330,7 +335,11 @@ OB_HD int ob_repack_out_range(const G &g, const ObRepack *rp, int begin, int end
         const int ret = ob_ext_parse(rp->paddings[i], rp->padding_len[i], all_ext + ext_count, &n);
         if (ret == OB_BUFFER_TOO_SMALL) return OB_UNIMPLEMENTED;          // more extensions than this build keeps (device path only)
         if (ret < 0) return OB_INTERNAL_ERROR;
-        for (int j = 0; j < n; j++) all_ext[ext_count + j].frame += i - begin;
+        // every lane of the group has just parsed the same records into the shared all_ext (identical stores); the frame fix-up is a
+        // read-modify-write, so exactly one lane does it, between two group barriers
+        g.sync();
+        if (w0) for (int j = 0; j < n; j++) all_ext[ext_count + j].frame += i - begin;
+        g.sync();
         ext_count += n;
     }
     uint8_t *ptr = data;

@@ -649,6 +649,11 @@ static unsigned collapse_mask_of(const int *iy, int N, int B)                   
     return mask;
 }
 
+/* pulse-vector tap: where decode_partition records every decoded iy[] (index = position in the frame's X, channel c at c*N) */
+static __thread int16_t *g_iy_tap = NULL;
+static __thread uint8_t *g_iy_set = NULL;
+static __thread const float *g_iy_base = NULL;
+
 static unsigned decode_partition(bctx *ctx, float *X, int N, int b, int B, float *lowband, int LM, float gain, int fill)
 {                                                                                              /* bands.c:943-1105 */
     const uint8_t *cache = pcache(ctx->band, LM);
@@ -697,6 +702,7 @@ static unsigned decode_partition(bctx *ctx, float *X, int N, int b, int B, float
         if (q != 0) {                           /* alg_unquant, vq.c:363-380 */
             int K = get_pulses(q), iy[176], j; uint32_t Ryy; float g;
             Ryy = co_cwrsi(N, K, rd_uint(ctx->ec, co_pvq_v(N, K)), iy);
+            if (g_iy_tap) for (j = 0; j < N; j++) { g_iy_tap[(X - g_iy_base) + j] = (int16_t)iy[j]; g_iy_set[(X - g_iy_base) + j] = 1; }
             g = (1.f / (float)sqrt((float)Ryy)) * gain;      /* normalise_residual, vq.c:121-141 */
             for (j = 0; j < N; j++) X[j] = g * iy[j];
             exp_rotation_inv(X, N, B, K, ctx->spread);
@@ -1319,9 +1325,11 @@ static int celt_decode_frame(co_decoder *st, const uint8_t *data, int len, float
 
     seed_in = st->rng;
     memset(collapse_masks, 0, sizeof(collapse_masks));
+    if (tap) { memset(tap->iy_set, 0, sizeof(tap->iy_set)); g_iy_tap = tap->iy; g_iy_set = tap->iy_set; g_iy_base = X; }
     decode_all_bands(start, end, X, C == 2 ? X + N : NULL, collapse_masks, pulses, shortBlocks, spread, dual_stereo,
             intensity, tf_res, len * (8 << BITRES) - anti_collapse_rsv, balance, &dec, LM, codedBands, &st->rng,
             CC == 1);
+    g_iy_tap = NULL;
     if (tap) { memcpy(tap->X, X, sizeof(float) * N); if (C == 2) memcpy(tap->X + N, X + N, sizeof(float) * N); tap->seed_out = st->rng; }
     if (anti_collapse_rsv > 0) anti_collapse_on = (int)rd_bits(&dec, 1);
     {   /* unquant_energy_finalise (quant_bands.c:516-542) */

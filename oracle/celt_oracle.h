@@ -36,6 +36,8 @@ typedef struct {
     float bandLogE[42];            /* energies after finalise */
     float freq[2 * 960];           /* denormalised MDCT coefficients */
     float presyn[2 * (960 + 120)]; /* IMDCT output (incl. overlap tail) before the comb filter */
+    int16_t iy[2 * 960];           /* decoded PVQ pulse vectors at their position in X (transformed domain of the leaf), where iy_set != 0 */
+    uint8_t iy_set[2 * 960];
 } co_tap_t;
 
 typedef struct co_decoder co_decoder;

@@ -25,7 +25,7 @@ class Tap(C.Structure):
         ("coarse_qi", C.c_int * 42), ("collapse_masks", C.c_uint8 * 42),
         ("seed_in", C.c_uint32), ("seed_out", C.c_uint32), ("final_range", C.c_uint32),
         ("X", C.c_float * 1920), ("bandLogE", C.c_float * 42), ("freq", C.c_float * 1920),
-        ("presyn", C.c_float * 2160),
+        ("presyn", C.c_float * 2160), ("iy", C.c_int16 * 1920), ("iy_set", C.c_uint8 * 1920),
     ]
 
 

@@ -36,6 +36,8 @@ unsafe extern "C" {
     pub fn ob_encode_float_multi(enc: *mut ObEncoder, n_frames: i32, pcm: *const f32, frame_size: i32, out: *mut u8,
                                  max_bytes: i32, lens_out: *mut i32, ranges_out: *mut u32) -> i32;
     pub fn ob_encoder_set_bitrate(enc: *mut ObEncoder, bitrate: i32) -> i32;
+    pub fn ob_encoder_set_mapping(enc: *mut ObEncoder, mapping: i32) -> i32;      // 0 auto, 1 one warp per stream, 2 one lane per stream
+    pub fn ob_encoder_get_mapping(enc: *mut ObEncoder, value: *mut i32) -> i32;
     pub fn ob_encoder_get_bitrate(enc: *mut ObEncoder, value: *mut i32) -> i32;
     pub fn ob_encoder_set_complexity(enc: *mut ObEncoder, complexity: i32) -> i32;
     pub fn ob_encoder_set_vbr(enc: *mut ObEncoder, vbr: i32) -> i32;
@@ -256,6 +258,12 @@ pub fn repacketize_batch(device: i32, n_streams: usize, n_in: usize, packets: &[
                          pad_to: usize, max_bytes: usize) -> Result<Vec<Result<Vec<u8>>>> {
     if offsets.len() != n_streams * n_in || lens.len() != offsets.len() || group == 0 || max_bytes == 0 {
         return Err(Error::BadArg);
+    }
+    // the C side reads lens[i] bytes at packets + offsets[i]: a safe wrapper must not let either run past the slice
+    for (&o, &l) in offsets.iter().zip(lens.iter()) {
+        if l < 0 || (l > 0 && (o < 0 || (o as usize) + (l as usize) > packets.len())) {
+            return Err(Error::BadArg);
+        }
     }
     let n_out = n_streams * n_in.div_ceil(group);
     let mut out = vec![0u8; n_out * max_bytes];

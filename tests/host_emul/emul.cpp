@@ -6,6 +6,15 @@
 #include "../../opus_codec_b200/csrc/dec_symbols.cuh"
 
 extern "C" {
+// the framing pass alone: status (0 decode, > 0 conceal, < 0 error) and packet index of every slot; returns the slot count
+int emul_frame_packets(const uint8_t *pkts, const int *offs, const int *lens, int F, int frame_size, int cap, int *status, int *pkt)
+{
+    ObSlot *sl = new ObSlot[cap > 0 ? cap : 1];
+    const int n = ob_frame_packets(pkts, offs, lens, F, frame_size, sl, cap);
+    for (int i = 0; i < n; i++) { status[i] = sl[i].status; pkt[i] = sl[i].pkt; }
+    delete[] sl;
+    return n;
+}
 int emul_ir_size() { return (int)sizeof(ObFrameIR); }
 int emul_hdr_size() { return (int)sizeof(ObFrameHdr); }
 void emul_decode_symbols(const uint8_t *pkt, int len, int dec_channels, int max_frame, ObFrameIR *ir)

@@ -30,7 +30,7 @@ def _decode_all(g, max_frames=None, streams=None):
 
 
 @pytest.mark.parametrize("name", golden_names())
-def test_golden_final_range_and_pcm(name):
+def test_golden_final_range_and_pcm(name, have_ref):
     from oracle import oraclepy
     g = load_golden(name)
     pcm, samples, ranges = _decode_all(g)
@@ -42,6 +42,12 @@ def test_golden_final_range_and_pcm(name):
         opcm, orng, _ = oraclepy.decode_stream(g["packets"][s], g["lens"][s], g["frame_size"], g["dec_channels"])
         assert (ranges[s] == orng).all()
         assert np.abs(pcm[s] - opcm).max() <= PCM_TOL
+    if have_ref:                                     # ... and EVERY stream against the unmodified reference decoder run here on the same packets
+        from oracle import refpy                     # (the stored fixture keeps the reference's PCM of one stream per configuration)
+        for s in range(g["packets"].shape[0]):
+            rpcm, rrng, rsmp = refpy.decode_stream(g["packets"][s], g["lens"][s], g["frame_size"], g["dec_channels"])
+            assert (rsmp == samples[s]).all() and (rrng == ranges[s]).all()
+            assert np.abs(pcm[s] - rpcm).max() <= PCM_TOL, (name, s)
 
 
 def test_streaming_one_frame_per_call_matches_multi():
@@ -308,6 +314,27 @@ def test_multiframe_packets(have_ref, name):
                 assert np.abs(pcm[s, f, :rs[f] * dc] - ref[f, :rs[f] * dc]).max() <= tol, (s, f)
 
 
+def test_multiframe_packets_with_too_few_frame_slots_report_buffer_too_small():
+    """A decoder created with max_frames == the number of packets, fed multi-frame packets: every packet must still get a status -- the
+    ones that fit decode, the ones whose frames would eat the slots of later packets are OPUS_BUFFER_TOO_SMALL (include/opus_b200.h), and
+    nothing is left unwritten (ob_frame_packets keeps one slot in reserve for every packet still to come)."""
+    from conftest import repacketize
+    from opus_codec_b200.batch import BatchDecoder
+    g = load_golden("cfg2_mono_20ms_64k_cbr")
+    fs, dc = g["frame_size"], g["dec_channels"]
+    pk0, ln0 = g["packets"][0], g["lens"][0]
+    fr = [bytes(pk0[f, :ln0[f]]) for f in range(8)]
+    for maxf, want in ((4, (2 * fs, -2, fs)), (3, (-2, -2, fs)), (5, (2 * fs, 2 * fs, fs))):
+        pkts = [repacketize(fr[0:2], 1), repacketize(fr[2:4], 1), fr[4]]
+        stride = max(len(p) for p in pkts)
+        buf = np.zeros((1, 3, stride), np.uint8); ln = np.zeros((1, 3), np.int32)
+        for i, p in enumerate(pkts):
+            buf[0, i, :len(p)] = np.frombuffer(p, np.uint8); ln[0, i] = len(p)
+        with BatchDecoder(1, 48000, dc, device=0, max_frames=maxf) as dec:
+            pcm, samples, ranges = dec.decode_float_multi(buf.reshape(-1), _offsets(1, 3, stride), ln, 2 * fs)
+        assert tuple(int(v) for v in samples[0]) == want, (maxf, samples)
+
+
 def test_int16_api_soft_clip_matches_reference(have_ref):
     """ob_decode_multi (Decoder::decode): with +12 dB of decode gain the signal clips, so the soft clipper and its packet-to-packet
     state are exercised; int16 PCM must equal the reference's up to rounding flips: the float paths differ by up to ~0.2 LSB after
@@ -338,6 +365,34 @@ def test_int16_api_soft_clip_matches_reference(have_ref):
             # and the float API afterwards forgets the clipper state (opus_decoder.c:806)
             f32, _, _ = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, fs)
             assert np.isfinite(f32).all()
+
+
+def test_int16_api_lost_packets_after_clipping_match_reference(have_ref):
+    """A lost packet right after a clipped one, int16 API: libopus leaves opus_decode_native through its len == 0 branch (opus_decoder.c:714-729),
+    i.e. BEFORE the soft clipper -- the concealment is only saturated and the clipper's carried state is not touched.  Concealed frames differ
+    between the reference's own builds by ~2e-3 of full scale (see the PLC test), so they get that tolerance; the packets after the loss must
+    again agree to +-1 LSB, which they only do if the clipper state was carried across the loss exactly as the reference carries it."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from oracle import refpy
+    from opus_codec_b200.batch import BatchDecoder
+    g = load_golden("cfg1_stereo_20ms_128k_cbr")
+    fs, dc = g["frame_size"], g["dec_channels"]
+    S, F, stride = g["packets"].shape
+    S, F = min(S, 3), min(F, 40)
+    pk = np.ascontiguousarray(g["packets"][:S, :F]); ln = g["lens"][:S, :F].copy()
+    lost = (7, 8, 20, 31)
+    ln[:, lost] = 0
+    with BatchDecoder(S, 48000, dc, device=0, max_frames=F) as dec:
+        dec.set_gain(3072)
+        pcm, samples, ranges = dec.decode_multi(pk.reshape(-1), _offsets(S, F, stride), ln, fs)
+    for s in range(S):
+        ref, rr, rs = refpy.decode_stream_i16(pk[s], ln[s], fs, dc, gain_q8=3072)
+        assert (samples[s] == rs).all() and (ranges[s] == rr).all()
+        d = np.abs(pcm[s].astype(np.int32) - ref.astype(np.int32)).reshape(F, -1)
+        for f in range(F):
+            near_loss = any(0 <= f - l <= 2 for l in lost)
+            assert d[f].max() <= (int(3e-3 * 32768 * 4) if near_loss else 1), (s, f, int(d[f].max()))
 
 
 @pytest.mark.parametrize("fs_out", [24000, 16000, 12000, 8000])
@@ -551,3 +606,67 @@ def test_single_frame_call_split_over_two_compute_streams_with_stereo_frames():
     with BatchDecoder(len(sub), 48000, 1, device=0, max_frames=F) as dec:
         p, smp, r = dec.decode_float_multi(np.ascontiguousarray(pk[sub]).reshape(-1), _offsets(len(sub), F, stride), ln[sub], 960)
     assert np.array_equal(p, out[sub]) and (r == rngs[sub]).all()
+
+
+class _IrHdr(__import__("ctypes").Structure):
+    import ctypes as _C
+    _fields_ = [("status", _C.c_int32), ("final_range", _C.c_uint32), ("n_leaves", _C.c_uint16), ("pf_pitch", _C.c_uint16),
+                ("LM", _C.c_uint8), ("C", _C.c_uint8), ("end", _C.c_uint8), ("flags", _C.c_uint8),
+                ("spread", _C.c_uint8), ("pf_tapset", _C.c_uint8), ("pf_qg", _C.c_uint8), ("coded_bands", _C.c_uint8),
+                ("intensity", _C.c_uint8), ("dual_stereo", _C.c_uint8), ("skip_in", _C.c_uint8), ("end_in", _C.c_uint8),
+                ("lcg_total", _C.c_uint32), ("seed_in", _C.c_uint32), ("loss_in", _C.c_int32), ("lastfs_in", _C.c_uint16), ("pad2", _C.c_uint16),
+                ("coarse_qi", _C.c_int16 * 42), ("pulses", _C.c_int16 * 21), ("fine_quant", _C.c_uint8 * 21), ("fine_q2", _C.c_uint8 * 42),
+                ("final_bit", _C.c_int8 * 42), ("collapse_masks", _C.c_uint8 * 42), ("tf_change", _C.c_int8 * 21), ("pad1", _C.c_uint8 * 3)]
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_integer_ir_on_the_device_matches_oracle_and_reference_taps(have_ref, name):
+    """BASELINE north_star: 'decoded energy indices and pulse vectors must match exactly'.  The symbol kernel's integer record of every frame
+    (csrc/ob_ir.h) is read back from the device (ob_decoder_debug_read_ir) and compared field by field with the oracle's taps -- coarse energy
+    indices, tf, PVQ bit allocation, fine-energy bits, collapse masks, spread / intensity / dual stereo / coded bands, post-filter parameters,
+    and every decoded pulse vector iy[] at its position -- and, where the compiled reference is present, with the values the REFERENCE
+    itself passed to quant_all_bands (the --wrap taps of oracle/ref_shim.c)."""
+    import ctypes as C
+    from opus_codec_b200 import _lib
+    from opus_codec_b200.batch import BatchDecoder
+    from oracle import oraclepy
+    L = _lib.lib()
+    lay = (C.c_int32 * 8)()
+    assert L.ob_debug_ir_layout(lay, 8) == 0
+    ir_size, hdr_size, _, _, iy_off = lay[0], lay[1], lay[2], lay[3], lay[4]
+    assert hdr_size == C.sizeof(_IrHdr)
+    g = load_golden(name)
+    fs, dc = g["frame_size"], g["dec_channels"]
+    S, F, stride = g["packets"].shape
+    S, F = min(S, 2), min(F, 30)
+    pk = np.ascontiguousarray(g["packets"][:S, :F]); ln = np.ascontiguousarray(g["lens"][:S, :F])
+    buf = C.create_string_buffer(ir_size)
+    with BatchDecoder(S, 48000, dc, device=0, max_frames=F) as dec:
+        dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, fs)
+        for s in range(S):
+            _, orng, _, taps = oraclepy.decode_stream(pk[s], ln[s], fs, dc, want_taps=True)
+            rtaps = None
+            if have_ref:
+                from oracle import refpy
+                rtaps = refpy.decode_stream(pk[s], ln[s], fs, dc, want_taps=True)[3]
+            for f in range(F):
+                assert L.ob_decoder_debug_read_ir(dec._h, s, f, buf, ir_size) == 0
+                h = _IrHdr.from_buffer_copy(buf.raw[:hdr_size]); t = taps[f]
+                C_, end = h.C, h.end
+                assert h.status == fs and h.final_range == int(orng[f]) and h.LM == t.LM and C_ == t.C and end == t.end
+                assert [h.coarse_qi[c * 21 + i] for c in range(C_) for i in range(end)] == [t.coarse_qi[c * 21 + i] for c in range(C_) for i in range(end)]
+                assert list(h.pulses)[:end] == list(t.pulses)[:end] and list(h.fine_quant)[:end] == list(t.fine_quant)[:end]
+                assert list(h.tf_change)[:end] == list(t.tf_res)[:end]
+                assert list(h.collapse_masks)[:C_ * end] == list(t.collapse_masks)[:C_ * end]
+                assert (h.spread, h.intensity, h.dual_stereo, h.coded_bands) == (t.spread, t.intensity, t.dual_stereo, t.coded_bands)
+                assert bool(h.flags & 8) == bool(t.pf_on) and (not t.pf_on or (h.pf_pitch, h.pf_tapset, h.pf_qg) == (t.pf_pitch, t.pf_tapset, t.pf_qg))
+                assert bool(h.flags & 2) == bool(t.transient) and bool(h.flags & 1) == bool(t.silence)
+                iy = np.frombuffer(buf.raw, np.int16, 1920, iy_off)
+                want = np.frombuffer(bytes(t.iy), np.int16); mask = np.frombuffer(bytes(t.iy_set), np.uint8) != 0
+                assert mask.any() or t.silence or ln[s, f] < 12
+                assert np.array_equal(iy[mask], want[mask]), (name, s, f)
+                if rtaps is not None and rtaps[f].n_qab == 1:
+                    r = rtaps[f]
+                    assert list(h.pulses)[:end] == list(r.pulses)[:end] and list(h.tf_change)[:end] == list(r.tf_res)[:end]
+                    assert list(h.collapse_masks)[:C_ * end] == list(r.collapse_masks)[:C_ * end]
+                    assert (h.spread, h.intensity, h.dual_stereo, h.coded_bands, h.seed_in) == (r.spread, r.intensity, r.dual_stereo, r.codedBands, r.seed_in)

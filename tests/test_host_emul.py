@@ -324,3 +324,90 @@ def test_encoder_ctls_signal_prediction_phase_inversion_dtx_fec(emul, have_ref, 
         L.ref_set_encoder_force_celt(1)
         emul.emul_set_encoder_extras(0, 0, 0, 0, 0, 0)
     assert (dtx_packets > 20) == bool(extras[3])
+
+
+def test_framing_pass_reserves_a_slot_for_every_packet(emul):
+    """ob_frame_packets with as many frame slots as packets: a multi-frame packet that would eat the slots of later packets is
+    OPUS_BUFFER_TOO_SMALL, and EVERY packet of the call gets at least one slot (so its samples / range are always written)."""
+    from conftest import repacketize
+    g = load_golden("cfg2_mono_20ms_64k_cbr")
+    fs = g["frame_size"]
+    pk0, ln0 = g["packets"][0], g["lens"][0]
+    fr = [bytes(pk0[f, :ln0[f]]) for f in range(8)]
+    pkts = [repacketize(fr[0:2], 1), repacketize(fr[2:4], 1), fr[4]]
+    buf = np.frombuffer(b"".join(pkts), np.uint8).copy()
+    lens = np.array([len(p) for p in pkts], np.int32)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int32)
+    for cap, want in ((4, [(0, 0), (0, 0), (-2, 1), (0, 2)]), (3, [(-2, 0), (-2, 1), (0, 2)]), (5, [(0, 0), (0, 0), (0, 1), (0, 1), (0, 2)])):
+        status = np.zeros(16, np.int32); pkt = np.zeros(16, np.int32)
+        n = emul.emul_frame_packets(P(buf, C.c_ubyte), P(offs, C.c_int), P(lens, C.c_int), 3, 2 * fs, cap, P(status, C.c_int), P(pkt, C.c_int))
+        assert [(int(status[i]), int(pkt[i])) for i in range(n)] == want, (cap, status[:n], pkt[:n])
+        assert set(pkt[:n]) == {0, 1, 2}
+
+
+@pytest.mark.parametrize("ch,br,fs,vbr,cx", [(2, 128000, 960, 0, 10), (2, 96000, 960, 0, 10), (1, 64000, 960, 1, 10), (2, 64000, 480, 2, 9), (1, 48000, 120, 1, 7),
+                                             (2, 96000, 2880, 1, 10)])
+def test_encoder_in_warp_summation_order_is_a_valid_encoder(emul, have_ref, ch, br, fs, vbr, cx):
+    """The encoder source evaluated in the 32-lane warp's order (ObSoloW: strided partial sums + butterfly, chunk-per-lane scans, lane
+    winners ranked by quotient) -- the packets the warp-per-stream GPU mapping must produce.  Not bit-identical to the reference's C build
+    (nor is the reference's own SSE build), so the gates are north_star's: the REFERENCE decoder accepts every packet with the encoder's
+    final range, and on BASELINE configs 1 / 3 the decoded audio passes the reference's opus_compare against the reference encoder's round trip."""
+    if not have_ref:
+        pytest.skip("oracle/_ref not built")
+    from conftest import emul_warp_encode, opus_compare
+    from opus_codec_b200 import synth
+    from oracle import refpy
+    L = refpy.lib_c()
+    u8p, i32p, u32p, f32p = (C.POINTER(C.c_ubyte), C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_float))
+    L.ref_encode_stream.argtypes = [f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_int, i32p, u32p]
+    for s in range(3):
+        pcm = np.ascontiguousarray(synth.stream_pcm(s, 48000 * 2, ch, base_seed=4242))
+        out, lens, rng, rc = emul_warp_encode(pcm, fs, ch, br, vbr, cx)
+        assert rc == 0 and (lens > 0).all()
+        ours, dec_rng, smp = refpy.decode_stream(out, lens, fs, ch)
+        assert (smp == fs).all() and (dec_rng == rng).all()
+        if fs == 960 and ch == 2 and vbr == 0:
+            nf = pcm.size // (fs * ch)
+            a = np.zeros((nf, 1276), np.uint8); al = np.zeros(nf, np.int32); ar = np.zeros(nf, np.uint32)
+            assert L.ref_encode_stream(P(pcm, C.c_float), nf, fs, ch, 2051, br, vbr, cx, P(a, C.c_ubyte), 1276, P(al, C.c_int), P(ar, C.c_uint32)) == 0
+            theirs, _, _ = refpy.decode_stream(a, al, fs, ch)
+            ok, err, text = opus_compare(theirs, ours, ch)
+            assert ok, (s, text)
+
+
+class _IrHdr(C.Structure):
+    _fields_ = [("status", C.c_int32), ("final_range", C.c_uint32), ("n_leaves", C.c_uint16), ("pf_pitch", C.c_uint16),
+                ("LM", C.c_uint8), ("C", C.c_uint8), ("end", C.c_uint8), ("flags", C.c_uint8),
+                ("spread", C.c_uint8), ("pf_tapset", C.c_uint8), ("pf_qg", C.c_uint8), ("coded_bands", C.c_uint8),
+                ("intensity", C.c_uint8), ("dual_stereo", C.c_uint8), ("skip_in", C.c_uint8), ("end_in", C.c_uint8),
+                ("lcg_total", C.c_uint32), ("seed_in", C.c_uint32), ("loss_in", C.c_int32), ("lastfs_in", C.c_uint16), ("pad2", C.c_uint16),
+                ("coarse_qi", C.c_int16 * 42), ("pulses", C.c_int16 * 21), ("fine_quant", C.c_uint8 * 21), ("fine_q2", C.c_uint8 * 42),
+                ("final_bit", C.c_int8 * 42), ("collapse_masks", C.c_uint8 * 42), ("tf_change", C.c_int8 * 21), ("pad1", C.c_uint8 * 3)]
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_symbol_pass_integer_ir_matches_oracle_taps(emul, name):
+    """The symbol kernel's device code (one emulated thread per frame, stateless) against the oracle's taps: energy indices, allocation,
+    tf, masks, flags and every pulse vector, exactly.  (The same comparison runs on the GPU in tests/test_gpu_decode.py.)"""
+    assert C.sizeof(_IrHdr) == emul.emul_hdr_size()
+    g = load_golden(name)
+    fs, dc = g["frame_size"], g["dec_channels"]
+    buf = C.create_string_buffer(emul.emul_ir_size())
+    iy_off = emul.emul_ir_size() - 2 * 1920
+    for s in range(min(2, g["packets"].shape[0])):
+        nf = min(40, g["packets"].shape[1])
+        pk = np.ascontiguousarray(g["packets"][s, :nf]); ln = np.ascontiguousarray(g["lens"][s, :nf])
+        _, orng, _, taps = oraclepy.decode_stream(pk, ln, fs, dc, want_taps=True)
+        for f in range(nf):
+            row = np.ascontiguousarray(pk[f])
+            emul.emul_decode_symbols(P(row, C.c_ubyte), int(ln[f]), dc, 960, buf)
+            h = _IrHdr.from_buffer_copy(buf.raw[:C.sizeof(_IrHdr)]); t = taps[f]
+            C_, end = h.C, h.end
+            assert h.status == fs and h.final_range == int(orng[f]) and (h.LM, C_, end) == (t.LM, t.C, t.end)
+            assert [h.coarse_qi[c * 21 + i] for c in range(C_) for i in range(end)] == [t.coarse_qi[c * 21 + i] for c in range(C_) for i in range(end)]
+            assert list(h.pulses)[:end] == list(t.pulses)[:end] and list(h.fine_quant)[:end] == list(t.fine_quant)[:end]
+            assert list(h.tf_change)[:end] == list(t.tf_res)[:end] and list(h.collapse_masks)[:C_ * end] == list(t.collapse_masks)[:C_ * end]
+            assert (h.spread, h.intensity, h.dual_stereo, h.coded_bands) == (t.spread, t.intensity, t.dual_stereo, t.coded_bands)
+            iy = np.frombuffer(buf.raw, np.int16, 1920, iy_off)
+            want = np.frombuffer(bytes(t.iy), np.int16); mask = np.frombuffer(bytes(t.iy_set), np.uint8) != 0
+            assert np.array_equal(iy[mask], want[mask]), (name, s, f)
