@@ -5,7 +5,7 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--frames F] [--impl ours|reference]
 
 A "step" is one pass of the hot path over one batch: every one of the 4096 streams advances by F consecutive
-20 ms frames (default F=50 = 1 s of audio per stream per step).  Packets were pre-encoded by the reference
+20 ms frames (default F=200 = 4 s of audio per stream per step, ~60 ms of GPU time: the timed region of a default run is ~2 s).  Packets were pre-encoded by the reference
 (tests/golden/make_golden.py -> tests/golden/pool_cfg2_mono_20ms_64k_cbr.npz: 256 distinct streams, tiled).
 
   value  = audio-seconds decoded per second (= number of real-time streams one GPU sustains), whole job over all
@@ -116,10 +116,14 @@ def enc_algorithmic_bytes_per_frame(F, C=2, N=FRAME, P=240):
     return 4 * C * N + P + s_enc / F
 
 
+_ENC_POOL = {}
+
+
 def enc_pcm(nstreams, F):
     from opus_codec_b200 import synth
-    pool = np.stack([synth.stream_pcm(s, FRAME * F, 2, base_seed=31337) for s in range(64)])      # 64 distinct streams, tiled
-    return np.ascontiguousarray(pool[np.arange(nstreams) % 64]).reshape(nstreams, F, FRAME * 2)
+    if F not in _ENC_POOL:
+        _ENC_POOL[F] = np.stack([synth.stream_pcm(s, FRAME * F, 2, base_seed=31337) for s in range(64)])      # 64 distinct streams, tiled
+    return np.ascontiguousarray(_ENC_POOL[F][np.arange(nstreams) % 64]).reshape(nstreams, F, FRAME * 2)
 
 
 def cpu_reference_encode(nthreads, nstreams, F):
@@ -152,7 +156,7 @@ def run_encode_leg(args, L, local, world, rank, dev, barrier):
 
     step()
     barrier()
-    steps = max(1, min(args.steps, 3))
+    steps = max(3, min(args.steps, 6))                           # ~0.35 s of GPU time per step: >= 1 s timed
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(ext)
     kms = 0.0
@@ -204,14 +208,20 @@ def run_encode_leg(args, L, local, world, rank, dev, barrier):
             pass
         k = kms / steps
         ach = enc_algorithmic_bytes_per_frame(F) * S * F / (k / 1000.0) / 1e9
-        res["roofline"] = {"bound": "hbm", "kernel": "ob_k_encode", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                           "traffic": 8.259e9 * F, "traffic_unit": "bytes per step of F frames (dram__bytes_read.sum + dram__bytes_write.sum per 16384-stream frame x F)",
-                           "traffic_source": "profiles/r01l_ncu_encoder_kernel.txt (ncu --set full --clock-control none, tools/prof_encode.py 16384 1 2)",
+        traffic, tsrc = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")))["encode"]
+            traffic, tsrc = tj["dram_bytes_per_stream_frame"] * S * F, tj["source"]
+        except Exception:
+            pass
+        res["roofline"] = {"bound": "hbm", "kernel": "ob_k_encode_thread (OB_ENC_MAP_AUTO at %d streams: one lane per stream)" % S, "achieved": ach, "peak": peak,
+                           "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                           "traffic_unit": "bytes per step of F frames (dram__bytes_read.sum + dram__bytes_write.sum per stream-frame x S x F)", "traffic_source": tsrc,
                            "kernel_ms": k, "algorithmic_bytes_per_frame": enc_algorithmic_bytes_per_frame(F)}
         if not args.kernels_only:
             cores = os.cpu_count() or 1
             try:
-                v, sample = cpu_reference_encode(cores, cores * 16, 50)
+                v, sample = cpu_reference_encode(cores, cores * 16, 400)      # >= 16 streams per core x 8 s of audio: >= 1 s of wall time on any host
                 res["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample}
             except Exception as ex:
                 res["cpu_baseline"] = {"value": None, "sample": "unavailable: %r" % (ex,)}
@@ -220,7 +230,8 @@ def run_encode_leg(args, L, local, world, rank, dev, barrier):
 
 def run_transcode_leg(args, L, local, world, rank, dev, barrier):
     """BASELINE configs[4] per GPU: 16384 stereo streams decoded and re-encoded (96 kb/s CBR, complexity 10) without leaving the device --
-    the decoder's PCM buffer is the encoder's input (keep decoded PCM on-device)."""
+    the decoder's PCM buffer is the encoder's input (keep decoded PCM on-device) -- and the decode half alone, which is BASELINE's
+    target case (stereo CELT decode), kernel-resident and end to end, every final range verified."""
     import torch
     from opus_codec_b200.batch import BatchDecoder, BatchEncoder
     from opus_codec_b200.shard import max_over_ranks
@@ -229,6 +240,7 @@ def run_transcode_leg(args, L, local, world, rank, dev, barrier):
     pk0, ln0 = z["packets"], z["lens"]                         # [6, 50, stride]: tiled over streams, the first F frames of each
     idx = np.arange(S) % pk0.shape[0]
     pk = np.ascontiguousarray(pk0[idx, :F]); ln = np.ascontiguousarray(ln0[idx, :F]).astype(np.int32)
+    rng_expect = np.ascontiguousarray(z["dec_rng"][idx, :F])
     stride = pk.shape[2]
     offsets = (np.arange(S * F, dtype=np.int32) * stride).reshape(S, F)
     dec = BatchDecoder(S, 48000, 2, device=local, max_frames=F)
@@ -257,7 +269,7 @@ def run_transcode_leg(args, L, local, world, rank, dev, barrier):
     consumed.record(eext)
     step()
     barrier()
-    steps = max(1, min(args.steps, 3))
+    steps = max(3, min(args.steps, 6))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(dext)
     for _ in range(steps):
@@ -266,28 +278,192 @@ def run_transcode_leg(args, L, local, world, rank, dev, barrier):
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1), dev)
     assert (d_smp.cpu().numpy() == FRAME).all() and (d_olen.cpu().numpy() == 240).all()
+    assert (d_rng.cpu().numpy().view(np.uint32).reshape(S, F) == rng_expect).all(), "transcode leg: decoder final range != reference"
+    verified = "decoder final ranges equal the reference's on all %d frames" % (S * F)
+    if rank == 0:                                               # checker only: the reference decoder takes a sample of the re-encoded packets
+        try:
+            from oracle import refpy
+            o = d_out.cpu().numpy().reshape(S, F, 256); ol = d_olen.cpu().numpy().reshape(S, F); og = d_orng.cpu().numpy().view(np.uint32).reshape(S, F)
+            # the streams restart every step from the encoder's carried state: decode the LAST step's packets with a decoder primed by nothing --
+            # final ranges are a function of the packet alone, so they must match whatever the decoder's history is
+            sidx = list(range(0, S, max(1, S // 16)))[:16]
+            for s_ in sidx:
+                _, dr, smp = refpy.decode_stream(o[s_], ol[s_], FRAME, 2)
+                assert (smp == FRAME).all() and (dr == og[s_]).all(), "transcode leg: reference decoder final range != GPU encoder final range (stream %d)" % s_
+            verified += "; the reference decoder accepts the re-encoded packets of %d sampled streams with equal final ranges" % len(sidx)
+        except ImportError:
+            verified += "; re-encoded packets not checked (oracle/_ref missing)"
     launches = dec.launches() + enc.launches()
-    # the decode half alone: BASELINE's target is stated for STEREO streams (>= 4096 real-time 48 kHz stereo CELT decode streams per B200)
+    enc.close()
+    # ---- the decode half alone: BASELINE's target is stated for STEREO streams (>= 4096 real-time 48 kHz stereo CELT decode streams per B200) ----
     torch.cuda.synchronize()
     barrier()
+    dsteps = max(4, min(args.steps, 24))
     g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     g0.record(dext)
-    for _ in range(steps):
+    kms = np.zeros(3)
+    for _ in range(dsteps):
         r = L.ob_decode_float_device(dec.handle, F, d_pk.data_ptr(), d_off.data_ptr(), d_len.data_ptr(), d_pcm.data_ptr(), FRAME, d_smp.data_ptr(), d_rng.data_ptr(), 0)
         assert r == 0, r
+        kms += np.array(dec.kernel_ms())
     g1.record(dext)
     barrier()
     ms_dec = max_over_ranks(g0.elapsed_time(g1), dev)
-    kms_stereo = [float(v) for v in dec.kernel_ms()]           # symbols, bands, synthesis of the last step
-    dec.close(); enc.close()
+    kms /= dsteps
+    assert (d_rng.cpu().numpy().view(np.uint32).reshape(S, F) == rng_expect).all(), "stereo decode: final range mismatch"
+    # end to end: host-pointer ABI, two calls in flight, pinned buffers (1.26 GB of float PCM per step come down)
+    del d_pcm, d_out
+    h_pk = torch.from_numpy(pk.reshape(-1).copy()).pin_memory(); h_off = torch.from_numpy(offsets.reshape(-1).copy()).pin_memory()
+    h_len = torch.from_numpy(ln.reshape(-1).copy()).pin_memory()
+    h_pcm = [torch.empty(S * F * FRAME * 2, dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_smp = [torch.empty(S * F, dtype=torch.int32).pin_memory() for _ in range(2)]
+    h_rng = [torch.empty(S * F, dtype=torch.int32).pin_memory() for _ in range(2)]
+
+    def submit(n):
+        p = n & 1
+        r = L.ob_decode_float_multi_async(dec.handle, F, h_pk.data_ptr(), h_off.data_ptr(), h_len.data_ptr(), h_pcm[p].data_ptr(), FRAME,
+                                          h_smp[p].data_ptr(), h_rng[p].data_ptr())
+        assert r == 0, r
+    for n in range(3):
+        submit(n)
+        assert L.ob_decoder_wait(dec.handle, 0) == 0
+    barrier()
+    esteps = 6
+    t0 = time.perf_counter()
+    for n in range(esteps):
+        submit(n)
+        if n:
+            assert L.ob_decoder_wait(dec.handle, 1) == 0
+    assert L.ob_decoder_wait(dec.handle, 0) == 0
+    torch.cuda.synchronize()
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
+    for p in range(2):
+        assert (h_rng[p].numpy().view(np.uint32).reshape(S, F) == rng_expect).all() and (h_smp[p].numpy() == FRAME).all()
+    dec.close()
     audio = world * S * F * 0.02
-    stereo = {"workload": "%d stereo 48 kHz CELT-only 20 ms @96 kb/s decode streams per GPU, kernel-resident" % S, "value": audio * steps / (ms_dec / 1000.0),
-              "unit": "audio-s/s", "ms_per_step": ms_dec / steps, "rt_stream_capacity_per_gpu": audio * steps / (ms_dec / 1000.0) / world, "target": 4096,
-              "kernel_ms": dict(zip(["ob_k_symbols", "ob_k_bands", "ob_k_synth"], kms_stereo))}
+    bytes_pf = algorithmic_bytes_per_frame(F, C=2, P=240)
+    dom = int(np.argmax(kms))
+    names = ["ob_k_symbols", "ob_k_bands", "ob_k_synth"]
+    stereo = {"workload": "%d stereo 48 kHz CELT-only 20 ms @96 kb/s decode streams per GPU (BASELINE's target case), %d frames per stream per step" % (S, F),
+              "value": audio * dsteps / (ms_dec / 1000.0), "unit": "audio-s/s", "ms_per_step": ms_dec / dsteps, "steps": dsteps,
+              "streams_equivalent_per_gpu": audio * dsteps / (ms_dec / 1000.0) / world, "target_rt_streams": 4096,
+              "final_range_verified": "all %d frames, kernel-resident and end-to-end legs" % (S * F),
+              "e2e": {"value": audio * esteps / (ms_e2e / 1000.0), "unit": "audio-s/s", "steps": esteps,
+                      "h2d_bytes_per_step": int(h_pk.numel() + 8 * h_off.numel()), "d2h_bytes_per_step": int(4 * h_pcm[0].numel() + 8 * h_smp[0].numel())},
+              "kernel_ms": dict(zip(names, [float(v) for v in kms])),
+              "roofline": {"bound": "hbm", "kernel": names[dom], "algorithmic_bytes_per_frame": bytes_pf,
+                           "achieved": bytes_pf * S * F / (float(kms[dom]) / 1e3) / 1e9, "unit": "GB/s",
+                           "pipeline_achieved_GBps": bytes_pf * S * F / (float(kms.sum()) / 1e3) / 1e9}}
     return {"decode_stereo": stereo, "workload": "%d stereo streams per GPU decoded (96 kb/s CBR packets) and re-encoded at 96 kb/s CBR, complexity 10, PCM stays on the device "
                         "(BASELINE configs[4] per-GPU share)" % S,
             "frames_per_stream_per_step": F, "steps": steps, "value": audio * steps / (ms / 1000.0), "unit": "audio-s/s", "ms_per_step": ms / steps,
-            "gpu_launches": int(launches)}
+            "gpu_launches": int(launches), "verified": verified}
+
+
+def host_d2h_ceiling(dev, barrier, seconds=1.0, nbytes=512 << 20):
+    """What this host can absorb: every rank copies device -> pinned host memory at the same time (one stream, 512 MB copies back to back)
+    for `seconds`; returns this rank's GB/s.  With N ranks on one box the sum over ranks is the box's host-bound ceiling -- the number the
+    float end-to-end leg (788 MB of PCM per step and GPU at F=50) runs into at N = 8 (tools/host_d2h_ceiling.py is the stand-alone form)."""
+    import torch
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    h.copy_(d, non_blocking=True); torch.cuda.synchronize()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n, t0 = 0, time.perf_counter()
+    e0.record()
+    while time.perf_counter() - t0 < seconds:
+        h.copy_(d, non_blocking=True); n += 1
+        if n % 4 == 0:
+            torch.cuda.current_stream().synchronize()
+    e1.record(); torch.cuda.synchronize()
+    barrier()
+    return n * nbytes / (e0.elapsed_time(e1) / 1e3) / 1e9
+
+
+def run_live_leg(args, L, local, world, rank, dev, barrier):
+    """The LIVE case (SURVEY 8d, F = 1): one packet per stream per call, as Decoder::decode_float is called (src/decoder.rs:134-182), through the
+    host-pointer ABI with pinned buffers -- upload, kernels and download inside the timed call.  A frame is 20 ms of audio, so the batch is
+    real time while a call takes < 20 ms: rt_stream_capacity is the largest swept batch that does (per GPU).  Same for the encoder."""
+    import torch
+    from opus_codec_b200.batch import BatchDecoder, BatchEncoder
+    from opus_codec_b200.shard import max_over_ranks
+    out = {"definition": "one 20 ms frame per stream per call (F = 1), host-pointer C ABI, pinned host buffers; real time while a call takes < 20 ms",
+           "frame_ms": 20.0}
+    z3 = np.load(os.path.join(ROOT, "tests", "golden", "cfg3_stereo_20ms_96k_cbr.npz"))
+    zp = np.load(POOL)
+    NSTEP, WARM = 6, 3
+    for key, CC, pk0, ln0, rg0, sizes in (("decode_mono_64k", 1, zp["packets"], zp["lens"], zp["dec_rng"], (4096, 16384, 65536, 131072, 147456, 163840, 196608)),
+                                          ("decode_stereo_96k", 2, z3["packets"], z3["lens"], z3["dec_rng"], (4096, 16384, 65536, 73728, 81920, 98304))):
+        rows, cap = [], 0
+        stride = pk0.shape[2]
+        for S in sizes:
+            idx = np.arange(S) % pk0.shape[0]
+            nfr = WARM + NSTEP
+            h_pk = [torch.from_numpy(np.ascontiguousarray(pk0[idx, f]).reshape(-1)).pin_memory() for f in range(nfr)]
+            h_ln = [torch.from_numpy(np.ascontiguousarray(ln0[idx, f]).astype(np.int32)).pin_memory() for f in range(nfr)]
+            h_off = torch.from_numpy(np.arange(S, dtype=np.int32) * stride).pin_memory()
+            h_pcm = [torch.empty(S * FRAME * CC, dtype=torch.float32).pin_memory() for _ in range(2)]
+            h_smp = [torch.empty(S, dtype=torch.int32).pin_memory() for _ in range(2)]
+            h_rng = [torch.empty(S, dtype=torch.int32).pin_memory() for _ in range(2)]
+            dec = BatchDecoder(S, 48000, CC, device=local, max_frames=1)
+
+            def call(n, wait):
+                p = n & 1
+                r = L.ob_decode_float_multi_async(dec.handle, 1, h_pk[n].data_ptr(), h_off.data_ptr(), h_ln[n].data_ptr(), h_pcm[p].data_ptr(), FRAME,
+                                                  h_smp[p].data_ptr(), h_rng[p].data_ptr())
+                assert r == 0, r
+                if wait:
+                    assert L.ob_decoder_wait(dec.handle, 0) == 0
+            for n in range(WARM):
+                call(n, True)
+            barrier()
+            lat = []
+            for n in range(WARM, nfr):                                  # blocking: the latency of one call, nothing overlapped
+                t0 = time.perf_counter()
+                call(n, True)
+                lat.append((time.perf_counter() - t0) * 1e3)
+                assert (h_rng[n & 1].numpy().view(np.uint32) == rg0[idx, n]).all(), "final range mismatch (live leg)"
+                assert (h_smp[n & 1].numpy() == FRAME).all()
+            dec.close()
+            ms = max_over_ranks(float(np.median(lat)), dev)
+            rows.append({"streams_per_gpu": S, "ms_per_call": ms, "realtime": bool(ms < 20.0)})
+            if ms < 20.0:
+                cap = S
+            del h_pk, h_ln, h_pcm, h_smp, h_rng
+            if ms > 24.0:
+                break
+        P = 160 if CC == 1 else 240
+        bytes_f1 = algorithmic_bytes_per_frame(1, C=CC, P=P)
+        best = [r for r in rows if r["realtime"]]
+        out[key] = {"sweep": rows, "rt_stream_capacity_per_gpu": cap, "final_range_verified": True, "algorithmic_bytes_per_frame_F1": bytes_f1,
+                    "achieved_GBps_at_capacity": (bytes_f1 * best[-1]["streams_per_gpu"] / (best[-1]["ms_per_call"] / 1e3) / 1e9) if best else None}
+    # live encode: one warp per stream is the low-latency mapping (include/opus_b200.h OB_ENC_MAP_WARP)
+    rows, cap = [], 0
+    for S in (1184, 2368, 4736, 5920, 7104):
+        pcm = enc_pcm(S, WARM + NSTEP)
+        h_in = [torch.from_numpy(np.ascontiguousarray(pcm[:, f]).reshape(-1)).pin_memory() for f in range(WARM + NSTEP)]
+        h_out = torch.empty(S * 256, dtype=torch.uint8).pin_memory()
+        h_len = torch.empty(S, dtype=torch.int32).pin_memory(); h_rg = torch.empty(S, dtype=torch.int32).pin_memory()
+        enc = BatchEncoder(S, 48000, 2, device=local, max_frames=1)
+        enc.set_mapping(1); enc.set_bitrate(96000); enc.set_complexity(10); enc.set_vbr(False)
+        lat = []
+        for n in range(WARM + NSTEP):
+            t0 = time.perf_counter()
+            r = L.ob_encode_float_multi(enc.handle, 1, h_in[n].data_ptr(), FRAME, h_out.data_ptr(), 256, h_len.data_ptr(), h_rg.data_ptr())
+            assert r == 0, r
+            if n >= WARM:
+                lat.append((time.perf_counter() - t0) * 1e3)
+            assert (h_len.numpy() == 240).all()
+        enc.close()
+        ms = max_over_ranks(float(np.median(lat)), dev)
+        rows.append({"streams_per_gpu": S, "ms_per_call": ms, "realtime": bool(ms < 20.0)})
+        if ms < 20.0:
+            cap = S
+        if ms > 24.0:
+            break
+    out["encode_stereo_96k_c10"] = {"sweep": rows, "rt_stream_capacity_per_gpu": cap, "mapping": "one warp per stream (OB_ENC_MAP_WARP)"}
+    return out
 
 
 def run_reference(args):
@@ -504,11 +680,28 @@ def run_ours(args):
     value = audio_per_step * args.steps / (ms_dev / 1000.0)
     e2e = audio_per_step * e2e_steps / (ms_e2e / 1000.0) if e2e_steps else None
 
-    encode = transcode = None
+    # what the host can absorb when every rank copies at once (the float leg's ceiling at N > 1), measured in this very run
+    host_ceiling = host_d2h_ceiling(dev, barrier) if not args.kernels_only else None
+    host_ceiling_sum = None
+    if host_ceiling is not None:
+        t = torch.tensor([host_ceiling], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t)
+        host_ceiling_sum = float(t.item())
+    encode = transcode = live = None
+    dec.close()
+    def leg(fn):                                                 # a secondary leg that fails must not take the headline line with it
+        try:
+            return fn(args, L, local, world, rank, dev, barrier)
+        except Exception as ex:
+            import traceback
+            traceback.print_exc()
+            return {"error": repr(ex)[:300]}
     if not args.no_encode:
-        dec.close()
-        encode = run_encode_leg(args, L, local, world, rank, dev, barrier)
-        transcode = run_transcode_leg(args, L, local, world, rank, dev, barrier)
+        encode = leg(run_encode_leg)
+        transcode = leg(run_transcode_leg)
+    if not args.no_live and not args.kernels_only:
+        live = leg(run_live_leg)
     if rank == 0:
         peaks = {}
         try:
@@ -522,9 +715,8 @@ def run_ours(args):
         achieved = bytes_per_launch / (kms[dom] / 1000.0) / 1e9
         traffic, traffic_src = None, None
         try:      # DRAM bytes of one launch of that kernel at this shape, from the committed ncu --set full capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01m_dram_traffic.json")))
-            if tj["frames_per_launch"] == S * F:
-                traffic, traffic_src = tj["kernels"][names[dom]]["dram_bytes"], tj["source"]
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")))["decode"]
+            traffic, traffic_src = tj["kernels"][names[dom]]["dram_bytes_per_frame"] * S * F, tj["source"]      # captured per frame at tj["frames_per_launch"]
         except Exception:
             pass
         roof = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -546,19 +738,22 @@ def run_ours(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams_per_gpu": S, "frames_per_stream_per_step": F, "frame_ms": 20, "bitrate": 64000,
-                       "packet_bytes": 160, "rt_stream_capacity": value,
+                       "packet_bytes": 160, "note": "value is offline throughput (F frames per call); the real-time capacity (F = 1) is in `live`",
                        "l2": "per-step working set (IR+spectrum+PCM, %.1f GB) exceeds the 126 MB L2" % ((S * F * (12.6e3 + 7.7e3 + 3.84e3)) / 1e9),
                        "sharding": "streams split by rank, no collective"},
             "e2e": {"value": e2e, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                     "pcie_d2h_GBps": pcie, "d2h_achieved_GBps": (d2h * e2e_steps / (ms_e2e / 1000.0) / 1e9) if e2e_steps else None,
+                    "host_ceiling_GBps": host_ceiling, "host_ceiling_all_ranks_GBps": host_ceiling_sum,
+                    "host_ceiling_note": "device->pinned-host copy rate of this rank while ALL ranks copy at once (1 s, 512 MB copies): what the host can absorb; "
+                                         "d2h_achieved_GBps / host_ceiling_GBps is how much of it the float leg uses",
                     "pcie_note": "the float leg needs d2h_bytes_per_step x steps/s of sustained host-bound traffic; pcie_d2h_GBps is a short 256 MB probe", "numa": numa,
                     "int16_api": {"value": audio_per_step * e2e_steps / (ms_i16 / 1000.0) if ms_i16 else None, "unit": "audio-s/s",
                                   "d2h_bytes_per_step": int(2 * h_pcm[0].numel() + 8 * h_smp[0].numel())},
                     "mode": "host wall clock; two host-pointer calls in flight (ob_decode_float_multi_async + ob_decoder_wait), pinned buffers"},
             "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "encode": encode, "transcode": transcode,
+            "decode_stereo": transcode.get("decode_stereo") if transcode else None, "live": live,
         }
         print(json.dumps(line))
-    dec.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -566,12 +761,13 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--frames", type=int, default=50, help="consecutive 20 ms frames per stream per step")
+    ap.add_argument("--frames", type=int, default=200, help="consecutive 20 ms frames per stream per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--enc-frames", type=int, default=10, help="frames per stream per step of the encode leg")
-    ap.add_argument("--no-encode", action="store_true", help="skip the secondary encode measurement")
+    ap.add_argument("--no-encode", action="store_true", help="skip the secondary encode / transcode measurements")
+    ap.add_argument("--no-live", action="store_true", help="skip the live-streaming (one frame per call) sweeps")
     ap.add_argument("--kernels-only", action="store_true", help="profiling aid: skip the e2e and cpu_baseline legs")
     args = ap.parse_args()
     if args.impl == "reference":
