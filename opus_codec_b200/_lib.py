@@ -25,7 +25,7 @@ SYMBOLS = [
     "ob_packet_get_nb_samples", "ob_packet_has_lbrr", "ob_packet_parse", "ob_packet_pad", "ob_packet_unpad", "ob_multistream_packet_pad", "ob_multistream_packet_unpad", "ob_repacketizer_create", "ob_repacketizer_destroy", "ob_repacketizer_init", "ob_repacketizer_cat",
     "ob_repacketizer_get_nb_frames", "ob_repacketizer_out_range", "ob_repacketizer_out", "ob_repacketize_batch", "ob_repacketize_batch_device", "ob_pcm_soft_clip_batch",
     "ob_encoder_create", "ob_encoder_destroy", "ob_encode_float", "ob_encode_float_multi", "ob_encode_float_device",
-    "ob_encoder_set_bitrate", "ob_encoder_get_bitrate", "ob_encoder_set_mapping", "ob_encoder_get_mapping", "ob_encoder_set_complexity", "ob_encoder_get_complexity",
+    "ob_encoder_set_bitrate", "ob_encoder_get_bitrate", "ob_encoder_set_mapping", "ob_encoder_get_mapping", "ob_encoder_get_split", "ob_encoder_set_complexity", "ob_encoder_get_complexity",
     "ob_encoder_set_vbr", "ob_encoder_get_vbr", "ob_encoder_set_vbr_constraint", "ob_encoder_get_vbr_constraint",
     "ob_encoder_set_max_bandwidth", "ob_encoder_set_bandwidth", "ob_encoder_set_force_channels",
     "ob_encoder_set_packet_loss_perc", "ob_encoder_set_lsb_depth", "ob_encoder_final_range", "ob_encoder_reset",
@@ -99,6 +99,7 @@ def lib():
     L.ob_encoder_get_lsb_depth.argtypes = [vp, vp]; L.ob_encoder_get_lsb_depth.restype = i32
     L.ob_encoder_set_mapping.argtypes = [vp, i32]; L.ob_encoder_set_mapping.restype = i32
     L.ob_encoder_get_mapping.argtypes = [vp, vp]; L.ob_encoder_get_mapping.restype = i32
+    L.ob_encoder_get_split.argtypes = [vp, vp]; L.ob_encoder_get_split.restype = i32
     L.ob_encoder_set_signal.argtypes = [vp, i32]; L.ob_encoder_set_signal.restype = i32
     L.ob_encoder_get_signal.argtypes = [vp, vp]; L.ob_encoder_get_signal.restype = i32
     L.ob_encoder_set_prediction_disabled.argtypes = [vp, i32]; L.ob_encoder_set_prediction_disabled.restype = i32

@@ -285,6 +285,10 @@ class BatchEncoder:
 
     def mapping(self): return self._get(self._L.ob_encoder_get_mapping)
 
+    def split(self):
+        """Streams [0, n) of the last call were coded one warp per stream, the rest one lane per stream (ob_encoder_get_split)."""
+        return self._get(self._L.ob_encoder_get_split)
+
     def _get(self, fn):
         v = C.c_int32(0)
         _check(fn(self._h, C.byref(v)))

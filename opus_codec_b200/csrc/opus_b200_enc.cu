@@ -27,15 +27,15 @@ struct ObEncStream {           // the scalar state one stream owns on the device
 #define OB_ENC_WARPS 16               // ob_k_encode: warps (= streams in flight) per block; 16 x 13.2 KB of shared memory = one block per SM
 #endif
 struct ObEncBlockShared {
-    ObEncShared sh[OB_ENC_WARPS];
-    int progress[OB_ENC_WARPS];       // ObWarpPaced: how far each warp of the block has come
-    int base_stream;
+    int progress[32];                 // ObWarpPaced: how far each warp of the block has come
+    int base_stream, pad[31];
+    ObEncShared sh[OB_ENC_WARPS];     // as many as the launch has warps (dynamic shared memory: 256 bytes + warps x sizeof(ObEncShared))
 };
 __global__ void __launch_bounds__(32 * OB_ENC_WARPS, 1)
 ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *__restrict__ lens, uint32_t *__restrict__ ranges,
             ObEncStream *__restrict__ streams, ObEncHist *__restrict__ hist, ObEncWork *__restrict__ work, int *__restrict__ counter,
             const ObAnalysisInfo *__restrict__ info, ObTonalState *__restrict__ tonal, float *__restrict__ delay,
-            ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes, int f0, int Fc, int paced)
+            ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes, int f0, int Fc, int paced, int s_lo)
 {
     extern __shared__ __align__(16) unsigned char ob_enc_smem[];
     ObEncBlockShared &bs = *reinterpret_cast<ObEncBlockShared *>(ob_enc_smem);
@@ -49,8 +49,8 @@ ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *_
         if (threadIdx.x == 0) bs.base_stream = atomicAdd(counter, nw);
         if (g.lane == 0) bs.progress[w] = 0;
         __syncthreads();
-        const int s = bs.base_stream + w;
-        if (bs.base_stream >= S) break;
+        const int s = s_lo + bs.base_stream + w;                 // this launch codes the streams [s_lo, S)
+        if (s_lo + bs.base_stream >= S) break;
         if (s >= S) { g.publish(0x7fffffff); continue; }          // a tail block: this warp has nothing to do and must hold nobody up
         ObEncStream es = streams[s];
         es.os.delay = delay ? delay + (size_t)s * OB_ENC_BUFFER * es.st.channels : nullptr;      // AUDIO / VOIP: the 4 ms delay compensation, state in global memory
@@ -84,9 +84,9 @@ __global__ void __launch_bounds__(32)
 ob_k_encode_thread(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *__restrict__ lens, uint32_t *__restrict__ ranges,
                    ObEncStream *__restrict__ streams, ObEncHist *__restrict__ hist,
                    const ObAnalysisInfo *__restrict__ info, ObTonalState *__restrict__ tonal, float *__restrict__ delay,
-                   ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes, int f0, int Fc)
+                   ObOpusEncCfg cfg, int S, int F, int frame_size, int max_bytes, int f0, int Fc, int s_lo)
 {
-    const int s = blockIdx.x * 32 + threadIdx.x;
+    const int s = s_lo + blockIdx.x * 32 + threadIdx.x;          // this launch codes the streams [s_lo, S)
     if (s >= S) return;
     const ObSolo g;
     ObEncShared sh;       // not initialised: no stage reads what it (or an earlier frame) has not written (tests/test_host_emul.py poisons it)
@@ -189,7 +189,9 @@ struct ObEncoder {
     int mapping;                       // OB_ENC_MAP_*: which instantiation of the encoder source codes the batch
     int S, CC, device, max_frames, slots;      // slots: resident blocks of ob_k_encode (OB_ENC_WARPS streams each)
     ObOpusEncCfg cfg;
-    cudaStream_t stream, copy_stream, an_stream;
+    cudaStream_t stream, copy_stream, an_stream, split_stream;   // split_stream: the warp-per-stream part of a split batch
+    cudaEvent_t split_go, split_done;
+    int n_warp;                        // streams [0, n_warp) are coded one warp per stream, [n_warp, S) one lane per stream (ob_enc_launch)
     cudaEvent_t ev[2], win_ev[4], an_ev[4], enc_done;
     bool timed, tonal_dirty;
     ObEncStream *d_streams;
@@ -247,6 +249,8 @@ ObEncoder *ob_encoder_create(int32_t n_streams, int32_t fs, int32_t channels, in
         }
         ok = ok && cudaMalloc(&e->d_work, sizeof(ObEncWork) * e->slots * OB_ENC_WARPS) == cudaSuccess;
         ok = ok && cudaMalloc(&e->d_counter, sizeof(int)) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&e->split_stream, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&e->split_go, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&e->split_done, cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaStreamCreateWithFlags(&e->an_stream, cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < 4 && ok; i++) ok = cudaEventCreateWithFlags(&e->an_ev[i], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaEventCreateWithFlags(&e->enc_done, cudaEventDisableTiming) == cudaSuccess;
@@ -271,12 +275,16 @@ void ob_encoder_destroy(ObEncoder *e)
     cudaSetDevice(e->device);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     if (e->an_stream) cudaStreamSynchronize(e->an_stream);
+    if (e->split_stream) cudaStreamSynchronize(e->split_stream);
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_streams); cudaFree(e->d_hist); cudaFree(e->d_work); cudaFree(e->d_counter); cudaFree(e->d_pcm); cudaFree(e->d_pcm16); cudaFree(e->d_out); cudaFree(e->d_lens); cudaFree(e->d_ranges);
     for (int i = 0; i < 2; i++) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     for (int i = 0; i < 4; i++) { if (e->win_ev[i]) cudaEventDestroy(e->win_ev[i]); if (e->an_ev[i]) cudaEventDestroy(e->an_ev[i]); }
     if (e->enc_done) cudaEventDestroy(e->enc_done);
     if (e->an_stream) cudaStreamDestroy(e->an_stream);
+    if (e->split_stream) cudaStreamDestroy(e->split_stream);
+    if (e->split_go) cudaEventDestroy(e->split_go);
+    if (e->split_done) cudaEventDestroy(e->split_done);
     cudaFree(e->d_tonal); cudaFree(e->d_info); cudaFree(e->d_delay);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -324,6 +332,8 @@ int32_t ob_encoder_get_bitrate(ObEncoder *e, int32_t *v) { if (!e || !v) return 
 // which instantiation of the encoder source codes the batch (see ob_k_encode / ob_k_encode_thread)
 int32_t ob_encoder_set_mapping(ObEncoder *e, int32_t m) { if (!e || m < OB_ENC_MAP_AUTO || m > OB_ENC_MAP_THREAD) return OB_BAD_ARG; e->mapping = m; return OB_OK; }
 int32_t ob_encoder_get_mapping(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->mapping; return OB_OK; }
+// how the last call was laid out: streams [0, *n_warp) one warp per stream, the rest one lane per stream
+int32_t ob_encoder_get_split(ObEncoder *e, int32_t *n_warp) { if (!e || !n_warp) return OB_BAD_ARG; *n_warp = e->n_warp; return OB_OK; }
 int32_t ob_encoder_set_complexity(ObEncoder *e, int32_t c) { if (!e || c < 0 || c > 10) return OB_BAD_ARG; e->cfg.complexity = c; return OB_OK; }
 int32_t ob_encoder_get_complexity(ObEncoder *e, int32_t *v) { if (!e || !v) return OB_BAD_ARG; *v = e->cfg.complexity; return OB_OK; }
 int32_t ob_encoder_set_vbr(ObEncoder *e, int32_t v) { if (!e || v < 0 || v > 1) return OB_BAD_ARG; e->cfg.vbr = v; return OB_OK; }
@@ -401,12 +411,39 @@ static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size
     OB_CUDA(cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
     int paced = 3;                                                 // pace level (0 none, 1 stages, 2 + bands, 3 + leaves) | slack << 4
     if (const char *v = getenv("OB_ENC_PACED")) paced = atoi(v);                                            // tuning aid
-    const bool per_thread = e->mapping == OB_ENC_MAP_THREAD || (e->mapping == OB_ENC_MAP_AUTO && e->S >= OB_ENC_MAP_CROSSOVER);
-    if (per_thread)
-        ob_k_encode_thread<<<(e->S + 31) / 32, 32, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->d_hist, an ? e->d_info : nullptr,
-                                                                   an_inline ? e->d_tonal : nullptr, e->d_delay, e->cfg, e->S, F, frame_size, max_bytes, f0, Fc);
-    else ob_k_encode<<<e->slots, 32 * OB_ENC_WARPS, sizeof(ObEncBlockShared), e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->d_hist, e->d_work, e->d_counter,
-            an ? e->d_info : nullptr, an_inline ? e->d_tonal : nullptr, e->d_delay, e->cfg, e->S, F, frame_size, max_bytes, f0, Fc, paced);
+    // Which streams go where.  WARP / THREAD: all of them.  AUTO: below the crossover one warp per stream (latency), from the crossover up one
+    // lane per stream (throughput).  A SPLIT of a bulk batch between the two mappings (first n_warp streams on a second CUDA stream, 12 warps
+    // per block so that both kernels fit an SM's registers) was measured on B200 and rejected: 16 384 stereo complexity-10 streams x 4 frames
+    // take 143 ms all lane-per-stream, 167 / 183 / 197 ms with 20 / 30 / 40 % of the streams warp-per-stream -- the two kernels do not share an
+    // SM (one wants the maximal shared-memory carve-out, the other its L1; forcing the same carve-out on both: 244 ms).  OB_ENC_SPLIT keeps
+    // the experiment reproducible.  A stream keeps its mapping for the life of the encoder.
+    int n_warp = e->mapping == OB_ENC_MAP_WARP ? e->S : 0;
+    if (e->mapping == OB_ENC_MAP_AUTO) {
+        if (e->S < OB_ENC_MAP_CROSSOVER) n_warp = e->S;
+        else {
+            double frac = 0.0;
+            if (const char *v = getenv("OB_ENC_SPLIT")) frac = atof(v);                                     // tuning aid (see above)
+            n_warp = (int)(e->S * frac) / 12 * 12;
+        }
+    }
+    e->n_warp = n_warp;
+    const bool split = n_warp > 0 && n_warp < e->S;
+    if (n_warp > 0) {
+        cudaStream_t ws = split ? e->split_stream : e->stream;
+        const int warps = split ? 12 : OB_ENC_WARPS;
+        if (split) { OB_CUDA(cudaEventRecord(e->split_go, e->stream)); OB_CUDA(cudaStreamWaitEvent(ws, e->split_go, 0)); }
+        OB_CUDA(cudaMemsetAsync(e->d_counter, 0, sizeof(int), ws));
+        int blocks = (n_warp + warps - 1) / warps;
+        if (blocks > e->slots) blocks = e->slots;
+        ob_k_encode<<<blocks, 32 * warps, sizeof(ObEncShared) * warps + 256, ws>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->d_hist, e->d_work, e->d_counter,
+                an ? e->d_info : nullptr, an_inline ? e->d_tonal : nullptr, e->d_delay, e->cfg, n_warp, F, frame_size, max_bytes, f0, Fc, paced, 0);
+        if (split) OB_CUDA(cudaEventRecord(e->split_done, ws));
+    }
+    if (n_warp < e->S) {
+        ob_k_encode_thread<<<(e->S - n_warp + 31) / 32, 32, 0, e->stream>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->d_hist, an ? e->d_info : nullptr,
+                                                                            an_inline ? e->d_tonal : nullptr, e->d_delay, e->cfg, e->S, F, frame_size, max_bytes, f0, Fc, n_warp);
+        if (split) OB_CUDA(cudaStreamWaitEvent(e->stream, e->split_done, 0));
+    }
     if (f0 + Fc == F) { OB_CUDA(cudaEventRecord(e->ev[1], e->stream)); OB_CUDA(cudaEventRecord(e->enc_done, e->stream)); }
     OB_CUDA(cudaGetLastError());
     e->launches += 1;

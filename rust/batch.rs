@@ -38,6 +38,7 @@ unsafe extern "C" {
     pub fn ob_encoder_set_bitrate(enc: *mut ObEncoder, bitrate: i32) -> i32;
     pub fn ob_encoder_set_mapping(enc: *mut ObEncoder, mapping: i32) -> i32;      // 0 auto, 1 one warp per stream, 2 one lane per stream
     pub fn ob_encoder_get_mapping(enc: *mut ObEncoder, value: *mut i32) -> i32;
+    pub fn ob_encoder_get_split(enc: *mut ObEncoder, n_warp_streams: *mut i32) -> i32;
     pub fn ob_encoder_get_bitrate(enc: *mut ObEncoder, value: *mut i32) -> i32;
     pub fn ob_encoder_set_complexity(enc: *mut ObEncoder, complexity: i32) -> i32;
     pub fn ob_encoder_set_vbr(enc: *mut ObEncoder, vbr: i32) -> i32;

@@ -363,18 +363,20 @@ def test_full_size_batch_16384_streams_tiling_property(have_ref):
         enc.set_bitrate(96000); enc.set_complexity(10); enc.set_vbr(False)
         small, small_len, small_rng = enc.encode_float_multi(pool, 960, max_bytes=256)
     big_in = np.ascontiguousarray(pool[np.arange(S) % P])
-    with BatchEncoder(S, 48000, 2, device=0, max_frames=F) as enc:
-        assert enc.mapping() == 0                                     # AUTO: 16 384 >= OB_ENC_MAP_CROSSOVER -> one lane per stream
-        enc.set_bitrate(96000); enc.set_complexity(10); enc.set_vbr(False)
-        out, lens, rng = enc.encode_float_multi(big_in, 960, max_bytes=256)
-    assert (lens == 240).all()
-    idx = np.arange(S) % P
-    assert np.array_equal(out, small[idx]) and np.array_equal(rng, small_rng[idx])
-    # ... and the warp-per-stream mapping at a size that fills every resident warp slot (148 SMs x 16), against its own small batch and the emulation
-    S2 = 4736
     with BatchEncoder(P, 48000, 2, device=0, max_frames=F) as enc:
         enc.set_mapping(1); enc.set_bitrate(96000); enc.set_complexity(10); enc.set_vbr(False)
         wsmall, wsmall_len, wsmall_rng = enc.encode_float_multi(pool, 960, max_bytes=256)
+    with BatchEncoder(S, 48000, 2, device=0, max_frames=F) as enc:
+        assert enc.mapping() == 0                                     # AUTO: 16 384 >= OB_ENC_MAP_CROSSOVER -> one lane per stream (ob_encoder_get_split says which streams)
+        enc.set_bitrate(96000); enc.set_complexity(10); enc.set_vbr(False)
+        out, lens, rng = enc.encode_float_multi(big_in, 960, max_bytes=256)
+        nw = enc.split()
+    assert (lens == 240).all() and 0 <= nw < S
+    idx = np.arange(S) % P
+    assert np.array_equal(out[nw:], small[idx[nw:]]) and np.array_equal(rng[nw:], small_rng[idx[nw:]])          # one lane per stream
+    assert np.array_equal(out[:nw], wsmall[idx[:nw]]) and np.array_equal(rng[:nw], wsmall_rng[idx[:nw]])        # one warp per stream
+    # ... and the warp-per-stream mapping at a size that fills every resident warp slot (148 SMs x 16), against its own small batch and the emulation
+    S2 = 4736
     with BatchEncoder(S2, 48000, 2, device=0, max_frames=F) as enc:
         assert enc.mapping() == 0                                     # AUTO below the crossover: one warp per stream
         enc.set_bitrate(96000); enc.set_complexity(10); enc.set_vbr(False)
