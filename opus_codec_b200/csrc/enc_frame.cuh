@@ -5,7 +5,7 @@
 // ONE WARP PER STREAM.  Memory plan per warp:
 //   shared (ObEncShared, ~18 KB): everything touched element by element or out of order -- the FFT / pitch / transient scratch, the band
 //     being quantised with its folding source, the coder's output bytes, and the per-band tables of the frame;
-//   global, per resident warp (ObEncWork, ~60 KB, stays in L2): the long time / frequency vectors that are only streamed with
+//   global, per resident warp (ObEncWork, ~48 KB, stays in L2): the long time / frequency vectors that are only streamed with
 //     lane-strided (coalesced) loops -- [history | frame] of the pre-filter, the MDCT input, the spectrum, the normalised spectrum;
 //   global, per stream (ObEncStream + ObEncHist): state between calls, read at the start and written at the end of a launch.
 #pragma once
@@ -60,11 +60,16 @@ struct ObEncShared {
     uint8_t bytes[1280];                              // the range coder's buffer (payload without the TOC)
 };
 struct ObEncWork {
-    float in[2 * (OB_MAX_N + OB_OVERLAP)];
-    float pre[2 * (OB_MAX_N + OB_MAXPERIOD)];
-    float freq[2 * OB_MAX_N];
-    float X[2 * OB_MAX_N];
-    float pcm_hp[2 * (OB_MAX_N + OB_ENC_DELAY)];      // [delay compensation | dc_reject / hp_cutoff output]: what CELT encodes
+    // Buffers whose lifetimes do not overlap share storage (48 KB instead of 73 KB per resident warp: 148 x 16 slots then fit the 126 MB L2):
+    union {
+        float pcm_hp[2 * (OB_MAX_N + OB_ENC_DELAY)];  // [delay compensation | dc_reject / hp_cutoff output]: what CELT encodes; dead after pre-emphasis
+        float pre[2 * (OB_MAX_N + OB_MAXPERIOD)];     // [pre-filter memory | frame] per channel; built after pre-emphasis, dead after the comb filter
+        float freq[2 * OB_MAX_N];                     // MDCT output, written after the pre-filter and the transient analysis
+    };
+    union {
+        float in[2 * (OB_MAX_N + OB_OVERLAP)];        // [overlap | pre-filtered frame] per channel: the MDCT's input
+        float X[2 * OB_MAX_N];                        // normalised spectrum: written from freq after the last MDCT of the frame
+    };
     float env[(OB_MAX_N + OB_OVERLAP + 7) >> 1];      // transient_analysis: the masking envelope (chunk-per-lane scans)
     ObEncHist hist;                                   // in_mem / prefilter_mem of the stream being coded (the four energy arrays live in shared memory)
     ObEncBandsWork bw;

@@ -23,6 +23,9 @@ struct ObEncStream {           // the scalar state one stream owns on the device
 };
 
 #define OB_ENC_THREADS 32             // ob_k_analysis: one thread per stream
+#ifndef OB_ENC_BLOCKS
+#define OB_ENC_BLOCKS 1                // resident blocks per SM the register allocation aims at (OB_ENC_WARPS x OB_ENC_BLOCKS x 32 x regs <= 64 K)
+#endif
 #ifndef OB_ENC_WARPS
 #define OB_ENC_WARPS 16               // ob_k_encode: warps (= streams in flight) per block; 16 x 13.2 KB of shared memory = one block per SM
 #endif
@@ -31,7 +34,7 @@ struct ObEncBlockShared {
     int base_stream, pad[31];
     ObEncShared sh[OB_ENC_WARPS];     // as many as the launch has warps (dynamic shared memory: 256 bytes + warps x sizeof(ObEncShared))
 };
-__global__ void __launch_bounds__(32 * OB_ENC_WARPS, 1)
+__global__ void __launch_bounds__(32 * OB_ENC_WARPS, OB_ENC_BLOCKS)
 ob_k_encode(const float *__restrict__ pcm, uint8_t *__restrict__ out, int32_t *__restrict__ lens, uint32_t *__restrict__ ranges,
             ObEncStream *__restrict__ streams, ObEncHist *__restrict__ hist, ObEncWork *__restrict__ work, int *__restrict__ counter,
             const ObAnalysisInfo *__restrict__ info, ObTonalState *__restrict__ tonal, float *__restrict__ delay,

@@ -1,10 +1,11 @@
 #!/usr/bin/env python
 """Per-source-line instruction counts for a kernel: joins `ncu --page source --print-source sass --csv` (executed
 instruction counts per SASS instruction) with `nvdisasm -g` line info of the cubin in the .so (same instruction order).
-Usage: ncu_hot_lines.py <report.ncu-rep> <kernel-regex> <lib.so> [top]"""
+Usage: ncu_hot_lines.py <report.ncu-rep> <kernel-regex (mangled section name)> <lib.so> [top] [ncu kernel-name regex, default = kernel-regex]"""
 import csv, os, re, subprocess, sys, tempfile, collections
 rep, kern, so = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 25
+ncu_kern = sys.argv[5] if len(sys.argv) > 5 else kern
 td = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(so)], cwd=td, check=True, stdout=subprocess.DEVNULL)
 dis = []
@@ -21,7 +22,7 @@ for l in dis:
     if m: loc = (os.path.basename(m.group(1)), int(m.group(2))); continue
     m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(.*?);", l)
     if m and cur: sections[cur].append((m.group(1).strip(), loc))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern, "--print-source", "sass"],
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + ncu_kern, "--print-source", "sass"],
                      capture_output=True, text=True).stdout.splitlines()
 rows = list(csv.reader(out))
 h = rows[1]; ia = h.index("Source"); ie = h.index("Instructions Executed"); it = h.index("Thread Instructions Executed"); iss = h.index("# Samples")
