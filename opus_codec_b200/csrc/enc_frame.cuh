@@ -748,7 +748,11 @@ OB_STAGE int ob_opus_encode(const G &g, const ObOpusEncCfg &cfg, ObOpusEncState 
             else {
                 read_pos_bak = os.tonal->read_pos; read_subframe_bak = os.tonal->read_subframe;
                 g.sync();
-                if (g.lane == 0) { ObAnalysisInfo a; a.valid = 0; ob_run_analysis(*os.tonal, pcm, frame_size, channels, lsb_depth, a, wk.pre); sh.an_tmp = a; }
+                {   // cooperative front (resampler scans, FFT, per-bin and per-band sums), scalar statistics + network on lane 0: the result reaches the warp through shared memory
+                    ObAnalysisInfo a; a.valid = 0;
+                    ob_run_analysis(g, *os.tonal, pcm, frame_size, channels, lsb_depth, a, wk.pre, sh.A);
+                    if (g.lane == 0) sh.an_tmp = a;
+                }
                 g.sync();
                 analysis_info = sh.an_tmp;
                 g.sync();

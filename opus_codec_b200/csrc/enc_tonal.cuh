@@ -93,57 +93,105 @@ OB_DEV_NOINLINE void ob_gru(float *state, const float *input)               // l
     for (int i = 0; i < N; i++) state[i] = h[i];
 }
 
-// silk_resampler_down2_hp (analysis.c:115-161), float build; returns the high-pass energy
-OB_DEV_NOINLINE float ob_down2_hp(float *S, float *out, const float *in, int inLen)
+// silk_resampler_down2_hp (analysis.c:115-161), float build; returns the high-pass energy.  The three all-pass memories are independent
+// first-order recurrences (S0 over the even samples, S1 and S2 over the odd ones): three exact-step scans write their contributions to
+// five temporaries, one element-wise pass combines them in the reference's order.  tmp: >= 5 * 240 floats; runs in chunks of 240 outputs.
+template <class G>
+OB_DEV float ob_down2_hp(const G &g, float *S, float *out, const float *in, int inLen, float *tmp)
 {
     const int len2 = inLen / 2;
-    float hp_ener = 0;
-    for (int k = 0; k < len2; k++) {
-        float in32 = in[2 * k];
-        float Y = in32 - S[0];
-        float X = 0.6074371f * Y;
-        float out32 = S[0] + X;
-        S[0] = in32 + X;
-        float out32_hp = out32;
-        in32 = in[2 * k + 1];
-        Y = in32 - S[1];
-        X = 0.15063f * Y;
-        out32 = out32 + S[1];
-        out32 = out32 + X;
-        S[1] = in32 + X;
-        Y = -in32 - S[2];
-        X = 0.15063f * Y;
-        out32_hp = out32_hp + S[2];
-        out32_hp = out32_hp + X;
-        S[2] = -in32 + X;
-        hp_ener += out32_hp * out32_hp;
-        out[k] = .5f * out32;
+    float hp_ener = 0, S0 = S[0], S1 = S[1], S2 = S[2];
+    if (ObOrder<G>::value == 1) {                                    // one lane, reference order: the reference's fused loop (same arithmetic, no temporaries)
+        for (int k = 0; k < len2; k++) {
+            float in32 = in[2 * k];
+            float Y = in32 - S0;
+            float X = 0.6074371f * Y;
+            float out32 = S0 + X;
+            S0 = in32 + X;
+            float out32_hp = out32;
+            in32 = in[2 * k + 1];
+            Y = in32 - S1;
+            X = 0.15063f * Y;
+            out32 = out32 + S1;
+            out32 = out32 + X;
+            S1 = in32 + X;
+            Y = -in32 - S2;
+            X = 0.15063f * Y;
+            out32_hp = out32_hp + S2;
+            out32_hp = out32_hp + X;
+            S2 = -in32 + X;
+            hp_ener += out32_hp * out32_hp;
+            out[k] = .5f * out32;
+        }
+        S[0] = S0; S[1] = S1; S[2] = S2;
+        return hp_ener;
     }
+    for (int base = 0; base < len2; base += 240) {
+        const int n = ob_imin(240, len2 - base);
+        const float *x = in + 2 * base;
+        float *a0 = tmp, *s1 = tmp + 240, *x1 = tmp + 480, *s2 = tmp + 720, *x2 = tmp + 960;
+        S0 = ob_scan1s(g, n, -0.6074371f, S0, [&](int k, float &m, bool emit) {
+            const float in32 = x[2 * k], Y = in32 - m, X = 0.6074371f * Y;
+            if (emit) a0[k] = m + X;
+            m = in32 + X;
+        });
+        S1 = ob_scan1s(g, n, -0.15063f, S1, [&](int k, float &m, bool emit) {
+            const float in32 = x[2 * k + 1], Y = in32 - m, X = 0.15063f * Y;
+            if (emit) { s1[k] = m; x1[k] = X; }
+            m = in32 + X;
+        });
+        S2 = ob_scan1s(g, n, -0.15063f, S2, [&](int k, float &m, bool emit) {
+            const float in32 = x[2 * k + 1], Y = -in32 - m, X = 0.15063f * Y;
+            if (emit) { s2[k] = m; x2[k] = X; }
+            m = -in32 + X;
+        });
+        g.sync();
+        for (int k = g.lane; k < n; k += g.n) {
+            float out32 = a0[k];
+            out32 = out32 + s1[k];
+            out32 = out32 + x1[k];
+            out[base + k] = .5f * out32;
+        }
+        hp_ener = ob_psum(g, n, hp_ener, [&](int k) {
+            float hp = a0[k];
+            hp = hp + s2[k];
+            hp = hp + x2[k];
+            return hp * hp;
+        });
+        g.sync();
+    }
+    if (g.lane == 0) { S[0] = S0; S[1] = S1; S[2] = S2; }
+    g.sync();
     return hp_ener;
 }
 
 // downmix_and_resample (analysis.c:163-215) with downmix_float (opus_encoder.c:657-678), c1 = 0, c2 = -2, Fs = 48000.
-// x: the caller's interleaved float PCM; tmp: >= 960 floats of scratch.
-OB_DEV float ob_downmix_and_resample(const float *x, float *y, float *S, int subframe, int offset, int C, float *tmp)
+// x: the caller's interleaved float PCM; dm: >= 960 floats of scratch; tmp: >= 1200 floats.
+template <class G>
+OB_DEV float ob_downmix_and_resample(const G &g, const float *x, float *y, float *S, int subframe, int offset, int C, float *dm, float *tmp)
 {
     if (subframe == 0) return 0;
     subframe *= 2;
     offset *= 2;
-    for (int j = 0; j < subframe; j++) tmp[j] = x[(j + offset) * C] * 32768.f;
-    for (int c = 1; c < C; c++) for (int j = 0; j < subframe; j++) tmp[j] += x[(j + offset) * C + c] * 32768.f;
     float scale = 1.f / 32768;
     scale /= C;
-    for (int j = 0; j < subframe; j++) tmp[j] *= scale;
-    return ob_down2_hp(S, y, tmp, subframe);
+    for (int j = g.lane; j < subframe; j += g.n) {
+        float v = x[(j + offset) * C] * 32768.f;
+        for (int c = 1; c < C; c++) v += x[(j + offset) * C + c] * 32768.f;
+        dm[j] = v * scale;
+    }
+    g.sync();
+    return ob_down2_hp(g, S, y, dm, subframe, tmp);
 }
 
-// opus_fft (kiss_fft.c:569-589) of 480 complex points: scale, bit-reverse, then the decoder's radix stages with one lane.
-OB_DEV_NOINLINE void ob_fft480(const float *fin, float *fout)
+// opus_fft (kiss_fft.c:569-589) of 480 complex points: scale, bit-reverse, then the decoder's radix stages (every butterfly a work item).
+template <class G>
+OB_DEV void ob_fft480(const G &g, const float *fin, float *fout)
 {
     const float scale = 0.002083333f;
     const int16_t *br = ob_fft_bitrev(0);
-    for (int i = 0; i < 480; i++) { fout[2 * br[i]] = scale * fin[2 * i]; fout[2 * br[i] + 1] = scale * fin[2 * i + 1]; }
-    ObSolo g;
+    for (int i = g.lane; i < 480; i += g.n) { fout[2 * br[i]] = scale * fin[2 * i]; fout[2 * br[i] + 1] = scale * fin[2 * i + 1]; }
+    g.sync();
     const int16_t *fac = ob_fft_factors(0);
     int fstride[9], L = 0, m, m2, p;
     fstride[0] = 1;
@@ -157,12 +205,17 @@ OB_DEV_NOINLINE void ob_fft480(const float *fin, float *fout)
 }
 
 // tonality_analysis (analysis.c:446-953).  x: interleaved float PCM of the frame being encoded; len/offset in 48 kHz samples.
-// work: >= 960 (fft in) + 960 (fft out) + 960 (down-mix) + 3 * 240 floats.
-OB_DEV_NOINLINE void ob_tonality_analysis(ObTonalState &tonal, const float *x, int len, int offset, int C, int lsb_depth, float *work)
+// Cooperative part (all lanes): down-mix + 2:1 resampling (three recurrence scans), windowing, the 480-point FFT, the per-bin phase statistics
+// and the per-band energy sums (one band per lane, each the reference's in-order sum).  The per-band statistics, the bandwidth detector and the
+// 25-32-24-2 network that follow are ~7 k instructions of scalar code on 18-element arrays: lane 0 runs them on the sums the warp left behind.
+// work: >= 2 720 floats (FFT input 960 | down-mix 960 | 3 x 240 per-bin values | 80 band sums); fbuf: >= 1 200 floats (resampler temporaries, then
+// the FFT's 960-float output) -- shared memory in the warp-per-stream kernel.
+template <class G>
+OB_DEV_NOINLINE void ob_tonality_analysis(const G &g, ObTonalState &tonal, const float *x, int len, int offset, int C, int lsb_depth, float *work, float *fbuf)
 {
     const int N = 480, N2 = 240, NB = OB_AN_NB_TBANDS;
     float *A = tonal.angle, *dA = tonal.d_angle, *d2A = tonal.d2_angle;
-    float *in = work, *out = work + 960, *dm = work + 1920, *tonality = work + 2880, *noisiness = work + 3120, *tonality2 = work + 3360;
+    float *in = work, *out = fbuf, *dm = work + 960, *tonality = work + 1920, *noisiness = work + 2160, *tonality2 = work + 2400, *bsum = work + 2640;
     float band_tonality[18], logE[18], BFCC[8], features[25], midE[8], band_log2[19], leakage_from[19], leakage_to[19], layer_out[32], frame_probs[2];
     int is_masked[19];
     const float pi4 = (float)(3.14159265358979323846 * 3.14159265358979323846 * 3.14159265358979323846 * 3.14159265358979323846);
@@ -170,85 +223,118 @@ OB_DEV_NOINLINE void ob_tonality_analysis(ObTonalState &tonal, const float *x, i
     float spec_variability = 0, below_max_pitch, above_max_pitch, hp_ener;
     int bandwidth = 0, b, i;
 
-    if (!tonal.initialized) { tonal.mem_fill = 240; tonal.initialized = 1; }
-    const float alpha = 1.f / ob_imin(10, 1 + tonal.count), alphaE = 1.f / ob_imin(25, 1 + tonal.count);
-    float alphaE2 = 1.f / ob_imin(100, 1 + tonal.count);
-    if (tonal.count <= 1) alphaE2 = 1;
+    // the scalar state is read by every lane (uniform) and written back by lane 0 alone
+    int mem_fill = tonal.mem_fill, write_pos = tonal.write_pos;
+    const int count = tonal.count;
+    float hp_accum = tonal.hp_ener_accum;
+    g.sync();
+    if (!tonal.initialized) mem_fill = 240;
+    const float alpha = 1.f / ob_imin(10, 1 + count), alphaE = 1.f / ob_imin(25, 1 + count);
+    float alphaE2 = 1.f / ob_imin(100, 1 + count);
+    if (count <= 1) alphaE2 = 1;
     len /= 2; offset /= 2;                                           // now at 24 kHz
-    tonal.hp_ener_accum += ob_downmix_and_resample(x, &tonal.inmem[tonal.mem_fill], tonal.downmix_state, ob_imin(len, OB_AN_BUF - tonal.mem_fill), offset, C, dm);
-    if (tonal.mem_fill + len < OB_AN_BUF) { tonal.mem_fill += len; return; }
-    hp_ener = tonal.hp_ener_accum;
-    ObAnalysisInfo *info = &tonal.info[tonal.write_pos++];
-    if (tonal.write_pos >= OB_AN_DETECT) tonal.write_pos -= OB_AN_DETECT;
-    const int is_silence = ob_maxabs(ObSolo(), tonal.inmem, OB_AN_BUF) <= (float)1 / (1 << lsb_depth);
-    for (i = 0; i < N2; i++) {
+    hp_accum += ob_downmix_and_resample(g, x, &tonal.inmem[mem_fill], tonal.downmix_state, ob_imin(len, OB_AN_BUF - mem_fill), offset, C, dm, fbuf);
+    if (mem_fill + len < OB_AN_BUF) {
+        if (g.lane == 0) { tonal.initialized = 1; tonal.mem_fill = mem_fill + len; tonal.hp_ener_accum = hp_accum; }
+        g.sync();
+        return;
+    }
+    hp_ener = hp_accum;
+    ObAnalysisInfo *info = &tonal.info[write_pos++];
+    if (write_pos >= OB_AN_DETECT) write_pos -= OB_AN_DETECT;
+    const int is_silence = ob_maxabs(g, tonal.inmem, OB_AN_BUF) <= (float)1 / (1 << lsb_depth);
+    for (i = g.lane; i < N2; i += g.n) {
         const float w = OB_AN_WINDOW[i];
         in[2 * i] = w * tonal.inmem[i];
         in[2 * i + 1] = w * tonal.inmem[N2 + i];
         in[2 * (N - i - 1)] = w * tonal.inmem[N - i - 1];
         in[2 * (N - i - 1) + 1] = w * tonal.inmem[N + N2 - i - 1];
     }
-    for (i = 0; i < 240; i++) tonal.inmem[i] = tonal.inmem[OB_AN_BUF - 240 + i];
-    const int remaining = len - (OB_AN_BUF - tonal.mem_fill);
-    tonal.hp_ener_accum = ob_downmix_and_resample(x, &tonal.inmem[240], tonal.downmix_state, remaining, offset + OB_AN_BUF - tonal.mem_fill, C, dm);
-    tonal.mem_fill = 240 + remaining;
+    g.sync();
+    for (i = g.lane; i < 240; i += g.n) tonal.inmem[i] = tonal.inmem[OB_AN_BUF - 240 + i];
+    g.sync();
+    const int remaining = len - (OB_AN_BUF - mem_fill);
+    hp_accum = ob_downmix_and_resample(g, x, &tonal.inmem[240], tonal.downmix_state, remaining, offset + OB_AN_BUF - mem_fill, C, dm, fbuf);
+    if (g.lane == 0) { tonal.initialized = 1; tonal.mem_fill = 240 + remaining; tonal.hp_ener_accum = hp_accum; tonal.write_pos = write_pos; }
+    g.sync();
     if (is_silence) {                                                // copy the previous analysis
-        int prev_pos = tonal.write_pos - 2;
+        int prev_pos = write_pos - 2;
         if (prev_pos < 0) prev_pos += OB_AN_DETECT;
-        *info = tonal.info[prev_pos];
+        if (g.lane == 0) *info = tonal.info[prev_pos];
+        g.sync();
         return;
     }
-    ob_fft480(in, out);
-    if (out[0] != out[0]) { info->valid = 0; return; }
+    ob_fft480(g, in, out);
+    if (out[0] != out[0]) { if (g.lane == 0) info->valid = 0; g.sync(); return; }
 #define RE(k) out[2 * (k)]
 #define IM(k) out[2 * (k) + 1]
-    for (i = 1; i < N2; i++) {
+    for (i = 1 + g.lane; i < N2; i += g.n) {
         const float X1r = RE(i) + RE(N - i), X1i = IM(i) - IM(N - i), X2r = IM(i) + IM(N - i), X2i = RE(N - i) - RE(i);
         const float angle = (float)(.5f / 3.14159265358979323846) * ob_fast_atan2f(X1i, X1r);
         const float d_angle = angle - A[i], d2_angle = d_angle - dA[i];
         const float angle2 = (float)(.5f / 3.14159265358979323846) * ob_fast_atan2f(X2i, X2r);
         const float d_angle2 = angle2 - angle, d2_angle2 = d_angle2 - d_angle;
         float mod1 = d2_angle - (float)OB_F2I_RN(d2_angle);
-        noisiness[i] = fabsf(mod1);
+        float nz = fabsf(mod1);
         mod1 *= mod1; mod1 *= mod1;
         float mod2 = d2_angle2 - (float)OB_F2I_RN(d2_angle2);
-        noisiness[i] += fabsf(mod2);
+        nz += fabsf(mod2);
+        noisiness[i] = nz;
         mod2 *= mod2; mod2 *= mod2;
         const float avg_mod = .25f * (d2A[i] + mod1 + 2 * mod2);
         tonality[i] = 1.f / (1.f + 40.f * 16.f * pi4 * avg_mod) - .015f;
         tonality2[i] = 1.f / (1.f + 40.f * 16.f * pi4 * mod2) - .015f;
         A[i] = angle2; dA[i] = d_angle2; d2A[i] = mod2;
     }
-    for (i = 2; i < N2 - 1; i++) {
+    g.sync();
+    for (i = 2 + g.lane; i < N2 - 1; i += g.n) {
         const float tt = ob_fmin(tonality2[i], ob_fmax(tonality2[i - 1], tonality2[i + 1]));
         tonality[i] = .9f * ob_fmax(tonality[i], tt - .1f);
     }
+    g.sync();
+#define BINE(k) (RE(k) * RE(k) + RE(N - (k)) * RE(N - (k)) + IM(k) * IM(k) + IM(N - (k)) * IM(N - (k)))
+    // per-band sums, one band per lane, each in the reference's order: bsum[b] = E, bsum[20 + b] = tonal energy, bsum[40 + b] = noisy energy,
+    // bsum[60] = the DC band's energy (bins 0..3)
+    for (b = g.lane; b <= NB; b += g.n) {
+        if (b == NB) {
+            const float X1r = 2 * RE(0), X2r = 2 * IM(0);
+            float E = X1r * X1r + X2r * X2r;
+            for (i = 1; i < 4; i++) { const float binE = BINE(i); E += binE; }
+            bsum[60] = E;
+        } else {
+            float E = 0, tE = 0, nE = 0;
+            for (i = OB_AN_TBANDS[b]; i < OB_AN_TBANDS[b + 1]; i++) {
+                const float binE = BINE(i);
+                E += binE;
+                tE += binE * ob_fmax(0, tonality[i]);
+                nE += binE * 2.f * (.5f - noisiness[i]);
+            }
+            bsum[b] = E; bsum[20 + b] = tE; bsum[40 + b] = nE;
+        }
+    }
+    g.sync();
+    if (g.lane == 0) {                                               // ---- from here on: scalar statistics, one lane ----
+    int E_count = tonal.E_count;
     frame_tonality = 0; max_frame_tonality = 0; info->activity = 0; frame_noisiness = 0; frame_stationarity = 0;
-    if (!tonal.count) for (b = 0; b < NB; b++) { tonal.lowE[b] = 1e10; tonal.highE[b] = -1e10; }
+    if (!count) for (b = 0; b < NB; b++) { tonal.lowE[b] = 1e10; tonal.highE[b] = -1e10; }
     relativeE = 0; frame_loudness = 0;
 #define BINE(k) (RE(k) * RE(k) + RE(N - (k)) * RE(N - (k)) + IM(k) * IM(k) + IM(N - (k)) * IM(N - (k)))
     {   // the very first band is special because of DC
-        const float X1r = 2 * RE(0), X2r = 2 * IM(0);
-        float E = X1r * X1r + X2r * X2r;
-        for (i = 1; i < 4; i++) { const float binE = BINE(i); E += binE; }
+        const float E = bsum[60];
         band_log2[0] = .5f * 1.442695f * (float)log((double)(E + 1e-10f));
     }
+    int bad = 0;
     for (b = 0; b < NB; b++) {
-        float E = 0, tE = 0, nE = 0, L1, L2, stationarity;
-        for (i = OB_AN_TBANDS[b]; i < OB_AN_TBANDS[b + 1]; i++) {
-            const float binE = BINE(i);
-            E += binE;
-            tE += binE * ob_fmax(0, tonality[i]);
-            nE += binE * 2.f * (.5f - noisiness[i]);
-        }
-        if (!(E < 1e9f) || E != E) { info->valid = 0; return; }
-        tonal.E[tonal.E_count][b] = E;
+        const float E = bsum[b], tE = bsum[20 + b], nE = bsum[40 + b];
+        float L1, L2, stationarity;
+        if (!(E < 1e9f) || E != E) { info->valid = 0; bad = 1; break; }
+        tonal.E[E_count][b] = E;
         frame_noisiness += nE / (1e-15f + E);
         frame_loudness += (float)sqrt((double)(E + 1e-10f));
         logE[b] = (float)log((double)(E + 1e-10f));
         band_log2[b + 1] = .5f * 1.442695f * (float)log((double)(E + 1e-10f));
-        tonal.logE[tonal.E_count][b] = logE[b];
-        if (tonal.count == 0) tonal.highE[b] = tonal.lowE[b] = logE[b];
+        tonal.logE[E_count][b] = logE[b];
+        if (count == 0) tonal.highE[b] = tonal.lowE[b] = logE[b];
         if ((double)tonal.highE[b] > (double)tonal.lowE[b] + 7.5) {
             if (tonal.highE[b] - logE[b] > logE[b] - tonal.lowE[b]) tonal.highE[b] -= .01f;
             else tonal.lowE[b] += .01f;
@@ -274,6 +360,7 @@ OB_DEV_NOINLINE void ob_tonality_analysis(ObTonalState &tonal, const float *x, i
         slope += band_tonality[b] * (b - 8);
         tonal.prev_band_tonality[b] = band_tonality[b];
     }
+    if (!bad) {
     leakage_from[0] = band_log2[0];
     leakage_to[0] = band_log2[0] - 2.5f;
     for (b = 1; b < NB + 1; b++) {
@@ -306,9 +393,9 @@ OB_DEV_NOINLINE void ob_tonality_analysis(ObTonalState &tonal, const float *x, i
     noise_floor *= noise_floor;
     below_max_pitch = 0; above_max_pitch = 0;
     for (b = 0; b < NB; b++) {
-        float E = 0, Em;
+        const float E = bsum[b];
+        float Em;
         const int band_start = OB_AN_TBANDS[b], band_end = OB_AN_TBANDS[b + 1];
-        for (i = band_start; i < band_end; i++) { const float binE = BINE(i); E += binE; }
         maxE = ob_fmax(maxE, E);
         if (band_start < 64) below_max_pitch += E; else above_max_pitch += E;
         tonal.meanE[b] = ob_fmax((1 - alphaE2) * tonal.meanE[b], E);
@@ -330,7 +417,7 @@ OB_DEV_NOINLINE void ob_tonality_analysis(ObTonalState &tonal, const float *x, i
     else info->max_pitch_ratio = 1;
     if (bandwidth == 20 && is_masked[NB]) bandwidth -= 2;
     else if (bandwidth > 0 && bandwidth <= NB && is_masked[bandwidth - 1]) bandwidth--;
-    if (tonal.count <= 2) bandwidth = 20;
+    if (count <= 2) bandwidth = 20;
     frame_loudness = 20 * (float)log10((double)frame_loudness);
     tonal.Etracker = ob_fmax(tonal.Etracker - .003f, frame_loudness);
     tonal.lowECount *= (1 - alphaE);
@@ -347,7 +434,7 @@ OB_DEV_NOINLINE void ob_tonality_analysis(ObTonalState &tonal, const float *x, i
     }
     frame_stationarity /= NB;
     relativeE /= NB;
-    if (tonal.count < 10) relativeE = .5f;
+    if (count < 10) relativeE = .5f;
     frame_noisiness /= NB;
     info->activity = frame_noisiness + (1 - frame_noisiness) * relativeE;
     frame_tonality = (max_frame_tonality / (NB - OB_AN_SKIP_BANDS));
@@ -355,8 +442,9 @@ OB_DEV_NOINLINE void ob_tonality_analysis(ObTonalState &tonal, const float *x, i
     tonal.prev_tonality = frame_tonality;
     slope /= 8 * 8;
     info->tonality_slope = slope;
-    tonal.E_count = (tonal.E_count + 1) % OB_AN_NB_FRAMES;
-    tonal.count = ob_imin(tonal.count + 1, OB_AN_COUNT_MAX);
+    tonal.E_count = (E_count + 1) % OB_AN_NB_FRAMES;
+    const int count1 = ob_imin(count + 1, OB_AN_COUNT_MAX);
+    tonal.count = count1;
     info->tonality = frame_tonality;
     for (i = 0; i < 4; i++)
         features[i] = -0.12299f * (BFCC[i] + tonal.mem[i + 24]) + 0.49195f * (tonal.mem[i] + tonal.mem[i + 16]) + 0.69693f * tonal.mem[i + 8] - 1.4349f * tonal.cmean[i];
@@ -364,7 +452,7 @@ OB_DEV_NOINLINE void ob_tonality_analysis(ObTonalState &tonal, const float *x, i
     for (i = 0; i < 4; i++) features[4 + i] = 0.63246f * (BFCC[i] - tonal.mem[i + 24]) + 0.31623f * (tonal.mem[i] - tonal.mem[i + 16]);
     for (i = 0; i < 3; i++)
         features[8 + i] = 0.53452f * (BFCC[i] + tonal.mem[i + 24]) - 0.26726f * (tonal.mem[i] + tonal.mem[i + 16]) - 0.53452f * tonal.mem[i + 8];
-    if (tonal.count > 5) for (i = 0; i < 9; i++) tonal.std[i] = (1 - alpha) * tonal.std[i] + alpha * features[i] * features[i];
+    if (count1 > 5) for (i = 0; i < 9; i++) tonal.std[i] = (1 - alpha) * tonal.std[i] + alpha * features[i] * features[i];
     for (i = 0; i < 4; i++) features[i] = BFCC[i] - midE[i];
     for (i = 0; i < 8; i++) {
         tonal.mem[i + 24] = tonal.mem[i + 16];
@@ -388,6 +476,9 @@ OB_DEV_NOINLINE void ob_tonality_analysis(ObTonalState &tonal, const float *x, i
     tonal.prev_bandwidth = bandwidth;
     info->noisiness = frame_noisiness;
     info->valid = 1;
+    }                                                                // !bad
+    }                                                                // lane 0
+    g.sync();
 #undef RE
 #undef IM
 #undef BINE
@@ -472,17 +563,22 @@ OB_DEV_NOINLINE void ob_tonality_get_info(ObTonalState &tonal, ObAnalysisInfo &i
 }
 
 // run_analysis (analysis.c:955-981) for one frame of frame_size samples at 48 kHz (analysis_frame_size == frame_size)
-OB_DEV void ob_run_analysis(ObTonalState &an, const float *pcm, int frame_size, int C, int lsb_depth, ObAnalysisInfo &info, float *work)
+template <class G>
+OB_DEV void ob_run_analysis(const G &g, ObTonalState &an, const float *pcm, int frame_size, int C, int lsb_depth, ObAnalysisInfo &info, float *work, float *fbuf)
 {
     int analysis_frame_size = frame_size - (frame_size & 1);
     analysis_frame_size = ob_imin((OB_AN_DETECT - 5) * 48000 / 50, analysis_frame_size);
-    int pcm_len = analysis_frame_size - an.analysis_offset, offset = an.analysis_offset;
+    const int offset0 = an.analysis_offset;
+    g.sync();
+    int pcm_len = analysis_frame_size - offset0, offset = offset0;
     while (pcm_len > 0) {
-        ob_tonality_analysis(an, pcm, ob_imin(48000 / 50, pcm_len), offset, C, lsb_depth, work);
+        ob_tonality_analysis(g, an, pcm, ob_imin(48000 / 50, pcm_len), offset, C, lsb_depth, work, fbuf);
         offset += 48000 / 50;
         pcm_len -= 48000 / 50;
     }
-    an.analysis_offset = analysis_frame_size;
-    an.analysis_offset -= frame_size;
-    ob_tonality_get_info(an, info, frame_size);
+    if (g.lane == 0) {
+        an.analysis_offset = analysis_frame_size - frame_size;
+        ob_tonality_get_info(an, info, frame_size);
+    }
+    g.sync();
 }

@@ -267,6 +267,56 @@ template <class S> OB_COOP ObState2 ob_scan2(const ObSoloW &, int n, float m00, 
 }
 #endif
 
+// ---- first-order recurrence given as an exact per-sample step: step(i, y, emit) advances the state y over sample i with the reference's own
+// arithmetic (and emits what it has to when emit is set); the homogeneous part of a step is y -> a * y.  Same chunk-per-lane scheme as ob_scan1. ----
+template <class S> OB_COOP float ob_scan1s(const ObSolo &, int n, float, float y0, S step)
+{
+    float y = y0;
+    for (int i = 0; i < n; i++) step(i, y, true);
+    return y;
+}
+#ifdef __CUDACC__
+template <class S> OB_COOP float ob_scan1s(const ObWarp &g, int n, float a, float y0, S step)
+{
+    const int L = (n + 31) >> 5, lo = ob_imin(n, g.lane * L), hi = ob_imin(n, lo + L);
+    float e = 0.f, A = 1.f;
+    for (int i = lo; i < hi; i++) { step(i, e, false); A = A * a; }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float Ap = __shfl_up_sync(0xffffffffu, A, o), ep = __shfl_up_sync(0xffffffffu, e, o);
+        if (g.lane >= o) { e = A * ep + e; A = A * Ap; }
+    }
+    const float yend = A * y0 + e;
+    float y = __shfl_up_sync(0xffffffffu, yend, 1);
+    if (g.lane == 0) y = y0;
+    for (int i = lo; i < hi; i++) step(i, y, true);
+    __syncwarp();
+    return __shfl_sync(0xffffffffu, yend, 31);
+}
+#else
+template <class S> OB_COOP float ob_scan1s(const ObSoloW &, int n, float a, float y0, S step)
+{
+    const int L = (n + 31) >> 5;
+    float e[32], A[32];
+    for (int l = 0; l < 32; l++) {
+        const int lo = ob_imin(n, l * L), hi = ob_imin(n, lo + L);
+        e[l] = 0.f; A[l] = 1.f;
+        for (int i = lo; i < hi; i++) { step(i, e[l], false); A[l] = A[l] * a; }
+    }
+    for (int o = 1; o < 32; o <<= 1) {
+        float e2[32], A2[32];
+        for (int l = 0; l < 32; l++) { if (l >= o) { e2[l] = A[l] * e[l - o] + e[l]; A2[l] = A[l] * A[l - o]; } else { e2[l] = e[l]; A2[l] = A[l]; } }
+        for (int l = 0; l < 32; l++) { e[l] = e2[l]; A[l] = A2[l]; }
+    }
+    for (int l = 0; l < 32; l++) {
+        const int lo = ob_imin(n, l * L), hi = ob_imin(n, lo + L);
+        float y = l == 0 ? y0 : A[l - 1] * y0 + e[l - 1];
+        for (int i = lo; i < hi; i++) step(i, y, true);
+    }
+    return A[31] * y0 + e[31];
+}
+#endif
+
 // ---- plain inclusive prefix sum of f(i) (float), out(i, sum_{t<=i} f(t)); warp form: chunk per lane + shuffle scan of the totals ----
 template <class F, class P> OB_COOP void ob_prefix_sum(const ObSolo &, int n, float y0, F f, P out)
 {

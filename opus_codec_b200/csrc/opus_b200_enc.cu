@@ -120,17 +120,18 @@ ob_k_encode_thread(const float *__restrict__ pcm, uint8_t *__restrict__ out, int
 // flight and hides the analysis (16 % of the fused kernel's time) almost completely.
 __global__ void __launch_bounds__(OB_ENC_THREADS)
 ob_k_analysis(const float *__restrict__ pcm, ObTonalState *__restrict__ tonal, ObAnalysisInfo *__restrict__ info, int S, int F, int frame_size,
-              int channels, int lsb_depth, int f0, int Fc)
+              int channels, int lsb_depth, int f0, int Fc, int s_lo)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = s_lo + blockIdx.x * blockDim.x + threadIdx.x;   // this launch covers the streams [s_lo, S)
     if (s >= S) return;
-    float work[3600];                                           // lane-interleaved local memory, like the encoder's scratch
+    float work[3920];                                           // lane-interleaved local memory, like the encoder's scratch: 2720 work + 1200 FFT / resampler
+    const ObSolo g;
     ObTonalState t = tonal[s];
     for (volatile int f = f0; f < f0 + Fc; f++) {
         const size_t w = (size_t)s * F + f;
         ObAnalysisInfo a;
         a.valid = 0;
-        ob_run_analysis(t, pcm + w * (size_t)frame_size * channels, frame_size, channels, lsb_depth, a, work);
+        ob_run_analysis(g, t, pcm + w * (size_t)frame_size * channels, frame_size, channels, lsb_depth, a, work, work + 2720);
         info[w] = a;
     }
     tonal[s] = t;
@@ -385,16 +386,34 @@ static int ob_frame_size_select(int frame_size, int variable_duration, int Fs)
 // One frame window [f0, f0+Fc) of every stream.  At complexity >= 7 the analysis kernel of the window runs on its own stream, right
 // away (it needs only the PCM), and the encode kernel of the window waits for it; while the encoder works on window k the analysis
 // of window k+1 is already running beside it.  analysis_ahead: the caller has already enqueued the analysis of this window.
+// Which streams go where (see ob_enc_launch): streams [0, n_warp) one warp per stream, the rest one lane per stream.
+static int ob_enc_plan(ObEncoder *e)
+{
+    int n_warp = e->mapping == OB_ENC_MAP_WARP ? e->S : 0;
+    if (e->mapping == OB_ENC_MAP_AUTO) {
+        if (e->S < OB_ENC_MAP_CROSSOVER) n_warp = e->S;
+        else {
+            double frac = 0.0;
+            if (const char *v = getenv("OB_ENC_SPLIT")) frac = atof(v);                                     // tuning aid (see ob_enc_launch)
+            n_warp = (int)(e->S * frac) / 12 * 12;
+        }
+    }
+    e->n_warp = n_warp;
+    return n_warp;
+}
+
 static int ob_enc_analysis(ObEncoder *e, int F, const float *d_pcm, int frame_size, int f0, int Fc, int k, cudaEvent_t pcm_ready)
 {
     if (e->cfg.complexity < 7 || frame_size > 960) return OB_OK;   // long packets interleave analysis reads with their 20 ms frames: done inline
+    const int n_warp = ob_enc_plan(e);
+    e->tonal_dirty = true;
+    if (n_warp >= e->S) return OB_OK;                              // the warp-per-stream kernel runs the analysis itself (cooperatively, in front of every frame)
     if (pcm_ready) OB_CUDA(cudaStreamWaitEvent(e->an_stream, pcm_ready, 0));
     if (f0 == 0) OB_CUDA(cudaStreamWaitEvent(e->an_stream, e->enc_done, 0));       // d_info of the previous call has been consumed
-    ob_k_analysis<<<(e->S + OB_ENC_THREADS - 1) / OB_ENC_THREADS, OB_ENC_THREADS, 0, e->an_stream>>>(d_pcm, e->d_tonal, e->d_info, e->S, F, frame_size, e->CC,
-                                                                                                     e->cfg.lsb_depth, f0, Fc);
+    ob_k_analysis<<<(e->S - n_warp + OB_ENC_THREADS - 1) / OB_ENC_THREADS, OB_ENC_THREADS, 0, e->an_stream>>>(d_pcm, e->d_tonal, e->d_info, e->S, F, frame_size, e->CC,
+                                                                                                              e->cfg.lsb_depth, f0, Fc, n_warp);
     OB_CUDA(cudaEventRecord(e->an_ev[k & 3], e->an_stream));
     e->launches += 1;
-    e->tonal_dirty = true;
     return OB_OK;
 }
 
@@ -410,7 +429,7 @@ static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size
         e->launches += 1;
     }
     if (f0 == 0) OB_CUDA(cudaEventRecord(e->ev[0], e->stream));
-    if (an) OB_CUDA(cudaStreamWaitEvent(e->stream, e->an_ev[k & 3], 0));
+    if (an && ob_enc_plan(e) < e->S) OB_CUDA(cudaStreamWaitEvent(e->stream, e->an_ev[k & 3], 0));
     OB_CUDA(cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
     int paced = 3;                                                 // pace level (0 none, 1 stages, 2 + bands, 3 + leaves) | slack << 4
     if (const char *v = getenv("OB_ENC_PACED")) paced = atoi(v);                                            // tuning aid
@@ -420,16 +439,7 @@ static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size
     // take 143 ms all lane-per-stream, 167 / 183 / 197 ms with 20 / 30 / 40 % of the streams warp-per-stream -- the two kernels do not share an
     // SM (one wants the maximal shared-memory carve-out, the other its L1; forcing the same carve-out on both: 244 ms).  OB_ENC_SPLIT keeps
     // the experiment reproducible.  A stream keeps its mapping for the life of the encoder.
-    int n_warp = e->mapping == OB_ENC_MAP_WARP ? e->S : 0;
-    if (e->mapping == OB_ENC_MAP_AUTO) {
-        if (e->S < OB_ENC_MAP_CROSSOVER) n_warp = e->S;
-        else {
-            double frac = 0.0;
-            if (const char *v = getenv("OB_ENC_SPLIT")) frac = atof(v);                                     // tuning aid (see above)
-            n_warp = (int)(e->S * frac) / 12 * 12;
-        }
-    }
-    e->n_warp = n_warp;
+    const int n_warp = ob_enc_plan(e);
     const bool split = n_warp > 0 && n_warp < e->S;
     if (n_warp > 0) {
         cudaStream_t ws = split ? e->split_stream : e->stream;
@@ -439,7 +449,7 @@ static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size
         int blocks = (n_warp + warps - 1) / warps;
         if (blocks > e->slots) blocks = e->slots;
         ob_k_encode<<<blocks, 32 * warps, sizeof(ObEncShared) * warps + 256, ws>>>(d_pcm, d_out, d_lens, d_ranges, e->d_streams, e->d_hist, e->d_work, e->d_counter,
-                an ? e->d_info : nullptr, an_inline ? e->d_tonal : nullptr, e->d_delay, e->cfg, n_warp, F, frame_size, max_bytes, f0, Fc, paced, 0);
+                nullptr, (an || an_inline) ? e->d_tonal : nullptr, e->d_delay, e->cfg, n_warp, F, frame_size, max_bytes, f0, Fc, paced, 0);
         if (split) OB_CUDA(cudaEventRecord(e->split_done, ws));
     }
     if (n_warp < e->S) {
