@@ -569,7 +569,9 @@ static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *p
     // d->stream, copies on d->copy_stream, one event per chunk).  With several frames per stream the chunks are FRAME windows
     // of all streams: every launch keeps the full stream-level parallelism the synthesis kernel needs (one block per stream),
     // and the per-stream state simply carries over from launch to launch.  Single-frame calls are split by stream ranges.
-    int nchunks = total >= 65536 ? 3 : (total >= 16384 ? 2 : 1);   // measured (204 800 frames, two calls in flight): 1: 202 k, 2: 208 k, 3: 209 k, 5: 209 k (int16: 205 / 206 / 206 / 200 k), 8: 202 k
+    int nchunks = total >= 400000 ? 6 : (total >= 65536 ? 3 : (total >= 16384 ? 2 : 1));      // 819 200 frames, blocking call: 3 chunks 96.8 ms, 6 chunks 89.4 ms; chunks as stream ranges
+                                                                                               // (contiguous copies instead of 2-D ones): no gain (97.9 ms)
+      // measured (204 800 frames, two calls in flight): 1: 202 k, 2: 208 k, 3: 209 k, 5: 209 k (int16: 205 / 206 / 206 / 200 k), 8: 202 k
     if (const char *v = getenv("OB_DEC_CHUNKS")) { const int t = atoi(v); if (t >= 1) nchunks = t; }      // tuning aid
     if (nchunks > OB_MAX_CHUNKS) nchunks = OB_MAX_CHUNKS;
     const size_t pf = (size_t)frame_size * d->CC;
