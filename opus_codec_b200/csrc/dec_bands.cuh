@@ -39,6 +39,18 @@ OB_DEV ObLcg ob_lcg_pow(uint32_t k)
 // Exact t / d for 0 <= t, d < 2^16 with one multiply: magic = floor(2^32 / d) + 1 (d >= 2).
 struct ObDiv { uint32_t d, magic; };
 OB_DEV ObDiv ob_div_make(int d) { ObDiv r; r.d = (uint32_t)d; r.magic = d > 1 ? 0xFFFFFFFFu / (uint32_t)d + 1u : 0u; return r; }
+// divisor for splitting a work-item index into (block, item) over nblk blocks of d items: with one block the quotient is always 0,
+// so the magic (a real division to compute) is not needed -- magic 0 makes ob_div_q return 0
+OB_DEV ObDiv ob_div_make_blocks(int d, int nblk) { ObDiv r; r.d = (uint32_t)d; r.magic = nblk > 1 ? 0xFFFFFFFFu / (uint32_t)d + 1u : 0u; return r; }
+// the quotient alone, for d >= 2 (one multiply-high on the device)
+OB_DEV int ob_div_q(int t, const ObDiv &dv)
+{
+#ifdef __CUDA_ARCH__
+    return (int)__umulhi((uint32_t)t, dv.magic);
+#else
+    return (int)(((uint64_t)(uint32_t)t * dv.magic) >> 32);
+#endif
+}
 OB_DEV int ob_div(int t, const ObDiv &dv)
 {
     if (dv.d <= 1) return t;

@@ -42,6 +42,9 @@ struct ObCpx { float r, i; };
 OB_DEV const int16_t *ob_fft_bitrev(int shift) { return shift == 0 ? OB_FFT_BITREV480 : shift == 1 ? OB_FFT_BITREV240 : shift == 2 ? OB_FFT_BITREV120 : OB_FFT_BITREV60; }
 OB_DEV const int16_t *ob_fft_factors(int shift) { return shift == 0 ? OB_FFT_FACTORS480 : shift == 1 ? OB_FFT_FACTORS240 : shift == 2 ? OB_FFT_FACTORS120 : OB_FFT_FACTORS60; }
 
+// n / ds for the output down-sampling factor ds (1, 2, 3, 4 or 6): 48 kHz output (ds == 1) skips the division
+OB_DEV int ob_div_ds(int n, int ds) { return ds == 1 ? n : n / ds; }
+
 // One decimation-in-time stage of opus_fft_impl (kiss_fft.c:521-567) over `nblk` independent transforms whose data
 // start blk_stride floats apart; every butterfly of the stage is an independent work item.
 template <class G>
@@ -50,9 +53,9 @@ OB_DEV void ob_fft_stage(const G &g, float *base, int nblk, int blk_stride, int 
     if (p == 2) {                                                   // kf_bfly2, m == 4 (kiss_fft.c:48-100)
         const float tw = 0.7071067812f;
         const int per = Nst * 4, total = nblk * per;
-        const ObDiv dper = ob_div_make(per);
+        const ObDiv dper = ob_div_make_blocks(per, nblk);
         for (int t = g.lane; t < total; t += g.n) {
-            const int blk = nblk > 1 ? ob_div(t, dper) : 0;
+            const int blk = ob_div_q(t, dper);
             ObCpx *F = (ObCpx *)(base + blk * blk_stride) + ((t - blk * per) >> 2) * 8;
             const int k = t & 3;
             ObCpx *F2 = F + 4, x = F2[k], tt;
@@ -65,9 +68,9 @@ OB_DEV void ob_fft_stage(const G &g, float *base, int nblk, int blk_stride, int 
         }
     } else if (p == 4) {                                            // kf_bfly4 (kiss_fft.c:102-171)
         const int per = Nst * m, total = nblk * per, lm = ob_log2i(m);       // m is a power of two in radix-4 stages
-        const ObDiv dper = ob_div_make(per);
+        const ObDiv dper = ob_div_make_blocks(per, nblk);
         for (int t = g.lane; t < total; t += g.n) {
-            const int blk = nblk > 1 ? ob_div(t, dper) : 0;
+            const int blk = ob_div_q(t, dper);
             const int w = t - blk * per, i = w >> lm, j = w & (m - 1);
             ObCpx *F = (ObCpx *)(base + blk * blk_stride) + i * mm + j;
             ObCpx s0, s1, s2, s3, s4, s5;
@@ -84,10 +87,10 @@ OB_DEV void ob_fft_stage(const G &g, float *base, int nblk, int blk_stride, int 
         }
     } else if (p == 3) {                                            // kf_bfly3 (kiss_fft.c:176-236)
         const int per = Nst * m, total = nblk * per, lm = ob_log2i(m);       // m is a power of two in radix-3 stages
-        const ObDiv dper = ob_div_make(per);
+        const ObDiv dper = ob_div_make_blocks(per, nblk);
         const float epi3i = OB_TW(fstride * m).i;
         for (int t = g.lane; t < total; t += g.n) {
-            const int blk = nblk > 1 ? ob_div(t, dper) : 0;
+            const int blk = ob_div_q(t, dper);
             const int w = t - blk * per, i = w >> lm, j = w & (m - 1);
             ObCpx *F = (ObCpx *)(base + blk * blk_stride) + i * mm + j;
             ObCpx s0, s1, s2, s3;
@@ -102,10 +105,10 @@ OB_DEV void ob_fft_stage(const G &g, float *base, int nblk, int blk_stride, int 
         }
     } else {                                                        // kf_bfly5 (kiss_fft.c:240-308)
         const int per = Nst * m, total = nblk * per;                          // radix-5 is always the last stage: Nst == 1
-        const ObDiv dper = ob_div_make(per);
+        const ObDiv dper = ob_div_make_blocks(per, nblk);
         const ObCpx ya = OB_TW(fstride * m), yb = OB_TW(fstride * 2 * m);
         for (int t = g.lane; t < total; t += g.n) {
-            const int blk = nblk > 1 ? ob_div(t, dper) : 0;
+            const int blk = ob_div_q(t, dper);
             const int i = 0, u = t - blk * per;
             ObCpx *F0 = (ObCpx *)(base + blk * blk_stride) + i * mm + u;
             ObCpx *F1 = F0 + m, *F2 = F0 + 2 * m, *F3 = F0 + 3 * m, *F4 = F0 + 4 * m;
@@ -136,9 +139,9 @@ OB_DEV void ob_imdct(const G &g, const float *in, float *out, int shift, int nbl
     const int N2 = 1920 >> (shift + 1), N4 = N2 >> 1;
     const float *trig = OB_MDCT_TRIG + (shift == 0 ? 0 : shift == 1 ? 960 : shift == 2 ? 1440 : 1680);
     const int16_t *br = ob_fft_bitrev(shift);
-    const ObDiv dN4 = ob_div_make(N4);
+    const ObDiv dN4 = ob_div_make_blocks(N4, nblk);
     for (int t = g.lane; t < nblk * N4; t += g.n) {                  // pre-rotation into bit-reversed order
-        const int b = nblk > 1 ? ob_div(t, dN4) : 0, i = t - b * N4;
+        const int b = ob_div_q(t, dN4), i = t - b * N4;
         const float x1 = in[b + nblk * (2 * i)], x2 = in[b + nblk * (N2 - 1 - 2 * i)];
         float *yp = out + b * N2 + (OB_OVERLAP >> 1);
         const int rev = br[i];
@@ -159,9 +162,9 @@ OB_DEV void ob_imdct(const G &g, const float *in, float *out, int shift, int nbl
         }
     }
     const int half = (N4 + 1) >> 1;
-    const ObDiv dhalf = ob_div_make(half);
+    const ObDiv dhalf = ob_div_make_blocks(half, nblk);
     for (int t = g.lane; t < nblk * half; t += g.n) {                // post-rotation, both ends at once
-        const int b = nblk > 1 ? ob_div(t, dhalf) : 0, i = t - b * half;
+        const int b = ob_div_q(t, dhalf), i = t - b * half;
         float *yp0 = out + b * N2 + (OB_OVERLAP >> 1) + 2 * i, *yp1 = out + b * N2 + (OB_OVERLAP >> 1) + N2 - 2 - 2 * i;
         float re = yp0[1], im = yp0[0], t0 = trig[i], t1 = trig[N4 + i];
         const float yr0 = re * t0 + im * t1, yi0 = re * t1 - im * t0;
@@ -317,10 +320,11 @@ OB_DEV void ob_denorm_imdct(const G &g, SH &sh, int C, int CC, int N, int LM, in
         sh.gain[t] = (i < end && !silence) ? (float)exp(0.6931471805599453094 * (double)(lg < 32.f ? lg : 32.f)) : 0.f;
     }
     g.sync();
+    const int lim = ob_div_ds(N, sh.ds);                                      // bound: bands.c:206-208
     for (int c = 0; c < C; c++)
         for (int j = g.lane; j < N; j += g.n) {
             const int bin = j >> LM, band = bin < 100 ? sh.band_of_bin[bin] : OB_NB;
-            sh.freq[c][j] = (band < OB_NB && j < N / sh.ds) ? sh.freq[c][j] * sh.gain[c * OB_NB + band] : 0.f;     // bound: bands.c:206-208
+            sh.freq[c][j] = (band < OB_NB && j < lim) ? sh.freq[c][j] * sh.gain[c * OB_NB + band] : 0.f;
         }
     g.sync();
     if (CC == 2 && C == 1) { for (int j = g.lane; j < N; j += g.n) sh.freq[1][j] = sh.freq[0][j]; g.sync(); }
@@ -346,29 +350,17 @@ OB_DEV void ob_synth_tail(const G &g, SH &sh, float *pcm, int N, int CC)
             // m = coef * (local response at the chunk end); affine map of the carry: m_out = a * m_in + m
             float a = 1.f;
             for (int j = lo; j < hi; j++) a *= coef;
-            sh.scanA[g.lane] = a; sh.scanB[g.lane] = m;
-            g.sync();
-            // exclusive scan of affine maps (Hillis-Steele inclusive, then shift)
-            for (int o = 1; o < g.n; o <<= 1) {
-                float pa = 1.f, pb = 0.f;
-                const int have = g.lane >= o;
-                if (have) { pa = sh.scanA[g.lane - o]; pb = sh.scanB[g.lane - o]; }
-                g.sync();
-                if (have) { sh.scanB[g.lane] = sh.scanA[g.lane] * pb + sh.scanB[g.lane]; sh.scanA[g.lane] = sh.scanA[g.lane] * pa; }
-                g.sync();
-            }
-            // carry-in of this lane = inclusive result of lane-1 applied to the stream's memory
-            float carry = sh.preemph_mem[c];
-            if (g.lane > 0) carry = sh.scanA[g.lane - 1] * sh.preemph_mem[c] + sh.scanB[g.lane - 1];
-            const float last_all = sh.scanA[g.n - 1] * sh.preemph_mem[c] + sh.scanB[g.n - 1];
+            // carry-in of this lane = the composition of the lanes before it applied to the stream's memory
+            float ea, eb, ta, tb;
+            g.affine_scan(a, m, ea, eb, ta, tb);
+            const float carry = ea * sh.preemph_mem[c] + eb, last_all = ta * sh.preemph_mem[c] + tb;
             m = carry;
             for (int j = lo; j < hi; j++) { const float t = x[j] + 1e-30f + m; m = coef * t; y[j] = t * (1.f / 32768.f); }
             g.sync();
-            if (g.lane == 0) sh.preemph_mem[c] = last_all;
-            g.sync();
+            if (g.lane == 0) sh.preemph_mem[c] = last_all;         // next read: the next frame, many barriers away
         }
         const float dg = sh.decode_gain;                             // OPUS_SET_GAIN, applied by the Opus layer (opus_decoder.c:639-649)
-        const int ds = sh.ds, Nd = N / ds;                           // output rates below 48 kHz keep every ds-th sample (celt_decoder.c:326-373)
+        const int ds = sh.ds, Nd = ob_div_ds(N, ds);                           // output rates below 48 kHz keep every ds-th sample (celt_decoder.c:326-373)
         if (CC == 1) { for (int t = g.lane; t < Nd; t += g.n) { const float v = sh.freq[0][t * ds]; pcm[t] = dg == 1.f ? v : v * dg; } }
         else { for (int t = g.lane; t < 2 * Nd; t += g.n) { const float v = sh.freq[t & 1][(t >> 1) * ds]; pcm[t] = dg == 1.f ? v : v * dg; } }
         g.sync();
@@ -400,9 +392,9 @@ OB_DEV_NOINLINE int ob_conceal(const G &g, SH &sh, float *pcm, int CC)
     const ObFrameHdr &h = sh.hdr;
     const int total = h.status;
     if (h.end_in == 0) {                                             // nothing decoded yet: zeros (opus_decoder.c:302-309)
-        for (int t = g.lane; t < total / sh.ds * CC; t += g.n) pcm[t] = 0.f;
+        for (int t = g.lane; t < ob_div_ds(total, sh.ds) * CC; t += g.n) pcm[t] = 0.f;
         g.sync();
-        return total / sh.ds;
+        return ob_div_ds(total, sh.ds);
     }
     ObPlanState p;
     p.rng = h.seed_in; p.loss_duration = h.loss_in; p.skip_plc = h.skip_in; p.plc_end = h.end_in;
@@ -421,10 +413,10 @@ OB_DEV_NOINLINE int ob_conceal(const G &g, SH &sh, float *pcm, int CC)
         }
         g.sync();
         ob_plc_advance(p, N, CC);
-        ob_synth_tail(g, sh, pcm + (size_t)(done / sh.ds) * CC, N, CC);
+        ob_synth_tail(g, sh, pcm + (size_t)ob_div_ds(done, sh.ds) * CC, N, CC);
         done += N;
     }
-    return total / sh.ds;
+    return ob_div_ds(total, sh.ds);
 }
 
 // opus_pcm_soft_clip (opus/src/opus.c:39-144) for ONE channel of an interleaved packet that has already been limited to +-2:
@@ -527,6 +519,22 @@ OB_DEV int ob_synth_frame(const G &g, SH &sh, const ObFrameIR *ir, const float *
     const int transient = (h.flags & OB_F_TRANSIENT) != 0, silence = (h.flags & OB_F_SILENCE) != 0;
     const uint32_t seed_in = h.seed_in;
 
+    // ---- X tile, first half: the global loads are issued here into registers and land in shared memory after the energy recurrence below,
+    // which does not depend on them (the synthesis kernel's largest single stall was the wait for this tile, profiles/r02_hot_lines_synth.txt) ----
+    const int bound = OB_EBANDS[end] << LM;                          // bands >= end were not written by the bands stage
+#ifdef __CUDA_ARCH__
+    constexpr int XR = (int)(sizeof(sh.buf) / sizeof(sh.buf[0])) * OB_MAX_N / 128 + 1;     // tile elements per thread of a 128-thread block
+    float xr[XR];
+    const bool x_early = g.n * XR >= C * N;
+    if (x_early) {
+#pragma unroll
+        for (int k = 0; k < XR; k++) {
+            const int t = g.lane + k * g.n, j = t >= N ? t - N : t;
+            xr[k] = (t < C * N && j < bound) ? Xg[t] : 0.f;
+        }
+    }
+#endif
+
     // ---- energies: coarse recurrence + fine + finalise (quant_bands.c:428-542); one lane per channel ----
     if (C == 1) for (int i = g.lane; i < OB_NB; i += g.n) sh.oldBandE[i] = fmaxf(sh.oldBandE[i], sh.oldBandE[OB_NB + i]);
     g.sync();
@@ -549,9 +557,17 @@ OB_DEV int ob_synth_frame(const G &g, SH &sh, const ObFrameIR *ir, const float *
     }
     g.sync();
 
-    // ---- X tile: global -> shared, anti-collapse ----
+    // ---- X tile -> shared, anti-collapse ----
+#ifdef __CUDA_ARCH__
+    if (x_early) {
+#pragma unroll
+        for (int k = 0; k < XR; k++) {
+            const int t = g.lane + k * g.n;
+            if (t < C * N) { if (t >= N) sh.freq[1][t - N] = xr[k]; else sh.freq[0][t] = xr[k]; }
+        }
+    } else
+#endif
     {
-        const int bound = OB_EBANDS[end] << LM;                      // bands >= end were not written by the bands stage
         for (int c = 0; c < C; c++)
             for (int j = g.lane; j < N; j += g.n) sh.freq[c][j] = j < bound ? Xg[c * N + j] : 0.f;
     }
@@ -600,5 +616,5 @@ OB_DEV int ob_synth_frame(const G &g, SH &sh, const ObFrameIR *ir, const float *
     g.sync();
 
     ob_synth_tail(g, sh, pcm, N, CC);
-    return N / sh.ds;
+    return ob_div_ds(N, sh.ds);
 }

@@ -42,6 +42,29 @@ struct ObBlock {
         for (int w = 0; w < (n + 31) >> 5; w++) t += red[w];
         return t;
     }
+    // Scan of affine maps m -> a*m + b, lane order = application order.  (ea, eb): the composition of all lanes BEFORE this one (identity for
+    // lane 0); (ta, tb): of all lanes.  Shuffles inside a warp, the warps' totals through `red`: two barriers instead of two per doubling step.
+    __device__ __forceinline__ void affine_scan(float a, float b, float &ea, float &eb, float &ta, float &tb) const
+    {
+        const int wl = lane & 31, w = lane >> 5, nw = (n + 31) >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float pa = __shfl_up_sync(0xffffffffu, a, o), pb = __shfl_up_sync(0xffffffffu, b, o);
+            if (wl >= o) { b = a * pb + b; a = a * pa; }
+        }
+        float ia = __shfl_up_sync(0xffffffffu, a, 1), ib = __shfl_up_sync(0xffffffffu, b, 1);
+        if (wl == 0) { ia = 1.f; ib = 0.f; }
+        __syncthreads();
+        if (wl == 31) { red[2 * w] = a; red[2 * w + 1] = b; }
+        __syncthreads();
+        float ca = 1.f, cb = 0.f;
+        ea = ia; eb = ib;
+        for (int v = 0; v < nw; v++) {
+            if (v == w) { ea = ia * ca; eb = ia * cb + ib; }
+            cb = red[2 * v] * cb + red[2 * v + 1]; ca = red[2 * v] * ca;
+        }
+        ta = ca; tb = cb;
+    }
 };
 #endif
 
@@ -59,4 +82,5 @@ struct ObSolo {
     OB_SOLO_FN void set_base(int) const {}
     OB_SOLO_FN float sum(float v) const { return v; }
     OB_SOLO_FN uint32_t sum_u32(uint32_t v) const { return v; }
+    OB_SOLO_FN void affine_scan(float a, float b, float &ea, float &eb, float &ta, float &tb) const { ea = 1.f; eb = 0.f; ta = a; tb = b; }
 };
