@@ -162,9 +162,10 @@ OB_DEV void ob_rot_pass(const G &g, float *X, int nblocks, int len, int stride, 
         return;
     }
 #endif
+    const int lgb = ob_log2i(nblocks);                                // nblocks (short blocks) is a power of two: chain t -> (block, residue) by shifts
     for (int t = g.lane; t < chains; t += g.n) {
-        float *x = X + (t / stride) * len;
-        const int r = t % stride;
+        float *x = X + (t & (nblocks - 1)) * len;
+        const int r = t >> lgb;
         // forward sweep over i = r, r+stride, ... < len-stride: the rotated x[i+stride] is carried in a register
         int i = r;
         if (i < len - stride) {
@@ -176,19 +177,17 @@ OB_DEV void ob_rot_pass(const G &g, float *X, int nblocks, int len, int stride, 
             }
             x[i] = x1;
         }
-        // backward sweep covers i = len-2*stride-1 .. 0, restricted to this residue class; x[i] is carried downwards
-        const int last = len - 2 * stride - 1;
-        if (last >= 0) {
-            i = last - ((last - r) % stride + stride) % stride;
-            if (i >= 0) {
-                float x2 = x[i + stride];
-                for (; i >= 0; i -= stride) {
-                    const float x1 = x[i];
-                    x[i + stride] = c * x2 + s * x1;
-                    x2 = c * x1 - s * x2;
-                }
-                x[i + stride] = x2;
+        // backward sweep covers i = len-2*stride-1 .. 0, restricted to this residue class; x[i] is carried downwards.  The forward sweep
+        // stopped at the first i >= len-stride of the class, so the largest one <= len-2*stride-1 is two strides below it.
+        i -= 2 * stride;
+        if (i >= 0) {
+            float x2 = x[i + stride];
+            for (; i >= 0; i -= stride) {
+                const float x1 = x[i];
+                x[i + stride] = c * x2 + s * x1;
+                x2 = c * x1 - s * x2;
             }
+            x[i + stride] = x2;
         }
     }
     g.sync();
@@ -201,14 +200,28 @@ OB_DEV void ob_exp_rotation_inv(const G &g, float *X, int len, int stride, int K
     const int factor = spread == 1 ? 15 : spread == 2 ? 10 : 5;
     const float gain = (float)(1.0f * len) / (float)(len + factor * K);
     const float theta = .5f * (gain * gain);
-    const float c = OB_COSF((.5f * 3.141592653f) * theta);
-    const float s = OB_COSF((.5f * 3.141592653f) * (1.0f - theta));
+    float c, s;
     int stride2 = 0;
-    if (len >= 8 * stride) {
-        stride2 = 1;
-        while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
+#ifdef __CUDA_ARCH__
+    if (G::n == 32) {
+        // the two cosines on two lanes at once, the stride search as one vote: lane k tests candidate k+1 (the predicate is monotone, stride2 <= 13)
+        const float v = OB_COSF((.5f * 3.141592653f) * ((g.lane & 1) ? 1.0f - theta : theta));
+        c = __shfl_sync(0xffffffffu, v, 0); s = __shfl_sync(0xffffffffu, v, 1);
+        if (len >= 8 * stride) {
+            const int k = g.lane + 1;
+            stride2 = 1 + __popc(__ballot_sync(0xffffffffu, (k * k + k) * stride + (stride >> 2) < len));
+        }
+    } else
+#endif
+    {
+        c = OB_COSF((.5f * 3.141592653f) * theta);
+        s = OB_COSF((.5f * 3.141592653f) * (1.0f - theta));
+        if (len >= 8 * stride) {
+            stride2 = 1;
+            while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++;
+        }
     }
-    len = len / stride;
+    len >>= ob_log2i(stride);                                         // stride = short blocks spanned: a power of two
     // one inlined copy of the pass for both strides (code size: see ob_reconstruct_bands)
 #ifdef __CUDACC__
 #pragma unroll 1
@@ -279,7 +292,7 @@ OB_DEV void ob_band_call(const G &g, SH &sh, const ObLeaf *leaves, int leaf_cnt,
         int tf_change, const float *lowband, float *lowband_out, uint32_t seed_in, const ObLcg &step, int spread)
 {
     const int N0 = N, longBlocks = B == 1;
-    int N_B = N / B, time_divide = 0, recombine = 0;
+    int N_B = N >> ob_log2i(B), time_divide = 0, recombine = 0;          // B (short blocks) is a power of two
     float *scratch = sh.scratch, *tmp = sh.tmp;
     if (N == 1) {
         ob_fill_leaf(g, leaves[0], Xb, 0, nullptr, seed_in, step, spread);
