@@ -99,10 +99,9 @@ OB_DEV int ob_ordery(int stride, int i)
 template <class G>
 OB_DEV void ob_hadamard(const G &g, float *X, float *tmp, int N0, int stride, int hadamard, int interleave)
 {
-    const int N = N0 * stride;
-    const ObDiv dv = ob_div_make(N0);
+    const int N = N0 * stride, ls = ob_log2i(stride);                 // stride is a power of two
     for (int t = g.lane; t < N; t += g.n) {
-        const int i = ob_div(t, dv), j = t - i * N0;      // i: block, j: position inside block
+        const int i = t & (stride - 1), j = t >> ls;      // i: block, j: position inside block (any enumeration of the pairs will do)
         const int row = hadamard ? ob_ordery(stride, i) : i;
         if (interleave) tmp[j * stride + i] = X[row * N0 + j];
         else tmp[row * N0 + j] = X[j * stride + i];
@@ -229,6 +228,7 @@ OB_DEV void ob_exp_rotation_inv(const G &g, float *X, int len, int stride, int K
     for (int p = stride2 ? 0 : 1; p < 2; p++) ob_rot_pass(g, X, stride, len, p ? 1 : stride2, p ? c : s, p ? s : c);
 }
 
+#define OB_LEAF_WIN 64
 // Per-warp shared-memory working set of the band-reconstruction stage.  CH = 1: room for mono frames only (5.3 KB instead of 8.5 KB per
 // warp: 30 instead of 24 resident warps per SM, the kernel is occupancy bound); the second-channel halves are then never touched.
 template <int CH>
@@ -238,7 +238,7 @@ struct ObBandsSharedT {
     float norm[CH * OB_NORM_LEN];       // folding source per channel (bands.c:1438)
     float scratch[OB_MAX_BAND];         // transformed copy of the folding source (lowband_scratch)
     float tmp[OB_MAX_BAND];             // Hadamard permutation buffer
-    ObLeaf leaves[32];                  // leaves of the current band (<= 16 per quant_band call, two calls)
+    ObLeaf leaves[OB_LEAF_WIN];         // window of the frame's leaf records: filled when a band's leaves (<= 16 per quant_band call, two calls) are not all inside
     ObBand bands[OB_NB];
 };
 typedef ObBandsSharedT<2> ObBandsShared;
@@ -384,16 +384,33 @@ OB_DEV void ob_reconstruct_bands(const G &g, const ObFrameIR *ir, uint32_t seed_
         for (int j = g.lane; j < (int)(sizeof(ObBand) / 4) * OB_NB; j += g.n) dst[j] = src[j];
     }
     g.sync();
+    int win0 = -2 * OB_LEAF_WIN;                                      // first leaf of the staged window: none yet
     for (int i = 0; i < end; i++) {
         const ObBand br = sh.bands[i];
         const int boff = M * OB_EBANDS[i], Nb = M * (OB_EBANDS[i + 1] - OB_EBANDS[i]);
         const int last = i == end - 1, tf_change = h.tf_change[i];
         const int na = br.leaf_cnt_a, nb = br.leaf_cnt_b;
-        {   // stage this band's leaves (12-byte records as 3 words each) and its pulse vector (as float)
-            const uint32_t *sa = (const uint32_t *)(ir->leaves + br.leaf_begin_a), *sb = (const uint32_t *)(ir->leaves + br.leaf_begin_b);
-            uint32_t *dst = (uint32_t *)sh.leaves;
-            for (int j = g.lane; j < 3 * na; j += g.n) dst[j] = sa[j];
-            for (int j = g.lane; j < 3 * nb; j += g.n) dst[3 * na + j] = sb[j];
+        const ObLeaf *la, *lbv;
+        {   // this band's leaves must lie in the staged window (12-byte records as 3 words each: ~one refill per frame); its pulse vector (as float)
+            int l0 = OB_MAX_LEAVES, l1 = 0;
+            if (na) { l0 = br.leaf_begin_a; l1 = l0 + na; }
+            if (nb) { l0 = ob_imin(l0, (int)br.leaf_begin_b); l1 = ob_imax(l1, (int)br.leaf_begin_b + nb); }
+            la = sh.leaves + ((int)br.leaf_begin_a - win0); lbv = sh.leaves + ((int)br.leaf_begin_b - win0);
+            if (l1 - l0 > OB_LEAF_WIN) {                             // the two calls' leaves are not neighbours (never seen): stage them one by one
+                const uint32_t *sa = (const uint32_t *)(ir->leaves + br.leaf_begin_a), *sb = (const uint32_t *)(ir->leaves + br.leaf_begin_b);
+                uint32_t *dst = (uint32_t *)sh.leaves;
+                for (int j = g.lane; j < 3 * na; j += g.n) dst[j] = sa[j];
+                for (int j = g.lane; j < 3 * nb; j += g.n) dst[3 * (OB_LEAF_WIN / 2) + j] = sb[j];
+                la = sh.leaves; lbv = sh.leaves + OB_LEAF_WIN / 2;
+                win0 = -2 * OB_LEAF_WIN;
+            } else if (l1 > l0 && (l0 < win0 || l1 > win0 + OB_LEAF_WIN)) {
+                win0 = l0;
+                const uint32_t *src = (const uint32_t *)(ir->leaves + win0);
+                uint32_t *dst = (uint32_t *)sh.leaves;
+                const int cnt = 3 * ob_imin(OB_LEAF_WIN, OB_MAX_LEAVES - win0);
+                for (int j = g.lane; j < cnt; j += g.n) dst[j] = src[j];
+                la = sh.leaves + ((int)br.leaf_begin_a - win0); lbv = sh.leaves + ((int)br.leaf_begin_b - win0);
+            }
             const int16_t *iy = ir->iy + boff;
             for (int j = g.lane; j < Nb; j += g.n) Xb[j] = (float)iy[j];
             if (C == 2) for (int j = g.lane; j < Nb; j += g.n) Yb[j] = (float)iy[N + j];
@@ -402,7 +419,6 @@ OB_DEV void ob_reconstruct_bands(const G &g, const ObFrameIR *ir, uint32_t seed_
             for (int j = g.lane; j < boff; j += g.n) norm[j] = .5f * (norm[j] + norm2[j]);
         }
         g.sync();
-        const ObLeaf *la = sh.leaves, *lbv = sh.leaves + na;
         const float *lb1 = br.eff_lowband >= 0 ? norm + br.eff_lowband : nullptr;
         const float *lb2 = br.eff_lowband >= 0 ? norm2 + br.eff_lowband : nullptr;
         float *lo1 = last ? nullptr : norm + boff, *lo2 = last ? nullptr : norm2 + boff;
