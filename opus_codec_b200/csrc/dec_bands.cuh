@@ -252,9 +252,7 @@ OB_DEV void ob_fill_leaf(const G &g, const ObLeaf &lf, float *Xb, int off_in_ban
     float *X = Xb + off_in_band;
     const int n = lf.n;
     if (lf.kind == OB_LEAF_PULSES) {
-        float ryy = 0.f;                                                   // exact: sum of squares of small integers
-        for (int j = g.lane; j < n; j += g.n) ryy += X[j] * X[j];
-        ryy = g.sum(ryy);
+        const float ryy = (float)lf.lcg_before;                            // the vector's squared norm, summed (exactly: small integers) by the symbol stage
         const float gg = OB_RSQRTF(ryy) * lf.gain;                         // normalise_residual (vq.c:121-141)
         for (int j = g.lane; j < n; j += g.n) X[j] = gg * X[j];
         g.sync();

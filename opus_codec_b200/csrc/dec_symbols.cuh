@@ -215,15 +215,16 @@ OB_DEV uint32_t ob_pvq_u(int n, int k) { int a = ob_imin(n, k), b = ob_imax(n, k
 OB_DEV uint32_t ob_pvq_v(int n, int k) { return ob_pvq_u(n, k) + ob_pvq_u(n, k + 1); }
 
 // Writes n pulse counts to y (int16) and returns the collapse mask of extract_collapse_mask (vq.c:143-163)
-// for B blocks of n/B coefficients, computed on the fly.
-OB_DEV uint32_t ob_cwrsi(int n, int k, uint32_t i, int16_t *y, int B)
+// for B blocks of n/B coefficients, computed on the fly; yy: the vector's squared norm (what decode_pulses returns, cwrs.c:535).
+OB_DEV uint32_t ob_cwrsi(int n, int k, uint32_t i, int16_t *y, int B, uint32_t &yy)
 {
+    yy = 0;
     const int blk = B > 1 ? n / B : n;   // coefficients per short block
     int left = blk;                      // coefficients left in the current block
     uint32_t bit = 1, mask = 0;
     uint32_t p;
     int s, k0, val;
-#define OB_EMIT(v) do { *y++ = (int16_t)(v); if (v) mask |= bit; if (--left == 0) { left = blk; bit <<= 1; } } while (0)
+#define OB_EMIT(v) do { *y++ = (int16_t)(v); yy += (uint32_t)((v) * (v)); if (v) mask |= bit; if (--left == 0) { left = blk; bit <<= 1; } } while (0)
     while (n > 2) {
         uint32_t q;
         if (k >= n) {
@@ -542,12 +543,12 @@ OB_DEV_NOINLINE void ob_decode_theta(ObBandCtx &ctx, ObSplit &sp, int N, int &b,
     sp.inv = inv; sp.imid = imid; sp.iside = iside; sp.delta = delta; sp.itheta = itheta;
 }
 
-OB_DEV void ob_emit_leaf(ObBandCtx &ctx, int off, int n, int K, int kind, int B, float gain)
+OB_DEV void ob_emit_leaf(ObBandCtx &ctx, int off, int n, int K, int kind, int B, float gain, uint32_t yy = 0)
 {
     if (ctx.n_leaves < OB_MAX_LEAVES) {
         ObLeaf &l = ctx.ir->leaves[ctx.n_leaves];
         l.off = (uint16_t)off; l.n = (uint8_t)n; l.K = (uint8_t)K; l.kind = (uint8_t)kind; l.B = (uint8_t)B;
-        l.lcg_before = (uint16_t)ctx.lcg; l.gain = gain;
+        l.lcg_before = (uint16_t)(kind == OB_LEAF_PULSES ? yy : ctx.lcg); l.gain = gain;
     }
     ctx.n_leaves++;
 }
@@ -647,8 +648,9 @@ OB_DEV_NOINLINE uint32_t ob_decode_partition(ObBandCtx &ctx, int off, int N, int
                 if (q != 0) {
                     int K = ob_get_pulses(q);
                     uint32_t idx = ctx.ec->uint(ob_pvq_v(f.N, K));
-                    cm = ob_cwrsi(f.N, K, idx, ctx.ir->iy + f.off, f.B);
-                    ob_emit_leaf(ctx, f.off, f.N, K, OB_LEAF_PULSES, f.B, f.gain);
+                    uint32_t yy;
+                    cm = ob_cwrsi(f.N, K, idx, ctx.ir->iy + f.off, f.B, yy);
+                    ob_emit_leaf(ctx, f.off, f.N, K, OB_LEAF_PULSES, f.B, f.gain, yy);
                 } else {
                     uint32_t cm_mask = (1u << f.B) - 1;
                     int fl = f.fill & (int)cm_mask;

@@ -34,7 +34,7 @@ struct ObLeaf {
     uint8_t K;            // pulses (PULSES) / sign bit (ONE)
     uint8_t kind;         // ObLeafKind
     uint8_t B;            // short blocks spanned (stride of exp_rotation, vq.c:74-117)
-    uint16_t lcg_before;  // celt_lcg_rand steps taken in this frame before this leaf (bands.c:1075,1085)
+    uint16_t lcg_before;  // NOISE / FOLD: celt_lcg_rand steps taken in this frame before this leaf (bands.c:1075,1085); PULSES: the pulse vector's squared norm (<= 255^2)
     float gain;           // product of the mid/side gains down the split tree (bands.c:1023-1034)
 };
 
