@@ -539,20 +539,32 @@ OB_DEV int ob_synth_frame(const G &g, SH &sh, const ObFrameIR *ir, const float *
     if (C == 1) for (int i = g.lane; i < OB_NB; i += g.n) sh.oldBandE[i] = fmaxf(sh.oldBandE[i], sh.oldBandE[OB_NB + i]);
     g.sync();
     if (!(h.flags & OB_F_INTRA) && h.loss_in != 0) ob_post_loss_energy(g, sh, LM, end, h.loss_in);
-    for (int c = g.lane; c < C; c += g.n) {
+    {
+        // Only the inter-band predictor `prev` is a recurrence (quant_bands.c:473): one lane per channel runs it (two operations per band) and
+        // leaves prev-before-band-i in sh.gain; the rest of the update is independent per (channel, band) and runs one per lane, with the
+        // reference's operations in the reference's order.
         const int intra = (h.flags & OB_F_INTRA) != 0;
         const float coef = intra ? 0.f : OB_PRED_COEF[LM], beta = intra ? OB_BETA_INTRA[0] : OB_BETA_COEF[LM];
-        float prev = 0.f;
-        for (int i = 0; i < end; i++) {
-            const float q = (float)h.coarse_qi[c * OB_NB + i];
-            float e = fmaxf(-9.f, sh.oldBandE[c * OB_NB + i]);
-            e = coef * e + prev + q;
-            prev = prev + q - beta * q;
+        for (int c = g.lane; c < C; c += g.n) {
+            float prev = 0.f;
+            for (int i = 0; i < end; i++) {
+                const float q = (float)h.coarse_qi[c * OB_NB + i];
+                sh.gain[c * OB_NB + i] = prev;
+                prev = prev + q - beta * q;
+            }
+        }
+        g.sync();
+        for (int t = g.lane; t < C * OB_NB; t += g.n) {
+            const int i = t >= OB_NB ? t - OB_NB : t;
+            if (i >= end) continue;
+            const float q = (float)h.coarse_qi[t];
+            float e = fmaxf(-9.f, sh.oldBandE[t]);
+            e = coef * e + sh.gain[t] + q;
             const int fq = h.fine_quant[i];
-            if (fq > 0) e += ((float)h.fine_q2[c * OB_NB + i] + .5f) * (float)(1 << (14 - fq)) * (1.f / 16384) - .5f;
-            const int fb = h.final_bit[c * OB_NB + i];
+            if (fq > 0) e += ((float)h.fine_q2[t] + .5f) * (float)(1 << (14 - fq)) * (1.f / 16384) - .5f;
+            const int fb = h.final_bit[t];
             if (fb >= 0) e += ((float)fb - .5f) * (float)(1 << (14 - fq - 1)) * (1.f / 16384);
-            sh.oldBandE[c * OB_NB + i] = e;
+            sh.oldBandE[t] = e;
         }
     }
     g.sync();
