@@ -219,42 +219,28 @@ OB_DEV uint32_t ob_pvq_v(int n, int k) { return ob_pvq_u(n, k) + ob_pvq_u(n, k +
 OB_DEV uint32_t ob_cwrsi(int n, int k, uint32_t i, int16_t *y, int B, uint32_t &yy)
 {
     yy = 0;
-    const int blk = B > 1 ? n / B : n;   // coefficients per short block
+    const int blk = n >> (31 - OB_CLZ((uint32_t)B));   // coefficients per short block (B is a power of two)
     int left = blk;                      // coefficients left in the current block
     uint32_t bit = 1, mask = 0;
     uint32_t p;
     int s, k0, val;
 #define OB_EMIT(v) do { *y++ = (int16_t)(v); yy += (uint32_t)((v) * (v)); if (v) mask |= bit; if (--left == 0) { left = blk; bit <<= 1; } } while (0)
+    // One coefficient per iteration: the sign from U(n,k+1), then the largest kk <= k with U(n,kk) <= i (cwrs.c:474-518 does the same search
+    // as two specialised linear scans).  This kernel waits on dependent table loads, not on issue slots, so the first three candidates are
+    // fetched together with U(n,k+1) -- one load round trip decides most coefficients -- and only longer runs fall back to the scan.
     while (n > 2) {
-        uint32_t q;
-        if (k >= n) {
-            const uint32_t *row = OB_PVQ_U_DATA + OB_PVQ_U_ROW[n];
-            p = row[k + 1];
-            s = -(int)(i >= p);
-            i -= p & (uint32_t)s;
-            k0 = k;
-            q = row[n];
-            if (q > i) {
-                k = n;
-                do p = OB_PVQ_U_DATA[OB_PVQ_U_ROW[--k] + n]; while (p > i);
-            } else for (p = row[k]; p > i; p = row[k]) k--;
-            i -= p;
-            val = (k0 - k + s) ^ s;
-            OB_EMIT(val);
-        } else {
-            p = OB_PVQ_U_DATA[OB_PVQ_U_ROW[k] + n];
-            q = OB_PVQ_U_DATA[OB_PVQ_U_ROW[k + 1] + n];
-            if (p <= i && i < q) { i -= p; OB_EMIT(0); }
-            else {
-                s = -(int)(i >= q);
-                i -= q & (uint32_t)s;
-                k0 = k;
-                do p = OB_PVQ_U_DATA[OB_PVQ_U_ROW[--k] + n]; while (p > i);
-                i -= p;
-                val = (k0 - k + s) ^ s;
-                OB_EMIT(val);
-            }
-        }
+        const int km1 = k > 0 ? k - 1 : 0, km2 = k > 1 ? k - 2 : 0;
+        const uint32_t pk1 = ob_pvq_u(n, k + 1), u0 = ob_pvq_u(n, k), u1 = ob_pvq_u(n, km1), u2 = ob_pvq_u(n, km2);
+        s = -(int)(i >= pk1);
+        i -= pk1 & (uint32_t)s;
+        k0 = k;
+        if (u0 <= i) p = u0;
+        else if (u1 <= i) { p = u1; k = km1; }
+        else if (u2 <= i) { p = u2; k = km2; }
+        else { k -= 3; for (p = ob_pvq_u(n, k); p > i; p = ob_pvq_u(n, k)) k--; }
+        i -= p;
+        val = (k0 - k + s) ^ s;
+        OB_EMIT(val);
         n--;
     }
     p = 2 * (uint32_t)k + 1;
