@@ -393,8 +393,8 @@ def run_live_leg(args, L, local, world, rank, dev, barrier):
     z3 = np.load(os.path.join(ROOT, "tests", "golden", "cfg3_stereo_20ms_96k_cbr.npz"))
     zp = np.load(POOL)
     NSTEP, WARM = 6, 3
-    for key, CC, pk0, ln0, rg0, sizes in (("decode_mono_64k", 1, zp["packets"], zp["lens"], zp["dec_rng"], (4096, 16384, 65536, 131072, 147456, 163840, 196608)),
-                                          ("decode_stereo_96k", 2, z3["packets"], z3["lens"], z3["dec_rng"], (4096, 16384, 65536, 73728, 81920, 98304))):
+    for key, CC, pk0, ln0, rg0, sizes in (("decode_mono_64k", 1, zp["packets"], zp["lens"], zp["dec_rng"], (4096, 16384, 65536, 131072, 163840, 180224, 196608)),
+                                          ("decode_stereo_96k", 2, z3["packets"], z3["lens"], z3["dec_rng"], (4096, 16384, 65536, 81920, 90112, 98304, 114688))):
         rows, cap = [], 0
         stride = pk0.shape[2]
         for S in sizes:

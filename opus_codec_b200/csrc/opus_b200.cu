@@ -572,6 +572,13 @@ static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *p
     int nchunks = total >= 400000 ? 6 : (total >= 65536 ? 3 : (total >= 16384 ? 2 : 1));      // 819 200 frames, blocking call: 3 chunks 96.8 ms, 6 chunks 89.4 ms; chunks as stream ranges
                                                                                                // (contiguous copies instead of 2-D ones): no gain (97.9 ms)
       // measured (204 800 frames, two calls in flight): 1: 202 k, 2: 208 k, 3: 209 k, 5: 209 k (int16: 205 / 206 / 206 / 200 k), 8: 202 k
+    if (n_frames < nchunks) {
+        // few frames per stream (the live case, F = 1): chunks are stream ranges, kernels alternate between two compute streams, and the copies of
+        // chunk k hide behind the kernels of chunk k+1.  Measured blocking latency of one call, mono: 131 072 streams 17.6 ms with 3 chunks, 14.5 with
+        // 12, 14.0 with 16 (24 / 32: no further gain); 65 536 streams 9.5 -> 7.6 ms; 163 840 streams 22.9 -> 18.4 ms.
+        const size_t by_size = total / 8192;
+        if (by_size > (size_t)nchunks) nchunks = by_size > OB_MAX_CHUNKS ? OB_MAX_CHUNKS : (int)by_size;
+    }
     if (const char *v = getenv("OB_DEC_CHUNKS")) { const int t = atoi(v); if (t >= 1) nchunks = t; }      // tuning aid
     if (nchunks > OB_MAX_CHUNKS) nchunks = OB_MAX_CHUNKS;
     const size_t pf = (size_t)frame_size * d->CC;
