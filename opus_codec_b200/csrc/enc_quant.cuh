@@ -375,11 +375,25 @@ OB_STAGE void ob_exp_rotation(const G &g, float *X, int len, int dir, int stride
     const int factor = spread == 1 ? 15 : spread == 2 ? 10 : 5;
     const float gain = (float)(1.0f * len) / (float)(len + factor * K);
     const float theta = .5f * (gain * gain);
-    const float c = OB_COSF((.5f * 3.141592653f) * theta);
-    const float s = OB_COSF((.5f * 3.141592653f) * (1.0f - theta));
+    float c, s;
     int stride2 = 0;
-    if (len >= 8 * stride) { stride2 = 1; while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++; }
-    len = len / stride;
+#ifdef __CUDA_ARCH__
+    if (G::n == 32) {
+        // as in the decoder (dec_bands.cuh ob_exp_rotation_inv): the two cosines on two lanes at once, the stride search as one vote
+        const float v = OB_COSF((.5f * 3.141592653f) * ((g.lane & 1) ? 1.0f - theta : theta));
+        c = __shfl_sync(0xffffffffu, v, 0); s = __shfl_sync(0xffffffffu, v, 1);
+        if (len >= 8 * stride) {
+            const int k = g.lane + 1;
+            stride2 = 1 + __popc(__ballot_sync(0xffffffffu, (k * k + k) * stride + (stride >> 2) < len));
+        }
+    } else
+#endif
+    {
+        c = OB_COSF((.5f * 3.141592653f) * theta);
+        s = OB_COSF((.5f * 3.141592653f) * (1.0f - theta));
+        if (len >= 8 * stride) { stride2 = 1; while ((stride2 * stride2 + stride2) * stride + (stride >> 2) < len) stride2++; }
+    }
+    len >>= ob_log2i(stride);                                         // stride = short blocks spanned: a power of two
     // dir < 0: (stride2: s, c) then (1: c, s);  dir > 0: (1: c, -s) then (stride2: s, -c) -- one inlined copy of the pass for all four
 #ifdef __CUDACC__
 #pragma unroll 1
@@ -461,22 +475,26 @@ OB_STAGE float ob_pvq_search(const G &g, float *X, int *iy, float *y, int K, int
 {
     float xy = 0, yy = 0;
     int pulsesLeft = K;
+    OB_ROLLED_G
     for (int j = g.lane; j < N; j += g.n) { iy[j] = 0; y[j] = 0; }
     g.sync();
     if (K > (N >> 1)) {
         float sum = ob_psum(g, N, 0.f, [&](int j) { return fabsf(X[j]); });
         if (!(sum > 1e-15f && sum < 64)) {
             g.sync();
+            OB_ROLLED_G
             for (int j = g.lane; j < N; j += g.n) X[j] = j == 0 ? (X[0] < 0 ? -1.f : 1.f) : 0.f;
             g.sync();
             sum = 1.f;
         }
         const float rcp = (K + 0.8f) * (1.f / sum);
+        OB_ROLLED_G
         for (int j = g.lane; j < N; j += g.n) { const int v = (int)floor((double)(rcp * fabsf(X[j]))); iy[j] = v; y[j] = (float)v; }
         g.sync();
         ob_psum2(g, N, yy, xy, [&](int j, float &a, float &b) { a = a + y[j] * y[j]; b = b + fabsf(X[j]) * y[j]; });
         pulsesLeft -= (int)ob_psum_u32(g, N, [&](int j) { return (uint32_t)iy[j]; });
         g.sync();
+        OB_ROLLED_G
         for (int j = g.lane; j < N; j += g.n) y[j] *= 2;
         g.sync();
     }
@@ -498,6 +516,7 @@ OB_STAGE float ob_pvq_search(const G &g, float *X, int *iy, float *y, int K, int
         if (g.lane == 0) { y[best_id] += 2; iy[best_id]++; }
         g.sync();
     }
+    OB_ROLLED_G
     for (int j = g.lane; j < N; j += g.n) if (X[j] < 0) iy[j] = -iy[j];
     g.sync();
     return yy;
@@ -582,6 +601,7 @@ OB_DEV uint32_t ob_alg_quant(const G &g, ObEncBandsShared &S, float *X, int N, i
     enc.uint(ob_icwrs(g, N, iy), ob_pvq_v(N, K));
     if (resynth) {
         const float gg = (1.f / sqrtf(yy)) * gain;                      // normalise_residual (vq.c:121-141)
+        OB_ROLLED_G
         for (int i = g.lane; i < N; i += g.n) X[i] = gg * (float)iy[i];
         g.sync();
         ob_exp_rotation(g, X, N, -1, B, K, spread);
@@ -594,6 +614,7 @@ OB_DEV void ob_renormalise(const G &g, float *X, int N, float gain)             
 {
     const float E = 1e-15f + ob_psum(g, N, 0.f, [&](int i) { return X[i] * X[i]; });
     const float gg = (1.f / sqrtf(E)) * gain;
+    OB_ROLLED_G
     for (int i = g.lane; i < N; i += g.n) X[i] = gg * X[i];
     g.sync();
 }
@@ -637,12 +658,14 @@ OB_DEV void ob_intensity_stereo(const G &g, float *X, const float *Y, const floa
     const float left = bandE[i], right = bandE[i + OB_NB];
     const float norm = 1e-15f + sqrtf(1e-15f + left * left + right * right);
     const float a1 = left / norm, a2 = right / norm;
+    OB_ROLLED_G
     for (int j = g.lane; j < N; j += g.n) X[j] = a1 * X[j] + a2 * Y[j];
     g.sync();
 }
 template <class G>
 OB_DEV void ob_stereo_split(const G &g, float *X, float *Y, int N)                                           // bands.c:412-424
 {
+    OB_ROLLED_G
     for (int j = g.lane; j < N; j += g.n) { const float l = .70710678f * X[j], r = .70710678f * Y[j]; X[j] = l + r; Y[j] = r - l; }
     g.sync();
 }
@@ -655,6 +678,7 @@ OB_DEV void ob_enc_stereo_merge(const G &g, float *X, float *Y, float mid, int N
     const float El = mid * mid + side - 2 * xp, Er = mid * mid + side + 2 * xp;
     if (Er < 6e-4f || El < 6e-4f) { for (int j = g.lane; j < N; j += g.n) Y[j] = X[j]; g.sync(); return; }
     const float lgain = 1.f / sqrtf(El), rgain = 1.f / sqrtf(Er);
+    OB_ROLLED_G
     for (int j = g.lane; j < N; j += g.n) { const float l = mid * X[j], r = Y[j]; X[j] = lgain * (l - r); Y[j] = rgain * (l + r); }
     g.sync();
 }
@@ -790,6 +814,7 @@ OB_DEV uint32_t ob_enc_partition(const G &g, ObEncBandsShared &S, ObEncBandCtx &
                         const float *lowband = f.lowband;
                         const ObLcg first = ob_lcg_pow((uint32_t)g.lane + 1u), step = ob_lcg_pow((uint32_t)g.n);
                         uint32_t seed = first.a * ctx.seed + first.c;
+                        OB_ROLLED_G
                         for (int j = g.lane; j < N; j += g.n) {
                             if (lowband == nullptr) X[j] = (float)((int32_t)seed >> 20);
                             else X[j] = lowband[j] + ((seed & 0x8000u) ? (1.0f / 256) : -(1.0f / 256));
@@ -848,11 +873,12 @@ OB_DEV uint32_t ob_enc_band(const G &g, ObEncBandsShared &S, ObEncBandCtx &ctx, 
         float *lowband_scratch, int fill)
 {
     const int N0 = N, longBlocks = B == 1;
-    int N_B = N / B, N_B0, B0 = B, time_divide = 0, recombine = 0, tf_change = ctx.tf_change;
+    int N_B = N >> ob_log2i(B), N_B0, B0 = B, time_divide = 0, recombine = 0, tf_change = ctx.tf_change;      // B (short blocks) is a power of two
     uint32_t cm;
     if (N == 1) { g.sync(); cm = ob_enc_band_n1(ctx, X, nullptr, lowband_out); g.sync(); return cm; }
     if (tf_change > 0) recombine = tf_change;
     if (lowband_scratch && lowband && (recombine || ((N_B & 1) == 0 && tf_change < 0) || B0 > 1)) {
+        OB_ROLLED_G
         for (int j = g.lane; j < N; j += g.n) lowband_scratch[j] = lowband[j];
         g.sync();
         lowband = lowband_scratch;
@@ -892,6 +918,7 @@ OB_DEV uint32_t ob_enc_band(const G &g, ObEncBandsShared &S, ObEncBandCtx &ctx, 
         B <<= recombine;
         if (lowband_out) {
             const float n = sqrtf((float)N0);
+            OB_ROLLED_G
             for (int j = g.lane; j < N0; j += g.n) lowband_out[j] = n * X[j];
             g.sync();
         }
@@ -994,6 +1021,7 @@ OB_STAGE void ob_enc_all_bands(const G &g, int end, const float *Xg, int C, int 
         ctx.pace = 64 + 64 * i;
         g.pace(ctx.pace++);
         g.sync();
+        OB_ROLLED_G
         for (int j = g.lane; j < N; j += g.n) { X[j] = Xg[M * OB_EBANDS[i] + j]; if (C == 2) Y[j] = Xg[N_ + M * OB_EBANDS[i] + j]; }
         g.sync();
         tell = (int32_t)ec.tell_frac();
@@ -1062,6 +1090,7 @@ OB_STAGE void ob_enc_all_bands(const G &g, int end, const float *Xg, int C, int 
                 ec_save = ec; ctx_save = ctx;
                 bytes_buf = ec_save.buf + ec_save.offs;
                 save_bytes = ec_save.storage - ec_save.offs;
+                OB_ROLLED_G
                 for (int j = g.lane; j < N; j += g.n) { W.X_save[j] = X[j]; W.Y_save[j] = Y[j]; }
                 g.sync();
             }
@@ -1072,10 +1101,12 @@ OB_STAGE void ob_enc_all_bands(const G &g, int end, const float *Xg, int C, int 
                 if (t == 1) {                                          // keep trial 0's result, rewind to the snapshot
                     cm2 = x_cm; ec_save2 = ec; ctx_save2 = ctx;
                     g.sync();
+                    OB_ROLLED_G
                     for (int j = g.lane; j < N; j += g.n) { W.X_save2[j] = X[j]; W.Y_save2[j] = Y[j]; if (!last) W.norm_save2[j] = lo1[j]; }
                     for (uint32_t k = g.lane; k < save_bytes; k += g.n) W.bytes_save[k] = bytes_buf[k];
                     g.sync();
                     { const int pc = ctx.pace; ec = ec_save; ctx = ctx_save; ctx.pace = pc; }
+                    OB_ROLLED_G
                     for (int j = g.lane; j < N; j += g.n) { X[j] = W.X_save[j]; Y[j] = W.Y_save[j]; }
                     g.sync();
                 }
@@ -1089,6 +1120,7 @@ OB_STAGE void ob_enc_all_bands(const G &g, int end, const float *Xg, int C, int 
             if (rdo && dist0 >= dist1) {
                 { const int pc = ctx.pace; x_cm = cm2; ec = ec_save2; ctx = ctx_save2; ctx.pace = pc; }
                 g.sync();
+                OB_ROLLED_G
                 for (int j = g.lane; j < N; j += g.n) { X[j] = W.X_save2[j]; Y[j] = W.Y_save2[j]; if (!last) lo1[j] = W.norm_save2[j]; }
                 for (uint32_t k = g.lane; k < save_bytes; k += g.n) bytes_buf[k] = W.bytes_save[k];
                 g.sync();

@@ -61,8 +61,14 @@ template <> struct ObOrder<ObSolo> { static constexpr int value = 1; };
 
 #ifdef __CUDACC__
 #define OB_COOP __device__ __forceinline__
+// lane-strided loops of the warp-per-stream encoder run 1-6 iterations (a band is <= 176 coefficients): unrolled four times they only cost
+// instruction-cache footprint, which is what bounds that kernel
+#define OB_ROLLED _Pragma("unroll 1")
+#define OB_ROLLED_G _Pragma("unroll (ObOrder<G>::value == 1 ? 4 : 1)")      // inside template <class G>: the one-lane instantiation keeps its unrolling
 #else
 #define OB_COOP static inline
+#define OB_ROLLED
+#define OB_ROLLED_G
 #endif
 
 #ifdef __CUDACC__
@@ -70,6 +76,7 @@ template <> struct ObOrder<ObSolo> { static constexpr int value = 1; };
 template <class F> OB_COOP float ob_psum(const ObWarp &g, int n, float init, F f)
 {
     float s = 0.f;
+    OB_ROLLED
     for (int j = g.lane; j < n; j += 32) s = s + f(j);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s = s + __shfl_xor_sync(0xffffffffu, s, o);
@@ -78,6 +85,7 @@ template <class F> OB_COOP float ob_psum(const ObWarp &g, int n, float init, F f
 template <class F> OB_COOP void ob_psum2(const ObWarp &g, int n, float &a, float &b, F f)       // f(j, a, b) accumulates into a and b
 {
     float sa = 0.f, sb = 0.f;
+    OB_ROLLED
     for (int j = g.lane; j < n; j += 32) f(j, sa, sb);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { sa = sa + __shfl_xor_sync(0xffffffffu, sa, o); sb = sb + __shfl_xor_sync(0xffffffffu, sb, o); }
@@ -86,6 +94,7 @@ template <class F> OB_COOP void ob_psum2(const ObWarp &g, int n, float &a, float
 template <class F> OB_COOP float ob_pmax(const ObWarp &g, int n, float init, F f)
 {
     float s = init;
+    OB_ROLLED
     for (int j = g.lane; j < n; j += 32) { const float v = f(j); s = v > s ? v : s; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const float v = __shfl_xor_sync(0xffffffffu, s, o); s = v > s ? v : s; }
@@ -94,12 +103,14 @@ template <class F> OB_COOP float ob_pmax(const ObWarp &g, int n, float init, F f
 template <class F> OB_COOP uint32_t ob_psum_u32(const ObWarp &g, int n, F f)
 {
     uint32_t s = 0;
+    OB_ROLLED
     for (int j = g.lane; j < n; j += 32) s += f(j);
     return __reduce_add_sync(0xffffffffu, s);
 }
 template <class F> OB_COOP uint32_t ob_por_u32(const ObWarp &g, int n, F f)
 {
     uint32_t s = 0;
+    OB_ROLLED
     for (int j = g.lane; j < n; j += 32) s |= f(j);
     return __reduce_or_sync(0xffffffffu, s);
 }

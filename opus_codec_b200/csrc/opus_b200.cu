@@ -569,9 +569,10 @@ static int32_t ob_decode_submit(ObDecoder *d, int32_t n_frames, const uint8_t *p
     // d->stream, copies on d->copy_stream, one event per chunk).  With several frames per stream the chunks are FRAME windows
     // of all streams: every launch keeps the full stream-level parallelism the synthesis kernel needs (one block per stream),
     // and the per-stream state simply carries over from launch to launch.  Single-frame calls are split by stream ranges.
-    int nchunks = total >= 400000 ? 6 : (total >= 65536 ? 3 : (total >= 16384 ? 2 : 1));      // 819 200 frames, blocking call: 3 chunks 96.8 ms, 6 chunks 89.4 ms; chunks as stream ranges
-                                                                                               // (contiguous copies instead of 2-D ones): no gain (97.9 ms)
-      // measured (204 800 frames, two calls in flight): 1: 202 k, 2: 208 k, 3: 209 k, 5: 209 k (int16: 205 / 206 / 206 / 200 k), 8: 202 k
+    // measured: 819 200 mono frames (F = 200), blocking call: 3 chunks 96.8 ms, 6 chunks 89.4 ms, chunks as stream ranges (contiguous copies instead of
+    // 2-D ones) 97.9 ms; 163 840 stereo frames (F = 10), two calls in flight: 2 / 3 / 5 / 10 chunks -> 120 / 123 / 126 / 96 k audio-s/s;
+    // 204 800 mono frames (F = 50), two calls in flight: 1: 202 k, 2: 208 k, 3: 209 k, 5: 209 k (int16: 205 / 206 / 206 / 200 k), 8: 202 k
+    int nchunks = total >= 400000 ? 6 : (total >= 131072 ? 5 : (total >= 65536 ? 3 : (total >= 16384 ? 2 : 1)));
     if (n_frames < nchunks) {
         // few frames per stream (the live case, F = 1): chunks are stream ranges, kernels alternate between two compute streams, and the copies of
         // chunk k hide behind the kernels of chunk k+1.  Measured blocking latency of one call, mono: 131 072 streams 17.6 ms with 3 chunks, 14.5 with
