@@ -869,7 +869,7 @@ OB_DEV uint32_t ob_enc_band_n1(ObEncBandCtx &ctx, float *X, float *Y, float *low
 
 // quant_band (bands.c:1109-1231), encode = 1
 template <class G>
-OB_DEV uint32_t ob_enc_band(const G &g, ObEncBandsShared &S, ObEncBandCtx &ctx, float *X, int N, int b, int B, float *lowband, int LM, float *lowband_out, float gain,
+OB_DEV uint32_t ob_enc_band_impl(const G &g, ObEncBandsShared &S, ObEncBandCtx &ctx, float *X, int N, int b, int B, float *lowband, int LM, float *lowband_out, float gain,
         float *lowband_scratch, int fill)
 {
     const int N0 = N, longBlocks = B == 1;
@@ -924,6 +924,22 @@ OB_DEV uint32_t ob_enc_band(const G &g, ObEncBandsShared &S, ObEncBandCtx &ctx, 
         }
         cm &= (1u << B) - 1;
     }
+    return cm;
+}
+
+// quant_band is used from two places (mono / dual-stereo bands, and the mid and side of a joint-stereo band): ONE out-of-line copy -- the
+// split tree, the PVQ stage and the transforms around them are ~4 k instructions, and the warp-per-stream kernel is bound by its instruction
+// footprint.  As in every OB_STAGE the range coder works on a register copy of its state inside.
+template <class G>
+OB_STAGE uint32_t ob_enc_band(const G &g, ObEncBandsShared &S, ObEncBandCtx &ctx_io, float *X, int N, int b, int B, float *lowband, int LM, float *lowband_out, float gain,
+        float *lowband_scratch, int fill)
+{
+    ObEncBandCtx ctx = ctx_io;
+    ObRangeEnc ec = *ctx_io.ec;
+    ctx.ec = &ec;
+    const uint32_t cm = ob_enc_band_impl(g, S, ctx, X, N, b, B, lowband, LM, lowband_out, gain, lowband_scratch, fill);
+    *ctx_io.ec = ec;
+    ctx_io.remaining_bits = ctx.remaining_bits; ctx_io.seed = ctx.seed; ctx_io.pace = ctx.pace;
     return cm;
 }
 
