@@ -14,6 +14,13 @@
 #include "ob_group.cuh"
 #include "dec_symbols.cuh"   // OB_DEV, tables
 
+// lane-strided loops over a band run 1-6 iterations on a warp: kept rolled (code size; see OB_ROLLED in ob_coop.cuh)
+#if defined(__CUDACC__) && !defined(OB_BANDS_UNROLL)
+#define OB_ROLLED_BANDS _Pragma("unroll 1")
+#else
+#define OB_ROLLED_BANDS
+#endif
+
 #ifdef __CUDACC__
 #define OB_SQRTF(x) sqrtf(x)
 #else
@@ -75,6 +82,7 @@ OB_DEV void ob_haar1(const G &g, float *X, int N0, int stride)
 {
     N0 >>= 1;
     const int total = N0 * stride, ls = ob_log2i(stride);
+    OB_ROLLED_BANDS
     for (int t = g.lane; t < total; t += g.n) {
         const int i = t & (stride - 1), j = t >> ls;
         const float t1 = .70710678f * X[stride * 2 * j + i], t2 = .70710678f * X[stride * (2 * j + 1) + i];
@@ -100,6 +108,7 @@ template <class G>
 OB_DEV void ob_hadamard(const G &g, float *X, float *tmp, int N0, int stride, int hadamard, int interleave)
 {
     const int N = N0 * stride, ls = ob_log2i(stride);                 // stride is a power of two
+    OB_ROLLED_BANDS
     for (int t = g.lane; t < N; t += g.n) {
         const int i = t & (stride - 1), j = t >> ls;      // i: block, j: position inside block (any enumeration of the pairs will do)
         const int row = hadamard ? ob_ordery(stride, i) : i;
@@ -107,6 +116,7 @@ OB_DEV void ob_hadamard(const G &g, float *X, float *tmp, int N0, int stride, in
         else tmp[row * N0 + j] = X[j * stride + i];
     }
     g.sync();
+    OB_ROLLED_BANDS
     for (int t = g.lane; t < N; t += g.n) X[t] = tmp[t];
     g.sync();
 }
@@ -162,6 +172,7 @@ OB_DEV void ob_rot_pass(const G &g, float *X, int nblocks, int len, int stride, 
     }
 #endif
     const int lgb = ob_log2i(nblocks);                                // nblocks (short blocks) is a power of two: chain t -> (block, residue) by shifts
+    OB_ROLLED_BANDS
     for (int t = g.lane; t < chains; t += g.n) {
         float *x = X + (t & (nblocks - 1)) * len;
         const int r = t >> lgb;
@@ -254,10 +265,12 @@ OB_DEV void ob_fill_leaf(const G &g, const ObLeaf &lf, float *Xb, int off_in_ban
     if (lf.kind == OB_LEAF_PULSES) {
         const float ryy = (float)lf.lcg_before;                            // the vector's squared norm, summed (exactly: small integers) by the symbol stage
         const float gg = OB_RSQRTF(ryy) * lf.gain;                         // normalise_residual (vq.c:121-141)
+        OB_ROLLED_BANDS
         for (int j = g.lane; j < n; j += g.n) X[j] = gg * X[j];
         g.sync();
         ob_exp_rotation_inv(g, X, n, lf.B, lf.K, spread);
     } else if (lf.kind == OB_LEAF_ZERO) {
+        OB_ROLLED_BANDS
         for (int j = g.lane; j < n; j += g.n) X[j] = 0.f;
         g.sync();
     } else if (lf.kind == OB_LEAF_ONE) {
@@ -268,6 +281,7 @@ OB_DEV void ob_fill_leaf(const G &g, const ObLeaf &lf, float *Xb, int off_in_ban
         const ObLcg first = ob_lcg_pow((uint32_t)lf.lcg_before + (uint32_t)g.lane + 1u);
         uint32_t seed = first.a * seed_in + first.c;
         float e = 0.f;
+        OB_ROLLED_BANDS
         for (int j = g.lane; j < n; j += g.n) {
             float v;
             if (lf.kind == OB_LEAF_NOISE) v = (float)((int32_t)seed >> 20);
@@ -278,6 +292,7 @@ OB_DEV void ob_fill_leaf(const G &g, const ObLeaf &lf, float *Xb, int off_in_ban
         }
         e = 1e-15f + g.sum(e);
         const float gg = OB_RSQRTF(e) * lf.gain;                           // renormalise_vector (vq.c:383-407)
+        OB_ROLLED_BANDS
         for (int j = g.lane; j < n; j += g.n) X[j] = gg * X[j];
         g.sync();
     }
@@ -302,6 +317,7 @@ OB_DEV void ob_band_call(const G &g, SH &sh, const ObLeaf *leaves, int leaf_cnt,
     float *lb = nullptr;
     if (lowband) {
         if (recombine || ((N_B & 1) == 0 && tf_change < 0) || B > 1) {
+            OB_ROLLED_BANDS
             for (int j = g.lane; j < N; j += g.n) scratch[j] = lowband[j];
             g.sync();
             lb = scratch;
@@ -336,6 +352,7 @@ OB_DEV void ob_band_call(const G &g, SH &sh, const ObLeaf *leaves, int leaf_cnt,
     }
     if (lowband_out) {
         const float n = OB_SQRTF((float)N0);
+        OB_ROLLED_BANDS
         for (int j = g.lane; j < N0; j += g.n) lowband_out[j] = n * Xb[j];
         g.sync();
     }
@@ -346,16 +363,19 @@ template <class G>
 OB_DEV void ob_stereo_merge(const G &g, float *X, float *Y, float mid, int N)
 {
     float xp = 0.f, side = 0.f;
+    OB_ROLLED_BANDS
     for (int j = g.lane; j < N; j += g.n) { xp += Y[j] * X[j]; side += Y[j] * Y[j]; }
     xp = g.sum(xp); side = g.sum(side);
     xp = mid * xp;
     const float El = mid * mid + side - 2 * xp, Er = mid * mid + side + 2 * xp;
     if (Er < 6e-4f || El < 6e-4f) {
+        OB_ROLLED_BANDS
         for (int j = g.lane; j < N; j += g.n) Y[j] = X[j];
         g.sync();
         return;
     }
     const float lgain = OB_RSQRTF(El), rgain = OB_RSQRTF(Er);
+    OB_ROLLED_BANDS
     for (int j = g.lane; j < N; j += g.n) {
         const float l = mid * X[j], r = Y[j];
         X[j] = lgain * (l - r);
@@ -379,6 +399,7 @@ OB_DEV void ob_reconstruct_bands(const G &g, const ObFrameIR *ir, uint32_t seed_
     {   // band records -> shared (16-byte records as 4 words each)
         const uint32_t *src = (const uint32_t *)ir->bands;
         uint32_t *dst = (uint32_t *)sh.bands;
+        OB_ROLLED_BANDS
         for (int j = g.lane; j < (int)(sizeof(ObBand) / 4) * OB_NB; j += g.n) dst[j] = src[j];
     }
     g.sync();
@@ -397,7 +418,9 @@ OB_DEV void ob_reconstruct_bands(const G &g, const ObFrameIR *ir, uint32_t seed_
             if (l1 - l0 > OB_LEAF_WIN) {                             // the two calls' leaves are not neighbours (never seen): stage them one by one
                 const uint32_t *sa = (const uint32_t *)(ir->leaves + br.leaf_begin_a), *sb = (const uint32_t *)(ir->leaves + br.leaf_begin_b);
                 uint32_t *dst = (uint32_t *)sh.leaves;
+                OB_ROLLED_BANDS
                 for (int j = g.lane; j < 3 * na; j += g.n) dst[j] = sa[j];
+                OB_ROLLED_BANDS
                 for (int j = g.lane; j < 3 * nb; j += g.n) dst[3 * (OB_LEAF_WIN / 2) + j] = sb[j];
                 la = sh.leaves; lbv = sh.leaves + OB_LEAF_WIN / 2;
                 win0 = -2 * OB_LEAF_WIN;
@@ -406,14 +429,17 @@ OB_DEV void ob_reconstruct_bands(const G &g, const ObFrameIR *ir, uint32_t seed_
                 const uint32_t *src = (const uint32_t *)(ir->leaves + win0);
                 uint32_t *dst = (uint32_t *)sh.leaves;
                 const int cnt = 3 * ob_imin(OB_LEAF_WIN, OB_MAX_LEAVES - win0);
+                OB_ROLLED_BANDS
                 for (int j = g.lane; j < cnt; j += g.n) dst[j] = src[j];
                 la = sh.leaves + ((int)br.leaf_begin_a - win0); lbv = sh.leaves + ((int)br.leaf_begin_b - win0);
             }
             const int16_t *iy = ir->iy + boff;
+            OB_ROLLED_BANDS
             for (int j = g.lane; j < Nb; j += g.n) Xb[j] = (float)iy[j];
             if (C == 2) for (int j = g.lane; j < Nb; j += g.n) Yb[j] = (float)iy[N + j];
         }
         if (br.flags & 8) {                                          // leaving dual stereo (bands.c:1551-1558)
+            OB_ROLLED_BANDS
             for (int j = g.lane; j < boff; j += g.n) norm[j] = .5f * (norm[j] + norm2[j]);
         }
         g.sync();
@@ -460,11 +486,13 @@ OB_DEV void ob_reconstruct_bands(const G &g, const ObFrameIR *ir, uint32_t seed_
                 const float mid = (1.f / 32768) * br.imid;
                 ob_stereo_merge(g, Xb, Yb, mid, Nb);
                 if (br.flags & 1) {
+                    OB_ROLLED_BANDS
                     for (int j = g.lane; j < Nb; j += g.n) Yb[j] = -Yb[j];
                     g.sync();
                 }
             }
         }
+        OB_ROLLED_BANDS
         for (int j = g.lane; j < Nb; j += g.n) Xout[boff + j] = Xb[j];
         if (C == 2) for (int j = g.lane; j < Nb; j += g.n) Xout[N + boff + j] = Yb[j];
         g.sync();

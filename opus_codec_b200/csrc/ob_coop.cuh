@@ -64,7 +64,7 @@ template <> struct ObOrder<ObSolo> { static constexpr int value = 1; };
 // lane-strided loops of the warp-per-stream encoder run 1-6 iterations (a band is <= 176 coefficients): unrolled four times they only cost
 // instruction-cache footprint, which is what bounds that kernel
 #define OB_ROLLED _Pragma("unroll 1")
-#define OB_ROLLED_G _Pragma("unroll (ObOrder<G>::value == 1 ? 4 : 1)")      // inside template <class G>: the one-lane instantiation keeps its unrolling
+#define OB_ROLLED_G _Pragma("unroll 1")
 #else
 #define OB_COOP static inline
 #define OB_ROLLED

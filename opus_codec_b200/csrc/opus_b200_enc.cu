@@ -431,7 +431,10 @@ static int ob_enc_launch(ObEncoder *e, int F, const float *d_pcm, int frame_size
     if (f0 == 0) OB_CUDA(cudaEventRecord(e->ev[0], e->stream));
     if (an && ob_enc_plan(e) < e->S) OB_CUDA(cudaStreamWaitEvent(e->stream, e->an_ev[k & 3], 0));
     OB_CUDA(cudaMemsetAsync(e->d_counter, 0, sizeof(int), e->stream));
-    int paced = 3;                                                 // pace level (0 none, 1 stages, 2 + bands, 3 + leaves) | slack << 4
+    // pace level (0 none, 1 stages, 2 + bands, 3 + leaves) | slack << 4.  Measured, ms per call of 4 frames, 2 368 / 16 384 streams, after the band
+    // loop's code was cut to ~11 k instructions: 0: 41.9 / 238.5, 1: 31.4 / 199.3, 2: 23.6 / 161.6, 3: 24.6 / 168.3; a slack of 1-4 ids: no gain.
+    // (With the 17 k-instruction band loop of the first version level 3 was the best: 50.7 against 53.7 ms per frame step of 16 384 streams.)
+    int paced = 2;
     if (const char *v = getenv("OB_ENC_PACED")) paced = atoi(v);                                            // tuning aid
     // Which streams go where.  WARP / THREAD: all of them.  AUTO: below the crossover one warp per stream (latency), from the crossover up one
     // lane per stream (throughput).  A SPLIT of a bulk batch between the two mappings (first n_warp streams on a second CUDA stream, 12 warps
