@@ -170,7 +170,7 @@ int32_t ob_encode_float_device(ObEncoder *enc, int32_t n_frames, const float *d_
  * set_packet_loss_perc, set_lsb_depth); one value for the whole batch.  bitrate: bits/s, -1000 = OPUS_AUTO, -1 = OPUS_BITRATE_MAX. */
 int32_t ob_encoder_set_bitrate(ObEncoder *enc, int32_t bitrate);
 /* Batch-only knob (no libopus counterpart): how the batch is laid onto the GPU.  OB_ENC_MAP_WARP: one warp per stream, cooperative stages --
- * the low-latency mapping (a frame step of <= ~2 400 streams takes ~7 ms), packets in the warp's summation order.  OB_ENC_MAP_THREAD: one
+ * the low-latency mapping (a frame step of <= ~2 400 streams takes ~5.5 ms), packets in the warp's summation order.  OB_ENC_MAP_THREAD: one
  * lane per stream, 32 streams per instruction -- the bulk mapping, packets bit-identical to the reference's C build.  OB_ENC_MAP_AUTO (default):
  * WARP below OB_ENC_MAP_CROSSOVER streams, THREAD from there up; ob_encoder_get_split reports how the last call was laid out (streams
  * [0, n_warp) one warp per stream, the rest one lane per stream).  A stream keeps its mapping for the life of the encoder.  Both are the same
@@ -178,7 +178,7 @@ int32_t ob_encoder_set_bitrate(ObEncoder *enc, int32_t bitrate);
 #define OB_ENC_MAP_AUTO 0
 #define OB_ENC_MAP_WARP 1
 #define OB_ENC_MAP_THREAD 2
-#define OB_ENC_MAP_CROSSOVER 8192
+#define OB_ENC_MAP_CROSSOVER 12288
 int32_t ob_encoder_set_mapping(ObEncoder *enc, int32_t mapping);
 int32_t ob_encoder_get_mapping(ObEncoder *enc, int32_t *value);
 int32_t ob_encoder_get_split(ObEncoder *enc, int32_t *n_warp_streams);

@@ -62,35 +62,45 @@ OB_DEV float ob_tansig(float x)
     return ob_fmax(-1.f, ob_fmin(1.f, num));
 }
 OB_DEV float ob_sigmoid(float x) { return .5f + .5f * ob_tansig(.5f * x); }
-OB_DEV void ob_gemm_accum(float *out, const int8_t *w, int rows, int cols, int col_stride, const float *x)
+// The network of analysis.c (mlp.c: analysis_compute_dense / analysis_compute_gru).  Output neuron i is one lane's work: its sum runs over the
+// inputs in the reference's order, so the result does not depend on how many lanes share the layer.  Callers sync before (inputs complete).
+template <class G>
+OB_DEV void ob_gemm_accum(const G &g, float *out, const int8_t *w, int rows, int cols, int col_stride, const float *x)
 {
-    for (int i = 0; i < rows; i++) for (int j = 0; j < cols; j++) out[i] += w[j * col_stride + i] * x[j];
+    for (int i = g.lane; i < rows; i += g.n) {
+        float a = out[i];
+        for (int j = 0; j < cols; j++) a += w[j * col_stride + i] * x[j];
+        out[i] = a;
+    }
 }
-OB_DEV_NOINLINE void ob_dense(const int8_t *bias, const int8_t *w, int M, int N, int sigmoid, float *output, const float *input)
+template <class G>
+OB_DEV void ob_dense(const G &g, const int8_t *bias, const int8_t *w, int M, int N, int sigmoid, float *output, const float *input)
 {
-    for (int i = 0; i < N; i++) output[i] = bias[i];
-    ob_gemm_accum(output, w, N, M, N, input);
-    for (int i = 0; i < N; i++) output[i] *= (1.f / 128);
-    for (int i = 0; i < N; i++) output[i] = sigmoid ? ob_sigmoid(output[i]) : ob_tansig(output[i]);
+    for (int i = g.lane; i < N; i += g.n) output[i] = bias[i];
+    ob_gemm_accum(g, output, w, N, M, N, input);
+    for (int i = g.lane; i < N; i += g.n) { const float v = output[i] * (1.f / 128); output[i] = sigmoid ? ob_sigmoid(v) : ob_tansig(v); }
+    g.sync();
 }
-OB_DEV_NOINLINE void ob_gru(float *state, const float *input)               // layer1: 32 inputs, 24 neurons
+template <class G>
+OB_DEV void ob_gru(const G &g, float *state, const float *input, float *scr)               // layer1: 32 inputs, 24 neurons; scr: 4 * 32 floats
 {
     const int M = 32, N = 24, stride = 3 * N;
-    float tmp[32], z[32], r[32], h[32];
-    for (int i = 0; i < N; i++) z[i] = OB_AN_L1_B[i];
-    ob_gemm_accum(z, OB_AN_L1_W, N, M, stride, input);
-    ob_gemm_accum(z, OB_AN_L1_R, N, N, stride, state);
-    for (int i = 0; i < N; i++) z[i] = ob_sigmoid((1.f / 128) * z[i]);
-    for (int i = 0; i < N; i++) r[i] = OB_AN_L1_B[N + i];
-    ob_gemm_accum(r, OB_AN_L1_W + N, N, M, stride, input);
-    ob_gemm_accum(r, OB_AN_L1_R + N, N, N, stride, state);
-    for (int i = 0; i < N; i++) r[i] = ob_sigmoid((1.f / 128) * r[i]);
-    for (int i = 0; i < N; i++) h[i] = OB_AN_L1_B[2 * N + i];
-    for (int i = 0; i < N; i++) tmp[i] = state[i] * r[i];
-    ob_gemm_accum(h, OB_AN_L1_W + 2 * N, N, M, stride, input);
-    ob_gemm_accum(h, OB_AN_L1_R + 2 * N, N, N, stride, tmp);
-    for (int i = 0; i < N; i++) h[i] = z[i] * state[i] + (1 - z[i]) * ob_tansig((1.f / 128) * h[i]);
-    for (int i = 0; i < N; i++) state[i] = h[i];
+    float *tmp = scr, *z = scr + 32, *r = scr + 64, *h = scr + 96;
+    for (int i = g.lane; i < N; i += g.n) { z[i] = OB_AN_L1_B[i]; r[i] = OB_AN_L1_B[N + i]; h[i] = OB_AN_L1_B[2 * N + i]; }
+    ob_gemm_accum(g, z, OB_AN_L1_W, N, M, stride, input);
+    ob_gemm_accum(g, z, OB_AN_L1_R, N, N, stride, state);
+    ob_gemm_accum(g, r, OB_AN_L1_W + N, N, M, stride, input);
+    ob_gemm_accum(g, r, OB_AN_L1_R + N, N, N, stride, state);
+    for (int i = g.lane; i < N; i += g.n) {
+        z[i] = ob_sigmoid((1.f / 128) * z[i]);
+        r[i] = ob_sigmoid((1.f / 128) * r[i]);
+        tmp[i] = state[i] * r[i];
+    }
+    g.sync();                                                        // every tmp[j] is read by every neuron below
+    ob_gemm_accum(g, h, OB_AN_L1_W + 2 * N, N, M, stride, input);
+    ob_gemm_accum(g, h, OB_AN_L1_R + 2 * N, N, N, stride, tmp);
+    for (int i = g.lane; i < N; i += g.n) state[i] = z[i] * state[i] + (1 - z[i]) * ob_tansig((1.f / 128) * h[i]);       // nobody reads state[j != i] any more
+    g.sync();
 }
 
 // silk_resampler_down2_hp (analysis.c:115-161), float build; returns the high-pass energy.  The three all-pass memories are independent
@@ -216,7 +226,7 @@ OB_DEV_NOINLINE void ob_tonality_analysis(const G &g, ObTonalState &tonal, const
     const int N = 480, N2 = 240, NB = OB_AN_NB_TBANDS;
     float *A = tonal.angle, *dA = tonal.d_angle, *d2A = tonal.d2_angle;
     float *in = work, *out = fbuf, *dm = work + 960, *tonality = work + 1920, *noisiness = work + 2160, *tonality2 = work + 2400, *bsum = work + 2640;
-    float band_tonality[18], logE[18], BFCC[8], features[25], midE[8], band_log2[19], leakage_from[19], leakage_to[19], layer_out[32], frame_probs[2];
+    float band_tonality[18], logE[18], BFCC[8], features[25], midE[8], band_log2[19], leakage_from[19], leakage_to[19];
     int is_masked[19];
     const float pi4 = (float)(3.14159265358979323846 * 3.14159265358979323846 * 3.14159265358979323846 * 3.14159265358979323846);
     float slope = 0, frame_tonality, max_frame_tonality, frame_noisiness, frame_stationarity, relativeE, frame_loudness, bandwidth_mask, maxE, noise_floor;
@@ -467,17 +477,22 @@ OB_DEV_NOINLINE void ob_tonality_analysis(const G &g, ObTonalState &tonal, const
     features[22] = frame_stationarity - 0.743717f;
     features[23] = info->tonality_slope + 0.069216f;
     features[24] = tonal.lowECount - 0.067930f;
-    ob_dense(OB_AN_L0_B, OB_AN_L0_W, 25, 32, 0, layer_out, features);
-    ob_gru(tonal.rnn_state, layer_out);
-    ob_dense(OB_AN_L2_B, OB_AN_L2_W, 24, 2, 1, frame_probs, tonal.rnn_state);
-    info->activity_probability = frame_probs[1];
-    info->music_prob = frame_probs[0];
+    for (i = 0; i < 25; i++) out[i] = features[i];                   // the FFT output is spent: its buffer carries the network's vectors
     info->bandwidth = bandwidth;
     tonal.prev_bandwidth = bandwidth;
     info->noisiness = frame_noisiness;
     info->valid = 1;
     }                                                                // !bad
+    out[255] = bad ? 0.f : 1.f;
     }                                                                // lane 0
+    g.sync();
+    if (out[255] != 0.f) {                                           // the network, all lanes: one output neuron per lane (mlp.c)
+        float *layer_out = out + 32, *frame_probs = out + 64;
+        ob_dense(g, OB_AN_L0_B, OB_AN_L0_W, 25, 32, 0, layer_out, out);
+        ob_gru(g, tonal.rnn_state, layer_out, out + 96);
+        ob_dense(g, OB_AN_L2_B, OB_AN_L2_W, 24, 2, 1, frame_probs, tonal.rnn_state);
+        if (g.lane == 0) { info->activity_probability = frame_probs[1]; info->music_prob = frame_probs[0]; }
+    }
     g.sync();
 #undef RE
 #undef IM
