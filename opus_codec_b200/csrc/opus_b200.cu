@@ -43,10 +43,11 @@ __global__ void ob_k_frame(const uint8_t *__restrict__ packets, const int32_t *_
 #ifndef OB_SYM_THREADS
 #define OB_SYM_THREADS 128
 #endif
-#ifndef OB_SYM_BLOCKS
-#define OB_SYM_BLOCKS 7      // measured on 204 800 frames: 6 blocks / SM (80 registers) 5.19 ms, 7 (72) 5.06 ms, 8 (64) 5.30 ms; 32- / 64-thread blocks: no change
-#endif
-__global__ void __launch_bounds__(OB_SYM_THREADS, OB_SYM_BLOCKS)
+// Resident blocks per SM = the register budget of the symbol kernel.  Measured after the round-2 changes (ms per 819 200 mono frames / per 163 840 stereo
+// frames): 6 blocks (80 registers) 17.77 / 7.56, 7 (72) 17.06 / 8.07, 8 (64) 16.74 / 8.39 -- mono packets want the occupancy, stereo packets (more state
+// per thread, more divergence) the registers: one instantiation per decoder channel count.
+template <int BLOCKS>
+__global__ void __launch_bounds__(OB_SYM_THREADS, BLOCKS)
 ob_k_symbols(const uint8_t *__restrict__ packets, const ObSlot *__restrict__ slots, const int32_t *__restrict__ nslots,
              ObFrameIR *__restrict__ ir, int total, int dec_channels, int cap, int f0, int Fc, int phase_inv_disabled)
 {
@@ -319,8 +320,12 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
         d->launches += 1;
     }
     if (which & 1) {
-        ob_k_symbols<<<(total + OB_SYM_THREADS - 1) / OB_SYM_THREADS, OB_SYM_THREADS, 0, stream>>>(
-            d_packets, slots, nslots, ir, total, d->CC, cap, f0, Fc, d->phase_inv_disabled);
+        if (d->CC == 1)
+            ob_k_symbols<8><<<(total + OB_SYM_THREADS - 1) / OB_SYM_THREADS, OB_SYM_THREADS, 0, stream>>>(
+                d_packets, slots, nslots, ir, total, d->CC, cap, f0, Fc, d->phase_inv_disabled);
+        else
+            ob_k_symbols<6><<<(total + OB_SYM_THREADS - 1) / OB_SYM_THREADS, OB_SYM_THREADS, 0, stream>>>(
+                d_packets, slots, nslots, ir, total, d->CC, cap, f0, Fc, d->phase_inv_disabled);
         d->launches += 1;
     }
     if (timed) OB_CUDA(cudaEventRecord(d->ev[1], stream));
