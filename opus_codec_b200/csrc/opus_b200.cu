@@ -294,6 +294,11 @@ struct ObDecoder {
 
 #define OB_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "opus_b200: %s failed: %s\n", #x, cudaGetErrorString(e_)); return OB_INTERNAL_ERROR; } } while (0)
 
+// Debugging aid (OB_DEBUG_SYNC=1 in the environment): wait for every kernel right after its launch and name the one that faults.
+static const bool ob_debug_sync = getenv("OB_DEBUG_SYNC") != nullptr;
+#define OB_KCHECK(name) do { if (ob_debug_sync) { cudaError_t e_ = cudaStreamSynchronize(stream); if (e_ == cudaSuccess) e_ = cudaGetLastError(); \
+        if (e_ != cudaSuccess) { fprintf(stderr, "opus_b200: kernel %s failed: %s\n", name, cudaGetErrorString(e_)); return OB_INTERNAL_ERROR; } } } while (0)
+
 // Launches the three kernels for streams [s0, s0+Sc).  All per-stream arrays are indexed by stream, so a sub-range is
 // just a pointer offset; timed != 0 brackets the kernels with the handle's events.
 static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packets, const int32_t *d_offsets, const int32_t *d_lens,
@@ -318,6 +323,7 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
     if (which & 4) {
         ob_k_frame<<<(Sc + 127) / 128, 128, 0, stream>>>(d_packets, d_offsets + w0, d_lens + w0, slots, nslots, Sc, F, frame_size, cap, d->d_multi, d->ds, d->decode_fec);
         d->launches += 1;
+        OB_KCHECK("ob_k_frame");
     }
     if (which & 1) {
         if (d->CC == 1)
@@ -327,10 +333,12 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
             ob_k_symbols<6><<<(total + OB_SYM_THREADS - 1) / OB_SYM_THREADS, OB_SYM_THREADS, 0, stream>>>(
                 d_packets, slots, nslots, ir, total, d->CC, cap, f0, Fc, d->phase_inv_disabled);
         d->launches += 1;
+        OB_KCHECK("ob_k_symbols");
     }
     if (timed) OB_CUDA(cudaEventRecord(d->ev[1], stream));
     if (which & 2) {
         ob_k_plan<<<(Sc + 3) / 4, 128, 0, stream>>>(ir, st, nslots, Sc, cap, f0, Fc, d->CC);
+        OB_KCHECK("ob_k_plan");
         if (d->CC == 1) {
             // one counter per compute stream (launches on a stream are ordered), one list region per stream range
             int32_t *cnt = d->d_strag_count + (stream == d->aux_stream ? 1 : 0), *list = d->d_strag_list + c0;
@@ -342,6 +350,7 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
         } else      // stereo-sized: 2 / 3 / 4 / 6 warps per block measured alike (30.0 ms per 163 840 stereo frames)
             ob_k_bands<2><<<(total + OB_BANDS_WARPS - 1) / OB_BANDS_WARPS, OB_BANDS_WARPS * 32, OB_BANDS_WARPS * OB_BANDS_SMEM_PER_WARP, stream>>>(
                 ir, nslots, X, Sc, cap, f0, Fc, nullptr, nullptr);
+        OB_KCHECK("ob_k_bands");
         if (timed) OB_CUDA(cudaEventRecord(d->ev[2], stream));
         float *pcm_w = d_pcm + w0 * (size_t)frame_size * d->CC;
         int16_t *pcm16_w = d->cur_pcm16 ? d->cur_pcm16 + w0 * (size_t)frame_size * d->CC : nullptr;
@@ -357,6 +366,7 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
             ob_k_synth<2><<<Sc, OB_SYNTH_THREADS, 0, stream>>>(nullptr, ir, slots, nslots, X, st, hist, ring, pcm_w, pcm16_w, d_samples + w0, ranges_w, Sc, F, cap, d->CC,
                                                                 frame_size, f0, Fc, d->gain_linear, d->ds);
         d->launches += 3;
+        OB_KCHECK("ob_k_synth");
     }
     if (timed) OB_CUDA(cudaEventRecord(d->ev[3], stream));
     OB_CUDA(cudaGetLastError());
