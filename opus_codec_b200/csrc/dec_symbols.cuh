@@ -211,7 +211,10 @@ OB_DEV uint32_t ob_isqrt32(uint32_t v)
 // ------------------------------------------------------------------------------------------------
 // PVQ: U(N,K) table, V(N,K), index -> pulse vector (opus/celt/cwrs.c:430-541)
 // ------------------------------------------------------------------------------------------------
-OB_DEV uint32_t ob_pvq_u(int n, int k) { int a = ob_imin(n, k), b = ob_imax(n, k); return OB_PVQ_U_DATA[OB_PVQ_U_ROW[a] + b]; }
+// U(n,k) = U(k,n): the reference keeps rows a = min <= 14 of the triangle behind row pointers (two dependent loads); OB_PVQ_U_RECT holds the same
+// numbers at [a * 177 + b] (oracle/gen_tables.c), one load -- the symbol kernel is bound by exactly these dependent table loads.
+OB_DEV uint32_t ob_pvq_u(int n, int k) { const int a = ob_imin(n, k), b = ob_imax(n, k); return OB_PVQ_U_RECT[a * 177 + b]; }
+OB_DEV uint32_t ob_pvq_u_tri(int n, int k) { const int a = ob_imin(n, k), b = ob_imax(n, k); return OB_PVQ_U_DATA[OB_PVQ_U_ROW[a] + b]; }      // the reference's layout (tests)
 OB_DEV uint32_t ob_pvq_v(int n, int k) { return ob_pvq_u(n, k) + ob_pvq_u(n, k + 1); }
 
 // Writes n pulse counts to y (int16) and returns the collapse mask of extract_collapse_mask (vq.c:143-163)

@@ -15,6 +15,16 @@ int emul_frame_packets(const uint8_t *pkts, const int *offs, const int *lens, in
     delete[] sl;
     return n;
 }
+// mismatches between the rectangular PVQ table and the reference's triangular one over every pair the reference's table holds
+int emul_pvq_table_check()
+{
+    int bad = 0, seen = 0;
+    for (int a = 0; a < 15; a++) {
+        const int end = a < 14 ? OB_PVQ_U_ROW[a + 1] + a + 1 : 1272;
+        for (int b = a; b < 177 && OB_PVQ_U_ROW[a] + b < end; b++) { seen++; bad += ob_pvq_u(a, b) != ob_pvq_u_tri(a, b) || ob_pvq_u(b, a) != ob_pvq_u_tri(a, b); }
+    }
+    return seen == 1272 ? bad : -1;
+}
 int emul_ir_size() { return (int)sizeof(ObFrameIR); }
 int emul_hdr_size() { return (int)sizeof(ObFrameHdr); }
 void emul_decode_symbols(const uint8_t *pkt, int len, int dec_channels, int max_frame, ObFrameIR *ir)

@@ -411,3 +411,10 @@ def test_symbol_pass_integer_ir_matches_oracle_taps(emul, name):
             iy = np.frombuffer(buf.raw, np.int16, 1920, iy_off)
             want = np.frombuffer(bytes(t.iy), np.int16); mask = np.frombuffer(bytes(t.iy_set), np.uint8) != 0
             assert np.array_equal(iy[mask], want[mask]), (name, s, f)
+
+
+def test_rectangular_pvq_table_equals_the_reference_triangle():
+    """OB_PVQ_U_RECT (one load per U(n,k)) holds exactly the 1272 numbers of CELT_PVQ_U_DATA behind CELT_PVQ_U_ROW (opus/celt/cwrs.c:213-428)."""
+    from conftest import emul_lib
+    assert emul_lib().emul_pvq_table_check() == 0
+
