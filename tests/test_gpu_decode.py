@@ -608,6 +608,33 @@ def test_single_frame_call_split_over_two_compute_streams_with_stereo_frames():
     assert np.array_equal(p, out[sub]) and (r == rngs[sub]).all()
 
 
+@pytest.mark.parametrize("channels,F", [(2, 8), (1, 2)])
+def test_chunking_of_a_host_call_never_changes_its_output(channels, F):
+    """How ob_decode_float_multi cuts a call into chunks (frame windows with 2-D copies, stream ranges with contiguous copies, up to 16 stream
+    ranges for live calls; opus_b200.cu ob_decode_submit) is a pipelining decision: PCM, sample counts and final ranges of a large batch must
+    equal, bit for bit, what the same streams give in a small batch that is not chunked at all -- over two consecutive calls (carried state)."""
+    from opus_codec_b200.batch import BatchDecoder
+    g = load_golden("cfg3_stereo_20ms_96k_cbr" if channels == 2 else "cfg2_mono_20ms_64k_cbr")
+    S = 17000 if channels == 2 else 70000           # 136 000 stereo frames per call: stream-range chunks (rows of a frame window would be 15 KB); 140 000 mono frames at F = 2: 16 stream ranges
+    P, stride, N = g["packets"].shape[0], g["packets"].shape[2], g["frame_size"]
+    idx = (np.arange(S) * 5) % P
+    calls = [(np.ascontiguousarray(g["packets"][idx, c * F:(c + 1) * F]), np.ascontiguousarray(g["lens"][idx, c * F:(c + 1) * F]).astype(np.int32)) for c in range(2)]
+    sub = np.r_[0:24, S // 2 - 12:S // 2 + 12, S - 24:S]
+    big, small = [], []
+    with BatchDecoder(S, 48000, channels, device=0, max_frames=F) as dec:
+        for pk, ln in calls:
+            p, smp, r = dec.decode_float_multi(pk.reshape(-1), _offsets(S, F, stride), ln, N)
+            assert (smp == N).all()
+            big.append((p[sub].copy(), r[sub].copy()))
+    with BatchDecoder(len(sub), 48000, channels, device=0, max_frames=F) as dec:
+        for pk, ln in calls:
+            p, smp, r = dec.decode_float_multi(np.ascontiguousarray(pk[sub]).reshape(-1), _offsets(len(sub), F, stride), ln[sub], N)
+            small.append((p, r))
+    for (pb, rb), (ps, rs) in zip(big, small):
+        assert (rb == rs).all() and np.array_equal(pb, ps)
+    assert (small[1][1] == g["dec_rng"][idx[sub], F:2 * F]).all()              # and the reference's final ranges
+
+
 class _IrHdr(__import__("ctypes").Structure):
     import ctypes as _C
     _fields_ = [("status", _C.c_int32), ("final_range", _C.c_uint32), ("n_leaves", _C.c_uint16), ("pf_pitch", _C.c_uint16),
