@@ -323,6 +323,21 @@ OB_DEV_NOINLINE void ob_tonality_analysis(const G &g, ObTonalState &tonal, const
         }
     }
     g.sync();
+    // per-band transcendental work of the statistics below, one band per lane (each value exactly what the one-lane loop computed: the double-precision
+    // log / sqrt of the band energy, and the eight-frame sums L1 / L2 in the reference's order), into the spent FFT buffer
+    float *pre = out + 320;                                          // [b] log, [32 + b] sqrt, [64 + b] L1, [96 + b] L2
+    {
+        const int Ec = tonal.E_count;
+        for (b = g.lane; b < NB; b += g.n) {
+            const float E = bsum[b];
+            float L1 = 0, L2 = 0;
+            pre[b] = (float)log((double)(E + 1e-10f));
+            pre[32 + b] = (float)sqrt((double)(E + 1e-10f));
+            for (i = 0; i < OB_AN_NB_FRAMES; i++) { const float Ei = i == Ec ? E : tonal.E[i][b]; L1 += (float)sqrt((double)Ei); L2 += Ei; }
+            pre[64 + b] = L1; pre[96 + b] = L2;
+        }
+    }
+    g.sync();
     if (g.lane == 0) {                                               // ---- from here on: scalar statistics, one lane ----
     int E_count = tonal.E_count;
     frame_tonality = 0; max_frame_tonality = 0; info->activity = 0; frame_noisiness = 0; frame_stationarity = 0;
@@ -340,9 +355,9 @@ OB_DEV_NOINLINE void ob_tonality_analysis(const G &g, ObTonalState &tonal, const
         if (!(E < 1e9f) || E != E) { info->valid = 0; bad = 1; break; }
         tonal.E[E_count][b] = E;
         frame_noisiness += nE / (1e-15f + E);
-        frame_loudness += (float)sqrt((double)(E + 1e-10f));
-        logE[b] = (float)log((double)(E + 1e-10f));
-        band_log2[b + 1] = .5f * 1.442695f * (float)log((double)(E + 1e-10f));
+        frame_loudness += pre[32 + b];
+        logE[b] = pre[b];
+        band_log2[b + 1] = .5f * 1.442695f * pre[b];
         tonal.logE[E_count][b] = logE[b];
         if (count == 0) tonal.highE[b] = tonal.lowE[b] = logE[b];
         if ((double)tonal.highE[b] > (double)tonal.lowE[b] + 7.5) {
@@ -357,8 +372,7 @@ OB_DEV_NOINLINE void ob_tonality_analysis(const G &g, ObTonalState &tonal, const
             tonal.highE[b] = ob_fmin(tonal.lowE[b] + 15, tonal.highE[b]);
         }
         relativeE += (logE[b] - tonal.lowE[b]) / (1e-5f + (tonal.highE[b] - tonal.lowE[b]));
-        L1 = L2 = 0;
-        for (i = 0; i < OB_AN_NB_FRAMES; i++) { L1 += (float)sqrt((double)tonal.E[i][b]); L2 += tonal.E[i][b]; }
+        L1 = pre[64 + b]; L2 = pre[96 + b];
         stationarity = ob_fmin(0.99f, L1 / (float)sqrt(1e-15 + (double)(OB_AN_NB_FRAMES * L2)));
         stationarity *= stationarity;
         stationarity *= stationarity;
@@ -388,16 +402,7 @@ OB_DEV_NOINLINE void ob_tonality_analysis(const G &g, ObTonalState &tonal, const
         info->leak_boost[b] = (uint8_t)ob_imin(255, (int)floor(.5 + (double)(64.f * boost)));
     }
     for (; b < OB_AN_LEAK_BANDS; b++) info->leak_boost[b] = 0;
-    for (i = 0; i < OB_AN_NB_FRAMES; i++) {
-        float mindist = 1e15f;
-        for (int j = 0; j < OB_AN_NB_FRAMES; j++) {
-            float dist = 0;
-            for (int k = 0; k < NB; k++) { const float tmp = tonal.logE[i][k] - tonal.logE[j][k]; dist += tmp * tmp; }
-            if (j != i) mindist = ob_fmin(mindist, dist);
-        }
-        spec_variability += mindist;
-    }
-    spec_variability = (float)sqrt((double)(spec_variability / OB_AN_NB_FRAMES / NB));
+    // spec_variability (analysis.c:803-820) only feeds the network: it is computed by all lanes after this block
     bandwidth_mask = 0; bandwidth = 0; maxE = 0;
     noise_floor = 5.7e-4f / (1 << ob_imax(0, lsb_depth - 8));
     noise_floor *= noise_floor;
@@ -487,6 +492,26 @@ OB_DEV_NOINLINE void ob_tonality_analysis(const G &g, ObTonalState &tonal, const
     }                                                                // lane 0
     g.sync();
     if (out[255] != 0.f) {                                           // the network, all lanes: one output neuron per lane (mlp.c)
+        {   // spec_variability: the 64 frame-pair distances one per lane (18 terms each, in the reference's order), then min / sum as the reference does
+            float *dm = out + 448;
+            for (int p = g.lane; p < OB_AN_NB_FRAMES * OB_AN_NB_FRAMES; p += g.n) {
+                const int fi = p / OB_AN_NB_FRAMES, fj = p % OB_AN_NB_FRAMES;
+                float dist = 0;
+                for (int k = 0; k < NB; k++) { const float tmp = tonal.logE[fi][k] - tonal.logE[fj][k]; dist += tmp * tmp; }
+                dm[p] = dist;
+            }
+            g.sync();
+            if (g.lane == 0) {
+                float sv = 0;
+                for (i = 0; i < OB_AN_NB_FRAMES; i++) {
+                    float mindist = 1e15f;
+                    for (int j = 0; j < OB_AN_NB_FRAMES; j++) if (j != i) mindist = ob_fmin(mindist, dm[i * OB_AN_NB_FRAMES + j]);
+                    sv += mindist;
+                }
+                out[18] = (float)sqrt((double)(sv / OB_AN_NB_FRAMES / NB)) - 0.78f;
+            }
+            g.sync();
+        }
         float *layer_out = out + 32, *frame_probs = out + 64;
         ob_dense(g, OB_AN_L0_B, OB_AN_L0_W, 25, 32, 0, layer_out, out);
         ob_gru(g, tonal.rnn_state, layer_out, out + 96);
