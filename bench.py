@@ -221,7 +221,7 @@ def run_encode_leg(args, L, local, world, rank, dev, barrier):
         if not args.kernels_only:
             cores = os.cpu_count() or 1
             try:
-                v, sample = cpu_reference_encode(cores, cores * 16, 400)      # >= 16 streams per core x 8 s of audio: >= 1 s of wall time on any host
+                v, sample = cpu_reference_encode(cores, cores * 16, 600)      # >= 16 streams per core x 12 s of audio: >= 1 s of wall time (0.86 s with 8 s of audio on a 16-core box)
                 res["cpu_baseline"] = {"value": v, "unit": "audio-s/s", "cores": cores, "kind": "reference", "sample": sample}
             except Exception as ex:
                 res["cpu_baseline"] = {"value": None, "sample": "unavailable: %r" % (ex,)}
