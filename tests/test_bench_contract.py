@@ -64,3 +64,13 @@ def test_algorithmic_bytes_follow_survey_8d():
     assert bench.algorithmic_bytes_per_frame(50) == pytest.approx(160 + 3840 + 10368 / 50)
     assert bench.algorithmic_bytes_per_frame(1) == pytest.approx(14368)
     assert bench.enc_algorithmic_bytes_per_frame(10) == pytest.approx(7680 + 240 + 19392 / 10)
+
+
+def test_traffic_file_is_what_the_committed_ncu_summaries_say():
+    """profiles/r02_dram_traffic.json (bench.py's roofline.traffic) is generated, not typed: tools/make_dram_traffic.py over the committed ncu summaries
+    must reproduce it."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_dram_traffic.py"), "profiles/r02z_ncu_decoder_kernels.txt",
+                          "profiles/r02z_ncu_encoder_thread_kernel.txt", "profiles/r02z_ncu_encoder_warp_kernel.txt"], cwd=ROOT, capture_output=True, text=True, check=True).stdout
+    assert json.loads(out) == json.load(open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")))
