@@ -5,6 +5,9 @@
 //   prefilter_and_fold (:515-550) and the post-loss energy safety of the next good frame (:1171-1198).
 // Included by dec_synth.cuh after ObSynthShared is defined.
 #pragma once
+// In-place FIR passes of the concealment compute every output of a lane's contiguous chunk into registers before any is written back: 1024 samples over
+// the synthesis block's lanes, so a chunk is <= 16 samples for blocks of >= 64 lanes (dec_synth.cuh ObSynthSharedT::synth_threads).
+#define OB_PLC_PER 16
 
 // Products that feed a decision (pitch lag, LPC) are kept un-fused so that they round like the reference's C code.
 #ifdef __CUDA_ARCH__
@@ -197,7 +200,7 @@ OB_DEV int ob_plc_pitch_search(const G &g, SH &sh, int CC, float *work, float *x
     }
     g.sync();
     {                                                             // celt_fir5 (pitch.c:105-137): FIR on the ORIGINAL samples, so every output is independent
-        const int per = (n + g.n - 1) / g.n;                      // <= 8 with 128 lanes; the host lane does it in order instead
+        const int per = (n + g.n - 1) / g.n;                      // <= OB_PLC_PER (blocks of >= 64 lanes); the host lane does it in order instead
         if constexpr (ObIsSolo<G>::value) {
             float m0 = 0, m1 = 0, m2 = 0, m3 = 0, m4 = 0;
             for (int i = 0; i < n; i++) {
@@ -207,8 +210,8 @@ OB_DEV int ob_plc_pitch_search(const G &g, SH &sh, int CC, float *work, float *x
                 lp[i] = sum;
             }
         } else {
-            float out[8];
-            for (int k = 0; k < per && k < 8; k++) {
+            float out[OB_PLC_PER];
+            for (int k = 0; k < per && k < OB_PLC_PER; k++) {
                 const int i = g.lane * per + k;
                 if (i < n) {
                     float sum = lp[i];
@@ -217,7 +220,7 @@ OB_DEV int ob_plc_pitch_search(const G &g, SH &sh, int CC, float *work, float *x
                 }
             }
             g.sync();
-            for (int k = 0; k < per && k < 8; k++) { const int i = g.lane * per + k; if (i < n) lp[i] = out[k]; }
+            for (int k = 0; k < per && k < OB_PLC_PER; k++) { const int i = g.lane * per + k; if (i < n) lp[i] = out[k]; }
         }
     }
     g.sync();
@@ -363,8 +366,8 @@ OB_DEV void ob_plc_pitch(const G &g, SH &sh, int N, int loss_duration, int CC)
                 }
                 for (int i = 0; i < exc_length; i++) x[i] = loc[i];
             } else {
-                float out[8];
-                for (int k = 0; k < per && k < 8; k++) {
+                float out[OB_PLC_PER];
+                for (int k = 0; k < per && k < OB_PLC_PER; k++) {
                     const int i = g.lane * per + k;
                     if (i < exc_length) {
                         float sum = x[i];
@@ -373,7 +376,7 @@ OB_DEV void ob_plc_pitch(const G &g, SH &sh, int N, int loss_duration, int CC)
                     }
                 }
                 g.sync();
-                for (int k = 0; k < per && k < 8; k++) { const int i = g.lane * per + k; if (i < exc_length) x[i] = out[k]; }
+                for (int k = 0; k < per && k < OB_PLC_PER; k++) { const int i = g.lane * per + k; if (i < exc_length) x[i] = out[k]; }
             }
         }
         g.sync();

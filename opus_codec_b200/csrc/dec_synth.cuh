@@ -221,6 +221,10 @@ OB_DEV void ob_comb_filter(const G &g, float *x, int T0, int T1, int N, float g0
 // Shared-memory working set of one stream.  CH = 1: a mono decoder that meets mono frames only (20 KB instead of 29 KB: 8 blocks per SM).
 template <int CH>
 struct ObSynthSharedT {
+    // Threads of the synthesis block and resident blocks per SM (opus_b200.cu ob_k_synth).  Measured, ms per 819 200 mono frames / per 163 840 stereo
+    // frames: 128 threads x 8 / 7 blocks 18.34 / 7.05, 96 x 10 / 9: 16.76 / 7.08, 96 x 9 / 7: 16.91 / 6.72, 96 x 8 / 6: 17.17 / 6.86, 64 x 10 / 7: 16.53 / 6.96,
+    // 160 x 6: 18.79, 192 x 5: 20.47 -- a frame is 960 samples and 120-240 butterflies per FFT stage: small blocks waste fewer lanes per barrier.
+    static constexpr int synth_threads = CH == 1 ? 64 : 96, synth_blocks = CH == 1 ? 10 : 7;
     float buf[CH][OB_BUF_LEN];       // [history | current frame | overlap tail] per channel (the tail of decode_mem)
     float freq[2][OB_MAX_N];         // X tile -> MDCT coefficients -> PCM staging; both halves are the pitch concealment's work area, mono or not
     float oldBandE[2 * OB_NB], oldLogE[2 * OB_NB], oldLogE2[2 * OB_NB], backgroundLogE[2 * OB_NB];
@@ -523,7 +527,7 @@ OB_DEV int ob_synth_frame(const G &g, SH &sh, const ObFrameIR *ir, const float *
     // which does not depend on them (the synthesis kernel's largest single stall was the wait for this tile, profiles/r02_hot_lines_synth.txt) ----
     const int bound = OB_EBANDS[end] << LM;                          // bands >= end were not written by the bands stage
 #ifdef __CUDA_ARCH__
-    constexpr int XR = (int)(sizeof(sh.buf) / sizeof(sh.buf[0])) * OB_MAX_N / 128 + 1;     // tile elements per thread of a 128-thread block
+    constexpr int XR = ((int)(sizeof(sh.buf) / sizeof(sh.buf[0])) * OB_MAX_N + SH::synth_threads - 1) / SH::synth_threads;     // tile elements per thread of the synthesis block
     float xr[XR];
     const bool x_early = g.n * XR >= C * N;
     if (x_early) {

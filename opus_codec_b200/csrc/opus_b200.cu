@@ -142,12 +142,11 @@ ob_k_bands_stragglers(const ObFrameIR *__restrict__ ir, float *__restrict__ Xg, 
     }
 }
 
-#define OB_SYNTH_THREADS 128
-// CH = 2: any decoder.  CH = 1: mono decoders while every frame of the launch is mono (mono-sized shared memory, 64 registers: 8 blocks
-// per SM instead of 7).  `stereo_frames` is the straggler counter the mono band kernel has just filled: the <1> instantiation runs when
+// CH = 2: any decoder.  CH = 1: mono decoders while every frame of the launch is mono (mono-sized shared memory: 10 blocks of 64 threads per SM
+// instead of 7 of 96; block shapes measured in dec_synth.cuh ObSynthSharedT).  `stereo_frames` is the straggler counter the mono band kernel has just filled: the <1> instantiation runs when
 // it is zero, the <2> instantiation launched behind it when it is not -- the choice needs no host round trip.
 template <int CH>
-__global__ void __launch_bounds__(OB_SYNTH_THREADS, CH == 1 ? 8 : 7)
+__global__ void __launch_bounds__(ObSynthSharedT<CH>::synth_threads, ObSynthSharedT<CH>::synth_blocks)
 ob_k_synth(const int32_t *__restrict__ stereo_frames, const ObFrameIR *__restrict__ ir, const ObSlot *__restrict__ slots, const int32_t *__restrict__ nslots, const float *__restrict__ Xg,
            ObDecState *__restrict__ st, float *__restrict__ hist, float *__restrict__ ring,
            float *__restrict__ pcm, int16_t *__restrict__ pcm16, int32_t *__restrict__ samples, uint32_t *__restrict__ ranges, int S, int F, int cap,
@@ -357,13 +356,13 @@ static int ob_launch(ObDecoder *d, int s0, int Sc, int F, const uint8_t *d_packe
         uint32_t *ranges_w = d_ranges ? d_ranges + w0 : nullptr;
         if (d->CC == 1) {
             const int32_t *cnt = d->d_strag_count + (stream == d->aux_stream ? 1 : 0);
-            ob_k_synth<1><<<Sc, OB_SYNTH_THREADS, 0, stream>>>(cnt, ir, slots, nslots, X, st, hist, ring, pcm_w, pcm16_w, d_samples + w0, ranges_w, Sc, F, cap, d->CC,
+            ob_k_synth<1><<<Sc, ObSynthSharedT<1>::synth_threads, 0, stream>>>(cnt, ir, slots, nslots, X, st, hist, ring, pcm_w, pcm16_w, d_samples + w0, ranges_w, Sc, F, cap, d->CC,
                                                                 frame_size, f0, Fc, d->gain_linear, d->ds);
-            ob_k_synth<2><<<Sc, OB_SYNTH_THREADS, 0, stream>>>(cnt, ir, slots, nslots, X, st, hist, ring, pcm_w, pcm16_w, d_samples + w0, ranges_w, Sc, F, cap, d->CC,
+            ob_k_synth<2><<<Sc, ObSynthSharedT<2>::synth_threads, 0, stream>>>(cnt, ir, slots, nslots, X, st, hist, ring, pcm_w, pcm16_w, d_samples + w0, ranges_w, Sc, F, cap, d->CC,
                                                                 frame_size, f0, Fc, d->gain_linear, d->ds);
             d->launches += 1;
         } else
-            ob_k_synth<2><<<Sc, OB_SYNTH_THREADS, 0, stream>>>(nullptr, ir, slots, nslots, X, st, hist, ring, pcm_w, pcm16_w, d_samples + w0, ranges_w, Sc, F, cap, d->CC,
+            ob_k_synth<2><<<Sc, ObSynthSharedT<2>::synth_threads, 0, stream>>>(nullptr, ir, slots, nslots, X, st, hist, ring, pcm_w, pcm16_w, d_samples + w0, ranges_w, Sc, F, cap, d->CC,
                                                                 frame_size, f0, Fc, d->gain_linear, d->ds);
         d->launches += 3;
         OB_KCHECK("ob_k_synth");
