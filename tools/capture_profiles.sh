@@ -13,6 +13,7 @@ python tools/prof_decode.py 4096 200 1 > $O/${TAG}_plain_dec.log 2>&1 &&
 python tools/ncu_summary.py $T/dec.ncu-rep > $O/${TAG}_ncu_decoder_kernels.txt 2>&1
 python tools/ncu_hot_lines.py $T/dec.ncu-rep ob_k_symbolsILi8 $SO 60 'ob_k_symbols$' > $O/${TAG}_hot_lines_symbols.txt 2>&1
 python tools/ncu_hot_lines.py $T/dec.ncu-rep ob_k_bandsILi1 $SO 60 'ob_k_bands$' > $O/${TAG}_hot_lines_bands.txt 2>&1
+python tools/ncu_hot_lines.py $T/dec.ncu-rep ob_k_synthILi1 $SO 60 'ob_k_synth$' > $O/${TAG}_hot_lines_synth.txt 2>&1
 # decoder, stereo (16 384 streams x 10 frames)
 python tools/prof_decode_stereo.py 16384 10 1 2 > $O/${TAG}_plain_dec_stereo.log 2>&1 &&
   $NCU -k 'regex:ob_k_(symbols|bands|synth)' -s 6 -c 3 -o $T/dec_stereo python tools/prof_decode_stereo.py 16384 10 1 2 > $O/${TAG}_ncu_dec_stereo.log 2>&1
