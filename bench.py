@@ -328,7 +328,7 @@ def run_transcode_leg(args, L, local, world, rank, dev, barrier):
         submit(n)
         assert L.ob_decoder_wait(dec.handle, 0) == 0
     barrier()
-    esteps = 6
+    esteps = dsteps                                       # as many as the device-timed leg: the pipeline's fill / drain is one step's worth
     t0 = time.perf_counter()
     for n in range(esteps):
         submit(n)

@@ -71,6 +71,6 @@ def test_traffic_file_is_what_the_committed_ncu_summaries_say():
     must reproduce it."""
     import subprocess
     import sys
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_dram_traffic.py"), "profiles/r02z_ncu_decoder_kernels.txt",
-                          "profiles/r02z_ncu_encoder_thread_kernel.txt", "profiles/r02z_ncu_encoder_warp_kernel.txt"], cwd=ROOT, capture_output=True, text=True, check=True).stdout
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_dram_traffic.py"), "profiles/r02fin_ncu_decoder_kernels.txt",
+                          "profiles/r02fin_ncu_encoder_thread_kernel.txt", "profiles/r02fin_ncu_encoder_warp_kernel.txt"], cwd=ROOT, capture_output=True, text=True, check=True).stdout
     assert json.loads(out) == json.load(open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")))
