@@ -74,3 +74,15 @@ def test_traffic_file_is_what_the_committed_ncu_summaries_say():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "make_dram_traffic.py"), "profiles/r02fin_ncu_decoder_kernels.txt",
                           "profiles/r02fin_ncu_encoder_thread_kernel.txt", "profiles/r02fin_ncu_encoder_warp_kernel.txt"], cwd=ROOT, capture_output=True, text=True, check=True).stdout
     assert json.loads(out) == json.load(open(os.path.join(ROOT, "profiles", "r02_dram_traffic.json")))
+
+
+def test_both_arms_print_the_same_config_object():
+    """The driver compares the `config` of `--impl ours` with that of `--impl reference`: they come from one function, and the committed lines of the two
+    arms (same box, same tree) carry equal objects."""
+    import bench
+    c = bench.workload_config(200)
+    assert c["workload"] == bench.WORKLOAD and c["streams_per_gpu"] == bench.STREAMS_PER_GPU and c["frames_per_stream_per_step"] == 200
+    assert "L2" in c["l2"] and "collective" in c["sharding"]
+    ref = json.loads(open(os.path.join(ROOT, "profiles", "r02final_bench_reference.json")).read().strip().splitlines()[-1])
+    assert ref["impl"] == "reference" and ref["config"] == _line()["config"]
+    assert ref["e2e"]["value"] == ref["value"] and ref["cpu_baseline"]["kind"] == "reference" and ref["gpu_launches"] == 0
